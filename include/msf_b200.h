@@ -1,0 +1,217 @@
+/* msf_b200.h — C ABI of the B200-native HybridFusion hot path.
+ *
+ * The reference (Rutgers-ECE-MML4SS/multimodal-sensor-fusion-with-attention-RajeevAtla)
+ * is pure Python/PyTorch and has no FFI of its own; this header is the boundary
+ * a maintainer binds (ctypes stub in INTEGRATION.md) to move the arithmetic of
+ *
+ *   src/fusion.py:331-479     HybridFusion.forward / compute_adaptive_weights
+ *   src/attention.py:68-146   CrossModalAttention.forward (q_len = k_len = 1 inside HybridFusion)
+ *   src/train.py:185-186,310  CrossEntropyLoss(label_smoothing)
+ *   src/train.py:378-382,416-430  AdamW step + global-norm clip
+ *   src/eval.py:89-90         softmax -> max -> (confidence, prediction)
+ *   src/uncertainty.py:84-171,218-241  ECE / MCE / reliability-diagram binning
+ *
+ * onto sm_100a kernels.  Conventions:
+ *   - plain C, POD structs, raw DEVICE pointers, sizes, a cudaStream_t passed as void*;
+ *   - every entry point returns 0 on success or a negative MSF_E_* code and never
+ *     throws; msf_last_error() returns a thread-local message for the last failure;
+ *   - the library BORROWS all buffers for the duration of the call (PyTorch owns
+ *     them); it allocates nothing persistent except small per-device caches
+ *     (TMA descriptors) that it owns;
+ *   - all work is enqueued on the given stream; no entry point synchronises.
+ *
+ * Parameter ("master") arena layout, fp32, in the reference's registration
+ * order (src/fusion.py:291-328) so that it equals
+ * torch.nn.utils.parameters_to_vector(model.parameters()):
+ *
+ *   for m in modalities:            projections.m.0.weight (H x D_m), .bias (H)
+ *   for q in modalities, k != q:    attention_modules.q_to_k.{query,key,value,out}_proj
+ *                                   .weight (H x H), .bias (H)        [4 x (H*H + H)]
+ *   for m in modalities:            gating_layers.m.weight (1 x H), .bias (1)
+ *   classifier.0.weight (H x H), .bias (H); classifier.3.weight (C x H), .bias (C)
+ *
+ * A pair module deleted from the ModuleDict (src/fusion.py:388-389) keeps its
+ * slot; clear its bit in msf_fusion_shape.pair_present.
+ */
+#ifndef MSF_B200_H_
+#define MSF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSF_ABI_VERSION 1
+#define MSF_MAX_MODALITIES 8
+
+enum {
+  MSF_OK = 0,
+  MSF_E_INVALID = -1,      /* bad argument / unsupported shape */
+  MSF_E_CUDA = -2,         /* a CUDA runtime/driver call failed */
+  MSF_E_WORKSPACE = -3,    /* workspace too small */
+  MSF_E_UNSUPPORTED = -4   /* shape not eligible for the requested precision */
+};
+
+/* Arithmetic the path computes in. */
+enum {
+  MSF_PREC_F32 = 0,   /* fp32 FFMA kernels: parity mode, max-abs <= 1e-5 vs the fp32 oracle */
+  MSF_PREC_BF16 = 1   /* bf16 operands, fp32 accumulate on tcgen05/TMEM: <= 1e-2 */
+};
+
+typedef struct msf_fusion_shape {
+  int32_t num_modalities;               /* M, 1..MSF_MAX_MODALITIES            */
+  int32_t hidden;                       /* H  (fusion.py hidden_dim)           */
+  int32_t num_heads;                    /* heads; H % heads == 0               */
+  int32_t num_classes;                  /* C                                   */
+  int32_t in_dims[MSF_MAX_MODALITIES];  /* D_m                                 */
+  uint64_t pair_present;                /* bit (q*M + k): attention_modules[q_to_k] exists */
+} msf_fusion_shape;
+
+/* One forward or backward invocation over a batch of windows. */
+typedef struct msf_fusion_call {
+  int32_t batch;        /* B windows                                          */
+  int32_t precision;    /* MSF_PREC_*                                         */
+  int32_t training;     /* nonzero: dropout active with probability dropout_p */
+  float dropout_p;
+  uint64_t seed;        /* Philox4x32-10 key; identical (seed, offset) in     */
+  uint64_t offset;      /* forward and backward regenerate identical masks    */
+  const uint64_t* rng_state;    /* optional DEVICE {seed, offset[, step]}: overrides seed/offset so a
+                                   captured CUDA graph draws fresh masks on every replay */
+  const float* params;          /* master arena, fp32                          */
+  const void* params_bf16;      /* compute arena made by msf_fusion_pack_bf16 (BF16 precision) */
+  const float* x[MSF_MAX_MODALITIES];  /* (B, D_m) row-major fp32 encoder outputs */
+  const float* mask;            /* (B, M) fp32 availability, or NULL = all ones */
+  void* workspace;              /* msf_fusion_workspace_bytes(); forward fills it, backward reads it */
+  size_t workspace_bytes;
+  /* forward outputs */
+  float* logits;                /* (B, C)                                      */
+  float* fusion_weights;        /* (B, M) or NULL                              */
+  float* attn_gates;            /* (M*(M-1), B, heads): attention_maps values, q-major pair order, or NULL */
+  /* backward inputs / outputs */
+  const float* grad_logits;     /* (B, C)                                      */
+  float* grad_params;           /* master layout, fully overwritten (dead q/k slots = 0) */
+  float* grad_x[MSF_MAX_MODALITIES];   /* (B, D_m) or NULL                     */
+} msf_fusion_call;
+
+/* ---- library ------------------------------------------------------------ */
+int msf_abi_version(void);
+/* sizeof(msf_fusion_shape), sizeof(msf_fusion_call) as compiled, for binding self-checks */
+int msf_struct_sizes(int32_t* shape_bytes, int32_t* call_bytes);
+const char* msf_last_error(void);
+/* kernels launched by this library so far in this process (host-side counter) */
+uint64_t msf_launch_count(void);
+/* sm count / compute capability of the current device; fails unless cc >= 10.0 */
+int msf_device_check(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+/* ---- HybridFusion (src/fusion.py:248-479) -------------------------------- */
+int msf_fusion_param_count(const msf_fusion_shape* shape, int64_t* count);
+/* element offset of a tensor in the master arena.
+ * kind: 0 proj.weight 1 proj.bias (idx = m); 2..9 pair {q,k,v,o}x{weight,bias}
+ * (idx = q*M + k); 10 gate.weight 11 gate.bias (idx = m); 12..15 classifier
+ * {0.weight, 0.bias, 3.weight, 3.bias}. */
+int msf_fusion_param_offset(const msf_fusion_shape* shape, int32_t kind, int32_t idx, int64_t* offset);
+int msf_fusion_workspace_bytes(const msf_fusion_shape* shape, int32_t batch, int32_t precision,
+                               size_t* bytes);
+/* bytes of the bf16 compute arena and the conversion master -> compute layout */
+int msf_fusion_bf16_arena_bytes(const msf_fusion_shape* shape, size_t* bytes);
+int msf_fusion_pack_bf16(const msf_fusion_shape* shape, const float* params, void* params_bf16,
+                         void* stream);
+int msf_fusion_forward(const msf_fusion_shape* shape, const msf_fusion_call* call, void* stream);
+int msf_fusion_backward(const msf_fusion_shape* shape, const msf_fusion_call* call, void* stream);
+/* HybridFusion.compute_adaptive_weights (src/fusion.py:429-479) stand-alone:
+ * agg (M, B, H), gate_w (M, H), gate_b (M), mask (B, M) -> weights (B, M). */
+int msf_adaptive_weights(const float* agg, const float* gate_w, const float* gate_b, const float* mask,
+                         int64_t batch, int32_t num_modalities, int32_t hidden, float* weights,
+                         void* stream);
+/* Dropout multipliers (0 or 1/(1-p)) exactly as the kernels draw them, for
+ * injecting into the oracle.  site: 0 input (sub = m, rows x D_m), 1 projection
+ * (sub = m, rows x H), 2 attention weights (sub = q*M + k, rows x heads),
+ * 3 classifier hidden (sub = 0, rows x H). */
+int msf_dropout_mask(uint64_t seed, uint64_t offset, int32_t site, int32_t sub, int64_t rows,
+                     int64_t cols, float p, float* out, void* stream);
+
+/* gather/scatter between per-tensor storage and a flat arena.  `table` is a
+ * DEVICE array of n_tensors {int64 ptr, int64 arena_offset, int64 numel}. */
+int msf_arena_gather(const int64_t* table, int32_t n_tensors, int64_t total, float* arena, void* stream);
+int msf_arena_scatter(const int64_t* table, int32_t n_tensors, int64_t total, const float* arena, void* stream);
+
+/* ---- loss / confidence (src/train.py:185-186,310; src/eval.py:89-90) ------ */
+/* loss_out[0] = mean CE with label smoothing; grad_logits = d loss / d logits * grad_scale.
+ * row_loss: (B) scratch. labels int64. */
+int msf_cross_entropy(const float* logits, const int64_t* labels, int64_t batch, int32_t classes,
+                      float smoothing, float grad_scale, float* row_loss, float* loss_out,
+                      float* grad_logits, void* stream);
+int msf_softmax_conf_pred(const float* logits, int64_t batch, int32_t classes, float* conf,
+                          int64_t* pred, void* stream);
+
+/* ---- ECE / reliability binning (src/uncertainty.py:84-171,218-241) -------- */
+/* Single pass. edges: HOST array of num_bins+1 ascending doubles (fp32
+ * torch.linspace edges promoted, or np.linspace f64 edges). Bin i holds
+ * edges[i] <= c < edges[i+1]; the last bin also takes c == edges[num_bins].
+ * NaN / out-of-range confidences fall in no bin.  Accumulates INTO
+ * count/correct (int64[num_bins]) and conf_sum_q32 (uint64[num_bins], sum of
+ * round(c * 2^32)) — zero them first; integer adds make the result
+ * order-independent, hence deterministic and shard-mergeable. */
+int msf_ece_bin(const float* conf, const int64_t* pred, const int64_t* label, int64_t n,
+                const double* edges, int32_t num_bins, int64_t* count, int64_t* correct,
+                uint64_t* conf_sum_q32, void* stream);
+
+/* ---- optimizer (src/train.py:378-382,416-430) ------------------------------ */
+/* sq_norm[0] += sum(g^2) (double); zero it first. */
+int msf_grad_sq_norm(const float* grad, int64_t n, double* sq_norm, void* stream);
+/* AdamW over a flat arena.  clip: if max_norm > 0 the gradient is scaled by
+ * min(1, max_norm / (sqrt(sq_norm[0]) * grad_scale + 1e-6)) after grad_scale
+ * (1/world_size under data parallelism).  step is 1-based. */
+int msf_adamw_step(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                   int64_t step, float lr, float beta1, float beta2, float eps, float weight_decay,
+                   float grad_scale, float max_norm, const double* sq_norm, void* stream);
+/* Same, with the 1-based step read from device memory (train_state[2]) so the
+ * update can live inside a replayed CUDA graph. */
+int msf_adamw_step_dev(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                       const uint64_t* train_state, float lr, float beta1, float beta2, float eps,
+                       float weight_decay, float grad_scale, float max_norm, const double* sq_norm,
+                       void* stream);
+/* train_state = DEVICE {seed, offset, step}: offset += 1, step += 1. */
+int msf_train_state_advance(uint64_t* train_state, void* stream);
+
+/* ---- dense layer (nn.Linear) on the fp32 FFMA path ------------------------- */
+/* y[rows,out] = x[rows,in] . w[out,in]^T + b  (b may be NULL); relu != 0 applies max(.,0).
+ * Used by the stand-alone CrossModalAttention / encoder projection modules
+ * (src/attention.py:104-106,140; src/encoders.py:165). */
+int msf_linear_forward(const float* x, const float* w, const float* b, float* y, int64_t rows,
+                       int32_t in_dim, int32_t out_dim, int32_t relu, void* stream);
+/* dx = dy . w (NULL to skip); dw = dy^T . x; db = colsum(dy) (NULL to skip).
+ * If relu != 0, dy is first masked by y > 0 into dy_scratch (rows x out). */
+int msf_linear_backward(const float* x, const float* w, const float* y, const float* dy,
+                        float* dy_scratch, float* dx, float* dw, float* db, int64_t rows,
+                        int32_t in_dim, int32_t out_dim, int32_t relu, void* stream);
+
+/* ---- generic attention core (src/attention.py:108-139) --------------------- */
+/* q (B,Lq,H), k/v (B,Lk,H) already projected; mask (B,Lk) or NULL (0 = masked key).
+ * weights (B,heads,Lq,Lk) receives the post-dropout attention weights the
+ * reference returns; out (B,Lq,H) the merged-head context before out_proj. */
+int msf_attention_core_forward(const float* q, const float* k, const float* v, const float* mask,
+                               int64_t batch, int32_t q_len, int32_t k_len, int32_t hidden, int32_t heads,
+                               float dropout_p, int32_t training, uint64_t seed, uint64_t offset,
+                               float* weights, float* out, void* stream);
+/* scratch: (B,heads,Lq,Lk).  dk/dv are zeroed then accumulated. */
+int msf_attention_core_backward(const float* q, const float* k, const float* v, const float* mask,
+                                int64_t batch, int32_t q_len, int32_t k_len, int32_t hidden, int32_t heads,
+                                float dropout_p, int32_t training, uint64_t seed, uint64_t offset,
+                                const float* weights, const float* grad_out, float* scratch, float* dq,
+                                float* dk, float* dv, void* stream);
+
+/* ---- tensor-core GEMM building block (encoder/attention projections) ------ */
+/* D[M,N] (fp32 or bf16) = A[M,K] . B[N,K]^T, bf16 operands K-major, fp32 accumulate
+ * in TMEM via tcgen05.mma, operands staged by TMA.  M, N, K need not be tile
+ * multiples (TMA zero-fills); K % 8 == 0 and 16-byte aligned rows required. */
+int msf_gemm_bf16_nt(const void* a_bf16, const void* b_bf16, void* d, int32_t d_is_bf16,
+                     int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb, int64_t ldd,
+                     const float* bias, int32_t relu, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSF_B200_H_ */

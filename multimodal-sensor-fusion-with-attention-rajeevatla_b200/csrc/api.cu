@@ -1,0 +1,130 @@
+// Library-level entry points: version, error string, device check, arena layout.
+#include <stdarg.h>
+#include <string.h>
+
+#include "msf_common.cuh"
+
+namespace msf {
+
+static thread_local char g_err[512] = "";
+unsigned long long g_launch_count = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int make_layout(const msf_fusion_shape* s, Layout* L) {
+  MSF_REQUIRE(s != nullptr && L != nullptr, "null shape");
+  MSF_REQUIRE(s->num_modalities >= 1 && s->num_modalities <= MSF_MAX_MODALITIES,
+              "num_modalities %d out of range [1, %d]", s->num_modalities, MSF_MAX_MODALITIES);
+  MSF_REQUIRE(s->hidden >= 1 && s->num_heads >= 1 && s->hidden % s->num_heads == 0,
+              "hidden_dim (%d) must be divisible by num_heads (%d)", s->hidden, s->num_heads);
+  MSF_REQUIRE(s->num_classes >= 1, "num_classes must be >= 1");
+  L->M = s->num_modalities;
+  L->H = s->hidden;
+  L->heads = s->num_heads;
+  L->C = s->num_classes;
+  L->present = s->pair_present;
+  int64_t off = 0;
+  const int64_t H = L->H;
+  for (int m = 0; m < L->M; ++m) {
+    MSF_REQUIRE(s->in_dims[m] >= 1, "in_dims[%d] must be >= 1", m);
+    L->D[m] = s->in_dims[m];
+    L->proj_w[m] = off;
+    off += H * L->D[m];
+    L->proj_b[m] = off;
+    off += H;
+  }
+  L->pair_base = off;
+  L->pair_stride = 4 * (H * H + H);
+  off += (int64_t)L->num_pairs() * L->pair_stride;
+  for (int m = 0; m < L->M; ++m) {
+    L->gate_w[m] = off;
+    off += H;
+    L->gate_b[m] = off;
+    off += 1;
+  }
+  L->cls_w1 = off;
+  off += H * H;
+  L->cls_b1 = off;
+  off += H;
+  L->cls_w2 = off;
+  off += (int64_t)L->C * H;
+  L->cls_b2 = off;
+  off += L->C;
+  L->total = off;
+  return MSF_OK;
+}
+
+}  // namespace msf
+
+extern "C" {
+
+int msf_abi_version(void) { return MSF_ABI_VERSION; }
+
+int msf_struct_sizes(int32_t* shape_bytes, int32_t* call_bytes) {
+  if (shape_bytes) *shape_bytes = (int32_t)sizeof(msf_fusion_shape);
+  if (call_bytes) *call_bytes = (int32_t)sizeof(msf_fusion_call);
+  return MSF_OK;
+}
+
+uint64_t msf_launch_count(void) { return msf::g_launch_count; }
+
+const char* msf_last_error(void) { return msf::g_err; }
+
+int msf_device_check(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
+  int dev = 0;
+  MSF_CHECK_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  MSF_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  if (prop.major < 10) {
+    msf::set_error("device '%s' is sm_%d%d; this library is built for sm_100a only", prop.name,
+                   prop.major, prop.minor);
+    return MSF_E_UNSUPPORTED;
+  }
+  return MSF_OK;
+}
+
+int msf_fusion_param_count(const msf_fusion_shape* shape, int64_t* count) {
+  msf::Layout L;
+  int rc = msf::make_layout(shape, &L);
+  if (rc) return rc;
+  MSF_REQUIRE(count != nullptr, "null count");
+  *count = L.total;
+  return MSF_OK;
+}
+
+int msf_fusion_param_offset(const msf_fusion_shape* shape, int32_t kind, int32_t idx, int64_t* offset) {
+  msf::Layout L;
+  int rc = msf::make_layout(shape, &L);
+  if (rc) return rc;
+  MSF_REQUIRE(offset != nullptr, "null offset");
+  const int M = L.M;
+  if (kind == 0 || kind == 1 || kind == 10 || kind == 11) {
+    MSF_REQUIRE(idx >= 0 && idx < M, "modality index %d out of range", idx);
+    *offset = kind == 0 ? L.proj_w[idx] : kind == 1 ? L.proj_b[idx] : kind == 10 ? L.gate_w[idx] : L.gate_b[idx];
+    return MSF_OK;
+  }
+  if (kind >= 2 && kind <= 9) {
+    const int q = idx / M, k = idx % M;
+    MSF_REQUIRE(idx >= 0 && q < M && q != k, "pair index %d invalid", idx);
+    const int p = L.pair_index(q, k);
+    const int which = (kind - 2) / 2;
+    *offset = ((kind - 2) % 2 == 0) ? L.pair_w(p, which) : L.pair_b(p, which);
+    return MSF_OK;
+  }
+  if (kind >= 12 && kind <= 15) {
+    *offset = kind == 12 ? L.cls_w1 : kind == 13 ? L.cls_b1 : kind == 14 ? L.cls_w2 : L.cls_b2;
+    return MSF_OK;
+  }
+  msf::set_error("unknown tensor kind %d", kind);
+  return MSF_E_INVALID;
+}
+
+}  // extern "C"

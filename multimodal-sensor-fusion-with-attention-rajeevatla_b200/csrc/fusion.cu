@@ -1,0 +1,105 @@
+// C-ABI entry points of the HybridFusion path: validation + precision dispatch.
+#include "msf_common.cuh"
+
+namespace msf {
+size_t fusion_f32_workspace_bytes(const Layout& L, int64_t B);
+int fusion_f32_forward(const Layout& L, const msf_fusion_call* c, cudaStream_t st);
+int fusion_f32_backward(const Layout& L, const msf_fusion_call* c, cudaStream_t st);
+
+// tensor-core path (fusion_bf16.cu)
+bool fusion_bf16_eligible(const Layout& L);
+size_t fusion_bf16_workspace_bytes(const Layout& L, int64_t B);
+size_t fusion_bf16_arena_bytes(const Layout& L);
+int fusion_bf16_pack(const Layout& L, const float* params, void* arena, cudaStream_t st);
+int fusion_bf16_forward(const Layout& L, const msf_fusion_call* c, cudaStream_t st);
+int fusion_bf16_backward(const Layout& L, const msf_fusion_call* c, cudaStream_t st);
+
+static int check_call(const Layout& L, const msf_fusion_call* c, bool backward) {
+  MSF_REQUIRE(c != nullptr, "null call");
+  MSF_REQUIRE(c->batch >= 1, "batch must be >= 1 (got %d)", c->batch);
+  MSF_REQUIRE(c->precision == MSF_PREC_F32 || c->precision == MSF_PREC_BF16, "unknown precision %d",
+              c->precision);
+  MSF_REQUIRE(c->dropout_p >= 0.0f && c->dropout_p < 1.0f, "dropout_p must be in [0, 1)");
+  MSF_REQUIRE(c->params != nullptr, "null params");
+  for (int m = 0; m < L.M; ++m) MSF_REQUIRE(c->x[m] != nullptr, "null features for modality %d", m);
+  MSF_REQUIRE(c->workspace != nullptr, "null workspace");
+  if (!backward) MSF_REQUIRE(c->logits != nullptr, "null logits");
+  if (c->precision == MSF_PREC_BF16) {
+    MSF_REQUIRE(c->params_bf16 != nullptr, "BF16 precision needs params_bf16 (msf_fusion_pack_bf16)");
+    if (!fusion_bf16_eligible(L)) {
+      set_error("shape not eligible for the tensor-core path (needs hidden %% 64 == 0, hidden <= 256, "
+                "every in_dim %% 16 == 0)");
+      return MSF_E_UNSUPPORTED;
+    }
+  }
+  return MSF_OK;
+}
+}  // namespace msf
+
+extern "C" {
+
+int msf_fusion_workspace_bytes(const msf_fusion_shape* shape, int32_t batch, int32_t precision, size_t* bytes) {
+  msf::Layout L;
+  int rc = msf::make_layout(shape, &L);
+  if (rc) return rc;
+  MSF_REQUIRE(bytes != nullptr && batch >= 1, "msf_fusion_workspace_bytes: bad arguments");
+  if (precision == MSF_PREC_F32) {
+    *bytes = msf::fusion_f32_workspace_bytes(L, batch);
+    return MSF_OK;
+  }
+  if (precision == MSF_PREC_BF16) {
+    if (!msf::fusion_bf16_eligible(L)) {
+      msf::set_error("shape not eligible for the tensor-core path");
+      return MSF_E_UNSUPPORTED;
+    }
+    *bytes = msf::fusion_bf16_workspace_bytes(L, batch);
+    return MSF_OK;
+  }
+  msf::set_error("unknown precision %d", precision);
+  return MSF_E_INVALID;
+}
+
+int msf_fusion_bf16_arena_bytes(const msf_fusion_shape* shape, size_t* bytes) {
+  msf::Layout L;
+  int rc = msf::make_layout(shape, &L);
+  if (rc) return rc;
+  MSF_REQUIRE(bytes != nullptr, "null bytes");
+  if (!msf::fusion_bf16_eligible(L)) {
+    msf::set_error("shape not eligible for the tensor-core path");
+    return MSF_E_UNSUPPORTED;
+  }
+  *bytes = msf::fusion_bf16_arena_bytes(L);
+  return MSF_OK;
+}
+
+int msf_fusion_pack_bf16(const msf_fusion_shape* shape, const float* params, void* params_bf16, void* stream) {
+  msf::Layout L;
+  int rc = msf::make_layout(shape, &L);
+  if (rc) return rc;
+  MSF_REQUIRE(params && params_bf16, "msf_fusion_pack_bf16: null pointer");
+  if (!msf::fusion_bf16_eligible(L)) {
+    msf::set_error("shape not eligible for the tensor-core path");
+    return MSF_E_UNSUPPORTED;
+  }
+  return msf::fusion_bf16_pack(L, params, params_bf16, (cudaStream_t)stream);
+}
+
+int msf_fusion_forward(const msf_fusion_shape* shape, const msf_fusion_call* call, void* stream) {
+  msf::Layout L;
+  int rc = msf::make_layout(shape, &L);
+  if (rc) return rc;
+  if ((rc = msf::check_call(L, call, false))) return rc;
+  return call->precision == MSF_PREC_F32 ? msf::fusion_f32_forward(L, call, (cudaStream_t)stream)
+                                         : msf::fusion_bf16_forward(L, call, (cudaStream_t)stream);
+}
+
+int msf_fusion_backward(const msf_fusion_shape* shape, const msf_fusion_call* call, void* stream) {
+  msf::Layout L;
+  int rc = msf::make_layout(shape, &L);
+  if (rc) return rc;
+  if ((rc = msf::check_call(L, call, true))) return rc;
+  return call->precision == MSF_PREC_F32 ? msf::fusion_f32_backward(L, call, (cudaStream_t)stream)
+                                         : msf::fusion_bf16_backward(L, call, (cudaStream_t)stream);
+}
+
+}  // extern "C"

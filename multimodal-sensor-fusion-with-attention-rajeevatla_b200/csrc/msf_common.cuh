@@ -1,0 +1,144 @@
+// Shared helpers for the msf_b200 kernels: error plumbing, parameter-arena
+// layout, Philox4x32-10 dropout draws.  sm_100a only.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/msf_b200.h"
+
+namespace msf {
+
+// ---------------------------------------------------------------------------
+// error plumbing (never throw across the C ABI)
+// ---------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+
+#define MSF_CHECK_CUDA(expr)                                                          \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess) {                                                          \
+      ::msf::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,             \
+                       cudaGetErrorString(_e));                                       \
+      return MSF_E_CUDA;                                                              \
+    }                                                                                 \
+  } while (0)
+
+#define MSF_REQUIRE(cond, ...)                                                        \
+  do {                                                                                \
+    if (!(cond)) {                                                                    \
+      ::msf::set_error(__VA_ARGS__);                                                  \
+      return MSF_E_INVALID;                                                           \
+    }                                                                                 \
+  } while (0)
+
+// every kernel launch of the library is counted (bench.py reports it as gpu_launches)
+extern unsigned long long g_launch_count;
+#define MSF_LAUNCH_CHECK()                  \
+  do {                                      \
+    ++::msf::g_launch_count;                \
+    MSF_CHECK_CUDA(cudaGetLastError());     \
+  } while (0)
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------
+// master-arena layout (see include/msf_b200.h; src/fusion.py:291-328 order)
+// ---------------------------------------------------------------------------
+struct Layout {
+  int M, H, heads, C;
+  int D[MSF_MAX_MODALITIES];
+  uint64_t present;
+  int64_t proj_w[MSF_MAX_MODALITIES], proj_b[MSF_MAX_MODALITIES];
+  int64_t pair_base;   // first attention module
+  int64_t pair_stride; // 4*(H*H+H)
+  int64_t gate_w[MSF_MAX_MODALITIES], gate_b[MSF_MAX_MODALITIES];
+  int64_t cls_w1, cls_b1, cls_w2, cls_b2;
+  int64_t total;
+
+  __host__ __device__ int num_pairs() const { return M * (M - 1); }
+  // q-major index among ordered pairs q != k
+  __host__ __device__ int pair_index(int q, int k) const { return q * (M - 1) + (k < q ? k : k - 1); }
+  __host__ __device__ bool has_pair(int q, int k) const { return (present >> (q * M + k)) & 1ull; }
+  // which: 0 query, 1 key, 2 value, 3 out
+  __host__ __device__ int64_t pair_w(int p, int which) const {
+    return pair_base + (int64_t)p * pair_stride + (int64_t)which * ((int64_t)H * H + H);
+  }
+  __host__ __device__ int64_t pair_b(int p, int which) const { return pair_w(p, which) + (int64_t)H * H; }
+  // number of tensors averaged into aggregated[q]: itself + present pair modules (fusion.py:403-407)
+  __host__ __device__ int mean_count(int q) const {
+    int c = 1;
+    for (int k = 0; k < M; ++k) c += (k != q && has_pair(q, k)) ? 1 : 0;
+    return c;
+  }
+};
+
+int make_layout(const msf_fusion_shape* s, Layout* out);
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 (counter-based; forward and backward regenerate the same draw)
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+  const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+  const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+  const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+  c[0] = hi1 ^ c[1] ^ k0;
+  c[1] = lo1;
+  c[2] = hi0 ^ c[3] ^ k1;
+  c[3] = lo0;
+}
+
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
+struct DropCfg {
+  uint64_t seed, offset;
+  float p;         // drop probability
+  float scale;     // 1/(1-p)
+  int active;      // training && p > 0
+  const unsigned long long* state;  // optional device {seed, offset}: overrides the two fields above
+};
+
+// Resolve a device-resident RNG state once per kernel (block-uniform).
+__device__ __forceinline__ DropCfg resolve_drop(DropCfg d) {
+  if (d.state != nullptr) {
+    d.seed = d.state[0];
+    d.offset = d.state[1];
+  }
+  return d;
+}
+
+// Four multipliers for elements (row, col4*4 .. col4*4+3) of a dropout site.
+__host__ __device__ __forceinline__ void drop4(const DropCfg& d, int site, int sub, int64_t row,
+                                               int col4, float (&out)[4]) {
+  uint32_t c[4] = {(uint32_t)row, (uint32_t)col4, ((uint32_t)site << 24) | (uint32_t)sub,
+                   (uint32_t)d.offset};  // rows < 2^32
+  philox4x32_10(c, (uint32_t)d.seed, (uint32_t)(d.seed >> 32) ^ (uint32_t)(d.offset >> 32));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float u = (float)(c[i] >> 8) * (1.0f / 16777216.0f);  // [0,1), 24 bits
+    out[i] = (u >= d.p) ? d.scale : 0.0f;
+  }
+}
+
+// Single multiplier for element (row, col).
+__host__ __device__ __forceinline__ float drop1(const DropCfg& d, int site, int sub, int64_t row, int col) {
+  if (!d.active) return 1.0f;
+  float v[4];
+  drop4(d, site, sub, row, col >> 2, v);
+  return v[col & 3];
+}
+
+enum { SITE_INPUT = 0, SITE_PROJ = 1, SITE_ATTN = 2, SITE_CLS = 3 };
+
+}  // namespace msf

@@ -1,0 +1,183 @@
+// Flat-arena optimizer pieces: gradient square-norm, AdamW with global-norm
+// clipping, and gather/scatter between per-tensor storage and the arena.
+//   src/train.py:378-382   torch.optim.AdamW(lr, weight_decay)
+//   src/train.py:416-430   clip_gradients(..., gradient_clip_algorithm="norm")
+#include "msf_common.cuh"
+
+namespace msf {
+namespace {
+
+__global__ void __launch_bounds__(256) sq_norm_kernel(const float* __restrict__ g, long long n,
+                                                      double* __restrict__ out) {
+  double s = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double v = (double)__ldg(g + i);
+    s += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ double sh[8];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += sh[i];
+    atomicAdd(out, t);
+  }
+}
+
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                    float* __restrict__ m, float* __restrict__ v, long long n,
+                                                    float lr, float beta1, float beta2, float eps, float wd,
+                                                    float bc1, float sqrt_bc2, float grad_scale,
+                                                    float max_norm, const double* __restrict__ sq_norm,
+                                                    const unsigned long long* __restrict__ train_state) {
+  if (train_state != nullptr) {  // step lives on the device (CUDA-graph replay)
+    const double step = (double)train_state[2];
+    bc1 = (float)(1.0 - pow((double)beta1, step));
+    sqrt_bc2 = (float)sqrt(1.0 - pow((double)beta2, step));
+  }
+  float gs = grad_scale;
+  if (max_norm > 0.0f && sq_norm != nullptr) {
+    const float total = (float)sqrt(*sq_norm) * grad_scale;
+    const float coef = max_norm / (total + 1e-6f);
+    gs *= fminf(coef, 1.0f);
+  }
+  const float step_size = lr / bc1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gs;
+    float pi = p[i] * (1.0f - lr * wd);
+    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+    const float denom = sqrtf(vi) / sqrt_bc2 + eps;
+    pi -= step_size * (mi / denom);
+    p[i] = pi;
+    m[i] = mi;
+    v[i] = vi;
+  }
+}
+
+// table: n_tensors x {ptr, arena_offset, numel}
+template <bool GATHER>
+__global__ void __launch_bounds__(256) arena_copy_kernel(const long long* __restrict__ table, int n_tensors,
+                                                         float* __restrict__ arena) {
+  const int t = blockIdx.y;
+  if (t >= n_tensors) return;
+  float* ptr = reinterpret_cast<float*>(table[3 * t]);
+  const long long off = table[3 * t + 1], numel = table[3 * t + 2];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < numel;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (GATHER) arena[off + i] = ptr[i];
+    else ptr[i] = arena[off + i];
+  }
+}
+
+__global__ void train_state_advance_kernel(unsigned long long* state) {
+  state[1] += 1ull;
+  state[2] += 1ull;
+}
+
+__global__ void __launch_bounds__(256) dropout_mask_kernel(DropCfg d, int site, int sub, long long rows,
+                                                           long long cols, float* __restrict__ out) {
+  const long long quads = (cols + 3) >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < rows * quads;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / quads;
+    const int c4 = (int)(i % quads);
+    float v[4];
+    drop4(d, site, sub, row, c4, v);
+    for (int j = 0; j < 4; ++j)
+      if (c4 * 4 + j < cols) out[row * cols + c4 * 4 + j] = v[j];
+  }
+}
+
+}  // namespace
+}  // namespace msf
+
+extern "C" {
+
+int msf_grad_sq_norm(const float* grad, int64_t n, double* sq_norm, void* stream) {
+  MSF_REQUIRE(grad && sq_norm && n >= 0, "msf_grad_sq_norm: bad arguments");
+  if (n == 0) return MSF_OK;
+  long long blocks = msf::ceil_div(n, 256 * 8);
+  if (blocks > 592) blocks = 592;
+  msf::sq_norm_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(grad, n, sq_norm);
+  MSF_LAUNCH_CHECK();
+  return MSF_OK;
+}
+
+int msf_adamw_step(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                   int64_t step, float lr, float beta1, float beta2, float eps, float weight_decay,
+                   float grad_scale, float max_norm, const double* sq_norm, void* stream) {
+  MSF_REQUIRE(params && grad && exp_avg && exp_avg_sq && n >= 0 && step >= 1, "msf_adamw_step: bad arguments");
+  if (n == 0) return MSF_OK;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  long long blocks = msf::ceil_div(n, 256 * 4);
+  if (blocks > 1184) blocks = 1184;
+  msf::adamw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      params, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, (float)bc1,
+      (float)sqrt(bc2), grad_scale, max_norm, sq_norm, nullptr);
+  MSF_LAUNCH_CHECK();
+  return MSF_OK;
+}
+
+int msf_adamw_step_dev(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                       const uint64_t* train_state, float lr, float beta1, float beta2, float eps,
+                       float weight_decay, float grad_scale, float max_norm, const double* sq_norm,
+                       void* stream) {
+  MSF_REQUIRE(params && grad && exp_avg && exp_avg_sq && train_state && n >= 0, "msf_adamw_step_dev: bad arguments");
+  if (n == 0) return MSF_OK;
+  long long blocks = msf::ceil_div(n, 256 * 4);
+  if (blocks > 1184) blocks = 1184;
+  msf::adamw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      params, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, 1.0f, 1.0f, grad_scale,
+      max_norm, sq_norm, reinterpret_cast<const unsigned long long*>(train_state));
+  MSF_LAUNCH_CHECK();
+  return MSF_OK;
+}
+
+int msf_train_state_advance(uint64_t* train_state, void* stream) {
+  MSF_REQUIRE(train_state != nullptr, "msf_train_state_advance: null state");
+  msf::train_state_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<unsigned long long*>(train_state));
+  MSF_LAUNCH_CHECK();
+  return MSF_OK;
+}
+
+int msf_arena_gather(const int64_t* table, int32_t n_tensors, int64_t total, float* arena, void* stream) {
+  MSF_REQUIRE(table && arena && n_tensors >= 0 && total >= 0, "msf_arena_gather: bad arguments");
+  if (n_tensors == 0) return MSF_OK;
+  dim3 grid(64, (unsigned)n_tensors);
+  msf::arena_copy_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const long long*>(table), n_tensors, arena);
+  MSF_LAUNCH_CHECK();
+  return MSF_OK;
+}
+
+int msf_arena_scatter(const int64_t* table, int32_t n_tensors, int64_t total, const float* arena, void* stream) {
+  MSF_REQUIRE(table && arena && n_tensors >= 0 && total >= 0, "msf_arena_scatter: bad arguments");
+  if (n_tensors == 0) return MSF_OK;
+  dim3 grid(64, (unsigned)n_tensors);
+  msf::arena_copy_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const long long*>(table), n_tensors, const_cast<float*>(arena));
+  MSF_LAUNCH_CHECK();
+  return MSF_OK;
+}
+
+int msf_dropout_mask(uint64_t seed, uint64_t offset, int32_t site, int32_t sub, int64_t rows, int64_t cols,
+                     float p, float* out, void* stream) {
+  MSF_REQUIRE(out && rows >= 0 && cols >= 0 && p >= 0.0f && p < 1.0f, "msf_dropout_mask: bad arguments");
+  if (rows * cols == 0) return MSF_OK;
+  msf::DropCfg d;
+  d.seed = seed; d.offset = offset; d.p = p; d.scale = 1.0f / (1.0f - p); d.active = 1; d.state = nullptr;
+  long long blocks = msf::ceil_div(rows * ((cols + 3) / 4), 256);
+  if (blocks > 2048) blocks = 2048;
+  msf::dropout_mask_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d, site, sub, rows, cols, out);
+  MSF_LAUNCH_CHECK();
+  return MSF_OK;
+}
+
+}  // extern "C"

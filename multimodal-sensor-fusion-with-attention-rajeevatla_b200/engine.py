@@ -1,0 +1,215 @@
+"""Fused HybridFusion train step / inference pass with flat arenas, CUDA graphs
+and batch-sharded data parallelism.
+
+One process per GPU.  Everything a training step of the reference does around
+the fusion model (``train.MultimodalFusionModule.training_step`` +
+``configure_gradient_clipping`` + ``AdamW``; src/train.py:302-324,378-382,
+416-430) is enqueued as one stream of msf_b200 kernels:
+
+    forward -> CE(label smoothing) -> backward -> [NCCL all-reduce of the
+    gradient arena] -> global grad norm -> clip + AdamW -> (bf16 re-pack)
+
+and captured once into a CUDA graph; ``step()`` copies the batch into static
+buffers and replays it.  Dropout masks and the Adam step count live in a small
+device-side state so every replay draws fresh masks.
+
+Windows are independent, so data parallelism shards the batch across ranks with
+replicated parameters; the only collective is the gradient all-reduce
+(SURVEY.md §8e).  Evaluation / ECE are shard-local followed by one integer
+all-reduce of the bin counts.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import _native as N
+from . import ops
+
+
+class FusionEngine:
+    def __init__(self, model, batch: int, *, precision: str = "bf16", lr: float = 1e-3,
+                 weight_decay: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
+                 label_smoothing: float = 0.05, max_grad_norm: float = 1.0, seed: int = 1234,
+                 process_group=None, use_graph: bool = True, device: Optional[torch.device] = None):
+        self.dev = device or ops.require_cuda("FusionEngine")
+        self.model = model.to(self.dev)
+        self.plan = model._plan()
+        self.batch = int(batch)
+        self.prec = ops.PRECISIONS[precision]
+        self.precision = precision
+        self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.smoothing, self.max_norm = label_smoothing, max_grad_norm
+        self.p = float(model.dropout.p)
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self.use_graph = use_graph
+        plan, dev, B = self.plan, self.dev, self.batch
+        f32 = dict(dtype=torch.float32, device=dev)
+
+        # flat master arena; the module's parameters become views into it
+        own = dict(self.model.named_parameters())
+        self.arena = torch.zeros(plan.total, **f32)
+        with torch.no_grad():
+            for key, off, shape in plan.slots:
+                prm = own[key]
+                n = prm.numel()
+                self.arena[off:off + n].copy_(prm.detach().reshape(-1))
+                prm.data = self.arena[off:off + n].view(shape)
+        self.grad = torch.zeros(plan.total, **f32)
+        self.exp_avg = torch.zeros(plan.total, **f32)
+        self.exp_avg_sq = torch.zeros(plan.total, **f32)
+        self.arena_bf16 = None
+        if self.prec == N.MSF_PREC_BF16:
+            self.arena_bf16 = plan.pack_bf16(self.arena)
+        self.ws = torch.empty(plan.workspace_bytes(B, self.prec), dtype=torch.uint8, device=dev)
+
+        # static I/O buffers (graph inputs / outputs)
+        self.x = [torch.zeros(B, d, **f32) for d in plan.dims]
+        self.mask = torch.ones(B, plan.M, **f32)
+        self.labels = torch.zeros(B, dtype=torch.int64, device=dev)
+        self.logits = torch.zeros(B, plan.C, **f32)
+        self.dlogits = torch.zeros(B, plan.C, **f32)
+        self.row_loss = torch.zeros(B, **f32)
+        self.loss = torch.zeros(1, **f32)
+        self.sq_norm = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.conf = torch.zeros(B, **f32)
+        self.pred = torch.zeros(B, dtype=torch.int64, device=dev)
+        # {seed, offset, step}; step is 1-based when the optimizer kernel reads it
+        self.state = torch.tensor([seed, 0, 1], dtype=torch.int64, device=dev)
+        self._train_graph = None
+        self._infer_graph = None
+        self.launches_per_step = 0
+
+    # -- enqueue helpers (all on the current stream) ---------------------------------
+    def _call(self, training: bool) -> N.FusionCall:
+        c = ops._make_call(self.plan, self.batch, self.prec, training and self.p > 0, self.p, 0, 0,
+                           self.arena, self.arena_bf16, self.x, self.mask, self.ws)
+        c.rng_state = self.state.data_ptr()
+        return c
+
+    def _enqueue_forward(self, training: bool) -> None:
+        c = self._call(training)
+        c.logits = self.logits.data_ptr()
+        N.check(N.lib().msf_fusion_forward(ctypes_ref(self.plan.shape), ctypes_ref(c), ops._stream()))
+
+    def _enqueue_train_step(self) -> None:
+        lib = N.lib()
+        st = ops._stream()
+        self._enqueue_forward(True)
+        # mean over the GLOBAL batch: each rank scales by 1/(B*world), the all-reduce sums
+        N.check(lib.msf_cross_entropy(self.logits.data_ptr(), self.labels.data_ptr(), self.batch, self.plan.C,
+                                      self.smoothing, 1.0 / (self.batch * self.world), self.row_loss.data_ptr(),
+                                      self.loss.data_ptr(), self.dlogits.data_ptr(), st))
+        c = self._call(True)
+        c.grad_logits, c.grad_params = self.dlogits.data_ptr(), self.grad.data_ptr()
+        N.check(lib.msf_fusion_backward(ctypes_ref(self.plan.shape), ctypes_ref(c), st))
+        if self.world > 1:
+            torch.distributed.all_reduce(self.grad, group=self.pg)
+        self.sq_norm.zero_()
+        N.check(lib.msf_grad_sq_norm(self.grad.data_ptr(), self.plan.total, self.sq_norm.data_ptr(), st))
+        N.check(lib.msf_adamw_step_dev(self.arena.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
+                                       self.exp_avg_sq.data_ptr(), self.plan.total, self.state.data_ptr(),
+                                       self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 1.0,
+                                       self.max_norm, self.sq_norm.data_ptr(), st))
+        if self.arena_bf16 is not None:
+            N.check(lib.msf_fusion_pack_bf16(ctypes_ref(self.plan.shape), self.arena.data_ptr(),
+                                             self.arena_bf16.data_ptr(), st))
+        N.check(lib.msf_train_state_advance(self.state.data_ptr(), st))
+
+    def _enqueue_inference(self) -> None:
+        self._enqueue_forward(False)
+        N.check(N.lib().msf_softmax_conf_pred(self.logits.data_ptr(), self.batch, self.plan.C,
+                                              self.conf.data_ptr(), self.pred.data_ptr(), ops._stream()))
+
+    def _capture(self, fn):
+        if not self.use_graph:
+            return None
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            fn()  # warm-up outside capture (lazy module loading, NCCL channel setup)
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            fn()
+        return graph
+
+    # -- public API --------------------------------------------------------------------
+    def load_batch(self, features: Dict[str, torch.Tensor] | Sequence[torch.Tensor],
+                   mask: Optional[torch.Tensor], labels: Optional[torch.Tensor] = None) -> int:
+        """Copy one batch (host-pinned or device tensors) into the static buffers.
+        Returns the bytes that crossed host->device."""
+        feats = [features[m] for m in self.plan.names] if isinstance(features, dict) else list(features)
+        moved = 0
+        for dst, src in zip(self.x, feats):
+            dst.copy_(src, non_blocking=True)
+            moved += src.numel() * src.element_size() if src.device.type == "cpu" else 0
+        if mask is None:
+            self.mask.fill_(1.0)
+        else:
+            self.mask.copy_(mask, non_blocking=True)
+            moved += mask.numel() * mask.element_size() if mask.device.type == "cpu" else 0
+        if labels is not None:
+            self.labels.copy_(labels, non_blocking=True)
+            moved += labels.numel() * labels.element_size() if labels.device.type == "cpu" else 0
+        return moved
+
+    def train_step_resident(self) -> torch.Tensor:
+        """One optimizer step on the batch already in the static buffers.
+        Returns the (device) mean loss of this rank's shard scaled to the global batch."""
+        if self.use_graph:
+            if self._train_graph is None:
+                snap = (self.arena.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(), self.state.clone())
+                self._train_graph = self._capture(self._enqueue_train_step)
+                # the warm-up run inside _capture advanced the model once: roll it back
+                for dst, src in zip((self.arena, self.exp_avg, self.exp_avg_sq, self.state), snap):
+                    dst.copy_(src)
+                if self.arena_bf16 is not None:
+                    self.arena_bf16.copy_(self.plan.pack_bf16(self.arena))
+            self._train_graph.replay()
+        else:
+            self._enqueue_train_step()
+        return self.loss
+
+    def train_step(self, features, mask, labels) -> torch.Tensor:
+        self.load_batch(features, mask, labels)
+        return self.train_step_resident()
+
+    def infer_resident(self):
+        if self.use_graph:
+            if self._infer_graph is None:
+                self._infer_graph = self._capture(self._enqueue_inference)
+            self._infer_graph.replay()
+        else:
+            self._enqueue_inference()
+        return self.logits, self.conf, self.pred
+
+    def infer(self, features, mask):
+        self.load_batch(features, mask)
+        return self.infer_resident()
+
+    def ece_bins(self, labels: torch.Tensor, edges: Sequence[float], out=None) -> torch.Tensor:
+        """Shard-local binning of the last inference, then one integer all-reduce
+        of the (3, num_bins) statistics."""
+        stats = ops.ece_bin(self.conf, self.pred, labels.to(self.dev), edges, out=out)
+        if self.world > 1:
+            torch.distributed.all_reduce(stats, group=self.pg)
+        return stats
+
+
+def ctypes_ref(obj):
+    import ctypes
+    return ctypes.byref(obj)
+
+
+def shard_batch(global_batch: int, rank: int, world: int) -> slice:
+    """Contiguous, equal shards (equal sizes keep mean-of-means == global mean)."""
+    if global_batch % world != 0:
+        raise ValueError(f"global batch {global_batch} is not divisible by world size {world}")
+    per = global_batch // world
+    return slice(rank * per, (rank + 1) * per)

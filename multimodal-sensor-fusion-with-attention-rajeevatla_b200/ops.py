@@ -1,0 +1,412 @@
+"""torch-facing wrappers over the C ABI: device-pointer plumbing, workspaces and
+``torch.autograd.Function`` glue.  PyTorch only owns memory and streams here;
+every FLOP of the path runs in ``libmsf_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes
+import itertools
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _native as N
+
+PRECISIONS = {"fp32": N.MSF_PREC_F32, "bf16": N.MSF_PREC_BF16}
+
+
+def require_cuda(what: str = "this operation") -> torch.device:
+    """The product has no CPU path: fail loudly instead of falling back."""
+    if not torch.cuda.is_available():
+        raise N.MsfError(
+            f"{what} needs a CUDA device (sm_100a); msf_b200 has no CPU or PyTorch-eager fallback"
+        )
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _f32c(t: torch.Tensor, dev: torch.device) -> torch.Tensor:
+    return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+# ---------------------------------------------------------------------------
+# HybridFusion plan: shape struct + master-arena slots
+# ---------------------------------------------------------------------------
+class FusionPlan:
+    """Static description of one HybridFusion instance (src/fusion.py:267-329)."""
+
+    def __init__(self, names: Sequence[str], dims: Sequence[int], hidden: int, heads: int,
+                 classes: int, present_pairs: Sequence[Tuple[int, int]]):
+        self.names = list(names)
+        self.dims = [int(d) for d in dims]
+        self.M, self.H, self.heads, self.C = len(self.names), int(hidden), int(heads), int(classes)
+        if not 1 <= self.M <= N.MSF_MAX_MODALITIES:
+            raise ValueError(f"msf_b200 supports 1..{N.MSF_MAX_MODALITIES} modalities, got {self.M}")
+        self.present = sorted(set(present_pairs))
+        bits = 0
+        for q, k in self.present:
+            bits |= 1 << (q * self.M + k)
+        self.shape = N.FusionShape()
+        self.shape.num_modalities, self.shape.hidden = self.M, self.H
+        self.shape.num_heads, self.shape.num_classes = self.heads, self.C
+        for i, d in enumerate(self.dims):
+            self.shape.in_dims[i] = d
+        self.shape.pair_present = bits
+        cnt = ctypes.c_int64()
+        N.check(N.lib().msf_fusion_param_count(ctypes.byref(self.shape), ctypes.byref(cnt)))
+        self.total = cnt.value
+        self.slots = self._slots()  # [(state_dict key, offset, shape)] in master order, present tensors only
+        self._tables: Dict[tuple, torch.Tensor] = {}
+
+    def key(self):
+        return (tuple(self.names), tuple(self.dims), self.H, self.heads, self.C, tuple(self.present))
+
+    def _offset(self, kind: int, idx: int) -> int:
+        off = ctypes.c_int64()
+        N.check(N.lib().msf_fusion_param_offset(ctypes.byref(self.shape), kind, idx, ctypes.byref(off)))
+        return off.value
+
+    def _slots(self):
+        H, M, C = self.H, self.M, self.C
+        out = []
+        for m, name in enumerate(self.names):
+            out.append((f"projections.{name}.0.weight", self._offset(0, m), (H, self.dims[m])))
+            out.append((f"projections.{name}.0.bias", self._offset(1, m), (H,)))
+        for q, k in itertools.permutations(range(M), 2):
+            if (q, k) not in self.present:
+                continue
+            pre = f"attention_modules.{self.names[q]}_to_{self.names[k]}"
+            for w, proj in enumerate(("query_proj", "key_proj", "value_proj", "out_proj")):
+                out.append((f"{pre}.{proj}.weight", self._offset(2 + 2 * w, q * M + k), (H, H)))
+                out.append((f"{pre}.{proj}.bias", self._offset(3 + 2 * w, q * M + k), (H,)))
+        for m, name in enumerate(self.names):
+            out.append((f"gating_layers.{name}.weight", self._offset(10, m), (1, H)))
+            out.append((f"gating_layers.{name}.bias", self._offset(11, m), (1,)))
+        out.append(("classifier.0.weight", self._offset(12, 0), (H, H)))
+        out.append(("classifier.0.bias", self._offset(13, 0), (H,)))
+        out.append(("classifier.3.weight", self._offset(14, 0), (C, H)))
+        out.append(("classifier.3.bias", self._offset(15, 0), (C,)))
+        return out
+
+    @property
+    def dense(self) -> bool:
+        return len(self.present) == self.M * (self.M - 1)
+
+    def workspace_bytes(self, batch: int, precision: int) -> int:
+        b = ctypes.c_size_t()
+        N.check(N.lib().msf_fusion_workspace_bytes(ctypes.byref(self.shape), batch, precision, ctypes.byref(b)))
+        return b.value
+
+    def bf16_arena_bytes(self) -> int:
+        b = ctypes.c_size_t()
+        N.check(N.lib().msf_fusion_bf16_arena_bytes(ctypes.byref(self.shape), ctypes.byref(b)))
+        return b.value
+
+    # -- per-tensor storage <-> flat master arena --------------------------------
+    def _table(self, tensors: Sequence[torch.Tensor]) -> torch.Tensor:
+        ptrs = tuple(t.data_ptr() for t in tensors)
+        tab = self._tables.get(ptrs)
+        if tab is None:
+            rows = [[t.data_ptr(), off, t.numel()] for t, (_, off, _) in zip(tensors, self.slots)]
+            tab = torch.tensor(rows, dtype=torch.int64).to(tensors[0].device)
+            if len(self._tables) > 16:
+                self._tables.clear()
+            self._tables[ptrs] = tab
+        return tab
+
+    def gather(self, tensors: Sequence[torch.Tensor]) -> torch.Tensor:
+        """Pack per-parameter tensors (slot order) into a fresh master arena."""
+        dev = tensors[0].device
+        alloc = torch.empty if self.dense else torch.zeros
+        arena = alloc(self.total, dtype=torch.float32, device=dev)
+        N.check(N.lib().msf_arena_gather(_p(self._table(tensors)), len(tensors), self.total, _p(arena), _stream()))
+        return arena
+
+    def scatter(self, arena: torch.Tensor, tensors: Sequence[torch.Tensor]) -> None:
+        N.check(N.lib().msf_arena_scatter(_p(self._table(tensors)), len(tensors), self.total, _p(arena), _stream()))
+
+    def pack_bf16(self, arena: torch.Tensor) -> torch.Tensor:
+        out = torch.empty(self.bf16_arena_bytes(), dtype=torch.uint8, device=arena.device)
+        N.check(N.lib().msf_fusion_pack_bf16(ctypes.byref(self.shape), _p(arena), _p(out), _stream()))
+        return out
+
+
+_PLANS: Dict[tuple, FusionPlan] = {}
+
+
+def get_plan(names, dims, hidden, heads, classes, present) -> FusionPlan:
+    """Process-wide plan cache: modules stay free of ctypes state (deepcopy / pickle safe)."""
+    key = (tuple(names), tuple(int(d) for d in dims), int(hidden), int(heads), int(classes),
+           tuple(sorted(set(present))))
+    plan = _PLANS.get(key)
+    if plan is None:
+        if len(_PLANS) > 64:
+            _PLANS.clear()
+        plan = _PLANS[key] = FusionPlan(names, dims, hidden, heads, classes, present)
+    return plan
+
+
+def _make_call(plan: FusionPlan, batch: int, precision: int, training: bool, p: float, seed: int,
+               offset: int, arena: torch.Tensor, arena_bf16: Optional[torch.Tensor],
+               xs: Sequence[torch.Tensor], mask: Optional[torch.Tensor], ws: torch.Tensor) -> N.FusionCall:
+    c = N.FusionCall()
+    c.batch, c.precision, c.training, c.dropout_p = batch, precision, int(bool(training)), float(p)
+    c.seed, c.offset = seed & (2**64 - 1), offset & (2**64 - 1)
+    c.params, c.params_bf16 = _p(arena), _p(arena_bf16)
+    for i, x in enumerate(xs):
+        c.x[i] = _p(x)
+    c.mask = _p(mask)
+    c.workspace, c.workspace_bytes = _p(ws), ws.numel()
+    return c
+
+
+def fusion_forward_raw(plan: FusionPlan, arena: torch.Tensor, xs: Sequence[torch.Tensor],
+                       mask: Optional[torch.Tensor], *, precision: int = N.MSF_PREC_F32,
+                       training: bool = False, p: float = 0.0, seed: int = 0, offset: int = 0,
+                       arena_bf16: Optional[torch.Tensor] = None, want_aux: bool = True,
+                       workspace: Optional[torch.Tensor] = None):
+    """One msf_fusion_forward call on already-prepared device buffers."""
+    dev = arena.device
+    B = xs[0].shape[0]
+    if workspace is None:
+        workspace = torch.empty(plan.workspace_bytes(B, precision), dtype=torch.uint8, device=dev)
+    logits = torch.empty(B, plan.C, dtype=torch.float32, device=dev)
+    fw = gates = None
+    call = _make_call(plan, B, precision, training, p, seed, offset, arena, arena_bf16, xs, mask, workspace)
+    call.logits = _p(logits)
+    if want_aux:
+        fw = torch.empty(B, plan.M, dtype=torch.float32, device=dev)
+        gates = torch.empty(plan.M * (plan.M - 1), B, plan.heads, dtype=torch.float32, device=dev)
+        call.fusion_weights, call.attn_gates = _p(fw), _p(gates)
+    N.check(N.lib().msf_fusion_forward(ctypes.byref(plan.shape), ctypes.byref(call), _stream()))
+    return logits, fw, gates, workspace
+
+
+def fusion_backward_raw(plan: FusionPlan, arena: torch.Tensor, xs: Sequence[torch.Tensor],
+                        mask: Optional[torch.Tensor], workspace: torch.Tensor, grad_logits: torch.Tensor,
+                        *, precision: int = N.MSF_PREC_F32, training: bool = False, p: float = 0.0,
+                        seed: int = 0, offset: int = 0, arena_bf16: Optional[torch.Tensor] = None,
+                        need_dx: Sequence[bool] = (), grad_arena: Optional[torch.Tensor] = None):
+    dev = arena.device
+    B = xs[0].shape[0]
+    if grad_arena is None:
+        grad_arena = torch.empty(plan.total, dtype=torch.float32, device=dev)
+    call = _make_call(plan, B, precision, training, p, seed, offset, arena, arena_bf16, xs, mask, workspace)
+    call.grad_logits, call.grad_params = _p(grad_logits), _p(grad_arena)
+    dxs: List[Optional[torch.Tensor]] = []
+    for i, x in enumerate(xs):
+        need = bool(need_dx[i]) if i < len(need_dx) else False
+        dx = torch.empty_like(x) if need else None
+        call.grad_x[i] = _p(dx)
+        dxs.append(dx)
+    N.check(N.lib().msf_fusion_backward(ctypes.byref(plan.shape), ctypes.byref(call), _stream()))
+    return grad_arena, dxs
+
+
+class HybridFusionFunction(torch.autograd.Function):
+    """Autograd node for HybridFusion.forward (src/fusion.py:331-427).
+
+    ``tensors`` = the M feature tensors followed by the parameters in
+    ``plan.slots`` order, all fp32 CUDA.  Dead query/key projection parameters
+    receive exact-zero gradient tensors (never ``None``), matching the
+    reference's autograd (SURVEY.md §7 hard part 2).
+    """
+
+    @staticmethod
+    def forward(ctx, plan: FusionPlan, cfg: dict, mask: Optional[torch.Tensor], *tensors):
+        M = plan.M
+        xs = [t.contiguous() for t in tensors[:M]]
+        params = [t.contiguous() for t in tensors[M:]]
+        precision = cfg["precision"]
+        arena = plan.gather(params)
+        arena_bf16 = plan.pack_bf16(arena) if precision == N.MSF_PREC_BF16 else None
+        logits, fw, gates, ws = fusion_forward_raw(
+            plan, arena, xs, mask, precision=precision, training=cfg["training"], p=cfg["p"],
+            seed=cfg["seed"], offset=cfg["offset"], arena_bf16=arena_bf16, want_aux=True)
+        ctx.plan, ctx.cfg, ctx.mask = plan, cfg, mask
+        ctx.saved = (arena, arena_bf16, xs, ws)
+        ctx.param_shapes = [t.shape for t in tensors[M:]]
+        ctx.mark_non_differentiable(fw, gates)
+        return logits, fw, gates
+
+    @staticmethod
+    def backward(ctx, grad_logits, _gfw, _ggates):
+        plan, cfg = ctx.plan, ctx.cfg
+        arena, arena_bf16, xs, ws = ctx.saved
+        M = plan.M
+        need_dx = ctx.needs_input_grad[3:3 + M]
+        g = grad_logits.to(torch.float32).contiguous()
+        grad_arena, dxs = fusion_backward_raw(
+            plan, arena, xs, ctx.mask, ws, g, precision=cfg["precision"], training=cfg["training"],
+            p=cfg["p"], seed=cfg["seed"], offset=cfg["offset"], arena_bf16=arena_bf16, need_dx=need_dx)
+        grads = [grad_arena[off:off + int(torch.Size(shape).numel())].view(shape)
+                 for (_, off, _), shape in zip(plan.slots, ctx.param_shapes)]
+        return (None, None, None, *dxs, *grads)
+
+
+def adaptive_weights(feats: Sequence[torch.Tensor], gate_w: Sequence[torch.Tensor],
+                     gate_b: Sequence[torch.Tensor], mask: torch.Tensor) -> torch.Tensor:
+    """HybridFusion.compute_adaptive_weights (src/fusion.py:429-479) on the tail kernel."""
+    M, (B, H) = len(feats), feats[0].shape
+    agg = torch.stack([f.contiguous() for f in feats], dim=0).contiguous()        # [M][B][H]
+    gw = torch.stack([w.reshape(-1) for w in gate_w], dim=0).contiguous()          # [M][H]
+    gb = torch.cat([b.reshape(-1) for b in gate_b]).contiguous()                   # [M]
+    out = torch.empty(B, M, dtype=torch.float32, device=agg.device)
+    N.check(N.lib().msf_adaptive_weights(_p(agg), _p(gw), _p(gb), _p(mask.contiguous()), B, M, H, _p(out),
+                                         _stream()))
+    return out
+
+
+def dropout_mask(seed: int, offset: int, site: int, sub: int, rows: int, cols: int, p: float,
+                 device=None) -> torch.Tensor:
+    """The multipliers the kernels draw for one dropout site (for oracle injection)."""
+    dev = device or require_cuda("dropout_mask")
+    out = torch.empty(rows, cols, dtype=torch.float32, device=dev)
+    N.check(N.lib().msf_dropout_mask(seed & (2**64 - 1), offset & (2**64 - 1), site, sub, rows, cols,
+                                     float(p), _p(out), _stream()))
+    return out
+
+
+# ---------------------------------------------------------------------------
+# nn.Linear on the fp32 FFMA path (stand-alone attention / encoder projections)
+# ---------------------------------------------------------------------------
+class LinearFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu: bool):
+        lead = x.shape[:-1]
+        x2 = x.reshape(-1, x.shape[-1]).to(torch.float32).contiguous()
+        w = weight.to(torch.float32).contiguous()
+        b = None if bias is None else bias.to(torch.float32).contiguous()
+        y = torch.empty(x2.shape[0], w.shape[0], dtype=torch.float32, device=x2.device)
+        N.check(N.lib().msf_linear_forward(_p(x2), _p(w), _p(b), _p(y), x2.shape[0], w.shape[1],
+                                           w.shape[0], int(relu), _stream()))
+        ctx.save_for_backward(x2, w, y if relu else None)
+        ctx.relu, ctx.has_bias, ctx.in_shape = relu, bias is not None, x.shape
+        return y.reshape(*lead, w.shape[0])
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, w, y = ctx.saved_tensors
+        g = gy.reshape(-1, w.shape[0]).to(torch.float32).contiguous()
+        dx = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w)
+        db = torch.empty(w.shape[0], dtype=torch.float32, device=w.device) if ctx.has_bias else None
+        scratch = torch.empty_like(g) if ctx.relu else None
+        N.check(N.lib().msf_linear_backward(_p(x2), _p(w), _p(y), _p(g), _p(scratch), _p(dx), _p(dw),
+                                            _p(db), x2.shape[0], w.shape[1], w.shape[0], int(ctx.relu),
+                                            _stream()))
+        return (None if dx is None else dx.reshape(ctx.in_shape)), dw, db, None
+
+
+def linear(x, weight, bias=None, relu: bool = False):
+    return LinearFunction.apply(x, weight, bias, relu)
+
+
+class AttentionCoreFunction(torch.autograd.Function):
+    """Scores -> key mask -> softmax -> NaN->0 -> dropout -> weights . V
+    (src/attention.py:108-139) for projected q (B,Lq,H), k/v (B,Lk,H)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, mask, heads: int, p: float, training: bool, seed: int):
+        q, k, v = (t.to(torch.float32).contiguous() for t in (q, k, v))
+        B, Lq, H = q.shape
+        Lk = k.shape[1]
+        if mask is not None:
+            mask = mask.detach().to(device=q.device, dtype=torch.float32).expand(B, Lk).contiguous()
+        weights = torch.empty(B, heads, Lq, Lk, dtype=torch.float32, device=q.device)
+        out = torch.empty(B, Lq, H, dtype=torch.float32, device=q.device)
+        N.check(N.lib().msf_attention_core_forward(_p(q), _p(k), _p(v), _p(mask), B, Lq, Lk, H, heads,
+                                                   float(p), int(training), seed, 0, _p(weights), _p(out),
+                                                   _stream()))
+        ctx.save_for_backward(q, k, v, mask, weights)
+        ctx.cfg = (heads, float(p), int(training), seed)
+        ctx.mark_non_differentiable(weights)
+        return out, weights
+
+    @staticmethod
+    def backward(ctx, gout, _gw):
+        q, k, v, mask, weights = ctx.saved_tensors
+        heads, p, training, seed = ctx.cfg
+        B, Lq, H = q.shape
+        Lk = k.shape[1]
+        g = gout.to(torch.float32).contiguous()
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        scratch = torch.empty_like(weights)
+        N.check(N.lib().msf_attention_core_backward(_p(q), _p(k), _p(v), _p(mask), B, Lq, Lk, H, heads, p,
+                                                    training, seed, 0, _p(weights), _p(g), _p(scratch),
+                                                    _p(dq), _p(dk), _p(dv), _stream()))
+        return dq, dk, dv, None, None, None, None, None
+
+
+def attention_core(q, k, v, mask, heads: int, p: float = 0.0, training: bool = False, seed: int = 0):
+    return AttentionCoreFunction.apply(q, k, v, mask, heads, p, training, seed)
+
+
+# ---------------------------------------------------------------------------
+# loss / confidence / calibration binning / optimizer
+# ---------------------------------------------------------------------------
+def cross_entropy(logits: torch.Tensor, labels: torch.Tensor, smoothing: float = 0.0,
+                  grad_scale: Optional[float] = None):
+    """Mean CE with label smoothing and its gradient w.r.t. logits
+    (src/train.py:185-186,310).  Returns ``(loss[1], grad_logits)``."""
+    B, C = logits.shape
+    logits = logits.to(torch.float32).contiguous()
+    labels = labels.to(torch.int64).contiguous()
+    row = torch.empty(B, dtype=torch.float32, device=logits.device)
+    loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+    grad = torch.empty_like(logits)
+    scale = (1.0 / B) if grad_scale is None else grad_scale
+    N.check(N.lib().msf_cross_entropy(_p(logits), _p(labels), B, C, float(smoothing), float(scale),
+                                      _p(row), _p(loss), _p(grad), _stream()))
+    return loss, grad
+
+
+def softmax_conf_pred(logits: torch.Tensor):
+    """``conf, pred = max(softmax(logits, 1), 1)`` (src/eval.py:89-90)."""
+    B, C = logits.shape
+    logits = logits.to(torch.float32).contiguous()
+    conf = torch.empty(B, dtype=torch.float32, device=logits.device)
+    pred = torch.empty(B, dtype=torch.int64, device=logits.device)
+    N.check(N.lib().msf_softmax_conf_pred(_p(logits), B, C, _p(conf), _p(pred), _stream()))
+    return conf, pred
+
+
+def ece_bin(conf: torch.Tensor, pred: torch.Tensor, label: torch.Tensor, edges: Sequence[float],
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Single-pass binning (src/uncertainty.py:113-126,231-241).  Returns an
+    int64 tensor ``(3, num_bins)`` on the device: counts, correct, and the
+    Q32 fixed-point confidence sums; accumulates into ``out`` when given."""
+    nb = len(edges) - 1
+    dev = conf.device
+    conf = conf.detach().to(torch.float32).contiguous()
+    pred = pred.detach().to(torch.int64).contiguous()
+    label = label.detach().to(torch.int64).contiguous()
+    if out is None:
+        out = torch.zeros(3, nb, dtype=torch.int64, device=dev)
+    e = (ctypes.c_double * (nb + 1))(*[float(v) for v in edges])
+    N.check(N.lib().msf_ece_bin(_p(conf), _p(pred), _p(label), conf.numel(), e, nb, _p(out[0]),
+                                _p(out[1]), _p(out[2]), _stream()))
+    return out
+
+
+def grad_sq_norm(grad: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if out is None:
+        out = torch.zeros(1, dtype=torch.float64, device=grad.device)
+    N.check(N.lib().msf_grad_sq_norm(_p(grad), grad.numel(), _p(out), _stream()))
+    return out
+
+
+def adamw_step(params, grad, exp_avg, exp_avg_sq, step: int, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8,
+               weight_decay=1e-4, grad_scale=1.0, max_norm=0.0, sq_norm: Optional[torch.Tensor] = None):
+    """AdamW over flat fp32 arenas with optional global-norm clip
+    (src/train.py:378-382,416-430)."""
+    N.check(N.lib().msf_adamw_step(_p(params), _p(grad), _p(exp_avg), _p(exp_avg_sq), params.numel(),
+                                   int(step), lr, beta1, beta2, eps, weight_decay, grad_scale, max_norm,
+                                   _p(sq_norm), _stream()))

@@ -1,0 +1,275 @@
+"""Fusion heads — drop-in for the reference's ``src/fusion.py``.
+
+Same classes, constructor signatures, parameter names and registration order
+as the reference (so ``load_state_dict`` and same-seed construction both line
+up), but ``HybridFusion.forward`` does not run PyTorch ops: it hands raw device
+pointers to the sm_100a kernels in ``libmsf_b200.so`` through the C ABI of
+``include/msf_b200.h`` and is differentiable through
+``ops.HybridFusionFunction``.
+
+Reference mapping (paths relative to the reference repo):
+  HybridFusion.__init__/forward      src/fusion.py:267-427
+  compute_adaptive_weights           src/fusion.py:429-479
+  build_fusion_model                 src/fusion.py:485-515
+  EarlyFusion / LateFusion           src/fusion.py:17-245  (outside the hot path: plain PyTorch)
+
+Device policy: there is no CPU implementation.  CUDA inputs run in place; CPU
+inputs (the reference's unit tests) are staged through the current CUDA device
+and the results copied back; with no CUDA device the call raises.
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+from typing import Any, Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from attention import CrossModalAttention
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
+_pkg = importlib.import_module(os.path.basename(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+ops = importlib.import_module(_pkg.__name__ + ".ops")
+
+
+def _default_precision() -> str:
+    return os.environ.get("MSF_PRECISION", "fp32")
+
+
+def _mlp(in_dim: int, hidden: int, out_dim: int, p: float, depth: int) -> nn.Sequential:
+    layers: List[nn.Module] = []
+    d = in_dim
+    for _ in range(depth):
+        layers += [nn.Linear(d, hidden), nn.ReLU(), nn.Dropout(p)]
+        d = hidden
+    layers.append(nn.Linear(d, out_dim))
+    return nn.Sequential(*layers)
+
+
+def _resolve_mask(mask, batch, count, like):
+    if mask is None:
+        return torch.ones(batch, count, device=like.device, dtype=like.dtype)
+    return mask.to(device=like.device, dtype=like.dtype)
+
+
+class EarlyFusion(nn.Module):
+    """Concatenate (masked) modality features, then one MLP (fusion.py:17-123).
+    Not on the accelerated path; kept for interface parity."""
+
+    def __init__(self, modality_dims: Dict[str, int], hidden_dim: int = 256, num_classes: int = 11,
+                 dropout: float = 0.1):
+        super().__init__()
+        self.modality_dims = dict(modality_dims)
+        self.modality_names = list(self.modality_dims)
+        self.num_classes, self.hidden_dim = num_classes, hidden_dim
+        width = sum(self.modality_dims.values())
+        self.fusion = nn.Identity() if width == 0 else _mlp(width, hidden_dim, num_classes, dropout, 2)
+
+    def forward(self, modality_features, modality_mask=None):
+        if not self.modality_names:
+            raise ValueError("No modalities configured for EarlyFusion.")
+        first = modality_features[self.modality_names[0]]
+        mask = _resolve_mask(modality_mask, first.size(0), len(self.modality_names), first)
+        parts = []
+        for i, name in enumerate(self.modality_names):
+            if name not in modality_features:
+                raise KeyError(f"Missing features for modality '{name}' in EarlyFusion forward pass.")
+            x = modality_features[name]
+            if x.dim() != 2:
+                raise ValueError(f"Expected 2D tensor for modality '{name}', got shape {x.shape}.")
+            parts.append(x.to(first.device) * mask[:, i:i + 1])
+        return self.fusion(torch.cat(parts, dim=1))
+
+
+class LateFusion(nn.Module):
+    """Per-modality classifiers combined by learned softmax weights
+    (fusion.py:126-245).  Not on the accelerated path."""
+
+    def __init__(self, modality_dims: Dict[str, int], hidden_dim: int = 256, num_classes: int = 11,
+                 dropout: float = 0.1):
+        super().__init__()
+        self.modality_dims = dict(modality_dims)
+        self.modality_names = list(self.modality_dims)
+        self.num_modalities = len(self.modality_names)
+        self.classifiers = nn.ModuleDict(
+            {m: _mlp(d, hidden_dim, num_classes, dropout, 1) for m, d in self.modality_dims.items()})
+        self.weight_logits = nn.Parameter(torch.zeros(self.num_modalities))
+        self.dropout = nn.Dropout(dropout)
+
+    def forward(self, modality_features, modality_mask=None):
+        if not self.modality_names:
+            raise ValueError("No modalities configured for LateFusion.")
+        first = modality_features[self.modality_names[0]]
+        mask = _resolve_mask(modality_mask, first.size(0), self.num_modalities, first)
+        per_modality: Dict[str, torch.Tensor] = {}
+        for i, name in enumerate(self.modality_names):
+            if name not in modality_features:
+                raise KeyError(f"Missing features for modality '{name}' in LateFusion forward pass.")
+            x = modality_features[name].to(first.device) * mask[:, i:i + 1]
+            per_modality[name] = self.classifiers[name](self.dropout(x))
+        stacked = torch.stack([per_modality[m] for m in self.modality_names], dim=1)
+        w = torch.softmax(self.weight_logits, dim=0).to(first.device).unsqueeze(0) * mask
+        total = w.sum(dim=1, keepdim=True)
+        w = torch.where(total > 0, w / (total + 1e-8), torch.full_like(w, 1.0 / self.num_modalities))
+        return (stacked * w.unsqueeze(-1)).sum(dim=1), per_modality
+
+
+class HybridFusion(nn.Module):
+    """Cross-modal attention + learned modality weighting, on sm_100a kernels.
+
+    ``precision``: ``"fp32"`` (default; FFMA kernels, <= 1e-5 of the reference)
+    or ``"bf16"`` (tcgen05 tensor cores, <= 1e-2); also settable through the
+    ``MSF_PRECISION`` environment variable.
+    """
+
+    def __init__(self, modality_dims: Dict[str, int], hidden_dim: int = 256, num_classes: int = 11,
+                 num_heads: int = 4, dropout: float = 0.1):
+        super().__init__()
+        dims = dict(modality_dims)
+        self.modality_names: List[str] = list(dims)
+        self.num_modalities: int = len(self.modality_names)
+        self.hidden_dim: int = hidden_dim
+        self.precision: str = _default_precision()
+
+        # registration order = reference order (fusion.py:291-329): checkpoint keys and
+        # same-seed initialisation depend on it
+        self.projections = nn.ModuleDict(
+            {m: nn.Sequential(nn.Linear(d, hidden_dim), nn.ReLU(), nn.Dropout(dropout)) for m, d in dims.items()})
+        self.attention_modules = nn.ModuleDict({
+            f"{q}_to_{k}": CrossModalAttention(hidden_dim, hidden_dim, hidden_dim=hidden_dim,
+                                               num_heads=num_heads, dropout=dropout)
+            for q in self.modality_names for k in self.modality_names if q != k})
+        self.gating_layers = nn.ModuleDict({m: nn.Linear(hidden_dim, 1) for m in self.modality_names})
+        self.classifier = nn.Sequential(nn.Linear(hidden_dim, hidden_dim), nn.ReLU(), nn.Dropout(dropout),
+                                        nn.Linear(hidden_dim, num_classes))
+        self.dropout = nn.Dropout(dropout)
+
+    # -- structure -> kernel plan ------------------------------------------------
+    def _plan(self):
+        names = self.modality_names
+        present, heads = [], None
+        for qi, q in enumerate(names):
+            for ki, k in enumerate(names):
+                key = f"{q}_to_{k}"
+                if q != k and key in self.attention_modules:  # deleted pairs are skipped (fusion.py:388-389)
+                    present.append((qi, ki))
+                    heads = self.attention_modules[key].num_heads
+        try:
+            dims = [self.projections[m][0].in_features for m in names]
+            classes = self.classifier[3].out_features
+        except (AttributeError, IndexError, KeyError, TypeError) as exc:
+            raise RuntimeError(
+                "HybridFusion sub-modules were replaced by non-canonical modules; the fused sm_100a "
+                "path needs projections[m] = Sequential(Linear, ReLU, Dropout) and the stock classifier"
+            ) from exc
+        return ops.get_plan(names, dims, self.hidden_dim, heads or 1, classes, present)
+
+    def _slot_tensors(self, plan, device) -> List[torch.Tensor]:
+        own = dict(self.named_parameters())
+        out = []
+        for key, _, shape in plan.slots:
+            p = own[key]
+            if tuple(p.shape) != tuple(shape):
+                raise RuntimeError(f"parameter {key} has shape {tuple(p.shape)}, expected {tuple(shape)}")
+            out.append(p.to(device=device, dtype=torch.float32))
+        return out
+
+    # -- forward -------------------------------------------------------------------
+    def forward(self, modality_features: Dict[str, torch.Tensor], modality_mask: Optional[torch.Tensor] = None,
+                return_attention: bool = False):
+        """``logits`` or ``(logits, {"attention_maps", "fusion_weights"})``."""
+        if not self.modality_names:
+            raise ValueError("No modalities configured for HybridFusion.")
+        names = self.modality_names
+        for name in names:
+            if name not in modality_features:
+                raise KeyError(f"Missing features for modality '{name}' in HybridFusion forward pass.")
+        first = modality_features[names[0]]
+        home, out_dtype, batch = first.device, first.dtype, first.size(0)
+        dev = home if home.type == "cuda" else ops.require_cuda("HybridFusion.forward")
+
+        plan = self._plan()
+        xs = [modality_features[m].to(device=dev, dtype=torch.float32) for m in names]
+        mask = None
+        if modality_mask is not None:
+            mask = modality_mask.detach().to(device=dev, dtype=torch.float32).contiguous()
+        p = float(self.dropout.p)
+        training = bool(self.training and p > 0.0)
+        cfg = {
+            "precision": ops.PRECISIONS[self.precision],
+            "training": training,
+            "p": p,
+            # drawn from torch's CPU generator so torch.manual_seed() controls the masks
+            "seed": int(torch.randint(0, 2**62, (1,)).item()) if training else 0,
+            "offset": 0,
+        }
+        with torch.cuda.device(dev):
+            logits, fusion_w, gates = ops.HybridFusionFunction.apply(
+                plan, cfg, mask, *xs, *self._slot_tensors(plan, dev))
+        logits = logits.to(device=home, dtype=out_dtype)
+        if not return_attention:
+            return logits
+        maps: Dict[str, torch.Tensor] = {}
+        for pi, (qi, ki) in enumerate((q, k) for q in range(plan.M) for k in range(plan.M) if q != k):
+            if (qi, ki) in plan.present:  # (B, heads) -> (B, heads, 1, 1) like attention.py:86
+                maps[f"{names[qi]}_to_{names[ki]}"] = gates[pi].reshape(batch, plan.heads, 1, 1).to(
+                    device=home, dtype=out_dtype)
+        return logits, {"attention_maps": maps, "fusion_weights": fusion_w.to(device=home, dtype=out_dtype)}
+
+    def compute_adaptive_weights(self, modality_features: Dict[str, torch.Tensor],
+                                 modality_mask: torch.Tensor) -> torch.Tensor:
+        """Masked-softmax modality weights with the reference's fallbacks
+        (fusion.py:429-479): the same kernel stage ``forward`` uses."""
+        if modality_mask is None:
+            raise ValueError("modality_mask must be provided for adaptive weighting.")
+        for name in self.modality_names:
+            if name not in modality_features:
+                raise KeyError(f"Missing aggregated features for modality '{name}'.")
+        home = modality_mask.device
+        dev = home if home.type == "cuda" else ops.require_cuda("compute_adaptive_weights")
+        feats = [modality_features[m] for m in self.modality_names]
+        with torch.cuda.device(dev):
+            w = ops.adaptive_weights(
+                [f.detach().to(device=dev, dtype=torch.float32) for f in feats],
+                [self.gating_layers[m].weight.detach().to(device=dev, dtype=torch.float32)
+                 for m in self.modality_names],
+                [self.gating_layers[m].bias.detach().to(device=dev, dtype=torch.float32)
+                 for m in self.modality_names],
+                modality_mask.detach().to(device=dev, dtype=torch.float32))
+        return w.to(device=home, dtype=feats[0].dtype)
+
+
+_FUSION_TYPES = {"early": EarlyFusion, "late": LateFusion, "hybrid": HybridFusion}
+
+
+def build_fusion_model(fusion_type: str, modality_dims: Dict[str, int], num_classes: int, **kwargs) -> nn.Module:
+    """Factory used by ``train.MultimodalFusionModule`` (fusion.py:485-515)."""
+    cls = _FUSION_TYPES.get(fusion_type)
+    if cls is None:
+        raise ValueError(f"Unknown fusion type: {fusion_type}")
+    if cls is not HybridFusion:
+        kwargs = {k: v for k, v in kwargs.items() if k != "num_heads"}
+    return cls(modality_dims=modality_dims, num_classes=num_classes, **kwargs)
+
+
+if __name__ == "__main__":
+    print("Testing fusion architectures...")
+    demo_dims = {"video": 512, "imu": 64}
+    demo = {name: torch.randn(4, d) for name, d in demo_dims.items()}
+    availability = torch.tensor([[1, 1], [1, 0], [0, 1], [1, 1]])
+    for kind in ("early", "late", "hybrid"):
+        print(f"\nTesting {kind} fusion...")
+        try:
+            net = build_fusion_model(kind, demo_dims, 11)
+            result = net(demo, availability)
+            scores = result[0] if isinstance(result, tuple) else result
+            assert scores.shape == (4, 11), f"Expected shape (4, 11), got {scores.shape}"
+            print(f"✓ {kind} fusion working! Output shape: {scores.shape}")
+        except NotImplementedError:
+            print(f"✗ {kind} fusion not implemented yet")
+        except Exception as err:  # noqa: BLE001 - demo block reports and continues
+            print(f"✗ {kind} fusion error: {err}")

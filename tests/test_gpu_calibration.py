@@ -1,0 +1,141 @@
+"""ECE / reliability binning, CE loss, conf/pred and optimizer kernels against
+the oracle and the reference's golden vectors.  Bin counts are bit-exact."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import Golden, dropin_src, load_pkg
+from oracle import ece_oracle, fusion_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    return importlib.import_module(load_pkg().__name__ + ".ops")
+
+
+def _unpack(stats):
+    h = stats.cpu().numpy()
+    return h[0], h[1], h[2].astype(np.uint64).astype(np.float64) / 2.0 ** 32
+
+
+@pytest.mark.parametrize("nb", [15, 10, 2])
+def test_bins_bit_exact_vs_reference_golden(nb):
+    ops = _ops()
+    g = Golden("ece_seeded.npz")
+    conf = g.t("conf").cuda()
+    pred, label = g.t("pred").long().cuda(), g.t("label").long().cuda()
+    cnt, cor, cs = _unpack(ops.ece_bin(conf, pred, label, g[f"edges_f32/{nb}"].astype(np.float64).tolist()))
+    assert np.array_equal(cnt, g[f"count_f32/{nb}"])
+    assert np.array_equal(cor, g[f"correct_f32/{nb}"])
+    assert np.allclose(cs, g[f"confsum_f32/{nb}"], rtol=1e-6)
+    cnt64, _, _ = _unpack(ops.ece_bin(conf, pred, label, np.linspace(0.0, 1.0, nb + 1).tolist()))
+    assert np.array_equal(cnt64, g[f"count_f64/{nb}"])
+    # unaligned views exercise the scalar path
+    c2, k2, s2 = _unpack(ops.ece_bin(conf[1:], pred[1:], label[1:], g[f"edges_f32/{nb}"].astype(np.float64).tolist()))
+    r = ece_oracle.bin_masks(g["conf"][1:], g["pred"][1:], g["label"][1:], g[f"edges_f32/{nb}"])
+    assert np.array_equal(c2, r[0]) and np.array_equal(k2, r[1])
+
+
+@pytest.mark.parametrize("nb", [15, 10, 2])
+def test_dropin_metrics_match_reference_floats(nb):
+    import sys
+    sys.path.insert(0, dropin_src())
+    import uncertainty
+    g = Golden("ece_seeded.npz")
+    conf, pred, label = g.t("conf"), g.t("pred").long(), g.t("label").long()
+    CM = uncertainty.CalibrationMetrics
+    for tensors in ((conf, pred, label), (conf.cuda(), pred.cuda(), label.cuda())):
+        ece = CM.expected_calibration_error(*tensors, num_bins=nb)
+        mce = CM.maximum_calibration_error(*tensors, num_bins=nb)
+        assert isinstance(ece, float) and abs(ece - float(g[f"ece/{nb}"])) <= 1e-6
+        assert abs(mce - float(g[f"mce/{nb}"])) <= 1e-6
+    counts, avg, acc, _ = CM.reliability_bins(conf.numpy(), pred.numpy(), label.numpy(), nb)
+    rc, ra, rk = ece_oracle.reliability_bins(conf.numpy(), pred.numpy(), label.numpy(), nb)
+    assert np.array_equal(counts, rc) and np.allclose(avg, ra, atol=1e-6) and np.allclose(acc, rk, atol=1e-7)
+
+
+def test_survey_kats():
+    import sys
+    sys.path.insert(0, dropin_src())
+    import uncertainty
+    CM = uncertainty.CalibrationMetrics
+    assert CM.expected_calibration_error(torch.tensor([0.8, 0.7]), torch.tensor([0, 1]), torch.tensor([0, 1]), 2) == 0.25
+    assert CM.maximum_calibration_error(torch.tensor([0.8, 0.7]), torch.tensor([0, 1]), torch.tensor([0, 1]), 2) == 0.25
+    g = Golden("ece_kat.npz")
+    gen = torch.Generator().manual_seed(1234)
+    logits = torch.randn(100000, 25, generator=gen) * 2
+    labels = torch.randint(0, 25, (100000,), generator=gen)
+    conf, pred = _ops().softmax_conf_pred(logits.cuda())
+    ref_conf, ref_pred = fusion_oracle.softmax_conf_pred(logits)
+    assert torch.equal(pred.cpu(), ref_pred)  # argmax bit-exact on identical logits (first-max rule)
+    assert float((conf.cpu() - ref_conf).abs().max()) <= 1e-6
+    ece = CM.expected_calibration_error(ref_conf, ref_pred, labels, 15)
+    assert abs(ece - float(g["ece15_seed1234"])) <= 1e-6
+    nll = CM.negative_log_likelihood(logits, labels)
+    assert abs(nll - float(torch.nn.functional.cross_entropy(logits, labels))) <= 1e-5
+
+
+def test_full_size_properties_and_shard_merge():
+    """N = 2^24 samples (320 MB of inputs, > L2): totals, shard-merge exactness, C oracle."""
+    ops = _ops()
+    n = 1 << 24
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    conf = torch.rand(n, device="cuda", generator=gen)
+    conf[::1000] = float("nan")
+    conf[1::1000] = 1.0
+    conf[2::1000] = 0.0
+    conf[3::1000] = 1.5
+    pred = torch.randint(0, 25, (n,), device="cuda", generator=gen)
+    label = torch.randint(0, 25, (n,), device="cuda", generator=gen)
+    edges = ece_oracle.linspace_f32(15).astype(np.float64).tolist()
+    whole = ops.ece_bin(conf, pred, label, edges)
+    in_range = int(((conf >= 0) & (conf <= 1)).sum())
+    assert int(whole[0].sum()) == in_range  # NaN / out-of-range land in no bin
+    cut = 5_000_003
+    parts = ops.ece_bin(conf[:cut], pred[:cut], label[:cut], edges)
+    parts = ops.ece_bin(conf[cut:], pred[cut:], label[cut:], edges, out=parts)
+    assert torch.equal(parts, whole)  # integer accumulation: shards merge bit-exactly (incl. Q32 sums)
+    assert torch.equal(ops.ece_bin(conf, pred, label, edges), whole)  # run-to-run deterministic
+    m = 1 << 22
+    cnt, cor, cs = ece_oracle.bin_masks_c(conf[:m].cpu().numpy(), pred[:m].cpu().numpy(),
+                                          label[:m].cpu().numpy(), np.array(edges), threads=8)
+    got = ops.ece_bin(conf[:m], pred[:m], label[:m], edges).cpu().numpy()
+    assert np.array_equal(got[0], cnt) and np.array_equal(got[1], cor)
+    assert np.allclose(got[2].astype(np.uint64).astype(np.float64) / 2.0 ** 32, cs, rtol=1e-7)
+
+
+def test_empty_and_tiny_inputs():
+    ops = _ops()
+    edges = ece_oracle.linspace_f32(15).astype(np.float64).tolist()
+    e = torch.empty(0, device="cuda")
+    z = torch.empty(0, dtype=torch.long, device="cuda")
+    assert int(ops.ece_bin(e, z, z, edges).abs().sum()) == 0
+    one = ops.ece_bin(torch.tensor([1.0], device="cuda"), torch.tensor([3], device="cuda"),
+                      torch.tensor([3], device="cuda"), edges).cpu()
+    assert one[0].tolist() == [0] * 14 + [1] and one[1].tolist() == [0] * 14 + [1]
+    assert int(one[2][14]) == 2 ** 32
+
+
+def test_cross_entropy_and_optimizer_match_oracle():
+    ops = _ops()
+    g = Golden("fusion_pamap_small.npz")
+    logits = g.t("train/logits").cuda()
+    labels = g.t("labels").cuda()
+    loss, grad = ops.cross_entropy(logits, labels, 0.05)
+    ref = g.t("train/logits").clone().requires_grad_(True)
+    ref_loss = fusion_oracle.cross_entropy_label_smoothing(ref, g.t("labels"), 0.05)
+    ref_loss.backward()
+    assert abs(float(loss) - float(ref_loss)) <= 1e-6
+    assert float((grad.cpu() - ref.grad).abs().max()) <= 1e-7
+    # AdamW + clip on the flat arena vs torch.optim.AdamW / clip_grad_norm_ (golden "opt/*")
+    keys = list(g.group("sd").keys())
+    flat = lambda grp: torch.cat([g.t(f"{grp}/{k}").flatten() for k in keys]).cuda()
+    p, gr = flat("sd"), flat("grad")
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    sq = ops.grad_sq_norm(gr)
+    assert abs(float(sq.sqrt()) - float(g["opt/grad_norm"])) <= 1e-5
+    ops.adamw_step(p, gr, m, v, step=1, lr=1e-3, weight_decay=1e-4, max_norm=1.0, sq_norm=sq)
+    assert float((p.cpu() - flat("opt").cpu()).abs().max()) <= 1e-6
