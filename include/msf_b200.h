@@ -204,12 +204,16 @@ int msf_attention_core_backward(const float* q, const float* k, const float* v, 
                                 float* dk, float* dv, void* stream);
 
 /* ---- tensor-core GEMM building block (encoder/attention projections) ------ */
-/* D[M,N] (fp32 or bf16) = A[M,K] . B[N,K]^T, bf16 operands K-major, fp32 accumulate
- * in TMEM via tcgen05.mma, operands staged by TMA.  M, N, K need not be tile
- * multiples (TMA zero-fills); K % 8 == 0 and 16-byte aligned rows required. */
-int msf_gemm_bf16_nt(const void* a_bf16, const void* b_bf16, void* d, int32_t d_is_bf16,
-                     int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb, int64_t ldd,
-                     const float* bias, int32_t relu, void* stream);
+/* bf16 operands, fp32 accumulate in TMEM via tcgen05.mma, operands staged by TMA
+ * into 128B-swizzled shared memory; D is fp32 or bf16 row-major (ldd elements).
+ *   mn_major == 0:  D[m,n] = sum_k A[m,k] * B[n,k]   A (m x k, lda), B (n x k, ldb): nn.Linear forward / dgrad
+ *   mn_major != 0:  D[m,n] = sum_k A[k,m] * B[k,n]   A (k x m, lda), B (k x n, ldb): weight gradient dY^T . X
+ * then D = D + bias[n] (bias fp32 or NULL), then max(D, 0) if relu != 0.
+ * m, n, k need not be tile multiples (TMA zero-fills out-of-range boxes); operand
+ * base pointers must be 16-byte aligned and lda, ldb multiples of 8 elements. */
+int msf_gemm_bf16(const void* a_bf16, const void* b_bf16, void* d, int32_t d_is_bf16, int64_t m, int64_t n,
+                  int64_t k, int64_t lda, int64_t ldb, int64_t ldd, int32_t mn_major, const float* bias,
+                  int32_t relu, void* stream);
 
 #ifdef __cplusplus
 }

@@ -98,8 +98,8 @@ PROTOTYPES = {
                                               c_int32, c_int32, c_int32, c_float, c_int32, c_uint64,
                                               c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                               c_void_p, c_void_p]),
-    "msf_gemm_bf16_nt": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int64,
-                                   c_int64, c_int64, c_int64, c_void_p, c_int32, c_void_p]),
+    "msf_gemm_bf16": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int64,
+                                c_int64, c_int64, c_int64, c_int32, c_void_p, c_int32, c_void_p]),
 }
 
 

@@ -12,8 +12,3 @@ int fusion_bf16_forward(const Layout&, const msf_fusion_call*, cudaStream_t) { r
 int fusion_bf16_backward(const Layout&, const msf_fusion_call*, cudaStream_t) { return MSF_E_UNSUPPORTED; }
 }  // namespace msf
 
-extern "C" int msf_gemm_bf16_nt(const void*, const void*, void*, int32_t, int64_t, int64_t, int64_t, int64_t,
-                                int64_t, int64_t, const float*, int32_t, void*) {
-  msf::set_error("msf_gemm_bf16_nt: not built yet");
-  return MSF_E_UNSUPPORTED;
-}

@@ -1,0 +1,93 @@
+// Grouped bf16 GEMM on 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM,
+// operands staged by TMA into 128B-swizzled shared memory) with the
+// HybridFusion epilogues fused in.  sm_100a only.
+//
+// One persistent launch processes a list of problems; each problem may sum up
+// to 7 K-segments (different A / B per segment) into one TMEM accumulator.
+// Operands are addressed through a small table of TMA descriptors over
+// *stacked* tensors ([z][rows][cols]); a segment names (descriptor, z).
+//
+//   MAJOR_K  (forward / dgrad):  A[M,K] and B[N,K] row-major, K contiguous
+//   MAJOR_MN (wgrad):            A = dY[Kb,M], B = X[Kb,N] row-major, contraction
+//                                 over the rows (windows), M / N contiguous
+#pragma once
+
+#include <cuda.h>
+
+#include "msf_common.cuh"
+
+namespace msf {
+
+constexpr int TC_MAX_SEG = 7;
+constexpr int TC_MAX_PROBLEMS = 24;
+constexpr int TC_MAX_MAPS = 16;
+constexpr int TC_BLOCK_M = 128;
+constexpr int TC_BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
+constexpr int TC_STAGES = 4;
+
+enum TcEpilogue {
+  TC_EPI_STORE = 0,        // v = acc*scale + bias
+  TC_EPI_BIAS_RELU_DROP,   // v = relu(acc + bias) * drop(site, sub, row, col)
+  TC_EPI_VALUE_GATE,       // v = (acc + bias) * gate(row, head); records gate
+  TC_EPI_OUT_MEAN,         // v = (acc + sum bias + aux) / scale * mask[row, mask_col]
+  TC_EPI_RELU_GRAD,        // v = acc * (aux > 0 ? scale : 0)
+  TC_EPI_GATE_MUL,         // v = acc * gate_in[row, head]
+  TC_EPI_ADD_RELU_GRAD,    // v = (acc + aux) * (aux2 > 0 ? scale : 0)
+  TC_EPI_DX                // v = acc * mask[row, mask_col] * drop(site, sub, row, col)
+};
+
+struct TcSegment {
+  short a_map, b_map;   // indices into TcLaunch::maps
+  int a_z, b_z;         // slice of the stacked tensor
+};
+
+struct TcProblem {
+  TcSegment seg[TC_MAX_SEG];
+  const float* bias[TC_MAX_SEG];  // fp32, summed
+  int nseg;
+  int M, N, K;            // output rows, output cols, contraction length per segment
+  void* C;                // row-major, ld elements
+  long long ldc;
+  int c_bf16;             // 1: bf16 output, 0: fp32 output
+  int epi;
+  float scale;
+  const __nv_bfloat16* aux;
+  long long ld_aux;
+  const __nv_bfloat16* aux2;
+  long long ld_aux2;
+  const float* mask;
+  int mask_ld, mask_col;
+  float* gate_out;
+  const float* gate_in;
+  int head_dim, heads;
+  int site, sub;
+  int tile_begin;
+};
+
+struct TcLaunch {
+  CUtensorMap maps[TC_MAX_MAPS];
+  TcProblem p[TC_MAX_PROBLEMS];
+  int count;
+  int total_tiles;
+  int block_n;            // 32..256, multiple of 16; uniform per launch
+  DropCfg drop;
+};
+
+// Host-side builder for one launch.
+struct TcBuilder {
+  TcLaunch L;
+  int nmaps;
+  bool mn_major;
+  TcBuilder(bool mn, int block_n);
+  // Stacked bf16 tensor [depth][rows][cols] (row pitch = ld elements, slice pitch = slice elements).
+  // role_rows: box height along `rows` for a K-major operand (TC_BLOCK_M for A, block_n for B);
+  // ignored for MN-major operands (box = 64 x 64).
+  int add_map(const void* base, long long rows, long long cols, long long ld, long long depth,
+              long long slice, int role_rows);
+  int add_problem(const TcProblem& p);
+  int launch(const DropCfg& drop, cudaStream_t stream);
+};
+
+int tc_init();  // resolves cuTensorMapEncodeTiled; MSF_OK or error
+
+}  // namespace msf

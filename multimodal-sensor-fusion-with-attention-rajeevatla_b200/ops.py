@@ -410,3 +410,22 @@ def adamw_step(params, grad, exp_avg, exp_avg_sq, step: int, lr=1e-3, beta1=0.9,
     N.check(N.lib().msf_adamw_step(_p(params), _p(grad), _p(exp_avg), _p(exp_avg_sq), params.numel(),
                                    int(step), lr, beta1, beta2, eps, weight_decay, grad_scale, max_norm,
                                    _p(sq_norm), _stream()))
+
+
+def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, mn_major: bool = False, bias: Optional[torch.Tensor] = None,
+              relu: bool = False, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """tcgen05 GEMM building block.  ``mn_major=False``: ``a (m,k) @ b (n,k).T`` (nn.Linear forward /
+    dgrad); ``mn_major=True``: ``a (k,m).T @ b (k,n)`` (weight gradient).  bf16 operands, fp32 accumulate."""
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.dim() == 2 and b.dim() == 2
+    assert a.stride(1) == 1 and b.stride(1) == 1
+    if mn_major:
+        (k, m), (k2, n) = a.shape, b.shape
+    else:
+        (m, k), (n, k2) = a.shape, b.shape
+    assert k == k2, "contraction lengths differ"
+    d = torch.empty(m, n, dtype=out_dtype, device=a.device)
+    if bias is not None:
+        bias = bias.to(torch.float32).contiguous()
+    N.check(N.lib().msf_gemm_bf16(_p(a), _p(b), _p(d), int(out_dtype == torch.bfloat16), m, n, k, a.stride(0),
+                                  b.stride(0), d.stride(0), int(mn_major), _p(bias), int(relu), _stream()))
+    return d
