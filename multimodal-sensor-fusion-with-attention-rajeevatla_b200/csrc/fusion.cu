@@ -27,8 +27,7 @@ static int check_call(const Layout& L, const msf_fusion_call* c, bool backward) 
   if (c->precision == MSF_PREC_BF16) {
     MSF_REQUIRE(c->params_bf16 != nullptr, "BF16 precision needs params_bf16 (msf_fusion_pack_bf16)");
     if (!fusion_bf16_eligible(L)) {
-      set_error("shape not eligible for the tensor-core path (needs hidden %% 64 == 0, hidden <= 256, "
-                "every in_dim %% 16 == 0)");
+      set_error("shape not eligible for the tensor-core path (needs hidden %% 64 == 0 and every in_dim %% 8 == 0)");
       return MSF_E_UNSUPPORTED;
     }
   }

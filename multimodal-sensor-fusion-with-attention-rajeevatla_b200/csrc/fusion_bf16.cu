@@ -1,14 +1,885 @@
 // HybridFusion forward / backward on the tensor-core path (MSF_PREC_BF16).
-// Placeholder until the tcgen05 pipeline lands: reports the shape as ineligible
-// so callers get MSF_E_UNSUPPORTED rather than a silent fallback.
-#include "msf_common.cuh"
+//
+// Same stage structure as the fp32 path (fusion_f32.cu; src/fusion.py:331-479,
+// src/attention.py:68-146) with bf16 activations / weights, fp32 accumulation in
+// TMEM (tcgen05.mma) and every elementwise step fused into a GEMM epilogue:
+//
+//   F0 prep      xt_m  = bf16(drop0(x_m * mask_m))                          [elementwise]
+//   F1 proj      P_m   = drop1(relu(xt_m Wp_m^T + bp_m))                    tc_gemm, 1 launch, M problems
+//   F2 value     U_qk  = g_qk * (P_k Wv_qk^T + bv_qk)      (records g)      tc_gemm, 1 launch, M(M-1) problems
+//   F3 out+mean  agg_q = (P_q + sum_k (U_qk Wo_qk^T + bo_qk)) / cnt_q * mask_q   tc_gemm, K-segments summed in TMEM
+//   F4 tail      gating dot, masked softmax + fallbacks, weighted sum        [warp per window]
+//   F5 cls1      Hr = drop3(relu(fused W1^T + b1));  F6 logits = Hr W2^T + b2
+//
+// Backward: dgrad GEMMs are K-major launches against transposed bf16 weight
+// copies kept in the compute arena; all weight gradients (dY^T . X, contraction
+// over the windows) go into ONE MN-major launch at the end; bias gradients are
+// column sums.  Dead query/key projection slots are exact zeros (memset).
+#include "fusion_common.cuh"
+#include "tc_gemm.cuh"
 
 namespace msf {
-bool fusion_bf16_eligible(const Layout&) { return false; }
-size_t fusion_bf16_workspace_bytes(const Layout&, int64_t) { return 0; }
-size_t fusion_bf16_arena_bytes(const Layout&) { return 0; }
-int fusion_bf16_pack(const Layout&, const float*, void*, cudaStream_t) { return MSF_E_UNSUPPORTED; }
-int fusion_bf16_forward(const Layout&, const msf_fusion_call*, cudaStream_t) { return MSF_E_UNSUPPORTED; }
-int fusion_bf16_backward(const Layout&, const msf_fusion_call*, cudaStream_t) { return MSF_E_UNSUPPORTED; }
-}  // namespace msf
 
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------------------
+// bf16 compute arena (element offsets) and workspace
+// ---------------------------------------------------------------------------
+struct ArenaBf16 {
+  size_t wp[MSF_MAX_MODALITIES], wpT[MSF_MAX_MODALITIES];  // [H][D_m], [D_m][H]
+  size_t wv, wo, wvT, woT;                                 // [pairs][H][H]
+  size_t w1, w1T;                                          // [H][H]
+  size_t w2;                                               // [C][H]
+  size_t w2T;                                              // [H][Cp]  (Cp = C rounded up to 8, zero padded)
+  size_t total;
+  int Cp;
+};
+
+static ArenaBf16 arena_layout(const Layout& L) {
+  ArenaBf16 a;
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    const size_t o = off;
+    off += align_up(n, 128);  // 256-byte aligned tensors (TMA needs 16)
+    return o;
+  };
+  const size_t H = L.H;
+  a.Cp = (int)align_up(L.C, 8);
+  for (int m = 0; m < L.M; ++m) a.wp[m] = take(H * L.D[m]);
+  for (int m = 0; m < L.M; ++m) a.wpT[m] = take(H * L.D[m]);
+  const size_t pairs = L.num_pairs();
+  a.wv = take(pairs * H * H);
+  a.wo = take(pairs * H * H);
+  a.wvT = take(pairs * H * H);
+  a.woT = take(pairs * H * H);
+  a.w1 = take(H * H);
+  a.w1T = take(H * H);
+  a.w2 = take((size_t)L.C * H);
+  a.w2T = take(H * a.Cp);
+  a.total = off;
+  return a;
+}
+
+struct WsBf16 {
+  bf16* xt[MSF_MAX_MODALITIES];  // [B][D_m]
+  bf16* P;       // [M][B][H]
+  bf16* U;       // [pairs][B][H]
+  float* G;      // [pairs][B][heads]
+  bf16* agg;     // [M][B][H]
+  float* soft;   // [B][M]
+  float* w;      // [B][M]
+  bf16* fused;   // [B][H]
+  bf16* Hr;      // [B][H]
+  // backward
+  bf16* dlog;    // [B][Cp]
+  bf16* dH1;     // [B][H]
+  bf16* dfused;  // [B][H]
+  float* ds;     // [B][M]  d loss / d gating score
+  bf16* dS;      // [M][B][H]
+  bf16* dV;      // [pairs][B][H]
+  bf16* dZ;      // [M][B][H]
+  size_t bytes;
+};
+
+static void carve_bf16(const Layout& L, int64_t B, void* base, WsBf16* ws) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* p = base ? reinterpret_cast<char*>(base) + off : nullptr;
+    off += align_up(bytes, 256);
+    return p;
+  };
+  const size_t BH = (size_t)B * L.H;
+  const size_t pairs = L.num_pairs() > 0 ? L.num_pairs() : 1;
+  const int Cp = (int)align_up(L.C, 8);
+  for (int m = 0; m < L.M; ++m) ws->xt[m] = (bf16*)take((size_t)B * L.D[m] * 2);
+  ws->P = (bf16*)take(BH * L.M * 2);
+  ws->U = (bf16*)take(BH * pairs * 2);
+  ws->G = (float*)take((size_t)B * L.heads * pairs * 4);
+  ws->agg = (bf16*)take(BH * L.M * 2);
+  ws->soft = (float*)take((size_t)B * L.M * 4);
+  ws->w = (float*)take((size_t)B * L.M * 4);
+  ws->fused = (bf16*)take(BH * 2);
+  ws->Hr = (bf16*)take(BH * 2);
+  ws->dlog = (bf16*)take((size_t)B * Cp * 2);
+  ws->dH1 = (bf16*)take(BH * 2);
+  ws->dfused = (bf16*)take(BH * 2);
+  ws->ds = (float*)take((size_t)B * L.M * 4);
+  ws->dS = (bf16*)take(BH * L.M * 2);
+  ws->dV = (bf16*)take(BH * pairs * 2);
+  ws->dZ = (bf16*)take(BH * L.M * 2);
+  ws->bytes = off;
+}
+
+bool fusion_bf16_eligible(const Layout& L) {
+  if (L.H % 64 != 0) return false;
+  for (int m = 0; m < L.M; ++m)
+    if (L.D[m] % 8 != 0) return false;
+  return true;
+}
+size_t fusion_bf16_workspace_bytes(const Layout& L, int64_t B) {
+  WsBf16 ws;
+  carve_bf16(L, B, nullptr, &ws);
+  return ws.bytes;
+}
+size_t fusion_bf16_arena_bytes(const Layout& L) { return arena_layout(L).total * sizeof(bf16); }
+
+static int block_n_for(int n) { return n >= 256 ? 256 : (int)align_up(n, 64); }
+
+// ---------------------------------------------------------------------------
+// pack: fp32 master -> bf16 compute arena (plain and transposed copies)
+// ---------------------------------------------------------------------------
+struct PackJob {
+  long long src, src_batch;   // element offsets in the master arena
+  long long dst, dst_batch;   // element offsets in the compute arena
+  int rows, cols;             // source matrix (rows x cols, row-major)
+  int dst_ld;                 // destination row pitch
+  int batch;
+  int transpose;              // destination holds cols x rows
+  int tile_begin;
+};
+constexpr int PACK_MAX_JOBS = 4 * MSF_MAX_MODALITIES + 8;
+struct PackList {
+  PackJob j[PACK_MAX_JOBS];
+  int count, total_tiles;
+};
+
+// one 32x32 tile per block iteration; transposes go through shared memory so both sides coalesce
+__global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ PackList list,
+                                                   const float* __restrict__ master, bf16* __restrict__ arena) {
+  __shared__ float tile[32][33];
+  for (int t = blockIdx.x; t < list.total_tiles; t += gridDim.x) {
+    int ji = 0;
+    while (ji + 1 < list.count && t >= list.j[ji + 1].tile_begin) ++ji;
+    const PackJob& J = list.j[ji];
+    const int tr = (J.rows + 31) >> 5, tc = (J.cols + 31) >> 5;
+    int local = t - J.tile_begin;
+    const int b = local / (tr * tc);
+    local -= b * tr * tc;
+    const int r0 = (local / tc) << 5, c0 = (local % tc) << 5;
+    const float* src = master + J.src + (long long)b * J.src_batch;
+    bf16* dst = arena + J.dst + (long long)b * J.dst_batch;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    if (!J.transpose) {
+      for (int i = ty; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + tx;
+        if (r < J.rows && c < J.cols) dst[(long long)r * J.dst_ld + c] = __float2bfloat16_rn(__ldg(src + (long long)r * J.cols + c));
+      }
+    } else {
+      for (int i = ty; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + tx;
+        tile[i][tx] = (r < J.rows && c < J.cols) ? __ldg(src + (long long)r * J.cols + c) : 0.0f;
+      }
+      __syncthreads();
+      for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + tx;  // destination row = source column
+        if (c < J.cols && r < J.rows) dst[(long long)c * J.dst_ld + r] = __float2bfloat16_rn(tile[tx][i]);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+int fusion_bf16_pack(const Layout& L, const float* params, void* arena_v, cudaStream_t st) {
+  const ArenaBf16 A = arena_layout(L);
+  bf16* arena = reinterpret_cast<bf16*>(arena_v);
+  PackList list;
+  memset(&list, 0, sizeof(list));
+  const long long H = L.H;
+  auto add = [&](long long src, long long sb, long long dst, long long db, int rows, int cols, int dst_ld,
+                 int batch, int transpose) {
+    if (batch <= 0) return;
+    PackJob& J = list.j[list.count++];
+    J.src = src; J.src_batch = sb; J.dst = dst; J.dst_batch = db;
+    J.rows = rows; J.cols = cols; J.dst_ld = dst_ld; J.batch = batch; J.transpose = transpose;
+    J.tile_begin = list.total_tiles;
+    list.total_tiles += batch * ((rows + 31) / 32) * ((cols + 31) / 32);
+  };
+  for (int m = 0; m < L.M; ++m) {
+    add(L.proj_w[m], 0, (long long)A.wp[m], 0, L.H, L.D[m], L.D[m], 1, 0);
+    add(L.proj_w[m], 0, (long long)A.wpT[m], 0, L.H, L.D[m], L.H, 1, 1);
+  }
+  const int pairs = L.num_pairs();
+  if (pairs > 0) {
+    add(L.pair_w(0, 2), L.pair_stride, (long long)A.wv, H * H, L.H, L.H, L.H, pairs, 0);
+    add(L.pair_w(0, 3), L.pair_stride, (long long)A.wo, H * H, L.H, L.H, L.H, pairs, 0);
+    add(L.pair_w(0, 2), L.pair_stride, (long long)A.wvT, H * H, L.H, L.H, L.H, pairs, 1);
+    add(L.pair_w(0, 3), L.pair_stride, (long long)A.woT, H * H, L.H, L.H, L.H, pairs, 1);
+  }
+  add(L.cls_w1, 0, (long long)A.w1, 0, L.H, L.H, L.H, 1, 0);
+  add(L.cls_w1, 0, (long long)A.w1T, 0, L.H, L.H, L.H, 1, 1);
+  add(L.cls_w2, 0, (long long)A.w2, 0, L.C, L.H, L.H, 1, 0);
+  // w2T is (H x Cp) with zero padding columns C..Cp-1: clear it first
+  MSF_CHECK_CUDA(cudaMemsetAsync(arena + A.w2T, 0, (size_t)L.H * A.Cp * sizeof(bf16), st));
+  add(L.cls_w2, 0, (long long)A.w2T, 0, L.C, L.H, A.Cp, 1, 1);
+  const int grid = list.total_tiles < 1184 ? list.total_tiles : 1184;
+  pack_kernel<<<grid, 256, 0, st>>>(list, params, arena);
+  MSF_LAUNCH_CHECK();
+  return MSF_OK;
+}
+
+// ---------------------------------------------------------------------------
+// small vector helpers: 8 consecutive bf16 <-> 8 floats
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
+  const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = __bfloat1622float2(h[e]);
+    v[2 * e] = f.x;
+    v[2 * e + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
+  uint4 pk;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+  *reinterpret_cast<uint4*>(p) = pk;
+}
+// 8 fp32 values from the master arena (tensors there are only 4-byte aligned)
+__device__ __forceinline__ void load8f(const float* p, float (&v)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = __ldg(p + j);
+}
+
+// ---------------------------------------------------------------------------
+// F0: xt = bf16(drop0(x * mask))           (fusion.py:370-374)
+// ---------------------------------------------------------------------------
+struct PrepArgs16 {
+  const float* x[MSF_MAX_MODALITIES];
+  bf16* xt[MSF_MAX_MODALITIES];
+  int D[MSF_MAX_MODALITIES];
+  int M;
+  long long B;
+  const float* mask;
+  DropCfg drop;
+};
+
+__global__ void __launch_bounds__(256) prep16_kernel(const __grid_constant__ PrepArgs16 a) {
+  const int m = blockIdx.y;
+  const int D = a.D[m];
+  const DropCfg drop = resolve_drop(a.drop);
+  const int quads = D >> 2;  // D % 8 == 0
+  const long long total = a.B * quads;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / quads;
+    const int c4 = (int)(i % quads);
+    const float mk = a.mask ? __ldg(a.mask + row * a.M + m) : 1.0f;
+    float dm[4] = {1.f, 1.f, 1.f, 1.f};
+    if (drop.active) drop4(drop, SITE_INPUT, m, row, c4, dm);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(a.x[m] + row * D) + c4);
+    uint2 pk;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+    h[0] = __floats2bfloat162_rn(v.x * mk * dm[0], v.y * mk * dm[1]);
+    h[1] = __floats2bfloat162_rn(v.z * mk * dm[2], v.w * mk * dm[3]);
+    *reinterpret_cast<uint2*>(a.xt[m] + row * D + c4 * 4) = pk;
+  }
+}
+
+// dlogits (B, C) fp32 -> (B, Cp) bf16, zero padded
+__global__ void __launch_bounds__(256) cvt_pad_kernel(const float* __restrict__ src, bf16* __restrict__ dst,
+                                                      long long rows, int cols, int ld) {
+  const long long total = rows * ld;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / ld;
+    const int c = (int)(i % ld);
+    dst[i] = __float2bfloat16_rn(c < cols ? __ldg(src + r * cols + c) : 0.0f);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// F4: gating, masked softmax with fallbacks, weighted sum   (fusion.py:410-418, 429-479)
+// one warp per window; each lane owns 8-column chunks
+// ---------------------------------------------------------------------------
+struct Tail16Args {
+  const bf16* agg;     // [M][B][H]
+  const float* gate_w[MSF_MAX_MODALITIES];
+  const float* gate_b[MSF_MAX_MODALITIES];
+  const float* mask;
+  float* soft;
+  float* w;
+  float* w_out;
+  bf16* fused;         // (B, H)
+  long long B;
+  int M, H;
+};
+
+__global__ void __launch_bounds__(256) tail16_fwd_kernel(const __grid_constant__ Tail16Args a) {
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= a.B) return;
+  float s[MSF_MAX_MODALITIES], mk[MSF_MAX_MODALITIES], soft[MSF_MAX_MODALITIES], w[MSF_MAX_MODALITIES];
+  for (int q = 0; q < a.M; ++q) {
+    const bf16* ag = a.agg + ((long long)q * a.B + row) * a.H;
+    float part = 0.0f;
+    for (int c = lane * 8; c < a.H; c += 256) {
+      float v[8], g[8];
+      load8(ag + c, v);
+      load8f(a.gate_w[q] + c, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) part = fmaf(v[j], g[j], part);
+    }
+    s[q] = warp_sum(part) + __ldg(a.gate_b[q]);  // fusion.py:459
+    mk[q] = a.mask ? __ldg(a.mask + row * a.M + q) : 1.0f;
+  }
+  adaptive_weights_row(s, mk, a.M, soft, w);
+  if (lane == 0)
+    for (int q = 0; q < a.M; ++q) {
+      a.soft[row * a.M + q] = soft[q];
+      a.w[row * a.M + q] = w[q];
+      if (a.w_out) a.w_out[row * a.M + q] = w[q];
+    }
+  for (int c = lane * 8; c < a.H; c += 256) {
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int q = 0; q < a.M; ++q) {
+      float v[8];
+      load8(a.agg + ((long long)q * a.B + row) * a.H + c, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaf(v[j], w[q], f[j]);
+    }
+    store8(a.fused + row * a.H + c, f);  // fusion.py:416-418
+  }
+}
+
+// ---------------------------------------------------------------------------
+// B4: backward of F4.  dfused -> dS_q (already scaled by mask_q / cnt_q) and the
+// per-window score gradients ds (B, M); gating-layer gradients are weighted
+// column sums of agg with ds, done by wcolsum16_kernel.
+// ---------------------------------------------------------------------------
+struct Tail16BwdArgs {
+  const bf16* agg;
+  const bf16* dfused;
+  const float* gate_w[MSF_MAX_MODALITIES];
+  const float* mask;
+  const float* soft;
+  const float* w;
+  bf16* dS;       // [M][B][H]
+  float* ds;      // (B, M)
+  float inv_cnt[MSF_MAX_MODALITIES];
+  long long B;
+  int M, H;
+};
+
+__global__ void __launch_bounds__(256) tail16_bwd_kernel(const __grid_constant__ Tail16BwdArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= a.B) return;
+  float mk[MSF_MAX_MODALITIES], p[MSF_MAX_MODALITIES], w[MSF_MAX_MODALITIES], dw[MSF_MAX_MODALITIES];
+  float ds[MSF_MAX_MODALITIES];
+  for (int q = 0; q < a.M; ++q) {
+    mk[q] = a.mask ? __ldg(a.mask + row * a.M + q) : 1.0f;
+    p[q] = __ldg(a.soft + row * a.M + q);
+    w[q] = __ldg(a.w + row * a.M + q);
+    const bf16* ag = a.agg + ((long long)q * a.B + row) * a.H;
+    float part = 0.0f;
+    for (int c = lane * 8; c < a.H; c += 256) {
+      float v[8], g[8];
+      load8(ag + c, v);
+      load8(a.dfused + row * a.H + c, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) part = fmaf(v[j], g[j], part);
+    }
+    dw[q] = warp_sum(part);  // d loss / d w_q
+  }
+  // w = n / (S + 1e-8), n = p * mask (only when S > 0; the fallbacks are constants)
+  float S = 0.0f;
+  for (int q = 0; q < a.M; ++q) S += p[q] * mk[q];
+  if (S > 0.0f) {
+    const float inv = 1.0f / (S + 1e-8f);
+    float dot = 0.0f;
+    for (int q = 0; q < a.M; ++q) dot += dw[q] * p[q] * mk[q];
+    float dp[MSF_MAX_MODALITIES], pdot = 0.0f;
+    for (int q = 0; q < a.M; ++q) {
+      dp[q] = (dw[q] * inv - dot * inv * inv) * mk[q];
+      pdot += dp[q] * p[q];
+    }
+    for (int q = 0; q < a.M; ++q) ds[q] = (mk[q] > 0.0f) ? p[q] * (dp[q] - pdot) : 0.0f;
+  } else {
+    for (int q = 0; q < a.M; ++q) ds[q] = 0.0f;
+  }
+  if (lane == 0)
+    for (int q = 0; q < a.M; ++q) a.ds[row * a.M + q] = ds[q];
+  for (int q = 0; q < a.M; ++q) {
+    bf16* out = a.dS + ((long long)q * a.B + row) * a.H;
+    const float sc = mk[q] * a.inv_cnt[q];
+    for (int c = lane * 8; c < a.H; c += 256) {
+      float g[8], gw[8], o[8];
+      load8(a.dfused + row * a.H + c, g);
+      load8f(a.gate_w[q] + c, gw);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(w[q], g[j], ds[q] * gw[j]) * sc;
+      store8(out + c, o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// (weighted) column sums of bf16 / fp32 matrices, accumulated with fp32 atomics
+// into pre-zeroed destinations: bias gradients and gating-layer gradients.
+//   dst[c] += sum_r coef[r*coef_ld] * src[r*ld + c]        (coef == nullptr: 1)
+// grid = (row chunks, problems); a warp covers 256 columns of one row per step.
+// ---------------------------------------------------------------------------
+struct Colsum16Problem {
+  const void* src;
+  int src_f32;         // 1: fp32 source, 0: bf16
+  long long ld;
+  int rows, cols;
+  const float* coef;
+  int coef_ld;
+  float* dst;
+};
+constexpr int COLSUM16_MAX = 48;
+struct Colsum16List {
+  Colsum16Problem p[COLSUM16_MAX];
+  int count;
+  int rows_per_block;
+};
+
+__global__ void __launch_bounds__(256) colsum16_kernel(const __grid_constant__ Colsum16List list) {
+  const Colsum16Problem& P = list.p[blockIdx.y];
+  const int r0 = blockIdx.x * list.rows_per_block;
+  if (r0 >= P.rows) return;
+  const int r1 = min(P.rows, r0 + list.rows_per_block);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ float red[8][256];
+  for (int cbase = 0; cbase < P.cols; cbase += 256) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int c = cbase + lane * 8;
+    if (c < P.cols) {
+      const bool vec = (c + 8 <= P.cols) && ((P.ld & 7) == 0);
+      for (int r = r0 + warp; r < r1; r += 8) {
+        const float k = P.coef ? __ldg(P.coef + (long long)r * P.coef_ld) : 1.0f;
+        if (k == 0.0f) continue;
+        float v[8];
+        if (P.src_f32) {
+          const float* s = reinterpret_cast<const float*>(P.src) + (long long)r * P.ld + c;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = (c + j < P.cols) ? __ldg(s + j) : 0.0f;
+        } else {
+          const bf16* s = reinterpret_cast<const bf16*>(P.src) + (long long)r * P.ld + c;
+          if (vec) {
+            load8(s, v);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = (c + j < P.cols) ? __bfloat162float(s[j]) : 0.0f;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(k, v[j], acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = acc[j];
+    __syncthreads();
+    const int col = cbase + threadIdx.x;
+    if (col < P.cols) {
+      float t = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+      if (t != 0.0f) atomicAdd(P.dst + col, t);
+    }
+    __syncthreads();
+  }
+}
+
+static int colsum16_launch(const Colsum16Problem* probs, int count, cudaStream_t st) {
+  int done = 0;
+  while (done < count) {
+    Colsum16List list;
+    const int n = (count - done) < COLSUM16_MAX ? (count - done) : COLSUM16_MAX;
+    int max_rows = 0;
+    for (int i = 0; i < n; ++i) {
+      list.p[i] = probs[done + i];
+      if (list.p[i].rows > max_rows) max_rows = list.p[i].rows;
+    }
+    list.count = n;
+    // ~4 waves of blocks over 148 SMs x 8 resident blocks
+    int chunks = (int)ceil_div(148 * 8, n);
+    if (chunks < 1) chunks = 1;
+    int rpb = (int)ceil_div(max_rows, chunks);
+    if (rpb < 64) rpb = 64;
+    list.rows_per_block = rpb;
+    if (max_rows > 0) {
+      dim3 grid((unsigned)ceil_div(max_rows, rpb), (unsigned)n);
+      colsum16_kernel<<<grid, 256, 0, st>>>(list);
+      MSF_LAUNCH_CHECK();
+    }
+    done += n;
+  }
+  return MSF_OK;
+}
+
+__global__ void copy_gates16_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+
+// ---------------------------------------------------------------------------
+// host orchestration
+// ---------------------------------------------------------------------------
+static int check_ws(const WsBf16& ws, const msf_fusion_call* c) {
+  if (c->workspace == nullptr || c->workspace_bytes < ws.bytes) {
+    set_error("workspace too small: need %zu bytes, have %zu", ws.bytes, c->workspace_bytes);
+    return MSF_E_WORKSPACE;
+  }
+  if (c->batch >= (1 << 24)) {
+    set_error("batch %d too large for one call of the tensor-core path", c->batch);
+    return MSF_E_INVALID;
+  }
+  return MSF_OK;
+}
+
+int fusion_bf16_forward(const Layout& L, const msf_fusion_call* c, cudaStream_t st) {
+  const int64_t B = c->batch;
+  const int M = L.M, H = L.H;
+  WsBf16 ws;
+  carve_bf16(L, B, c->workspace, &ws);
+  int rc = check_ws(ws, c);
+  if (rc) return rc;
+  const ArenaBf16 A = arena_layout(L);
+  const bf16* W16 = reinterpret_cast<const bf16*>(c->params_bf16);
+  const float* W = c->params;
+  const DropCfg drop = make_drop(c);
+  const long long BH = (long long)B * H;
+  const int pairs = L.num_pairs();
+  const int bnH = block_n_for(H);
+
+  {  // F0
+    PrepArgs16 a;
+    memset(&a, 0, sizeof(a));
+    int maxd = 8;
+    for (int m = 0; m < M; ++m) {
+      a.x[m] = c->x[m];
+      a.xt[m] = ws.xt[m];
+      a.D[m] = L.D[m];
+      if (L.D[m] > maxd) maxd = L.D[m];
+      MSF_REQUIRE((reinterpret_cast<uintptr_t>(c->x[m]) & 15) == 0, "features of modality %d are not 16-byte aligned", m);
+    }
+    a.M = M;
+    a.B = B;
+    a.mask = c->mask;
+    a.drop = drop;
+    const long long work = B * (maxd / 4);
+    dim3 grid((unsigned)(ceil_div(work, 256) < 1184 ? ceil_div(work, 256) : 1184), (unsigned)M);
+    prep16_kernel<<<grid, 256, 0, st>>>(a);
+    MSF_LAUNCH_CHECK();
+  }
+
+  {  // F1: P_m = drop1(relu(xt_m Wp_m^T + bp_m))
+    TcBuilder tb(false, bnH, drop, st);
+    for (int m = 0; m < M; ++m) {
+      TcProblem p = tc_blank_problem();
+      p.seg[0].a_map = (short)tb.add_map(ws.xt[m], B, L.D[m], L.D[m], 1, 0, TC_BLOCK_M);
+      p.seg[0].b_map = (short)tb.add_map(W16 + A.wp[m], H, L.D[m], L.D[m], 1, 0, bnH);
+      p.bias[0] = W + L.proj_b[m];
+      p.M = (int)B; p.N = H; p.K = L.D[m];
+      p.C = ws.P + (long long)m * BH; p.ldc = H; p.c_bf16 = 1;
+      p.epi = TC_EPI_BIAS_RELU_DROP; p.site = SITE_PROJ; p.sub = m;
+      tb.add_problem(p);
+    }
+    if ((rc = tb.flush())) return rc;
+  }
+
+  if (pairs > 0) {  // F2: U_qk = g_qk * (P_k Wv_qk^T + bv_qk)
+    TcBuilder tb(false, bnH, drop, st);
+    const short mapP = (short)tb.add_map(ws.P, B, H, H, M, BH, TC_BLOCK_M);
+    const short mapW = (short)tb.add_map(W16 + A.wv, H, H, H, pairs, (long long)H * H, bnH);
+    for (int q = 0; q < M; ++q)
+      for (int k = 0; k < M; ++k) {
+        if (q == k || !L.has_pair(q, k)) continue;
+        const int pi = L.pair_index(q, k);
+        TcProblem p = tc_blank_problem();
+        p.seg[0].a_map = mapP; p.seg[0].a_z = k;
+        p.seg[0].b_map = mapW; p.seg[0].b_z = pi;
+        p.bias[0] = W + L.pair_b(pi, 2);
+        p.M = (int)B; p.N = H; p.K = H;
+        p.C = ws.U + (long long)pi * BH; p.ldc = H; p.c_bf16 = 1;
+        p.epi = TC_EPI_VALUE_GATE;
+        p.mask = c->mask; p.mask_ld = M; p.mask_col = k;
+        p.gate_out = ws.G + (long long)pi * B * L.heads;
+        p.head_dim = H / L.heads; p.heads = L.heads;
+        p.sub = q * M + k;
+        tb.add_problem(p);
+      }
+    if ((rc = tb.flush())) return rc;
+  }
+
+  {  // F3: agg_q = (P_q + sum_k (U_qk Wo_qk^T + bo_qk)) / cnt_q * mask_q
+    TcBuilder tb(false, bnH, drop, st);
+    const short mapU = (short)tb.add_map(ws.U, B, H, H, pairs > 0 ? pairs : 1, BH, TC_BLOCK_M);
+    const short mapW = pairs > 0 ? (short)tb.add_map(W16 + A.wo, H, H, H, pairs, (long long)H * H, bnH) : mapU;
+    for (int q = 0; q < M; ++q) {
+      TcProblem p = tc_blank_problem();
+      int seg = 0;
+      for (int k = 0; k < M; ++k) {
+        if (q == k || !L.has_pair(q, k)) continue;
+        const int pi = L.pair_index(q, k);
+        p.seg[seg].a_map = mapU; p.seg[seg].a_z = pi;
+        p.seg[seg].b_map = mapW; p.seg[seg].b_z = pi;
+        p.bias[seg] = W + L.pair_b(pi, 3);
+        ++seg;
+      }
+      p.M = (int)B; p.N = H; p.K = seg ? H : 0;
+      if (seg == 0) { p.seg[0].a_map = mapU; p.seg[0].b_map = mapW; seg = 1; }  // epilogue only
+      p.nseg = seg;
+      p.C = ws.agg + (long long)q * BH; p.ldc = H; p.c_bf16 = 1;
+      p.epi = TC_EPI_OUT_MEAN; p.scale = (float)L.mean_count(q);
+      p.aux = ws.P + (long long)q * BH; p.ld_aux = H;
+      p.mask = c->mask; p.mask_ld = M; p.mask_col = q;
+      tb.add_problem(p);
+    }
+    if ((rc = tb.flush())) return rc;
+  }
+
+  {  // F4
+    Tail16Args a;
+    memset(&a, 0, sizeof(a));
+    a.agg = ws.agg;
+    for (int m = 0; m < M; ++m) {
+      a.gate_w[m] = W + L.gate_w[m];
+      a.gate_b[m] = W + L.gate_b[m];
+    }
+    a.mask = c->mask; a.soft = ws.soft; a.w = ws.w; a.w_out = c->fusion_weights; a.fused = ws.fused;
+    a.B = B; a.M = M; a.H = H;
+    tail16_fwd_kernel<<<(unsigned)ceil_div(B, 8), 256, 0, st>>>(a);
+    MSF_LAUNCH_CHECK();
+  }
+
+  {  // F5: Hr = drop3(relu(fused W1^T + b1))
+    TcBuilder tb(false, bnH, drop, st);
+    TcProblem p = tc_blank_problem();
+    p.seg[0].a_map = (short)tb.add_map(ws.fused, B, H, H, 1, 0, TC_BLOCK_M);
+    p.seg[0].b_map = (short)tb.add_map(W16 + A.w1, H, H, H, 1, 0, bnH);
+    p.bias[0] = W + L.cls_b1;
+    p.M = (int)B; p.N = H; p.K = H;
+    p.C = ws.Hr; p.ldc = H; p.c_bf16 = 1;
+    p.epi = TC_EPI_BIAS_RELU_DROP; p.site = SITE_CLS; p.sub = 0;
+    tb.add_problem(p);
+    if ((rc = tb.flush())) return rc;
+  }
+  {  // F6: logits = Hr W2^T + b2 (fp32 out)
+    const int bnC = L.C <= 32 ? 32 : block_n_for(L.C);
+    TcBuilder tb(false, bnC, drop, st);
+    TcProblem p = tc_blank_problem();
+    p.seg[0].a_map = (short)tb.add_map(ws.Hr, B, H, H, 1, 0, TC_BLOCK_M);
+    p.seg[0].b_map = (short)tb.add_map(W16 + A.w2, L.C, H, H, 1, 0, bnC);
+    p.bias[0] = W + L.cls_b2;
+    p.M = (int)B; p.N = L.C; p.K = H;
+    p.C = c->logits; p.ldc = L.C; p.c_bf16 = 0;
+    p.epi = TC_EPI_STORE;
+    tb.add_problem(p);
+    if ((rc = tb.flush())) return rc;
+  }
+
+  if (c->attn_gates && pairs > 0) {
+    const long long ng = (long long)pairs * B * L.heads;
+    for (int q = 0; q < M; ++q)
+      for (int k = 0; k < M; ++k)
+        if (q != k && !L.has_pair(q, k))
+          MSF_CHECK_CUDA(cudaMemsetAsync(ws.G + (size_t)L.pair_index(q, k) * B * L.heads, 0,
+                                         (size_t)B * L.heads * sizeof(float), st));
+    copy_gates16_kernel<<<(unsigned)(ceil_div(ng, 256) < 1184 ? ceil_div(ng, 256) : 1184), 256, 0, st>>>(
+        ws.G, c->attn_gates, ng);
+    MSF_LAUNCH_CHECK();
+  }
+  return MSF_OK;
+}
+
+int fusion_bf16_backward(const Layout& L, const msf_fusion_call* c, cudaStream_t st) {
+  const int64_t B = c->batch;
+  const int M = L.M, H = L.H, C = L.C;
+  WsBf16 ws;
+  carve_bf16(L, B, c->workspace, &ws);
+  int rc = check_ws(ws, c);
+  if (rc) return rc;
+  MSF_REQUIRE(c->grad_logits && c->grad_params, "backward needs grad_logits and grad_params");
+  const ArenaBf16 A = arena_layout(L);
+  const bf16* W16 = reinterpret_cast<const bf16*>(c->params_bf16);
+  const float* W = c->params;
+  float* dW = c->grad_params;
+  const DropCfg drop = make_drop(c);
+  const long long BH = (long long)B * H;
+  const int pairs = L.num_pairs();
+  const int bnH = block_n_for(H);
+  const int Cp = A.Cp;
+
+  // dead query/key projections and every slot accumulated below start from exact zeros
+  MSF_CHECK_CUDA(cudaMemsetAsync(dW, 0, (size_t)L.total * sizeof(float), st));
+  {
+    const long long total = B * Cp;
+    cvt_pad_kernel<<<(unsigned)(ceil_div(total, 256) < 1184 ? ceil_div(total, 256) : 1184), 256, 0, st>>>(
+        c->grad_logits, ws.dlog, B, C, Cp);
+    MSF_LAUNCH_CHECK();
+  }
+
+  {  // B1: dH1 = (dlogits W2) * relu'(Hr) * drop3
+    TcBuilder tb(false, bnH, drop, st);
+    TcProblem p = tc_blank_problem();
+    p.seg[0].a_map = (short)tb.add_map(ws.dlog, B, Cp, Cp, 1, 0, TC_BLOCK_M);
+    p.seg[0].b_map = (short)tb.add_map(W16 + A.w2T, H, Cp, Cp, 1, 0, bnH);
+    p.M = (int)B; p.N = H; p.K = Cp;
+    p.C = ws.dH1; p.ldc = H; p.c_bf16 = 1;
+    p.epi = TC_EPI_RELU_GRAD; p.scale = drop.scale; p.aux = ws.Hr; p.ld_aux = H;
+    tb.add_problem(p);
+    if ((rc = tb.flush())) return rc;
+  }
+  {  // B2: dfused = dH1 W1
+    TcBuilder tb(false, bnH, drop, st);
+    TcProblem p = tc_blank_problem();
+    p.seg[0].a_map = (short)tb.add_map(ws.dH1, B, H, H, 1, 0, TC_BLOCK_M);
+    p.seg[0].b_map = (short)tb.add_map(W16 + A.w1T, H, H, H, 1, 0, bnH);
+    p.M = (int)B; p.N = H; p.K = H;
+    p.C = ws.dfused; p.ldc = H; p.c_bf16 = 1;
+    p.epi = TC_EPI_STORE;
+    tb.add_problem(p);
+    if ((rc = tb.flush())) return rc;
+  }
+  {  // B4: tail backward
+    Tail16BwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.agg = ws.agg; a.dfused = ws.dfused; a.mask = c->mask; a.soft = ws.soft; a.w = ws.w;
+    a.dS = ws.dS; a.ds = ws.ds;
+    for (int m = 0; m < M; ++m) {
+      a.gate_w[m] = W + L.gate_w[m];
+      a.inv_cnt[m] = 1.0f / (float)L.mean_count(m);
+    }
+    a.B = B; a.M = M; a.H = H;
+    tail16_bwd_kernel<<<(unsigned)ceil_div(B, 8), 256, 0, st>>>(a);
+    MSF_LAUNCH_CHECK();
+  }
+  if (pairs > 0) {  // B5: dV_qk = (dS_q Wo_qk) * g_qk
+    TcBuilder tb(false, bnH, drop, st);
+    const short mapS = (short)tb.add_map(ws.dS, B, H, H, M, BH, TC_BLOCK_M);
+    const short mapW = (short)tb.add_map(W16 + A.woT, H, H, H, pairs, (long long)H * H, bnH);
+    for (int q = 0; q < M; ++q)
+      for (int k = 0; k < M; ++k) {
+        if (q == k || !L.has_pair(q, k)) continue;
+        const int pi = L.pair_index(q, k);
+        TcProblem p = tc_blank_problem();
+        p.seg[0].a_map = mapS; p.seg[0].a_z = q;
+        p.seg[0].b_map = mapW; p.seg[0].b_z = pi;
+        p.M = (int)B; p.N = H; p.K = H;
+        p.C = ws.dV + (long long)pi * BH; p.ldc = H; p.c_bf16 = 1;
+        p.epi = TC_EPI_GATE_MUL; p.gate_in = ws.G + (long long)pi * B * L.heads;
+        p.head_dim = H / L.heads; p.heads = L.heads;
+        tb.add_problem(p);
+      }
+    if ((rc = tb.flush())) return rc;
+  }
+  {  // B7: dZ_k = (dS_k + sum_q dV_qk Wv_qk) * relu'(P_k) * drop1
+    TcBuilder tb(false, bnH, drop, st);
+    const short mapV = (short)tb.add_map(ws.dV, B, H, H, pairs > 0 ? pairs : 1, BH, TC_BLOCK_M);
+    const short mapW = pairs > 0 ? (short)tb.add_map(W16 + A.wvT, H, H, H, pairs, (long long)H * H, bnH) : mapV;
+    for (int k = 0; k < M; ++k) {
+      TcProblem p = tc_blank_problem();
+      int seg = 0;
+      for (int q = 0; q < M; ++q) {
+        if (q == k || !L.has_pair(q, k)) continue;
+        const int pi = L.pair_index(q, k);
+        p.seg[seg].a_map = mapV; p.seg[seg].a_z = pi;
+        p.seg[seg].b_map = mapW; p.seg[seg].b_z = pi;
+        ++seg;
+      }
+      p.M = (int)B; p.N = H; p.K = seg ? H : 0;
+      if (seg == 0) { p.seg[0].a_map = mapV; p.seg[0].b_map = mapW; seg = 1; }
+      p.nseg = seg;
+      p.C = ws.dZ + (long long)k * BH; p.ldc = H; p.c_bf16 = 1;
+      p.epi = TC_EPI_ADD_RELU_GRAD; p.scale = drop.scale;
+      p.aux = ws.dS + (long long)k * BH; p.ld_aux = H;
+      p.aux2 = ws.P + (long long)k * BH; p.ld_aux2 = H;
+      tb.add_problem(p);
+    }
+    if ((rc = tb.flush())) return rc;
+  }
+  {  // B9a: dx_m = (dZ_m Wp_m) * mask_m * drop0   (fp32 out, only where requested)
+    for (int m = 0; m < M; ++m) {
+      if (!c->grad_x[m]) continue;
+      const int bnD = block_n_for(L.D[m]);
+      TcBuilder tb(false, bnD, drop, st);
+      TcProblem p = tc_blank_problem();
+      p.seg[0].a_map = (short)tb.add_map(ws.dZ + (long long)m * BH, B, H, H, 1, 0, TC_BLOCK_M);
+      p.seg[0].b_map = (short)tb.add_map(W16 + A.wpT[m], L.D[m], H, H, 1, 0, bnD);
+      p.M = (int)B; p.N = L.D[m]; p.K = H;
+      p.C = c->grad_x[m]; p.ldc = L.D[m]; p.c_bf16 = 0;
+      p.epi = TC_EPI_DX; p.site = SITE_INPUT; p.sub = m;
+      p.mask = c->mask; p.mask_ld = M; p.mask_col = m;
+      tb.add_problem(p);
+      if ((rc = tb.flush())) return rc;
+    }
+  }
+
+  // ---- all weight gradients: one MN-major launch, dW[out,in] = dY^T . X over the windows ----
+  {
+    const int bn = 128;
+    TcBuilder tb(true, bn, drop, st);
+    const short mapDlog = (short)tb.add_map(ws.dlog, B, Cp, Cp, 1, 0, 0);
+    const short mapHr = (short)tb.add_map(ws.Hr, B, H, H, 1, 0, 0);
+    const short mapDH1 = (short)tb.add_map(ws.dH1, B, H, H, 1, 0, 0);
+    const short mapFused = (short)tb.add_map(ws.fused, B, H, H, 1, 0, 0);
+    const short mapDS = (short)tb.add_map(ws.dS, B, H, H, M, BH, 0);
+    const short mapU = (short)tb.add_map(ws.U, B, H, H, pairs > 0 ? pairs : 1, BH, 0);
+    const short mapDV = (short)tb.add_map(ws.dV, B, H, H, pairs > 0 ? pairs : 1, BH, 0);
+    const short mapP = (short)tb.add_map(ws.P, B, H, H, M, BH, 0);
+    const short mapDZ = (short)tb.add_map(ws.dZ, B, H, H, M, BH, 0);
+    auto wgrad = [&](short am, int az, short bm, int bz, int rows, int cols, float* dst) {
+      TcProblem g = tc_blank_problem();
+      g.seg[0].a_map = am; g.seg[0].a_z = az;
+      g.seg[0].b_map = bm; g.seg[0].b_z = bz;
+      g.M = rows; g.N = cols; g.K = (int)B;
+      g.C = dst; g.ldc = cols; g.c_bf16 = 0; g.epi = TC_EPI_STORE;
+      tb.add_problem(g);
+    };
+    wgrad(mapDlog, 0, mapHr, 0, C, H, dW + L.cls_w2);      // dW2 = dlogits^T Hr
+    wgrad(mapDH1, 0, mapFused, 0, H, H, dW + L.cls_w1);    // dW1 = dH1^T fused
+    for (int q = 0; q < M; ++q)
+      for (int k = 0; k < M; ++k) {
+        if (q == k || !L.has_pair(q, k)) continue;
+        const int pi = L.pair_index(q, k);
+        wgrad(mapDS, q, mapU, pi, H, H, dW + L.pair_w(pi, 3));   // dWo_qk = dS_q^T U_qk
+        wgrad(mapDV, pi, mapP, k, H, H, dW + L.pair_w(pi, 2));   // dWv_qk = dV_qk^T P_k
+      }
+    // projections: xt_m may have a different width per modality -> one descriptor each
+    for (int m = 0; m < M; ++m) {
+      if (tb.nmaps >= TC_MAX_MAPS) {  // descriptor table full: launch and start a new one
+        if ((rc = tb.flush())) return rc;
+        tb.nmaps = 9;  // keep the shared maps above
+      }
+      const short mapX = (short)tb.add_map(ws.xt[m], B, L.D[m], L.D[m], 1, 0, 0);
+      wgrad(mapDZ, m, mapX, 0, H, L.D[m], dW + L.proj_w[m]);     // dWp_m = dZ_m^T xt_m
+    }
+    if ((rc = tb.flush())) return rc;
+  }
+
+  // ---- bias and gating-layer gradients: (weighted) column sums ----
+  {
+    Colsum16Problem cs[2 * MSF_MAX_MODALITIES * MSF_MAX_MODALITIES + 4 * MSF_MAX_MODALITIES + 4];
+    int nc = 0;
+    auto add = [&](const void* src, int f32, long long ld, int cols, const float* coef, int coef_ld, float* dst) {
+      Colsum16Problem p;
+      p.src = src; p.src_f32 = f32; p.ld = ld; p.rows = (int)B; p.cols = cols;
+      p.coef = coef; p.coef_ld = coef_ld; p.dst = dst;
+      cs[nc++] = p;
+    };
+    add(c->grad_logits, 1, C, C, nullptr, 0, dW + L.cls_b2);
+    add(ws.dH1, 0, H, H, nullptr, 0, dW + L.cls_b1);
+    for (int q = 0; q < M; ++q) {
+      add(ws.agg + (long long)q * BH, 0, H, H, ws.ds + q, M, dW + L.gate_w[q]);   // d gate_w_q = sum_r ds[r,q] agg_q[r,:]
+      add(ws.ds + q, 1, M, 1, nullptr, 0, dW + L.gate_b[q]);
+      add(ws.dZ + (long long)q * BH, 0, H, H, nullptr, 0, dW + L.proj_b[q]);
+      for (int k = 0; k < M; ++k) {
+        if (q == k || !L.has_pair(q, k)) continue;
+        const int pi = L.pair_index(q, k);
+        add(ws.dS + (long long)q * BH, 0, H, H, nullptr, 0, dW + L.pair_b(pi, 3));
+        add(ws.dV + (long long)pi * BH, 0, H, H, nullptr, 0, dW + L.pair_b(pi, 2));
+      }
+    }
+    if ((rc = colsum16_launch(cs, nc, st))) return rc;
+  }
+  return MSF_OK;
+}
+
+}  // namespace msf

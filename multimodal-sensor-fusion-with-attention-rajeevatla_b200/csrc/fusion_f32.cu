@@ -15,6 +15,7 @@
 //   F5 cls1      Hr    = drop3(relu(fused W1^T + b1))
 //   F6 cls2      logits = Hr W2^T + b2
 // Backward mirrors it (B1..B9 below).
+#include "fusion_common.cuh"
 #include "simt_gemm.cuh"
 
 namespace msf {
@@ -122,40 +123,6 @@ struct TailArgs {
   long long B;
   int M, H;
 };
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// weights for one window from scores s[] and mask mk[]; returns branch taken (1 = softmax branch)
-__device__ __forceinline__ int adaptive_weights_row(const float* s, const float* mk, int M, float* soft,
-                                                    float* w) {
-  float mx = -INFINITY;
-  for (int q = 0; q < M; ++q)
-    if (mk[q] > 0.0f) mx = fmaxf(mx, s[q]);  // masked_fill(mask <= 0, -inf)   fusion.py:464
-  float den = 0.0f;
-  for (int q = 0; q < M; ++q) {
-    // all-masked row: softmax of all -inf is NaN -> nan_to_num -> 0          fusion.py:465-466
-    soft[q] = (mk[q] > 0.0f && mx > -INFINITY) ? expf(s[q] - mx) : 0.0f;
-    den += soft[q];
-  }
-  float sum_w = 0.0f, mask_sum = 0.0f;
-  for (int q = 0; q < M; ++q) {
-    soft[q] = den > 0.0f ? soft[q] / den : 0.0f;
-    w[q] = soft[q] * mk[q];  // fusion.py:467
-    sum_w += w[q];
-    mask_sum += mk[q];
-  }
-  if (sum_w > 0.0f) {  // fusion.py:476-478
-    for (int q = 0; q < M; ++q) w[q] = w[q] / (sum_w + 1e-8f);
-    return 1;
-  }
-  for (int q = 0; q < M; ++q)  // fusion.py:471-475
-    w[q] = mask_sum > 0.0f ? mk[q] / (mask_sum + 1e-8f) : 1.0f / (float)M;
-  return 0;
-}
 
 __global__ void __launch_bounds__(256) tail_fwd_kernel(const __grid_constant__ TailArgs a) {
   const int lane = threadIdx.x & 31;
@@ -265,17 +232,6 @@ __global__ void copy_gates_kernel(const float* __restrict__ src, float* __restri
 // ---------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------
-static DropCfg make_drop(const msf_fusion_call* c) {
-  DropCfg d;
-  d.seed = c->seed;
-  d.offset = c->offset;
-  d.p = c->dropout_p;
-  d.active = (c->training && c->dropout_p > 0.0f) ? 1 : 0;
-  d.scale = d.active ? 1.0f / (1.0f - c->dropout_p) : 1.0f;
-  d.state = reinterpret_cast<const unsigned long long*>(c->rng_state);
-  return d;
-}
-
 static SimtProblem blank_problem() {
   SimtProblem p;
   memset(&p, 0, sizeof(p));

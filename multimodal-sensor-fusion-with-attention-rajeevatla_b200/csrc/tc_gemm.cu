@@ -149,118 +149,132 @@ __device__ __forceinline__ TileCoord locate(const TcLaunch& L, int tile) {
 __device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
 
 // ---------------------------------------------------------------------------
-// epilogue: 32 consecutive columns of one output row
+// epilogue
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void epilogue_chunk(const TcProblem& P, const DropCfg& drop, int row, int col0,
-                                               const uint32_t (&acc)[32], float mrow, int& cur_head,
-                                               float& cur_gate) {
+// Everything an epilogue thread needs about its tile, copied out of the kernel
+// parameters once per tile so the per-element code touches registers only.
+struct EpiTile {
+  int epi, M, N, nseg, c_bf16, head_dim, heads, site, sub;
+  float scale;
+  void* C;
+  long long ldc;
+  const __nv_bfloat16* aux;
+  long long ld_aux;
+  const __nv_bfloat16* aux2;
+  long long ld_aux2;
+  float* gate_out;
+  const float* gate_in;
+};
+
+__device__ __forceinline__ void load_row32(const __nv_bfloat16* src, bool vec, int ncols, float (&out)[32]) {
+  if (vec) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(src) + q);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(h[e]);
+        out[q * 8 + 2 * e] = f.x;
+        out[q * 8 + 2 * e + 1] = f.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) out[j] = (j < ncols) ? bf2f(src[j]) : 0.0f;
+  }
+}
+
+// One chunk: 32 consecutive columns [col0, col0+32) of output row `row`.
+// bias_lane: sum of the segment biases for column col0 + lane (0 beyond N).
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const EpiTile& T, const DropCfg& drop, int row, bool row_ok, int col0,
+                                               const uint32_t (&acc)[32], float bias_lane, float mrow) {
+  const int ncols = min(32, T.N - col0);
+  const bool full = ncols == 32;
   float v[32];
-  const bool row_ok = row < P.M;
-  const bool full = (col0 + 32 <= P.N);
 
   float aux[32], aux2[32];
-  const bool need_aux = (P.epi == TC_EPI_OUT_MEAN || P.epi == TC_EPI_RELU_GRAD || P.epi == TC_EPI_ADD_RELU_GRAD);
-  const bool need_aux2 = (P.epi == TC_EPI_ADD_RELU_GRAD);
-  if (need_aux) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) aux[j] = 0.0f;
+  if (EPI == TC_EPI_OUT_MEAN || EPI == TC_EPI_RELU_GRAD || EPI == TC_EPI_ADD_RELU_GRAD) {
     if (row_ok) {
-      const __nv_bfloat16* src = P.aux + (long long)row * P.ld_aux + col0;
-      if (full && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+      const __nv_bfloat16* src = T.aux + (long long)row * T.ld_aux + col0;
+      load_row32(src, full && ((reinterpret_cast<uintptr_t>(src) & 15) == 0), ncols, aux);
+    } else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint4 raw = __ldg(reinterpret_cast<const uint4*>(src) + q);
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+      for (int j = 0; j < 32; ++j) aux[j] = 0.0f;
+    }
+  }
+  if (EPI == TC_EPI_ADD_RELU_GRAD) {
+    if (row_ok) {
+      const __nv_bfloat16* src = T.aux2 + (long long)row * T.ld_aux2 + col0;
+      load_row32(src, full && ((reinterpret_cast<uintptr_t>(src) & 15) == 0), ncols, aux2);
+    } else {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 f = __bfloat1622float2(h[e]);
-            aux[q * 8 + 2 * e] = f.x;
-            aux[q * 8 + 2 * e + 1] = f.y;
-          }
-        }
+      for (int j = 0; j < 32; ++j) aux2[j] = 0.0f;
+    }
+  }
+
+  // per-(row, head) gate: heads are runs of head_dim columns
+  int head = 0, rem = 0;
+  float gate = 0.0f;
+  if (EPI == TC_EPI_VALUE_GATE || EPI == TC_EPI_GATE_MUL) {
+    head = col0 / T.head_dim;
+    rem = col0 - head * T.head_dim;
+    if (rem != 0) {  // chunk starts inside a head: fetch its gate (already recorded by the owner of its first column)
+      if (EPI == TC_EPI_VALUE_GATE) {
+        gate = (mrow != 0.0f) ? 1.0f : 0.0f;
+        if (drop.active && head < T.heads) gate *= drop1(drop, SITE_ATTN, T.sub, row, head);
       } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < P.N) aux[j] = bf2f(src[j]);
+        gate = (row_ok && head < T.heads) ? __ldg(T.gate_in + (long long)row * T.heads + head) : 0.0f;
       }
     }
   }
-  if (need_aux2) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) aux2[j] = 0.0f;
-    if (row_ok) {
-      const __nv_bfloat16* src = P.aux2 + (long long)row * P.ld_aux2 + col0;
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < P.N) aux2[j] = bf2f(src[j]);
-    }
-  }
 
-  const bool need_drop = drop.active && (P.epi == TC_EPI_BIAS_RELU_DROP || P.epi == TC_EPI_DX);
 #pragma unroll
   for (int g4 = 0; g4 < 8; ++g4) {
     float dm[4] = {1.f, 1.f, 1.f, 1.f};
-    if (need_drop && row_ok && col0 + g4 * 4 < P.N) drop4(drop, P.site, P.sub, row, (col0 >> 2) + g4, dm);
+    if (EPI == TC_EPI_BIAS_RELU_DROP || EPI == TC_EPI_DX) {
+      if (drop.active && row_ok && g4 * 4 < ncols) drop4(drop, T.site, T.sub, row, (col0 >> 2) + g4, dm);
+    }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int j = g4 * 4 + e;
-      const int col = col0 + j;
       const float a = __uint_as_float(acc[j]);
       float bias = 0.0f;
-      if (col < P.N) {
-        for (int s = 0; s < P.nseg; ++s)
-          if (P.bias[s]) bias += __ldg(P.bias[s] + col);
+      if (EPI == TC_EPI_STORE || EPI == TC_EPI_BIAS_RELU_DROP || EPI == TC_EPI_VALUE_GATE || EPI == TC_EPI_OUT_MEAN)
+        bias = __shfl_sync(0xffffffffu, bias_lane, j);
+      if (EPI == TC_EPI_VALUE_GATE || EPI == TC_EPI_GATE_MUL) {
+        if (rem == 0) {  // first column of a head
+          if (EPI == TC_EPI_VALUE_GATE) {
+            gate = (mrow != 0.0f) ? 1.0f : 0.0f;
+            if (drop.active && head < T.heads) gate *= drop1(drop, SITE_ATTN, T.sub, row, head);
+            if (T.gate_out != nullptr && row_ok && head < T.heads && j < ncols)
+              T.gate_out[(long long)row * T.heads + head] = gate;
+          } else {
+            gate = (row_ok && head < T.heads) ? __ldg(T.gate_in + (long long)row * T.heads + head) : 0.0f;
+          }
+        }
+        if (++rem == T.head_dim) {
+          rem = 0;
+          ++head;
+        }
       }
       float r;
-      switch (P.epi) {
-        default:
-        case TC_EPI_STORE:
-          r = a * P.scale + bias;
-          break;
-        case TC_EPI_BIAS_RELU_DROP:
-          r = fmaxf(a + bias, 0.0f) * dm[e];
-          break;
-        case TC_EPI_VALUE_GATE: {
-          const int head = col / P.head_dim;
-          if (head != cur_head) {
-            cur_head = head;
-            cur_gate = (mrow != 0.0f) ? 1.0f : 0.0f;
-            if (drop.active && head < P.heads) cur_gate *= drop1(drop, SITE_ATTN, P.sub, row, head);
-            if (P.gate_out != nullptr && row_ok && head < P.heads)
-              P.gate_out[(long long)row * P.heads + head] = cur_gate;
-          }
-          r = (a + bias) * cur_gate;
-          break;
-        }
-        case TC_EPI_OUT_MEAN:
-          r = (a + bias + aux[j]) / P.scale * mrow;
-          break;
-        case TC_EPI_RELU_GRAD:
-          r = a * (aux[j] > 0.0f ? P.scale : 0.0f);
-          break;
-        case TC_EPI_GATE_MUL: {
-          const int head = col / P.head_dim;
-          if (head != cur_head) {
-            cur_head = head;
-            cur_gate = (row_ok && head < P.heads) ? __ldg(P.gate_in + (long long)row * P.heads + head) : 0.0f;
-          }
-          r = a * cur_gate;
-          break;
-        }
-        case TC_EPI_ADD_RELU_GRAD:
-          r = (a + aux[j]) * (aux2[j] > 0.0f ? P.scale : 0.0f);
-          break;
-        case TC_EPI_DX:
-          r = a * mrow * dm[e];
-          break;
-      }
+      if (EPI == TC_EPI_STORE) r = fmaf(a, T.scale, bias);
+      else if (EPI == TC_EPI_BIAS_RELU_DROP) r = fmaxf(a + bias, 0.0f) * dm[e];
+      else if (EPI == TC_EPI_VALUE_GATE) r = (a + bias) * gate;
+      else if (EPI == TC_EPI_OUT_MEAN) r = (a + bias + aux[j]) / T.scale * mrow;
+      else if (EPI == TC_EPI_RELU_GRAD) r = a * (aux[j] > 0.0f ? T.scale : 0.0f);
+      else if (EPI == TC_EPI_GATE_MUL) r = a * gate;
+      else if (EPI == TC_EPI_ADD_RELU_GRAD) r = (a + aux[j]) * (aux2[j] > 0.0f ? T.scale : 0.0f);
+      else r = a * mrow * dm[e];  // TC_EPI_DX
       v[j] = r;
     }
   }
 
   if (!row_ok) return;
-  if (P.c_bf16) {
-    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(P.C) + (long long)row * P.ldc + col0;
+  if (T.c_bf16) {
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(T.C) + (long long)row * T.ldc + col0;
     if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -273,10 +287,10 @@ __device__ __forceinline__ void epilogue_chunk(const TcProblem& P, const DropCfg
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (col0 + j < P.N) dst[j] = __float2bfloat16_rn(v[j]);
+        if (j < ncols) dst[j] = __float2bfloat16_rn(v[j]);
     }
   } else {
-    float* dst = reinterpret_cast<float*>(P.C) + (long long)row * P.ldc + col0;
+    float* dst = reinterpret_cast<float*>(T.C) + (long long)row * T.ldc + col0;
     if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
       for (int q = 0; q < 8; ++q)
@@ -284,8 +298,35 @@ __device__ __forceinline__ void epilogue_chunk(const TcProblem& P, const DropCfg
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (col0 + j < P.N) dst[j] = v[j];
+        if (j < ncols) dst[j] = v[j];
     }
+  }
+}
+
+// All chunks this warp owns in one tile: chunk c (32 columns) belongs to column group c % TC_EPI_COLGROUPS.
+template <int EPI>
+__device__ __forceinline__ void epilogue_tile(const EpiTile& T, const float* const (&bias)[TC_MAX_SEG], const DropCfg& drop,
+                                              uint32_t tmem_acc, int row, float mrow, int n0, int ncols, int colgroup,
+                                              bool has_acc, int lane) {
+  const bool row_ok = row < T.M;
+  for (int c = colgroup * 32; c < ncols; c += 32 * TC_EPI_COLGROUPS) {
+    uint32_t acc[32];
+    if (has_acc) {
+      tmem_ld32(tmem_acc + (uint32_t)c, acc);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] = 0u;  // epilogue-only problem: nothing was accumulated
+    }
+    float bias_lane = 0.0f;
+    if (EPI == TC_EPI_STORE || EPI == TC_EPI_BIAS_RELU_DROP || EPI == TC_EPI_VALUE_GATE || EPI == TC_EPI_OUT_MEAN) {
+      const int col = n0 + c + lane;
+      if (col < T.N) {
+#pragma unroll
+        for (int s = 0; s < TC_MAX_SEG; ++s)
+          if (s < T.nseg && bias[s] != nullptr) bias_lane += __ldg(bias[s] + col);
+      }
+    }
+    epilogue_chunk<EPI>(T, drop, row, row_ok, n0 + c, acc, bias_lane, mrow);
   }
 }
 
@@ -293,7 +334,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcProblem& P, const DropCfg
 // the kernel
 // ---------------------------------------------------------------------------
 template <bool MN_MAJOR>
-__global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__ TcLaunch L) {
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcLaunch L) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // carve: [A stages][B stages][barriers][tmem base]
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -314,7 +355,7 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
   const uint32_t tmem_cols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < TC_MAX_MAPS; ++i) tma_prefetch_desc(&L.maps[i]);
+    for (int i = 0; i < L.nmaps; ++i) tma_prefetch_desc(&L.maps[i]);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
@@ -323,7 +364,7 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(a), TC_EPI_WARPS);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -337,9 +378,6 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int kblocks_of = TC_BLOCK_K;
-  (void)kblocks_of;
-
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
@@ -347,11 +385,12 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < L.total_tiles; tile += gridDim.x) {
         const TileCoord t = locate(L, tile);
-        const TcProblem& P = L.p[t.problem];
-        const int kb_per_seg = (P.K + TC_BLOCK_K - 1) / TC_BLOCK_K;
-        for (int s = 0; s < P.nseg; ++s) {
-          const CUtensorMap* amap = &L.maps[P.seg[s].a_map];
-          const CUtensorMap* bmap = &L.maps[P.seg[s].b_map];
+        const int nseg = L.p[t.problem].nseg;
+        const int kb_per_seg = (L.p[t.problem].K + TC_BLOCK_K - 1) / TC_BLOCK_K;
+        for (int s = 0; s < nseg; ++s) {
+          const CUtensorMap* amap = &L.maps[L.p[t.problem].seg[s].a_map];
+          const CUtensorMap* bmap = &L.maps[L.p[t.problem].seg[s].b_map];
+          const int a_z = L.p[t.problem].seg[s].a_z, b_z = L.p[t.problem].seg[s].b_z;
           for (int kb = 0; kb < kb_per_seg; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             mbar_expect_tx(full_bar(stage), A_STAGE_BYTES + B_STAGE);
@@ -359,14 +398,14 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
             const uint32_t b_dst = b_base + stage * B_STAGE;
             const int k0 = kb * TC_BLOCK_K;
             if (!MN_MAJOR) {
-              tma_load_3d(a_dst, amap, k0, t.m0, P.seg[s].a_z, full_bar(stage));
-              tma_load_3d(b_dst, bmap, k0, t.n0, P.seg[s].b_z, full_bar(stage));
+              tma_load_3d(a_dst, amap, k0, t.m0, a_z, full_bar(stage));
+              tma_load_3d(b_dst, bmap, k0, t.n0, b_z, full_bar(stage));
             } else {
               // 64(mn) x 64(k) slabs, 8 KiB each, mn-slab major
               for (int j = 0; j < TC_BLOCK_M / 64; ++j)
-                tma_load_3d(a_dst + j * 8192u, amap, t.m0 + 64 * j, k0, P.seg[s].a_z, full_bar(stage));
+                tma_load_3d(a_dst + j * 8192u, amap, t.m0 + 64 * j, k0, a_z, full_bar(stage));
               for (int j = 0; j < (int)BN / 64; ++j)
-                tma_load_3d(b_dst + j * 8192u, bmap, t.n0 + 64 * j, k0, P.seg[s].b_z, full_bar(stage));
+                tma_load_3d(b_dst + j * 8192u, bmap, t.n0 + 64 * j, k0, b_z, full_bar(stage));
             }
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
           }
@@ -385,8 +424,7 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
       int it = 0;
       for (int tile = blockIdx.x; tile < L.total_tiles; tile += gridDim.x, ++it) {
         const TileCoord t = locate(L, tile);
-        const TcProblem& P = L.p[t.problem];
-        const int total_kb = P.nseg * ((P.K + TC_BLOCK_K - 1) / TC_BLOCK_K);
+        const int total_kb = L.p[t.problem].nseg * ((L.p[t.problem].K + TC_BLOCK_K - 1) / TC_BLOCK_K);
         const int acc = it & 1;
         const uint32_t use = (uint32_t)(it >> 1);
         mbar_wait(tempty_bar(acc), (use & 1u) ^ 1u);  // epilogue has drained this accumulator
@@ -412,25 +450,39 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
   } else if (warp >= 4) {
     // =========================== epilogue ===============================
     const DropCfg drop = resolve_drop(L.drop);
-    const int ew = warp & 3;  // TMEM lane quarter this warp may read
+    const int lq = warp & 3;               // TMEM lane quarter this warp may read
+    const int colgroup = (warp - 4) >> 2;  // which 32-column chunks it owns
     int it = 0;
     for (int tile = blockIdx.x; tile < L.total_tiles; tile += gridDim.x, ++it) {
       const TileCoord t = locate(L, tile);
       const TcProblem& P = L.p[t.problem];
+      EpiTile T;
+      T.epi = P.epi; T.M = P.M; T.N = P.N; T.nseg = P.nseg; T.c_bf16 = P.c_bf16;
+      T.head_dim = P.head_dim; T.heads = P.heads; T.site = P.site; T.sub = P.sub; T.scale = P.scale;
+      T.C = P.C; T.ldc = P.ldc; T.aux = P.aux; T.ld_aux = P.ld_aux; T.aux2 = P.aux2; T.ld_aux2 = P.ld_aux2;
+      T.gate_out = P.gate_out; T.gate_in = P.gate_in;
+      const float* bias[TC_MAX_SEG];
+#pragma unroll
+      for (int s = 0; s < TC_MAX_SEG; ++s) bias[s] = P.bias[s];
+      const bool has_acc = P.K > 0;
+      const int row = t.m0 + lq * 32 + lane;
+      const float mrow = (P.mask != nullptr && row < T.M) ? __ldg(P.mask + (long long)row * P.mask_ld + P.mask_col) : 1.0f;
+      const int ncols = min((int)BN, T.N - t.n0);
       const int acc = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
       mbar_wait(tfull_bar(acc), use & 1u);
       tc_fence_after();
-      const int row = t.m0 + ew * 32 + lane;
-      const float mrow = (P.mask != nullptr && row < P.M) ? __ldg(P.mask + (long long)row * P.mask_ld + P.mask_col) : 1.0f;
-      int cur_head = -1;
-      float cur_gate = 0.0f;
-      const int ncols = min((int)BN, P.N - t.n0);
-      for (int c = 0; c < ncols; c += 32) {
-        uint32_t acc_regs[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * BN + (uint32_t)c;
-        tmem_ld32(taddr, acc_regs);
-        epilogue_chunk(P, drop, row, t.n0 + c, acc_regs, mrow, cur_head, cur_gate);
+      const uint32_t tmem_acc = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)acc * BN;
+      switch (T.epi) {
+        default:
+        case TC_EPI_STORE: epilogue_tile<TC_EPI_STORE>(T, bias, drop, tmem_acc, row, mrow, t.n0, ncols, colgroup, has_acc, lane); break;
+        case TC_EPI_BIAS_RELU_DROP: epilogue_tile<TC_EPI_BIAS_RELU_DROP>(T, bias, drop, tmem_acc, row, mrow, t.n0, ncols, colgroup, has_acc, lane); break;
+        case TC_EPI_VALUE_GATE: epilogue_tile<TC_EPI_VALUE_GATE>(T, bias, drop, tmem_acc, row, mrow, t.n0, ncols, colgroup, has_acc, lane); break;
+        case TC_EPI_OUT_MEAN: epilogue_tile<TC_EPI_OUT_MEAN>(T, bias, drop, tmem_acc, row, mrow, t.n0, ncols, colgroup, has_acc, lane); break;
+        case TC_EPI_RELU_GRAD: epilogue_tile<TC_EPI_RELU_GRAD>(T, bias, drop, tmem_acc, row, mrow, t.n0, ncols, colgroup, has_acc, lane); break;
+        case TC_EPI_GATE_MUL: epilogue_tile<TC_EPI_GATE_MUL>(T, bias, drop, tmem_acc, row, mrow, t.n0, ncols, colgroup, has_acc, lane); break;
+        case TC_EPI_ADD_RELU_GRAD: epilogue_tile<TC_EPI_ADD_RELU_GRAD>(T, bias, drop, tmem_acc, row, mrow, t.n0, ncols, colgroup, has_acc, lane); break;
+        case TC_EPI_DX: epilogue_tile<TC_EPI_DX>(T, bias, drop, tmem_acc, row, mrow, t.n0, ncols, colgroup, has_acc, lane); break;
       }
       tc_fence_before();
       __syncwarp();
@@ -465,20 +517,44 @@ int tc_init() {
   return MSF_OK;
 }
 
-TcBuilder::TcBuilder(bool mn, int block_n) : nmaps(0), mn_major(mn) {
+TcBuilder::TcBuilder(bool mn, int block_n, const DropCfg& drop, cudaStream_t st)
+    : nmaps(0), mn_major(mn), stream(st), status(MSF_OK) {
   memset(&L, 0, sizeof(L));
   L.block_n = block_n;
+  L.drop = drop;
+}
+
+TcProblem tc_blank_problem() {
+  TcProblem p;
+  memset(&p, 0, sizeof(p));
+  p.nseg = 1;
+  p.scale = 1.0f;
+  p.head_dim = 1;
+  p.heads = 1;
+  return p;
+}
+
+DropCfg no_dropout() {
+  DropCfg d;
+  memset(&d, 0, sizeof(d));
+  d.scale = 1.0f;
+  return d;
 }
 
 int TcBuilder::add_map(const void* base, long long rows, long long cols, long long ld, long long depth,
                        long long slice, int role_rows) {
   if (nmaps >= TC_MAX_MAPS) {
     set_error("tc_gemm: too many tensor maps in one launch");
+    status = MSF_E_INVALID;
     return -1;
   }
-  if (tc_init() != MSF_OK) return -1;
+  if (tc_init() != MSF_OK) {
+    status = MSF_E_CUDA;
+    return -1;
+  }
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld % 8) || (depth > 1 && (slice % 8))) {
     set_error("tc_gemm: operand not 16-byte aligned (base %p, ld %lld, slice %lld)", base, ld, slice);
+    status = MSF_E_INVALID;
     return -1;
   }
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(depth < 1 ? 1 : depth)};
@@ -491,21 +567,25 @@ int TcBuilder::add_map(const void* base, long long rows, long long cols, long lo
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): rows %lld cols %lld ld %lld depth %lld box %u", (int)r, rows, cols,
               ld, depth, box[1]);
+    status = MSF_E_CUDA;
     return -1;
   }
   return nmaps++;
 }
 
 int TcBuilder::add_problem(const TcProblem& p) {
+  if (status != MSF_OK) return status;
   if (p.M <= 0 || p.N <= 0) return MSF_OK;
   if (L.count >= TC_MAX_PROBLEMS) {
-    set_error("tc_gemm: too many problems in one launch");
-    return MSF_E_INVALID;
+    const int rc = flush();
+    if (rc) return rc;
   }
   if (p.nseg < 1 || p.nseg > TC_MAX_SEG) {
     set_error("tc_gemm: nseg %d out of range", p.nseg);
-    return MSF_E_INVALID;
+    return status = MSF_E_INVALID;
   }
+  for (int s = 0; s < p.nseg; ++s)
+    if (p.seg[s].a_map < 0 || p.seg[s].b_map < 0) return status = MSF_E_INVALID;  // add_map failed earlier
   TcProblem q = p;
   q.tile_begin = L.total_tiles;
   L.total_tiles += (int)(ceil_div(p.M, TC_BLOCK_M) * ceil_div(p.N, L.block_n));
@@ -513,13 +593,14 @@ int TcBuilder::add_problem(const TcProblem& p) {
   return MSF_OK;
 }
 
-int TcBuilder::launch(const DropCfg& drop, cudaStream_t stream) {
+int TcBuilder::flush() {
+  if (status != MSF_OK) return status;
   if (L.total_tiles == 0) return MSF_OK;
   MSF_REQUIRE(L.block_n >= 32 && L.block_n <= 256 && L.block_n % 16 == 0 && (!mn_major || L.block_n % 64 == 0),
               "tc_gemm: block_n %d unsupported", L.block_n);
   // fill unused descriptor slots with a valid descriptor (they are prefetched)
   for (int i = nmaps; i < TC_MAX_MAPS; ++i) L.maps[i] = L.maps[0];
-  L.drop = drop;
+  L.nmaps = nmaps;
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
@@ -530,12 +611,14 @@ int TcBuilder::launch(const DropCfg& drop, cudaStream_t stream) {
   const int grid = L.total_tiles < sms ? L.total_tiles : sms;
   if (mn_major) {
     MSF_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_gemm_kernel<true><<<grid, 256, smem, stream>>>(L);
+    tc_gemm_kernel<true><<<grid, TC_THREADS, smem, stream>>>(L);
   } else {
     MSF_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_gemm_kernel<false><<<grid, 256, smem, stream>>>(L);
+    tc_gemm_kernel<false><<<grid, TC_THREADS, smem, stream>>>(L);
   }
   MSF_LAUNCH_CHECK();
+  L.count = 0;
+  L.total_tiles = 0;
   return MSF_OK;
 }
 
@@ -551,7 +634,7 @@ extern "C" int msf_gemm_bf16(const void* a, const void* b, void* d, int32_t d_is
   MSF_REQUIRE(m < (1ll << 31) && n < (1ll << 31) && k < (1ll << 31), "msf_gemm_bf16: dimension too large");
   int bn = n >= 256 ? 256 : n > 128 ? 256 : n > 64 ? 128 : 64;
   if (!mn_major && n <= 32) bn = 32;
-  msf::TcBuilder tb(mn_major != 0, bn);
+  msf::TcBuilder tb(mn_major != 0, bn, msf::no_dropout(), (cudaStream_t)stream);
   int am, bm;
   if (!mn_major) {
     am = tb.add_map(a, m, k, lda, 1, 0, msf::TC_BLOCK_M);   // A[m, k]
@@ -561,19 +644,13 @@ extern "C" int msf_gemm_bf16(const void* a, const void* b, void* d, int32_t d_is
     bm = tb.add_map(b, k, n, ldb, 1, 0, 0);                 // B[k, n]
   }
   if (am < 0 || bm < 0) return MSF_E_INVALID;
-  msf::TcProblem p;
-  memset(&p, 0, sizeof(p));
-  p.nseg = 1;
+  msf::TcProblem p = msf::tc_blank_problem();
   p.seg[0].a_map = (short)am; p.seg[0].b_map = (short)bm;
   p.bias[0] = bias;
   p.M = (int)m; p.N = (int)n; p.K = (int)k;
   p.C = d; p.ldc = ldd; p.c_bf16 = d_is_bf16;
   p.epi = relu ? msf::TC_EPI_BIAS_RELU_DROP : msf::TC_EPI_STORE;
-  p.scale = 1.0f; p.head_dim = 1; p.heads = 1;
   int rc = tb.add_problem(p);
   if (rc) return rc;
-  msf::DropCfg nd;
-  memset(&nd, 0, sizeof(nd));
-  nd.scale = 1.0f;
-  return tb.launch(nd, (cudaStream_t)stream);
+  return tb.flush();
 }

@@ -19,11 +19,14 @@
 namespace msf {
 
 constexpr int TC_MAX_SEG = 7;
-constexpr int TC_MAX_PROBLEMS = 24;
+constexpr int TC_MAX_PROBLEMS = 40;
 constexpr int TC_MAX_MAPS = 16;
 constexpr int TC_BLOCK_M = 128;
 constexpr int TC_BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
 constexpr int TC_STAGES = 4;
+constexpr int TC_EPI_COLGROUPS = 2;                 // epilogue warps per TMEM lane quarter
+constexpr int TC_EPI_WARPS = 4 * TC_EPI_COLGROUPS;
+constexpr int TC_THREADS = 128 + 32 * TC_EPI_WARPS; // TMA, MMA, TMEM-alloc, spare + epilogue warps
 
 enum TcEpilogue {
   TC_EPI_STORE = 0,        // v = acc*scale + bias
@@ -68,25 +71,33 @@ struct TcLaunch {
   CUtensorMap maps[TC_MAX_MAPS];
   TcProblem p[TC_MAX_PROBLEMS];
   int count;
+  int nmaps;
   int total_tiles;
   int block_n;            // 32..256, multiple of 16; uniform per launch
   DropCfg drop;
 };
 
-// Host-side builder for one launch.
+// Host-side builder: collects problems over a shared table of TMA descriptors and
+// launches them; more than TC_MAX_PROBLEMS problems are split over several
+// launches (the descriptor table is kept).
 struct TcBuilder {
   TcLaunch L;
   int nmaps;
   bool mn_major;
-  TcBuilder(bool mn, int block_n);
+  cudaStream_t stream;
+  int status;             // first error seen (MSF_OK otherwise)
+  TcBuilder(bool mn, int block_n, const DropCfg& drop, cudaStream_t st);
   // Stacked bf16 tensor [depth][rows][cols] (row pitch = ld elements, slice pitch = slice elements).
   // role_rows: box height along `rows` for a K-major operand (TC_BLOCK_M for A, block_n for B);
   // ignored for MN-major operands (box = 64 x 64).
   int add_map(const void* base, long long rows, long long cols, long long ld, long long depth,
               long long slice, int role_rows);
   int add_problem(const TcProblem& p);
-  int launch(const DropCfg& drop, cudaStream_t stream);
+  int flush();            // launch what has been collected so far
 };
+
+TcProblem tc_blank_problem();
+DropCfg no_dropout();
 
 int tc_init();  // resolves cuTensorMapEncodeTiled; MSF_OK or error
 

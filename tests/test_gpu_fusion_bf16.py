@@ -1,0 +1,199 @@
+"""Tensor-core (MSF_PREC_BF16: bf16 operands, fp32 accumulate in TMEM) HybridFusion
+path against the fp32 CPU oracle and the reference's golden vectors.
+Tolerance (BASELINE.json north_star): max-abs <= 1e-2 on logits, fusion weights
+and gradients; attention gates, fallbacks and dead q/k gradients stay exact."""
+import importlib
+
+import pytest
+import torch
+
+from conftest import Golden, load_pkg
+from helpers import PAMAP2, module_from_golden, seeded_case
+from oracle import fusion_oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-2
+
+
+def _ops():
+    return importlib.import_module(load_pkg().__name__ + ".ops")
+
+
+def _maxabs(a, b):
+    return float((a.detach().cpu().double() - b.detach().cpu().double()).abs().max())
+
+
+def _relfro(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def test_eval_matches_reference_golden():
+    g = Golden("fusion_tc_shape.npz")
+    model = module_from_golden(g, device="cuda", precision="bf16").eval()
+    feats = {k: v.cuda() for k, v in g.group("x").items()}
+    mask = g.t("mask").cuda()
+    logits, info = model(feats, mask, return_attention=True)
+    assert logits.dtype == torch.float32
+    assert _maxabs(logits, g.t("eval/logits")) <= TOL
+    assert _maxabs(info["fusion_weights"], g.t("eval/fusion_weights")) <= TOL
+    for key, ref in g.group("eval/attn").items():
+        assert torch.equal(info["attention_maps"][key].cpu(), ref), key  # gates are exactly {0,1}
+    fw = info["fusion_weights"].cpu()
+    M = fw.shape[1]
+    assert torch.equal(fw[1], torch.full((M,), 1.0 / M))      # all-missing window: uniform fallback, exact
+    assert torch.equal(fw[2], torch.eye(M)[M - 1])            # single modality: one-hot, exact
+    assert _maxabs(model(feats), g.t("eval/logits_nomask")) <= TOL
+
+
+def test_train_grads_match_reference_golden():
+    g = Golden("fusion_tc_shape.npz")
+    ops = _ops()
+    model = module_from_golden(g, device="cuda", dropout=0.0, precision="bf16").train()
+    feats = {k: v.cuda().requires_grad_(True) for k, v in g.group("x").items()}
+    logits = model(feats, g.t("mask").cuda())
+    loss, dlogits = ops.cross_entropy(logits.detach(), g.t("labels").cuda(), float(g["smoothing"]))
+    logits.backward(dlogits)
+    assert _maxabs(logits, g.t("train/logits")) <= TOL
+    assert abs(float(loss) - float(g["train/loss"])) <= TOL
+    grads = dict(model.named_parameters())
+    for key, ref in g.group("grad").items():
+        got = grads[key].grad
+        assert got is not None, key
+        assert _maxabs(got, ref) <= TOL, key
+        # relative check too: bf16 must track the gradient, not just stay under an absolute bound.
+        # ReLU masks are taken from bf16 activations, so a few near-zero units flip; each flip is a
+        # full-size error in that unit's gradient: Frobenius-relative error ~ sqrt(flip rate) ~ 5 %.
+        assert _relfro(got, ref) <= 0.10, key
+        if ".query_proj." in key or ".key_proj." in key:
+            assert float(got.abs().max()) == 0.0, key
+    for key, ref in g.group("gradx").items():
+        assert _maxabs(feats[key].grad, ref) <= TOL, key
+
+
+@pytest.mark.parametrize("batch", [384, 1000])
+def test_config2_shape_matches_oracle(batch):
+    """PAMAP2 shape of BASELINE config 2 (M=4, D=128, H=256, heads=4, C=25); B not a tile multiple."""
+    ops = _ops()
+    model, feats, mask, labels = seeded_case(PAMAP2, 256, 4, 25, batch, seed=5, device="cuda")
+    model.precision = "bf16"
+    model.train()
+    xs = {k: v.clone().requires_grad_(True) for k, v in feats.items()}
+    logits, info = model(xs, mask, return_attention=True)
+    loss, dlogits = ops.cross_entropy(logits.detach(), labels, 0.05)
+    logits.backward(dlogits)
+
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    xo = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in feats.items()}
+    ref_logits, ref_info = fusion_oracle.hybrid_fusion_forward(sd, model.modality_names, 4, xo, mask.cpu())
+    ref_loss = fusion_oracle.cross_entropy_label_smoothing(ref_logits, labels.cpu(), 0.05)
+    ref_loss.backward()
+    assert _maxabs(logits, ref_logits) <= TOL
+    assert _maxabs(info["fusion_weights"], ref_info["fusion_weights"]) <= TOL
+    assert abs(float(loss) - float(ref_loss)) <= TOL
+    for key, p in model.named_parameters():
+        ref = sd[key].grad
+        assert _maxabs(p.grad, ref) <= TOL, key
+        if ".query_proj." in key or ".key_proj." in key:
+            assert float(p.grad.abs().max()) == 0.0, key
+        else:
+            assert _relfro(p.grad, ref) <= 0.10, key  # see test_train_grads_match_reference_golden
+    for key in xs:
+        assert _maxabs(xs[key].grad, xo[key].grad) <= TOL, key
+    for key, ref in ref_info["attention_maps"].items():
+        assert torch.equal(info["attention_maps"][key].cpu(), ref), key
+    top2 = ref_logits.detach().topk(2, dim=1).values
+    safe = (top2[:, 0] - top2[:, 1]) > 4 * TOL
+    assert torch.equal(logits.argmax(1).cpu()[safe], ref_logits.argmax(1)[safe])
+
+
+def test_dropout_masks_injected_into_oracle():
+    """Train mode, p = 0.1 on the tensor-core path: the Philox masks the GEMM epilogues
+    drew are dumped, injected into the fp32 oracle, and everything must agree to bf16 tolerance."""
+    ops = _ops()
+    model, feats, mask, labels = seeded_case(PAMAP2, 256, 4, 25, 300, seed=11, device="cuda")
+    model.precision = "bf16"
+    model.dropout.p = 0.1
+    for mod in model.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.1
+    model.train()
+    plan = model._plan()
+    names, B, H, heads, M = model.modality_names, 300, plan.H, plan.heads, plan.M
+    torch.manual_seed(77)
+    expect_seed = int(torch.randint(0, 2**62, (1,)).item())
+    torch.manual_seed(77)
+    xs = {k: v.clone().requires_grad_(True) for k, v in feats.items()}
+    logits, info = model(xs, mask, return_attention=True)
+    loss, dlogits = ops.cross_entropy(logits.detach(), labels, 0.05)
+    logits.backward(dlogits)
+
+    p = 0.1
+    drops = {"input": {}, "proj": {}, "attn": {}}
+    for m, name in enumerate(names):
+        drops["input"][name] = ops.dropout_mask(expect_seed, 0, 0, m, B, plan.dims[m], p).cpu()
+        drops["proj"][name] = ops.dropout_mask(expect_seed, 0, 1, m, B, H, p).cpu()
+    for q in range(M):
+        for k in range(M):
+            if q != k:
+                d = ops.dropout_mask(expect_seed, 0, 2, q * M + k, B, heads, p).cpu()
+                drops["attn"][f"{names[q]}_to_{names[k]}"] = d.reshape(B, heads, 1, 1)
+    drops["cls"] = ops.dropout_mask(expect_seed, 0, 3, 0, B, H, p).cpu()
+
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    xo = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in feats.items()}
+    ref_logits, ref_info = fusion_oracle.hybrid_fusion_forward(sd, names, heads, xo, mask.cpu(), drops=drops)
+    fusion_oracle.cross_entropy_label_smoothing(ref_logits, labels.cpu(), 0.05).backward()
+    assert _maxabs(logits, ref_logits) <= TOL
+    for key, ref in ref_info["attention_maps"].items():
+        assert torch.equal(info["attention_maps"][key].cpu(), ref), key  # {0, 1/(1-p)} per (window, head)
+    for key, prm in model.named_parameters():
+        assert _maxabs(prm.grad, sd[key].grad) <= TOL, key
+    for key in xo:
+        assert _maxabs(xs[key].grad, xo[key].grad) <= TOL, key
+
+
+def test_full_size_properties():
+    """BASELINE config 2 size (B=4096): size-independent properties on the tensor-core path."""
+    model, feats, mask, _ = seeded_case(PAMAP2, 256, 4, 25, 4096, seed=9, device="cuda")
+    model.precision = "bf16"
+    model.eval()
+    with torch.no_grad():
+        logits, info = model(feats, mask, return_attention=True)
+        # windows are independent: any 128-aligned batch split gives bit-identical rows
+        half = model({k: v[1024:3072] for k, v in feats.items()}, mask[1024:3072])
+        assert torch.equal(half, logits[1024:3072])
+        # features of a missing modality cannot influence the result (fusion.py:370-374)
+        noisy = {k: v.clone() for k, v in feats.items()}
+        gone = mask[:, 2] == 0
+        noisy["imu_ankle"][gone] = 1e3
+        assert torch.equal(model(noisy, mask), logits)
+        fw = info["fusion_weights"]
+        assert torch.all(fw[mask == 0] == 0) and float((fw.sum(1) - 1).abs().max()) < 1e-6
+        for gate in info["attention_maps"].values():
+            assert set(torch.unique(gate).tolist()) <= {0.0, 1.0}
+        # fp32 path on the same weights: the two precisions agree to bf16 tolerance
+        model.precision = "fp32"
+        assert _maxabs(model(feats, mask), logits) <= TOL
+
+
+def test_engine_bf16_tracks_fp32_engine():
+    """Three optimizer steps of the fused train step (graph-captured) in bf16 follow the fp32 engine."""
+    pkg = load_pkg()
+    engine = importlib.import_module(pkg.__name__ + ".engine")
+    losses = {}
+    params = {}
+    for prec in ("fp32", "bf16"):
+        model, feats, mask, labels = seeded_case(PAMAP2, 256, 4, 25, 512, seed=21, device="cuda")
+        eng = engine.FusionEngine(model, 512, precision=prec, seed=5, use_graph=True)
+        eng.p = 0.0  # identical arithmetic up to precision
+        out = []
+        for _ in range(3):
+            out.append(float(eng.train_step(feats, mask, labels).item()))
+        losses[prec] = out
+        params[prec] = eng.arena.clone()
+    assert losses["bf16"][-1] < losses["bf16"][0]
+    for a, b in zip(losses["fp32"], losses["bf16"]):
+        assert abs(a - b) <= 2e-2, (losses,)
+    assert float((params["fp32"] - params["bf16"]).abs().max()) <= 6.1e-3  # 3 Adam steps of lr 1e-3: sign flips of ~0 grads
