@@ -662,7 +662,7 @@ int fusion_bf16_forward(const Layout& L, const msf_fusion_call* c, cudaStream_t 
     if ((rc = tb.flush())) return rc;
   }
   {  // F6: logits = Hr W2^T + b2 (fp32 out)
-    const int bnC = L.C <= 32 ? 32 : block_n_for(L.C);
+    const int bnC = L.C <= 32 ? 32 : (L.C > 64 ? 128 : 64);  // fp32 output: at most 128 columns per tile
     TcBuilder tb(false, bnC, drop, st);
     TcProblem p = tc_blank_problem();
     p.seg[0].a_map = (short)tb.add_map(ws.Hr, B, H, H, 1, 0, TC_BLOCK_M);
@@ -798,7 +798,7 @@ int fusion_bf16_backward(const Layout& L, const msf_fusion_call* c, cudaStream_t
   {  // B9a: dx_m = (dZ_m Wp_m) * mask_m * drop0   (fp32 out, only where requested)
     for (int m = 0; m < M; ++m) {
       if (!c->grad_x[m]) continue;
-      const int bnD = block_n_for(L.D[m]);
+      const int bnD = L.D[m] > 64 ? 128 : 64;  // fp32 output: tiles of at most 128 columns
       TcBuilder tb(false, bnD, drop, st);
       TcProblem p = tc_blank_problem();
       p.seg[0].a_map = (short)tb.add_map(ws.dZ + (long long)m * BH, B, H, H, 1, 0, TC_BLOCK_M);

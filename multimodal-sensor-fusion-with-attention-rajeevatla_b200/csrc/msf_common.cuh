@@ -118,25 +118,40 @@ __device__ __forceinline__ DropCfg resolve_drop(DropCfg d) {
   return d;
 }
 
-// Four multipliers for elements (row, col4*4 .. col4*4+3) of a dropout site.
-__host__ __device__ __forceinline__ void drop4(const DropCfg& d, int site, int sub, int64_t row,
-                                               int col4, float (&out)[4]) {
-  uint32_t c[4] = {(uint32_t)row, (uint32_t)col4, ((uint32_t)site << 24) | (uint32_t)sub,
+// Eight multipliers for elements (row, col8*8 .. col8*8+7) of a dropout site: one
+// Philox4x32-10 call yields 8 x 16-bit uniforms; an element is kept when its
+// uniform u16 >= round(p * 65536) (keep probability 1 - p to within 2^-16).
+__host__ __device__ __forceinline__ void drop8(const DropCfg& d, int site, int sub, int64_t row,
+                                               int col8, float (&out)[8]) {
+  uint32_t c[4] = {(uint32_t)row, (uint32_t)col8, ((uint32_t)site << 24) | (uint32_t)sub,
                    (uint32_t)d.offset};  // rows < 2^32
   philox4x32_10(c, (uint32_t)d.seed, (uint32_t)(d.seed >> 32) ^ (uint32_t)(d.offset >> 32));
+  const uint32_t thr = (uint32_t)(d.p * 65536.0f + 0.5f);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float u = (float)(c[i] >> 8) * (1.0f / 16777216.0f);  // [0,1), 24 bits
-    out[i] = (u >= d.p) ? d.scale : 0.0f;
+    out[2 * i] = ((c[i] & 0xffffu) >= thr) ? d.scale : 0.0f;
+    out[2 * i + 1] = ((c[i] >> 16) >= thr) ? d.scale : 0.0f;
   }
+}
+
+// Four multipliers for elements (row, col4*4 .. col4*4+3): one half of a drop8 group.
+__host__ __device__ __forceinline__ void drop4(const DropCfg& d, int site, int sub, int64_t row,
+                                               int col4, float (&out)[4]) {
+  float v[8];
+  drop8(d, site, sub, row, col4 >> 1, v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) out[i] = (col4 & 1) ? v[4 + i] : v[i];
 }
 
 // Single multiplier for element (row, col).
 __host__ __device__ __forceinline__ float drop1(const DropCfg& d, int site, int sub, int64_t row, int col) {
   if (!d.active) return 1.0f;
-  float v[4];
-  drop4(d, site, sub, row, col >> 2, v);
-  return v[col & 3];
+  float v[8];
+  drop8(d, site, sub, row, col >> 3, v);
+  float r = v[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) r = ((col & 7) == i) ? v[i] : r;
+  return r;
 }
 
 enum { SITE_INPUT = 0, SITE_PROJ = 1, SITE_ATTN = 2, SITE_CLS = 3 };

@@ -11,6 +11,8 @@
 // instead of hanging the GPU.
 #include "tc_gemm.cuh"
 
+#include <stdlib.h>
+
 namespace msf {
 
 namespace {
@@ -99,6 +101,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// issue only: the registers are not valid until tmem_wait16() on the same array
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// waits for every outstanding tcgen05.ld of this thread; the "+r" operands make later uses of r depend on it
+__device__ __forceinline__ void tmem_wait16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+
 // ---------------------------------------------------------------------------
 // descriptors
 // ---------------------------------------------------------------------------
@@ -154,7 +175,7 @@ __device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float
 // Everything an epilogue thread needs about its tile, copied out of the kernel
 // parameters once per tile so the per-element code touches registers only.
 struct EpiTile {
-  int epi, M, N, nseg, c_bf16, head_dim, heads, site, sub;
+  int epi, M, N, nseg, c_bf16, head_dim, heads, site, sub, dbg;
   float scale;
   void* C;
   long long ldc;
@@ -166,168 +187,239 @@ struct EpiTile {
   const float* gate_in;
 };
 
-__device__ __forceinline__ void load_row32(const __nv_bfloat16* src, bool vec, int ncols, float (&out)[32]) {
-  if (vec) {
+// 16 consecutive bf16 of one row, raw (two 16-byte loads) or zero when out of range.
+struct Raw16 {
+  uint4 lo, hi;
+};
+__device__ __forceinline__ Raw16 load_raw16(const __nv_bfloat16* row_ptr, int col, int n_cols, bool row_ok, bool vec_ok) {
+  Raw16 r;
+  r.lo = make_uint4(0u, 0u, 0u, 0u);
+  r.hi = r.lo;
+  if (!row_ok || col >= n_cols) return r;
+  const __nv_bfloat16* src = row_ptr + col;
+  if (vec_ok && col + 16 <= n_cols) {
+    r.lo = __ldg(reinterpret_cast<const uint4*>(src));
+    r.hi = __ldg(reinterpret_cast<const uint4*>(src) + 1);
+  } else {  // ragged edge or unaligned rows
+    unsigned short h[16];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(src) + q);
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    for (int j = 0; j < 16; ++j) h[j] = (col + j < n_cols) ? __bfloat16_as_ushort(src[j]) : (unsigned short)0;
+    r.lo = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+    r.hi = make_uint4(h[8] | (h[9] << 16), h[10] | (h[11] << 16), h[12] | (h[13] << 16), h[14] | (h[15] << 16));
+  }
+  return r;
+}
+__device__ __forceinline__ void unpack16(const Raw16& r, float (&out)[16]) {
+  const uint32_t w[8] = {r.lo.x, r.lo.y, r.lo.z, r.lo.w, r.hi.x, r.hi.y, r.hi.z, r.hi.w};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = __bfloat1622float2(h[e]);
-        out[q * 8 + 2 * e] = f.x;
-        out[q * 8 + 2 * e + 1] = f.y;
-      }
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) out[j] = (j < ncols) ? bf2f(src[j]) : 0.0f;
+  for (int e = 0; e < 8; ++e) {
+    out[2 * e] = __uint_as_float(w[e] << 16);
+    out[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
   }
 }
 
-// One chunk: 32 consecutive columns [col0, col0+32) of output row `row`.
-// bias_lane: sum of the segment biases for column col0 + lane (0 beyond N).
+// Gate of one (row, column) when heads are narrower than a 16-column group.
+__device__ __noinline__ float column_gate(bool value_gate, const DropCfg& drop, int sub, int head_dim, int heads,
+                                          float* gate_out, const float* gate_in, int row, bool row_ok, int col,
+                                          bool col_ok, float mrow) {
+  const int head = col / head_dim;
+  if (!value_gate) return (row_ok && head < heads) ? __ldg(gate_in + (long long)row * heads + head) : 0.0f;
+  float gate = (mrow != 0.0f) ? 1.0f : 0.0f;
+  if (drop.active && head < heads) gate *= drop1(drop, SITE_ATTN, sub, row, head);
+  if (col == head * head_dim && col_ok && gate_out != nullptr && row_ok && head < heads)
+    gate_out[(long long)row * heads + head] = gate;
+  return gate;
+}
+
+// Everything a warp does for one output tile: its 16-column groups of one
+// 32-row slab.  Kept as a rolled loop (an unrolled, branchy epilogue thrashed
+// the instruction cache: ncu stall_no_inst), all per-tile state in registers,
+// and the auxiliary rows of the NEXT group are fetched before the current
+// group is processed so their L2 latency overlaps the arithmetic.
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const EpiTile& T, const DropCfg& drop, int row, bool row_ok, int col0,
-                                               const uint32_t (&acc)[32], float bias_lane, float mrow) {
-  const int ncols = min(32, T.N - col0);
-  const bool full = ncols == 32;
-  float v[32];
+__device__ __forceinline__ void epilogue_tile(const EpiTile T, const float* bias_s, const DropCfg& drop,
+                                              uint32_t tmem_acc, uint32_t tfull, uint32_t tfull_parity, int row,
+                                              float mrow, int n0, int ncols, int col_begin, int col_end, bool has_acc,
+                                              unsigned char* stage, int stage_pitch, int row0, int lane) {
+  constexpr bool kBias = EPI == TC_EPI_STORE || EPI == TC_EPI_BIAS_RELU_DROP || EPI == TC_EPI_VALUE_GATE ||
+                         EPI == TC_EPI_OUT_MEAN;
+  constexpr bool kAux = EPI == TC_EPI_OUT_MEAN || EPI == TC_EPI_RELU_GRAD || EPI == TC_EPI_ADD_RELU_GRAD;
+  constexpr bool kAux2 = EPI == TC_EPI_ADD_RELU_GRAD;
+  constexpr bool kGate = EPI == TC_EPI_VALUE_GATE || EPI == TC_EPI_GATE_MUL;
+  constexpr bool kDrop = EPI == TC_EPI_BIAS_RELU_DROP || EPI == TC_EPI_DX;
 
-  float aux[32], aux2[32];
-  if (EPI == TC_EPI_OUT_MEAN || EPI == TC_EPI_RELU_GRAD || EPI == TC_EPI_ADD_RELU_GRAD) {
-    if (row_ok) {
-      const __nv_bfloat16* src = T.aux + (long long)row * T.ld_aux + col0;
-      load_row32(src, full && ((reinterpret_cast<uintptr_t>(src) & 15) == 0), ncols, aux);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) aux[j] = 0.0f;
-    }
-  }
-  if (EPI == TC_EPI_ADD_RELU_GRAD) {
-    if (row_ok) {
-      const __nv_bfloat16* src = T.aux2 + (long long)row * T.ld_aux2 + col0;
-      load_row32(src, full && ((reinterpret_cast<uintptr_t>(src) & 15) == 0), ncols, aux2);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) aux2[j] = 0.0f;
-    }
-  }
+  const bool row_ok = row < T.M;
+  const __nv_bfloat16* aux_row = kAux ? T.aux + (long long)row * T.ld_aux : nullptr;
+  const __nv_bfloat16* aux2_row = kAux2 ? T.aux2 + (long long)row * T.ld_aux2 : nullptr;
+  const bool aux_vec = kAux && ((reinterpret_cast<uintptr_t>(T.aux) & 15) == 0) && ((T.ld_aux & 7) == 0);
+  const bool aux2_vec = kAux2 && ((reinterpret_cast<uintptr_t>(T.aux2) & 15) == 0) && ((T.ld_aux2 & 7) == 0);
+  const bool c_vec = ((reinterpret_cast<uintptr_t>(T.C) & 15) == 0) && ((T.ldc & (T.c_bf16 ? 7 : 3)) == 0);
+  const float inv_scale = 1.0f / T.scale;
+  (void)inv_scale;
 
-  // per-(row, head) gate: heads are runs of head_dim columns
-  int head = 0, rem = 0;
-  float gate = 0.0f;
-  if (EPI == TC_EPI_VALUE_GATE || EPI == TC_EPI_GATE_MUL) {
-    head = col0 / T.head_dim;
-    rem = col0 - head * T.head_dim;
-    if (rem != 0) {  // chunk starts inside a head: fetch its gate (already recorded by the owner of its first column)
-      if (EPI == TC_EPI_VALUE_GATE) {
-        gate = (mrow != 0.0f) ? 1.0f : 0.0f;
-        if (drop.active && head < T.heads) gate *= drop1(drop, SITE_ATTN, T.sub, row, head);
+  // this warp owns tile columns [col_begin, col_end) (a contiguous range, so its rows leave as long runs);
+  // group g covers 16 of them
+  const int my_end = min(ncols, col_end);
+  auto group_col = [&](int g) { return col_begin + g * 16; };
+  const int esize = T.c_bf16 ? 2 : 4;
+  unsigned char* my_row = stage + lane * stage_pitch;
+
+  // everything that can be fetched before the accumulator is ready is fetched now
+  Raw16 nxt_aux, nxt_aux2;
+  if (kAux) nxt_aux = load_raw16(aux_row, n0 + group_col(0), T.N, row_ok && group_col(0) < my_end, aux_vec);
+  if (kAux2) nxt_aux2 = load_raw16(aux2_row, n0 + group_col(0), T.N, row_ok && group_col(0) < my_end, aux2_vec);
+
+  mbar_wait(tfull, tfull_parity);
+  tc_fence_after();
+
+  int cur_head = -1;
+  float cur_gate = 0.0f;
+#pragma unroll 1
+  for (int g = 0;; ++g) {
+    const int c = group_col(g);
+    if (c >= my_end) break;
+    const int col0 = n0 + c;
+    const int gcols = min(16, T.N - col0);
+    const int cn = group_col(g + 1);
+
+    uint32_t acc[16];
+    if (has_acc) {
+      if (!(T.dbg & 2)) {
+        tmem_ld16_issue(tmem_acc + (uint32_t)c, acc);
+        tmem_wait16(acc);
       } else {
-        gate = (row_ok && head < T.heads) ? __ldg(T.gate_in + (long long)row * T.heads + head) : 0.0f;
+        for (int j = 0; j < 16; ++j) acc[j] = 0u;
       }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = 0u;  // epilogue-only problem: nothing was accumulated
     }
-  }
 
-#pragma unroll
-  for (int g4 = 0; g4 < 8; ++g4) {
-    float dm[4] = {1.f, 1.f, 1.f, 1.f};
-    if (EPI == TC_EPI_BIAS_RELU_DROP || EPI == TC_EPI_DX) {
-      if (drop.active && row_ok && g4 * 4 < ncols) drop4(drop, T.site, T.sub, row, (col0 >> 2) + g4, dm);
+    float aux[16], aux2[16];
+    if (kAux) {
+      unpack16(nxt_aux, aux);
+      nxt_aux = load_raw16(aux_row, n0 + cn, T.N, row_ok && cn < my_end, aux_vec);
     }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int j = g4 * 4 + e;
-      const float a = __uint_as_float(acc[j]);
-      float bias = 0.0f;
-      if (EPI == TC_EPI_STORE || EPI == TC_EPI_BIAS_RELU_DROP || EPI == TC_EPI_VALUE_GATE || EPI == TC_EPI_OUT_MEAN)
-        bias = __shfl_sync(0xffffffffu, bias_lane, j);
-      if (EPI == TC_EPI_VALUE_GATE || EPI == TC_EPI_GATE_MUL) {
-        if (rem == 0) {  // first column of a head
-          if (EPI == TC_EPI_VALUE_GATE) {
-            gate = (mrow != 0.0f) ? 1.0f : 0.0f;
-            if (drop.active && head < T.heads) gate *= drop1(drop, SITE_ATTN, T.sub, row, head);
-            if (T.gate_out != nullptr && row_ok && head < T.heads && j < ncols)
-              T.gate_out[(long long)row * T.heads + head] = gate;
-          } else {
-            gate = (row_ok && head < T.heads) ? __ldg(T.gate_in + (long long)row * T.heads + head) : 0.0f;
-          }
-        }
-        if (++rem == T.head_dim) {
-          rem = 0;
-          ++head;
+    if (kAux2) {
+      unpack16(nxt_aux2, aux2);
+      nxt_aux2 = load_raw16(aux2_row, n0 + cn, T.N, row_ok && cn < my_end, aux2_vec);
+    }
+
+    // per-(row, head) gate; the group lies inside one head when head_dim is a multiple of 16
+    const bool one_head = kGate && (T.head_dim & 15) == 0;
+    if (kGate && one_head) {
+      const int head = col0 / T.head_dim;
+      if (head != cur_head) {
+        cur_head = head;
+        if (EPI == TC_EPI_VALUE_GATE) {
+          cur_gate = (mrow != 0.0f) ? 1.0f : 0.0f;
+          if (drop.active && head < T.heads) cur_gate *= drop1(drop, SITE_ATTN, T.sub, row, head);
+          if (col0 == head * T.head_dim && T.gate_out != nullptr && row_ok && head < T.heads)
+            T.gate_out[(long long)row * T.heads + head] = cur_gate;
+        } else {
+          cur_gate = (row_ok && head < T.heads) ? __ldg(T.gate_in + (long long)row * T.heads + head) : 0.0f;
         }
       }
+    }
+
+    float dm[16];
+    if (kDrop) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) dm[j] = 1.0f;
+      if (drop.active && row_ok) {
+        float d8[8];
+        drop8(drop, T.site, T.sub, row, col0 >> 3, d8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dm[j] = d8[j];
+        if (gcols > 8) {
+          drop8(drop, T.site, T.sub, row, (col0 >> 3) + 1, d8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dm[8 + j] = d8[j];
+        }
+      }
+    }
+
+    float bias[16];
+    if (kBias) {  // broadcast reads of the tile's summed bias row staged in shared memory
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c + 4 * q);
+        bias[4 * q] = b4.x; bias[4 * q + 1] = b4.y; bias[4 * q + 2] = b4.z; bias[4 * q + 3] = b4.w;
+      }
+    }
+
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float a = __uint_as_float(acc[j]);
+      const float b = kBias ? bias[j] : 0.0f;
+      float gate = cur_gate;
+      if (kGate && !one_head)  // narrow / unaligned heads: per-column gate (rare shapes, out of line)
+        gate = column_gate(EPI == TC_EPI_VALUE_GATE, drop, T.sub, T.head_dim, T.heads, T.gate_out, T.gate_in, row,
+                           row_ok, col0 + j, j < gcols, mrow);
       float r;
-      if (EPI == TC_EPI_STORE) r = fmaf(a, T.scale, bias);
-      else if (EPI == TC_EPI_BIAS_RELU_DROP) r = fmaxf(a + bias, 0.0f) * dm[e];
-      else if (EPI == TC_EPI_VALUE_GATE) r = (a + bias) * gate;
-      else if (EPI == TC_EPI_OUT_MEAN) r = (a + bias + aux[j]) / T.scale * mrow;
+      if (EPI == TC_EPI_STORE) r = fmaf(a, T.scale, b);
+      else if (EPI == TC_EPI_BIAS_RELU_DROP) r = fmaxf(a + b, 0.0f) * dm[j];
+      else if (EPI == TC_EPI_VALUE_GATE) r = (a + b) * gate;
+      else if (EPI == TC_EPI_OUT_MEAN) r = (a + b + aux[j]) * inv_scale * mrow;
       else if (EPI == TC_EPI_RELU_GRAD) r = a * (aux[j] > 0.0f ? T.scale : 0.0f);
       else if (EPI == TC_EPI_GATE_MUL) r = a * gate;
       else if (EPI == TC_EPI_ADD_RELU_GRAD) r = (a + aux[j]) * (aux2[j] > 0.0f ? T.scale : 0.0f);
-      else r = a * mrow * dm[e];  // TC_EPI_DX
+      else r = a * mrow * dm[j];  // TC_EPI_DX
       v[j] = r;
     }
-  }
 
-  if (!row_ok) return;
-  if (T.c_bf16) {
-    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(T.C) + (long long)row * T.ldc + col0;
-    if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+    // results go to this warp's shared-memory staging rows first (row pitch padded by 16 B: conflict-free)
+    {
+      unsigned char* dst = my_row + (c - col_begin) * esize;
+      if (T.c_bf16) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint4 pk;
-        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+        for (int q = 0; q < 2; ++q) {
+          uint4 pk;
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
-        reinterpret_cast<uint4*>(dst)[q] = pk;
-      }
-    } else {
+          for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
+          reinterpret_cast<uint4*>(dst)[q] = pk;
+        }
+      } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncols) dst[j] = __float2bfloat16_rn(v[j]);
-    }
-  } else {
-    float* dst = reinterpret_cast<float*>(T.C) + (long long)row * T.ldc + col0;
-    if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncols) dst[j] = v[j];
-    }
-  }
-}
-
-// All chunks this warp owns in one tile: chunk c (32 columns) belongs to column group c % TC_EPI_COLGROUPS.
-template <int EPI>
-__device__ __forceinline__ void epilogue_tile(const EpiTile& T, const float* const (&bias)[TC_MAX_SEG], const DropCfg& drop,
-                                              uint32_t tmem_acc, int row, float mrow, int n0, int ncols, int colgroup,
-                                              bool has_acc, int lane) {
-  const bool row_ok = row < T.M;
-  for (int c = colgroup * 32; c < ncols; c += 32 * TC_EPI_COLGROUPS) {
-    uint32_t acc[32];
-    if (has_acc) {
-      tmem_ld32(tmem_acc + (uint32_t)c, acc);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = 0u;  // epilogue-only problem: nothing was accumulated
-    }
-    float bias_lane = 0.0f;
-    if (EPI == TC_EPI_STORE || EPI == TC_EPI_BIAS_RELU_DROP || EPI == TC_EPI_VALUE_GATE || EPI == TC_EPI_OUT_MEAN) {
-      const int col = n0 + c + lane;
-      if (col < T.N) {
-#pragma unroll
-        for (int s = 0; s < TC_MAX_SEG; ++s)
-          if (s < T.nseg && bias[s] != nullptr) bias_lane += __ldg(bias[s] + col);
+        for (int q = 0; q < 4; ++q)
+          reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
       }
     }
-    epilogue_chunk<EPI>(T, drop, row, row_ok, n0 + c, acc, bias_lane, mrow);
   }
+
+  // flush: the warp walks its 32 x (col_end - col_begin) block row by row, 16 bytes per lane, so every
+  // store instruction writes long contiguous runs (per-thread row stores were request-rate bound)
+  __syncwarp();
+  if (!(T.dbg & 1) && col_begin < my_end) {
+    const int epc = 16 / esize;                               // elements per 16-byte chunk
+    const int nch = ((my_end - col_begin) * esize + 15) >> 4;   // chunks per row that hold data
+    const int total = 32 * nch;
+#pragma unroll 1
+    for (int f = lane; f < total; f += 32) {
+      const int r = f / nch, ch = f - r * nch;
+      const int grow = row0 + r;
+      if (grow >= T.M) continue;
+      const uint4 val = *reinterpret_cast<const uint4*>(stage + r * stage_pitch + ch * 16);
+      const int gcol = n0 + col_begin + ch * epc;
+      unsigned char* gdst = reinterpret_cast<unsigned char*>(T.C) + ((long long)grow * T.ldc + gcol) * esize;
+      if (c_vec && gcol + epc <= T.N) {
+        *reinterpret_cast<uint4*>(gdst) = val;
+      } else if (T.c_bf16) {
+        const unsigned short* hv = reinterpret_cast<const unsigned short*>(&val);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (gcol + e < T.N) reinterpret_cast<unsigned short*>(gdst)[e] = hv[e];
+      } else {
+        const float* fv = reinterpret_cast<const float*>(&val);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (gcol + e < T.N) reinterpret_cast<float*>(gdst)[e] = fv[e];
+      }
+    }
+  }
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------------------
@@ -340,16 +432,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t BN = (uint32_t)L.block_n;
   const uint32_t B_STAGE = b_stage_bytes(L.block_n);
+  const int STAGES = L.stages;
   const uint32_t a_base = smem_base;
-  const uint32_t b_base = a_base + TC_STAGES * A_STAGE_BYTES;
-  const uint32_t bar_base = b_base + TC_STAGES * B_STAGE;
+  const uint32_t b_base = a_base + STAGES * A_STAGE_BYTES;
+  const uint32_t stg_base = b_base + STAGES * B_STAGE;          // epilogue staging, TC_EPI_WARPS x 32 rows
+  const uint32_t bar_base = stg_base + (uint32_t)(TC_EPI_WARPS * 32 * L.stage_pitch);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * TC_STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * TC_STAGES + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 4);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (TC_MAX_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * TC_MAX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * TC_MAX_STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * TC_MAX_STAGES + 4);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  // two summed-bias rows (one per accumulator buffer), 16-byte aligned
+  float* bias_smem = reinterpret_cast<float*>(smem_raw + (bar_base + 8u * (2 * TC_MAX_STAGES + 6) - smem_u32(smem_raw)));
+  unsigned char* stage_smem = smem_raw + (stg_base - smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tmem_cols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
@@ -358,7 +455,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     for (int i = 0; i < L.nmaps; ++i) tma_prefetch_desc(&L.maps[i]);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
@@ -407,7 +504,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
               for (int j = 0; j < (int)BN / 64; ++j)
                 tma_load_3d(b_dst + j * 8192u, bmap, t.n0 + 64 * j, k0, b_z, full_bar(stage));
             }
-            if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
       }
@@ -442,7 +539,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
             tc_mma_bf16(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
           tc_commit(empty_bar(stage));  // stage reusable once these MMAs have read it
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         tc_commit(tfull_bar(acc));  // accumulator complete
       }
@@ -451,7 +548,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     // =========================== epilogue ===============================
     const DropCfg drop = resolve_drop(L.drop);
     const int lq = warp & 3;               // TMEM lane quarter this warp may read
-    const int colgroup = (warp - 4) >> 2;  // which 32-column chunks it owns
+    const int colgroup = (warp - 4) >> 2;  // which contiguous column range of the tile it owns
+    const int cols_per_warp = BN >= 64 ? (int)BN / TC_EPI_COLGROUPS : (int)BN;
+    const int col_begin = colgroup * cols_per_warp;
+    const int col_end = (BN >= 64 || colgroup == 0) ? col_begin + cols_per_warp : col_begin;
+    unsigned char* stage = stage_smem + (warp - 4) * 32 * L.stage_pitch;
+    const int et = threadIdx.x - 128;      // 0 .. 32*TC_EPI_WARPS-1
     int it = 0;
     for (int tile = blockIdx.x; tile < L.total_tiles; tile += gridDim.x, ++it) {
       const TileCoord t = locate(L, tile);
@@ -460,29 +562,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       T.epi = P.epi; T.M = P.M; T.N = P.N; T.nseg = P.nseg; T.c_bf16 = P.c_bf16;
       T.head_dim = P.head_dim; T.heads = P.heads; T.site = P.site; T.sub = P.sub; T.scale = P.scale;
       T.C = P.C; T.ldc = P.ldc; T.aux = P.aux; T.ld_aux = P.ld_aux; T.aux2 = P.aux2; T.ld_aux2 = P.ld_aux2;
-      T.gate_out = P.gate_out; T.gate_in = P.gate_in;
-      const float* bias[TC_MAX_SEG];
-#pragma unroll
-      for (int s = 0; s < TC_MAX_SEG; ++s) bias[s] = P.bias[s];
+      T.gate_out = P.gate_out; T.gate_in = P.gate_in; T.dbg = L.dbg;
       const bool has_acc = P.K > 0;
+      const int acc = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
       const int row = t.m0 + lq * 32 + lane;
       const float mrow = (P.mask != nullptr && row < T.M) ? __ldg(P.mask + (long long)row * P.mask_ld + P.mask_col) : 1.0f;
       const int ncols = min((int)BN, T.N - t.n0);
-      const int acc = it & 1;
-      const uint32_t use = (uint32_t)(it >> 1);
-      mbar_wait(tfull_bar(acc), use & 1u);
-      tc_fence_after();
+      // summed segment biases of this tile's columns -> shared memory (double-buffered by accumulator parity)
+      float* bias_s = bias_smem + acc * 256;
+      for (int e = et; e < (int)BN; e += 32 * TC_EPI_WARPS) {
+        float bsum = 0.0f;
+        const int col = t.n0 + e;
+        if (col < T.N) {
+#pragma unroll
+          for (int s = 0; s < TC_MAX_SEG; ++s)
+            if (s < T.nseg && P.bias[s] != nullptr) bsum += __ldg(P.bias[s] + col);
+        }
+        bias_s[e] = bsum;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");  // epilogue warps only
       const uint32_t tmem_acc = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)acc * BN;
+      const uint32_t tf = tfull_bar(acc), tp = use & 1u;
       switch (T.epi) {
         default:
-        case TC_EPI_STORE: epilogue_tile<TC_EPI_STORE>(T, bias, drop, tmem_acc, row, mrow, t.n0, ncols, colgroup, has_acc, lane); break;
-        case TC_EPI_BIAS_RELU_DROP: epilogue_tile<TC_EPI_BIAS_RELU_DROP>(T, bias, drop, tmem_acc, row, mrow, t.n0, ncols, colgroup, has_acc, lane); break;
-        case TC_EPI_VALUE_GATE: epilogue_tile<TC_EPI_VALUE_GATE>(T, bias, drop, tmem_acc, row, mrow, t.n0, ncols, colgroup, has_acc, lane); break;
-        case TC_EPI_OUT_MEAN: epilogue_tile<TC_EPI_OUT_MEAN>(T, bias, drop, tmem_acc, row, mrow, t.n0, ncols, colgroup, has_acc, lane); break;
-        case TC_EPI_RELU_GRAD: epilogue_tile<TC_EPI_RELU_GRAD>(T, bias, drop, tmem_acc, row, mrow, t.n0, ncols, colgroup, has_acc, lane); break;
-        case TC_EPI_GATE_MUL: epilogue_tile<TC_EPI_GATE_MUL>(T, bias, drop, tmem_acc, row, mrow, t.n0, ncols, colgroup, has_acc, lane); break;
-        case TC_EPI_ADD_RELU_GRAD: epilogue_tile<TC_EPI_ADD_RELU_GRAD>(T, bias, drop, tmem_acc, row, mrow, t.n0, ncols, colgroup, has_acc, lane); break;
-        case TC_EPI_DX: epilogue_tile<TC_EPI_DX>(T, bias, drop, tmem_acc, row, mrow, t.n0, ncols, colgroup, has_acc, lane); break;
+        case TC_EPI_STORE: epilogue_tile<TC_EPI_STORE>(T, bias_s, drop, tmem_acc, tf, tp, row, mrow, t.n0, ncols, col_begin, col_end, has_acc, stage, L.stage_pitch, t.m0 + lq * 32, lane); break;
+        case TC_EPI_BIAS_RELU_DROP: epilogue_tile<TC_EPI_BIAS_RELU_DROP>(T, bias_s, drop, tmem_acc, tf, tp, row, mrow, t.n0, ncols, col_begin, col_end, has_acc, stage, L.stage_pitch, t.m0 + lq * 32, lane); break;
+        case TC_EPI_VALUE_GATE: epilogue_tile<TC_EPI_VALUE_GATE>(T, bias_s, drop, tmem_acc, tf, tp, row, mrow, t.n0, ncols, col_begin, col_end, has_acc, stage, L.stage_pitch, t.m0 + lq * 32, lane); break;
+        case TC_EPI_OUT_MEAN: epilogue_tile<TC_EPI_OUT_MEAN>(T, bias_s, drop, tmem_acc, tf, tp, row, mrow, t.n0, ncols, col_begin, col_end, has_acc, stage, L.stage_pitch, t.m0 + lq * 32, lane); break;
+        case TC_EPI_RELU_GRAD: epilogue_tile<TC_EPI_RELU_GRAD>(T, bias_s, drop, tmem_acc, tf, tp, row, mrow, t.n0, ncols, col_begin, col_end, has_acc, stage, L.stage_pitch, t.m0 + lq * 32, lane); break;
+        case TC_EPI_GATE_MUL: epilogue_tile<TC_EPI_GATE_MUL>(T, bias_s, drop, tmem_acc, tf, tp, row, mrow, t.n0, ncols, col_begin, col_end, has_acc, stage, L.stage_pitch, t.m0 + lq * 32, lane); break;
+        case TC_EPI_ADD_RELU_GRAD: epilogue_tile<TC_EPI_ADD_RELU_GRAD>(T, bias_s, drop, tmem_acc, tf, tp, row, mrow, t.n0, ncols, col_begin, col_end, has_acc, stage, L.stage_pitch, t.m0 + lq * 32, lane); break;
+        case TC_EPI_DX: epilogue_tile<TC_EPI_DX>(T, bias_s, drop, tmem_acc, tf, tp, row, mrow, t.n0, ncols, col_begin, col_end, has_acc, stage, L.stage_pitch, t.m0 + lq * 32, lane); break;
       }
       tc_fence_before();
       __syncwarp();
@@ -498,9 +609,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   }
 }
 
-size_t tc_smem_bytes(int block_n) {
-  return 1024 + (size_t)TC_STAGES * (A_STAGE_BYTES + b_stage_bytes(block_n)) + 8 * (2 * TC_STAGES + 4) + 16;
-}
+constexpr size_t TC_SMEM_LIMIT = 232448;  // 227 KiB per CTA on sm_100
+
+size_t tc_fixed_smem_bytes() { return 1024 + 8 * (2 * TC_MAX_STAGES + 6) + 2 * 256 * 4; }
 
 }  // namespace
 
@@ -601,13 +712,26 @@ int TcBuilder::flush() {
   // fill unused descriptor slots with a valid descriptor (they are prefetched)
   for (int i = nmaps; i < TC_MAX_MAPS; ++i) L.maps[i] = L.maps[0];
   L.nmaps = nmaps;
+  { const char* e = getenv("MSF_TC_DEBUG"); L.dbg = e ? atoi(e) : 0; }
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
     MSF_CHECK_CUDA(cudaGetDevice(&dev));
     MSF_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const size_t smem = tc_smem_bytes(L.block_n);
+  // epilogue staging: each epilogue warp stages 32 rows x its column range in the widest output type of the launch
+  int esize = 2;
+  for (int i = 0; i < L.count; ++i)
+    if (!L.p[i].c_bf16) esize = 4;
+  const int cols_per_warp = L.block_n >= 64 ? L.block_n / TC_EPI_COLGROUPS : L.block_n;
+  L.stage_pitch = cols_per_warp * esize + 16;
+  const size_t staging = (size_t)TC_EPI_WARPS * 32 * L.stage_pitch;
+  const size_t per_stage = A_STAGE_BYTES + b_stage_bytes(L.block_n);
+  int stages = (int)((TC_SMEM_LIMIT - tc_fixed_smem_bytes() - staging) / per_stage);
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  MSF_REQUIRE(stages >= 2, "tc_gemm: block_n %d with fp32 output does not leave room for the operand pipeline", L.block_n);
+  L.stages = stages;
+  const size_t smem = tc_fixed_smem_bytes() + staging + (size_t)stages * per_stage;
   const int grid = L.total_tiles < sms ? L.total_tiles : sms;
   if (mn_major) {
     MSF_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -632,7 +756,8 @@ extern "C" int msf_gemm_bf16(const void* a, const void* b, void* d, int32_t d_is
                              const float* bias, int32_t relu, void* stream) {
   MSF_REQUIRE(a && b && d && m >= 1 && n >= 1 && k >= 1, "msf_gemm_bf16: bad arguments");
   MSF_REQUIRE(m < (1ll << 31) && n < (1ll << 31) && k < (1ll << 31), "msf_gemm_bf16: dimension too large");
-  int bn = n >= 256 ? 256 : n > 128 ? 256 : n > 64 ? 128 : 64;
+  int bn = n > 128 ? 256 : n > 64 ? 128 : 64;
+  if (!d_is_bf16 && bn > 128) bn = 128;  // fp32 tiles are staged in shared memory: 128 x 128 x 4 B
   if (!mn_major && n <= 32) bn = 32;
   msf::TcBuilder tb(mn_major != 0, bn, msf::no_dropout(), (cudaStream_t)stream);
   int am, bm;

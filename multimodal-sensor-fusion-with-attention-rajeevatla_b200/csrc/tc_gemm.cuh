@@ -23,7 +23,7 @@ constexpr int TC_MAX_PROBLEMS = 40;
 constexpr int TC_MAX_MAPS = 16;
 constexpr int TC_BLOCK_M = 128;
 constexpr int TC_BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
-constexpr int TC_STAGES = 4;
+constexpr int TC_MAX_STAGES = 6;   // operand pipeline depth is chosen per launch from the shared memory left
 constexpr int TC_EPI_COLGROUPS = 2;                 // epilogue warps per TMEM lane quarter
 constexpr int TC_EPI_WARPS = 4 * TC_EPI_COLGROUPS;
 constexpr int TC_THREADS = 128 + 32 * TC_EPI_WARPS; // TMA, MMA, TMEM-alloc, spare + epilogue warps
@@ -72,6 +72,9 @@ struct TcLaunch {
   TcProblem p[TC_MAX_PROBLEMS];
   int count;
   int nmaps;
+  int stages;             // operand pipeline depth of this launch
+  int stage_pitch;        // bytes between rows of an epilogue warp's staging block
+  int dbg;                // debug switches (MSF_TC_DEBUG): 1 = skip stores, 2 = skip TMEM loads
   int total_tiles;
   int block_n;            // 32..256, multiple of 16; uniform per launch
   DropCfg drop;
