@@ -102,6 +102,12 @@ int msf_struct_sizes(int32_t* shape_bytes, int32_t* call_bytes);
 const char* msf_last_error(void);
 /* kernels launched by this library so far in this process (host-side counter) */
 uint64_t msf_launch_count(void);
+/* Per-launch timing of the tensor-core GEMM launches with CUDA events on the launching stream.
+ * enable(1) clears earlier records and starts recording, enable(0) stops.  report() synchronises the
+ * device and writes one line per launch label: "label\tlaunches\ttotal_ms\ttotal_flops\n".
+ * Must not be enabled while the stream is being captured into a CUDA graph. */
+int msf_prof_enable(int32_t on);
+int msf_prof_report(char* buf, size_t cap);
 /* sm count / compute capability of the current device; fails unless cc >= 10.0 */
 int msf_device_check(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
 

@@ -2,9 +2,39 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <string>
+#include <vector>
+
 #include "msf_common.cuh"
 
 namespace msf {
+
+namespace {
+struct ProfRecord {
+  const char* label;
+  double flops;
+  cudaEvent_t start, stop;
+};
+bool g_prof_on = false;
+std::vector<ProfRecord> g_prof;
+}  // namespace
+
+bool prof_enabled() { return g_prof_on; }
+
+void prof_begin(const char* label, double flops, cudaStream_t stream) {
+  if (!g_prof_on) return;
+  ProfRecord r;
+  r.label = label;
+  r.flops = flops;
+  if (cudaEventCreate(&r.start) != cudaSuccess || cudaEventCreate(&r.stop) != cudaSuccess) return;
+  cudaEventRecord(r.start, stream);
+  g_prof.push_back(r);
+}
+
+void prof_end(cudaStream_t stream) {
+  if (!g_prof_on || g_prof.empty()) return;
+  cudaEventRecord(g_prof.back().stop, stream);
+}
 
 static thread_local char g_err[512] = "";
 unsigned long long g_launch_count = 0;
@@ -74,6 +104,49 @@ int msf_struct_sizes(int32_t* shape_bytes, int32_t* call_bytes) {
 uint64_t msf_launch_count(void) { return msf::g_launch_count; }
 
 const char* msf_last_error(void) { return msf::g_err; }
+
+int msf_prof_enable(int32_t on) {
+  for (auto& r : msf::g_prof) {
+    cudaEventDestroy(r.start);
+    cudaEventDestroy(r.stop);
+  }
+  msf::g_prof.clear();
+  msf::g_prof_on = on != 0;
+  return MSF_OK;
+}
+
+int msf_prof_report(char* buf, size_t cap) {
+  MSF_REQUIRE(buf != nullptr && cap > 0, "msf_prof_report: no buffer");
+  MSF_CHECK_CUDA(cudaDeviceSynchronize());
+  struct Agg { std::string label; long long n; double ms, flops; };
+  std::vector<Agg> agg;
+  for (auto& r : msf::g_prof) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, r.start, r.stop) != cudaSuccess) continue;
+    Agg* a = nullptr;
+    for (auto& x : agg)
+      if (x.label == r.label) a = &x;
+    if (!a) {
+      agg.push_back(Agg{r.label, 0, 0.0, 0.0});
+      a = &agg.back();
+    }
+    a->n += 1;
+    a->ms += ms;
+    a->flops += r.flops;
+  }
+  std::string out;
+  char line[256];
+  for (auto& x : agg) {
+    snprintf(line, sizeof(line), "%s\t%lld\t%.6f\t%.0f\n", x.label.c_str(), x.n, x.ms, x.flops);
+    out += line;
+  }
+  if (out.size() + 1 > cap) {
+    msf::set_error("msf_prof_report: buffer too small (%zu needed)", out.size() + 1);
+    return MSF_E_INVALID;
+  }
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return MSF_OK;
+}
 
 int msf_device_check(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
   int dev = 0;

@@ -125,6 +125,16 @@ size_t fusion_bf16_arena_bytes(const Layout& L) { return arena_layout(L).total *
 
 static int block_n_for(int n) { return n >= 256 ? 256 : (int)align_up(n, 64); }
 
+// Tile width for a launch of `problems` GEMMs with `rows` output rows and n columns each: wide tiles
+// (fewer operand re-reads) when that already fills the 148 SMs, otherwise narrower ones so that a
+// small launch spreads over more SMs and each CTA's epilogue is shorter.
+static int block_n_fill(int n, long long rows, int problems) {
+  int bn = block_n_for(n);
+  const long long m_tiles = ceil_div(rows, TC_BLOCK_M) * problems;
+  while (bn > 64 && m_tiles * ceil_div(n, bn) < 120 && (bn / 2) % 64 == 0) bn /= 2;
+  return bn;
+}
+
 // ---------------------------------------------------------------------------
 // pack: fp32 master -> bf16 compute arena (plain and transposed copies)
 // ---------------------------------------------------------------------------
@@ -570,7 +580,7 @@ int fusion_bf16_forward(const Layout& L, const msf_fusion_call* c, cudaStream_t 
   }
 
   {  // F1: P_m = drop1(relu(xt_m Wp_m^T + bp_m))
-    TcBuilder tb(false, bnH, drop, st);
+    TcBuilder tb(false, bnH, drop, st, "F1 projections");
     for (int m = 0; m < M; ++m) {
       TcProblem p = tc_blank_problem();
       p.seg[0].a_map = (short)tb.add_map(ws.xt[m], B, L.D[m], L.D[m], 1, 0, TC_BLOCK_M);
@@ -585,7 +595,7 @@ int fusion_bf16_forward(const Layout& L, const msf_fusion_call* c, cudaStream_t 
   }
 
   if (pairs > 0) {  // F2: U_qk = g_qk * (P_k Wv_qk^T + bv_qk)
-    TcBuilder tb(false, bnH, drop, st);
+    TcBuilder tb(false, bnH, drop, st, "F2 value_proj");
     const short mapP = (short)tb.add_map(ws.P, B, H, H, M, BH, TC_BLOCK_M);
     const short mapW = (short)tb.add_map(W16 + A.wv, H, H, H, pairs, (long long)H * H, bnH);
     for (int q = 0; q < M; ++q)
@@ -609,7 +619,7 @@ int fusion_bf16_forward(const Layout& L, const msf_fusion_call* c, cudaStream_t 
   }
 
   {  // F3: agg_q = (P_q + sum_k (U_qk Wo_qk^T + bo_qk)) / cnt_q * mask_q
-    TcBuilder tb(false, bnH, drop, st);
+    TcBuilder tb(false, bnH, drop, st, "F3 out_proj+mean");
     const short mapU = (short)tb.add_map(ws.U, B, H, H, pairs > 0 ? pairs : 1, BH, TC_BLOCK_M);
     const short mapW = pairs > 0 ? (short)tb.add_map(W16 + A.wo, H, H, H, pairs, (long long)H * H, bnH) : mapU;
     for (int q = 0; q < M; ++q) {
@@ -650,10 +660,11 @@ int fusion_bf16_forward(const Layout& L, const msf_fusion_call* c, cudaStream_t 
   }
 
   {  // F5: Hr = drop3(relu(fused W1^T + b1))
-    TcBuilder tb(false, bnH, drop, st);
+    const int bn1 = block_n_fill(H, B, 1);
+    TcBuilder tb(false, bn1, drop, st, "F5 classifier.0");
     TcProblem p = tc_blank_problem();
     p.seg[0].a_map = (short)tb.add_map(ws.fused, B, H, H, 1, 0, TC_BLOCK_M);
-    p.seg[0].b_map = (short)tb.add_map(W16 + A.w1, H, H, H, 1, 0, bnH);
+    p.seg[0].b_map = (short)tb.add_map(W16 + A.w1, H, H, H, 1, 0, bn1);
     p.bias[0] = W + L.cls_b1;
     p.M = (int)B; p.N = H; p.K = H;
     p.C = ws.Hr; p.ldc = H; p.c_bf16 = 1;
@@ -663,7 +674,7 @@ int fusion_bf16_forward(const Layout& L, const msf_fusion_call* c, cudaStream_t 
   }
   {  // F6: logits = Hr W2^T + b2 (fp32 out)
     const int bnC = L.C <= 32 ? 32 : (L.C > 64 ? 128 : 64);  // fp32 output: at most 128 columns per tile
-    TcBuilder tb(false, bnC, drop, st);
+    TcBuilder tb(false, bnC, drop, st, "F6 classifier.3");
     TcProblem p = tc_blank_problem();
     p.seg[0].a_map = (short)tb.add_map(ws.Hr, B, H, H, 1, 0, TC_BLOCK_M);
     p.seg[0].b_map = (short)tb.add_map(W16 + A.w2, L.C, H, H, 1, 0, bnC);
@@ -716,11 +727,12 @@ int fusion_bf16_backward(const Layout& L, const msf_fusion_call* c, cudaStream_t
     MSF_LAUNCH_CHECK();
   }
 
+  const int bn1 = block_n_fill(H, B, 1);
   {  // B1: dH1 = (dlogits W2) * relu'(Hr) * drop3
-    TcBuilder tb(false, bnH, drop, st);
+    TcBuilder tb(false, bn1, drop, st, "B1 d classifier.3");
     TcProblem p = tc_blank_problem();
     p.seg[0].a_map = (short)tb.add_map(ws.dlog, B, Cp, Cp, 1, 0, TC_BLOCK_M);
-    p.seg[0].b_map = (short)tb.add_map(W16 + A.w2T, H, Cp, Cp, 1, 0, bnH);
+    p.seg[0].b_map = (short)tb.add_map(W16 + A.w2T, H, Cp, Cp, 1, 0, bn1);
     p.M = (int)B; p.N = H; p.K = Cp;
     p.C = ws.dH1; p.ldc = H; p.c_bf16 = 1;
     p.epi = TC_EPI_RELU_GRAD; p.scale = drop.scale; p.aux = ws.Hr; p.ld_aux = H;
@@ -728,10 +740,10 @@ int fusion_bf16_backward(const Layout& L, const msf_fusion_call* c, cudaStream_t
     if ((rc = tb.flush())) return rc;
   }
   {  // B2: dfused = dH1 W1
-    TcBuilder tb(false, bnH, drop, st);
+    TcBuilder tb(false, bn1, drop, st, "B2 d classifier.0");
     TcProblem p = tc_blank_problem();
     p.seg[0].a_map = (short)tb.add_map(ws.dH1, B, H, H, 1, 0, TC_BLOCK_M);
-    p.seg[0].b_map = (short)tb.add_map(W16 + A.w1T, H, H, H, 1, 0, bnH);
+    p.seg[0].b_map = (short)tb.add_map(W16 + A.w1T, H, H, H, 1, 0, bn1);
     p.M = (int)B; p.N = H; p.K = H;
     p.C = ws.dfused; p.ldc = H; p.c_bf16 = 1;
     p.epi = TC_EPI_STORE;
@@ -752,7 +764,7 @@ int fusion_bf16_backward(const Layout& L, const msf_fusion_call* c, cudaStream_t
     MSF_LAUNCH_CHECK();
   }
   if (pairs > 0) {  // B5: dV_qk = (dS_q Wo_qk) * g_qk
-    TcBuilder tb(false, bnH, drop, st);
+    TcBuilder tb(false, bnH, drop, st, "B5 d out_proj");
     const short mapS = (short)tb.add_map(ws.dS, B, H, H, M, BH, TC_BLOCK_M);
     const short mapW = (short)tb.add_map(W16 + A.woT, H, H, H, pairs, (long long)H * H, bnH);
     for (int q = 0; q < M; ++q)
@@ -771,7 +783,7 @@ int fusion_bf16_backward(const Layout& L, const msf_fusion_call* c, cudaStream_t
     if ((rc = tb.flush())) return rc;
   }
   {  // B7: dZ_k = (dS_k + sum_q dV_qk Wv_qk) * relu'(P_k) * drop1
-    TcBuilder tb(false, bnH, drop, st);
+    TcBuilder tb(false, bnH, drop, st, "B7 d value_proj");
     const short mapV = (short)tb.add_map(ws.dV, B, H, H, pairs > 0 ? pairs : 1, BH, TC_BLOCK_M);
     const short mapW = pairs > 0 ? (short)tb.add_map(W16 + A.wvT, H, H, H, pairs, (long long)H * H, bnH) : mapV;
     for (int k = 0; k < M; ++k) {
@@ -799,7 +811,7 @@ int fusion_bf16_backward(const Layout& L, const msf_fusion_call* c, cudaStream_t
     for (int m = 0; m < M; ++m) {
       if (!c->grad_x[m]) continue;
       const int bnD = L.D[m] > 64 ? 128 : 64;  // fp32 output: tiles of at most 128 columns
-      TcBuilder tb(false, bnD, drop, st);
+      TcBuilder tb(false, bnD, drop, st, "B9 d projections (dx)");
       TcProblem p = tc_blank_problem();
       p.seg[0].a_map = (short)tb.add_map(ws.dZ + (long long)m * BH, B, H, H, 1, 0, TC_BLOCK_M);
       p.seg[0].b_map = (short)tb.add_map(W16 + A.wpT[m], L.D[m], H, H, 1, 0, bnD);
@@ -815,7 +827,7 @@ int fusion_bf16_backward(const Layout& L, const msf_fusion_call* c, cudaStream_t
   // ---- all weight gradients: one MN-major launch, dW[out,in] = dY^T . X over the windows ----
   {
     const int bn = 128;
-    TcBuilder tb(true, bn, drop, st);
+    TcBuilder tb(true, bn, drop, st, "WG weight gradients");
     const short mapDlog = (short)tb.add_map(ws.dlog, B, Cp, Cp, 1, 0, 0);
     const short mapHr = (short)tb.add_map(ws.Hr, B, H, H, 1, 0, 0);
     const short mapDH1 = (short)tb.add_map(ws.dH1, B, H, H, 1, 0, 0);

@@ -42,6 +42,12 @@ extern unsigned long long g_launch_count;
     MSF_CHECK_CUDA(cudaGetLastError());     \
   } while (0)
 
+// Optional per-launch timing with CUDA events on the launching stream (msf_prof_enable / msf_prof_report);
+// bench.py uses it to time the dominant kernel live.  Not usable while a stream is being captured.
+bool prof_enabled();
+void prof_begin(const char* label, double flops, cudaStream_t stream);
+void prof_end(cudaStream_t stream);
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -628,8 +628,8 @@ int tc_init() {
   return MSF_OK;
 }
 
-TcBuilder::TcBuilder(bool mn, int block_n, const DropCfg& drop, cudaStream_t st)
-    : nmaps(0), mn_major(mn), stream(st), status(MSF_OK) {
+TcBuilder::TcBuilder(bool mn, int block_n, const DropCfg& drop, cudaStream_t st, const char* lbl)
+    : nmaps(0), mn_major(mn), stream(st), status(MSF_OK), label(lbl) {
   memset(&L, 0, sizeof(L));
   L.block_n = block_n;
   L.drop = drop;
@@ -733,6 +733,11 @@ int TcBuilder::flush() {
   L.stages = stages;
   const size_t smem = tc_fixed_smem_bytes() + staging + (size_t)stages * per_stage;
   const int grid = L.total_tiles < sms ? L.total_tiles : sms;
+  if (prof_enabled()) {
+    double flops = 0.0;
+    for (int i = 0; i < L.count; ++i) flops += 2.0 * L.p[i].M * L.p[i].N * (double)L.p[i].K * L.p[i].nseg;
+    prof_begin(label, flops, stream);
+  }
   if (mn_major) {
     MSF_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tc_gemm_kernel<true><<<grid, TC_THREADS, smem, stream>>>(L);
@@ -741,6 +746,7 @@ int TcBuilder::flush() {
     tc_gemm_kernel<false><<<grid, TC_THREADS, smem, stream>>>(L);
   }
   MSF_LAUNCH_CHECK();
+  prof_end(stream);
   L.count = 0;
   L.total_tiles = 0;
   return MSF_OK;

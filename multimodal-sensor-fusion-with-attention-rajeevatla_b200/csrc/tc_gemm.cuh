@@ -89,7 +89,8 @@ struct TcBuilder {
   bool mn_major;
   cudaStream_t stream;
   int status;             // first error seen (MSF_OK otherwise)
-  TcBuilder(bool mn, int block_n, const DropCfg& drop, cudaStream_t st);
+  const char* label;      // shown by msf_prof_report
+  TcBuilder(bool mn, int block_n, const DropCfg& drop, cudaStream_t st, const char* label = "tc_gemm");
   // Stacked bf16 tensor [depth][rows][cols] (row pitch = ld elements, slice pitch = slice elements).
   // role_rows: box height along `rows` for a K-major operand (TC_BLOCK_M for A, block_n for B);
   // ignored for MN-major operands (box = 64 x 64).
