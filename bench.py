@@ -259,7 +259,8 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(e2e_step, max(5, min(args.steps, 50)), 3)
 
-    kern = profile_dominant_kernel(torch, pkg, eng, ring, ring_n) if rank == 0 else None
+    # every rank runs the profiled steps: the eager step contains the gradient all-reduce
+    kern = profile_dominant_kernel(torch, pkg, eng, ring, ring_n)
 
     if rank != 0:
         if world > 1:

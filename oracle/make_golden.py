@@ -289,6 +289,64 @@ def survey_kat(ref_uncertainty):
                           "ece15_seed1234": np.float64(e15), "mce15_seed1234": np.float64(m15)})
 
 
+def encoder_cases():
+    """SequenceEncoder (lstm with and without lengths, gru) and SimpleMLPEncoder of the unmodified
+    reference (src/encoders.py), eval-mode outputs plus dropout-free training gradients."""
+    sys.path.insert(0, REF_SRC)
+    import encoders as ref_enc  # noqa
+    assert ref_enc.__file__.startswith(REF_SRC), ref_enc.__file__
+    sys.path.pop(0)
+    gen = torch.Generator().manual_seed(31)
+    payload = {}
+    B, T, F_in, H, D = 6, 14, 17, 32, 16
+    x = torch.randn(B, T, F_in, generator=gen) * 2.0
+    lengths = torch.tensor([14, 9, 1, 14, 5, 12])
+    payload["seq/x"], payload["seq/lengths"] = _np(x), _np(lengths)
+    for kind in ("lstm", "gru"):
+        torch.manual_seed(41 if kind == "lstm" else 42)
+        enc = ref_enc.SequenceEncoder(F_in, hidden_dim=H, output_dim=D, num_layers=2, encoder_type=kind, dropout=0.0)
+        enc.eval()
+        for k, v in enc.state_dict().items():
+            payload[f"{kind}/sd/{k}"] = _np(v)
+        payload[f"{kind}/out"] = _np(enc(x))
+        if kind == "lstm":
+            payload["lstm/out_lengths"] = _np(enc(x, lengths))
+        enc.train()
+        xg = x.clone().requires_grad_(True)
+        out = enc(xg)
+        w = torch.linspace(-1, 1, D).unsqueeze(0)
+        (out * w).sum().backward()
+        payload[f"{kind}/gradx"] = _np(xg.grad)
+        for k, p in enc.named_parameters():
+            payload[f"{kind}/grad/{k}"] = _np(p.grad)
+    # SimpleMLPEncoder: heart-rate style features, batch-norm batch statistics in train mode
+    torch.manual_seed(43)
+    mlp = ref_enc.SimpleMLPEncoder(12, hidden_dim=24, output_dim=D, num_layers=2, dropout=0.0, batch_norm=True)
+    xm = torch.randn(10, 12, generator=gen)
+    payload["mlp/x"] = _np(xm)
+    for k, v in mlp.state_dict().items():
+        payload[f"mlp/sd/{k}"] = _np(v)
+    mlp.eval()
+    payload["mlp/out_eval"] = _np(mlp(xm))
+    mlp.train()
+    xg = xm.clone().requires_grad_(True)
+    out = mlp(xg)
+    payload["mlp/out_train"] = _np(out)
+    (out * torch.linspace(-1, 1, D).unsqueeze(0)).sum().backward()
+    payload["mlp/gradx"] = _np(xg.grad)
+    for k, p in mlp.named_parameters():
+        payload[f"mlp/grad/{k}"] = _np(p.grad)
+    # LayerNorm glue of train.py:170-171,267-268 on an encoder output
+    torch.manual_seed(44)
+    ln = nn.LayerNorm(D)
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5)
+        ln.bias.uniform_(-0.2, 0.2)
+    payload["ln/weight"], payload["ln/bias"] = _np(ln.weight), _np(ln.bias)
+    payload["ln/out"] = _np(ln(torch.from_numpy(payload["lstm/out"])))
+    _save("encoders_small.npz", payload)
+
+
 def main():
     ref_fusion, ref_attention, ref_uncertainty = _import_reference()
     # the reference's own test configuration (tests/test_fusion.py:50-80)
@@ -303,6 +361,7 @@ def main():
     attention_case(ref_attention, "attention_generic.npz", seed=21)
     ece_case(ref_uncertainty, "ece_seeded.npz", seed=1234, n=20000, classes=25)
     survey_kat(ref_uncertainty)
+    encoder_cases()
 
 
 if __name__ == "__main__":

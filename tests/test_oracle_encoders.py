@@ -1,0 +1,98 @@
+"""CPU: the encoder restatements in oracle/encoder_oracle.py against golden vectors made by the
+unmodified reference encoders (oracle/make_golden.py: encoder_cases), plus the drop-in's module
+surface (names, routing, error strings) which needs no GPU."""
+import sys
+
+import pytest
+import torch
+import torch.nn as nn
+
+from conftest import Golden, dropin_src
+from oracle import encoder_oracle
+
+if dropin_src() not in sys.path:
+    sys.path.insert(0, dropin_src())
+import encoders as dropin_encoders  # noqa: E402
+
+TOL = 1e-5
+
+
+def _maxabs(a, b):
+    return float((a.double() - b.double()).abs().max())
+
+
+@pytest.mark.parametrize("kind", ["lstm", "gru"])
+def test_sequence_encoder_oracle_matches_reference(kind):
+    g = Golden("encoders_small.npz")
+    sd = g.group(f"{kind}/sd")
+    x = g.t("seq/x")
+    out = encoder_oracle.sequence_encoder_forward(sd, x, 2, kind)
+    assert _maxabs(out, g.t(f"{kind}/out")) <= TOL
+    # gradients through the restated recurrence (dropout 0): d(sum(out * w)) / dx and / d params
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xg = x.clone().requires_grad_(True)
+    out = encoder_oracle.sequence_encoder_forward(sdg, xg, 2, kind)
+    (out * torch.linspace(-1, 1, out.shape[1]).unsqueeze(0)).sum().backward()
+    assert _maxabs(xg.grad, g.t(f"{kind}/gradx")) <= TOL
+    for key, ref in g.group(f"{kind}/grad").items():
+        assert _maxabs(sdg[key].grad, ref) <= 5 * TOL, key
+
+
+def test_lstm_lengths_stop_the_state():
+    g = Golden("encoders_small.npz")
+    out = encoder_oracle.sequence_encoder_forward(g.group("lstm/sd"), g.t("seq/x"), 2, "lstm", g.t("seq/lengths"))
+    assert _maxabs(out, g.t("lstm/out_lengths")) <= TOL
+
+
+def test_mlp_encoder_and_layernorm_oracle_match_reference():
+    g = Golden("encoders_small.npz")
+    sd = g.group("mlp/sd")
+    assert _maxabs(encoder_oracle.mlp_encoder_forward(sd, g.t("mlp/x"), 2, True, training=False), g.t("mlp/out_eval")) <= TOL
+    assert _maxabs(encoder_oracle.mlp_encoder_forward(sd, g.t("mlp/x"), 2, True, training=True), g.t("mlp/out_train")) <= TOL
+    assert _maxabs(encoder_oracle.layer_norm(g.t("lstm/out"), g.t("ln/weight"), g.t("ln/bias")), g.t("ln/out")) <= TOL
+
+
+def test_dropin_state_dict_keys_and_same_seed_init():
+    g = Golden("encoders_small.npz")
+    torch.manual_seed(41)  # seed used by make_golden for the lstm case: same registration order -> same weights
+    enc = dropin_encoders.SequenceEncoder(17, hidden_dim=32, output_dim=16, num_layers=2, encoder_type="lstm", dropout=0.0)
+    ref = g.group("lstm/sd")
+    assert list(enc.state_dict().keys()) == list(ref.keys())
+    for k, v in ref.items():
+        assert torch.equal(enc.state_dict()[k], v), k
+    torch.manual_seed(43)
+    mlp = dropin_encoders.SimpleMLPEncoder(12, hidden_dim=24, output_dim=16, num_layers=2, dropout=0.0)
+    for k, v in g.group("mlp/sd").items():
+        assert torch.equal(mlp.state_dict()[k], v), k
+
+
+def test_factory_routing_and_errors():
+    E = dropin_encoders
+    assert isinstance(E.build_encoder("imu_hand", 17, 128), E.SequenceEncoder)
+    assert isinstance(E.build_encoder("heart_rate", 1, 128), E.SimpleMLPEncoder)
+    assert isinstance(E.build_encoder("video", 512, 128), E.FrameEncoder)
+    assert isinstance(E.build_encoder("heart_rate", 1, 128, {"type": "sequence", "encoder_type": "gru"}), E.SequenceEncoder)
+    assert isinstance(E.build_encoder("audio", 8, 16, {"type": "bogus"}), E.SequenceEncoder)  # falls back to the name
+    with pytest.raises(ValueError, match="Unknown encoder type"):
+        E.SequenceEncoder(4, encoder_type="nope")
+    with pytest.raises(ValueError, match="Unknown pooling"):
+        E.FrameEncoder(4, temporal_pooling="nope")
+    enc = E.SequenceEncoder(4, hidden_dim=8, output_dim=4, num_layers=1)
+    with pytest.raises(ValueError, match="Expected 3D input sequence"):
+        enc(torch.zeros(2, 4))
+    enc.rnn = None
+    with pytest.raises(RuntimeError, match="RNN module not initialized."):
+        enc(torch.zeros(2, 3, 4))
+    enc.encoder_type = "bogus"
+    with pytest.raises(ValueError, match="Unsupported encoder type"):
+        enc(torch.zeros(2, 3, 4))
+    with pytest.raises(ValueError, match="Expected 2D feature tensor"):
+        E.SimpleMLPEncoder(4)(torch.zeros(2, 3, 4))
+    # no CUDA device here: a kernel-backed layer must fail loudly instead of falling back
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception, match="no CPU or PyTorch-eager fallback"):
+            E.SimpleMLPEncoder(4, hidden_dim=8, output_dim=4)(torch.zeros(2, 4))
+    # a swapped-in projection is simply called (tests/test_encoders.py hot-swapping)
+    enc2 = E.SequenceEncoder(4, hidden_dim=8, output_dim=4, num_layers=1)
+    enc2.projection = nn.Identity()
+    assert enc2(torch.zeros(2, 3, 4)).shape == (2, 8)
