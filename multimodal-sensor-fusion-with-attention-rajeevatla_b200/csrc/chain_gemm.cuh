@@ -1,0 +1,57 @@
+// Chained pair GEMMs of HybridFusion on the tensor cores: for one 128-window tile and one
+// "outer" modality the kernel runs, for every partner modality,
+//
+//     T   = A1[inner] . W1[pair]^T        (tcgen05.mma into TMEM)
+//     T'  = epilogue1(T)  -> bf16 -> swizzled shared memory (+ TMA store to global when training)
+//     ACC += T' . W2[pair]^T              (A operand read straight from that shared memory)
+//
+// and finishes with one epilogue over ACC.  Forward (src/fusion.py:383-408 with the q_len = k_len = 1
+// attention of src/attention.py:104-140): outer = query q, inner = key k, W1 = value_proj, epilogue1 =
+// (+bias) * gate, W2 = out_proj, final = (ACC + sum bias_o + P_q) / count * mask_q -> aggregated[q].
+// Backward: outer = key k, inner = query q, A1 = d aggregated[q], W1 = out_proj^T, epilogue1 = * gate,
+// W2 = value_proj^T, final = (ACC + dS_k) * relu'(P_k) -> dZ_k.
+// The intermediate never makes a round trip through L2/HBM on its way to the second GEMM.
+#pragma once
+
+#include <cuda.h>
+
+#include "msf_common.cuh"
+
+namespace msf {
+
+constexpr int CHAIN_MAX_INNER = MSF_MAX_MODALITIES - 1;
+constexpr int CHAIN_MAX_PAIRS = MSF_MAX_MODALITIES * (MSF_MAX_MODALITIES - 1);
+
+struct ChainOuter {
+  int n;                           // partner modalities with a pair module
+  short inner[CHAIN_MAX_INNER];    // z index of A1 for each partner
+  short pair[CHAIN_MAX_INNER];     // pair index (z of W1 / W2 / out1, gate slot)
+  short sub[CHAIN_MAX_INNER];      // dropout sub-stream of the attention gate (q*M + k)
+  short mask_col[CHAIN_MAX_INNER]; // mask column deciding the gate (forward: the key modality)
+};
+
+struct ChainLaunch {
+  CUtensorMap map_a1, map_w1, map_w2, map_out1, map_out;
+  int mode;            // 0 forward, 1 backward
+  int M, H, heads, head_dim;
+  int rows, row_tiles, items;
+  int store1;          // write epilogue1's result to global memory (needed by the backward pass)
+  int stages;
+  ChainOuter outer[MSF_MAX_MODALITIES];
+  const float* bias1[CHAIN_MAX_PAIRS];   // forward: value_proj bias per pair
+  const float* bias2[CHAIN_MAX_PAIRS];   // forward: out_proj bias per pair (summed in the final epilogue)
+  float* gate_out;                       // forward: [pairs][rows][heads]
+  const float* gate_in;                  // backward
+  const float* mask;                     // (rows, M) or nullptr
+  const __nv_bfloat16* aux;              // forward: P stack; backward: dS stack      [M][rows][H]
+  const __nv_bfloat16* aux2;             // backward: P stack
+  float inv_cnt[MSF_MAX_MODALITIES];     // forward: 1 / (1 + present pairs of q)
+  float scale;                           // backward: dropout scale of the projection site
+  DropCfg drop;
+};
+
+bool chain_eligible(int H, int M);
+// Fills stages / items / row_tiles and launches.  Tensor maps must already be encoded (tc_encode_map).
+int chain_launch(ChainLaunch& L, cudaStream_t stream, const char* label);
+
+}  // namespace msf

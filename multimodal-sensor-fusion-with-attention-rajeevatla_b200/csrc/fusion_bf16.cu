@@ -15,6 +15,9 @@
 // copies kept in the compute arena; all weight gradients (dY^T . X, contraction
 // over the windows) go into ONE MN-major launch at the end; bias gradients are
 // column sums.  Dead query/key projection slots are exact zeros (memset).
+#include <stdlib.h>
+
+#include "chain_gemm.cuh"
 #include "fusion_common.cuh"
 #include "tc_gemm.cuh"
 
@@ -594,55 +597,84 @@ int fusion_bf16_forward(const Layout& L, const msf_fusion_call* c, cudaStream_t 
     if ((rc = tb.flush())) return rc;
   }
 
-  if (pairs > 0) {  // F2: U_qk = g_qk * (P_k Wv_qk^T + bv_qk)
-    TcBuilder tb(false, bnH, drop, st, "F2 value_proj");
-    const short mapP = (short)tb.add_map(ws.P, B, H, H, M, BH, TC_BLOCK_M);
-    const short mapW = (short)tb.add_map(W16 + A.wv, H, H, H, pairs, (long long)H * H, bnH);
-    for (int q = 0; q < M; ++q)
+  const bool use_chain = chain_eligible(H, M) && !getenv("MSF_NO_CHAIN");
+  if (use_chain) {  // F2 + F3 chained per (window tile, query): U never leaves the SM on its way to out_proj
+    ChainLaunch C;
+    memset(&C, 0, sizeof(C));
+    C.mode = 0; C.M = M; C.H = H; C.heads = L.heads; C.head_dim = H / L.heads; C.rows = (int)B;
+    C.store1 = 1;  // U is an operand of the out_proj weight gradient
+    const int np = pairs > 0 ? pairs : 1;
+    if ((rc = tc_encode_map(&C.map_a1, ws.P, B, H, H, M, BH, 64, 128))) return rc;
+    if ((rc = tc_encode_map(&C.map_w1, pairs > 0 ? (const void*)(W16 + A.wv) : (const void*)ws.P, H, H, H, np, (long long)H * H, 64, H))) return rc;
+    if ((rc = tc_encode_map(&C.map_w2, pairs > 0 ? (const void*)(W16 + A.wo) : (const void*)ws.P, H, H, H, np, (long long)H * H, 64, H))) return rc;
+    if ((rc = tc_encode_map(&C.map_out1, ws.U, B, H, H, np, BH, 64, 128))) return rc;
+    if ((rc = tc_encode_map(&C.map_out, ws.agg, B, H, H, M, BH, 64, 128))) return rc;
+    for (int q = 0; q < M; ++q) {
+      ChainOuter& O = C.outer[q];
       for (int k = 0; k < M; ++k) {
         if (q == k || !L.has_pair(q, k)) continue;
         const int pi = L.pair_index(q, k);
+        O.inner[O.n] = (short)k; O.pair[O.n] = (short)pi; O.sub[O.n] = (short)(q * M + k); O.mask_col[O.n] = (short)k;
+        ++O.n;
+        C.bias1[pi] = W + L.pair_b(pi, 2);
+        C.bias2[pi] = W + L.pair_b(pi, 3);
+      }
+      C.inv_cnt[q] = 1.0f / (float)L.mean_count(q);
+    }
+    C.gate_out = ws.G; C.mask = c->mask; C.aux = ws.P; C.drop = drop;
+    if ((rc = chain_launch(C, st, "F2+F3 value->out chain"))) return rc;
+  } else {
+  if (pairs > 0) {  // F2: U_qk = g_qk * (P_k Wv_qk^T + bv_qk)
+      TcBuilder tb(false, bnH, drop, st, "F2 value_proj");
+      const short mapP = (short)tb.add_map(ws.P, B, H, H, M, BH, TC_BLOCK_M);
+      const short mapW = (short)tb.add_map(W16 + A.wv, H, H, H, pairs, (long long)H * H, bnH);
+      for (int q = 0; q < M; ++q)
+        for (int k = 0; k < M; ++k) {
+          if (q == k || !L.has_pair(q, k)) continue;
+          const int pi = L.pair_index(q, k);
+          TcProblem p = tc_blank_problem();
+          p.seg[0].a_map = mapP; p.seg[0].a_z = k;
+          p.seg[0].b_map = mapW; p.seg[0].b_z = pi;
+          p.bias[0] = W + L.pair_b(pi, 2);
+          p.M = (int)B; p.N = H; p.K = H;
+          p.C = ws.U + (long long)pi * BH; p.ldc = H; p.c_bf16 = 1;
+          p.epi = TC_EPI_VALUE_GATE;
+          p.mask = c->mask; p.mask_ld = M; p.mask_col = k;
+          p.gate_out = ws.G + (long long)pi * B * L.heads;
+          p.head_dim = H / L.heads; p.heads = L.heads;
+          p.sub = q * M + k;
+          tb.add_problem(p);
+        }
+      if ((rc = tb.flush())) return rc;
+    }
+  
+    {  // F3: agg_q = (P_q + sum_k (U_qk Wo_qk^T + bo_qk)) / cnt_q * mask_q
+      TcBuilder tb(false, bnH, drop, st, "F3 out_proj+mean");
+      const short mapU = (short)tb.add_map(ws.U, B, H, H, pairs > 0 ? pairs : 1, BH, TC_BLOCK_M);
+      const short mapW = pairs > 0 ? (short)tb.add_map(W16 + A.wo, H, H, H, pairs, (long long)H * H, bnH) : mapU;
+      for (int q = 0; q < M; ++q) {
         TcProblem p = tc_blank_problem();
-        p.seg[0].a_map = mapP; p.seg[0].a_z = k;
-        p.seg[0].b_map = mapW; p.seg[0].b_z = pi;
-        p.bias[0] = W + L.pair_b(pi, 2);
-        p.M = (int)B; p.N = H; p.K = H;
-        p.C = ws.U + (long long)pi * BH; p.ldc = H; p.c_bf16 = 1;
-        p.epi = TC_EPI_VALUE_GATE;
-        p.mask = c->mask; p.mask_ld = M; p.mask_col = k;
-        p.gate_out = ws.G + (long long)pi * B * L.heads;
-        p.head_dim = H / L.heads; p.heads = L.heads;
-        p.sub = q * M + k;
+        int seg = 0;
+        for (int k = 0; k < M; ++k) {
+          if (q == k || !L.has_pair(q, k)) continue;
+          const int pi = L.pair_index(q, k);
+          p.seg[seg].a_map = mapU; p.seg[seg].a_z = pi;
+          p.seg[seg].b_map = mapW; p.seg[seg].b_z = pi;
+          p.bias[seg] = W + L.pair_b(pi, 3);
+          ++seg;
+        }
+        p.M = (int)B; p.N = H; p.K = seg ? H : 0;
+        if (seg == 0) { p.seg[0].a_map = mapU; p.seg[0].b_map = mapW; seg = 1; }  // epilogue only
+        p.nseg = seg;
+        p.C = ws.agg + (long long)q * BH; p.ldc = H; p.c_bf16 = 1;
+        p.epi = TC_EPI_OUT_MEAN; p.scale = (float)L.mean_count(q);
+        p.aux = ws.P + (long long)q * BH; p.ld_aux = H;
+        p.mask = c->mask; p.mask_ld = M; p.mask_col = q;
         tb.add_problem(p);
       }
-    if ((rc = tb.flush())) return rc;
-  }
-
-  {  // F3: agg_q = (P_q + sum_k (U_qk Wo_qk^T + bo_qk)) / cnt_q * mask_q
-    TcBuilder tb(false, bnH, drop, st, "F3 out_proj+mean");
-    const short mapU = (short)tb.add_map(ws.U, B, H, H, pairs > 0 ? pairs : 1, BH, TC_BLOCK_M);
-    const short mapW = pairs > 0 ? (short)tb.add_map(W16 + A.wo, H, H, H, pairs, (long long)H * H, bnH) : mapU;
-    for (int q = 0; q < M; ++q) {
-      TcProblem p = tc_blank_problem();
-      int seg = 0;
-      for (int k = 0; k < M; ++k) {
-        if (q == k || !L.has_pair(q, k)) continue;
-        const int pi = L.pair_index(q, k);
-        p.seg[seg].a_map = mapU; p.seg[seg].a_z = pi;
-        p.seg[seg].b_map = mapW; p.seg[seg].b_z = pi;
-        p.bias[seg] = W + L.pair_b(pi, 3);
-        ++seg;
-      }
-      p.M = (int)B; p.N = H; p.K = seg ? H : 0;
-      if (seg == 0) { p.seg[0].a_map = mapU; p.seg[0].b_map = mapW; seg = 1; }  // epilogue only
-      p.nseg = seg;
-      p.C = ws.agg + (long long)q * BH; p.ldc = H; p.c_bf16 = 1;
-      p.epi = TC_EPI_OUT_MEAN; p.scale = (float)L.mean_count(q);
-      p.aux = ws.P + (long long)q * BH; p.ld_aux = H;
-      p.mask = c->mask; p.mask_ld = M; p.mask_col = q;
-      tb.add_problem(p);
+      if ((rc = tb.flush())) return rc;
     }
-    if ((rc = tb.flush())) return rc;
+  
   }
 
   {  // F4
@@ -763,49 +795,73 @@ int fusion_bf16_backward(const Layout& L, const msf_fusion_call* c, cudaStream_t
     tail16_bwd_kernel<<<(unsigned)ceil_div(B, 8), 256, 0, st>>>(a);
     MSF_LAUNCH_CHECK();
   }
-  if (pairs > 0) {  // B5: dV_qk = (dS_q Wo_qk) * g_qk
-    TcBuilder tb(false, bnH, drop, st, "B5 d out_proj");
-    const short mapS = (short)tb.add_map(ws.dS, B, H, H, M, BH, TC_BLOCK_M);
-    const short mapW = (short)tb.add_map(W16 + A.woT, H, H, H, pairs, (long long)H * H, bnH);
-    for (int q = 0; q < M; ++q)
-      for (int k = 0; k < M; ++k) {
-        if (q == k || !L.has_pair(q, k)) continue;
-        const int pi = L.pair_index(q, k);
-        TcProblem p = tc_blank_problem();
-        p.seg[0].a_map = mapS; p.seg[0].a_z = q;
-        p.seg[0].b_map = mapW; p.seg[0].b_z = pi;
-        p.M = (int)B; p.N = H; p.K = H;
-        p.C = ws.dV + (long long)pi * BH; p.ldc = H; p.c_bf16 = 1;
-        p.epi = TC_EPI_GATE_MUL; p.gate_in = ws.G + (long long)pi * B * L.heads;
-        p.head_dim = H / L.heads; p.heads = L.heads;
-        tb.add_problem(p);
-      }
-    if ((rc = tb.flush())) return rc;
-  }
-  {  // B7: dZ_k = (dS_k + sum_q dV_qk Wv_qk) * relu'(P_k) * drop1
-    TcBuilder tb(false, bnH, drop, st, "B7 d value_proj");
-    const short mapV = (short)tb.add_map(ws.dV, B, H, H, pairs > 0 ? pairs : 1, BH, TC_BLOCK_M);
-    const short mapW = pairs > 0 ? (short)tb.add_map(W16 + A.wvT, H, H, H, pairs, (long long)H * H, bnH) : mapV;
+  const bool use_chain = chain_eligible(H, M) && !getenv("MSF_NO_CHAIN");
+  if (use_chain) {  // B5 + B7 chained per (window tile, key): dV goes straight from the epilogue into the value_proj dgrad
+    ChainLaunch C;
+    memset(&C, 0, sizeof(C));
+    C.mode = 1; C.M = M; C.H = H; C.heads = L.heads; C.head_dim = H / L.heads; C.rows = (int)B;
+    C.store1 = 1;  // dV is an operand of the value_proj weight / bias gradients
+    const int np = pairs > 0 ? pairs : 1;
+    if ((rc = tc_encode_map(&C.map_a1, ws.dS, B, H, H, M, BH, 64, 128))) return rc;
+    if ((rc = tc_encode_map(&C.map_w1, pairs > 0 ? (const void*)(W16 + A.woT) : (const void*)ws.dS, H, H, H, np, (long long)H * H, 64, H))) return rc;
+    if ((rc = tc_encode_map(&C.map_w2, pairs > 0 ? (const void*)(W16 + A.wvT) : (const void*)ws.dS, H, H, H, np, (long long)H * H, 64, H))) return rc;
+    if ((rc = tc_encode_map(&C.map_out1, ws.dV, B, H, H, np, BH, 64, 128))) return rc;
+    if ((rc = tc_encode_map(&C.map_out, ws.dZ, B, H, H, M, BH, 64, 128))) return rc;
     for (int k = 0; k < M; ++k) {
-      TcProblem p = tc_blank_problem();
-      int seg = 0;
+      ChainOuter& O = C.outer[k];
       for (int q = 0; q < M; ++q) {
         if (q == k || !L.has_pair(q, k)) continue;
-        const int pi = L.pair_index(q, k);
-        p.seg[seg].a_map = mapV; p.seg[seg].a_z = pi;
-        p.seg[seg].b_map = mapW; p.seg[seg].b_z = pi;
-        ++seg;
+        O.inner[O.n] = (short)q; O.pair[O.n] = (short)L.pair_index(q, k);
+        ++O.n;
       }
-      p.M = (int)B; p.N = H; p.K = seg ? H : 0;
-      if (seg == 0) { p.seg[0].a_map = mapV; p.seg[0].b_map = mapW; seg = 1; }
-      p.nseg = seg;
-      p.C = ws.dZ + (long long)k * BH; p.ldc = H; p.c_bf16 = 1;
-      p.epi = TC_EPI_ADD_RELU_GRAD; p.scale = drop.scale;
-      p.aux = ws.dS + (long long)k * BH; p.ld_aux = H;
-      p.aux2 = ws.P + (long long)k * BH; p.ld_aux2 = H;
-      tb.add_problem(p);
     }
-    if ((rc = tb.flush())) return rc;
+    C.gate_in = ws.G; C.aux = ws.dS; C.aux2 = ws.P; C.scale = drop.scale; C.drop = drop;
+    if ((rc = chain_launch(C, st, "B5+B7 d-out->d-value chain"))) return rc;
+  } else {
+  if (pairs > 0) {  // B5: dV_qk = (dS_q Wo_qk) * g_qk
+      TcBuilder tb(false, bnH, drop, st, "B5 d out_proj");
+      const short mapS = (short)tb.add_map(ws.dS, B, H, H, M, BH, TC_BLOCK_M);
+      const short mapW = (short)tb.add_map(W16 + A.woT, H, H, H, pairs, (long long)H * H, bnH);
+      for (int q = 0; q < M; ++q)
+        for (int k = 0; k < M; ++k) {
+          if (q == k || !L.has_pair(q, k)) continue;
+          const int pi = L.pair_index(q, k);
+          TcProblem p = tc_blank_problem();
+          p.seg[0].a_map = mapS; p.seg[0].a_z = q;
+          p.seg[0].b_map = mapW; p.seg[0].b_z = pi;
+          p.M = (int)B; p.N = H; p.K = H;
+          p.C = ws.dV + (long long)pi * BH; p.ldc = H; p.c_bf16 = 1;
+          p.epi = TC_EPI_GATE_MUL; p.gate_in = ws.G + (long long)pi * B * L.heads;
+          p.head_dim = H / L.heads; p.heads = L.heads;
+          tb.add_problem(p);
+        }
+      if ((rc = tb.flush())) return rc;
+    }
+    {  // B7: dZ_k = (dS_k + sum_q dV_qk Wv_qk) * relu'(P_k) * drop1
+      TcBuilder tb(false, bnH, drop, st, "B7 d value_proj");
+      const short mapV = (short)tb.add_map(ws.dV, B, H, H, pairs > 0 ? pairs : 1, BH, TC_BLOCK_M);
+      const short mapW = pairs > 0 ? (short)tb.add_map(W16 + A.wvT, H, H, H, pairs, (long long)H * H, bnH) : mapV;
+      for (int k = 0; k < M; ++k) {
+        TcProblem p = tc_blank_problem();
+        int seg = 0;
+        for (int q = 0; q < M; ++q) {
+          if (q == k || !L.has_pair(q, k)) continue;
+          const int pi = L.pair_index(q, k);
+          p.seg[seg].a_map = mapV; p.seg[seg].a_z = pi;
+          p.seg[seg].b_map = mapW; p.seg[seg].b_z = pi;
+          ++seg;
+        }
+        p.M = (int)B; p.N = H; p.K = seg ? H : 0;
+        if (seg == 0) { p.seg[0].a_map = mapV; p.seg[0].b_map = mapW; seg = 1; }
+        p.nseg = seg;
+        p.C = ws.dZ + (long long)k * BH; p.ldc = H; p.c_bf16 = 1;
+        p.epi = TC_EPI_ADD_RELU_GRAD; p.scale = drop.scale;
+        p.aux = ws.dS + (long long)k * BH; p.ld_aux = H;
+        p.aux2 = ws.P + (long long)k * BH; p.ld_aux2 = H;
+        tb.add_problem(p);
+      }
+      if ((rc = tb.flush())) return rc;
+    }
   }
   {  // B9a: dx_m = (dZ_m Wp_m) * mask_m * drop0   (fp32 out, only where requested)
     for (int m = 0; m < M; ++m) {

@@ -104,5 +104,9 @@ TcProblem tc_blank_problem();
 DropCfg no_dropout();
 
 int tc_init();  // resolves cuTensorMapEncodeTiled; MSF_OK or error
+// 3-D bf16 tensor map over [depth][rows][cols] (row pitch ld, slice pitch slice elements), 128B swizzle,
+// box = box_cols x box_rows x 1 (box_cols * 2 bytes must be 128)
+int tc_encode_map(CUtensorMap* out, const void* base, long long rows, long long cols, long long ld, long long depth,
+                  long long slice, int box_cols, int box_rows);
 
 }  // namespace msf
