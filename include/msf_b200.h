@@ -179,6 +179,14 @@ int msf_adamw_step_dev(float* params, const float* grad, float* exp_avg, float* 
                        const uint64_t* train_state, float lr, float beta1, float beta2, float eps,
                        float weight_decay, float grad_scale, float max_norm, const double* sq_norm,
                        void* stream);
+/* Clip + AdamW over a HybridFusion master arena, aware of its layout: the gradient square-norm is
+ * computed here (sq_norm is scratch, zeroed by the call) and the dead query/key projection slots —
+ * whose gradient and Adam moments are identically zero — only receive the decoupled weight decay,
+ * which is exactly what AdamW does to them (src/train.py:378-382).  step is read from train_state[2]. */
+int msf_fusion_optimizer_step(const msf_fusion_shape* shape, float* params, const float* grad, float* exp_avg,
+                              float* exp_avg_sq, const uint64_t* train_state, float lr, float beta1, float beta2,
+                              float eps, float weight_decay, float grad_scale, float max_norm, double* sq_norm,
+                              void* stream);
 /* train_state = DEVICE {seed, offset, step}: offset += 1, step += 1. */
 int msf_train_state_advance(uint64_t* train_state, void* stream);
 

@@ -88,6 +88,9 @@ PROTOTYPES = {
     "msf_adamw_step_dev": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float,
                                      c_float, c_float, c_float, c_float, c_float, c_float, c_void_p,
                                      c_void_p]),
+    "msf_fusion_optimizer_step": (c_int32, [POINTER(FusionShape), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                            c_float, c_float, c_float, c_float, c_float, c_float, c_float,
+                                            c_void_p, c_void_p]),
     "msf_train_state_advance": (c_int32, [c_void_p, c_void_p]),
     "msf_linear_forward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
                                      c_int32, c_void_p]),

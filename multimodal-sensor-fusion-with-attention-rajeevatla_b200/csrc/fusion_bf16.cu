@@ -534,6 +534,29 @@ __global__ void copy_gates16_kernel(const float* __restrict__ src, float* __rest
 // ---------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------
+// A second stream per device so independent kernels of one step overlap (the weight-gradient GEMM
+// occupies ~110 SMs; the bias-gradient column sums run beside it).  Forked and joined with events,
+// which also works while the caller's stream is being captured into a CUDA graph.
+struct SideStream {
+  cudaStream_t stream;
+  cudaEvent_t fork, join;
+};
+static int side_stream(SideStream** out) {
+  static SideStream cache[16];
+  static bool made[16] = {false};
+  int dev = 0;
+  MSF_CHECK_CUDA(cudaGetDevice(&dev));
+  MSF_REQUIRE(dev >= 0 && dev < 16, "device index %d out of range", dev);
+  if (!made[dev]) {
+    MSF_CHECK_CUDA(cudaStreamCreateWithFlags(&cache[dev].stream, cudaStreamNonBlocking));
+    MSF_CHECK_CUDA(cudaEventCreateWithFlags(&cache[dev].fork, cudaEventDisableTiming));
+    MSF_CHECK_CUDA(cudaEventCreateWithFlags(&cache[dev].join, cudaEventDisableTiming));
+    made[dev] = true;
+  }
+  *out = &cache[dev];
+  return MSF_OK;
+}
+
 static int check_ws(const WsBf16& ws, const msf_fusion_call* c) {
   if (c->workspace == nullptr || c->workspace_bytes < ws.bytes) {
     set_error("workspace too small: need %zu bytes, have %zu", ws.bytes, c->workspace_bytes);
@@ -880,6 +903,36 @@ int fusion_bf16_backward(const Layout& L, const msf_fusion_call* c, cudaStream_t
     }
   }
 
+  // fork: the column sums only read activations that are complete at this point
+  SideStream* side = nullptr;
+  if ((rc = side_stream(&side))) return rc;
+  MSF_CHECK_CUDA(cudaEventRecord(side->fork, st));
+  MSF_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+  // ---- bias and gating-layer gradients: (weighted) column sums ----
+  {
+    Colsum16Problem cs[2 * MSF_MAX_MODALITIES * MSF_MAX_MODALITIES + 4 * MSF_MAX_MODALITIES + 4];
+    int nc = 0;
+    auto add = [&](const void* src, int f32, long long ld, int cols, const float* coef, int coef_ld, float* dst) {
+      Colsum16Problem p;
+      p.src = src; p.src_f32 = f32; p.ld = ld; p.rows = (int)B; p.cols = cols;
+      p.coef = coef; p.coef_ld = coef_ld; p.dst = dst;
+      cs[nc++] = p;
+    };
+    add(c->grad_logits, 1, C, C, nullptr, 0, dW + L.cls_b2);
+    add(ws.dH1, 0, H, H, nullptr, 0, dW + L.cls_b1);
+    for (int q = 0; q < M; ++q) {
+      add(ws.agg + (long long)q * BH, 0, H, H, ws.ds + q, M, dW + L.gate_w[q]);   // d gate_w_q = sum_r ds[r,q] agg_q[r,:]
+      add(ws.ds + q, 1, M, 1, nullptr, 0, dW + L.gate_b[q]);
+      add(ws.dZ + (long long)q * BH, 0, H, H, nullptr, 0, dW + L.proj_b[q]);
+      for (int k = 0; k < M; ++k) {
+        if (q == k || !L.has_pair(q, k)) continue;
+        const int pi = L.pair_index(q, k);
+        add(ws.dS + (long long)q * BH, 0, H, H, nullptr, 0, dW + L.pair_b(pi, 3));
+        add(ws.dV + (long long)pi * BH, 0, H, H, nullptr, 0, dW + L.pair_b(pi, 2));
+      }
+    }
+    if ((rc = colsum16_launch(cs, nc, side->stream))) return rc;
+  }
   // ---- all weight gradients: one MN-major launch, dW[out,in] = dY^T . X over the windows ----
   {
     const int bn = 128;
@@ -922,31 +975,8 @@ int fusion_bf16_backward(const Layout& L, const msf_fusion_call* c, cudaStream_t
     if ((rc = tb.flush())) return rc;
   }
 
-  // ---- bias and gating-layer gradients: (weighted) column sums ----
-  {
-    Colsum16Problem cs[2 * MSF_MAX_MODALITIES * MSF_MAX_MODALITIES + 4 * MSF_MAX_MODALITIES + 4];
-    int nc = 0;
-    auto add = [&](const void* src, int f32, long long ld, int cols, const float* coef, int coef_ld, float* dst) {
-      Colsum16Problem p;
-      p.src = src; p.src_f32 = f32; p.ld = ld; p.rows = (int)B; p.cols = cols;
-      p.coef = coef; p.coef_ld = coef_ld; p.dst = dst;
-      cs[nc++] = p;
-    };
-    add(c->grad_logits, 1, C, C, nullptr, 0, dW + L.cls_b2);
-    add(ws.dH1, 0, H, H, nullptr, 0, dW + L.cls_b1);
-    for (int q = 0; q < M; ++q) {
-      add(ws.agg + (long long)q * BH, 0, H, H, ws.ds + q, M, dW + L.gate_w[q]);   // d gate_w_q = sum_r ds[r,q] agg_q[r,:]
-      add(ws.ds + q, 1, M, 1, nullptr, 0, dW + L.gate_b[q]);
-      add(ws.dZ + (long long)q * BH, 0, H, H, nullptr, 0, dW + L.proj_b[q]);
-      for (int k = 0; k < M; ++k) {
-        if (q == k || !L.has_pair(q, k)) continue;
-        const int pi = L.pair_index(q, k);
-        add(ws.dS + (long long)q * BH, 0, H, H, nullptr, 0, dW + L.pair_b(pi, 3));
-        add(ws.dV + (long long)pi * BH, 0, H, H, nullptr, 0, dW + L.pair_b(pi, 2));
-      }
-    }
-    if ((rc = colsum16_launch(cs, nc, st))) return rc;
-  }
+  MSF_CHECK_CUDA(cudaEventRecord(side->join, side->stream));
+  MSF_CHECK_CUDA(cudaStreamWaitEvent(st, side->join, 0));
   return MSF_OK;
 }
 

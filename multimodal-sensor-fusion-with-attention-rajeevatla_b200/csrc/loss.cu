@@ -20,10 +20,12 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-__global__ void __launch_bounds__(256) ce_kernel(const float* __restrict__ logits,
-                                                 const int64_t* __restrict__ labels, long long B, int C,
-                                                 float smoothing, float grad_scale,
-                                                 float* __restrict__ row_loss, float* __restrict__ grad) {
+// blocks that have finished their rows; the last one to arrive reduces row_loss (fixed order:
+// deterministic) and resets the ticket, so the mean needs no second launch
+__device__ unsigned int g_ce_ticket = 0;
+
+__device__ void ce_rows(const float* __restrict__ logits, const int64_t* __restrict__ labels, long long B, int C,
+                        float smoothing, float grad_scale, float* __restrict__ row_loss, float* __restrict__ grad) {
   const int lane = threadIdx.x & 31;
   const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= B) return;
@@ -57,19 +59,33 @@ __global__ void __launch_bounds__(256) ce_kernel(const float* __restrict__ logit
   }
 }
 
-// deterministic mean of row_loss: one block, fixed tree
-__global__ void __launch_bounds__(1024) mean_kernel(const float* __restrict__ v, long long n,
-                                                    float* __restrict__ out) {
-  __shared__ double sh[1024];
+__global__ void __launch_bounds__(256) ce_kernel(const float* __restrict__ logits,
+                                                 const int64_t* __restrict__ labels, long long B, int C,
+                                                 float smoothing, float grad_scale,
+                                                 float* __restrict__ row_loss, float* __restrict__ grad,
+                                                 float* __restrict__ loss_out) {
+  ce_rows(logits, labels, B, C, smoothing, grad_scale, row_loss, grad);
+  if (loss_out == nullptr) return;
+  __shared__ bool last;
+  __shared__ double sh[256];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(&g_ce_ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
   double s = 0.0;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) s += (double)v[i];
+  for (long long i = threadIdx.x; i < B; i += blockDim.x) s += (double)__ldcg(row_loss + i);
   sh[threadIdx.x] = s;
   __syncthreads();
-  for (int o = 512; o > 0; o >>= 1) {
+  for (int o = 128; o > 0; o >>= 1) {
     if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) out[0] = (float)(sh[0] / (double)n);
+  if (threadIdx.x == 0) {
+    loss_out[0] = (float)(sh[0] / (double)B);
+    g_ce_ticket = 0;
+  }
 }
 
 __global__ void __launch_bounds__(256) conf_pred_kernel(const float* __restrict__ logits, long long B, int C,
@@ -123,12 +139,8 @@ int msf_cross_entropy(const float* logits, const int64_t* labels, int64_t batch,
   MSF_REQUIRE(loss_out == nullptr || row_loss != nullptr, "msf_cross_entropy: loss_out needs row_loss scratch");
   cudaStream_t st = (cudaStream_t)stream;
   msf::ce_kernel<<<(unsigned)msf::ceil_div(batch, 8), 256, 0, st>>>(logits, labels, batch, classes, smoothing,
-                                                                     grad_scale, row_loss, grad_logits);
+                                                                     grad_scale, row_loss, grad_logits, loss_out);
   MSF_LAUNCH_CHECK();
-  if (loss_out) {
-    msf::mean_kernel<<<1, 1024, 0, st>>>(row_loss, batch, loss_out);
-    MSF_LAUNCH_CHECK();
-  }
   return MSF_OK;
 }
 

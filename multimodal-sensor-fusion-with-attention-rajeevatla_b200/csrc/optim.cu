@@ -2,6 +2,8 @@
 // clipping, and gather/scatter between per-tensor storage and the arena.
 //   src/train.py:378-382   torch.optim.AdamW(lr, weight_decay)
 //   src/train.py:416-430   clip_gradients(..., gradient_clip_algorithm="norm")
+#include <string.h>
+
 #include "msf_common.cuh"
 
 namespace msf {
@@ -74,6 +76,128 @@ __global__ void __launch_bounds__(256) arena_copy_kernel(const long long* __rest
   }
 }
 
+// ---- layout-aware optimizer over the HybridFusion master arena -------------------------------------
+// The query/key projections of every pair module are dead inside HybridFusion: their gradient and both
+// Adam moments are identically zero, so AdamW reduces to the weight-decay multiply p *= 1 - lr*wd
+// (m = v = 0 gives a zero Adam update exactly).  Dead segments therefore touch 8 bytes per parameter
+// instead of 28 and are skipped by the gradient norm.
+struct ArenaSeg {
+  long long begin, count;
+  int dead;
+};
+constexpr int OPT_MAX_SEGS = 2 * MSF_MAX_MODALITIES * (MSF_MAX_MODALITIES - 1) + 2;
+struct ArenaSegs {
+  ArenaSeg s[OPT_MAX_SEGS];
+  int n;
+};
+
+__global__ void __launch_bounds__(256) seg_sq_norm_kernel(const __grid_constant__ ArenaSegs segs,
+                                                          const float* __restrict__ g, double* __restrict__ out) {
+  const ArenaSeg sg = segs.s[blockIdx.y];
+  if (sg.dead) return;
+  double s = 0.0;
+  const float* p = g + sg.begin;
+  if ((sg.begin & 3) == 0) {
+    const long long n4 = sg.count >> 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p) + i);
+      s += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (sg.count & 3)) {
+      const double v = (double)__ldg(p + (n4 << 2) + threadIdx.x);
+      s += v * v;
+    }
+  } else {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < sg.count; i += (long long)gridDim.x * blockDim.x) {
+      const double v = (double)__ldg(p + i);
+      s += v * v;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ double sh[8];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += sh[i];
+    if (t != 0.0) atomicAdd(out, t);
+  }
+}
+
+struct AdamCfg {
+  float lr, beta1, beta2, eps, wd, grad_scale, max_norm;
+};
+
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, const AdamCfg& c, float gs, float decay,
+                                         float step_size, float inv_sqrt_bc2) {
+  const float gi = g * gs;
+  float pi = p * decay;
+  m = c.beta1 * m + (1.0f - c.beta1) * gi;
+  v = c.beta2 * v + (1.0f - c.beta2) * gi * gi;
+  const float denom = sqrtf(v) * inv_sqrt_bc2 + c.eps;
+  p = pi - step_size * (m / denom);
+}
+
+__global__ void __launch_bounds__(256) seg_adamw_kernel(const __grid_constant__ ArenaSegs segs, const AdamCfg c,
+                                                        float* __restrict__ p, const float* __restrict__ g,
+                                                        float* __restrict__ m, float* __restrict__ v,
+                                                        const double* __restrict__ sq_norm,
+                                                        const unsigned long long* __restrict__ train_state) {
+  const ArenaSeg sg = segs.s[blockIdx.y];
+  const double step = (double)train_state[2];
+  const float bc1 = (float)(1.0 - pow((double)c.beta1, step));
+  const float sqrt_bc2 = (float)sqrt(1.0 - pow((double)c.beta2, step));
+  float gs = c.grad_scale;
+  if (c.max_norm > 0.0f && sq_norm != nullptr) {
+    const float total = (float)sqrt(*sq_norm) * c.grad_scale;
+    gs *= fminf(c.max_norm / (total + 1e-6f), 1.0f);
+  }
+  const float step_size = c.lr / bc1, decay = 1.0f - c.lr * c.wd;
+  const long long stride = (long long)gridDim.x * blockDim.x, t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const bool vec = (sg.begin & 3) == 0;
+  const long long n4 = vec ? (sg.count >> 2) : 0;
+  float4* p4 = reinterpret_cast<float4*>(p + sg.begin);
+  if (sg.dead) {  // g = m = v = 0: only the decoupled weight decay acts
+    for (long long i = t0; i < n4; i += stride) {
+      float4 x = p4[i];
+      x.x *= decay; x.y *= decay; x.z *= decay; x.w *= decay;
+      p4[i] = x;
+    }
+    for (long long i = (n4 << 2) + t0; i < sg.count; i += stride) p[sg.begin + i] *= decay;
+    return;
+  }
+  const float4* g4 = reinterpret_cast<const float4*>(g + sg.begin);
+  float4* m4 = reinterpret_cast<float4*>(m + sg.begin);
+  float4* v4 = reinterpret_cast<float4*>(v + sg.begin);
+  const float inv_sqrt_bc2 = 1.0f / sqrt_bc2;
+  for (long long i = t0; i < n4; i += stride) {
+    float4 x = p4[i], mm = m4[i], vv = v4[i];
+    const float4 gg = __ldg(g4 + i);
+    // same operation order as adamw_kernel: sqrt(v) / sqrt(bc2) + eps
+    const float gx = gg.x * gs, gy = gg.y * gs, gz = gg.z * gs, gw = gg.w * gs;
+    mm.x = c.beta1 * mm.x + (1.0f - c.beta1) * gx; vv.x = c.beta2 * vv.x + (1.0f - c.beta2) * gx * gx;
+    mm.y = c.beta1 * mm.y + (1.0f - c.beta1) * gy; vv.y = c.beta2 * vv.y + (1.0f - c.beta2) * gy * gy;
+    mm.z = c.beta1 * mm.z + (1.0f - c.beta1) * gz; vv.z = c.beta2 * vv.z + (1.0f - c.beta2) * gz * gz;
+    mm.w = c.beta1 * mm.w + (1.0f - c.beta1) * gw; vv.w = c.beta2 * vv.w + (1.0f - c.beta2) * gw * gw;
+    x.x = x.x * decay - step_size * (mm.x / (sqrtf(vv.x) / sqrt_bc2 + c.eps));
+    x.y = x.y * decay - step_size * (mm.y / (sqrtf(vv.y) / sqrt_bc2 + c.eps));
+    x.z = x.z * decay - step_size * (mm.z / (sqrtf(vv.z) / sqrt_bc2 + c.eps));
+    x.w = x.w * decay - step_size * (mm.w / (sqrtf(vv.w) / sqrt_bc2 + c.eps));
+    p4[i] = x; m4[i] = mm; v4[i] = vv;
+  }
+  (void)inv_sqrt_bc2;
+  for (long long i = (n4 << 2) + t0; i < sg.count; i += stride) {
+    const long long e = sg.begin + i;
+    const float gi = g[e] * gs;
+    const float mi = c.beta1 * m[e] + (1.0f - c.beta1) * gi;
+    const float vi = c.beta2 * v[e] + (1.0f - c.beta2) * gi * gi;
+    p[e] = p[e] * decay - step_size * (mi / (sqrtf(vi) / sqrt_bc2 + c.eps));
+    m[e] = mi;
+    v[e] = vi;
+  }
+}
+
 __global__ void train_state_advance_kernel(unsigned long long* state) {
   state[1] += 1ull;
   state[2] += 1ull;
@@ -135,6 +259,42 @@ int msf_adamw_step_dev(float* params, const float* grad, float* exp_avg, float* 
   msf::adamw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       params, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, 1.0f, 1.0f, grad_scale,
       max_norm, sq_norm, reinterpret_cast<const unsigned long long*>(train_state));
+  MSF_LAUNCH_CHECK();
+  return MSF_OK;
+}
+
+int msf_fusion_optimizer_step(const msf_fusion_shape* shape, float* params, const float* grad, float* exp_avg,
+                              float* exp_avg_sq, const uint64_t* train_state, float lr, float beta1, float beta2,
+                              float eps, float weight_decay, float grad_scale, float max_norm, double* sq_norm,
+                              void* stream) {
+  msf::Layout L;
+  int rc = msf::make_layout(shape, &L);
+  if (rc) return rc;
+  MSF_REQUIRE(params && grad && exp_avg && exp_avg_sq && train_state && sq_norm, "msf_fusion_optimizer_step: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  msf::ArenaSegs segs;
+  memset(&segs, 0, sizeof(segs));
+  auto add = [&](long long begin, long long count, int dead) {
+    if (count <= 0) return;
+    segs.s[segs.n].begin = begin; segs.s[segs.n].count = count; segs.s[segs.n].dead = dead;
+    ++segs.n;
+  };
+  const long long half = 2 * ((long long)L.H * L.H + L.H);
+  add(0, L.pair_base, 0);
+  for (int p = 0; p < L.num_pairs(); ++p) {
+    add(L.pair_base + p * L.pair_stride, half, 1);         // query_proj + key_proj: dead
+    add(L.pair_base + p * L.pair_stride + half, half, 0);  // value_proj + out_proj
+  }
+  const long long tail = L.pair_base + (long long)L.num_pairs() * L.pair_stride;
+  add(tail, L.total - tail, 0);
+  MSF_CHECK_CUDA(cudaMemsetAsync(sq_norm, 0, sizeof(double), st));
+  dim3 grid(24, (unsigned)segs.n);
+  msf::seg_sq_norm_kernel<<<grid, 256, 0, st>>>(segs, grad, sq_norm);
+  MSF_LAUNCH_CHECK();
+  msf::AdamCfg c{lr, beta1, beta2, eps, weight_decay, grad_scale, max_norm};
+  dim3 grid2(48, (unsigned)segs.n);
+  msf::seg_adamw_kernel<<<grid2, 256, 0, st>>>(segs, c, params, grad, exp_avg, exp_avg_sq, sq_norm,
+                                                reinterpret_cast<const unsigned long long*>(train_state));
   MSF_LAUNCH_CHECK();
   return MSF_OK;
 }

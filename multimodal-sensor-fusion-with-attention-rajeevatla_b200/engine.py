@@ -109,12 +109,12 @@ class FusionEngine:
         N.check(lib.msf_fusion_backward(ctypes_ref(self.plan.shape), ctypes_ref(c), st))
         if self.world > 1:
             torch.distributed.all_reduce(self.grad, group=self.pg)
-        self.sq_norm.zero_()
-        N.check(lib.msf_grad_sq_norm(self.grad.data_ptr(), self.plan.total, self.sq_norm.data_ptr(), st))
-        N.check(lib.msf_adamw_step_dev(self.arena.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
-                                       self.exp_avg_sq.data_ptr(), self.plan.total, self.state.data_ptr(),
-                                       self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 1.0,
-                                       self.max_norm, self.sq_norm.data_ptr(), st))
+        # global-norm clip + AdamW, skipping the dead q/k slots' moments (their gradients are exact zeros)
+        N.check(lib.msf_fusion_optimizer_step(ctypes_ref(self.plan.shape), self.arena.data_ptr(),
+                                              self.grad.data_ptr(), self.exp_avg.data_ptr(),
+                                              self.exp_avg_sq.data_ptr(), self.state.data_ptr(), self.lr,
+                                              self.betas[0], self.betas[1], self.eps, self.wd, 1.0, self.max_norm,
+                                              self.sq_norm.data_ptr(), st))
         if self.arena_bf16 is not None:
             N.check(lib.msf_fusion_pack_bf16(ctypes_ref(self.plan.shape), self.arena.data_ptr(),
                                              self.arena_bf16.data_ptr(), st))

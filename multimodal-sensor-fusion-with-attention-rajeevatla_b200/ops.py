@@ -429,3 +429,17 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, mn_major: bool = False, bias:
     N.check(N.lib().msf_gemm_bf16(_p(a), _p(b), _p(d), int(out_dtype == torch.bfloat16), m, n, k, a.stride(0),
                                   b.stride(0), d.stride(0), int(mn_major), _p(bias), int(relu), _stream()))
     return d
+
+
+def fusion_optimizer_step(plan: FusionPlan, params, grad, exp_avg, exp_avg_sq, train_state, lr=1e-3, beta1=0.9,
+                          beta2=0.999, eps=1e-8, weight_decay=1e-4, grad_scale=1.0, max_norm=0.0,
+                          sq_norm: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Global-norm clip + AdamW over a HybridFusion master arena (src/train.py:378-382,416-430) with the
+    dead query/key slots handled as pure weight decay.  ``train_state`` = int64 {seed, offset, step}
+    on the device (step 1-based).  Returns the gradient square-norm scratch (float64[1])."""
+    if sq_norm is None:
+        sq_norm = torch.zeros(1, dtype=torch.float64, device=params.device)
+    N.check(N.lib().msf_fusion_optimizer_step(ctypes.byref(plan.shape), _p(params), _p(grad), _p(exp_avg),
+                                              _p(exp_avg_sq), _p(train_state), lr, beta1, beta2, eps,
+                                              weight_decay, grad_scale, max_norm, _p(sq_norm), _stream()))
+    return sq_norm

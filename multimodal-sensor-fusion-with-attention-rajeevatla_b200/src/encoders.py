@@ -51,6 +51,13 @@ def _dense(layer: nn.Module, x: torch.Tensor, relu: bool = False) -> torch.Tenso
     return y.to(device=home, dtype=dtype)
 
 
+def _rnn_fp32(rnn: nn.Module, inp):
+    """Run the library recurrence in true fp32: cuDNN's RNN kernels default to TF32, which is
+    ~1e-4 away from the reference's CPU arithmetic."""
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        return rnn(inp)
+
+
 def _run_sequential(seq: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
     """An ``nn.Sequential`` with its Linear layers on the kernels; ``Linear -> ReLU`` pairs are fused."""
     mods = list(seq)
@@ -108,9 +115,9 @@ class SequenceEncoder(nn.Module):
             if lengths is not None:  # ragged windows: pack, like encoders.py:141-156
                 lens = lengths.to(device=sequence.device).to(torch.int64).cpu()
                 packed = nn.utils.rnn.pack_padded_sequence(sequence, lens, batch_first=True, enforce_sorted=False)
-                _, hidden = self.rnn(packed)
+                _, hidden = _rnn_fp32(self.rnn, packed)
             else:
-                _, hidden = self.rnn(sequence)
+                _, hidden = _rnn_fp32(self.rnn, sequence)
             state = hidden[0] if self.encoder_type == "lstm" else hidden
             return _dense(self.projection, self.dropout_layer(state[-1]))
 

@@ -139,3 +139,31 @@ def test_cross_entropy_and_optimizer_match_oracle():
     assert abs(float(sq.sqrt()) - float(g["opt/grad_norm"])) <= 1e-5
     ops.adamw_step(p, gr, m, v, step=1, lr=1e-3, weight_decay=1e-4, max_norm=1.0, sq_norm=sq)
     assert float((p.cpu() - flat("opt").cpu()).abs().max()) <= 1e-6
+
+
+def test_layout_aware_optimizer_matches_torch_adamw():
+    """msf_fusion_optimizer_step (dead q/k slots = weight decay only, live slots = AdamW, global-norm clip)
+    against the parameters torch.optim.AdamW + clip_grad_norm_ produced in the reference run (golden "opt/*")."""
+    from helpers import module_from_golden
+    ops = _ops()
+    g = Golden("fusion_pamap_small.npz")
+    plan = module_from_golden(g)._plan()
+    keys = [k for k, _, _ in plan.slots]
+    assert keys == list(g.group("sd").keys())
+    flat = lambda grp: torch.cat([g.t(f"{grp}/{k}").flatten() for k in keys]).cuda()
+    p, gr = flat("sd"), flat("grad")
+    p2 = p.clone()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    state = torch.tensor([0, 0, 1], dtype=torch.int64, device="cuda")
+    sq = ops.fusion_optimizer_step(plan, p, gr, m, v, state, lr=1e-3, weight_decay=1e-4, max_norm=1.0)
+    assert abs(float(sq.sqrt()) - float(g["opt/grad_norm"])) <= 1e-5
+    assert float((p.cpu() - flat("opt").cpu()).abs().max()) <= 1e-6
+    # identical to the generic flat AdamW, and the dead slots never grow moments
+    m2, v2 = torch.zeros_like(p2), torch.zeros_like(p2)
+    ops.adamw_step(p2, gr, m2, v2, step=1, lr=1e-3, weight_decay=1e-4, max_norm=1.0, sq_norm=ops.grad_sq_norm(gr))
+    assert float((p - p2).abs().max()) <= 1e-7 and float((m - m2).abs().max()) <= 1e-9
+    for key, off, shape in plan.slots:
+        if ".query_proj." in key or ".key_proj." in key:
+            n = int(np.prod(shape))
+            assert float(m[off:off + n].abs().max()) == 0.0 and float(v[off:off + n].abs().max()) == 0.0
+            assert torch.equal(p[off:off + n], (flat("sd")[off:off + n] * (1.0 - 1e-3 * 1e-4)))
