@@ -192,10 +192,20 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    t_start = time.perf_counter()
+
+    def mark(what):
+        if os.environ.get("MSF_BENCH_TRACE"):
+            print(f"[bench rank {rank} +{time.perf_counter() - t_start:6.1f}s] {what}", file=sys.stderr, flush=True)
+
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries exactly one JSON line: NCCL / library chatter written to fd 1 goes to stderr instead
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    mark("process group ready")
     pkg = importlib.import_module(PKG)
     engine_mod = importlib.import_module(PKG + ".engine")
     sys.path.insert(0, os.path.join(ROOT, PKG, "src"))
@@ -246,25 +256,41 @@ def run_ours(args):
         loss = eng.train_step(f, m, y)        # H2D from pinned memory inside the timed region
         losses.append(float(loss.item()))     # D2H read of the step's result
 
+    mark("engine and batches built")
     warm = max(3, args.warmup)
     before = lib.msf_launch_count()
     resident_step(0)
     torch.cuda.synchronize()
+    mark("first step (graph captured)")
     per_step_launches = eng_launches(lib, before, eng)
+    mark("launch count taken")
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ms = timed(resident_step, args.steps, warm)
     clocks = sampler.stop() if rank == 0 else None
+    mark("resident loop timed")
     ms_e2e = timed(e2e_step, max(5, min(args.steps, 50)), 3)
 
+    mark("e2e loop timed")
     # every rank runs the profiled steps: the eager step contains the gradient all-reduce
     kern = profile_dominant_kernel(torch, pkg, eng, ring, ring_n)
+    mark("kernel profile done")
+
+    def finish():
+        """Leave without tearing the NCCL communicator down: destroy_process_group() blocks while CUDA
+        graphs that captured collectives on it are alive, so drop the graphs, meet at a barrier and exit."""
+        if world > 1:
+            eng._train_graph = eng._infer_graph = None
+            torch.cuda.synchronize()
+            dist.barrier()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish()
         return
     peaks = _peaks()
     value = BATCH * world / (ms * 1e-3)
@@ -286,9 +312,8 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         cpu = oracle_cpu_throughput(torch, budget_s=12.0)
         line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
+    finish()
 
 
 def profile_dominant_kernel(torch, pkg, eng, ring, ring_n, steps=12):

@@ -24,23 +24,27 @@ def _maxabs(a, b):
 def test_sequence_encoder_matches_reference_golden(kind, where):
     g = Golden("encoders_small.npz")
     dev = "cuda" if where == "cuda" else "cpu"
+    # cpu_staged: the recurrence runs in PyTorch's CPU LSTM (the reference's own arithmetic) and only the
+    # projection on our kernel -> 1e-5.  cuda: the recurrence is cuDNN (library code, different summation
+    # order / gate approximations, ~1e-4 on gradients) -> 2e-4 for everything downstream of it.
+    tol = TOL if where == "cpu_staged" else 2e-4
     enc = dropin_encoders.SequenceEncoder(17, hidden_dim=32, output_dim=16, num_layers=2, encoder_type=kind, dropout=0.0)
     enc.load_state_dict(g.group(f"{kind}/sd"))
     enc = enc.to(dev).eval()
     x = g.t("seq/x").to(dev)
     out = enc(x)
     assert out.device.type == dev
-    assert _maxabs(out, g.t(f"{kind}/out")) <= TOL
+    assert _maxabs(out, g.t(f"{kind}/out")) <= tol
     if kind == "lstm":
-        assert _maxabs(enc(x, g.t("seq/lengths")), g.t("lstm/out_lengths")) <= TOL
+        assert _maxabs(enc(x, g.t("seq/lengths")), g.t("lstm/out_lengths")) <= tol
     enc.train()
     xg = x.clone().requires_grad_(True)
     out = enc(xg)
     (out * torch.linspace(-1, 1, 16, device=dev).unsqueeze(0)).sum().backward()
-    assert _maxabs(xg.grad, g.t(f"{kind}/gradx")) <= TOL
+    assert _maxabs(xg.grad, g.t(f"{kind}/gradx")) <= tol
     grads = dict(enc.named_parameters())
     for key, ref in g.group(f"{kind}/grad").items():
-        assert _maxabs(grads[key].grad, ref) <= 5 * TOL, key
+        assert _maxabs(grads[key].grad, ref) <= 5 * tol, key
 
 
 def test_mlp_encoder_matches_reference_golden():
