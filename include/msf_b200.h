@@ -187,6 +187,24 @@ int msf_fusion_optimizer_step(const msf_fusion_shape* shape, float* params, cons
                               float* exp_avg_sq, const uint64_t* train_state, float lr, float beta1, float beta2,
                               float eps, float weight_decay, float grad_scale, float max_norm, double* sq_norm,
                               void* stream);
+/* Data-parallel variant: gradient reduction over NVLink peer memory fused with clip + AdamW (one
+ * process per GPU).  grads[r] / stages[r] / reds[r] / sigs[r] are the peer-mapped (symmetric) gradient
+ * arena, staging arena, reduced-gradient arena (all msf_fusion_param_count floats) and 64-word uint64
+ * signal block (zero-initialised) of rank r, in rank order, as seen from THIS process.  Only stages,
+ * reds and sigs of the peers are written; nothing is read across NVLink.  Every rank must call it once per step with the same
+ * arguments; the call replaces all-reduce + msf_fusion_optimizer_step.  Each rank's gradient must be
+ * pre-scaled so that the SUM over ranks is the wanted gradient (engine: 1/(B*world)). */
+#define MSF_DP_MAX_RANKS 8
+typedef struct msf_dp_comm {
+  int32_t rank, world;
+  const float* grads[MSF_DP_MAX_RANKS];
+  float* stages[MSF_DP_MAX_RANKS];
+  float* reds[MSF_DP_MAX_RANKS];
+  uint64_t* sigs[MSF_DP_MAX_RANKS];
+} msf_dp_comm;
+int msf_dp_optimizer_step(const msf_fusion_shape* shape, const msf_dp_comm* comm, float* params, float* exp_avg,
+                          float* exp_avg_sq, const uint64_t* train_state, float lr, float beta1, float beta2,
+                          float eps, float weight_decay, float grad_scale, float max_norm, void* stream);
 /* train_state = DEVICE {seed, offset, step}: offset += 1, step += 1. */
 int msf_train_state_advance(uint64_t* train_state, void* stream);
 

@@ -54,6 +54,17 @@ class FusionCall(Structure):
     ]
 
 
+class DpComm(Structure):
+    _fields_ = [
+        ("rank", c_int32),
+        ("world", c_int32),
+        ("grads", c_void_p * 8),
+        ("stages", c_void_p * 8),
+        ("reds", c_void_p * 8),
+        ("sigs", c_void_p * 8),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/msf_b200.h declares
 PROTOTYPES = {
     "msf_abi_version": (c_int32, []),
@@ -91,6 +102,8 @@ PROTOTYPES = {
     "msf_fusion_optimizer_step": (c_int32, [POINTER(FusionShape), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                             c_float, c_float, c_float, c_float, c_float, c_float, c_float,
                                             c_void_p, c_void_p]),
+    "msf_dp_optimizer_step": (c_int32, [POINTER(FusionShape), POINTER(DpComm), c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_float, c_float, c_float, c_float, c_float, c_float, c_float, c_void_p]),
     "msf_train_state_advance": (c_int32, [c_void_p, c_void_p]),
     "msf_linear_forward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
                                      c_int32, c_void_p]),

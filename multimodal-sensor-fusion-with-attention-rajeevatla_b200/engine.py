@@ -32,7 +32,8 @@ class FusionEngine:
     def __init__(self, model, batch: int, *, precision: str = "bf16", lr: float = 1e-3,
                  weight_decay: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
                  label_smoothing: float = 0.05, max_grad_norm: float = 1.0, seed: int = 1234,
-                 process_group=None, use_graph: bool = True, device: Optional[torch.device] = None):
+                 process_group=None, use_graph: bool = True, device: Optional[torch.device] = None,
+                 comm: str = "auto"):
         self.dev = device or ops.require_cuda("FusionEngine")
         self.model = model.to(self.dev)
         self.plan = model._plan()
@@ -59,7 +60,23 @@ class FusionEngine:
                 n = prm.numel()
                 self.arena[off:off + n].copy_(prm.detach().reshape(-1))
                 prm.data = self.arena[off:off + n].view(shape)
-        self.grad = torch.zeros(plan.total, **f32)
+        # gradient exchange under data parallelism: "p2p" = fused reduce + AdamW kernels over NVLink peer
+        # memory (msf_dp_optimizer_step), "nccl" = all-reduce then optimizer, "auto" = p2p when available
+        self.comm, self.dp_comm = "none", None
+        self.grad = None
+        if self.world > 1 and comm in ("auto", "p2p"):
+            try:
+                self._setup_peer_memory()
+                self.comm = "p2p"
+            except Exception as exc:  # noqa: BLE001 - symmetric memory is optional plumbing
+                if comm == "p2p":
+                    raise
+                import sys
+                print(f"msf_b200: peer-memory gradient exchange unavailable ({exc}); using NCCL", file=sys.stderr)
+        if self.world > 1 and self.comm != "p2p":
+            self.comm = "nccl"
+        if self.grad is None:
+            self.grad = torch.zeros(plan.total, **f32)
         self.exp_avg = torch.zeros(plan.total, **f32)
         self.exp_avg_sq = torch.zeros(plan.total, **f32)
         self.arena_bf16 = None
@@ -107,6 +124,20 @@ class FusionEngine:
         c = self._call(True)
         c.grad_logits, c.grad_params = self.dlogits.data_ptr(), self.grad.data_ptr()
         N.check(lib.msf_fusion_backward(ctypes_ref(self.plan.shape), ctypes_ref(c), st))
+        if self.comm == "p2p":
+            # reduce-scatter + norm, then all-gather + clip + AdamW, both over NVLink peer memory
+            N.check(lib.msf_dp_optimizer_step(ctypes_ref(self.plan.shape), ctypes_ref(self.dp_comm),
+                                              self.arena.data_ptr(), self.exp_avg.data_ptr(),
+                                              self.exp_avg_sq.data_ptr(), self.state.data_ptr(), self.lr,
+                                              self.betas[0], self.betas[1], self.eps, self.wd, 1.0, self.max_norm, st))
+        else:
+            self._nccl_step(lib, st)
+        if self.arena_bf16 is not None:
+            N.check(lib.msf_fusion_pack_bf16(ctypes_ref(self.plan.shape), self.arena.data_ptr(),
+                                             self.arena_bf16.data_ptr(), st))
+        N.check(lib.msf_train_state_advance(self.state.data_ptr(), st))
+
+    def _nccl_step(self, lib, st) -> None:
         if self.world > 1:
             self._all_reduce_gradients()
         # global-norm clip + AdamW, skipping the dead q/k slots' moments (their gradients are exact zeros)
@@ -115,10 +146,34 @@ class FusionEngine:
                                               self.exp_avg_sq.data_ptr(), self.state.data_ptr(), self.lr,
                                               self.betas[0], self.betas[1], self.eps, self.wd, 1.0, self.max_norm,
                                               self.sq_norm.data_ptr(), st))
-        if self.arena_bf16 is not None:
-            N.check(lib.msf_fusion_pack_bf16(ctypes_ref(self.plan.shape), self.arena.data_ptr(),
-                                             self.arena_bf16.data_ptr(), st))
-        N.check(lib.msf_train_state_advance(self.state.data_ptr(), st))
+
+    def _setup_peer_memory(self) -> None:
+        """Gradient / reduced-gradient arenas and the signal block in symmetric memory, peer pointers
+        gathered through torch's rendezvous (plumbing only: the kernels are ours)."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        group = self.pg if self.pg is not None else dist.group.WORLD
+        n = self.plan.total
+        self.grad = symm_mem.empty(n, dtype=torch.float32, device=self.dev)
+        self.stage = symm_mem.empty(n, dtype=torch.float32, device=self.dev)
+        self.red = symm_mem.empty(n, dtype=torch.float32, device=self.dev)
+        self.sig = symm_mem.empty(64, dtype=torch.int64, device=self.dev)
+        handles = [symm_mem.rendezvous(t, group) for t in (self.grad, self.red, self.sig, self.stage)]
+        self.grad.zero_()
+        self.stage.zero_()
+        self.red.zero_()
+        self.sig.zero_()
+        torch.cuda.synchronize(self.dev)
+        dist.barrier(group)  # nobody signals into a block that is not zeroed yet
+        comm = N.DpComm()
+        comm.rank, comm.world = dist.get_rank(group), self.world
+        for r in range(self.world):
+            comm.grads[r] = int(handles[0].buffer_ptrs[r])
+            comm.reds[r] = int(handles[1].buffer_ptrs[r])
+            comm.sigs[r] = int(handles[2].buffer_ptrs[r])
+            comm.stages[r] = int(handles[3].buffer_ptrs[r])
+        self._symm_handles = handles
+        self.dp_comm = comm
 
     def _live_gradient_views(self):
         """Views of the gradient arena that can be non-zero: everything except the query/key projection

@@ -1,0 +1,65 @@
+"""Worker of tests/test_gpu_dp.py (launched with torch.distributed.run, one process per GPU): steps the fused
+train step on batch shards with the peer-memory exchange and with NCCL, and rank 0 also steps one process on
+the global batch.  Prints one JSON line (rank 0)."""
+import faulthandler
+import importlib
+import json
+import os
+import sys
+
+faulthandler.dump_traceback_later(100, exit=True)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+from conftest import load_pkg  # noqa: E402
+from helpers import PAMAP2, seeded_case  # noqa: E402
+
+GLOBAL_B, STEPS = 512, 3
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    engine = importlib.import_module(load_pkg().__name__ + ".engine")
+    sl = engine.shard_batch(GLOBAL_B, rank, world)
+    res = {}
+    for comm in ("p2p", "nccl"):
+        model, feats, mask, labels = seeded_case(PAMAP2, 256, 4, 25, GLOBAL_B, seed=31, device=dev)
+        eng = engine.FusionEngine(model, GLOBAL_B // world, precision="fp32", seed=9, use_graph=True, comm=comm)
+        assert eng.comm == comm, eng.comm
+        eng.p = 0.0
+        shard = ({k: v[sl] for k, v in feats.items()}, mask[sl], labels[sl])
+        for _ in range(STEPS):
+            eng.train_step(*shard)
+        torch.cuda.synchronize()
+        res[comm] = eng.arena.clone()
+    mine = res["p2p"]
+    other = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(other, mine)
+    out = {"replicas_identical": all(bool(torch.equal(o, mine)) for o in other),
+           "p2p_vs_nccl": float((res["p2p"] - res["nccl"]).abs().max())}
+    if rank == 0:
+        model, feats, mask, labels = seeded_case(PAMAP2, 256, 4, 25, GLOBAL_B, seed=31, device=dev)
+        start = torch.cat([p.detach().flatten() for p in model.parameters()]).clone()
+        single = engine.FusionEngine(model, GLOBAL_B, precision="fp32", seed=9, use_graph=False, comm="nccl")
+        single.world, single.comm, single.p = 1, "none", 0.0   # one process, the whole batch, no exchange
+        for _ in range(STEPS):
+            single.train_step(feats, mask, labels)
+        torch.cuda.synchronize()
+        out["p2p_vs_single"] = float((res["p2p"] - single.arena).abs().max())
+        out["moved"] = float((res["p2p"] - start).abs().max())
+        print(json.dumps(out), flush=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    sys.stdout.flush()
+    os._exit(0)  # communicator teardown with live CUDA graphs can block (see bench.py)
+
+
+if __name__ == "__main__":
+    main()
