@@ -72,14 +72,10 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ int g_dp_dbg = 0;
-__device__ __forceinline__ float4 ld_peer4(const float* p) {  // peer / freshly reduced data: never from a stale L1 line
+// data a peer pushed into this GPU's memory: system-scope load, never served from a stale L1 line
+__device__ __forceinline__ float4 ld_peer4(const float* p) {
   float4 v;
-  if (g_dp_dbg & 1) {
-    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-  } else {
-    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-  }
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ float ld_peer1(const float* p) {
