@@ -84,10 +84,12 @@ class FusionEngine:
             self.arena_bf16 = plan.pack_bf16(self.arena)
         self.ws = torch.empty(plan.workspace_bytes(B, self.prec), dtype=torch.uint8, device=dev)
 
-        # static I/O buffers (graph inputs / outputs)
-        self.x = [torch.zeros(B, d, **f32) for d in plan.dims]
-        self.mask = torch.ones(B, plan.M, **f32)
-        self.labels = torch.zeros(B, dtype=torch.int64, device=dev)
+        # static I/O buffers (graph inputs / outputs).  Two input slots: the host-facing stream API
+        # (train_stream) copies batch i+1 into one slot on a copy stream while the graph captured over the
+        # other slot computes batch i; the resident API uses slot 0 only.
+        self._slots = [([torch.zeros(B, d, **f32) for d in plan.dims], torch.ones(B, plan.M, **f32),
+                        torch.zeros(B, dtype=torch.int64, device=dev)) for _ in range(2)]
+        self.x, self.mask, self.labels = self._slots[0]
         self.logits = torch.zeros(B, plan.C, **f32)
         self.dlogits = torch.zeros(B, plan.C, **f32)
         self.row_loss = torch.zeros(B, **f32)
@@ -98,30 +100,33 @@ class FusionEngine:
         # {seed, offset, step}; step is 1-based when the optimizer kernel reads it
         self.state = torch.tensor([seed, 0, 1], dtype=torch.int64, device=dev)
         self._train_graph = None
+        self._train_graphs = [None, None]
         self._infer_graph = None
+        self._copy_stream = None
         self.launches_per_step = 0
 
     # -- enqueue helpers (all on the current stream) ---------------------------------
-    def _call(self, training: bool) -> N.FusionCall:
+    def _call(self, training: bool, slot: int = 0) -> N.FusionCall:
+        x, mask, _ = self._slots[slot]
         c = ops._make_call(self.plan, self.batch, self.prec, training and self.p > 0, self.p, 0, 0,
-                           self.arena, self.arena_bf16, self.x, self.mask, self.ws)
+                           self.arena, self.arena_bf16, x, mask, self.ws)
         c.rng_state = self.state.data_ptr()
         return c
 
-    def _enqueue_forward(self, training: bool) -> None:
-        c = self._call(training)
+    def _enqueue_forward(self, training: bool, slot: int = 0) -> None:
+        c = self._call(training, slot)
         c.logits = self.logits.data_ptr()
         N.check(N.lib().msf_fusion_forward(ctypes_ref(self.plan.shape), ctypes_ref(c), ops._stream()))
 
-    def _enqueue_train_step(self) -> None:
+    def _enqueue_train_step(self, slot: int = 0) -> None:
         lib = N.lib()
         st = ops._stream()
-        self._enqueue_forward(True)
+        self._enqueue_forward(True, slot)
         # mean over the GLOBAL batch: each rank scales by 1/(B*world), the all-reduce sums
-        N.check(lib.msf_cross_entropy(self.logits.data_ptr(), self.labels.data_ptr(), self.batch, self.plan.C,
-                                      self.smoothing, 1.0 / (self.batch * self.world), self.row_loss.data_ptr(),
-                                      self.loss.data_ptr(), self.dlogits.data_ptr(), st))
-        c = self._call(True)
+        N.check(lib.msf_cross_entropy(self.logits.data_ptr(), self._slots[slot][2].data_ptr(), self.batch,
+                                      self.plan.C, self.smoothing, 1.0 / (self.batch * self.world),
+                                      self.row_loss.data_ptr(), self.loss.data_ptr(), self.dlogits.data_ptr(), st))
+        c = self._call(True, slot)
         c.grad_logits, c.grad_params = self.dlogits.data_ptr(), self.grad.data_ptr()
         N.check(lib.msf_fusion_backward(ctypes_ref(self.plan.shape), ctypes_ref(c), st))
         if self.comm == "p2p":
@@ -220,44 +225,104 @@ class FusionEngine:
 
     # -- public API --------------------------------------------------------------------
     def load_batch(self, features: Dict[str, torch.Tensor] | Sequence[torch.Tensor],
-                   mask: Optional[torch.Tensor], labels: Optional[torch.Tensor] = None) -> int:
-        """Copy one batch (host-pinned or device tensors) into the static buffers.
-        Returns the bytes that crossed host->device."""
+                   mask: Optional[torch.Tensor], labels: Optional[torch.Tensor] = None, slot: int = 0) -> int:
+        """Copy one batch (host-pinned or device tensors) into the static buffers of `slot` on the current
+        stream.  Returns the bytes that crossed host->device."""
         feats = [features[m] for m in self.plan.names] if isinstance(features, dict) else list(features)
+        x, msk, lab = self._slots[slot]
         moved = 0
-        for dst, src in zip(self.x, feats):
+        for dst, src in zip(x, feats):
             dst.copy_(src, non_blocking=True)
             moved += src.numel() * src.element_size() if src.device.type == "cpu" else 0
         if mask is None:
-            self.mask.fill_(1.0)
+            msk.fill_(1.0)
         else:
-            self.mask.copy_(mask, non_blocking=True)
+            msk.copy_(mask, non_blocking=True)
             moved += mask.numel() * mask.element_size() if mask.device.type == "cpu" else 0
         if labels is not None:
-            self.labels.copy_(labels, non_blocking=True)
+            lab.copy_(labels, non_blocking=True)
             moved += labels.numel() * labels.element_size() if labels.device.type == "cpu" else 0
         return moved
+
+    def _replay_train(self, slot: int = 0) -> None:
+        if not self.use_graph:
+            self._enqueue_train_step(slot)
+            return
+        if self._train_graphs[slot] is None:
+            self._replay_train_capture_only(slot)
+        self._train_graphs[slot].replay()
 
     def train_step_resident(self) -> torch.Tensor:
         """One optimizer step on the batch already in the static buffers.
         Returns the (device) mean loss of this rank's shard scaled to the global batch."""
-        if self.use_graph:
-            if self._train_graph is None:
-                snap = (self.arena.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(), self.state.clone())
-                self._train_graph = self._capture(self._enqueue_train_step)
-                # the warm-up run inside _capture advanced the model once: roll it back
-                for dst, src in zip((self.arena, self.exp_avg, self.exp_avg_sq, self.state), snap):
-                    dst.copy_(src)
-                if self.arena_bf16 is not None:
-                    self.arena_bf16.copy_(self.plan.pack_bf16(self.arena))
-            self._train_graph.replay()
-        else:
-            self._enqueue_train_step()
+        self._replay_train(0)
         return self.loss
 
     def train_step(self, features, mask, labels) -> torch.Tensor:
         self.load_batch(features, mask, labels)
         return self.train_step_resident()
+
+    def train_stream(self, batches):
+        """Host-facing training loop: `batches` yields (features, mask, labels) on the host (pinned memory
+        makes the copies asynchronous); yields one Python-float loss per batch, in order.
+
+        Two-deep pipeline: while the graph captured over input slot s computes batch i, the host->device
+        copies of batch i+1 run on a copy stream into slot s^1, and the loss of batch i is read back
+        (device->pinned host) after batch i+1 has been enqueued, so neither PCIe direction stalls the
+        compute stream.  Every batch still crosses host->device and every loss device->host."""
+        dev = self.dev
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+            self._ev_ready = [torch.cuda.Event() for _ in range(2)]   # slot inputs landed
+            self._ev_free = [torch.cuda.Event() for _ in range(2)]    # graph over the slot finished
+            self._ev_loss = [torch.cuda.Event() for _ in range(2)]    # loss of the slot's step is on the host
+        if self.use_graph:
+            for s in range(2):                                        # capture before the pipeline starts
+                if self._train_graphs[s] is None:
+                    self._replay_train_capture_only(s)
+        cs = self._copy_stream
+        main = torch.cuda.current_stream(dev)
+
+        cs.wait_stream(main)
+
+        def stage(batch, slot):
+            cs.wait_event(self._ev_free[slot])   # no-op until the slot's first step has been recorded
+            with torch.cuda.stream(cs):
+                self.load_batch(batch[0], batch[1], batch[2], slot=slot)
+                self._ev_ready[slot].record(cs)
+
+        it = iter(batches)
+        nxt = next(it, None)
+        if nxt is None:
+            return
+        stage(nxt, 0)
+        slot, pending = 0, None
+        while nxt is not None:
+            main.wait_event(self._ev_ready[slot])
+            self._replay_train(slot)
+            self._ev_free[slot].record(main)
+            self._loss_host[slot:slot + 1].copy_(self.loss, non_blocking=True)
+            self._ev_loss[slot].record(main)
+            nxt = next(it, None)
+            if nxt is not None:
+                stage(nxt, slot ^ 1)
+            if pending is not None:
+                self._ev_loss[pending].synchronize()
+                yield float(self._loss_host[pending])
+            pending, slot = slot, slot ^ 1
+        self._ev_loss[pending].synchronize()
+        yield float(self._loss_host[pending])
+
+    def _replay_train_capture_only(self, slot: int) -> None:
+        """Capture the train graph over `slot` without leaving a net model update behind."""
+        snap = (self.arena.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(), self.state.clone())
+        self._train_graphs[slot] = self._capture(lambda: self._enqueue_train_step(slot))
+        for dst, src in zip((self.arena, self.exp_avg, self.exp_avg_sq, self.state), snap):
+            dst.copy_(src)
+        if self.arena_bf16 is not None:
+            self.arena_bf16.copy_(self.plan.pack_bf16(self.arena))
+        self._train_graph = self._train_graphs[0]
 
     def infer_resident(self):
         if self.use_graph:

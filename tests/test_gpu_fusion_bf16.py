@@ -197,3 +197,30 @@ def test_engine_bf16_tracks_fp32_engine():
     for a, b in zip(losses["fp32"], losses["bf16"]):
         assert abs(a - b) <= 2e-2, (losses,)
     assert float((params["fp32"] - params["bf16"]).abs().max()) <= 6.1e-3  # 3 Adam steps of lr 1e-3: sign flips of ~0 grads
+
+
+def test_train_stream_pipeline_equals_step_by_step():
+    """The 2-slot pipelined host-facing loop (H2D of batch i+1 overlapping step i, loss read one step late)
+    follows the blocking load_batch + train_step loop (bias gradients are fp32 atomic column sums, so two
+    runs agree to rounding, not bit for bit; Adam turns a sign flip of a ~0 gradient into 2*lr per step)."""
+    pkg = load_pkg()
+    engine = importlib.import_module(pkg.__name__ + ".engine")
+    batches = []
+    for i in range(5):
+        _, feats, mask, labels = seeded_case(PAMAP2, 256, 4, 25, 512, seed=40 + i, device="cpu")
+        batches.append(([f.pin_memory() for f in feats.values()], mask.pin_memory(), labels.pin_memory()))
+    out = {}
+    for mode in ("blocking", "stream"):
+        model, *_ = seeded_case(PAMAP2, 256, 4, 25, 512, seed=21, device="cuda")
+        eng = engine.FusionEngine(model, 512, precision="bf16", seed=5, use_graph=True)
+        if mode == "blocking":
+            losses = [float(eng.train_step(*b).item()) for b in batches]
+        else:
+            losses = list(eng.train_stream(iter(batches)))
+            assert list(eng.train_stream(iter([]))) == []
+        out[mode] = (losses, eng.arena.clone())
+    assert len(out["stream"][0]) == len(batches)
+    for a, b in zip(out["blocking"][0], out["stream"][0]):
+        assert abs(a - b) <= 1e-3 * abs(a), out
+    diff = (out["blocking"][1] - out["stream"][1]).abs()
+    assert float(diff.max()) <= 1.01e-2 and float(diff.mean()) <= 1e-4
