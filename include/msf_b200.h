@@ -126,6 +126,23 @@ int msf_fusion_pack_bf16(const msf_fusion_shape* shape, const float* params, voi
                          void* stream);
 int msf_fusion_forward(const msf_fusion_shape* shape, const msf_fusion_call* call, void* stream);
 int msf_fusion_backward(const msf_fusion_shape* shape, const msf_fusion_call* call, void* stream);
+/* One training pass of src/train.py:302-324 around the fusion model: forward, CrossEntropyLoss(label_smoothing)
+ * (mean over `batch`; d logits scaled by grad_scale, normally 1/(batch*world)) and backward, as one enqueue.
+ * call->logits receives the logits, call->grad_params the gradients, loss_out[0] the mean loss (may be NULL),
+ * row_loss (batch) is scratch.  With MSF_PREC_BF16 and num_classes <= 32, hidden <= 256 everything between
+ * the aggregated modality tokens and their gradients (gating softmax, classifier, loss, their backward) is ONE
+ * kernel; otherwise this is msf_fusion_forward + msf_cross_entropy + msf_fusion_backward and
+ * grad_logits_scratch (batch x C) is required. */
+int msf_fusion_train_pass(const msf_fusion_shape* shape, const msf_fusion_call* call, const int64_t* labels,
+                          float smoothing, float grad_scale, float* row_loss, float* loss_out,
+                          float* grad_logits_scratch, void* stream);
+/* Inference pass of src/eval.py:84-90: logits, then softmax -> max -> (confidence, prediction), with the
+ * softmax fused into the classifier epilogue on the tensor-core path. */
+int msf_fusion_infer_pass(const msf_fusion_shape* shape, const msf_fusion_call* call, float* conf, int64_t* pred,
+                          void* stream);
+/* Debugging aid: clock64 stamps (SM cycles) of the phases of CTA 0 in the last fused head-kernel launch
+ * (P0 start/end, then acquire/finish of E1..E4, P5 start/end).  Synchronises the device. */
+int msf_debug_head_stamps(int64_t* out16);
 /* HybridFusion.compute_adaptive_weights (src/fusion.py:429-479) stand-alone:
  * agg (M, B, H), gate_w (M, H), gate_b (M), mask (B, M) -> weights (B, M). */
 int msf_adaptive_weights(const float* agg, const float* gate_w, const float* gate_b, const float* mask,
@@ -187,6 +204,15 @@ int msf_fusion_optimizer_step(const msf_fusion_shape* shape, float* params, cons
                               float* exp_avg_sq, const uint64_t* train_state, float lr, float beta1, float beta2,
                               float eps, float weight_decay, float grad_scale, float max_norm, double* sq_norm,
                               void* stream);
+/* The same step fused with what follows it in a bf16 training loop: every live parameter is updated, its
+ * bf16 copy (and transposed copy) in the compute arena `params_bf16` rewritten from registers, and — if
+ * advance_state != 0 — train_state {seed, offset, step} moved on by the last CTA (offset += 1, step += 1),
+ * replacing msf_fusion_optimizer_step + msf_fusion_pack_bf16 + msf_train_state_advance. */
+int msf_fusion_optimizer_step_packed(const msf_fusion_shape* shape, float* params, const float* grad,
+                                     float* exp_avg, float* exp_avg_sq, uint64_t* train_state, float lr,
+                                     float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                                     float max_norm, double* sq_norm, void* params_bf16, int32_t advance_state,
+                                     void* stream);
 /* Data-parallel variant: gradient reduction over NVLink peer memory fused with clip + AdamW (one
  * process per GPU).  grads[r] / stages[r] / reds[r] / sigs[r] are the peer-mapped (symmetric) gradient
  * arena, staging arena, reduced-gradient arena (all msf_fusion_param_count floats) and 64-word uint64

@@ -81,6 +81,10 @@ PROTOTYPES = {
     "msf_fusion_pack_bf16": (c_int32, [POINTER(FusionShape), c_void_p, c_void_p, c_void_p]),
     "msf_fusion_forward": (c_int32, [POINTER(FusionShape), POINTER(FusionCall), c_void_p]),
     "msf_fusion_backward": (c_int32, [POINTER(FusionShape), POINTER(FusionCall), c_void_p]),
+    "msf_fusion_train_pass": (c_int32, [POINTER(FusionShape), POINTER(FusionCall), c_void_p, c_float, c_float,
+                                        c_void_p, c_void_p, c_void_p, c_void_p]),
+    "msf_fusion_infer_pass": (c_int32, [POINTER(FusionShape), POINTER(FusionCall), c_void_p, c_void_p, c_void_p]),
+    "msf_debug_head_stamps": (c_int32, [c_void_p]),
     "msf_adaptive_weights": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
                                        c_void_p, c_void_p]),
     "msf_dropout_mask": (c_int32, [c_uint64, c_uint64, c_int32, c_int32, c_int64, c_int64, c_float,
@@ -102,6 +106,9 @@ PROTOTYPES = {
     "msf_fusion_optimizer_step": (c_int32, [POINTER(FusionShape), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                             c_float, c_float, c_float, c_float, c_float, c_float, c_float,
                                             c_void_p, c_void_p]),
+    "msf_fusion_optimizer_step_packed": (c_int32, [POINTER(FusionShape), c_void_p, c_void_p, c_void_p, c_void_p,
+                                                   c_void_p, c_float, c_float, c_float, c_float, c_float, c_float,
+                                                   c_float, c_void_p, c_void_p, c_int32, c_void_p]),
     "msf_dp_optimizer_step": (c_int32, [POINTER(FusionShape), POINTER(DpComm), c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_float, c_float, c_float, c_float, c_float, c_float, c_float, c_void_p]),
     "msf_train_state_advance": (c_int32, [c_void_p, c_void_p]),

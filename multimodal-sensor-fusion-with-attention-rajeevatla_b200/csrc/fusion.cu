@@ -13,6 +13,11 @@ size_t fusion_bf16_arena_bytes(const Layout& L);
 int fusion_bf16_pack(const Layout& L, const float* params, void* arena, cudaStream_t st);
 int fusion_bf16_forward(const Layout& L, const msf_fusion_call* c, cudaStream_t st);
 int fusion_bf16_backward(const Layout& L, const msf_fusion_call* c, cudaStream_t st);
+bool fusion_bf16_head_fused(const Layout& L);
+int head_debug_stamps(long long* out16);
+int fusion_bf16_train(const Layout& L, const msf_fusion_call* c, const int64_t* labels, float smoothing,
+                      float grad_scale, float* row_loss, float* loss_out, cudaStream_t st);
+int fusion_bf16_infer(const Layout& L, const msf_fusion_call* c, float* conf, int64_t* pred, cudaStream_t st);
 
 static int check_call(const Layout& L, const msf_fusion_call* c, bool backward) {
   MSF_REQUIRE(c != nullptr, "null call");
@@ -99,6 +104,45 @@ int msf_fusion_backward(const msf_fusion_shape* shape, const msf_fusion_call* ca
   if ((rc = msf::check_call(L, call, true))) return rc;
   return call->precision == MSF_PREC_F32 ? msf::fusion_f32_backward(L, call, (cudaStream_t)stream)
                                          : msf::fusion_bf16_backward(L, call, (cudaStream_t)stream);
+}
+
+int msf_fusion_train_pass(const msf_fusion_shape* shape, const msf_fusion_call* call, const int64_t* labels,
+                          float smoothing, float grad_scale, float* row_loss, float* loss_out,
+                          float* grad_logits_scratch, void* stream) {
+  msf::Layout L;
+  int rc = msf::make_layout(shape, &L);
+  if (rc) return rc;
+  if ((rc = msf::check_call(L, call, false))) return rc;
+  MSF_REQUIRE(labels && row_loss && call->grad_params, "msf_fusion_train_pass: labels, row_loss and grad_params are required");
+  if (call->precision == MSF_PREC_BF16 && msf::fusion_bf16_head_fused(L))
+    return msf::fusion_bf16_train(L, call, labels, smoothing, grad_scale, row_loss, loss_out, (cudaStream_t)stream);
+  // un-fused composition (fp32 parity path, shapes outside the head kernel): same three steps
+  MSF_REQUIRE(grad_logits_scratch != nullptr, "msf_fusion_train_pass: this precision / shape needs grad_logits_scratch");
+  if ((rc = msf_fusion_forward(shape, call, stream))) return rc;
+  if ((rc = msf_cross_entropy(call->logits, labels, call->batch, L.C, smoothing, grad_scale, row_loss, loss_out,
+                              grad_logits_scratch, stream)))
+    return rc;
+  msf_fusion_call back = *call;
+  back.grad_logits = grad_logits_scratch;
+  return msf_fusion_backward(shape, &back, stream);
+}
+
+int msf_fusion_infer_pass(const msf_fusion_shape* shape, const msf_fusion_call* call, float* conf, int64_t* pred,
+                          void* stream) {
+  msf::Layout L;
+  int rc = msf::make_layout(shape, &L);
+  if (rc) return rc;
+  if ((rc = msf::check_call(L, call, false))) return rc;
+  MSF_REQUIRE(conf && pred, "msf_fusion_infer_pass: conf and pred are required");
+  if (call->precision == MSF_PREC_BF16 && msf::fusion_bf16_head_fused(L))
+    return msf::fusion_bf16_infer(L, call, conf, pred, (cudaStream_t)stream);
+  if ((rc = msf_fusion_forward(shape, call, stream))) return rc;
+  return msf_softmax_conf_pred(call->logits, call->batch, L.C, conf, pred, stream);
+}
+
+int msf_debug_head_stamps(int64_t* out16) {
+  MSF_REQUIRE(out16 != nullptr, "msf_debug_head_stamps: null output");
+  return msf::head_debug_stamps(reinterpret_cast<long long*>(out16));
 }
 
 }  // extern "C"

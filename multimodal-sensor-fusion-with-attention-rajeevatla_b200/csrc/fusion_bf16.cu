@@ -19,49 +19,12 @@
 
 #include "chain_gemm.cuh"
 #include "fusion_common.cuh"
+#include "fusion_bf16_layout.cuh"
+#include "head_gemm.cuh"
 #include "tc_gemm.cuh"
 
 namespace msf {
 
-typedef __nv_bfloat16 bf16;
-
-// ---------------------------------------------------------------------------
-// bf16 compute arena (element offsets) and workspace
-// ---------------------------------------------------------------------------
-struct ArenaBf16 {
-  size_t wp[MSF_MAX_MODALITIES], wpT[MSF_MAX_MODALITIES];  // [H][D_m], [D_m][H]
-  size_t wv, wo, wvT, woT;                                 // [pairs][H][H]
-  size_t w1, w1T;                                          // [H][H]
-  size_t w2;                                               // [C][H]
-  size_t w2T;                                              // [H][Cp]  (Cp = C rounded up to 8, zero padded)
-  size_t total;
-  int Cp;
-};
-
-static ArenaBf16 arena_layout(const Layout& L) {
-  ArenaBf16 a;
-  size_t off = 0;
-  auto take = [&](size_t n) {
-    const size_t o = off;
-    off += align_up(n, 128);  // 256-byte aligned tensors (TMA needs 16)
-    return o;
-  };
-  const size_t H = L.H;
-  a.Cp = (int)align_up(L.C, 8);
-  for (int m = 0; m < L.M; ++m) a.wp[m] = take(H * L.D[m]);
-  for (int m = 0; m < L.M; ++m) a.wpT[m] = take(H * L.D[m]);
-  const size_t pairs = L.num_pairs();
-  a.wv = take(pairs * H * H);
-  a.wo = take(pairs * H * H);
-  a.wvT = take(pairs * H * H);
-  a.woT = take(pairs * H * H);
-  a.w1 = take(H * H);
-  a.w1T = take(H * H);
-  a.w2 = take((size_t)L.C * H);
-  a.w2T = take(H * a.Cp);
-  a.total = off;
-  return a;
-}
 
 struct WsBf16 {
   bf16* xt[MSF_MAX_MODALITIES];  // [B][D_m]
@@ -569,14 +532,12 @@ static int check_ws(const WsBf16& ws, const msf_fusion_call* c) {
   return MSF_OK;
 }
 
-int fusion_bf16_forward(const Layout& L, const msf_fusion_call* c, cudaStream_t st) {
+// F0..F3: inputs -> aggregated modality tokens (ws.agg), gates in ws.G
+static int forward_front(const Layout& L, const msf_fusion_call* c, const WsBf16& ws, const ArenaBf16& A,
+                         cudaStream_t st) {
   const int64_t B = c->batch;
   const int M = L.M, H = L.H;
-  WsBf16 ws;
-  carve_bf16(L, B, c->workspace, &ws);
-  int rc = check_ws(ws, c);
-  if (rc) return rc;
-  const ArenaBf16 A = arena_layout(L);
+  int rc = MSF_OK;
   const bf16* W16 = reinterpret_cast<const bf16*>(c->params_bf16);
   const float* W = c->params;
   const DropCfg drop = make_drop(c);
@@ -699,6 +660,62 @@ int fusion_bf16_forward(const Layout& L, const msf_fusion_call* c, cudaStream_t 
     }
   
   }
+  return MSF_OK;
+}
+
+// Head of the network as ONE kernel (head_gemm.cu).  train: labels etc. must be set by the caller in `hl`.
+static int launch_head(const Layout& L, const msf_fusion_call* c, const WsBf16& ws, const ArenaBf16& A, HeadLaunch& hl,
+                       cudaStream_t st, const char* label) {
+  const int64_t B = c->batch;
+  const int M = L.M, H = L.H;
+  const bf16* W16 = reinterpret_cast<const bf16*>(c->params_bf16);
+  const float* W = c->params;
+  int rc;
+  if ((rc = tc_encode_map(&hl.map_w1, W16 + A.w1, H, H, H, 1, 0, 64, H))) return rc;
+  if ((rc = tc_encode_map(&hl.map_w2, W16 + A.w2, L.C, H, H, 1, 0, 64, 32))) return rc;
+  if ((rc = tc_encode_map(&hl.map_w2t, W16 + A.w2T, H, A.Cp, A.Cp, 1, 0, 64, H))) return rc;
+  if ((rc = tc_encode_map(&hl.map_w1t, W16 + A.w1T, H, H, H, 1, 0, 64, H))) return rc;
+  if ((rc = tc_encode_map(&hl.map_fused, ws.fused, B, H, H, 1, 0, 64, 128))) return rc;
+  if ((rc = tc_encode_map(&hl.map_hr, ws.Hr, B, H, H, 1, 0, 64, 128))) return rc;
+  if ((rc = tc_encode_map(&hl.map_dh1, ws.dH1, B, H, H, 1, 0, 64, 128))) return rc;
+  hl.M = M; hl.H = H; hl.C = L.C; hl.Cp = A.Cp; hl.rows = (int)B;
+  hl.agg = ws.agg;
+  for (int m = 0; m < M; ++m) {
+    hl.gate_w[m] = W + L.gate_w[m];
+    hl.gate_b[m] = W + L.gate_b[m];
+    hl.inv_cnt[m] = 1.0f / (float)L.mean_count(m);
+  }
+  hl.mask = c->mask; hl.soft = ws.soft; hl.w = ws.w; hl.w_out = c->fusion_weights;
+  hl.b1 = W + L.cls_b1; hl.b2 = W + L.cls_b2;
+  hl.logits = c->logits;
+  hl.drop = make_drop(c);
+  return head_launch(hl, st, label);
+}
+
+static bool use_head(const Layout& L) { return head_eligible(L.H, L.M, L.C) && !getenv("MSF_NO_HEAD"); }
+
+static int export_gates(const Layout& L, const msf_fusion_call* c, const WsBf16& ws, cudaStream_t st);
+
+int fusion_bf16_forward(const Layout& L, const msf_fusion_call* c, cudaStream_t st) {
+  const int64_t B = c->batch;
+  const int M = L.M, H = L.H;
+  WsBf16 ws;
+  carve_bf16(L, B, c->workspace, &ws);
+  int rc = check_ws(ws, c);
+  if (rc) return rc;
+  const ArenaBf16 A = arena_layout(L);
+  const bf16* W16 = reinterpret_cast<const bf16*>(c->params_bf16);
+  const float* W = c->params;
+  const DropCfg drop = make_drop(c);
+  if ((rc = forward_front(L, c, ws, A, st))) return rc;
+
+  if (use_head(L)) {  // F4 + F5 + F6 in one kernel
+    HeadLaunch hl;
+    memset(&hl, 0, sizeof(hl));
+    hl.train = 0; hl.store_acts = 1;
+    if ((rc = launch_head(L, c, ws, A, hl, st, "HEAD gating+classifier"))) return rc;
+    return export_gates(L, c, ws, st);
+  }
 
   {  // F4
     Tail16Args a;
@@ -741,6 +758,12 @@ int fusion_bf16_forward(const Layout& L, const msf_fusion_call* c, cudaStream_t 
     if ((rc = tb.flush())) return rc;
   }
 
+  return export_gates(L, c, ws, st);
+}
+
+static int export_gates(const Layout& L, const msf_fusion_call* c, const WsBf16& ws, cudaStream_t st) {
+  const int64_t B = c->batch;
+  const int M = L.M, pairs = L.num_pairs();
   if (c->attn_gates && pairs > 0) {
     const long long ng = (long long)pairs * B * L.heads;
     for (int q = 0; q < M; ++q)
@@ -755,6 +778,9 @@ int fusion_bf16_forward(const Layout& L, const msf_fusion_call* c, cudaStream_t 
   return MSF_OK;
 }
 
+static int backward_back(const Layout& L, const msf_fusion_call* c, const WsBf16& ws, const ArenaBf16& A,
+                         cudaStream_t st, bool head_fused);
+
 int fusion_bf16_backward(const Layout& L, const msf_fusion_call* c, cudaStream_t st) {
   const int64_t B = c->batch;
   const int M = L.M, H = L.H, C = L.C;
@@ -768,9 +794,6 @@ int fusion_bf16_backward(const Layout& L, const msf_fusion_call* c, cudaStream_t
   const float* W = c->params;
   float* dW = c->grad_params;
   const DropCfg drop = make_drop(c);
-  const long long BH = (long long)B * H;
-  const int pairs = L.num_pairs();
-  const int bnH = block_n_for(H);
   const int Cp = A.Cp;
 
   // dead query/key projections and every slot accumulated below start from exact zeros
@@ -818,6 +841,23 @@ int fusion_bf16_backward(const Layout& L, const msf_fusion_call* c, cudaStream_t
     tail16_bwd_kernel<<<(unsigned)ceil_div(B, 8), 256, 0, st>>>(a);
     MSF_LAUNCH_CHECK();
   }
+  return backward_back(L, c, ws, A, st, false);
+}
+
+// From d aggregated (ws.dS) back to the inputs, plus every bias / weight gradient.  head_fused: the head
+// kernel already produced the classifier.3 bias gradient.
+static int backward_back(const Layout& L, const msf_fusion_call* c, const WsBf16& ws, const ArenaBf16& A,
+                         cudaStream_t st, bool head_fused) {
+  const int64_t B = c->batch;
+  const int M = L.M, H = L.H, C = L.C;
+  int rc = MSF_OK;
+  const bf16* W16 = reinterpret_cast<const bf16*>(c->params_bf16);
+  float* dW = c->grad_params;
+  const DropCfg drop = make_drop(c);
+  const long long BH = (long long)B * H;
+  const int pairs = L.num_pairs();
+  const int bnH = block_n_for(H);
+  const int Cp = A.Cp;
   const bool use_chain = chain_eligible(H, M) && !getenv("MSF_NO_CHAIN");
   if (use_chain) {  // B5 + B7 chained per (window tile, key): dV goes straight from the epilogue into the value_proj dgrad
     ChainLaunch C;
@@ -918,7 +958,7 @@ int fusion_bf16_backward(const Layout& L, const msf_fusion_call* c, cudaStream_t
       p.coef = coef; p.coef_ld = coef_ld; p.dst = dst;
       cs[nc++] = p;
     };
-    add(c->grad_logits, 1, C, C, nullptr, 0, dW + L.cls_b2);
+    if (!head_fused) add(c->grad_logits, 1, C, C, nullptr, 0, dW + L.cls_b2);
     add(ws.dH1, 0, H, H, nullptr, 0, dW + L.cls_b1);
     for (int q = 0; q < M; ++q) {
       add(ws.agg + (long long)q * BH, 0, H, H, ws.ds + q, M, dW + L.gate_w[q]);   // d gate_w_q = sum_r ds[r,q] agg_q[r,:]
@@ -979,5 +1019,50 @@ int fusion_bf16_backward(const Layout& L, const msf_fusion_call* c, cudaStream_t
   MSF_CHECK_CUDA(cudaStreamWaitEvent(st, side->join, 0));
   return MSF_OK;
 }
+
+// One training pass: forward, CE(label smoothing) and backward with the head of the network fused into
+// one kernel (no logits / d logits round trip, 6 launches fewer than forward + msf_cross_entropy + backward).
+int fusion_bf16_train(const Layout& L, const msf_fusion_call* c, const int64_t* labels, float smoothing,
+                      float grad_scale, float* row_loss, float* loss_out, cudaStream_t st) {
+  const int64_t B = c->batch;
+  WsBf16 ws;
+  carve_bf16(L, B, c->workspace, &ws);
+  int rc = check_ws(ws, c);
+  if (rc) return rc;
+  MSF_REQUIRE(c->grad_params && c->logits && labels && row_loss, "train pass needs grad_params, logits, labels, row_loss");
+  MSF_REQUIRE(use_head(L), "fused train pass not available for this shape");
+  const ArenaBf16 A = arena_layout(L);
+  float* dW = c->grad_params;
+  MSF_CHECK_CUDA(cudaMemsetAsync(dW, 0, (size_t)L.total * sizeof(float), st));
+  if ((rc = forward_front(L, c, ws, A, st))) return rc;
+  HeadLaunch hl;
+  memset(&hl, 0, sizeof(hl));
+  hl.train = 1; hl.store_acts = 1;
+  hl.labels = reinterpret_cast<const long long*>(labels);
+  hl.smoothing = smoothing; hl.grad_scale = grad_scale; hl.row_loss = row_loss; hl.loss_out = loss_out;
+  hl.dlog = ws.dlog; hl.db2 = dW + L.cls_b2; hl.dS = ws.dS; hl.ds = ws.ds;
+  if ((rc = launch_head(L, c, ws, A, hl, st, "HEAD gating+classifier+CE fwd/bwd"))) return rc;
+  if ((rc = export_gates(L, c, ws, st))) return rc;
+  return backward_back(L, c, ws, A, st, true);
+}
+
+// Inference pass: logits plus softmax -> (confidence, prediction) from the head kernel's epilogue.
+int fusion_bf16_infer(const Layout& L, const msf_fusion_call* c, float* conf, int64_t* pred, cudaStream_t st) {
+  WsBf16 ws;
+  carve_bf16(L, c->batch, c->workspace, &ws);
+  int rc = check_ws(ws, c);
+  if (rc) return rc;
+  MSF_REQUIRE(use_head(L), "fused inference pass not available for this shape");
+  const ArenaBf16 A = arena_layout(L);
+  if ((rc = forward_front(L, c, ws, A, st))) return rc;
+  HeadLaunch hl;
+  memset(&hl, 0, sizeof(hl));
+  hl.train = 0; hl.store_acts = 0;
+  hl.conf = conf; hl.pred = reinterpret_cast<long long*>(pred);
+  if ((rc = launch_head(L, c, ws, A, hl, st, "HEAD gating+classifier+softmax"))) return rc;
+  return export_gates(L, c, ws, st);
+}
+
+bool fusion_bf16_head_fused(const Layout& L) { return use_head(L); }
 
 }  // namespace msf

@@ -217,7 +217,42 @@ __global__ void __launch_bounds__(256) dropout_mask_kernel(DropCfg d, int site, 
   }
 }
 
+static void live_segments(const Layout& L, ArenaSegs* segs) {
+  memset(segs, 0, sizeof(*segs));
+  auto add = [&](long long begin, long long count, int dead) {
+    if (count <= 0) return;
+    segs->s[segs->n].begin = begin; segs->s[segs->n].count = count; segs->s[segs->n].dead = dead;
+    ++segs->n;
+  };
+  const long long half = 2 * ((long long)L.H * L.H + L.H);
+  add(0, L.pair_base, 0);
+  for (int p = 0; p < L.num_pairs(); ++p) {
+    add(L.pair_base + p * L.pair_stride, half, 1);         // query_proj + key_proj: dead
+    add(L.pair_base + p * L.pair_stride + half, half, 0);  // value_proj + out_proj
+  }
+  const long long tail = L.pair_base + (long long)L.num_pairs() * L.pair_stride;
+  add(tail, L.total - tail, 0);
+}
+
 }  // namespace
+
+// sq_norm[0] = sum of g^2 over the live slots (the dead query/key slots hold exact zeros)
+int fusion_live_sq_norm(const Layout& L, const float* grad, double* sq_norm, cudaStream_t st) {
+  ArenaSegs segs;
+  live_segments(L, &segs);
+  MSF_CHECK_CUDA(cudaMemsetAsync(sq_norm, 0, sizeof(double), st));
+  dim3 grid(24, (unsigned)segs.n);
+  seg_sq_norm_kernel<<<grid, 256, 0, st>>>(segs, grad, sq_norm);
+  MSF_LAUNCH_CHECK();
+  return MSF_OK;
+}
+
+bool fusion_bf16_eligible(const Layout& L);
+int fusion_bf16_opt_pack(const Layout& L, float* params, const float* grad, float* exp_avg, float* exp_avg_sq,
+                         uint64_t* train_state, float lr, float beta1, float beta2, float eps, float wd,
+                         float grad_scale, float max_norm, double* sq_norm, void* arena_v, int advance,
+                         cudaStream_t st);
+
 }  // namespace msf
 
 extern "C" {
@@ -272,31 +307,34 @@ int msf_fusion_optimizer_step(const msf_fusion_shape* shape, float* params, cons
   if (rc) return rc;
   MSF_REQUIRE(params && grad && exp_avg && exp_avg_sq && train_state && sq_norm, "msf_fusion_optimizer_step: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = msf::fusion_live_sq_norm(L, grad, sq_norm, st))) return rc;
   msf::ArenaSegs segs;
-  memset(&segs, 0, sizeof(segs));
-  auto add = [&](long long begin, long long count, int dead) {
-    if (count <= 0) return;
-    segs.s[segs.n].begin = begin; segs.s[segs.n].count = count; segs.s[segs.n].dead = dead;
-    ++segs.n;
-  };
-  const long long half = 2 * ((long long)L.H * L.H + L.H);
-  add(0, L.pair_base, 0);
-  for (int p = 0; p < L.num_pairs(); ++p) {
-    add(L.pair_base + p * L.pair_stride, half, 1);         // query_proj + key_proj: dead
-    add(L.pair_base + p * L.pair_stride + half, half, 0);  // value_proj + out_proj
-  }
-  const long long tail = L.pair_base + (long long)L.num_pairs() * L.pair_stride;
-  add(tail, L.total - tail, 0);
-  MSF_CHECK_CUDA(cudaMemsetAsync(sq_norm, 0, sizeof(double), st));
-  dim3 grid(24, (unsigned)segs.n);
-  msf::seg_sq_norm_kernel<<<grid, 256, 0, st>>>(segs, grad, sq_norm);
-  MSF_LAUNCH_CHECK();
+  msf::live_segments(L, &segs);
   msf::AdamCfg c{lr, beta1, beta2, eps, weight_decay, grad_scale, max_norm};
   dim3 grid2(48, (unsigned)segs.n);
   msf::seg_adamw_kernel<<<grid2, 256, 0, st>>>(segs, c, params, grad, exp_avg, exp_avg_sq, sq_norm,
                                                 reinterpret_cast<const unsigned long long*>(train_state));
   MSF_LAUNCH_CHECK();
   return MSF_OK;
+}
+
+int msf_fusion_optimizer_step_packed(const msf_fusion_shape* shape, float* params, const float* grad,
+                                     float* exp_avg, float* exp_avg_sq, uint64_t* train_state, float lr,
+                                     float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                                     float max_norm, double* sq_norm, void* params_bf16, int32_t advance_state,
+                                     void* stream) {
+  msf::Layout L;
+  int rc = msf::make_layout(shape, &L);
+  if (rc) return rc;
+  MSF_REQUIRE(params && grad && exp_avg && exp_avg_sq && train_state && sq_norm && params_bf16,
+              "msf_fusion_optimizer_step_packed: null pointer");
+  if (!msf::fusion_bf16_eligible(L)) {
+    msf::set_error("shape not eligible for the tensor-core path");
+    return MSF_E_UNSUPPORTED;
+  }
+  return msf::fusion_bf16_opt_pack(L, params, grad, exp_avg, exp_avg_sq, train_state, lr, beta1, beta2, eps,
+                                   weight_decay, grad_scale, max_norm, sq_norm, params_bf16, advance_state,
+                                   (cudaStream_t)stream);
 }
 
 int msf_train_state_advance(uint64_t* train_state, void* stream) {

@@ -121,14 +121,14 @@ class FusionEngine:
     def _enqueue_train_step(self, slot: int = 0) -> None:
         lib = N.lib()
         st = ops._stream()
-        self._enqueue_forward(True, slot)
-        # mean over the GLOBAL batch: each rank scales by 1/(B*world), the all-reduce sums
-        N.check(lib.msf_cross_entropy(self.logits.data_ptr(), self._slots[slot][2].data_ptr(), self.batch,
-                                      self.plan.C, self.smoothing, 1.0 / (self.batch * self.world),
-                                      self.row_loss.data_ptr(), self.loss.data_ptr(), self.dlogits.data_ptr(), st))
+        # forward + CE(label smoothing) + backward as one enqueue (msf_fusion_train_pass).  Mean over the
+        # GLOBAL batch: each rank scales by 1/(B*world), the gradient exchange sums.
         c = self._call(True, slot)
-        c.grad_logits, c.grad_params = self.dlogits.data_ptr(), self.grad.data_ptr()
-        N.check(lib.msf_fusion_backward(ctypes_ref(self.plan.shape), ctypes_ref(c), st))
+        c.logits, c.grad_params = self.logits.data_ptr(), self.grad.data_ptr()
+        N.check(lib.msf_fusion_train_pass(ctypes_ref(self.plan.shape), ctypes_ref(c),
+                                          self._slots[slot][2].data_ptr(), self.smoothing,
+                                          1.0 / (self.batch * self.world), self.row_loss.data_ptr(),
+                                          self.loss.data_ptr(), self.dlogits.data_ptr(), st))
         if self.comm == "p2p":
             # reduce-scatter + norm, then all-gather + clip + AdamW, both over NVLink peer memory
             N.check(lib.msf_dp_optimizer_step(ctypes_ref(self.plan.shape), ctypes_ref(self.dp_comm),
@@ -136,21 +136,30 @@ class FusionEngine:
                                               self.exp_avg_sq.data_ptr(), self.state.data_ptr(), self.lr,
                                               self.betas[0], self.betas[1], self.eps, self.wd, 1.0, self.max_norm, st))
         else:
-            self._nccl_step(lib, st)
+            if self._nccl_step(lib, st):
+                return   # optimizer, bf16 re-pack and state advance were one launch
         if self.arena_bf16 is not None:
             N.check(lib.msf_fusion_pack_bf16(ctypes_ref(self.plan.shape), self.arena.data_ptr(),
                                              self.arena_bf16.data_ptr(), st))
         N.check(lib.msf_train_state_advance(self.state.data_ptr(), st))
 
-    def _nccl_step(self, lib, st) -> None:
+    def _nccl_step(self, lib, st) -> bool:
         if self.world > 1:
             self._all_reduce_gradients()
+        if self.arena_bf16 is not None:
+            # clip + AdamW + bf16 re-pack + train-state advance in one kernel
+            N.check(lib.msf_fusion_optimizer_step_packed(
+                ctypes_ref(self.plan.shape), self.arena.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
+                self.exp_avg_sq.data_ptr(), self.state.data_ptr(), self.lr, self.betas[0], self.betas[1], self.eps,
+                self.wd, 1.0, self.max_norm, self.sq_norm.data_ptr(), self.arena_bf16.data_ptr(), 1, st))
+            return True
         # global-norm clip + AdamW, skipping the dead q/k slots' moments (their gradients are exact zeros)
         N.check(lib.msf_fusion_optimizer_step(ctypes_ref(self.plan.shape), self.arena.data_ptr(),
                                               self.grad.data_ptr(), self.exp_avg.data_ptr(),
                                               self.exp_avg_sq.data_ptr(), self.state.data_ptr(), self.lr,
                                               self.betas[0], self.betas[1], self.eps, self.wd, 1.0, self.max_norm,
                                               self.sq_norm.data_ptr(), st))
+        return False
 
     def _setup_peer_memory(self) -> None:
         """Gradient / reduced-gradient arenas and the signal block in symmetric memory, peer pointers
@@ -205,9 +214,10 @@ class FusionEngine:
         torch.distributed.all_reduce(self.grad, group=self.pg)
 
     def _enqueue_inference(self) -> None:
-        self._enqueue_forward(False)
-        N.check(N.lib().msf_softmax_conf_pred(self.logits.data_ptr(), self.batch, self.plan.C,
-                                              self.conf.data_ptr(), self.pred.data_ptr(), ops._stream()))
+        c = self._call(False)
+        c.logits = self.logits.data_ptr()
+        N.check(N.lib().msf_fusion_infer_pass(ctypes_ref(self.plan.shape), ctypes_ref(c), self.conf.data_ptr(),
+                                              self.pred.data_ptr(), ops._stream()))
 
     def _capture(self, fn):
         if not self.use_graph:

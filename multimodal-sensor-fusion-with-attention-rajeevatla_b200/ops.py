@@ -133,7 +133,7 @@ class FusionPlan:
         N.check(N.lib().msf_arena_scatter(_p(self._table(tensors)), len(tensors), self.total, _p(arena), _stream()))
 
     def pack_bf16(self, arena: torch.Tensor) -> torch.Tensor:
-        out = torch.empty(self.bf16_arena_bytes(), dtype=torch.uint8, device=arena.device)
+        out = torch.zeros(self.bf16_arena_bytes(), dtype=torch.uint8, device=arena.device)
         N.check(N.lib().msf_fusion_pack_bf16(ctypes.byref(self.shape), _p(arena), _p(out), _stream()))
         return out
 
@@ -208,6 +208,54 @@ def fusion_backward_raw(plan: FusionPlan, arena: torch.Tensor, xs: Sequence[torc
         dxs.append(dx)
     N.check(N.lib().msf_fusion_backward(ctypes.byref(plan.shape), ctypes.byref(call), _stream()))
     return grad_arena, dxs
+
+
+def fusion_train_pass_raw(plan: FusionPlan, arena: torch.Tensor, xs: Sequence[torch.Tensor],
+                          mask: Optional[torch.Tensor], labels: torch.Tensor, *, smoothing: float = 0.0,
+                          grad_scale: Optional[float] = None, precision: int = N.MSF_PREC_F32,
+                          training: bool = True, p: float = 0.0, seed: int = 0, offset: int = 0,
+                          arena_bf16: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None):
+    """One msf_fusion_train_pass call: forward + CE(label smoothing) + backward.
+    Returns ``(logits, loss[1], grad_arena, fusion_weights, gates)``."""
+    dev = arena.device
+    B = xs[0].shape[0]
+    if workspace is None:
+        workspace = torch.empty(plan.workspace_bytes(B, precision), dtype=torch.uint8, device=dev)
+    f32 = dict(dtype=torch.float32, device=dev)
+    logits = torch.empty(B, plan.C, **f32)
+    scratch = torch.empty(B, plan.C, **f32)
+    row = torch.empty(B, **f32)
+    loss = torch.empty(1, **f32)
+    grad = torch.empty(plan.total, **f32)
+    fw = torch.empty(B, plan.M, **f32)
+    gates = torch.empty(plan.M * (plan.M - 1), B, plan.heads, **f32)
+    call = _make_call(plan, B, precision, training, p, seed, offset, arena, arena_bf16, xs, mask, workspace)
+    call.logits, call.grad_params = _p(logits), _p(grad)
+    call.fusion_weights, call.attn_gates = _p(fw), _p(gates)
+    labels = labels.to(torch.int64).contiguous()
+    scale = (1.0 / B) if grad_scale is None else grad_scale
+    N.check(N.lib().msf_fusion_train_pass(ctypes.byref(plan.shape), ctypes.byref(call), _p(labels),
+                                          float(smoothing), float(scale), _p(row), _p(loss), _p(scratch),
+                                          _stream()))
+    return logits, loss, grad, fw, gates
+
+
+def fusion_infer_pass_raw(plan: FusionPlan, arena: torch.Tensor, xs: Sequence[torch.Tensor],
+                          mask: Optional[torch.Tensor], *, precision: int = N.MSF_PREC_F32,
+                          arena_bf16: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None):
+    """One msf_fusion_infer_pass call: ``(logits, conf, pred)`` (src/eval.py:84-90)."""
+    dev = arena.device
+    B = xs[0].shape[0]
+    if workspace is None:
+        workspace = torch.empty(plan.workspace_bytes(B, precision), dtype=torch.uint8, device=dev)
+    logits = torch.empty(B, plan.C, dtype=torch.float32, device=dev)
+    conf = torch.empty(B, dtype=torch.float32, device=dev)
+    pred = torch.empty(B, dtype=torch.int64, device=dev)
+    call = _make_call(plan, B, precision, False, 0.0, 0, 0, arena, arena_bf16, xs, mask, workspace)
+    call.logits = _p(logits)
+    N.check(N.lib().msf_fusion_infer_pass(ctypes.byref(plan.shape), ctypes.byref(call), _p(conf), _p(pred),
+                                          _stream()))
+    return logits, conf, pred
 
 
 class HybridFusionFunction(torch.autograd.Function):
@@ -442,4 +490,18 @@ def fusion_optimizer_step(plan: FusionPlan, params, grad, exp_avg, exp_avg_sq, t
     N.check(N.lib().msf_fusion_optimizer_step(ctypes.byref(plan.shape), _p(params), _p(grad), _p(exp_avg),
                                               _p(exp_avg_sq), _p(train_state), lr, beta1, beta2, eps,
                                               weight_decay, grad_scale, max_norm, _p(sq_norm), _stream()))
+    return sq_norm
+
+
+def fusion_optimizer_step_packed(plan: FusionPlan, params, grad, exp_avg, exp_avg_sq, train_state, arena_bf16,
+                                 lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-4, grad_scale=1.0,
+                                 max_norm=0.0, sq_norm: Optional[torch.Tensor] = None,
+                                 advance: bool = True) -> torch.Tensor:
+    """``fusion_optimizer_step`` fused with the bf16 re-pack of the compute arena and the advance of
+    ``train_state`` (one launch instead of three)."""
+    if sq_norm is None:
+        sq_norm = torch.zeros(1, dtype=torch.float64, device=params.device)
+    N.check(N.lib().msf_fusion_optimizer_step_packed(
+        ctypes.byref(plan.shape), _p(params), _p(grad), _p(exp_avg), _p(exp_avg_sq), _p(train_state), lr, beta1,
+        beta2, eps, weight_decay, grad_scale, max_norm, _p(sq_norm), _p(arena_bf16), int(advance), _stream()))
     return sq_norm

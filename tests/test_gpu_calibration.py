@@ -167,3 +167,33 @@ def test_layout_aware_optimizer_matches_torch_adamw():
             n = int(np.prod(shape))
             assert float(m[off:off + n].abs().max()) == 0.0 and float(v[off:off + n].abs().max()) == 0.0
             assert torch.equal(p[off:off + n], (flat("sd")[off:off + n] * (1.0 - 1e-3 * 1e-4)))
+
+
+def test_packed_optimizer_step_equals_step_plus_pack():
+    """msf_fusion_optimizer_step_packed = msf_fusion_optimizer_step + msf_fusion_pack_bf16 +
+    msf_train_state_advance, bit for bit (same arithmetic, one launch), over three steps (config-2 shape)."""
+    from helpers import PAMAP2, seeded_case
+    ops = _ops()
+    model, *_ = seeded_case(PAMAP2, 256, 4, 25, 8, seed=3, device="cuda")
+    plan = model._plan()
+    own = dict(model.named_parameters())
+    pa = plan.gather([own[k].detach() for k, _, _ in plan.slots])
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    gr = torch.randn(pa.shape, generator=gen, device="cuda") * 1e-2
+    for key, off, shape in plan.slots:   # dead query/key slots carry exact-zero gradients
+        if ".query_proj." in key or ".key_proj." in key:
+            gr[off:off + int(np.prod(shape))] = 0.0
+    pb = pa.clone()
+    ma, va, mb, vb = (torch.zeros_like(pa) for _ in range(4))
+    sa = torch.tensor([7, 3, 1], dtype=torch.int64, device="cuda")
+    sb = sa.clone()
+    a16 = plan.pack_bf16(pa)
+    for step in range(3):
+        gstep = gr * (1.0 + 0.25 * step)
+        ops.fusion_optimizer_step(plan, pa, gstep, ma, va, sa, lr=1e-3, weight_decay=1e-4, max_norm=1.0)
+        ref16 = plan.pack_bf16(pa)
+        sa[1:] += 1
+        ops.fusion_optimizer_step_packed(plan, pb, gstep, mb, vb, sb, a16, lr=1e-3, weight_decay=1e-4, max_norm=1.0)
+        assert torch.equal(pa, pb) and torch.equal(ma, mb) and torch.equal(va, vb)
+        assert torch.equal(ref16.view(torch.int16), a16.view(torch.int16))
+        assert torch.equal(sa, sb)

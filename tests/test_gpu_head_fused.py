@@ -1,0 +1,132 @@
+"""The fused head kernel (gating softmax + classifier + CE + their backward in one launch,
+msf_fusion_train_pass / msf_fusion_infer_pass) against the un-fused kernel sequence it replaces
+(MSF_NO_HEAD=1: tail, F5, F6, msf_cross_entropy, B1, B2, tail backward) and against the CPU oracle.
+Both sides run the same bf16 tensor-core arithmetic, so they agree far inside the bf16 tolerance."""
+import importlib
+
+import pytest
+import torch
+
+from conftest import load_pkg
+from helpers import PAMAP2, seeded_case
+from oracle import fusion_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _mods():
+    pkg = load_pkg()
+    return importlib.import_module(pkg.__name__ + ".ops"), importlib.import_module(pkg.__name__ + "._native")
+
+
+def _setup(batch, seed, dims=PAMAP2, hidden=256, heads=4, classes=25):
+    ops, N = _mods()
+    model, feats, mask, labels = seeded_case(dims, hidden, heads, classes, batch, seed=seed, device="cuda")
+    plan = model._plan()
+    own = dict(model.named_parameters())
+    arena = plan.gather([own[k].detach() for k, _, _ in plan.slots])
+    return ops, N, model, plan, arena, plan.pack_bf16(arena), [feats[m].contiguous() for m in plan.names], mask, labels
+
+
+def _slot(plan, grad, key):
+    for k, off, shape in plan.slots:
+        if k == key:
+            return grad[off:off + int(torch.Size(shape).numel())].view(shape)
+    raise KeyError(key)
+
+
+@pytest.mark.parametrize("batch,p", [(384, 0.0), (1000, 0.1), (4096, 0.1)])
+def test_fused_train_pass_equals_unfused_sequence(batch, p, monkeypatch):
+    ops, N, model, plan, arena, arena16, xs, mask, labels = _setup(batch, seed=7)
+    kw = dict(precision=N.MSF_PREC_BF16, training=p > 0, p=p, seed=11, offset=3, arena_bf16=arena16)
+    monkeypatch.delenv("MSF_NO_HEAD", raising=False)
+    logits, loss, grad, fw, gates = ops.fusion_train_pass_raw(plan, arena, xs, mask, labels, smoothing=0.05, **kw)
+    monkeypatch.setenv("MSF_NO_HEAD", "1")
+    l2, fw2, g2, ws = ops.fusion_forward_raw(plan, arena, xs, mask, **kw)
+    loss2, dl = ops.cross_entropy(l2, labels, 0.05)
+    grad2, _ = ops.fusion_backward_raw(plan, arena, xs, mask, ws, dl, **kw)
+    monkeypatch.delenv("MSF_NO_HEAD")
+    torch.cuda.synchronize()
+    assert torch.isfinite(grad).all() and torch.isfinite(logits).all()
+    assert float((logits - l2).abs().max()) <= 5e-4   # 1-ulp bf16 flips of the fused tile, far inside 1e-2
+    assert float((fw - fw2).abs().max()) <= 5e-6, float((fw - fw2).abs().max())
+    assert torch.equal(gates, g2)
+    assert abs(float(loss) - float(loss2)) <= 1e-4
+    scale = float(grad2.abs().max())
+    for key, off, shape in plan.slots:
+        n = int(torch.Size(shape).numel())
+        a, b = grad[off:off + n], grad2[off:off + n]
+        if ".query_proj." in key or ".key_proj." in key:
+            assert float(a.abs().max()) == 0.0, key
+            continue
+        assert float((a - b).abs().max()) <= 2e-3 * scale + 1e-7, key
+        assert float((a - b).norm()) <= 2e-2 * float(b.norm()) + 1e-7, key
+
+
+def test_fused_train_pass_matches_oracle():
+    """Fused pass (dropout off) against the fp32 CPU oracle: the tolerances of test_gpu_fusion_bf16."""
+    ops, N, model, plan, arena, arena16, xs, mask, labels = _setup(640, seed=9)
+    logits, loss, grad, fw, gates = ops.fusion_train_pass_raw(
+        plan, arena, xs, mask, labels, smoothing=0.05, precision=N.MSF_PREC_BF16, training=False, p=0.0,
+        arena_bf16=arena16)
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    xo = {m: x.cpu() for m, x in zip(plan.names, xs)}
+    ref_logits, ref_info = fusion_oracle.hybrid_fusion_forward(sd, model.modality_names, 4, xo, mask.cpu())
+    ref_loss = fusion_oracle.cross_entropy_label_smoothing(ref_logits, labels.cpu(), 0.05)
+    ref_loss.backward()
+    assert float((logits.cpu() - ref_logits.detach()).abs().max()) <= 1e-2
+    assert float((fw.cpu() - ref_info["fusion_weights"].detach()).abs().max()) <= 1e-2
+    assert abs(float(loss) - float(ref_loss)) <= 1e-2
+    for key, _, _ in plan.slots:
+        got, ref = _slot(plan, grad, key).cpu(), sd[key].grad
+        assert float((got - ref).abs().max()) <= 1e-2, key
+        if ".query_proj." in key or ".key_proj." in key:
+            assert float(got.abs().max()) == 0.0, key
+        else:
+            assert float((got - ref).norm()) <= 0.10 * float(ref.norm()) + 1e-12, key
+
+
+@pytest.mark.parametrize("batch", [1, 130, 2048])
+def test_fused_infer_pass_equals_forward_plus_softmax(batch, monkeypatch):
+    ops, N, model, plan, arena, arena16, xs, mask, labels = _setup(batch, seed=13)
+    monkeypatch.delenv("MSF_NO_HEAD", raising=False)
+    logits, conf, pred = ops.fusion_infer_pass_raw(plan, arena, xs, mask, precision=N.MSF_PREC_BF16, arena_bf16=arena16)
+    monkeypatch.setenv("MSF_NO_HEAD", "1")
+    l2, _, _, _ = ops.fusion_forward_raw(plan, arena, xs, mask, precision=N.MSF_PREC_BF16, arena_bf16=arena16)
+    monkeypatch.delenv("MSF_NO_HEAD")
+    c2, p2 = ops.softmax_conf_pred(logits)   # same logits -> argmax must be bit-exact
+    assert float((logits - l2).abs().max()) <= 5e-4
+    assert torch.equal(pred, p2)
+    assert float((conf - c2).abs().max()) <= 1e-6
+    ref_conf, ref_pred = torch.softmax(logits, 1).max(1)
+    assert torch.equal(pred, ref_pred)
+    assert float((conf - ref_conf).abs().max()) <= 1e-6
+
+
+def test_small_shapes_and_missing_pairs():
+    """H = 64 / 128, C = 11, M = 2 / 3, a deleted pair module and all-missing rows through the fused pass."""
+    ops, N = _mods()
+    for hidden, heads, classes, dims in ((64, 2, 11, {"a": 16, "b": 24}), (128, 4, 5, {"a": 8, "b": 8, "c": 40})):
+        model, feats, mask, labels = seeded_case(dims, hidden, heads, classes, 300, seed=3, device="cuda")
+        mask[:7] = 0.0
+        if len(dims) == 3:
+            del model.attention_modules["a_to_c"]
+        plan = model._plan()
+        own = dict(model.named_parameters())
+        arena = plan.gather([own[k].detach() for k, _, _ in plan.slots])
+        xs = [feats[m].contiguous() for m in plan.names]
+        logits, loss, grad, fw, gates = ops.fusion_train_pass_raw(
+            plan, arena, xs, mask, labels, smoothing=0.05, precision=N.MSF_PREC_BF16, training=False, p=0.0,
+            arena_bf16=plan.pack_bf16(arena))
+        sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+        xo = {m: x.cpu() for m, x in zip(plan.names, xs)}
+        ref_logits, ref_info = fusion_oracle.hybrid_fusion_forward(sd, model.modality_names, heads, xo, mask.cpu())
+        ref_loss = fusion_oracle.cross_entropy_label_smoothing(ref_logits, labels.cpu(), 0.05)
+        ref_loss.backward()
+        assert float((logits.cpu() - ref_logits.detach()).abs().max()) <= 1e-2
+        assert torch.equal(fw[:7].cpu(), ref_info["fusion_weights"][:7].detach())  # uniform fallback, exact
+        assert abs(float(loss) - float(ref_loss)) <= 1e-2
+        for key, _, _ in plan.slots:
+            got, ref = _slot(plan, grad, key).cpu(), sd[key].grad
+            ref = torch.zeros_like(got) if ref is None else ref
+            assert float((got - ref).abs().max()) <= 1e-2, (hidden, key)
