@@ -11,6 +11,8 @@
 // produced exactly once.  All mbarrier waits are bounded (trap instead of hanging the GPU).
 #include "chain_gemm.cuh"
 
+#include <stdlib.h>
+
 #include "tc_ptx.cuh"
 
 namespace msf {
@@ -382,11 +384,18 @@ size_t chain_fixed_smem() { return 1024 + 8 * (2 * CH_MAX_STAGES + 8) + 3 * 256 
 
 }  // namespace
 
+bool chain2_eligible(int H, int M);                                          // chain2_gemm.cu
+int chain2_launch(ChainLaunch& L, cudaStream_t stream, const char* label);
+
+static bool use_chain2(int H, int M) { return chain2_eligible(H, M) && !getenv("MSF_CHAIN_V1"); }
+int chain_w1_box_rows(int H, int M) { return use_chain2(H, M) ? H / 2 : H; }
+
 bool chain_eligible(int H, int M) { return H % 64 == 0 && H >= 64 && H <= 256 && M >= 1 && M <= MSF_MAX_MODALITIES; }
 
 int chain_launch(ChainLaunch& L, cudaStream_t stream, const char* label) {
   MSF_REQUIRE(chain_eligible(L.H, L.M), "chain_gemm: hidden %d / modalities %d not supported", L.H, L.M);
   MSF_REQUIRE(L.rows >= 1, "chain_gemm: empty batch");
+  if (use_chain2(L.H, L.M)) return chain2_launch(L, stream, label);
   L.row_tiles = (int)ceil_div(L.rows, 128);
   L.items = L.row_tiles * L.M;
   const size_t per_stage = CH_A_BYTES + ch_b_bytes(L.H);

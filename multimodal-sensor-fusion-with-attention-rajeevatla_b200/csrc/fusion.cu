@@ -15,6 +15,7 @@ int fusion_bf16_forward(const Layout& L, const msf_fusion_call* c, cudaStream_t 
 int fusion_bf16_backward(const Layout& L, const msf_fusion_call* c, cudaStream_t st);
 bool fusion_bf16_head_fused(const Layout& L);
 int head_debug_stamps(long long* out16);
+int chain_debug_stamps(long long* out16);
 int fusion_bf16_train(const Layout& L, const msf_fusion_call* c, const int64_t* labels, float smoothing,
                       float grad_scale, float* row_loss, float* loss_out, cudaStream_t st);
 int fusion_bf16_infer(const Layout& L, const msf_fusion_call* c, float* conf, int64_t* pred, cudaStream_t st);
@@ -138,6 +139,11 @@ int msf_fusion_infer_pass(const msf_fusion_shape* shape, const msf_fusion_call* 
     return msf::fusion_bf16_infer(L, call, conf, pred, (cudaStream_t)stream);
   if ((rc = msf_fusion_forward(shape, call, stream))) return rc;
   return msf_softmax_conf_pred(call->logits, call->batch, L.C, conf, pred, stream);
+}
+
+int msf_debug_chain_stamps(int64_t* out16) {
+  MSF_REQUIRE(out16 != nullptr, "msf_debug_chain_stamps: null output");
+  return msf::chain_debug_stamps(reinterpret_cast<long long*>(out16));
 }
 
 int msf_debug_head_stamps(int64_t* out16) {

@@ -589,7 +589,7 @@ static int forward_front(const Layout& L, const msf_fusion_call* c, const WsBf16
     C.store1 = 1;  // U is an operand of the out_proj weight gradient
     const int np = pairs > 0 ? pairs : 1;
     if ((rc = tc_encode_map(&C.map_a1, ws.P, B, H, H, M, BH, 64, 128))) return rc;
-    if ((rc = tc_encode_map(&C.map_w1, pairs > 0 ? (const void*)(W16 + A.wv) : (const void*)ws.P, H, H, H, np, (long long)H * H, 64, H))) return rc;
+    if ((rc = tc_encode_map(&C.map_w1, pairs > 0 ? (const void*)(W16 + A.wv) : (const void*)ws.P, H, H, H, np, (long long)H * H, 64, chain_w1_box_rows(H, M)))) return rc;
     if ((rc = tc_encode_map(&C.map_w2, pairs > 0 ? (const void*)(W16 + A.wo) : (const void*)ws.P, H, H, H, np, (long long)H * H, 64, H))) return rc;
     if ((rc = tc_encode_map(&C.map_out1, ws.U, B, H, H, np, BH, 64, 128))) return rc;
     if ((rc = tc_encode_map(&C.map_out, ws.agg, B, H, H, M, BH, 64, 128))) return rc;
@@ -675,9 +675,11 @@ static int launch_head(const Layout& L, const msf_fusion_call* c, const WsBf16& 
   if ((rc = tc_encode_map(&hl.map_w2, W16 + A.w2, L.C, H, H, 1, 0, 64, 32))) return rc;
   if ((rc = tc_encode_map(&hl.map_w2t, W16 + A.w2T, H, A.Cp, A.Cp, 1, 0, 64, H))) return rc;
   if ((rc = tc_encode_map(&hl.map_w1t, W16 + A.w1T, H, H, H, 1, 0, 64, H))) return rc;
-  if ((rc = tc_encode_map(&hl.map_fused, ws.fused, B, H, H, 1, 0, 64, 128))) return rc;
-  if ((rc = tc_encode_map(&hl.map_hr, ws.Hr, B, H, H, 1, 0, 64, 128))) return rc;
-  if ((rc = tc_encode_map(&hl.map_dh1, ws.dH1, B, H, H, 1, 0, 64, 128))) return rc;
+  if ((rc = tc_encode_map(&hl.map_agg, ws.agg, B, H, H, M, (long long)B * H, 64, 32))) return rc;
+  const int tr = head_tile_rows(B);
+  if ((rc = tc_encode_map(&hl.map_fused, ws.fused, B, H, H, 1, 0, 64, tr))) return rc;
+  if ((rc = tc_encode_map(&hl.map_hr, ws.Hr, B, H, H, 1, 0, 64, tr))) return rc;
+  if ((rc = tc_encode_map(&hl.map_dh1, ws.dH1, B, H, H, 1, 0, 64, tr))) return rc;
   hl.M = M; hl.H = H; hl.C = L.C; hl.Cp = A.Cp; hl.rows = (int)B;
   hl.agg = ws.agg;
   for (int m = 0; m < M; ++m) {
@@ -866,7 +868,7 @@ static int backward_back(const Layout& L, const msf_fusion_call* c, const WsBf16
     C.store1 = 1;  // dV is an operand of the value_proj weight / bias gradients
     const int np = pairs > 0 ? pairs : 1;
     if ((rc = tc_encode_map(&C.map_a1, ws.dS, B, H, H, M, BH, 64, 128))) return rc;
-    if ((rc = tc_encode_map(&C.map_w1, pairs > 0 ? (const void*)(W16 + A.woT) : (const void*)ws.dS, H, H, H, np, (long long)H * H, 64, H))) return rc;
+    if ((rc = tc_encode_map(&C.map_w1, pairs > 0 ? (const void*)(W16 + A.woT) : (const void*)ws.dS, H, H, H, np, (long long)H * H, 64, chain_w1_box_rows(H, M)))) return rc;
     if ((rc = tc_encode_map(&C.map_w2, pairs > 0 ? (const void*)(W16 + A.wvT) : (const void*)ws.dS, H, H, H, np, (long long)H * H, 64, H))) return rc;
     if ((rc = tc_encode_map(&C.map_out1, ws.dV, B, H, H, np, BH, 64, 128))) return rc;
     if ((rc = tc_encode_map(&C.map_out, ws.dZ, B, H, H, M, BH, 64, 128))) return rc;

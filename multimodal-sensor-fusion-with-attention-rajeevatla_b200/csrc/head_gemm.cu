@@ -92,20 +92,25 @@ __device__ __forceinline__ void tr_step(float (&p)[NV], int lane) {
     p[k] = keep + __shfl_xor_sync(0xffffffffu, send, BIT);
   }
 }
-__device__ __forceinline__ float transpose_reduce16(float (&p)[16], int lane) {
-  tr_step<8, 16>(p, lane);
-  tr_step<4, 8>(p, lane);
-  tr_step<2, 4>(p, lane);
-  tr_step<1, 2>(p, lane);
-  return p[0] + __shfl_xor_sync(0xffffffffu, p[0], 1);
+// 4 values: afterwards every lane holds the total of value (lane >> 3) & 3
+__device__ __forceinline__ float transpose_reduce4(float (&p)[4], int lane) {
+  tr_step<2, 16>(p, lane);
+  tr_step<1, 8>(p, lane);
+  float r = p[0];
+  r += __shfl_xor_sync(0xffffffffu, r, 4);
+  r += __shfl_xor_sync(0xffffffffu, r, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
 }
-__device__ __forceinline__ float transpose_reduce32(float (&p)[32], int lane) {
-  tr_step<16, 16>(p, lane);
-  tr_step<8, 8>(p, lane);
-  tr_step<4, 4>(p, lane);
-  tr_step<2, 2>(p, lane);
-  tr_step<1, 1>(p, lane);
-  return p[0];
+// 8 values: afterwards every lane holds the total of value (lane >> 2) & 7
+__device__ __forceinline__ float transpose_reduce8(float (&p)[8], int lane) {
+  tr_step<4, 16>(p, lane);
+  tr_step<2, 8>(p, lane);
+  tr_step<1, 4>(p, lane);
+  float r = p[0];
+  r += __shfl_xor_sync(0xffffffffu, r, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
 }
 
 struct HeadSmem {
@@ -113,59 +118,68 @@ struct HeadSmem {
   float *b1s, *b2s, *gws, *gbs, *rw, *rsoft, *rmk;
 };
 
-// Sum over the (up to 4) modalities of one window: the lanes of a window's group differ in bits 1 and 2.
+// Sum / max over the (up to 4) modalities of a window: lane l holds modality (l >> 3) & 3.
 __device__ __forceinline__ float group_sum(float v) {
-  v += __shfl_xor_sync(0xffffffffu, v, 2);
-  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
   return v;
 }
 __device__ __forceinline__ float group_max(float v) {
-  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
-  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4));
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 8));
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));
   return v;
 }
 
-// ---- P0: gating + weighted sum.  A warp takes 4 windows per iteration: lanes own 8-column chunks for the
-// dot products / weighted sums; after the transposed reduction lane 8*i + 2*q (+1) owns the score of
-// (window i, modality q), so the softmax arithmetic of src/fusion.py:464-478 runs once, lane-parallel. ----
-__device__ __forceinline__ void head_p0(const HeadLaunch& L, const HeadSmem& S, int m0, int wq, int lane) {
+// Aggregated-token tiles reach P0 / P5 through the TMA ring: one sub-block = 32 windows x M modalities x H
+// columns, staged as ceil(M/2) ring stages of [2 modalities][H/64 k-blocks][32 rows x 128 B, 128B-swizzled].
+struct AggStage {
+  const unsigned char* base[2];   // stage holding modalities {0,1} and {2,3}
+  int KB;
+};
+// this lane's 16-byte chunk (columns lane*8 .. +8) of modality q, sub-block row rl
+__device__ __forceinline__ uint4 agg_chunk(const AggStage& st, int q, int rl, int lane) {
+  const unsigned char* p = st.base[q >> 1] + (((q & 1) * st.KB + (lane >> 3)) << 12) + rl * 128 +
+                           (((lane & 7) ^ (rl & 7)) << 4);
+  return *reinterpret_cast<const uint4*>(p);
+}
+
+// The row-wise phases are written for MINIMUM UNIQUE CODE: at small batches every CTA runs each phase once,
+// so its time is set by cold instruction fetch (ncu: stall_no_inst), not by arithmetic.  One window per
+// iteration of a rolled loop, everything else lane-parallel.
+//
+// ---- P0: gating + weighted sum for the 4 windows this warp owns in the staged 32-window sub-block.  Lanes own
+// 8-column chunks for the dot products / weighted sum; after the transposed reduction lane l holds the score of
+// modality (l >> 3) & 3, so the softmax arithmetic of src/fusion.py:464-478 is one pass of lane-parallel code. ----
+__device__ __forceinline__ void head_p0(const HeadLaunch& L, const HeadSmem& S, const AggStage& st, int m0, int sb,
+                                        int wq, int lane) {
   const int H = L.H, M = L.M, c = lane * 8;
   const bool c_ok = c < H;
-  const int qi = (lane >> 1) & 3, ri = lane >> 3;   // this lane's (modality, window) after the reduction
+  const int qi = (lane >> 3) & 3;
+  const bool lane_ok = qi < M;
   const float gb = S.gbs[qi];
 #pragma unroll 1
-  for (int rb = 0; rb < 16; rb += 4) {
-    uint4 raw[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const long long row = (long long)m0 + wq * 16 + rb + i;
-      const bool ok = c_ok && row < L.rows;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        raw[i][q] = make_uint4(0u, 0u, 0u, 0u);
-        if (ok && q < M) raw[i][q] = __ldg(reinterpret_cast<const uint4*>(L.agg + ((long long)q * L.rows + row) * H + c));
-      }
-    }
-    const int r_l = wq * 16 + rb + ri;
-    const long long row_l = (long long)m0 + r_l;
-    const bool lane_ok = qi < M, row_l_ok = row_l < L.rows;
-    float mk = 0.0f;
-    if (lane_ok) mk = (L.mask != nullptr && row_l_ok) ? __ldg(L.mask + row_l * M + qi) : 1.0f;
-    float part[16];
+  for (int i = 0; i < 4; ++i) {
+    const int rl = wq * 4 + i, r = sb * 32 + rl;
+    const long long row = (long long)m0 + r;
+    const bool row_ok = row < L.rows;
+    uint4 raw[4];
+    float part[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (c_ok && q < M) ld8_smem_f32(S.gws + q * H + c, g);
+      raw[q] = make_uint4(0u, 0u, 0u, 0u);
+      part[q] = 0.0f;
+      if (q < M && c_ok) {
+        raw[q] = agg_chunk(st, q, rl, lane);
+        float v[8], g[8];
+        unpack8(raw[q], v);
+        ld8_smem_f32(S.gws + q * H + c, g);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float v[8], acc = 0.0f;
-        unpack8(raw[i][q], v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc = fmaf(v[j], g[j], acc);
-        part[i * 4 + q] = acc;
+        for (int j = 0; j < 8; ++j) part[q] = fmaf(v[j], g[j], part[q]);
       }
     }
-    const float sc = transpose_reduce16(part, lane) + gb;          // fusion.py:459
+    const float sc = transpose_reduce4(part, lane) + gb;              // fusion.py:459
+    float mk = 0.0f;
+    if (lane_ok) mk = (L.mask != nullptr && row_ok) ? __ldg(L.mask + row * M + qi) : 1.0f;
     // masked softmax with the reference's fallbacks (fusion.py:464-478)
     const float mx = group_max((lane_ok && mk > 0.0f) ? sc : -INFINITY);
     const float e = (lane_ok && mk > 0.0f && mx > -INFINITY) ? expf(sc - mx) : 0.0f;
@@ -175,104 +189,80 @@ __device__ __forceinline__ void head_p0(const HeadLaunch& L, const HeadSmem& S, 
     const float sum_w = group_sum(w), mask_sum = group_sum(mk);
     if (sum_w > 0.0f) w = w / (sum_w + 1e-8f);
     else w = lane_ok ? (mask_sum > 0.0f ? mk / (mask_sum + 1e-8f) : 1.0f / (float)M) : 0.0f;
-    if (lane_ok && (lane & 1) == 0) {
-      S.rw[r_l * HD_RS + qi] = w;
-      S.rsoft[r_l * HD_RS + qi] = soft;
-      S.rmk[r_l * HD_RS + qi] = mk;
-      if (row_l_ok) {
-        L.soft[row_l * M + qi] = soft;
-        L.w[row_l * M + qi] = w;
-        if (L.w_out != nullptr) L.w_out[row_l * M + qi] = w;
+    if (lane_ok && (lane & 7) == 0) {
+      S.rw[r * HD_RS + qi] = w;
+      S.rsoft[r * HD_RS + qi] = soft;
+      S.rmk[r * HD_RS + qi] = mk;
+      if (row_ok) {
+        L.soft[row * M + qi] = soft;
+        L.w[row * M + qi] = w;
+        if (L.w_out != nullptr) L.w_out[row * M + qi] = w;
       }
     }
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int q = 0; q < 4; ++q) {
+      const float wb = __shfl_sync(0xffffffffu, w, 8 * q);
+      float v[8];
+      unpack8(raw[q], v);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float wb = __shfl_sync(0xffffffffu, w, 8 * i + 2 * q);
-        float v[8];
-        unpack8(raw[i][q], v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = fmaf(v[j], wb, f[j]);  // fusion.py:416-418
-      }
-      if (c_ok) *reinterpret_cast<uint4*>(S.ublk + swz_off(wq * 16 + rb + i, c)) = pack8(f);
+      for (int j = 0; j < 8; ++j) f[j] = fmaf(v[j], wb, f[j]);  // fusion.py:416-418
     }
+    // padding rows of the last tile stay zero
+    if (c_ok) *reinterpret_cast<uint4*>(S.ublk + swz_off(r, c)) = row_ok ? pack8(f) : make_uint4(0u, 0u, 0u, 0u);
   }
 }
 
 // ---- P5: backward of P0 with the same lane layout: d scores lane-parallel, then
-// dS_q = (w_q dfused + ds_q gw_q) * mask_q / cnt_q for the 4 windows of the iteration. ----
-__device__ __forceinline__ void head_p5(const HeadLaunch& L, const HeadSmem& S, int m0, int wq, int lane) {
+// dS_q = (w_q dfused + ds_q gw_q) * mask_q / cnt_q. ----
+__device__ __forceinline__ void head_p5(const HeadLaunch& L, const HeadSmem& S, const AggStage& st, int m0, int sb,
+                                        int wq, int lane) {
   const int H = L.H, M = L.M, c = lane * 8;
   const bool c_ok = c < H;
-  const int qi = (lane >> 1) & 3, ri = lane >> 3;
+  const int qi = (lane >> 3) & 3;
+  const bool lane_ok = qi < M;
   const float icnt = L.inv_cnt[qi];
 #pragma unroll 1
-  for (int rb = 0; rb < 16; rb += 4) {
-    uint4 raw[4][4], graw[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = wq * 16 + rb + i;
-      const long long row = (long long)m0 + r;
-      const bool ok = c_ok && row < L.rows;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        raw[i][q] = make_uint4(0u, 0u, 0u, 0u);
-        if (ok && q < M) raw[i][q] = __ldg(reinterpret_cast<const uint4*>(L.agg + ((long long)q * L.rows + row) * H + c));
-      }
-      graw[i] = make_uint4(0u, 0u, 0u, 0u);
-      if (ok) graw[i] = *reinterpret_cast<const uint4*>(S.ublk + swz_off(r, c));
-    }
-    const int r_l = wq * 16 + rb + ri;
-    const long long row_l = (long long)m0 + r_l;
-    const bool lane_ok = qi < M, row_l_ok = row_l < L.rows;
-    const float p = lane_ok ? S.rsoft[r_l * HD_RS + qi] : 0.0f;
-    const float w = lane_ok ? S.rw[r_l * HD_RS + qi] : 0.0f;
-    const float mk = lane_ok ? S.rmk[r_l * HD_RS + qi] : 0.0f;
-    float part[16];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float g[8];
-      unpack8(graw[i], g);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float v[8], acc = 0.0f;
-        unpack8(raw[i][q], v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc = fmaf(v[j], g[j], acc);
-        part[i * 4 + q] = acc;
-      }
-    }
-    const float dw = transpose_reduce16(part, lane);   // d loss / d w_q of this lane's (window, modality)
-    // w = n / (S + 1e-8), n = p * mask (only when S > 0; the fallbacks are constants)
-    const float Ssum = group_sum(p * mk);
-    float ds = 0.0f;
-    {
-      const float inv = 1.0f / (Ssum + 1e-8f);
-      const float dot = group_sum(dw * p * mk);
-      const float dp = (dw * inv - dot * inv * inv) * mk;
-      const float pdot = group_sum(dp * p);
-      if (Ssum > 0.0f && row_l_ok && mk > 0.0f) ds = p * (dp - pdot);
-    }
-    if (L.ds != nullptr && lane_ok && row_l_ok && (lane & 1) == 0) L.ds[row_l * M + qi] = ds;
-    const float scl = mk * icnt;
+  for (int i = 0; i < 4; ++i) {
+    const int rl = wq * 4 + i, r = sb * 32 + rl;
+    const long long row = (long long)m0 + r;
+    const bool row_ok = row < L.rows;
+    float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (c_ok && row_ok) unpack8(*reinterpret_cast<const uint4*>(S.ublk + swz_off(r, c)), g);
+    float part[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      float gwq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (c_ok && q < M) ld8_smem_f32(S.gws + q * H + c, gwq);
+      part[q] = 0.0f;
+      if (q < M && c_ok) {
+        float v[8];
+        unpack8(agg_chunk(st, q, rl, lane), v);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int src = 8 * i + 2 * q;
-        const float wb = __shfl_sync(0xffffffffu, w, src), dsb = __shfl_sync(0xffffffffu, ds, src);
-        const float sb = __shfl_sync(0xffffffffu, scl, src);
-        float g[8], o[8];
-        unpack8(graw[i], g);
+        for (int j = 0; j < 8; ++j) part[q] = fmaf(v[j], g[j], part[q]);
+      }
+    }
+    const float dw = transpose_reduce4(part, lane);   // d loss / d w_q for this lane's modality
+    const float p = lane_ok ? S.rsoft[r * HD_RS + qi] : 0.0f;
+    const float w = lane_ok ? S.rw[r * HD_RS + qi] : 0.0f;
+    const float mk = lane_ok ? S.rmk[r * HD_RS + qi] : 0.0f;
+    // w = n / (S + 1e-8), n = p * mask (only when S > 0; the fallbacks are constants)
+    const float Ssum = group_sum(p * mk);
+    const float inv = 1.0f / (Ssum + 1e-8f);
+    const float dot = group_sum(dw * p * mk);
+    const float dp = (dw * inv - dot * inv * inv) * mk;
+    const float pdot = group_sum(dp * p);
+    const float ds = (Ssum > 0.0f && row_ok && mk > 0.0f) ? p * (dp - pdot) : 0.0f;
+    if (L.ds != nullptr && lane_ok && row_ok && (lane & 7) == 0) L.ds[row * M + qi] = ds;
+    const float scl = mk * icnt;
+#pragma unroll 1
+    for (int q = 0; q < M; ++q) {
+      const float wb = __shfl_sync(0xffffffffu, w, 8 * q), dsb = __shfl_sync(0xffffffffu, ds, 8 * q);
+      const float sb2 = __shfl_sync(0xffffffffu, scl, 8 * q);
+      if (c_ok && row_ok) {
+        float gwq[8], o[8];
+        ld8_smem_f32(S.gws + q * H + c, gwq);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = fmaf(wb, g[j], dsb * gwq[j]) * sb;
-        const long long row = (long long)m0 + wq * 16 + rb + i;
-        if (c_ok && q < M && row < L.rows)
-          *reinterpret_cast<uint4*>(L.dS + ((long long)q * L.rows + row) * H + c) = pack8(o);
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(wb, g[j], dsb * gwq[j]) * sb2;
+        *reinterpret_cast<uint4*>(L.dS + ((long long)q * L.rows + row) * H + c) = pack8(o);
       }
     }
   }
@@ -308,9 +298,13 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_kernel(const __grid_consta
   S.rmk = S.rsoft + 128 * HD_RS;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  HD_STAMP(11);
   const int nsteps = L.train ? 4 : 2;   // async-consumed A-block contents per tile
+  const int TR = L.tile_rows, n_sb = TR >> 5;         // windows per tile (128, or 32 to spread a small batch over the SMs)
+  const int n_aq = (M + 1) >> 1, n_agg = n_sb * n_aq; // ring stages per 32-window sub-block / per P0 or P5 pass
 
   if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&L.map_agg);
     tma_prefetch_desc(&L.map_w1);
     tma_prefetch_desc(&L.map_w2);
     if (L.train) {
@@ -359,12 +353,27 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_kernel(const __grid_consta
         tma_load_3d(ring_base + stage * RING, map, kcol, 0, 0, full_bar(stage));
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       };
+      auto load_agg = [&](int m0) {   // sub-blocks of 32 windows, ceil(M/2) stages each
+        for (int sb = 0; sb < n_sb; ++sb)
+          for (int j = 0; j < n_aq; ++j) {
+            const int nq = (M - 2 * j) < 2 ? (M - 2 * j) : 2;
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_expect_tx(full_bar(stage), (uint32_t)(nq * KB) << 12);
+            for (int qq = 0; qq < nq; ++qq)
+              for (int kb = 0; kb < KB; ++kb)
+                tma_load_3d(ring_base + stage * RING + (uint32_t)((qq * KB + kb) << 12), &L.map_agg, kb * 64,
+                            m0 + sb * 32, 2 * j + qq, full_bar(stage));
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+      };
       for (int tile = blockIdx.x; tile < L.row_tiles; tile += gridDim.x) {
+        load_agg(tile * TR);                                                     // P0
         for (int kb = 0; kb < KB; ++kb) load(&L.map_w1, kb * 64, RING);          // G1: W1 [H][64]
         for (int kb = 0; kb < KB; ++kb) load(&L.map_w2, kb * 64, 32u * 128u);    // G2: W2 [32][64]
         if (L.train) {
           load(&L.map_w2t, 0, RING);                                             // G3: W2^T [H][64] (cols >= Cp zero)
           for (int kb = 0; kb < KB; ++kb) load(&L.map_w1t, kb * 64, RING);       // G4: W1^T [H][64]
+          load_agg(tile * TR);                                                   // P5
         }
       }
     }
@@ -391,12 +400,18 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_kernel(const __grid_consta
         tc_commit(acc_full);
         tc_commit(a_free);   // 1 of 2: the GEMM no longer reads the A block
       };
+      auto skip = [&](int n) {   // ring stages consumed by the workers (aggregated-token sub-blocks)
+        for (int i = 0; i < n; ++i)
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      };
       for (int tile = blockIdx.x; tile < L.row_tiles; tile += gridDim.x) {
+        skip(n_agg);                                     // P0
         gemm(tmem_base, idesc_h, KB, 4);                 // G1: fused . W1^T
         gemm(tmem_base + 256u, idesc_c, KB, 4);          // G2: Hr . W2^T
         if (L.train) {
           gemm(tmem_base, idesc_h, 1, 2);                // G3: dlog . W2   (K = 32)
           gemm(tmem_base + 256u, idesc_h, KB, 4);        // G4: dH1 . W1
+          skip(n_agg);                                   // P5
         }
       }
     }
@@ -405,7 +420,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_kernel(const __grid_consta
     if (lane == 0) {
       uint32_t n_ready = 0;
       for (int tile = blockIdx.x; tile < L.row_tiles; tile += gridDim.x) {
-        const int m0 = tile * 128;
+        const int m0 = tile * TR;
         for (int step = 0; step < nsteps; ++step) {
           mbar_wait(a_ready, n_ready & 1u);
           ++n_ready;
@@ -431,7 +446,38 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_kernel(const __grid_consta
     const int trow = lq * 32 + lane;                 // accumulator row = TMEM lane
     const int half = H >> 1, c_begin = cg * half;
     const uint32_t lane_base = (uint32_t)(lq * 32) << 16;
+    const bool warp_live = lq * 32 < L.tile_rows;    // 32-window tiles: TMEM lanes 32..127 are MMA padding
     uint32_t n_full = 0, n_free = 0;
+    int wstage = 0;          // the workers' view of the ring position
+    uint32_t wphase = 0;
+    auto ring_skip = [&](int n) {   // stages consumed by the MMA warp (weights)
+      for (int i = 0; i < n; ++i)
+        if (++wstage == STAGES) { wstage = 0; wphase ^= 1u; }
+    };
+    // One pass over the tile's aggregated tokens: staged sub-blocks of 32 windows, each warp 4 windows.
+    auto agg_pass = [&](int m0, bool backward) {
+#pragma unroll 1
+      for (int sb = 0; sb < n_sb; ++sb) {
+        AggStage st;
+        st.KB = KB;
+        st.base[0] = st.base[1] = nullptr;
+        int rel0 = 0, rel1 = 0;
+        for (int j = 0; j < n_aq; ++j) {
+          mbar_wait(full_bar(wstage), wphase);
+          st.base[j] = smem_raw + (ring_base + wstage * RING - off0);
+          if (j == 0) rel0 = wstage;
+          else rel1 = wstage;
+          if (++wstage == STAGES) { wstage = 0; wphase ^= 1u; }
+        }
+        if (backward) head_p5(L, S, st, m0, sb, wq, lane);
+        else head_p0(L, S, st, m0, sb, wq, lane);
+        workers_sync();   // every warp is done with the sub-block: its stages may be refilled
+        if (threadIdx.x == 128) {
+          mbar_arrive(empty_bar(rel0));
+          if (n_aq > 1) mbar_arrive(empty_bar(rel1));
+        }
+      }
+    };
     auto publish = [&]() {  // A block written: visible to the async proxy, then signal
       tc_fence_before();
       fence_async_smem();
@@ -446,47 +492,52 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_kernel(const __grid_consta
       ++n_free;
     };
     for (int tile = blockIdx.x; tile < L.row_tiles; tile += gridDim.x) {
-      const int m0 = tile * 128;
+      const int m0 = tile * TR;
       const long long row = (long long)m0 + trow;
-      const bool row_ok = row < L.rows;
+      const bool row_ok = trow < TR && row < L.rows;   // rows beyond the tile's windows are MMA padding
 
       // ---- P0 ----
       HD_STAMP(0);
-      head_p0(L, S, m0, wq, lane);
+      agg_pass(m0, false);
       publish();
       HD_STAMP(1);
 
-      // ---- E1: Hr = drop(relu(acc + b1)); the relu/dropout mask of this thread's columns stays in registers ----
-      unsigned long long bits_lo = 0ull, bits_hi = 0ull;
+      // ---- E1: Hr = drop(relu(acc + b1)); the relu/dropout mask of this thread's columns stays in registers.
+      // The Philox draws do not depend on the accumulator: they are made while G1 runs. ----
+      unsigned long long bits_lo = ~0ull, bits_hi = ~0ull;   // first the dropout keep mask, then keep & relu'
+      if (drop.active && warp_live) {
+        bits_lo = bits_hi = 0ull;
+#pragma unroll 1
+        for (int g8 = 0; g8 < (half >> 3); ++g8) {
+          float d8[8];
+          drop8(drop, SITE_CLS, 0, row, (c_begin >> 3) + g8, d8);
+          unsigned long long m8 = 0ull;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) m8 |= (d8[j] != 0.0f ? 1ull : 0ull) << j;
+          if (g8 < 8) bits_lo |= m8 << (8 * g8);
+          else bits_hi |= m8 << (8 * (g8 - 8));
+        }
+      }
+      ring_skip(2 * KB);   // W1, W2 stages belong to the MMA warp
       acquire();
       HD_STAMP(2);
 #pragma unroll 1
-      for (int it = 0; it < (half >> 4); ++it) {
+      for (int it = 0; it < (warp_live ? (half >> 4) : 0); ++it) {
         const int c = c_begin + it * 16;
         uint32_t acc[16];
         tmem_ld16_issue(tmem_base + lane_base + (uint32_t)c, acc);
         tmem_wait16(acc);
-        float dm[16], v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) dm[j] = 1.0f;
-        if (drop.active) {
-#pragma unroll 1
-          for (int h8 = 0; h8 < 2; ++h8) {
-            float d8[8];
-            drop8(drop, SITE_CLS, 0, row, (c >> 3) + h8, d8);
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if ((j >> 3) == h8) dm[j] = d8[j & 7];
-          }
-        }
+        const uint32_t k16 = (uint32_t)((it < 4 ? bits_lo >> (16 * it) : bits_hi >> (16 * (it - 4))) & 0xffffull);
+        float v[16];
         uint32_t m16 = 0u;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          v[j] = fmaxf(__uint_as_float(acc[j]) + S.b1s[c + j], 0.0f) * dm[j];
+          v[j] = ((k16 >> j) & 1u) ? fmaxf(__uint_as_float(acc[j]) + S.b1s[c + j], 0.0f) * drop.scale : 0.0f;
           m16 |= (v[j] > 0.0f ? 1u : 0u) << j;
         }
-        if (it < 4) bits_lo |= (unsigned long long)m16 << (16 * it);
-        else bits_hi |= (unsigned long long)m16 << (16 * (it - 4));
+        // keep & relu' replaces the keep bits of these 16 columns (m16 is a subset of k16)
+        if (it < 4) bits_lo &= ~(0xffffull << (16 * it)) | ((unsigned long long)m16 << (16 * it));
+        else bits_hi &= ~(0xffffull << (16 * (it - 4))) | ((unsigned long long)m16 << (16 * (it - 4)));
         st_swz16(S.ublk, trow, c, v);
       }
       publish();
@@ -495,35 +546,41 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_kernel(const __grid_consta
       // ---- E2: logits, softmax / cross-entropy (thread = window) ----
       acquire();
       HD_STAMP(4);
-      if (cg == 0) {
-        uint32_t acc[32];
-        tmem_ld32(tmem_base + lane_base + 256u, acc);
-        float z[32];
+      if (cg == 0 && warp_live) {
+        // three rolled passes over the 32 accumulator columns, 8 at a time (TMEM re-reads are cheap, code is not)
+        const uint32_t zaddr = tmem_base + lane_base + 256u;
         float mx = -INFINITY, zsum = 0.0f;
         int arg = 0;
         bool has_nan = false;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {   // pass 1: logits out, max / arg-max / sum
+          uint32_t acc[8];
+          tmem_ld8(zaddr + (uint32_t)(ch * 8), acc);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          z[c] = __uint_as_float(acc[c]) + S.b2s[c];
-          if (c < C) {
-            has_nan |= (z[c] != z[c]);
-            if (z[c] > mx) { mx = z[c]; arg = c; }   // first max (torch.max tie rule)
-            zsum += z[c];
+          for (int e = 0; e < 8; ++e) {
+            const int c = ch * 8 + e;
+            const float z = __uint_as_float(acc[e]) + S.b2s[c];
+            if (c < C) {
+              if (row_ok) L.logits[row * C + c] = z;
+              has_nan |= (z != z);
+              if (z > mx) { mx = z; arg = c; }   // first max (torch.max tie rule)
+              zsum += z;
+            }
           }
-        }
-        if (row_ok) {
-          float* lrow = L.logits + row * C;
-#pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if (c < C) lrow[c] = z[c];
         }
         const int y = (L.train && row_ok) ? (int)L.labels[row] : -1;
         float se = 0.0f, zy = 0.0f;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {   // pass 2: sum of exp(z - max), the label's logit
+          uint32_t acc[8];
+          tmem_ld8(zaddr + (uint32_t)(ch * 8), acc);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          if (c == y) zy = z[c];
-          z[c] = (c < C) ? expf(z[c] - mx) : 0.0f;   // z now holds exp(z - max)
-          se += z[c];
+          for (int e = 0; e < 8; ++e) {
+            const int c = ch * 8 + e;
+            const float z = __uint_as_float(acc[e]) + S.b2s[c];
+            if (c == y) zy = z;
+            if (c < C) se += expf(z - mx);
+          }
         }
         if (!L.train) {
           if (L.conf != nullptr && row_ok) {   // eval.py:89-90; a NaN logit gives (NaN, 0) like torch.max
@@ -539,21 +596,24 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_kernel(const __grid_consta
           }
           const float inv = row_ok ? L.grad_scale / se : 0.0f, off = L.smoothing / (float)C * L.grad_scale;
           const float hit = (1.0f - L.smoothing) * L.grad_scale;
+#pragma unroll 1
+          for (int ch = 0; ch < 4; ++ch) {   // pass 3: d logits -> A operand of G3 / global, column sums -> d b2
+            uint32_t acc[8];
+            tmem_ld8(zaddr + (uint32_t)(ch * 8), acc);
+            float dl[8];
 #pragma unroll
-          for (int c = 0; c < 32; ++c)   // z now holds d loss / d logits (zero beyond C and for padding rows)
-            z[c] = (c < C && row_ok) ? fmaf(z[c], inv, -(off + (c == y ? hit : 0.0f))) : 0.0f;
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            float h[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) h[e] = z[ch * 8 + e];
-            const uint4 pk = pack8(h);
-            *reinterpret_cast<uint4*>(S.ublk + swz_off(trow, ch * 8)) = pk;   // A operand of G3 (k < 32)
+            for (int e = 0; e < 8; ++e) {
+              const int c = ch * 8 + e;
+              const float z = __uint_as_float(acc[e]) + S.b2s[c];
+              dl[e] = (c < C && row_ok) ? fmaf(expf(z - mx), inv, -(off + (c == y ? hit : 0.0f))) : 0.0f;
+            }
+            const uint4 pk = pack8(dl);
+            *reinterpret_cast<uint4*>(S.ublk + swz_off(trow, ch * 8)) = pk;   // k < 32 of the dlog A block
             if (row_ok && ch * 8 < L.Cp) *reinterpret_cast<uint4*>(L.dlog + row * L.Cp + ch * 8) = pk;
+            const float colsum = transpose_reduce8(dl, lane);   // lane l: column ch*8 + ((l >> 2) & 7)
+            const int cc = ch * 8 + ((lane >> 2) & 7);
+            if ((lane & 3) == 0 && cc < C) atomicAdd(L.db2 + cc, colsum);
           }
-          // classifier.3 bias gradient: column sums of d logits, one column per lane after the reduction
-          const float colsum = transpose_reduce32(z, lane);
-          if (lane < C) atomicAdd(L.db2 + lane, colsum);
         }
       }
       HD_STAMP(5);
@@ -567,7 +627,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_kernel(const __grid_consta
       acquire();
       HD_STAMP(6);
 #pragma unroll 1
-      for (int it = 0; it < (half >> 4); ++it) {
+      for (int it = 0; it < (warp_live ? (half >> 4) : 0); ++it) {
         const int c = c_begin + it * 16;
         uint32_t acc[16];
         tmem_ld16_issue(tmem_base + lane_base + (uint32_t)c, acc);
@@ -585,7 +645,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_kernel(const __grid_consta
       acquire();
       HD_STAMP(8);
 #pragma unroll 1
-      for (int c = c_begin; c < c_begin + half; c += 16) {
+      for (int c = c_begin; c < (warp_live ? c_begin + half : c_begin); c += 16) {
         uint32_t acc[16];
         tmem_ld16_issue(tmem_base + lane_base + 256u + (uint32_t)c, acc);
         tmem_wait16(acc);
@@ -599,7 +659,8 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_kernel(const __grid_consta
       HD_STAMP(9);
 
       // ---- P5 ----
-      head_p5(L, S, m0, wq, lane);
+      ring_skip(1 + KB);   // W2^T, W1^T stages
+      agg_pass(m0, true);
       workers_sync();
       HD_STAMP(10);
     }
@@ -607,6 +668,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_kernel(const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  HD_STAMP(12);
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -620,6 +682,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_kernel(const __grid_consta
     __syncthreads();
     if (threadIdx.x == 0) last = (atomicAdd(&g_head_ticket, 1u) == gridDim.x - 1);
     __syncthreads();
+    HD_STAMP(13);
     if (!last) return;
     __threadfence();
     double s = 0.0;
@@ -647,11 +710,30 @@ bool head_eligible(int H, int M, int C) {
   return H % 64 == 0 && H >= 64 && H <= 256 && M >= 1 && M <= 4 && C >= 1 && C <= 32;
 }
 
+static int head_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      sms = 148;
+  }
+  return sms;
+}
+
+// small batches: 32-window tiles (the MMA tile is padded to 128 rows) so that the row-wise phases of more
+// tiles run at the same time on otherwise idle SMs
+int head_tile_rows(long long rows) {
+  return (ceil_div(rows, 128) * 2 <= head_sms() && !getenv("MSF_HEAD_TILE128")) ? 32 : 128;
+}
+
 int head_launch(HeadLaunch& L, cudaStream_t stream, const char* label) {
   MSF_REQUIRE(head_eligible(L.H, L.M, L.C), "head_gemm: hidden %d / modalities %d / classes %d not supported", L.H,
               L.M, L.C);
   MSF_REQUIRE(L.rows >= 1, "head_gemm: empty batch");
-  L.row_tiles = (int)ceil_div(L.rows, 128);
+  const int sms = head_sms();
+  L.tile_rows = head_tile_rows(L.rows);
+  L.row_tiles = (int)ceil_div(L.rows, L.tile_rows);
   const size_t fixed = 1024 + 8 * HD_NBAR + head_float_smem(L.H, L.M) + (size_t)(L.H / 64) * HD_A_BYTES;
   const size_t statics = 4096;   // the loss reduction's static shared memory
   int stages = (int)((HD_SMEM_LIMIT - statics - fixed) / hd_ring_bytes(L.H));
@@ -659,12 +741,6 @@ int head_launch(HeadLaunch& L, cudaStream_t stream, const char* label) {
   MSF_REQUIRE(stages >= 2, "head_gemm: not enough shared memory for hidden %d", L.H);
   L.stages = stages;
   const size_t smem = fixed + (size_t)stages * hd_ring_bytes(L.H);
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    MSF_CHECK_CUDA(cudaGetDevice(&dev));
-    MSF_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  }
   const int grid = L.row_tiles < sms ? L.row_tiles : sms;
   if (prof_enabled()) {
     const double fwd = 2.0 * (double)L.rows * ((double)L.H * L.H + (double)L.H * L.C);

@@ -23,10 +23,12 @@ namespace msf {
 
 struct HeadLaunch {
   CUtensorMap map_w1, map_w2, map_w2t, map_w1t;   // operand loads (bf16 compute arena)
-  CUtensorMap map_fused, map_hr, map_dh1;         // activation stores [rows][H]
+  CUtensorMap map_agg;                            // aggregated tokens [M][rows][H], box 64 x 32 (P0 / P5 staging)
+  CUtensorMap map_fused, map_hr, map_dh1;         // activation stores [rows][H], box 64 x tile_rows
   int train;              // 0: forward only, 1: forward + CE + backward
   int M, H, C, Cp;
   int rows, row_tiles, stages;
+  int tile_rows;          // windows per CTA tile: 128, or 32 for small batches (set by head_launch)
   int store_acts;         // forward-only: write fused / Hr (operands of a later backward)
   const __nv_bfloat16* agg;  // [M][rows][H]
   const float* gate_w[MSF_MAX_MODALITIES];
@@ -54,6 +56,8 @@ struct HeadLaunch {
 };
 
 bool head_eligible(int H, int M, int C);
+// Windows per tile head_launch will use for this batch: the box height of the three store maps.
+int head_tile_rows(long long rows);
 // Fills row_tiles / stages and launches.  Tensor maps must already be encoded (tc_encode_map).
 int head_launch(HeadLaunch& L, cudaStream_t stream, const char* label);
 // clock64 stamps of the phases of CTA 0 in the last launch (debugging aid)

@@ -43,4 +43,14 @@ for what in ("train", "infer"):
     st = (ctypes.c_int64 * 16)()
     N.check(lib.msf_debug_head_stamps(st))
     n = 11 if what == "train" else 6
-    print(what, " ".join(f"{names[i]}:{(st[i] - st[0]) / 1965.0:.1f}us" for i in range(n)))
+    print(what, " ".join(f"{names[i]}:{(st[i] - st[0]) / 1965.0:.1f}us" for i in range(n)),
+          f"| entry:{(st[11] - st[0]) / 1965.0:.1f}us all-done:{(st[12] - st[0]) / 1965.0:.1f}us ticket:{(st[13] - st[0]) / 1965.0:.1f}us")
+
+os.environ["MSF_NO_HEAD"] = "1"
+ops.fusion_forward_raw(plan, arena, xs, mask, precision=N.MSF_PREC_BF16, training=True, p=0.1, seed=1, arena_bf16=a16, workspace=ws)
+os.environ.pop("MSF_NO_HEAD")
+st = (ctypes.c_int64 * 16)()
+N.check(lib.msf_debug_chain_stamps(st))
+us = lambda x: x / 1965.0
+print("chain fwd CTA0: MMA stage-wait %.1f  T-drained-wait %.1f  u-staged-wait %.1f  MMA end @%.1f | epi: G1-wait %.1f u-free-wait %.1f compute %.1f final-wait %.1f end @%.1f | producer: free-stage-wait %.1f end @%.1f"
+      % (us(st[1]), us(st[2]), us(st[3]), us(st[4] - st[0]), us(st[5]), us(st[6]), us(st[7]), us(st[8]), us(st[9] - st[0]), us(st[10]), us(st[11] - st[0])))
