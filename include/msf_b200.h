@@ -132,10 +132,14 @@ int msf_fusion_backward(const msf_fusion_shape* shape, const msf_fusion_call* ca
  * row_loss (batch) is scratch.  With MSF_PREC_BF16 and num_classes <= 32, hidden <= 256 everything between
  * the aggregated modality tokens and their gradients (gating softmax, classifier, loss, their backward) is ONE
  * kernel; otherwise this is msf_fusion_forward + msf_cross_entropy + msf_fusion_backward and
- * grad_logits_scratch (batch x C) is required. */
+ * grad_logits_scratch (batch x C) is required.
+ * flags: MSF_TRAIN_DEAD_SLOTS_ZERO = the caller guarantees that the dead query/key slots of grad_params
+ * already hold zeros (a persistent gradient arena that only this entry point writes): they are then not
+ * rewritten, and no pass over the whole 13 MB arena is needed. */
+#define MSF_TRAIN_DEAD_SLOTS_ZERO 1
 int msf_fusion_train_pass(const msf_fusion_shape* shape, const msf_fusion_call* call, const int64_t* labels,
                           float smoothing, float grad_scale, float* row_loss, float* loss_out,
-                          float* grad_logits_scratch, void* stream);
+                          float* grad_logits_scratch, int32_t flags, void* stream);
 /* Inference pass of src/eval.py:84-90: logits, then softmax -> max -> (confidence, prediction), with the
  * softmax fused into the classifier epilogue on the tensor-core path. */
 int msf_fusion_infer_pass(const msf_fusion_shape* shape, const msf_fusion_call* call, float* conf, int64_t* pred,

@@ -9,6 +9,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int32, c_
 
 MSF_MAX_MODALITIES = 8
 MSF_PREC_F32, MSF_PREC_BF16 = 0, 1
+MSF_TRAIN_DEAD_SLOTS_ZERO = 1
 MSF_ABI_VERSION = 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -82,7 +83,7 @@ PROTOTYPES = {
     "msf_fusion_forward": (c_int32, [POINTER(FusionShape), POINTER(FusionCall), c_void_p]),
     "msf_fusion_backward": (c_int32, [POINTER(FusionShape), POINTER(FusionCall), c_void_p]),
     "msf_fusion_train_pass": (c_int32, [POINTER(FusionShape), POINTER(FusionCall), c_void_p, c_float, c_float,
-                                        c_void_p, c_void_p, c_void_p, c_void_p]),
+                                        c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
     "msf_fusion_infer_pass": (c_int32, [POINTER(FusionShape), POINTER(FusionCall), c_void_p, c_void_p, c_void_p]),
     "msf_debug_head_stamps": (c_int32, [c_void_p]),
     "msf_debug_chain_stamps": (c_int32, [c_void_p]),

@@ -17,7 +17,7 @@ bool fusion_bf16_head_fused(const Layout& L);
 int head_debug_stamps(long long* out16);
 int chain_debug_stamps(long long* out16);
 int fusion_bf16_train(const Layout& L, const msf_fusion_call* c, const int64_t* labels, float smoothing,
-                      float grad_scale, float* row_loss, float* loss_out, cudaStream_t st);
+                      float grad_scale, float* row_loss, float* loss_out, int flags, cudaStream_t st);
 int fusion_bf16_infer(const Layout& L, const msf_fusion_call* c, float* conf, int64_t* pred, cudaStream_t st);
 
 static int check_call(const Layout& L, const msf_fusion_call* c, bool backward) {
@@ -109,14 +109,14 @@ int msf_fusion_backward(const msf_fusion_shape* shape, const msf_fusion_call* ca
 
 int msf_fusion_train_pass(const msf_fusion_shape* shape, const msf_fusion_call* call, const int64_t* labels,
                           float smoothing, float grad_scale, float* row_loss, float* loss_out,
-                          float* grad_logits_scratch, void* stream) {
+                          float* grad_logits_scratch, int32_t flags, void* stream) {
   msf::Layout L;
   int rc = msf::make_layout(shape, &L);
   if (rc) return rc;
   if ((rc = msf::check_call(L, call, false))) return rc;
   MSF_REQUIRE(labels && row_loss && call->grad_params, "msf_fusion_train_pass: labels, row_loss and grad_params are required");
   if (call->precision == MSF_PREC_BF16 && msf::fusion_bf16_head_fused(L))
-    return msf::fusion_bf16_train(L, call, labels, smoothing, grad_scale, row_loss, loss_out, (cudaStream_t)stream);
+    return msf::fusion_bf16_train(L, call, labels, smoothing, grad_scale, row_loss, loss_out, flags, (cudaStream_t)stream);
   // un-fused composition (fp32 parity path, shapes outside the head kernel): same three steps
   MSF_REQUIRE(grad_logits_scratch != nullptr, "msf_fusion_train_pass: this precision / shape needs grad_logits_scratch");
   if ((rc = msf_fusion_forward(shape, call, stream))) return rc;

@@ -232,7 +232,44 @@ struct PrepArgs16 {
   DropCfg drop;
 };
 
-__global__ void __launch_bounds__(256) prep16_kernel(const __grid_constant__ PrepArgs16 a) {
+// Gradient slots that the backward pass ACCUMULATES into (bias / gating gradients via atomics), the dead
+// query/key slots and the slots of deleted pair modules: cleared by the first kernel of the train pass
+// instead of a 13 MB memset node over the whole arena (the GEMM weight gradients are plain stores).
+struct ZeroRange {
+  long long begin, count, stride;
+  int batch;
+};
+constexpr int PREP_MAX_ZERO = 24;
+struct ZeroList {
+  ZeroRange r[PREP_MAX_ZERO];
+  int n;
+  float* base;
+};
+
+__device__ __forceinline__ void zero_ranges(const ZeroList& z, long long tid, long long nthreads) {
+  for (int i = 0; i < z.n; ++i) {
+    const ZeroRange R = z.r[i];
+    for (int b = 0; b < R.batch; ++b) {
+      float* p = z.base + R.begin + (long long)b * R.stride;
+      if (((R.begin + (long long)b * R.stride) & 3) == 0) {
+        const long long n4 = R.count >> 2;
+        for (long long e = tid; e < n4; e += nthreads) reinterpret_cast<float4*>(p)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (long long e = (n4 << 2) + tid; e < R.count; e += nthreads) p[e] = 0.0f;
+      } else {
+        for (long long e = tid; e < R.count; e += nthreads) p[e] = 0.0f;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) prep16_kernel(const __grid_constant__ PrepArgs16 a,
+                                                     const __grid_constant__ ZeroList z) {
+  // a slice of the grid does the clearing (the ranges are small; every thread walking the list costs more)
+  constexpr int kZeroCtas = 64;
+  if (z.n > 0 && blockIdx.y == 0 && blockIdx.x < kZeroCtas) {
+    const int ctas = (int)gridDim.x < kZeroCtas ? (int)gridDim.x : kZeroCtas;
+    zero_ranges(z, blockIdx.x * (long long)blockDim.x + threadIdx.x, (long long)ctas * blockDim.x);
+  }
   const int m = blockIdx.y;
   const int D = a.D[m];
   const DropCfg drop = resolve_drop(a.drop);
@@ -534,7 +571,7 @@ static int check_ws(const WsBf16& ws, const msf_fusion_call* c) {
 
 // F0..F3: inputs -> aggregated modality tokens (ws.agg), gates in ws.G
 static int forward_front(const Layout& L, const msf_fusion_call* c, const WsBf16& ws, const ArenaBf16& A,
-                         cudaStream_t st) {
+                         cudaStream_t st, const ZeroList* zero = nullptr) {
   const int64_t B = c->batch;
   const int M = L.M, H = L.H;
   int rc = MSF_OK;
@@ -562,7 +599,10 @@ static int forward_front(const Layout& L, const msf_fusion_call* c, const WsBf16
     a.drop = drop;
     const long long work = B * (maxd / 4);
     dim3 grid((unsigned)(ceil_div(work, 256) < 1184 ? ceil_div(work, 256) : 1184), (unsigned)M);
-    prep16_kernel<<<grid, 256, 0, st>>>(a);
+    ZeroList zl;
+    memset(&zl, 0, sizeof(zl));
+    if (zero != nullptr) zl = *zero;
+    prep16_kernel<<<grid, 256, 0, st>>>(a, zl);
     MSF_LAUNCH_CHECK();
   }
 
@@ -1025,7 +1065,7 @@ static int backward_back(const Layout& L, const msf_fusion_call* c, const WsBf16
 // One training pass: forward, CE(label smoothing) and backward with the head of the network fused into
 // one kernel (no logits / d logits round trip, 6 launches fewer than forward + msf_cross_entropy + backward).
 int fusion_bf16_train(const Layout& L, const msf_fusion_call* c, const int64_t* labels, float smoothing,
-                      float grad_scale, float* row_loss, float* loss_out, cudaStream_t st) {
+                      float grad_scale, float* row_loss, float* loss_out, int flags, cudaStream_t st) {
   const int64_t B = c->batch;
   WsBf16 ws;
   carve_bf16(L, B, c->workspace, &ws);
@@ -1035,8 +1075,38 @@ int fusion_bf16_train(const Layout& L, const msf_fusion_call* c, const int64_t* 
   MSF_REQUIRE(use_head(L), "fused train pass not available for this shape");
   const ArenaBf16 A = arena_layout(L);
   float* dW = c->grad_params;
-  MSF_CHECK_CUDA(cudaMemsetAsync(dW, 0, (size_t)L.total * sizeof(float), st));
-  if ((rc = forward_front(L, c, ws, A, st))) return rc;
+  // every gradient slot that is accumulated into (or never written) starts from zero; see ZeroList
+  ZeroList zl;
+  memset(&zl, 0, sizeof(zl));
+  zl.base = dW;
+  bool fits = true;
+  auto zr = [&](long long begin, long long count, int batch, long long stride) {
+    if (count <= 0 || batch <= 0) return;
+    if (zl.n >= PREP_MAX_ZERO) { fits = false; return; }
+    zl.r[zl.n].begin = begin; zl.r[zl.n].count = count; zl.r[zl.n].batch = batch; zl.r[zl.n].stride = stride;
+    ++zl.n;
+  };
+  {
+    const long long H = L.H, half = 2 * (H * H + H);
+    const int pairs = L.num_pairs();
+    for (int m = 0; m < L.M; ++m) zr(L.proj_b[m], H, 1, 0);
+    if (pairs > 0) {
+      zr(L.pair_b(0, 2), H, pairs, L.pair_stride);
+      zr(L.pair_b(0, 3), H, pairs, L.pair_stride);
+      if (!(flags & MSF_TRAIN_DEAD_SLOTS_ZERO)) zr(L.pair_w(0, 0), half, pairs, L.pair_stride);
+    }
+    for (int q = 0; q < L.M; ++q)
+      for (int k = 0; k < L.M; ++k)
+        if (q != k && !L.has_pair(q, k)) zr(L.pair_w(L.pair_index(q, k), 2), half, 1, 0);   // deleted module: no writer
+    zr(L.gate_w[0], L.cls_w1 - L.gate_w[0], 1, 0);
+    zr(L.cls_b1, H, 1, 0);
+    zr(L.cls_b2, L.C, 1, 0);
+  }
+  if (!fits) {
+    MSF_CHECK_CUDA(cudaMemsetAsync(dW, 0, (size_t)L.total * sizeof(float), st));
+    zl.n = 0;
+  }
+  if ((rc = forward_front(L, c, ws, A, st, &zl))) return rc;
   HeadLaunch hl;
   memset(&hl, 0, sizeof(hl));
   hl.train = 1; hl.store_acts = 1;

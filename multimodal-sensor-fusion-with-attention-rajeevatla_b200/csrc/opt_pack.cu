@@ -5,6 +5,7 @@
 // registers, so the master arena is not read a second time and two launches disappear from the step.
 // The arithmetic is seg_adamw_kernel's (optim.cu), operation for operation.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "fusion_bf16_layout.cuh"
@@ -32,39 +33,110 @@ struct OptList {
 struct OptCfg {
   float lr, beta1, beta2, eps, wd, grad_scale, max_norm;
   int advance;
+  int fold_norm;   // compute the gradient norm in this launch (needs all CTAs resident: grid barrier)
 };
 constexpr int OPT_VEC_UNIT = 1024, OPT_DEAD_UNIT = 4096;
 
 __device__ unsigned int g_opt_ticket = 0;
+__device__ unsigned int g_opt_barrier = 0;   // grid barrier between the norm phase and the update phase
+__device__ double g_opt_sq = 0.0;            // sum of g^2 of the running launch (reset by its last CTA)
 
-__global__ void __launch_bounds__(256) opt_pack_kernel(const __grid_constant__ OptList list, const OptCfg c,
-                                                       float* __restrict__ p, const float* __restrict__ g,
-                                                       float* __restrict__ m, float* __restrict__ v,
-                                                       const double* __restrict__ sq_norm,
-                                                       unsigned long long* __restrict__ train_state,
-                                                       bf16* __restrict__ arena) {
-  __shared__ float tile[32][33];
-  const double step = (double)train_state[2];
-  const float bc1 = (float)(1.0 - pow((double)c.beta1, step));
-  const float sqrt_bc2 = (float)sqrt(1.0 - pow((double)c.beta2, step));
-  float gs = c.grad_scale;
-  if (c.max_norm > 0.0f) {
-    const float total = (float)sqrt(*sq_norm) * c.grad_scale;
-    gs *= fminf(c.max_norm / (total + 1e-6f), 1.0f);
+struct AdamConsts {
+  float gs, step_size, decay, sqrt_bc2, beta1, beta2, ob1, ob2, eps;
+};
+__device__ __forceinline__ float adam_elem(const AdamConsts& k, float g, float& m, float& v, float p) {
+  const float gi = g * k.gs;
+  m = k.beta1 * m + k.ob1 * gi;
+  v = k.beta2 * v + k.ob2 * gi * gi;
+  return p * k.decay - k.step_size * (m / (sqrtf(v) / k.sqrt_bc2 + k.eps));
+}
+
+// All CTAs are resident (grid <= SMs x occupancy, nothing else runs on the stream): a counter barrier.
+__device__ __forceinline__ void opt_grid_barrier() {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(&g_opt_barrier, 1u);
+    const long long t0 = clock64();
+    while (*reinterpret_cast<volatile unsigned int*>(&g_opt_barrier) < gridDim.x) {
+      if (clock64() - t0 > 4000000000ll) {
+        printf("msf_b200 opt_pack: grid barrier timed out (block %d)\n", blockIdx.x);
+        __trap();
+      }
+    }
+    __threadfence();
   }
-  const float step_size = c.lr / bc1, decay = 1.0f - c.lr * c.wd;
-  const float ob1 = 1.0f - c.beta1, ob2 = 1.0f - c.beta2;
-  auto adam = [&](long long e) -> float {
-    const float gi = __ldg(g + e) * gs;
-    const float mi = c.beta1 * m[e] + ob1 * gi;
-    const float vi = c.beta2 * v[e] + ob2 * gi * gi;
-    const float x = p[e] * decay - step_size * (mi / (sqrtf(vi) / sqrt_bc2 + c.eps));
-    p[e] = x;
-    m[e] = mi;
-    v[e] = vi;
-    return x;
-  };
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256, 4) opt_pack_kernel(const __grid_constant__ OptList list, const OptCfg c,
+                                                          float* __restrict__ p, const float* __restrict__ g,
+                                                          float* __restrict__ m, float* __restrict__ v,
+                                                          double* __restrict__ sq_norm,
+                                                          unsigned long long* __restrict__ train_state,
+                                                          bf16* __restrict__ arena) {
+  __shared__ float tile[32][33];
+  __shared__ double red[8];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+
+  if (c.fold_norm) {  // ---- phase 1: sum of g^2 over the live slots (dead slots hold exact zeros) ----
+    double sq = 0.0;
+    for (int unit = blockIdx.x; unit < list.total_units; unit += gridDim.x) {
+      int ji = 0;
+      while (ji + 1 < list.count && unit >= list.j[ji + 1].unit_begin) ++ji;
+      const OptJob& J = list.j[ji];
+      if (J.kind == 1) continue;
+      int local = unit - J.unit_begin;
+      const int b = local / J.units_per_batch;
+      local -= b * J.units_per_batch;
+      const long long base = J.begin + (long long)b * J.batch_stride;
+      if (J.kind == 2) {
+        const int tc = (J.cols + 31) >> 5;
+        const int r0 = (local / tc) << 5, c0 = (local % tc) << 5;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = r0 + ty + 8 * i, cc = c0 + tx;
+          if (r < J.rows && cc < J.cols) {
+            const double x = (double)__ldg(g + base + (long long)r * J.cols + cc);
+            sq += x * x;
+          }
+        }
+      } else {
+        const int e1 = min(J.cols, (local + 1) * OPT_VEC_UNIT);
+        for (int e = local * OPT_VEC_UNIT + threadIdx.x; e < e1; e += 256) {
+          const double x = (double)__ldg(g + base + e);
+          sq += x * x;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if (tx == 0) red[ty] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int i = 0; i < 8; ++i) t += red[i];
+      if (t != 0.0) atomicAdd(&g_opt_sq, t);
+    }
+    opt_grid_barrier();
+  }
+
+  // ---- phase 2: clip + AdamW + bf16 copies ----
+  const double sq_total = c.fold_norm ? *reinterpret_cast<volatile double*>(&g_opt_sq) : *sq_norm;
+  const double step = (double)train_state[2];
+  AdamConsts k;
+  {
+    const float bc1 = (float)(1.0 - pow((double)c.beta1, step));
+    k.sqrt_bc2 = (float)sqrt(1.0 - pow((double)c.beta2, step));
+    k.gs = c.grad_scale;
+    if (c.max_norm > 0.0f) {
+      const float total = (float)sqrt(sq_total) * c.grad_scale;
+      k.gs *= fminf(c.max_norm / (total + 1e-6f), 1.0f);
+    }
+    k.step_size = c.lr / bc1;
+    k.decay = 1.0f - c.lr * c.wd;
+    k.beta1 = c.beta1; k.beta2 = c.beta2; k.ob1 = 1.0f - c.beta1; k.ob2 = 1.0f - c.beta2; k.eps = c.eps;
+  }
   for (int unit = blockIdx.x; unit < list.total_units; unit += gridDim.x) {
     int ji = 0;
     while (ji + 1 < list.count && unit >= list.j[ji + 1].unit_begin) ++ji;
@@ -78,26 +150,74 @@ __global__ void __launch_bounds__(256) opt_pack_kernel(const __grid_constant__ O
       const int r0 = (local / tc) << 5, c0 = (local % tc) << 5;
       bf16* dst = arena + J.dst + (long long)b * J.dst_batch;
       bf16* dstT = arena + J.dstT + (long long)b * J.dst_batch;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = r0 + ty + 8 * i, cc = c0 + tx;
-        float x = 0.0f;
+      const bool vec4 = ((base & 3) == 0) && ((J.cols & 3) == 0) && ((J.dst_ld & 3) == 0) && ((J.dstT_ld & 3) == 0) &&
+                        ((J.rows & 3) == 0);
+      if (vec4) {  // thread = (row, 4 consecutive columns): 128-bit accesses on all four fp32 arrays
+        const int r = r0 + (threadIdx.x >> 3), cc = c0 + (threadIdx.x & 7) * 4;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r < J.rows && cc < J.cols) {
-          x = adam(base + (long long)r * J.cols + cc);
-          dst[(long long)r * J.dst_ld + cc] = __float2bfloat16_rn(x);
+          const long long e = base + (long long)r * J.cols + cc;
+          const float4 gg = __ldg(reinterpret_cast<const float4*>(g + e));
+          float4 mm = *reinterpret_cast<float4*>(m + e), vv = *reinterpret_cast<float4*>(v + e);
+          x = *reinterpret_cast<float4*>(p + e);
+          x.x = adam_elem(k, gg.x, mm.x, vv.x, x.x);
+          x.y = adam_elem(k, gg.y, mm.y, vv.y, x.y);
+          x.z = adam_elem(k, gg.z, mm.z, vv.z, x.z);
+          x.w = adam_elem(k, gg.w, mm.w, vv.w, x.w);
+          *reinterpret_cast<float4*>(p + e) = x;
+          *reinterpret_cast<float4*>(m + e) = mm;
+          *reinterpret_cast<float4*>(v + e) = vv;
+          uint2 pk;
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+          h[0] = __floats2bfloat162_rn(x.x, x.y);
+          h[1] = __floats2bfloat162_rn(x.z, x.w);
+          *reinterpret_cast<uint2*>(dst + (long long)r * J.dst_ld + cc) = pk;
         }
-        tile[ty + 8 * i][tx] = x;
-      }
-      __syncthreads();
+        const int lr = threadIdx.x >> 3, lc = (threadIdx.x & 7) * 4;
+        tile[lr][lc] = x.x; tile[lr][lc + 1] = x.y; tile[lr][lc + 2] = x.z; tile[lr][lc + 3] = x.w;
+        __syncthreads();
+        {  // destination row = source column; 4 consecutive destination columns = 4 source rows
+          const int tcn = c0 + (threadIdx.x >> 3), tr = r0 + (threadIdx.x & 7) * 4;
+          if (tcn < J.cols && tr < J.rows) {
+            const int sc = threadIdx.x >> 3, sr = (threadIdx.x & 7) * 4;
+            uint2 pk;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+            h[0] = __floats2bfloat162_rn(tile[sr][sc], tile[sr + 1][sc]);
+            h[1] = __floats2bfloat162_rn(tile[sr + 2][sc], tile[sr + 3][sc]);
+            *reinterpret_cast<uint2*>(dstT + (long long)tcn * J.dstT_ld + tr) = pk;
+          }
+        }
+        __syncthreads();
+      } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int cc = c0 + ty + 8 * i, r = r0 + tx;   // destination row = source column
-        if (cc < J.cols && r < J.rows) dstT[(long long)cc * J.dstT_ld + r] = __float2bfloat16_rn(tile[tx][ty + 8 * i]);
+        for (int i = 0; i < 4; ++i) {
+          const int r = r0 + ty + 8 * i, cc = c0 + tx;
+          float x = 0.0f;
+          if (r < J.rows && cc < J.cols) {
+            const long long e = base + (long long)r * J.cols + cc;
+            float mm = m[e], vv = v[e];
+            x = adam_elem(k, __ldg(g + e), mm, vv, p[e]);
+            p[e] = x; m[e] = mm; v[e] = vv;
+            dst[(long long)r * J.dst_ld + cc] = __float2bfloat16_rn(x);
+          }
+          tile[ty + 8 * i][tx] = x;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int cc = c0 + ty + 8 * i, r = r0 + tx;   // destination row = source column
+          if (cc < J.cols && r < J.rows) dstT[(long long)cc * J.dstT_ld + r] = __float2bfloat16_rn(tile[tx][ty + 8 * i]);
+        }
+        __syncthreads();
       }
-      __syncthreads();
     } else if (J.kind == 0) {
       const int e1 = min(J.cols, (local + 1) * OPT_VEC_UNIT);
-      for (int e = local * OPT_VEC_UNIT + threadIdx.x; e < e1; e += 256) adam(base + e);
+      for (int e = local * OPT_VEC_UNIT + threadIdx.x; e < e1; e += 256) {
+        const long long ee = base + e;
+        float mm = m[ee], vv = v[ee];
+        p[ee] = adam_elem(k, __ldg(g + ee), mm, vv, p[ee]);
+        m[ee] = mm; v[ee] = vv;
+      }
     } else {  // g = m = v = 0: only the decoupled weight decay acts
       const int e0 = local * OPT_DEAD_UNIT, e1 = min(J.cols, e0 + OPT_DEAD_UNIT);
       if (((base + e0) & 3) == 0) {
@@ -105,24 +225,32 @@ __global__ void __launch_bounds__(256) opt_pack_kernel(const __grid_constant__ O
         const int n4 = (e1 - e0) >> 2;
         for (int i = threadIdx.x; i < n4; i += 256) {
           float4 x = p4[i];
-          x.x *= decay; x.y *= decay; x.z *= decay; x.w *= decay;
+          x.x *= k.decay; x.y *= k.decay; x.z *= k.decay; x.w *= k.decay;
           p4[i] = x;
         }
-        for (int e = e0 + (n4 << 2) + threadIdx.x; e < e1; e += 256) p[base + e] *= decay;
+        for (int e = e0 + (n4 << 2) + threadIdx.x; e < e1; e += 256) p[base + e] *= k.decay;
       } else {
-        for (int e = e0 + threadIdx.x; e < e1; e += 256) p[base + e] *= decay;
+        for (int e = e0 + threadIdx.x; e < e1; e += 256) p[base + e] *= k.decay;
       }
     }
   }
-  if (c.advance) {  // the last CTA to finish moves the train state on: {seed, offset + 1, step + 1}
+  // the last CTA to finish publishes the norm, resets the launch-scoped globals and moves the train state on
+  {
     __shared__ bool last;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) last = (atomicAdd(&g_opt_ticket, 1u) == gridDim.x - 1);
     __syncthreads();
     if (last && threadIdx.x == 0) {
-      train_state[1] += 1ull;
-      train_state[2] += 1ull;
+      if (c.fold_norm) {
+        *sq_norm = sq_total;
+        g_opt_sq = 0.0;
+        g_opt_barrier = 0;
+      }
+      if (c.advance) {   // {seed, offset + 1, step + 1}
+        train_state[1] += 1ull;
+        train_state[2] += 1ull;
+      }
       g_opt_ticket = 0;
     }
   }
@@ -179,10 +307,22 @@ int fusion_bf16_opt_pack(const Layout& L, float* params, const float* grad, floa
   vec(L.cls_b2, 0, 1, L.C, 0);
   MSF_REQUIRE(list.count <= OPT_MAX_JOBS, "opt_pack: job table overflow");
 
-  int rc = fusion_live_sq_norm(L, grad, sq_norm, st);
-  if (rc) return rc;
-  OptCfg c{lr, beta1, beta2, eps, wd, grad_scale, max_norm, advance};
-  const int grid = list.total_units < 1184 ? list.total_units : 1184;
+  // One launch when every CTA can be resident at once (the norm phase ends in a grid barrier);
+  // MSF_OPT_TWO_PASS=1 keeps the separate norm kernel.
+  static int resident = -1;
+  if (resident < 0) {
+    int dev = 0, sms = 0, per_sm = 0;
+    MSF_CHECK_CUDA(cudaGetDevice(&dev));
+    MSF_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    MSF_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, opt_pack_kernel, 256, 0));
+    resident = sms * per_sm;
+  }
+  const bool fold = resident >= 148 && !getenv("MSF_OPT_TWO_PASS");
+  int rc = MSF_OK;
+  if (!fold && (rc = fusion_live_sq_norm(L, grad, sq_norm, st))) return rc;
+  OptCfg c{lr, beta1, beta2, eps, wd, grad_scale, max_norm, advance, fold ? 1 : 0};
+  int grid = list.total_units < 1184 ? list.total_units : 1184;
+  if (fold && grid > resident) grid = resident;
   opt_pack_kernel<<<grid, 256, 0, st>>>(list, c, params, grad, exp_avg, exp_avg_sq, sq_norm,
                                         reinterpret_cast<unsigned long long*>(train_state),
                                         reinterpret_cast<bf16*>(arena_v));

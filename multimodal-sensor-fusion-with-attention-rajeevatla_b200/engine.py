@@ -128,7 +128,9 @@ class FusionEngine:
         N.check(lib.msf_fusion_train_pass(ctypes_ref(self.plan.shape), ctypes_ref(c),
                                           self._slots[slot][2].data_ptr(), self.smoothing,
                                           1.0 / (self.batch * self.world), self.row_loss.data_ptr(),
-                                          self.loss.data_ptr(), self.dlogits.data_ptr(), st))
+                                          self.loss.data_ptr(), self.dlogits.data_ptr(),
+                                          N.MSF_TRAIN_DEAD_SLOTS_ZERO,   # self.grad is zero-initialised and only
+                                          st))                           # ever written by this entry point
         if self.comm == "p2p":
             # reduce-scatter + norm, then all-gather + clip + AdamW, both over NVLink peer memory
             N.check(lib.msf_dp_optimizer_step(ctypes_ref(self.plan.shape), ctypes_ref(self.dp_comm),

@@ -236,7 +236,7 @@ def fusion_train_pass_raw(plan: FusionPlan, arena: torch.Tensor, xs: Sequence[to
     scale = (1.0 / B) if grad_scale is None else grad_scale
     N.check(N.lib().msf_fusion_train_pass(ctypes.byref(plan.shape), ctypes.byref(call), _p(labels),
                                           float(smoothing), float(scale), _p(row), _p(loss), _p(scratch),
-                                          _stream()))
+                                          0, _stream()))
     return logits, loss, grad, fw, gates
 
 

@@ -171,7 +171,9 @@ def test_layout_aware_optimizer_matches_torch_adamw():
 
 def test_packed_optimizer_step_equals_step_plus_pack():
     """msf_fusion_optimizer_step_packed = msf_fusion_optimizer_step + msf_fusion_pack_bf16 +
-    msf_train_state_advance, bit for bit (same arithmetic, one launch), over three steps (config-2 shape)."""
+    msf_train_state_advance in one launch, over three steps (config-2 shape).  The packed arena is exactly the
+    pack of the updated parameters; the parameters agree to rounding (the gradient norm is summed in a
+    different order, which can move the clip factor by an ulp)."""
     from helpers import PAMAP2, seeded_case
     ops = _ops()
     model, *_ = seeded_case(PAMAP2, 256, 4, 25, 8, seed=3, device="cuda")
@@ -191,9 +193,11 @@ def test_packed_optimizer_step_equals_step_plus_pack():
     for step in range(3):
         gstep = gr * (1.0 + 0.25 * step)
         ops.fusion_optimizer_step(plan, pa, gstep, ma, va, sa, lr=1e-3, weight_decay=1e-4, max_norm=1.0)
-        ref16 = plan.pack_bf16(pa)
         sa[1:] += 1
-        ops.fusion_optimizer_step_packed(plan, pb, gstep, mb, vb, sb, a16, lr=1e-3, weight_decay=1e-4, max_norm=1.0)
-        assert torch.equal(pa, pb) and torch.equal(ma, mb) and torch.equal(va, vb)
-        assert torch.equal(ref16.view(torch.int16), a16.view(torch.int16))
+        sq = ops.fusion_optimizer_step_packed(plan, pb, gstep, mb, vb, sb, a16, lr=1e-3, weight_decay=1e-4,
+                                              max_norm=1.0)
+        assert abs(float(sq) - float((gstep.double() ** 2).sum())) <= 1e-9 * float(sq)
+        assert float((pa - pb).abs().max()) <= 1e-7 and float((ma - mb).abs().max()) <= 1e-9
+        assert float((va - vb).abs().max()) <= 1e-12
+        assert torch.equal(plan.pack_bf16(pb).view(torch.int16), a16.view(torch.int16))
         assert torch.equal(sa, sb)
