@@ -237,6 +237,12 @@ typedef struct msf_dp_comm {
 int msf_dp_optimizer_step(const msf_fusion_shape* shape, const msf_dp_comm* comm, float* params, float* exp_avg,
                           float* exp_avg_sq, const uint64_t* train_state, float lr, float beta1, float beta2,
                           float eps, float weight_decay, float grad_scale, float max_norm, void* stream);
+/* The same exchange with the update fused like msf_fusion_optimizer_step_packed: clip + AdamW from the
+ * reduced arena, bf16 re-pack of `params_bf16` and (advance_state != 0) the train-state advance in one launch. */
+int msf_dp_optimizer_step_packed(const msf_fusion_shape* shape, const msf_dp_comm* comm, float* params,
+                                 float* exp_avg, float* exp_avg_sq, uint64_t* train_state, float lr, float beta1,
+                                 float beta2, float eps, float weight_decay, float grad_scale, float max_norm,
+                                 void* params_bf16, int32_t advance_state, void* stream);
 /* train_state = DEVICE {seed, offset, step}: offset += 1, step += 1. */
 int msf_train_state_advance(uint64_t* train_state, void* stream);
 

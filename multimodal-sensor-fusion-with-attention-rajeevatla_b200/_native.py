@@ -113,6 +113,9 @@ PROTOTYPES = {
                                                    c_float, c_void_p, c_void_p, c_int32, c_void_p]),
     "msf_dp_optimizer_step": (c_int32, [POINTER(FusionShape), POINTER(DpComm), c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_float, c_float, c_float, c_float, c_float, c_float, c_float, c_void_p]),
+    "msf_dp_optimizer_step_packed": (c_int32, [POINTER(FusionShape), POINTER(DpComm), c_void_p, c_void_p, c_void_p,
+                                               c_void_p, c_float, c_float, c_float, c_float, c_float, c_float,
+                                               c_float, c_void_p, c_int32, c_void_p]),
     "msf_train_state_advance": (c_int32, [c_void_p, c_void_p]),
     "msf_linear_forward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
                                      c_int32, c_void_p]),

@@ -21,6 +21,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "dp_signals.cuh"
 #include "msf_common.cuh"
 
 namespace msf {
@@ -28,25 +29,6 @@ namespace {
 
 constexpr int DP_MAX_RANKS = 8;
 constexpr int DP_MAX_SEGS = 2 * MSF_MAX_MODALITIES * (MSF_MAX_MODALITIES - 1) + 2;
-
-// signal block layout (uint64 words)
-constexpr int SIG_DONE_B = 0;    // [p]: rank p has finished the backward pass of step s
-constexpr int SIG_DONE_R = 8;    // [p]: rank p has finished reducing its slice of step s
-constexpr int SIG_NORM = 16;     // [p]: square-norm of rank p's slice (double bits)
-constexpr int SIG_ACC = 32;      // local accumulator of the slice norm (double)
-constexpr int SIG_TICKET = 33;   // local last-block ticket (reduce kernel)
-constexpr int SIG_TICKET2 = 34;  // local last-block ticket (reduce kernel, phase 2)
-constexpr int SIG_TICKET3 = 35;  // local last-block ticket (update kernel)
-constexpr int SIG_EPOCH = 40;    // local count of completed data-parallel steps: the barrier epoch.  Kept apart from
-                                 // the Adam step counter, which callers may roll back (graph warm-up).
-
-constexpr int SIG_TIME = 48;     // [0..5]: %globaltimer stamps of the last step (reduce start / barrier passed / end,
-                                 // update start / barrier passed / end) — cheap always-on instrumentation
-__device__ __forceinline__ unsigned long long gtime() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
 
 struct DpSeg {
   long long begin, count;   // arena range
@@ -63,40 +45,6 @@ struct DpArgs {
   unsigned long long* sigs[DP_MAX_RANKS];
   const unsigned long long* train_state;  // {seed, offset, step}: step drives the Adam bias correction
 };
-
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-// data a peer pushed into this GPU's memory: system-scope load, never served from a stale L1 line
-__device__ __forceinline__ float4 ld_peer4(const float* p) {
-  float4 v;
-  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ float ld_peer1(const float* p) {
-  float v;
-  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-  return v;
-}
-
-// every thread of the block returns once all ranks have published `epoch` in words [base, base + world)
-__device__ void wait_all(const unsigned long long* sig, int base, int world, unsigned long long epoch) {
-  if ((int)threadIdx.x < world) {
-    const long long t0 = clock64();
-    while (ld_acquire_sys(sig + base + threadIdx.x) < epoch) {
-      if (clock64() - t0 > 8000000000ll) {
-        printf("msf_b200 dp_optim: rank wait timed out (word %d, peer %d, epoch %llu)\n", base, (int)threadIdx.x, epoch);
-        __trap();
-      }
-    }
-  }
-  __syncthreads();
-}
 
 // ---------------------------------------------------------------------------
 // reduce-scatter + norm, push based
@@ -293,10 +241,41 @@ __global__ void __launch_bounds__(256) dp_adamw_kernel(const __grid_constant__ D
 }  // namespace
 }  // namespace msf
 
+namespace msf {
+bool fusion_bf16_eligible(const Layout& L);
+int fusion_bf16_opt_pack_dp(const Layout& L, float* params, const float* reduced, unsigned long long* sig, int world,
+                            float* exp_avg, float* exp_avg_sq, uint64_t* train_state, float lr, float beta1,
+                            float beta2, float eps, float wd, float grad_scale, float max_norm, void* arena_v,
+                            int advance, cudaStream_t st);
+}
+
+static int dp_step(const msf_fusion_shape* shape, const msf_dp_comm* comm, float* params, float* exp_avg,
+                   float* exp_avg_sq, const uint64_t* train_state, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, float grad_scale, float max_norm, void* params_bf16, int advance,
+                   void* stream);
+
 extern "C" int msf_dp_optimizer_step(const msf_fusion_shape* shape, const msf_dp_comm* comm, float* params,
                                      float* exp_avg, float* exp_avg_sq, const uint64_t* train_state, float lr,
                                      float beta1, float beta2, float eps, float weight_decay, float grad_scale,
                                      float max_norm, void* stream) {
+  return dp_step(shape, comm, params, exp_avg, exp_avg_sq, train_state, lr, beta1, beta2, eps, weight_decay,
+                 grad_scale, max_norm, nullptr, 0, stream);
+}
+
+extern "C" int msf_dp_optimizer_step_packed(const msf_fusion_shape* shape, const msf_dp_comm* comm, float* params,
+                                            float* exp_avg, float* exp_avg_sq, uint64_t* train_state, float lr,
+                                            float beta1, float beta2, float eps, float weight_decay,
+                                            float grad_scale, float max_norm, void* params_bf16,
+                                            int32_t advance_state, void* stream) {
+  MSF_REQUIRE(params_bf16 != nullptr, "msf_dp_optimizer_step_packed: null params_bf16");
+  return dp_step(shape, comm, params, exp_avg, exp_avg_sq, train_state, lr, beta1, beta2, eps, weight_decay,
+                 grad_scale, max_norm, params_bf16, advance_state, stream);
+}
+
+static int dp_step(const msf_fusion_shape* shape, const msf_dp_comm* comm, float* params, float* exp_avg,
+                   float* exp_avg_sq, const uint64_t* train_state, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, float grad_scale, float max_norm, void* params_bf16, int advance,
+                   void* stream) {
   msf::Layout L;
   int rc = msf::make_layout(shape, &L);
   if (rc) return rc;
@@ -343,6 +322,15 @@ extern "C" int msf_dp_optimizer_step(const msf_fusion_shape* shape, const msf_dp
   if (blocks > 592) blocks = 592;
   msf::dp_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
   MSF_LAUNCH_CHECK();
+  if (params_bf16 != nullptr) {   // clip + AdamW + bf16 re-pack + state advance in one launch
+    if (!msf::fusion_bf16_eligible(L)) {
+      msf::set_error("shape not eligible for the tensor-core path");
+      return MSF_E_UNSUPPORTED;
+    }
+    return msf::fusion_bf16_opt_pack_dp(L, params, a.reds[a.rank], a.sigs[a.rank], a.world, exp_avg, exp_avg_sq,
+                                        const_cast<uint64_t*>(train_state), lr, beta1, beta2, eps, weight_decay,
+                                        grad_scale, max_norm, params_bf16, advance, st);
+  }
   msf::DpAdam c{lr, beta1, beta2, eps, weight_decay, grad_scale, max_norm};
   dim3 grid(48, (unsigned)a.nseg);
   msf::dp_adamw_kernel<<<grid, 256, 0, st>>>(a, c, params, exp_avg, exp_avg_sq);

@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "dp_signals.cuh"
 #include "fusion_bf16_layout.cuh"
 
 namespace msf {
@@ -34,7 +35,18 @@ struct OptCfg {
   float lr, beta1, beta2, eps, wd, grad_scale, max_norm;
   int advance;
   int fold_norm;   // compute the gradient norm in this launch (needs all CTAs resident: grid barrier)
+  // data-parallel mode (after dp_reduce_kernel): the gradient is this rank's reduced arena, filled by peer
+  // writes; wait for every rank's "slice reduced" flag, form the norm from the published partials and close
+  // the communicator epoch at the end
+  unsigned long long* dp_sig;
+  int dp_world;
 };
+template <bool DP>
+__device__ __forceinline__ float ld_grad(const float* p) { return DP ? ld_peer1(p) : __ldg(p); }
+template <bool DP>
+__device__ __forceinline__ float4 ld_grad4(const float* p) {
+  return DP ? ld_peer4(p) : __ldg(reinterpret_cast<const float4*>(p));
+}
 constexpr int OPT_VEC_UNIT = 1024, OPT_DEAD_UNIT = 4096;
 
 __device__ unsigned int g_opt_ticket = 0;
@@ -69,6 +81,7 @@ __device__ __forceinline__ void opt_grid_barrier() {
   __syncthreads();
 }
 
+template <bool DP>
 __global__ void __launch_bounds__(256, 4) opt_pack_kernel(const __grid_constant__ OptList list, const OptCfg c,
                                                           float* __restrict__ p, const float* __restrict__ g,
                                                           float* __restrict__ m, float* __restrict__ v,
@@ -78,8 +91,18 @@ __global__ void __launch_bounds__(256, 4) opt_pack_kernel(const __grid_constant_
   __shared__ float tile[32][33];
   __shared__ double red[8];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  unsigned long long dp_epoch = 0ull;
+  double dp_total = 0.0;
+  if (DP) {
+    dp_epoch = c.dp_sig[SIG_EPOCH] + 1ull;
+    if (blockIdx.x == 0 && threadIdx.x == 0) c.dp_sig[SIG_TIME + 3] = gtime();
+    wait_all(c.dp_sig, SIG_DONE_R, c.dp_world, dp_epoch);
+    if (blockIdx.x == 0 && threadIdx.x == 0) c.dp_sig[SIG_TIME + 4] = gtime();
+    for (int r = 0; r < c.dp_world; ++r)
+      dp_total += __longlong_as_double((long long)ld_acquire_sys(c.dp_sig + SIG_NORM + r));
+  }
 
-  if (c.fold_norm) {  // ---- phase 1: sum of g^2 over the live slots (dead slots hold exact zeros) ----
+  if (!DP && c.fold_norm) {  // ---- phase 1: sum of g^2 over the live slots (dead slots hold exact zeros) ----
     double sq = 0.0;
     for (int unit = blockIdx.x; unit < list.total_units; unit += gridDim.x) {
       int ji = 0;
@@ -122,7 +145,7 @@ __global__ void __launch_bounds__(256, 4) opt_pack_kernel(const __grid_constant_
   }
 
   // ---- phase 2: clip + AdamW + bf16 copies ----
-  const double sq_total = c.fold_norm ? *reinterpret_cast<volatile double*>(&g_opt_sq) : *sq_norm;
+  const double sq_total = DP ? dp_total : (c.fold_norm ? *reinterpret_cast<volatile double*>(&g_opt_sq) : *sq_norm);
   const double step = (double)train_state[2];
   AdamConsts k;
   {
@@ -157,7 +180,7 @@ __global__ void __launch_bounds__(256, 4) opt_pack_kernel(const __grid_constant_
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r < J.rows && cc < J.cols) {
           const long long e = base + (long long)r * J.cols + cc;
-          const float4 gg = __ldg(reinterpret_cast<const float4*>(g + e));
+          const float4 gg = ld_grad4<DP>(g + e);
           float4 mm = *reinterpret_cast<float4*>(m + e), vv = *reinterpret_cast<float4*>(v + e);
           x = *reinterpret_cast<float4*>(p + e);
           x.x = adam_elem(k, gg.x, mm.x, vv.x, x.x);
@@ -196,7 +219,7 @@ __global__ void __launch_bounds__(256, 4) opt_pack_kernel(const __grid_constant_
           if (r < J.rows && cc < J.cols) {
             const long long e = base + (long long)r * J.cols + cc;
             float mm = m[e], vv = v[e];
-            x = adam_elem(k, __ldg(g + e), mm, vv, p[e]);
+            x = adam_elem(k, ld_grad<DP>(g + e), mm, vv, p[e]);
             p[e] = x; m[e] = mm; v[e] = vv;
             dst[(long long)r * J.dst_ld + cc] = __float2bfloat16_rn(x);
           }
@@ -215,7 +238,7 @@ __global__ void __launch_bounds__(256, 4) opt_pack_kernel(const __grid_constant_
       for (int e = local * OPT_VEC_UNIT + threadIdx.x; e < e1; e += 256) {
         const long long ee = base + e;
         float mm = m[ee], vv = v[ee];
-        p[ee] = adam_elem(k, __ldg(g + ee), mm, vv, p[ee]);
+        p[ee] = adam_elem(k, ld_grad<DP>(g + ee), mm, vv, p[ee]);
         m[ee] = mm; v[ee] = vv;
       }
     } else {  // g = m = v = 0: only the decoupled weight decay acts
@@ -242,7 +265,11 @@ __global__ void __launch_bounds__(256, 4) opt_pack_kernel(const __grid_constant_
     if (threadIdx.x == 0) last = (atomicAdd(&g_opt_ticket, 1u) == gridDim.x - 1);
     __syncthreads();
     if (last && threadIdx.x == 0) {
-      if (c.fold_norm) {
+      if (DP) {   // close the communicator epoch
+        if (sq_norm != nullptr) *sq_norm = sq_total;
+        c.dp_sig[SIG_EPOCH] = dp_epoch;
+        c.dp_sig[SIG_TIME + 5] = gtime();
+      } else if (c.fold_norm) {
         *sq_norm = sq_total;
         g_opt_sq = 0.0;
         g_opt_barrier = 0;
@@ -258,12 +285,8 @@ __global__ void __launch_bounds__(256, 4) opt_pack_kernel(const __grid_constant_
 
 }  // namespace
 
-int fusion_bf16_opt_pack(const Layout& L, float* params, const float* grad, float* exp_avg, float* exp_avg_sq,
-                         uint64_t* train_state, float lr, float beta1, float beta2, float eps, float wd,
-                         float grad_scale, float max_norm, double* sq_norm, void* arena_v, int advance,
-                         cudaStream_t st) {
+static int build_jobs(const Layout& L, OptList& list) {
   const ArenaBf16 A = arena_layout(L);
-  OptList list;
   memset(&list, 0, sizeof(list));
   const long long H = L.H;
   auto push = [&](OptJob J, int units) {
@@ -306,7 +329,16 @@ int fusion_bf16_opt_pack(const Layout& L, float* params, const float* grad, floa
   matrix(L.cls_w2, 0, 1, L.C, L.H, A.w2, L.H, A.w2T, A.Cp, 0);   // w2T padding columns stay zero
   vec(L.cls_b2, 0, 1, L.C, 0);
   MSF_REQUIRE(list.count <= OPT_MAX_JOBS, "opt_pack: job table overflow");
+  return MSF_OK;
+}
 
+int fusion_bf16_opt_pack(const Layout& L, float* params, const float* grad, float* exp_avg, float* exp_avg_sq,
+                         uint64_t* train_state, float lr, float beta1, float beta2, float eps, float wd,
+                         float grad_scale, float max_norm, double* sq_norm, void* arena_v, int advance,
+                         cudaStream_t st) {
+  OptList list;
+  int rc0 = build_jobs(L, list);
+  if (rc0) return rc0;
   // One launch when every CTA can be resident at once (the norm phase ends in a grid barrier);
   // MSF_OPT_TWO_PASS=1 keeps the separate norm kernel.
   static int resident = -1;
@@ -314,18 +346,36 @@ int fusion_bf16_opt_pack(const Layout& L, float* params, const float* grad, floa
     int dev = 0, sms = 0, per_sm = 0;
     MSF_CHECK_CUDA(cudaGetDevice(&dev));
     MSF_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    MSF_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, opt_pack_kernel, 256, 0));
+    MSF_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, opt_pack_kernel<false>, 256, 0));
     resident = sms * per_sm;
   }
   const bool fold = resident >= 148 && !getenv("MSF_OPT_TWO_PASS");
   int rc = MSF_OK;
   if (!fold && (rc = fusion_live_sq_norm(L, grad, sq_norm, st))) return rc;
-  OptCfg c{lr, beta1, beta2, eps, wd, grad_scale, max_norm, advance, fold ? 1 : 0};
+  OptCfg c{lr, beta1, beta2, eps, wd, grad_scale, max_norm, advance, fold ? 1 : 0, nullptr, 0};
   int grid = list.total_units < 1184 ? list.total_units : 1184;
   if (fold && grid > resident) grid = resident;
-  opt_pack_kernel<<<grid, 256, 0, st>>>(list, c, params, grad, exp_avg, exp_avg_sq, sq_norm,
+  opt_pack_kernel<false><<<grid, 256, 0, st>>>(list, c, params, grad, exp_avg, exp_avg_sq, sq_norm,
                                         reinterpret_cast<unsigned long long*>(train_state),
                                         reinterpret_cast<bf16*>(arena_v));
+  MSF_LAUNCH_CHECK();
+  return MSF_OK;
+}
+
+// Data-parallel variant: `reduced` is this rank's reduced-gradient arena (pushed by the slice owners in
+// dp_reduce_kernel), `sig` its signal block.  Must follow dp_reduce_kernel on the same stream.
+int fusion_bf16_opt_pack_dp(const Layout& L, float* params, const float* reduced, unsigned long long* sig, int world,
+                            float* exp_avg, float* exp_avg_sq, uint64_t* train_state, float lr, float beta1,
+                            float beta2, float eps, float wd, float grad_scale, float max_norm, void* arena_v,
+                            int advance, cudaStream_t st) {
+  OptList list;
+  int rc = build_jobs(L, list);
+  if (rc) return rc;
+  OptCfg c{lr, beta1, beta2, eps, wd, grad_scale, max_norm, advance, 0, sig, world};
+  const int grid = list.total_units < 592 ? list.total_units : 592;
+  opt_pack_kernel<true><<<grid, 256, 0, st>>>(list, c, params, reduced, exp_avg, exp_avg_sq, nullptr,
+                                              reinterpret_cast<unsigned long long*>(train_state),
+                                              reinterpret_cast<bf16*>(arena_v));
   MSF_LAUNCH_CHECK();
   return MSF_OK;
 }

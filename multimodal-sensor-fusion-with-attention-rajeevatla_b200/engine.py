@@ -132,11 +132,15 @@ class FusionEngine:
                                           N.MSF_TRAIN_DEAD_SLOTS_ZERO,   # self.grad is zero-initialised and only
                                           st))                           # ever written by this entry point
         if self.comm == "p2p":
-            # reduce-scatter + norm, then all-gather + clip + AdamW, both over NVLink peer memory
-            N.check(lib.msf_dp_optimizer_step(ctypes_ref(self.plan.shape), ctypes_ref(self.dp_comm),
-                                              self.arena.data_ptr(), self.exp_avg.data_ptr(),
-                                              self.exp_avg_sq.data_ptr(), self.state.data_ptr(), self.lr,
-                                              self.betas[0], self.betas[1], self.eps, self.wd, 1.0, self.max_norm, st))
+            # reduce-scatter + norm over NVLink peer memory, then clip + AdamW (+ bf16 re-pack + state advance
+            # in the same launch on the tensor-core path) from the local reduced arena
+            args = (ctypes_ref(self.plan.shape), ctypes_ref(self.dp_comm), self.arena.data_ptr(),
+                    self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.state.data_ptr(), self.lr,
+                    self.betas[0], self.betas[1], self.eps, self.wd, 1.0, self.max_norm)
+            if self.arena_bf16 is not None:
+                N.check(lib.msf_dp_optimizer_step_packed(*args, self.arena_bf16.data_ptr(), 1, st))
+                return
+            N.check(lib.msf_dp_optimizer_step(*args, st))
         else:
             if self._nccl_step(lib, st):
                 return   # optimizer, bf16 re-pack and state advance were one launch

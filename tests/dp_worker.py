@@ -44,6 +44,22 @@ def main():
     dist.all_gather(other, mine)
     out = {"replicas_identical": all(bool(torch.equal(o, mine)) for o in other),
            "p2p_vs_nccl": float((res["p2p"] - res["nccl"]).abs().max())}
+    # tensor-core path: the exchange is fused with AdamW + bf16 re-pack + state advance (one launch)
+    model, feats, mask, labels = seeded_case(PAMAP2, 256, 4, 25, GLOBAL_B, seed=31, device=dev)
+    eng = engine.FusionEngine(model, GLOBAL_B // world, precision="bf16", seed=9, use_graph=True, comm="p2p")
+    eng.p = 0.0
+    shard = ({k: v[sl] for k, v in feats.items()}, mask[sl], labels[sl])
+    for _ in range(STEPS):
+        eng.train_step(*shard)
+    torch.cuda.synchronize()
+    mine16 = eng.arena.clone()
+    other = [torch.empty_like(mine16) for _ in range(world)]
+    dist.all_gather(other, mine16)
+    out["bf16_replicas_identical"] = all(bool(torch.equal(o, mine16)) for o in other)
+    out["bf16_pack_consistent"] = bool(torch.equal(eng.plan.pack_bf16(eng.arena).view(torch.int16),
+                                                   eng.arena_bf16.view(torch.int16)))
+    out["bf16_state"] = eng.state.tolist()
+    out["bf16_vs_fp32"] = float((mine16 - res["p2p"]).abs().max())
     if rank == 0:
         model, feats, mask, labels = seeded_case(PAMAP2, 256, 4, 25, GLOBAL_B, seed=31, device=dev)
         start = torch.cat([p.detach().flatten() for p in model.parameters()]).clone()

@@ -33,3 +33,8 @@ def test_peer_memory_step_matches_nccl_and_single_process():
     assert res["moved"] > 1e-4, res             # the optimizer did step
     assert res["p2p_vs_nccl"] <= 1e-6, res      # same sums (two ranks: a + b is order-free), same AdamW
     assert res["p2p_vs_single"] <= 2e-5, res    # shard sums vs one global sum differ only in rounding
+    # bf16 engine: exchange + AdamW + bf16 re-pack + state advance in one launch (msf_dp_optimizer_step_packed)
+    assert res["bf16_replicas_identical"], res
+    assert res["bf16_pack_consistent"], res     # the compute arena is exactly the pack of the updated parameters
+    assert res["bf16_state"][2] >= 3 and res["bf16_state"][1] == res["bf16_state"][2] - 1, res
+    assert res["bf16_vs_fp32"] <= 1.3e-2, res   # Adam turns sign flips of ~0 gradients into 2*lr per step
