@@ -74,6 +74,7 @@ PROTOTYPES = {
     "msf_launch_count": (c_uint64, []),
     "msf_prof_enable": (c_int32, [c_int32]),
     "msf_prof_report": (c_int32, [ctypes.c_char_p, c_size_t]),
+    "msf_memcpy_batch": (c_int32, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_size_t), c_int32, c_void_p]),
     "msf_device_check": (c_int32, [POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]),
     "msf_fusion_param_count": (c_int32, [POINTER(FusionShape), POINTER(c_int64)]),
     "msf_fusion_param_offset": (c_int32, [POINTER(FusionShape), c_int32, c_int32, POINTER(c_int64)]),

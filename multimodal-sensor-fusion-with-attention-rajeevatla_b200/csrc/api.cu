@@ -1,5 +1,6 @@
 // Library-level entry points: version, error string, device check, arena layout.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -20,6 +21,15 @@ std::vector<ProfRecord> g_prof;
 }  // namespace
 
 bool prof_enabled() { return g_prof_on; }
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MSF_PDL");
+    on = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
 
 void prof_begin(const char* label, double flops, cudaStream_t stream) {
   if (!g_prof_on) return;
@@ -198,6 +208,14 @@ int msf_fusion_param_offset(const msf_fusion_shape* shape, int32_t kind, int32_t
   }
   msf::set_error("unknown tensor kind %d", kind);
   return MSF_E_INVALID;
+}
+
+int msf_memcpy_batch(void* const* dst, const void* const* src, const size_t* bytes, int32_t n, void* stream) {
+  MSF_REQUIRE(dst && src && bytes && n >= 0, "msf_memcpy_batch: bad arguments");
+  for (int i = 0; i < n; ++i)
+    if (bytes[i] > 0)
+      MSF_CHECK_CUDA(cudaMemcpyAsync(dst[i], src[i], bytes[i], cudaMemcpyDefault, (cudaStream_t)stream));
+  return MSF_OK;
 }
 
 }  // extern "C"

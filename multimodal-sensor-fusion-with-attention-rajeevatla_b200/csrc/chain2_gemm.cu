@@ -134,6 +134,8 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();     // the prologue above overlapped the previous kernel; its outputs are visible from here on
+  pdl_launch();
   long long dbg_acc[4] = {0, 0, 0, 0};
   if (blockIdx.x == 0 && threadIdx.x == 0) g_chain_stamps[0] = clock64();
 
@@ -487,10 +489,10 @@ int chain2_launch(ChainLaunch& L, cudaStream_t stream, const char* label) {
   }
   if (L.mode == 0) {
     MSF_CHECK_CUDA(cudaFuncSetAttribute(chain2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    chain2_kernel<0><<<grid, C2_THREADS, smem, stream>>>(L);
+    MSF_CHECK_CUDA(launch_pdl(chain2_kernel<0>, dim3(grid), dim3(C2_THREADS), smem, stream, L));
   } else {
     MSF_CHECK_CUDA(cudaFuncSetAttribute(chain2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    chain2_kernel<1><<<grid, C2_THREADS, smem, stream>>>(L);
+    MSF_CHECK_CUDA(launch_pdl(chain2_kernel<1>, dim3(grid), dim3(C2_THREADS), smem, stream, L));
   }
   MSF_LAUNCH_CHECK();
   prof_end(stream);

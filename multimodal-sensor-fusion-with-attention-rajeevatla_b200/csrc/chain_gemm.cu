@@ -122,6 +122,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();
+  pdl_launch();
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -419,10 +421,10 @@ int chain_launch(ChainLaunch& L, cudaStream_t stream, const char* label) {
   }
   if (L.mode == 0) {
     MSF_CHECK_CUDA(cudaFuncSetAttribute(chain_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    chain_kernel<0><<<grid, CH_THREADS, smem, stream>>>(L);
+    MSF_CHECK_CUDA(launch_pdl(chain_kernel<0>, dim3(grid), dim3(CH_THREADS), smem, stream, L));
   } else {
     MSF_CHECK_CUDA(cudaFuncSetAttribute(chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    chain_kernel<1><<<grid, CH_THREADS, smem, stream>>>(L);
+    MSF_CHECK_CUDA(launch_pdl(chain_kernel<1>, dim3(grid), dim3(CH_THREADS), smem, stream, L));
   }
   MSF_LAUNCH_CHECK();
   prof_end(stream);

@@ -264,6 +264,8 @@ __device__ __forceinline__ void zero_ranges(const ZeroList& z, long long tid, lo
 
 __global__ void __launch_bounds__(256) prep16_kernel(const __grid_constant__ PrepArgs16 a,
                                                      const __grid_constant__ ZeroList z) {
+  pdl_wait();
+  pdl_launch();
   // a slice of the grid does the clearing (the ranges are small; every thread walking the list costs more)
   constexpr int kZeroCtas = 64;
   if (z.n > 0 && blockIdx.y == 0 && blockIdx.x < kZeroCtas) {
@@ -602,7 +604,7 @@ static int forward_front(const Layout& L, const msf_fusion_call* c, const WsBf16
     ZeroList zl;
     memset(&zl, 0, sizeof(zl));
     if (zero != nullptr) zl = *zero;
-    prep16_kernel<<<grid, 256, 0, st>>>(a, zl);
+    MSF_CHECK_CUDA(launch_pdl(prep16_kernel, grid, dim3(256), 0, st, a, zl));
     MSF_LAUNCH_CHECK();
   }
 

@@ -341,6 +341,8 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_kernel(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();     // everything above (incl. the parameter rows, written >= 2 kernels ago) overlapped the previous kernel
+  pdl_launch();
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -747,7 +749,7 @@ int head_launch(HeadLaunch& L, cudaStream_t stream, const char* label) {
     prof_begin(label, L.train ? 2.0 * fwd : fwd, stream);
   }
   MSF_CHECK_CUDA(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  head_kernel<<<grid, HD_THREADS, smem, stream>>>(L);
+  MSF_CHECK_CUDA(launch_pdl(head_kernel, dim3(grid), dim3(HD_THREADS), smem, stream, L));
   MSF_LAUNCH_CHECK();
   prof_end(stream);
   return MSF_OK;

@@ -6,6 +6,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/msf_b200.h"
 
@@ -47,6 +48,35 @@ extern unsigned long long g_launch_count;
 bool prof_enabled();
 void prof_begin(const char* label, double flops, cudaStream_t stream);
 void prof_end(cudaStream_t stream);
+
+// ---------------------------------------------------------------------------
+// Programmatic dependent launch: a kernel launched with launch_pdl() may start while its predecessor on the
+// stream is still running; it runs its prologue (barrier init, TMEM allocation, descriptor prefetch, constants
+// written at least two kernels earlier), then pdl_wait() blocks until the predecessor has completed and its
+// writes are visible.  Every such kernel calls pdl_launch() only AFTER pdl_wait(), so at most two kernels
+// overlap and whatever a prologue reads was written by a kernel that has already completed.
+// Works eagerly and under stream capture (programmatic graph edges).  MSF_PDL=0 turns it off.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

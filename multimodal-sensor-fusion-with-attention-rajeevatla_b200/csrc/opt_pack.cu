@@ -91,6 +91,8 @@ __global__ void __launch_bounds__(256, 4) opt_pack_kernel(const __grid_constant_
   __shared__ float tile[32][33];
   __shared__ double red[8];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  pdl_wait();
+  pdl_launch();
   unsigned long long dp_epoch = 0ull;
   double dp_total = 0.0;
   if (DP) {
@@ -355,9 +357,9 @@ int fusion_bf16_opt_pack(const Layout& L, float* params, const float* grad, floa
   OptCfg c{lr, beta1, beta2, eps, wd, grad_scale, max_norm, advance, fold ? 1 : 0, nullptr, 0};
   int grid = list.total_units < 1184 ? list.total_units : 1184;
   if (fold && grid > resident) grid = resident;
-  opt_pack_kernel<false><<<grid, 256, 0, st>>>(list, c, params, grad, exp_avg, exp_avg_sq, sq_norm,
-                                        reinterpret_cast<unsigned long long*>(train_state),
-                                        reinterpret_cast<bf16*>(arena_v));
+  MSF_CHECK_CUDA(launch_pdl(opt_pack_kernel<false>, dim3(grid), dim3(256), 0, st, list, c, params, grad, exp_avg,
+                            exp_avg_sq, sq_norm, reinterpret_cast<unsigned long long*>(train_state),
+                            reinterpret_cast<bf16*>(arena_v)));
   MSF_LAUNCH_CHECK();
   return MSF_OK;
 }

@@ -351,6 +351,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();     // prologue overlapped the previous kernel (programmatic dependent launch, msf_common.cuh)
+  pdl_launch();
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -640,10 +642,10 @@ int TcBuilder::flush() {
   }
   if (mn_major) {
     MSF_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_gemm_kernel<true><<<grid, TC_THREADS, smem, stream>>>(L);
+    MSF_CHECK_CUDA(launch_pdl(tc_gemm_kernel<true>, dim3(grid), dim3(TC_THREADS), smem, stream, L));
   } else {
     MSF_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_gemm_kernel<false><<<grid, TC_THREADS, smem, stream>>>(L);
+    MSF_CHECK_CUDA(launch_pdl(tc_gemm_kernel<false>, dim3(grid), dim3(TC_THREADS), smem, stream, L));
   }
   MSF_LAUNCH_CHECK();
   prof_end(stream);

@@ -101,6 +101,7 @@ class FusionEngine:
         self.state = torch.tensor([seed, 0, 1], dtype=torch.int64, device=dev)
         self._train_graph = None
         self._train_graphs = [None, None]
+        self._loss_ptr = {}          # slot -> where that slot's graph writes the mean loss (default: self.loss)
         self._infer_graph = None
         self._copy_stream = None
         self.launches_per_step = 0
@@ -128,7 +129,7 @@ class FusionEngine:
         N.check(lib.msf_fusion_train_pass(ctypes_ref(self.plan.shape), ctypes_ref(c),
                                           self._slots[slot][2].data_ptr(), self.smoothing,
                                           1.0 / (self.batch * self.world), self.row_loss.data_ptr(),
-                                          self.loss.data_ptr(), self.dlogits.data_ptr(),
+                                          self._loss_ptr.get(slot, self.loss.data_ptr()), self.dlogits.data_ptr(),
                                           N.MSF_TRAIN_DEAD_SLOTS_ZERO,   # self.grad is zero-initialised and only
                                           st))                           # ever written by this entry point
         if self.comm == "p2p":
@@ -246,18 +247,26 @@ class FusionEngine:
         stream.  Returns the bytes that crossed host->device."""
         feats = [features[m] for m in self.plan.names] if isinstance(features, dict) else list(features)
         x, msk, lab = self._slots[slot]
-        moved = 0
-        for dst, src in zip(x, feats):
-            dst.copy_(src, non_blocking=True)
-            moved += src.numel() * src.element_size() if src.device.type == "cpu" else 0
+        pairs = list(zip(x, feats))
         if mask is None:
             msk.fill_(1.0)
         else:
-            msk.copy_(mask, non_blocking=True)
-            moved += mask.numel() * mask.element_size() if mask.device.type == "cpu" else 0
+            pairs.append((msk, mask))
         if labels is not None:
-            lab.copy_(labels, non_blocking=True)
-            moved += labels.numel() * labels.element_size() if labels.device.type == "cpu" else 0
+            pairs.append((lab, labels))
+        moved = sum(src.numel() * src.element_size() for _, src in pairs if src.device.type == "cpu")
+        if all(src.dtype == dst.dtype and src.is_contiguous() and src.numel() == dst.numel()
+               and (src.device.type != "cpu" or src.is_pinned()) for dst, src in pairs):
+            # one library call issues all the asynchronous copies (no per-tensor dispatch on the host)
+            import ctypes
+            n = len(pairs)
+            dsts = (ctypes.c_void_p * n)(*[dst.data_ptr() for dst, _ in pairs])
+            srcs = (ctypes.c_void_p * n)(*[src.data_ptr() for _, src in pairs])
+            sizes = (ctypes.c_size_t * n)(*[src.numel() * src.element_size() for _, src in pairs])
+            N.check(N.lib().msf_memcpy_batch(dsts, srcs, sizes, n, ops._stream()))
+        else:
+            for dst, src in pairs:
+                dst.copy_(src, non_blocking=True)
         return moved
 
     def _replay_train(self, slot: int = 0) -> None:
@@ -267,6 +276,32 @@ class FusionEngine:
         if self._train_graphs[slot] is None:
             self._replay_train_capture_only(slot)
         self._train_graphs[slot].replay()
+
+    def add_resident_batch(self, features, mask: Optional[torch.Tensor], labels: torch.Tensor) -> int:
+        """Register a batch that already lives in device memory (fp32 features (B, D_m), fp32 mask (B, M),
+        int64 labels (B)) as an input slot of its own: `train_step_slot(slot)` then trains on it in place —
+        no copy into the static buffers.  For datasets that fit in HBM (PAMAP2 does many times over)."""
+        feats = [features[m] for m in self.plan.names] if isinstance(features, dict) else list(features)
+        B = self.batch
+        xs = []
+        for f, d in zip(feats, self.plan.dims):
+            if f.device != self.dev or f.dtype != torch.float32 or tuple(f.shape) != (B, d) or not f.is_contiguous():
+                raise ValueError("resident features must be contiguous fp32 (batch, in_dim) tensors on the engine's device")
+            xs.append(f)
+        msk = torch.ones(B, self.plan.M, dtype=torch.float32, device=self.dev) if mask is None else mask
+        if msk.device != self.dev or msk.dtype != torch.float32 or tuple(msk.shape) != (B, self.plan.M) \
+                or not msk.is_contiguous():
+            raise ValueError("resident mask must be a contiguous fp32 (batch, modalities) tensor on the engine's device")
+        if labels.device != self.dev or labels.dtype != torch.int64 or tuple(labels.shape) != (B,):
+            raise ValueError("resident labels must be an int64 (batch,) tensor on the engine's device")
+        self._slots.append((xs, msk, labels))
+        self._train_graphs.append(None)
+        return len(self._slots) - 1
+
+    def train_step_slot(self, slot: int) -> torch.Tensor:
+        """One optimizer step on the batch of input slot `slot` (see add_resident_batch)."""
+        self._replay_train(slot)
+        return self.loss
 
     def train_step_resident(self) -> torch.Tensor:
         """One optimizer step on the batch already in the static buffers.
@@ -282,52 +317,60 @@ class FusionEngine:
         """Host-facing training loop: `batches` yields (features, mask, labels) on the host (pinned memory
         makes the copies asynchronous); yields one Python-float loss per batch, in order.
 
-        Two-deep pipeline: while the graph captured over input slot s computes batch i, the host->device
-        copies of batch i+1 run on a copy stream into slot s^1, and the loss of batch i is read back
-        (device->pinned host) after batch i+1 has been enqueued, so neither PCIe direction stalls the
-        compute stream.  Every batch still crosses host->device and every loss device->host."""
+        Two-deep pipeline over two private input slots: while the graph captured over slot s computes batch i,
+        the host->device copies of batch i+1 run on a copy stream into the other slot, and the loss of batch i
+        is picked up after batch i+1 has been enqueued, so neither PCIe direction stalls the compute stream.
+        The step writes its loss straight into pinned host memory (the loss pointer of these two graphs is a
+        mapped host address), so no copy call sits between steps.  Every batch still crosses host->device and
+        every loss device->host."""
         dev = self.dev
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
             self._loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
             self._ev_ready = [torch.cuda.Event() for _ in range(2)]   # slot inputs landed
-            self._ev_free = [torch.cuda.Event() for _ in range(2)]    # graph over the slot finished
-            self._ev_loss = [torch.cuda.Event() for _ in range(2)]    # loss of the slot's step is on the host
+            self._ev_done = [torch.cuda.Event() for _ in range(2)]    # graph over the slot finished (loss on the host)
+            f32 = dict(dtype=torch.float32, device=dev)
+            self._stream_slots = []
+            for s in range(2):
+                self._slots.append(([torch.zeros(self.batch, d, **f32) for d in self.plan.dims],
+                                    torch.ones(self.batch, self.plan.M, **f32),
+                                    torch.zeros(self.batch, dtype=torch.int64, device=dev)))
+                self._train_graphs.append(None)
+                slot = len(self._slots) - 1
+                self._stream_slots.append(slot)
+                self._loss_ptr[slot] = self._loss_host[s:s + 1].data_ptr()   # UVA: host-pinned == device-visible
         if self.use_graph:
-            for s in range(2):                                        # capture before the pipeline starts
-                if self._train_graphs[s] is None:
-                    self._replay_train_capture_only(s)
+            for slot in self._stream_slots:                           # capture before the pipeline starts
+                if self._train_graphs[slot] is None:
+                    self._replay_train_capture_only(slot)
         cs = self._copy_stream
         main = torch.cuda.current_stream(dev)
-
         cs.wait_stream(main)
 
-        def stage(batch, slot):
-            cs.wait_event(self._ev_free[slot])   # no-op until the slot's first step has been recorded
+        def stage(batch, k):
+            cs.wait_event(self._ev_done[k])      # no-op until the slot's first step has been recorded
             with torch.cuda.stream(cs):
-                self.load_batch(batch[0], batch[1], batch[2], slot=slot)
-                self._ev_ready[slot].record(cs)
+                self.load_batch(batch[0], batch[1], batch[2], slot=self._stream_slots[k])
+                self._ev_ready[k].record(cs)
 
         it = iter(batches)
         nxt = next(it, None)
         if nxt is None:
             return
         stage(nxt, 0)
-        slot, pending = 0, None
+        k, pending = 0, None
         while nxt is not None:
-            main.wait_event(self._ev_ready[slot])
-            self._replay_train(slot)
-            self._ev_free[slot].record(main)
-            self._loss_host[slot:slot + 1].copy_(self.loss, non_blocking=True)
-            self._ev_loss[slot].record(main)
+            main.wait_event(self._ev_ready[k])
+            self._replay_train(self._stream_slots[k])
+            self._ev_done[k].record(main)
             nxt = next(it, None)
             if nxt is not None:
-                stage(nxt, slot ^ 1)
+                stage(nxt, k ^ 1)
             if pending is not None:
-                self._ev_loss[pending].synchronize()
+                self._ev_done[pending].synchronize()
                 yield float(self._loss_host[pending])
-            pending, slot = slot, slot ^ 1
-        self._ev_loss[pending].synchronize()
+            pending, k = k, k ^ 1
+        self._ev_done[pending].synchronize()
         yield float(self._loss_host[pending])
 
     def _replay_train_capture_only(self, slot: int) -> None:
