@@ -153,6 +153,8 @@ int msf_fusion_infer_pass(const msf_fusion_shape* shape, const msf_fusion_call* 
 int msf_debug_head_stamps(int64_t* out16);
 /* Same for the last chained pair-GEMM launch: wait-time accounting of CTA 0 (see chain2_gemm.cu). */
 int msf_debug_chain_stamps(int64_t* out16);
+/* Phase stamps of CTA 0 of the last input-projection launch (proj_gemm.cu). */
+int msf_debug_proj_stamps(int64_t* out16);
 /* HybridFusion.compute_adaptive_weights (src/fusion.py:429-479) stand-alone:
  * agg (M, B, H), gate_w (M, H), gate_b (M), mask (B, M) -> weights (B, M). */
 int msf_adaptive_weights(const float* agg, const float* gate_w, const float* gate_b, const float* mask,

@@ -16,6 +16,7 @@ int fusion_bf16_backward(const Layout& L, const msf_fusion_call* c, cudaStream_t
 bool fusion_bf16_head_fused(const Layout& L);
 int head_debug_stamps(long long* out16);
 int chain_debug_stamps(long long* out16);
+int proj_debug_stamps(long long* out16);
 int fusion_bf16_train(const Layout& L, const msf_fusion_call* c, const int64_t* labels, float smoothing,
                       float grad_scale, float* row_loss, float* loss_out, int flags, cudaStream_t st);
 int fusion_bf16_infer(const Layout& L, const msf_fusion_call* c, float* conf, int64_t* pred, cudaStream_t st);
@@ -144,6 +145,11 @@ int msf_fusion_infer_pass(const msf_fusion_shape* shape, const msf_fusion_call* 
 int msf_debug_chain_stamps(int64_t* out16) {
   MSF_REQUIRE(out16 != nullptr, "msf_debug_chain_stamps: null output");
   return msf::chain_debug_stamps(reinterpret_cast<long long*>(out16));
+}
+
+int msf_debug_proj_stamps(int64_t* out16) {
+  MSF_REQUIRE(out16 != nullptr, "msf_debug_proj_stamps: null output");
+  return msf::proj_debug_stamps(reinterpret_cast<long long*>(out16));
 }
 
 int msf_debug_head_stamps(int64_t* out16) {

@@ -21,6 +21,7 @@
 #include "fusion_common.cuh"
 #include "fusion_bf16_layout.cuh"
 #include "head_gemm.cuh"
+#include "proj_gemm.cuh"
 #include "tc_gemm.cuh"
 
 namespace msf {
@@ -584,6 +585,32 @@ static int forward_front(const Layout& L, const msf_fusion_call* c, const WsBf16
   const int pairs = L.num_pairs();
   const int bnH = block_n_for(H);
 
+  if (proj_eligible(H, M, L.D) && !getenv("MSF_NO_PROJ")) {  // F0 + F1 in one kernel (proj_gemm.cu)
+    ProjLaunch pl;
+    memset(&pl, 0, sizeof(pl));
+    pl.M = M; pl.H = H; pl.rows = (int)B;
+    for (int m = 0; m < M; ++m) {
+      MSF_REQUIRE((reinterpret_cast<uintptr_t>(c->x[m]) & 15) == 0, "features of modality %d are not 16-byte aligned", m);
+      pl.D[m] = L.D[m];
+      pl.x[m] = c->x[m];
+      pl.bias[m] = W + L.proj_b[m];
+      if ((rc = tc_encode_map(&pl.map_w[m], W16 + A.wp[m], H, L.D[m], L.D[m], 1, 0, 64, H))) return rc;
+      if ((rc = tc_encode_map(&pl.map_xt[m], ws.xt[m], B, L.D[m], L.D[m], 1, 0, 64, 128))) return rc;
+    }
+    if ((rc = tc_encode_map(&pl.map_p, ws.P, B, H, H, M, BH, 64, 128))) return rc;
+    pl.mask = c->mask;
+    pl.drop = drop;
+    if (zero != nullptr && zero->n > 0) {
+      MSF_REQUIRE(zero->n <= PROJ_MAX_ZERO, "too many gradient ranges to clear");
+      for (int i = 0; i < zero->n; ++i) {
+        pl.zero[i].begin = zero->r[i].begin; pl.zero[i].count = zero->r[i].count;
+        pl.zero[i].stride = zero->r[i].stride; pl.zero[i].batch = zero->r[i].batch;
+      }
+      pl.nzero = zero->n;
+      pl.zero_base = zero->base;
+    }
+    if ((rc = proj_launch(pl, st, "F0+F1 input prep + projections"))) return rc;
+  } else {
   {  // F0
     PrepArgs16 a;
     memset(&a, 0, sizeof(a));
@@ -621,6 +648,8 @@ static int forward_front(const Layout& L, const msf_fusion_call* c, const WsBf16
       tb.add_problem(p);
     }
     if ((rc = tb.flush())) return rc;
+  }
+
   }
 
   const bool use_chain = chain_eligible(H, M) && !getenv("MSF_NO_CHAIN");

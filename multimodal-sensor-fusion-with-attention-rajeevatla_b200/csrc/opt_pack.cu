@@ -148,20 +148,24 @@ __global__ void __launch_bounds__(256, 4) opt_pack_kernel(const __grid_constant_
 
   // ---- phase 2: clip + AdamW + bf16 copies ----
   const double sq_total = DP ? dp_total : (c.fold_norm ? *reinterpret_cast<volatile double*>(&g_opt_sq) : *sq_norm);
-  const double step = (double)train_state[2];
-  AdamConsts k;
-  {
+  __shared__ AdamConsts ks;
+  if (threadIdx.x == 0) {   // two fp64 pow() per CTA instead of per thread
+    const double step = (double)train_state[2];
+    AdamConsts t;
     const float bc1 = (float)(1.0 - pow((double)c.beta1, step));
-    k.sqrt_bc2 = (float)sqrt(1.0 - pow((double)c.beta2, step));
-    k.gs = c.grad_scale;
+    t.sqrt_bc2 = (float)sqrt(1.0 - pow((double)c.beta2, step));
+    t.gs = c.grad_scale;
     if (c.max_norm > 0.0f) {
       const float total = (float)sqrt(sq_total) * c.grad_scale;
-      k.gs *= fminf(c.max_norm / (total + 1e-6f), 1.0f);
+      t.gs *= fminf(c.max_norm / (total + 1e-6f), 1.0f);
     }
-    k.step_size = c.lr / bc1;
-    k.decay = 1.0f - c.lr * c.wd;
-    k.beta1 = c.beta1; k.beta2 = c.beta2; k.ob1 = 1.0f - c.beta1; k.ob2 = 1.0f - c.beta2; k.eps = c.eps;
+    t.step_size = c.lr / bc1;
+    t.decay = 1.0f - c.lr * c.wd;
+    t.beta1 = c.beta1; t.beta2 = c.beta2; t.ob1 = 1.0f - c.beta1; t.ob2 = 1.0f - c.beta2; t.eps = c.eps;
+    ks = t;
   }
+  __syncthreads();
+  const AdamConsts k = ks;
   for (int unit = blockIdx.x; unit < list.total_units; unit += gridDim.x) {
     int ji = 0;
     while (ji + 1 < list.count && unit >= list.j[ji + 1].unit_begin) ++ji;

@@ -54,3 +54,8 @@ N.check(lib.msf_debug_chain_stamps(st))
 us = lambda x: x / 1965.0
 print("chain fwd CTA0: MMA stage-wait %.1f  T-drained-wait %.1f  u-staged-wait %.1f  MMA end @%.1f | epi: G1-wait %.1f u-free-wait %.1f compute %.1f final-wait %.1f end @%.1f | producer: free-stage-wait %.1f end @%.1f"
       % (us(st[1]), us(st[2]), us(st[3]), us(st[4] - st[0]), us(st[5]), us(st[6]), us(st[7]), us(st[8]), us(st[9] - st[0]), us(st[10]), us(st[11] - st[0])))
+
+st = (ctypes.c_int64 * 16)()
+N.check(lib.msf_debug_proj_stamps(st))
+lab = ["entry", "setup done", "consts", "x landed", "X phase end", "philox end", "gemm done", "epilogue end", "all done"]
+print("proj CTA0:", " ".join(f"{lab[i]}:{us(st[i] - st[0]):.1f}" for i in range(9)))
