@@ -347,11 +347,33 @@ class FusionEngine:
         main = torch.cuda.current_stream(dev)
         cs.wait_stream(main)
 
+        import ctypes
+        lib = N.lib()
+        cs_handle = ctypes.c_void_p(cs.cuda_stream)
+        loss_np = self._loss_host.numpy()        # same pinned memory, cheap scalar reads
+        dst_tables = []
+        for slot in self._stream_slots:          # destination pointers / sizes never change
+            x, msk, lab = self._slots[slot]
+            tens = list(x) + [msk, lab]
+            dst_tables.append(((ctypes.c_void_p * len(tens))(*[t.data_ptr() for t in tens]),
+                               (ctypes.c_size_t * len(tens))(*[t.numel() * t.element_size() for t in tens]),
+                               [(t.dtype, t.numel()) for t in tens]))
+
         def stage(batch, k):
             cs.wait_event(self._ev_done[k])      # no-op until the slot's first step has been recorded
-            with torch.cuda.stream(cs):
-                self.load_batch(batch[0], batch[1], batch[2], slot=self._stream_slots[k])
-                self._ev_ready[k].record(cs)
+            feats = [batch[0][m] for m in self.plan.names] if isinstance(batch[0], dict) else list(batch[0])
+            srcs = feats + [batch[1], batch[2]]
+            dsts, sizes, meta = dst_tables[k]
+            if batch[1] is not None and all(
+                    t.dtype == d and t.numel() == n and t.is_contiguous() and (t.device.type != "cpu" or t.is_pinned())
+                    for t, (d, n) in zip(srcs, meta)):
+                # one library call issues every host->device copy of the batch on the copy stream
+                ptrs = (ctypes.c_void_p * len(srcs))(*[t.data_ptr() for t in srcs])
+                N.check(lib.msf_memcpy_batch(dsts, ptrs, sizes, len(srcs), cs_handle))
+            else:
+                with torch.cuda.stream(cs):
+                    self.load_batch(batch[0], batch[1], batch[2], slot=self._stream_slots[k])
+            self._ev_ready[k].record(cs)
 
         it = iter(batches)
         nxt = next(it, None)
@@ -368,10 +390,10 @@ class FusionEngine:
                 stage(nxt, k ^ 1)
             if pending is not None:
                 self._ev_done[pending].synchronize()
-                yield float(self._loss_host[pending])
+                yield float(loss_np[pending])
             pending, k = k, k ^ 1
         self._ev_done[pending].synchronize()
-        yield float(self._loss_host[pending])
+        yield float(loss_np[pending])
 
     def _replay_train_capture_only(self, slot: int) -> None:
         """Capture the train graph over `slot` without leaving a net model update behind."""
