@@ -402,6 +402,99 @@ def run_infer_sweep(args):
     os.write(json_fd, (json.dumps(line) + "\n").encode())
 
 
+def run_raw_infer(args):
+    """Boundary E of SURVEY.md §8d: inference from RAW windows — 4 single-layer LSTM SequenceEncoders
+    (T = 1024; F = 17, 17, 17, 1; hidden 256) -> Linear(256, 128) -> LayerNorm -> HybridFusion -> softmax/argmax,
+    B = 4096 windows on one GPU.  The recurrence runs on msf_lstm_forward (one tcgen05 launch per time step for
+    the four encoders); the same pass with the library (cuDNN) recurrence is timed beside it."""
+    import torch
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    pkg = importlib.import_module(PKG)
+    ops = importlib.import_module(PKG + ".ops")
+    engine_mod = importlib.import_module(PKG + ".engine")
+    sys.path.insert(0, os.path.join(ROOT, PKG, "src"))
+    fusion = importlib.import_module("fusion")
+    encoders = importlib.import_module("encoders")
+    B, T, HID = BATCH, 1024, 256
+    feats_in = {"imu_hand": 17, "imu_chest": 17, "imu_ankle": 17, "heart_rate": 1}
+    torch.manual_seed(0)
+    encs = {m: encoders.SequenceEncoder(f, hidden_dim=HID, output_dim=128, num_layers=1, encoder_type="lstm",
+                                        dropout=DROPOUT).to(dev).eval() for m, f in feats_in.items()}
+    norms = {m: torch.nn.LayerNorm(128).to(dev) for m in feats_in}
+    model = fusion.HybridFusion(DIMS, hidden_dim=HIDDEN, num_classes=CLASSES, num_heads=HEADS, dropout=DROPOUT).eval()
+    eng = engine_mod.FusionEngine(model, B, precision="bf16", use_graph=True)
+    g = torch.Generator(device=dev).manual_seed(1234)
+    xs = {m: torch.randn(B, T, f, device=dev, generator=g) for m, f in feats_in.items()}
+    mask = torch.ones(B, len(feats_in), device=dev)
+    packed_w = [ops.lstm_pack_weights(e.rnn.weight_ih_l0, e.rnn.weight_hh_l0, e.rnn.bias_ih_l0, e.rnn.bias_hh_l0)
+                for e in encs.values()]
+
+    def tail(hs):
+        with torch.no_grad():
+            enc_out = [norms[m](encoders._dense(encs[m].projection, h)) for m, h in zip(feats_in, hs)]
+        return eng.infer(enc_out, mask)
+
+    # the 1024 step launches are captured once into a CUDA graph over static packed-input buffers
+    static_x = [ops.lstm_pack_input(x) for x in xs.values()]
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        ops.lstm_forward(static_x, packed_w, HID)                           # warm-up outside capture
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize()
+    lstm_graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(lstm_graph, stream=side):
+        static_h = ops.lstm_forward(static_x, packed_w, HID)
+
+    def ours():
+        for dst, x in zip(static_x, xs.values()):                           # bf16, time-major, padded: part of the pass
+            dst[:, :, :x.shape[2]] = x.transpose(0, 1)
+        lstm_graph.replay()
+        return tail(static_h)
+
+    def library():
+        with torch.no_grad():
+            hs = [encoders._rnn_fp32(encs[m].rnn, xs[m])[1][0][-1] for m in feats_in]
+        return tail(hs)
+
+    def timed(fn, steps):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(steps):
+            fn()
+        stop.record()
+        torch.cuda.synchronize()
+        return start.elapsed_time(stop) / steps
+
+    steps = max(1, min(args.steps, 5))
+    logits_a = ours()[0].clone()
+    logits_b = library()[0].clone()
+    ms = timed(ours, steps)
+    ms_lib = timed(library, steps)
+    flop = B * sum(T * 2 * (f + HID) * 4 * HID + 2 * HID * 128 for f in feats_in.values()) + B * FLOP_FWD
+    peaks = _peaks()
+    tf = flop / (ms * 1e-3) / 1e12
+    line = {"metric": METRIC, "value": B / (ms * 1e-3), "unit": "windows/s", "n_gpus": 1, "steps": steps, "warmup": 2,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": "inference from raw windows (SURVEY 8d boundary E): 4 LSTM encoders T=1024 + "
+                                   "projection + LayerNorm + HybridFusion + softmax", "batch": B, "seq_len": T,
+                       "l2": "1.1 GB of raw windows per pass >> 126 MiB L2"},
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                         "frac": tf / peaks["tflops"], "traffic": None, "peak_source": peaks["src"],
+                         "kernel": "whole pass: 1024 LSTM-step launches (tc_gemm_kernel, TC_EPI_LSTM) + fusion forward"},
+            "library_recurrence": {"ms_per_step": ms_lib, "value": B / (ms_lib * 1e-3),
+                                   "what": "same pass with torch.nn.LSTM (cuDNN, fp32 no-TF32) for the recurrence"},
+            "max_abs_logit_diff_vs_library": float((logits_a - logits_b).abs().max())}
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
+
+
 def run_ece(args):
     """ECE / reliability binning kernel (uncertainty.py:84-171) on N = 2^28 samples resident in HBM:
     20 B/sample (f32 conf + i64 pred + i64 label), HBM-bound; buffers (5.4 GB) >> L2."""
@@ -540,7 +633,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("MSF_BENCH_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="train", choices=["train", "infer_sweep", "ece"],
+    ap.add_argument("--workload", default="train", choices=["train", "infer_sweep", "ece", "raw_infer"],
                     help="train = the benchmark proper (BASELINE configs[1]); the other two print extra evidence "
                          "lines for configs[2] and the ECE binning kernel (single GPU)")
     args = ap.parse_args()
@@ -550,6 +643,8 @@ def main():
         run_infer_sweep(args)
     elif args.workload == "ece":
         run_ece(args)
+    elif args.workload == "raw_infer":
+        run_raw_infer(args)
     else:
         run_ours(args)
 

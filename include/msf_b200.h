@@ -279,6 +279,29 @@ int msf_attention_core_backward(const float* q, const float* k, const float* v, 
                                 const float* weights, const float* grad_out, float* scratch, float* dq,
                                 float* dk, float* dv, void* stream);
 
+/* ---- LSTM recurrence of SequenceEncoder (src/encoders.py:54-65,135-166) ------ */
+/* nn.LSTM(F, H, num_layers=1, batch_first=True) forward over T steps with zero initial state, bf16 operands /
+ * fp32 accumulate and state, one grouped tensor-core launch per time step for up to MSF_LSTM_MAX_SEQS encoders
+ * of the same batch, length and hidden size.  Operand layouts (prepared once per model / batch by the caller):
+ *   x_bf16  [T][B][64]        bf16, time-major, the F <= 64 features zero-padded to 64 columns
+ *   w_hh    [H/64][4H][64]    bf16: row 4u+g = gate g (i,f,g,o) of hidden unit u, columns split into 64-wide k-blocks
+ *   w_ih    [4H][64]          bf16: same row order, F columns zero-padded to 64
+ *   bias    [4H]              fp32: bias_ih + bias_hh in the same row order
+ *   h_a,h_b [H/64][B][64]     bf16 scratch; h_a holds h_0 (zeros);  cell [B][H] fp32: c_0 in (zeros), c_T out
+ *   h_out   [B][H]            fp32: h_T (what SequenceEncoder feeds to its projection) */
+#define MSF_LSTM_MAX_SEQS 4
+typedef struct msf_lstm_seq {
+  const void* x_bf16;
+  const void* w_hh;
+  const void* w_ih;
+  const float* bias;
+  void* h_a;
+  void* h_b;
+  float* cell;
+  float* h_out;
+} msf_lstm_seq;
+int msf_lstm_forward(const msf_lstm_seq* seqs, int32_t n, int64_t batch, int32_t steps, int32_t hidden, void* stream);
+
 /* ---- tensor-core GEMM building block (encoder/attention projections) ------ */
 /* bf16 operands, fp32 accumulate in TMEM via tcgen05.mma, operands staged by TMA
  * into 128B-swizzled shared memory; D is fp32 or bf16 row-major (ldd elements).

@@ -66,6 +66,13 @@ class DpComm(Structure):
     ]
 
 
+class LstmSeq(ctypes.Structure):  # msf_lstm_seq
+    _fields_ = [
+        ("x_bf16", c_void_p), ("w_hh", c_void_p), ("w_ih", c_void_p), ("bias", c_void_p),
+        ("h_a", c_void_p), ("h_b", c_void_p), ("cell", c_void_p), ("h_out", c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/msf_b200.h declares
 PROTOTYPES = {
     "msf_abi_version": (c_int32, []),
@@ -130,6 +137,7 @@ PROTOTYPES = {
                                               c_int32, c_int32, c_int32, c_float, c_int32, c_uint64,
                                               c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                               c_void_p, c_void_p]),
+    "msf_lstm_forward": (c_int32, [POINTER(LstmSeq), c_int32, c_int64, c_int32, c_int32, c_void_p]),
     "msf_gemm_bf16": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int64,
                                 c_int64, c_int64, c_int64, c_int32, c_void_p, c_int32, c_void_p]),
 }

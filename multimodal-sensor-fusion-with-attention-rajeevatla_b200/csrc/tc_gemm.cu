@@ -62,6 +62,9 @@ struct EpiTile {
   long long ld_aux2;
   float* gate_out;
   const float* gate_in;
+  float* cell;
+  float* h32;
+  long long h_slice;
 };
 
 // 16 consecutive bf16 of one row, raw (two 16-byte loads) or zero when out of range.
@@ -106,6 +109,65 @@ __device__ __noinline__ float column_gate(bool value_gate, const DropCfg& drop, 
   if (col == head * head_dim && col_ok && gate_out != nullptr && row_ok && head < heads)
     gate_out[(long long)row * heads + head] = gate;
   return gate;
+}
+
+// LSTM cell on a tile whose columns are gate-interleaved pre-activations (nn.LSTM gate order i, f, g, o;
+// src/encoders.py:54-65,135-166): 16 accumulator columns = 4 hidden units.  sigmoid / tanh through __expf
+// (abs error ~1e-6, far inside the bf16 path's tolerance).
+__device__ __forceinline__ float lstm_sigmoid(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float lstm_tanh(float x) { return 2.0f / (1.0f + __expf(-2.0f * x)) - 1.0f; }
+
+__device__ __forceinline__ void lstm_tile(const EpiTile T, const float* bias_s, uint32_t tmem_acc, uint32_t tfull,
+                                          uint32_t tfull_parity, int row, int n0, int ncols, int col_begin,
+                                          int col_end) {
+  const bool row_ok = row < T.M;
+  const int hidden = T.N >> 2;
+  const int my_end = min(ncols, col_end);
+  constexpr int kGroups = 8;   // 128 accumulator columns per warp at block_n = 256
+  // the previous cell state of this thread's units is fetched before the accumulator wait: its L2 latency
+  // hides behind the MMAs instead of sitting in front of every 16-column group
+  float4 cprev[kGroups];
+#pragma unroll
+  for (int g = 0; g < kGroups; ++g) {
+    const int c = col_begin + 16 * g;
+    cprev[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row_ok && c < my_end) cprev[g] = *reinterpret_cast<const float4*>(T.cell + (long long)row * hidden + ((n0 + c) >> 2));
+  }
+  mbar_wait(tfull, tfull_parity);
+  tc_fence_after();
+#pragma unroll
+  for (int g = 0; g < kGroups; ++g) {
+    const int c = col_begin + 16 * g;
+    if (c < my_end) {
+      uint32_t acc[16];
+      tmem_ld16_issue(tmem_acc + (uint32_t)c, acc);
+      tmem_wait16(acc);
+      const int u0 = (n0 + c) >> 2;
+      const float cp[4] = {cprev[g].x, cprev[g].y, cprev[g].z, cprev[g].w};
+      float cn[4], hn[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c + 4 * j);
+        const float gi = lstm_sigmoid(__uint_as_float(acc[4 * j + 0]) + b4.x);
+        const float gf = lstm_sigmoid(__uint_as_float(acc[4 * j + 1]) + b4.y);
+        const float gg = lstm_tanh(__uint_as_float(acc[4 * j + 2]) + b4.z);
+        const float go = lstm_sigmoid(__uint_as_float(acc[4 * j + 3]) + b4.w);
+        cn[j] = gf * cp[j] + gi * gg;
+        hn[j] = go * lstm_tanh(cn[j]);
+      }
+      if (row_ok) {
+        *reinterpret_cast<float4*>(T.cell + (long long)row * hidden + u0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+        uint2 pk;
+        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+        h2[0] = __floats2bfloat162_rn(hn[0], hn[1]);
+        h2[1] = __floats2bfloat162_rn(hn[2], hn[3]);
+        __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(T.C) + (long long)(u0 >> 6) * T.h_slice + (long long)row * 64 + (u0 & 63);
+        *reinterpret_cast<uint2*>(hb) = pk;
+        if (T.h32 != nullptr)
+          *reinterpret_cast<float4*>(T.h32 + (long long)row * hidden + u0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+      }
+    }
+  }
 }
 
 // Everything a warp does for one output tile: its 16-column groups of one
@@ -442,6 +504,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       T.head_dim = P.head_dim; T.heads = P.heads; T.site = P.site; T.sub = P.sub; T.scale = P.scale;
       T.C = P.C; T.ldc = P.ldc; T.aux = P.aux; T.ld_aux = P.ld_aux; T.aux2 = P.aux2; T.ld_aux2 = P.ld_aux2;
       T.gate_out = P.gate_out; T.gate_in = P.gate_in; T.dbg = L.dbg;
+      T.cell = P.cell; T.h32 = P.h32; T.h_slice = P.h_slice;
       const bool has_acc = P.K > 0;
       const int acc = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
@@ -472,6 +535,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         case TC_EPI_RELU_GRAD: epilogue_tile<TC_EPI_RELU_GRAD>(T, bias_s, drop, tmem_acc, tf, tp, row, mrow, t.n0, ncols, col_begin, col_end, has_acc, stage, L.stage_pitch, t.m0 + lq * 32, lane); break;
         case TC_EPI_GATE_MUL: epilogue_tile<TC_EPI_GATE_MUL>(T, bias_s, drop, tmem_acc, tf, tp, row, mrow, t.n0, ncols, col_begin, col_end, has_acc, stage, L.stage_pitch, t.m0 + lq * 32, lane); break;
         case TC_EPI_ADD_RELU_GRAD: epilogue_tile<TC_EPI_ADD_RELU_GRAD>(T, bias_s, drop, tmem_acc, tf, tp, row, mrow, t.n0, ncols, col_begin, col_end, has_acc, stage, L.stage_pitch, t.m0 + lq * 32, lane); break;
+        case TC_EPI_LSTM: lstm_tile(T, bias_s, tmem_acc, tf, tp, row, t.n0, ncols, col_begin, col_end); break;
         case TC_EPI_DX: epilogue_tile<TC_EPI_DX>(T, bias_s, drop, tmem_acc, tf, tp, row, mrow, t.n0, ncols, col_begin, col_end, has_acc, stage, L.stage_pitch, t.m0 + lq * 32, lane); break;
       }
       tc_fence_before();
@@ -606,7 +670,7 @@ int TcBuilder::add_problem(const TcProblem& p) {
   return MSF_OK;
 }
 
-int TcBuilder::flush() {
+int TcBuilder::flush(bool keep) {
   if (status != MSF_OK) return status;
   if (L.total_tiles == 0) return MSF_OK;
   MSF_REQUIRE(L.block_n >= 32 && L.block_n <= 256 && L.block_n % 16 == 0 && (!mn_major || L.block_n % 64 == 0),
@@ -649,8 +713,10 @@ int TcBuilder::flush() {
   }
   MSF_LAUNCH_CHECK();
   prof_end(stream);
-  L.count = 0;
-  L.total_tiles = 0;
+  if (!keep) {
+    L.count = 0;
+    L.total_tiles = 0;
+  }
   return MSF_OK;
 }
 

@@ -20,7 +20,7 @@ namespace msf {
 
 constexpr int TC_MAX_SEG = 7;
 constexpr int TC_MAX_PROBLEMS = 40;
-constexpr int TC_MAX_MAPS = 16;
+constexpr int TC_MAX_MAPS = 24;
 constexpr int TC_BLOCK_M = 128;
 constexpr int TC_BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
 constexpr int TC_MAX_STAGES = 6;   // operand pipeline depth is chosen per launch from the shared memory left
@@ -36,7 +36,8 @@ enum TcEpilogue {
   TC_EPI_RELU_GRAD,        // v = acc * (aux > 0 ? scale : 0)
   TC_EPI_GATE_MUL,         // v = acc * gate_in[row, head]
   TC_EPI_ADD_RELU_GRAD,    // v = (acc + aux) * (aux2 > 0 ? scale : 0)
-  TC_EPI_DX                // v = acc * mask[row, mask_col] * drop(site, sub, row, col)
+  TC_EPI_DX,               // v = acc * mask[row, mask_col] * drop(site, sub, row, col)
+  TC_EPI_LSTM              // LSTM cell: columns are gate-interleaved (4*unit + {i,f,g,o}); updates `cell`, writes h
 };
 
 struct TcSegment {
@@ -65,6 +66,12 @@ struct TcProblem {
   int head_dim, heads;
   int site, sub;
   int tile_begin;
+  // TC_EPI_LSTM (N = 4 * hidden): c_t = f*c + i*g in place in `cell` (fp32, rows x hidden); h_t = o*tanh(c_t) goes
+  // to C as bf16 in k-block-major layout [hidden/64][rows][64] (slice pitch h_slice elements: the next step's A
+  // operand) and, if h32 != nullptr, to h32 (fp32, rows x hidden)
+  float* cell;
+  float* h32;
+  long long h_slice;
 };
 
 struct TcLaunch {
@@ -97,7 +104,8 @@ struct TcBuilder {
   int add_map(const void* base, long long rows, long long cols, long long ld, long long depth,
               long long slice, int role_rows);
   int add_problem(const TcProblem& p);
-  int flush();            // launch what has been collected so far
+  int flush(bool keep = false);   // launch what has been collected so far (keep: leave the problems in place
+                                  // so that the same launch can be patched and issued again)
 };
 
 TcProblem tc_blank_problem();

@@ -505,3 +505,62 @@ def fusion_optimizer_step_packed(plan: FusionPlan, params, grad, exp_avg, exp_av
         ctypes.byref(plan.shape), _p(params), _p(grad), _p(exp_avg), _p(exp_avg_sq), _p(train_state), lr, beta1,
         beta2, eps, weight_decay, grad_scale, max_norm, _p(sq_norm), _p(arena_bf16), int(advance), _stream()))
     return sq_norm
+
+
+# ---------------------------------------------------------------------------
+# LSTM recurrence of SequenceEncoder on the tensor cores (inference path)
+# ---------------------------------------------------------------------------
+def lstm_pack_weights(weight_ih: torch.Tensor, weight_hh: torch.Tensor, bias_ih: Optional[torch.Tensor],
+                      bias_hh: Optional[torch.Tensor]):
+    """nn.LSTM layer-0 parameters -> the operand layouts of msf_lstm_forward (include/msf_b200.h):
+    gate-interleaved rows (4u+g), bf16, W_hh split into 64-wide k-blocks, W_ih zero-padded to 64 columns."""
+    H4, F = weight_ih.shape
+    H = H4 // 4
+    if H % 64 != 0 or F > 64:
+        raise N.MsfError(f"msf_lstm_forward needs hidden % 64 == 0 and input_dim <= 64 (got {H}, {F})")
+    dev = weight_hh.device
+    inter = lambda w: w.detach().to(torch.float32).view(4, H, -1).permute(1, 0, 2).reshape(4 * H, -1)
+    w_hh = inter(weight_hh).view(4 * H, H // 64, 64).permute(1, 0, 2).contiguous().to(torch.bfloat16)
+    w_ih = torch.zeros(4 * H, 64, dtype=torch.float32, device=dev)
+    w_ih[:, :F] = inter(weight_ih)
+    bias = torch.zeros(4 * H, dtype=torch.float32, device=dev)
+    if bias_ih is not None:
+        bias = bias + bias_ih.detach().to(torch.float32)
+    if bias_hh is not None:
+        bias = bias + bias_hh.detach().to(torch.float32)
+    bias = bias.view(4, H).t().reshape(4 * H).contiguous()
+    return w_hh, w_ih.to(torch.bfloat16).contiguous(), bias
+
+
+def lstm_pack_input(x: torch.Tensor) -> torch.Tensor:
+    """(B, T, F) fp32 windows -> time-major bf16 [T][B][64] with the features zero-padded to 64 columns."""
+    B, T, F = x.shape
+    out = torch.zeros(T, B, 64, dtype=torch.bfloat16, device=x.device)
+    out[:, :, :F] = x.detach().transpose(0, 1)
+    return out
+
+
+def lstm_forward(xs: Sequence[torch.Tensor], packed: Sequence[tuple], hidden: int) -> List[torch.Tensor]:
+    """``h_T`` (fp32, (B, hidden)) of up to 4 single-layer LSTM encoders over packed inputs ``xs``
+    (``lstm_pack_input``) with packed weights (``lstm_pack_weights``): one tensor-core launch per time step
+    for all of them (msf_lstm_forward)."""
+    require_cuda("lstm_forward")
+    n = len(xs)
+    T, B, _ = xs[0].shape
+    dev = xs[0].device
+    KBH = hidden // 64
+    seqs = (N.LstmSeq * n)()
+    keep, outs = [], []
+    for i, (x, (w_hh, w_ih, bias)) in enumerate(zip(xs, packed)):
+        h_a = torch.zeros(KBH, B, 64, dtype=torch.bfloat16, device=dev)
+        h_b = torch.zeros(KBH, B, 64, dtype=torch.bfloat16, device=dev)
+        cell = torch.zeros(B, hidden, dtype=torch.float32, device=dev)
+        h_out = torch.empty(B, hidden, dtype=torch.float32, device=dev)
+        keep += [h_a, h_b, cell]
+        outs.append(h_out)
+        seqs[i].x_bf16, seqs[i].w_hh, seqs[i].w_ih, seqs[i].bias = _p(x), _p(w_hh), _p(w_ih), _p(bias)
+        seqs[i].h_a, seqs[i].h_b, seqs[i].cell, seqs[i].h_out = _p(h_a), _p(h_b), _p(cell), _p(h_out)
+    N.check(N.lib().msf_lstm_forward(seqs, n, B, T, hidden, _stream()))
+    for t in keep:   # the launches are asynchronous: keep the scratch alive on this stream
+        t.record_stream(torch.cuda.current_stream(dev))
+    return outs

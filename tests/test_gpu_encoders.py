@@ -75,3 +75,31 @@ def test_frame_encoder_shapes_and_masking():
     frames2 = frames.clone()
     frames2[0, 3:] = 100.0
     assert torch.allclose(enc(frames2, mask)[0], out[0], atol=1e-6)
+
+
+@pytest.mark.parametrize("batch,steps,feat,hidden", [(5, 7, 17, 64), (300, 96, 17, 256), (130, 1024, 1, 256)])
+def test_tensor_core_lstm_matches_oracle(batch, steps, feat, hidden):
+    """msf_lstm_forward (bf16 operands, fp32 accumulate / state, one tcgen05 launch per step) against the
+    fp32 CPU oracle of the reference's nn.LSTM call (src/encoders.py:135-166).  Tolerance of the bf16
+    path (BASELINE north_star): max-abs <= 1e-2 on h_T and on the encoder output."""
+    from oracle import encoder_oracle
+    torch.manual_seed(3)
+    enc = dropin_encoders.SequenceEncoder(feat, hidden_dim=hidden, output_dim=128, num_layers=1, encoder_type="lstm",
+                                          dropout=0.0).eval()
+    gen = torch.Generator().manual_seed(4)
+    x = torch.randn(batch, steps, feat, generator=gen)
+    sd = {k: v.detach().clone() for k, v in enc.state_dict().items()}
+    ref_h = encoder_oracle.lstm_last_hidden(sd, "rnn", x, 1)
+    ref_out = ref_h @ sd["projection.weight"].t() + sd["projection.bias"]
+    enc = enc.cuda()
+    enc.precision = "bf16"
+    with torch.no_grad():
+        out = enc(x.cuda())
+        h = dropin_encoders._lstm_tensor_core(enc.rnn, x.cuda())
+    assert torch.isfinite(h).all()
+    assert _maxabs(h, ref_h) <= 1e-2
+    assert _maxabs(out, ref_out) <= 1e-2
+    # the default (fp32) precision keeps the library recurrence
+    enc.precision = "fp32"
+    with torch.no_grad():
+        assert _maxabs(enc(x.cuda()), ref_out) <= 2e-4
