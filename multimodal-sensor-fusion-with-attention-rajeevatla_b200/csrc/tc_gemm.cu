@@ -114,8 +114,9 @@ __device__ __noinline__ float column_gate(bool value_gate, const DropCfg& drop, 
 // LSTM cell on a tile whose columns are gate-interleaved pre-activations (nn.LSTM gate order i, f, g, o;
 // src/encoders.py:54-65,135-166): 16 accumulator columns = 4 hidden units.  sigmoid / tanh through __expf
 // (abs error ~1e-6, far inside the bf16 path's tolerance).
-__device__ __forceinline__ float lstm_sigmoid(float x) { return 1.0f / (1.0f + __expf(-x)); }
-__device__ __forceinline__ float lstm_tanh(float x) { return 2.0f / (1.0f + __expf(-2.0f * x)) - 1.0f; }
+// (MUFU.EX2 + MUFU.RCP: no IEEE-division slow path, the epilogue has to stay small enough for the I-cache)
+__device__ __forceinline__ float lstm_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float lstm_tanh(float x) { return __fdividef(2.0f, 1.0f + __expf(-2.0f * x)) - 1.0f; }
 
 __device__ __forceinline__ void lstm_tile(const EpiTile T, const float* bias_s, uint32_t tmem_acc, uint32_t tfull,
                                           uint32_t tfull_parity, int row, int n0, int ncols, int col_begin,
@@ -123,49 +124,41 @@ __device__ __forceinline__ void lstm_tile(const EpiTile T, const float* bias_s, 
   const bool row_ok = row < T.M;
   const int hidden = T.N >> 2;
   const int my_end = min(ncols, col_end);
-  constexpr int kGroups = 8;   // 128 accumulator columns per warp at block_n = 256
-  // the previous cell state of this thread's units is fetched before the accumulator wait: its L2 latency
-  // hides behind the MMAs instead of sitting in front of every 16-column group
-  float4 cprev[kGroups];
-#pragma unroll
-  for (int g = 0; g < kGroups; ++g) {
-    const int c = col_begin + 16 * g;
-    cprev[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row_ok && c < my_end) cprev[g] = *reinterpret_cast<const float4*>(T.cell + (long long)row * hidden + ((n0 + c) >> 2));
-  }
+  // rolled loop (an unrolled body does not fit the instruction cache: ncu stall_no_inst); the previous cell
+  // state of the NEXT group is fetched before the current group is processed
+  float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row_ok && col_begin < my_end) nxt = *reinterpret_cast<const float4*>(T.cell + (long long)row * hidden + ((n0 + col_begin) >> 2));
   mbar_wait(tfull, tfull_parity);
   tc_fence_after();
+#pragma unroll 1
+  for (int c = col_begin; c < my_end; c += 16) {
+    uint32_t acc[16];
+    tmem_ld16_issue(tmem_acc + (uint32_t)c, acc);
+    const float cp[4] = {nxt.x, nxt.y, nxt.z, nxt.w};
+    if (row_ok && c + 16 < my_end) nxt = *reinterpret_cast<const float4*>(T.cell + (long long)row * hidden + ((n0 + c + 16) >> 2));
+    tmem_wait16(acc);
+    const int u0 = (n0 + c) >> 2;
+    float cn[4], hn[4];
 #pragma unroll
-  for (int g = 0; g < kGroups; ++g) {
-    const int c = col_begin + 16 * g;
-    if (c < my_end) {
-      uint32_t acc[16];
-      tmem_ld16_issue(tmem_acc + (uint32_t)c, acc);
-      tmem_wait16(acc);
-      const int u0 = (n0 + c) >> 2;
-      const float cp[4] = {cprev[g].x, cprev[g].y, cprev[g].z, cprev[g].w};
-      float cn[4], hn[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c + 4 * j);
-        const float gi = lstm_sigmoid(__uint_as_float(acc[4 * j + 0]) + b4.x);
-        const float gf = lstm_sigmoid(__uint_as_float(acc[4 * j + 1]) + b4.y);
-        const float gg = lstm_tanh(__uint_as_float(acc[4 * j + 2]) + b4.z);
-        const float go = lstm_sigmoid(__uint_as_float(acc[4 * j + 3]) + b4.w);
-        cn[j] = gf * cp[j] + gi * gg;
-        hn[j] = go * lstm_tanh(cn[j]);
-      }
-      if (row_ok) {
-        *reinterpret_cast<float4*>(T.cell + (long long)row * hidden + u0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-        uint2 pk;
-        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
-        h2[0] = __floats2bfloat162_rn(hn[0], hn[1]);
-        h2[1] = __floats2bfloat162_rn(hn[2], hn[3]);
-        __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(T.C) + (long long)(u0 >> 6) * T.h_slice + (long long)row * 64 + (u0 & 63);
-        *reinterpret_cast<uint2*>(hb) = pk;
-        if (T.h32 != nullptr)
-          *reinterpret_cast<float4*>(T.h32 + (long long)row * hidden + u0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-      }
+    for (int j = 0; j < 4; ++j) {
+      const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c + 4 * j);
+      const float gi = lstm_sigmoid(__uint_as_float(acc[4 * j + 0]) + b4.x);
+      const float gf = lstm_sigmoid(__uint_as_float(acc[4 * j + 1]) + b4.y);
+      const float gg = lstm_tanh(__uint_as_float(acc[4 * j + 2]) + b4.z);
+      const float go = lstm_sigmoid(__uint_as_float(acc[4 * j + 3]) + b4.w);
+      cn[j] = gf * cp[j] + gi * gg;
+      hn[j] = go * lstm_tanh(cn[j]);
+    }
+    if (row_ok) {
+      *reinterpret_cast<float4*>(T.cell + (long long)row * hidden + u0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+      uint2 pk;
+      __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+      h2[0] = __floats2bfloat162_rn(hn[0], hn[1]);
+      h2[1] = __floats2bfloat162_rn(hn[2], hn[3]);
+      __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(T.C) + (long long)(u0 >> 6) * T.h_slice + (long long)row * 64 + (u0 & 63);
+      *reinterpret_cast<uint2*>(hb) = pk;
+      if (T.h32 != nullptr)
+        *reinterpret_cast<float4*>(T.h32 + (long long)row * hidden + u0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
     }
   }
 }
