@@ -145,9 +145,13 @@ int msf_fusion_train_pass(const msf_fusion_shape* shape, const msf_fusion_call* 
                           float smoothing, float grad_scale, float* row_loss, float* loss_out,
                           float* grad_logits_scratch, int32_t flags, void* stream);
 /* Inference pass of src/eval.py:84-90: logits, then softmax -> max -> (confidence, prediction), with the
- * softmax fused into the classifier epilogue on the tensor-core path. */
+ * softmax fused into the classifier epilogue on the tensor-core path.
+ * present_hint: 0, or the set of modalities (bit m) that call->mask marks present in EVERY row while all others
+ * are absent in EVERY row — the missing-modality subset sweep of src/eval.py:342-404.  The result is the same as
+ * without the hint; the projections of absent modalities, the pair GEMMs with an absent key (attention gate 0:
+ * exactly the out_proj bias remains) and the rows of absent queries are not computed (tensor-core path). */
 int msf_fusion_infer_pass(const msf_fusion_shape* shape, const msf_fusion_call* call, float* conf, int64_t* pred,
-                          void* stream);
+                          uint32_t present_hint, void* stream);
 /* Debugging aid: clock64 stamps (SM cycles) of the phases of CTA 0 in the last fused head-kernel launch
  * (P0 start/end, then acquire/finish of E1..E4, P5 start/end).  Synchronises the device. */
 int msf_debug_head_stamps(int64_t* out16);

@@ -92,7 +92,8 @@ PROTOTYPES = {
     "msf_fusion_backward": (c_int32, [POINTER(FusionShape), POINTER(FusionCall), c_void_p]),
     "msf_fusion_train_pass": (c_int32, [POINTER(FusionShape), POINTER(FusionCall), c_void_p, c_float, c_float,
                                         c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
-    "msf_fusion_infer_pass": (c_int32, [POINTER(FusionShape), POINTER(FusionCall), c_void_p, c_void_p, c_void_p]),
+    "msf_fusion_infer_pass": (c_int32, [POINTER(FusionShape), POINTER(FusionCall), c_void_p, c_void_p, ctypes.c_uint32,
+                                        c_void_p]),
     "msf_debug_head_stamps": (c_int32, [c_void_p]),
     "msf_debug_chain_stamps": (c_int32, [c_void_p]),
     "msf_debug_proj_stamps": (c_int32, [c_void_p]),

@@ -307,6 +307,10 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
               const float* bsrc = L.bias2[L.outer[o].pair[j]];
               if (bsrc) val += __ldg(bsrc + cc);
             }
+            for (int j = 0; j < L.outer[o].nb; ++j) {
+              const float* bsrc = L.bias2[L.outer[o].bias_only[j]];
+              if (bsrc) val += __ldg(bsrc + cc);
+            }
           }
           bias_smem[e] = val;
         }
@@ -432,7 +436,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float a = __uint_as_float(acc[j]);
-          if (MODE == 0) v[j] = (a + bias_s[c + j] + aux[j]) * rscale;
+          if (MODE == 0) v[j] = rscale != 0.0f ? (a + bias_s[c + j] + aux[j]) * rscale : 0.0f;  // masked row: exact 0
           else v[j] = (a + aux[j]) * (aux2[j] > 0.0f ? L.scale : 0.0f);
         }
         st_swizzled16(u_smem, trow, c, v);

@@ -323,6 +323,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
             const float* bsrc = L.bias2[L.outer[o].pair[i]];
             if (bsrc) bsum += __ldg(bsrc + e);
           }
+          for (int i = 0; i < L.outer[o].nb; ++i) {
+            const float* bsrc = L.bias2[L.outer[o].bias_only[i]];
+            if (bsrc) bsum += __ldg(bsrc + e);
+          }
           bias_s[e] = bsum;
         }
         asm volatile("bar.sync 2, %0;" ::"n"(32 * CH_EPI_WARPS) : "memory");
@@ -359,7 +363,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float a = __uint_as_float(acc[j]);
-          if (MODE == 0) v[j] = (a + bias_s[c + j] + aux[j]) * rscale;
+          if (MODE == 0) v[j] = rscale != 0.0f ? (a + bias_s[c + j] + aux[j]) * rscale : 0.0f;  // masked row: exact 0
           else v[j] = (a + aux[j]) * (aux2[j] > 0.0f ? L.scale : 0.0f);
         }
         st_swizzled16(u_smem, trow, c, v);

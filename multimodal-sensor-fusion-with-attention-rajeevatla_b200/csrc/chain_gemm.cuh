@@ -28,6 +28,10 @@ struct ChainOuter {
   short pair[CHAIN_MAX_INNER];     // pair index (z of W1 / W2 / out1, gate slot)
   short sub[CHAIN_MAX_INNER];      // dropout sub-stream of the attention gate (q*M + k)
   short mask_col[CHAIN_MAX_INNER]; // mask column deciding the gate (forward: the key modality)
+  // forward with a batch-uniform mask: pairs whose key modality is absent everywhere have gate 0, i.e. they
+  // contribute exactly their out_proj bias — no GEMMs, only this list for the bias sum
+  short nb;
+  short bias_only[CHAIN_MAX_INNER];
 };
 
 struct ChainLaunch {

@@ -19,7 +19,8 @@ int chain_debug_stamps(long long* out16);
 int proj_debug_stamps(long long* out16);
 int fusion_bf16_train(const Layout& L, const msf_fusion_call* c, const int64_t* labels, float smoothing,
                       float grad_scale, float* row_loss, float* loss_out, int flags, cudaStream_t st);
-int fusion_bf16_infer(const Layout& L, const msf_fusion_call* c, float* conf, int64_t* pred, cudaStream_t st);
+int fusion_bf16_infer(const Layout& L, const msf_fusion_call* c, float* conf, int64_t* pred, unsigned present_hint,
+                      cudaStream_t st);
 
 static int check_call(const Layout& L, const msf_fusion_call* c, bool backward) {
   MSF_REQUIRE(c != nullptr, "null call");
@@ -130,14 +131,15 @@ int msf_fusion_train_pass(const msf_fusion_shape* shape, const msf_fusion_call* 
 }
 
 int msf_fusion_infer_pass(const msf_fusion_shape* shape, const msf_fusion_call* call, float* conf, int64_t* pred,
-                          void* stream) {
+                          uint32_t present_hint, void* stream) {
   msf::Layout L;
   int rc = msf::make_layout(shape, &L);
   if (rc) return rc;
   if ((rc = msf::check_call(L, call, false))) return rc;
   MSF_REQUIRE(conf && pred, "msf_fusion_infer_pass: conf and pred are required");
+  MSF_REQUIRE(present_hint < (1u << L.M), "msf_fusion_infer_pass: present_hint has bits beyond the modalities");
   if (call->precision == MSF_PREC_BF16 && msf::fusion_bf16_head_fused(L))
-    return msf::fusion_bf16_infer(L, call, conf, pred, (cudaStream_t)stream);
+    return msf::fusion_bf16_infer(L, call, conf, pred, present_hint, (cudaStream_t)stream);
   if ((rc = msf_fusion_forward(shape, call, stream))) return rc;
   return msf_softmax_conf_pred(call->logits, call->batch, L.C, conf, pred, stream);
 }

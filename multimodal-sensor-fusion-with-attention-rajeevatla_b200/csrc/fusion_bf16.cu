@@ -573,8 +573,12 @@ static int check_ws(const WsBf16& ws, const msf_fusion_call* c) {
 }
 
 // F0..F3: inputs -> aggregated modality tokens (ws.agg), gates in ws.G
+// present_hint: 0 = the mask varies per row; otherwise bit m says whether modality m is present in EVERY row
+// (absent in every row if clear) — the subset sweep of src/eval.py:342-404.  Work for absent modalities is
+// skipped: their projections, the chain items of absent queries (aggregated = 0 through the row mask) and the
+// GEMMs of pairs with an absent key (gate 0: they contribute exactly their out_proj bias).
 static int forward_front(const Layout& L, const msf_fusion_call* c, const WsBf16& ws, const ArenaBf16& A,
-                         cudaStream_t st, const ZeroList* zero = nullptr) {
+                         cudaStream_t st, const ZeroList* zero = nullptr, unsigned present_hint = 0u) {
   const int64_t B = c->batch;
   const int M = L.M, H = L.H;
   int rc = MSF_OK;
@@ -600,6 +604,7 @@ static int forward_front(const Layout& L, const msf_fusion_call* c, const WsBf16
     if ((rc = tc_encode_map(&pl.map_p, ws.P, B, H, H, M, BH, 64, 128))) return rc;
     pl.mask = c->mask;
     pl.drop = drop;
+    if (present_hint != 0u) pl.skip_bits = ~present_hint & ((1u << M) - 1u);
     if (zero != nullptr && zero->n > 0) {
       MSF_REQUIRE(zero->n <= PROJ_MAX_ZERO, "too many gradient ranges to clear");
       for (int i = 0; i < zero->n; ++i) {
@@ -666,13 +671,18 @@ static int forward_front(const Layout& L, const msf_fusion_call* c, const WsBf16
     if ((rc = tc_encode_map(&C.map_out, ws.agg, B, H, H, M, BH, 64, 128))) return rc;
     for (int q = 0; q < M; ++q) {
       ChainOuter& O = C.outer[q];
+      const bool q_absent = present_hint != 0u && !((present_hint >> q) & 1u);
       for (int k = 0; k < M; ++k) {
-        if (q == k || !L.has_pair(q, k)) continue;
+        if (q == k || !L.has_pair(q, k) || q_absent) continue;
         const int pi = L.pair_index(q, k);
-        O.inner[O.n] = (short)k; O.pair[O.n] = (short)pi; O.sub[O.n] = (short)(q * M + k); O.mask_col[O.n] = (short)k;
-        ++O.n;
         C.bias1[pi] = W + L.pair_b(pi, 2);
         C.bias2[pi] = W + L.pair_b(pi, 3);
+        if (present_hint != 0u && !((present_hint >> k) & 1u)) {   // absent key: bias only
+          O.bias_only[O.nb++] = (short)pi;
+          continue;
+        }
+        O.inner[O.n] = (short)k; O.pair[O.n] = (short)pi; O.sub[O.n] = (short)(q * M + k); O.mask_col[O.n] = (short)k;
+        ++O.n;
       }
       C.inv_cnt[q] = 1.0f / (float)L.mean_count(q);
     }
@@ -1150,14 +1160,17 @@ int fusion_bf16_train(const Layout& L, const msf_fusion_call* c, const int64_t* 
 }
 
 // Inference pass: logits plus softmax -> (confidence, prediction) from the head kernel's epilogue.
-int fusion_bf16_infer(const Layout& L, const msf_fusion_call* c, float* conf, int64_t* pred, cudaStream_t st) {
+int fusion_bf16_infer(const Layout& L, const msf_fusion_call* c, float* conf, int64_t* pred, unsigned present_hint,
+                      cudaStream_t st) {
   WsBf16 ws;
   carve_bf16(L, c->batch, c->workspace, &ws);
   int rc = check_ws(ws, c);
   if (rc) return rc;
   MSF_REQUIRE(use_head(L), "fused inference pass not available for this shape");
+  MSF_REQUIRE(present_hint == 0u || (c->attn_gates == nullptr && c->mask != nullptr && chain_eligible(L.H, L.M)),
+              "a uniform-mask hint needs a mask, no attention-gate export and the chained pair kernel");
   const ArenaBf16 A = arena_layout(L);
-  if ((rc = forward_front(L, c, ws, A, st))) return rc;
+  if ((rc = forward_front(L, c, ws, A, st, nullptr, present_hint))) return rc;
   HeadLaunch hl;
   memset(&hl, 0, sizeof(hl));
   hl.train = 0; hl.store_acts = 0;

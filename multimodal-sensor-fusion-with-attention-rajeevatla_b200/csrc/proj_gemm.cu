@@ -95,9 +95,11 @@ __global__ void __launch_bounds__(PJ_THREADS, 1) proj_kernel(const __grid_consta
     // =========================== TMA producer ===========================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int item = blockIdx.x; item < L.items; item += gridDim.x, ++it) {
+      for (int item = blockIdx.x; item < L.items; item += gridDim.x) {
         const int m = item % M, KB = L.D[m] >> 6, m0 = (item / M) * 128;
-        if (it > 0) mbar_wait(tile_done, (it - 1) & 1u);   // the staging tile in the weight area has been stored
+        if ((L.skip_bits >> m) & 1u) continue;
+        const uint32_t it_cur = it++;
+        if (it_cur > 0) mbar_wait(tile_done, (it_cur - 1) & 1u);   // the staging tile in the weight area has been stored
         if (staged) {   // the tile's fp32 rows are contiguous in global memory: one bulk copy
           const int nrows = (L.rows - m0) < 128 ? (L.rows - m0) : 128;
           const uint32_t bytes = (uint32_t)nrows * (uint32_t)L.D[m] * 4u;
@@ -115,10 +117,12 @@ __global__ void __launch_bounds__(PJ_THREADS, 1) proj_kernel(const __grid_consta
     if (lane == 0) {
       const uint32_t idesc = instr_desc(H, false, false);
       uint32_t it = 0;
-      for (int item = blockIdx.x; item < L.items; item += gridDim.x, ++it) {
+      for (int item = blockIdx.x; item < L.items; item += gridDim.x) {
         const int KB = L.D[item % M] >> 6;
-        mbar_wait(w_full, it & 1u);
-        mbar_wait(a_ready, it & 1u);
+        if ((L.skip_bits >> (item % M)) & 1u) continue;
+        const uint32_t it_cur = it++;
+        mbar_wait(w_full, it_cur & 1u);
+        mbar_wait(a_ready, it_cur & 1u);
         tc_fence_after();
         for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
@@ -132,12 +136,14 @@ __global__ void __launch_bounds__(PJ_THREADS, 1) proj_kernel(const __grid_consta
     // =========================== TMA store ==============================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int item = blockIdx.x; item < L.items; item += gridDim.x, ++it) {
+      for (int item = blockIdx.x; item < L.items; item += gridDim.x) {
         const int m = item % M, m0 = (item / M) * 128, KB = L.D[m] >> 6;
-        mbar_wait(a_ready, it & 1u);
+        if ((L.skip_bits >> m) & 1u) continue;
+        const uint32_t it_cur = it++;
+        mbar_wait(a_ready, it_cur & 1u);
         for (int kb = 0; kb < KB; ++kb) tma_store_3d(&L.map_xt[m], a_base + kb * PJ_A_BYTES, kb * 64, m0, 0);
         tma_store_commit();
-        mbar_wait(out_ready, it & 1u);
+        mbar_wait(out_ready, it_cur & 1u);
         for (int kb = 0; kb < KBO; ++kb) tma_store_3d(&L.map_p, w_base + kb * PJ_A_BYTES, kb * 64, m0, m);
         tma_store_commit();
         tma_store_wait_read();
@@ -165,9 +171,11 @@ __global__ void __launch_bounds__(PJ_THREADS, 1) proj_kernel(const __grid_consta
         }
     }
 
-    uint32_t it = 0;
-    for (int item = blockIdx.x; item < L.items; item += gridDim.x, ++it) {
+    uint32_t it_next = 0;
+    for (int item = blockIdx.x; item < L.items; item += gridDim.x) {
       const int m = item % M, m0 = (item / M) * 128, D = L.D[m], c8n = D >> 3;
+      if ((L.skip_bits >> m) & 1u) continue;
+      const uint32_t it = it_next++;
       if (it > 0) mbar_wait(tile_done, (it - 1) & 1u);   // previous tile's A block / staging / bias row are free
       for (int e = et; e < H; e += 32 * PJ_WORKERS) bias_s[e] = L.bias[m] ? __ldg(L.bias[m] + e) : 0.0f;
       if (et < 128) mask_s[et] = (L.mask && (long long)m0 + et < L.rows) ? __ldg(L.mask + ((long long)m0 + et) * M + m) : 1.0f;

@@ -103,6 +103,8 @@ class FusionEngine:
         self._train_graphs = [None, None]
         self._loss_ptr = {}          # slot -> where that slot's graph writes the mean loss (default: self.loss)
         self._infer_graph = None
+        self._subset_graphs = {}
+        self._subset_masks = {}
         self._copy_stream = None
         self.launches_per_step = 0
 
@@ -220,11 +222,11 @@ class FusionEngine:
         a grouped call over the live spans only was measured slower (335 vs 318 us/step at 2 GPUs)."""
         torch.distributed.all_reduce(self.grad, group=self.pg)
 
-    def _enqueue_inference(self) -> None:
+    def _enqueue_inference(self, present_hint: int = 0) -> None:
         c = self._call(False)
         c.logits = self.logits.data_ptr()
         N.check(N.lib().msf_fusion_infer_pass(ctypes_ref(self.plan.shape), ctypes_ref(c), self.conf.data_ptr(),
-                                              self.pred.data_ptr(), ops._stream()))
+                                              self.pred.data_ptr(), present_hint, ops._stream()))
 
     def _capture(self, fn):
         if not self.use_graph:
@@ -417,6 +419,33 @@ class FusionEngine:
     def infer(self, features, mask):
         self.load_batch(features, mask)
         return self.infer_resident()
+
+    def infer_subset(self, features, present: Sequence[int]):
+        """Inference with only the modalities `present` (indices into plan.names) available for the WHOLE batch:
+        the missing-modality sweep of src/eval.py:342-404.  Same result as `infer` with the corresponding
+        uniform mask; the work of the absent modalities is skipped (msf_fusion_infer_pass present_hint).
+        `features=None` keeps the features already in the static buffers (a sweep over the same batch)."""
+        bits = 0
+        for m in present:
+            bits |= 1 << int(m)
+        if bits == 0 or bits >= (1 << self.plan.M):
+            raise ValueError("present must name at least one valid modality")
+        mask = self._subset_masks.get(bits)
+        if mask is None:
+            mask = torch.zeros(self.batch, self.plan.M, dtype=torch.float32, device=self.dev)
+            mask[:, [int(m) for m in present]] = 1.0
+            self._subset_masks[bits] = mask
+        if features is None:
+            self.mask.copy_(mask, non_blocking=True)
+        else:
+            self.load_batch(features, mask)
+        if not self.use_graph or self.prec != N.MSF_PREC_BF16:
+            self._enqueue_inference(bits if self.prec == N.MSF_PREC_BF16 else 0)
+        else:
+            if bits not in self._subset_graphs:
+                self._subset_graphs[bits] = self._capture(lambda: self._enqueue_inference(bits))
+            self._subset_graphs[bits].replay()
+        return self.logits, self.conf, self.pred
 
     def ece_bins(self, labels: torch.Tensor, edges: Sequence[float], out=None) -> torch.Tensor:
         """Shard-local binning of the last inference, then one integer all-reduce

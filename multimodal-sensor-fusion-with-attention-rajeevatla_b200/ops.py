@@ -242,8 +242,10 @@ def fusion_train_pass_raw(plan: FusionPlan, arena: torch.Tensor, xs: Sequence[to
 
 def fusion_infer_pass_raw(plan: FusionPlan, arena: torch.Tensor, xs: Sequence[torch.Tensor],
                           mask: Optional[torch.Tensor], *, precision: int = N.MSF_PREC_F32,
-                          arena_bf16: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None):
-    """One msf_fusion_infer_pass call: ``(logits, conf, pred)`` (src/eval.py:84-90)."""
+                          arena_bf16: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None,
+                          present_hint: int = 0):
+    """One msf_fusion_infer_pass call: ``(logits, conf, pred)`` (src/eval.py:84-90).  ``present_hint``: bit set
+    of the modalities a batch-uniform mask marks present (0 = no hint)."""
     dev = arena.device
     B = xs[0].shape[0]
     if workspace is None:
@@ -254,7 +256,7 @@ def fusion_infer_pass_raw(plan: FusionPlan, arena: torch.Tensor, xs: Sequence[to
     call = _make_call(plan, B, precision, False, 0.0, 0, 0, arena, arena_bf16, xs, mask, workspace)
     call.logits = _p(logits)
     N.check(N.lib().msf_fusion_infer_pass(ctypes.byref(plan.shape), ctypes.byref(call), _p(conf), _p(pred),
-                                          _stream()))
+                                          int(present_hint), _stream()))
     return logits, conf, pred
 
 

@@ -130,3 +130,28 @@ def test_small_shapes_and_missing_pairs():
             got, ref = _slot(plan, grad, key).cpu(), sd[key].grad
             ref = torch.zeros_like(got) if ref is None else ref
             assert float((got - ref).abs().max()) <= 1e-2, (hidden, key)
+
+
+def test_uniform_mask_hint_equals_dense_path():
+    """The 15 missing-modality subsets of src/eval.py:342-348 through msf_fusion_infer_pass with the
+    present_hint (absent modalities' projections / pair GEMMs / query rows skipped) against the same pass
+    without it: identical predictions, logits equal up to the order of the bias sums."""
+    import itertools
+    ops, N, model, plan, arena, arena16, xs, mask, labels = _setup(700, seed=17)
+    M = plan.M
+    for r in range(1, M + 1):
+        for sub in itertools.combinations(range(M), r):
+            m = torch.zeros(700, M, device="cuda")
+            m[:, list(sub)] = 1.0
+            bits = sum(1 << i for i in sub)
+            kw = dict(precision=N.MSF_PREC_BF16, arena_bf16=arena16)
+            # a poisoned workspace: skipped buffers must never leak into the result
+            ws = torch.full((plan.workspace_bytes(700, N.MSF_PREC_BF16),), 0xFF, dtype=torch.uint8, device="cuda")
+            l_hint, c_hint, p_hint = ops.fusion_infer_pass_raw(plan, arena, xs, m, present_hint=bits, workspace=ws, **kw)
+            l_ref, c_ref, p_ref = ops.fusion_infer_pass_raw(plan, arena, xs, m, **kw)
+            assert torch.isfinite(l_hint).all(), sub
+            assert float((l_hint - l_ref).abs().max()) <= 1e-5, sub
+            assert torch.equal(p_hint, p_ref), sub
+            assert float((c_hint - c_ref).abs().max()) <= 1e-6, sub
+    with pytest.raises(Exception):
+        ops.fusion_infer_pass_raw(plan, arena, xs, mask, present_hint=1 << M, precision=N.MSF_PREC_BF16, arena_bf16=arena16)
