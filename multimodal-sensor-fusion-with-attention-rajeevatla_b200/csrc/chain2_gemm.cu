@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       };
       for (int item = blockIdx.x; item < L.items; item += gridDim.x) {
-        const int o = item % M, m0 = (item / M) * 128;
+        const int o = L.active[item % L.n_active], m0 = (item / L.n_active) * 128;
         const int nh = 2 * L.outer[o].n;
         auto load_g1 = [&](int h) {
           const int i = h >> 1, b = h & 1;
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       };
       for (int item = blockIdx.x; item < L.items; item += gridDim.x, ++item_cnt) {
-        const int nh = 2 * L.outer[item % M].n;
+        const int nh = 2 * L.outer[L.active[item % L.n_active]].n;
         mbar_wait(acc_empty, (item_cnt & 1u) ^ 1u);
         tc_fence_after();
         auto g1 = [&](int h) {   // T[b] = A1 . W1half^T
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
     if (lane == 0) {
       uint32_t u_uses[2] = {0u, 0u}, item_cnt = 0;
       for (int item = blockIdx.x; item < L.items; item += gridDim.x, ++item_cnt) {
-        const int o = item % M, m0 = (item / M) * 128;
+        const int o = L.active[item % L.n_active], m0 = (item / L.n_active) * 128;
         const int nh = 2 * L.outer[o].n;
         for (int h = 0; h < nh; ++h) {
           const int b = h & 1;
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
     const int hc_begin = cg * (HW >> 1), hc_end = hc_begin + (HW >> 1);   // this thread's columns inside a half
     uint32_t t_uses[2] = {0u, 0u}, f_uses[2] = {0u, 0u}, item_cnt = 0;
     for (int item = blockIdx.x; item < L.items; item += gridDim.x, ++item_cnt) {
-      const int o = item % M, m0 = (item / M) * 128;
+      const int o = L.active[item % L.n_active], m0 = (item / L.n_active) * 128;
       const int n = L.outer[o].n, nh = 2 * n;
       const long long row = (long long)m0 + trow;
       const bool row_ok = row < L.rows;
@@ -470,7 +470,11 @@ int chain2_launch(ChainLaunch& L, cudaStream_t stream, const char* label) {
   MSF_REQUIRE(chain2_eligible(L.H, L.M), "chain2_gemm: hidden %d / modalities %d not supported", L.H, L.M);
   MSF_REQUIRE(L.rows >= 1, "chain2_gemm: empty batch");
   L.row_tiles = (int)ceil_div(L.rows, 128);
-  L.items = L.row_tiles * L.M;
+  if (L.n_active <= 0) {   // default: every modality is an outer modality
+    L.n_active = L.M;
+    for (int m = 0; m < L.M; ++m) L.active[m] = (short)m;
+  }
+  L.items = L.row_tiles * L.n_active;
   const size_t g1_stage = C2_A_BYTES + (size_t)(L.H / 2) * 128, g2_stage = (size_t)L.H * 128;
   const size_t stage = g1_stage > g2_stage ? g1_stage : g2_stage;
   const size_t ublocks = (size_t)(L.H / 64) * C2_A_BYTES;

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < L.items; item += gridDim.x) {
-        const int o = item % M, m0 = (item / M) * 128;
+        const int o = L.active[item % L.n_active], m0 = (item / L.n_active) * 128;
         const int n = L.outer[o].n;
         for (int i = 0; i < n; ++i) {
           const int zin = L.outer[o].inner[i], zp = L.outer[o].pair[i];
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
       int stage = 0;
       uint32_t phase = 0, u_cnt = 0, item_cnt = 0;
       for (int item = blockIdx.x; item < L.items; item += gridDim.x, ++item_cnt) {
-        const int n = L.outer[item % M].n;
+        const int n = L.outer[L.active[item % L.n_active]].n;
         mbar_wait(acc_empty, (item_cnt & 1u) ^ 1u);
         tc_fence_after();
         for (int i = 0; i < n; ++i, ++u_cnt) {
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
     if (lane == 0) {
       uint32_t u_cnt = 0, item_cnt = 0;
       for (int item = blockIdx.x; item < L.items; item += gridDim.x, ++item_cnt) {
-        const int o = item % M, m0 = (item / M) * 128;
+        const int o = L.active[item % L.n_active], m0 = (item / L.n_active) * 128;
         const int n = L.outer[o].n;
         for (int i = 0; i < n; ++i, ++u_cnt) {
           mbar_wait(us_ready, u_cnt & 1u);
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
     const uint32_t lane_base = (uint32_t)(lq * 32) << 16;
     uint32_t u_cnt = 0, us_uses = 0, item_cnt = 0;
     for (int item = blockIdx.x; item < L.items; item += gridDim.x, ++item_cnt) {
-      const int o = item % M, m0 = (item / M) * 128;
+      const int o = L.active[item % L.n_active], m0 = (item / L.n_active) * 128;
       const int n = L.outer[o].n;
       const long long row = (long long)m0 + trow;
       const bool row_ok = row < L.rows;
@@ -403,7 +403,11 @@ int chain_launch(ChainLaunch& L, cudaStream_t stream, const char* label) {
   MSF_REQUIRE(L.rows >= 1, "chain_gemm: empty batch");
   if (use_chain2(L.H, L.M)) return chain2_launch(L, stream, label);
   L.row_tiles = (int)ceil_div(L.rows, 128);
-  L.items = L.row_tiles * L.M;
+  if (L.n_active <= 0) {   // default: every modality is an outer modality
+    L.n_active = L.M;
+    for (int m = 0; m < L.M; ++m) L.active[m] = (short)m;
+  }
+  L.items = L.row_tiles * L.n_active;
   const size_t per_stage = CH_A_BYTES + ch_b_bytes(L.H);
   const size_t ublock = (size_t)(L.H / 64) * CH_A_BYTES;
   int stages = (int)((CH_SMEM_LIMIT - chain_fixed_smem() - ublock) / per_stage);

@@ -39,6 +39,8 @@ struct ChainLaunch {
   int mode;            // 0 forward, 1 backward
   int M, H, heads, head_dim;
   int rows, row_tiles, items;
+  int n_active;                    // outer modalities that get items (0: all M); absent queries of a uniform-mask
+  short active[MSF_MAX_MODALITIES];  // inference pass are left out: the head never reads their aggregated token
   int store1;          // write epilogue1's result to global memory (needed by the backward pass)
   int stages;
   ChainOuter outer[MSF_MAX_MODALITIES];

@@ -604,7 +604,9 @@ static int forward_front(const Layout& L, const msf_fusion_call* c, const WsBf16
     if ((rc = tc_encode_map(&pl.map_p, ws.P, B, H, H, M, BH, 64, 128))) return rc;
     pl.mask = c->mask;
     pl.drop = drop;
-    if (present_hint != 0u) pl.skip_bits = ~present_hint & ((1u << M) - 1u);
+    if (present_hint != 0u)
+      for (int m = 0; m < M; ++m)
+        if ((present_hint >> m) & 1u) pl.active[pl.n_active++] = (short)m;
     if (zero != nullptr && zero->n > 0) {
       MSF_REQUIRE(zero->n <= PROJ_MAX_ZERO, "too many gradient ranges to clear");
       for (int i = 0; i < zero->n; ++i) {
@@ -685,6 +687,7 @@ static int forward_front(const Layout& L, const msf_fusion_call* c, const WsBf16
         ++O.n;
       }
       C.inv_cnt[q] = 1.0f / (float)L.mean_count(q);
+      if (present_hint != 0u && !q_absent) C.active[C.n_active++] = (short)q;   // absent queries get no items at all
     }
     C.gate_out = ws.G; C.mask = c->mask; C.aux = ws.P; C.drop = drop;
     if ((rc = chain_launch(C, st, "F2+F3 value->out chain"))) return rc;

@@ -205,8 +205,10 @@ __device__ __forceinline__ void head_p0(const HeadLaunch& L, const HeadSmem& S, 
       const float wb = __shfl_sync(0xffffffffu, w, 8 * q);
       float v[8];
       unpack8(raw[q], v);
+      if (wb != 0.0f) {   // weight 0 <=> masked token: exactly 0 in the reference, possibly never written here
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = fmaf(v[j], wb, f[j]);  // fusion.py:416-418
+        for (int j = 0; j < 8; ++j) f[j] = fmaf(v[j], wb, f[j]);  // fusion.py:416-418
+      }
     }
     // padding rows of the last tile stay zero
     if (c_ok) *reinterpret_cast<uint4*>(S.ublk + swz_off(r, c)) = row_ok ? pack8(f) : make_uint4(0u, 0u, 0u, 0u);

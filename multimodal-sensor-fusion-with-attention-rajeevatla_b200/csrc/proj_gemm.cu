@@ -96,8 +96,7 @@ __global__ void __launch_bounds__(PJ_THREADS, 1) proj_kernel(const __grid_consta
     if (lane == 0) {
       uint32_t it = 0;
       for (int item = blockIdx.x; item < L.items; item += gridDim.x) {
-        const int m = item % M, KB = L.D[m] >> 6, m0 = (item / M) * 128;
-        if ((L.skip_bits >> m) & 1u) continue;
+        const int m = L.active[item % L.n_active], KB = L.D[m] >> 6, m0 = (item / L.n_active) * 128;
         const uint32_t it_cur = it++;
         if (it_cur > 0) mbar_wait(tile_done, (it_cur - 1) & 1u);   // the staging tile in the weight area has been stored
         if (staged) {   // the tile's fp32 rows are contiguous in global memory: one bulk copy
@@ -118,8 +117,7 @@ __global__ void __launch_bounds__(PJ_THREADS, 1) proj_kernel(const __grid_consta
       const uint32_t idesc = instr_desc(H, false, false);
       uint32_t it = 0;
       for (int item = blockIdx.x; item < L.items; item += gridDim.x) {
-        const int KB = L.D[item % M] >> 6;
-        if ((L.skip_bits >> (item % M)) & 1u) continue;
+        const int KB = L.D[L.active[item % L.n_active]] >> 6;
         const uint32_t it_cur = it++;
         mbar_wait(w_full, it_cur & 1u);
         mbar_wait(a_ready, it_cur & 1u);
@@ -137,8 +135,7 @@ __global__ void __launch_bounds__(PJ_THREADS, 1) proj_kernel(const __grid_consta
     if (lane == 0) {
       uint32_t it = 0;
       for (int item = blockIdx.x; item < L.items; item += gridDim.x) {
-        const int m = item % M, m0 = (item / M) * 128, KB = L.D[m] >> 6;
-        if ((L.skip_bits >> m) & 1u) continue;
+        const int m = L.active[item % L.n_active], m0 = (item / L.n_active) * 128, KB = L.D[m] >> 6;
         const uint32_t it_cur = it++;
         mbar_wait(a_ready, it_cur & 1u);
         for (int kb = 0; kb < KB; ++kb) tma_store_3d(&L.map_xt[m], a_base + kb * PJ_A_BYTES, kb * 64, m0, 0);
@@ -173,8 +170,7 @@ __global__ void __launch_bounds__(PJ_THREADS, 1) proj_kernel(const __grid_consta
 
     uint32_t it_next = 0;
     for (int item = blockIdx.x; item < L.items; item += gridDim.x) {
-      const int m = item % M, m0 = (item / M) * 128, D = L.D[m], c8n = D >> 3;
-      if ((L.skip_bits >> m) & 1u) continue;
+      const int m = L.active[item % L.n_active], m0 = (item / L.n_active) * 128, D = L.D[m], c8n = D >> 3;
       const uint32_t it = it_next++;
       if (it > 0) mbar_wait(tile_done, (it - 1) & 1u);   // previous tile's A block / staging / bias row are free
       for (int e = et; e < H; e += 32 * PJ_WORKERS) bias_s[e] = L.bias[m] ? __ldg(L.bias[m] + e) : 0.0f;
@@ -289,7 +285,11 @@ int proj_launch(ProjLaunch& L, cudaStream_t stream, const char* label) {
   MSF_REQUIRE(proj_eligible(L.H, L.M, L.D), "proj_gemm: shape not supported");
   MSF_REQUIRE(L.rows >= 1, "proj_gemm: empty batch");
   L.row_tiles = (int)ceil_div(L.rows, 128);
-  L.items = L.row_tiles * L.M;
+  if (L.n_active <= 0) {
+    L.n_active = L.M;
+    for (int m = 0; m < L.M; ++m) L.active[m] = (short)m;
+  }
+  L.items = L.row_tiles * L.n_active;
   int max_d = 64;
   for (int m = 0; m < L.M; ++m) max_d = L.D[m] > max_d ? L.D[m] : max_d;
   const int max_kb = max_d / 64;

@@ -29,7 +29,8 @@ struct ProjLaunch {
   int D[MSF_MAX_MODALITIES];
   const float* x[MSF_MAX_MODALITIES];       // (rows, D_m) fp32
   const float* bias[MSF_MAX_MODALITIES];    // (H)
-  unsigned skip_bits;                       // bit m: modality m is absent in every row -> its items are skipped
+  int n_active;                             // modalities that get items (0: all M); absent ones of a uniform-mask
+  short active[MSF_MAX_MODALITIES];         // inference pass are left out
   const float* mask;                        // (rows, M) or nullptr
   DropCfg drop;
   // gradient slots to clear at the start of a train pass (first kernel of the step); see fusion_bf16.cu
