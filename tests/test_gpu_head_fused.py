@@ -155,3 +155,48 @@ def test_uniform_mask_hint_equals_dense_path():
             assert float((c_hint - c_ref).abs().max()) <= 1e-6, sub
     with pytest.raises(Exception):
         ops.fusion_infer_pass_raw(plan, arena, xs, mask, present_hint=1 << M, precision=N.MSF_PREC_BF16, arena_bf16=arena16)
+
+
+def test_128_window_tiles_train_pass(monkeypatch):
+    """Large batches use 128-window head tiles; MSF_HEAD_TILE128 forces that path at a test-sized batch
+    (several tiles per launch incl. a ragged last one) and compares it with the un-fused sequence."""
+    ops, N, model, plan, arena, arena16, xs, mask, labels = _setup(1000, seed=23)
+    kw = dict(precision=N.MSF_PREC_BF16, training=True, p=0.1, seed=5, offset=9, arena_bf16=arena16)
+    monkeypatch.setenv("MSF_HEAD_TILE128", "1")
+    logits, loss, grad, fw, gates = ops.fusion_train_pass_raw(plan, arena, xs, mask, labels, smoothing=0.05, **kw)
+    monkeypatch.delenv("MSF_HEAD_TILE128")
+    monkeypatch.setenv("MSF_NO_HEAD", "1")
+    l2, fw2, g2, ws = ops.fusion_forward_raw(plan, arena, xs, mask, **kw)
+    loss2, dl = ops.cross_entropy(l2, labels, 0.05)
+    grad2, _ = ops.fusion_backward_raw(plan, arena, xs, mask, ws, dl, **kw)
+    monkeypatch.delenv("MSF_NO_HEAD")
+    assert float((logits - l2).abs().max()) <= 5e-4
+    assert float((fw - fw2).abs().max()) <= 5e-6
+    assert abs(float(loss) - float(loss2)) <= 1e-4
+    scale = float(grad2.abs().max())
+    assert float((grad - grad2).abs().max()) <= 2e-3 * scale + 1e-7
+    assert float((grad - grad2).norm()) <= 2e-2 * float(grad2.norm())
+
+
+def test_projection_kernel_input_widths():
+    """proj_kernel over in_dims of 64 / 192 / 256 columns (1, 3 and 4 k-blocks; the 256-wide tile is read
+    directly instead of through the bulk-copy staging) against the CPU oracle."""
+    ops, N = _mods()
+    dims = {"a": 64, "b": 256, "c": 192}
+    model, feats, mask, labels = seeded_case(dims, 128, 4, 7, 333, seed=29, device="cuda")
+    plan = model._plan()
+    own = dict(model.named_parameters())
+    arena = plan.gather([own[k].detach() for k, _, _ in plan.slots])
+    xs = [feats[m].contiguous() for m in plan.names]
+    logits, loss, grad, fw, gates = ops.fusion_train_pass_raw(
+        plan, arena, xs, mask, labels, smoothing=0.05, precision=N.MSF_PREC_BF16, training=False, p=0.0,
+        arena_bf16=plan.pack_bf16(arena))
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    xo = {m: x.cpu() for m, x in zip(plan.names, xs)}
+    ref_logits, _ = fusion_oracle.hybrid_fusion_forward(sd, model.modality_names, 4, xo, mask.cpu())
+    ref_loss = fusion_oracle.cross_entropy_label_smoothing(ref_logits, labels.cpu(), 0.05)
+    ref_loss.backward()
+    assert float((logits.cpu() - ref_logits.detach()).abs().max()) <= 1e-2
+    for key, _, _ in plan.slots:
+        got, ref = _slot(plan, grad, key).cpu(), sd[key].grad
+        assert float((got - ref).abs().max()) <= 1e-2, key
