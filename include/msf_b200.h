@@ -157,6 +157,9 @@ int msf_fusion_infer_pass(const msf_fusion_shape* shape, const msf_fusion_call* 
 int msf_debug_head_stamps(int64_t* out16);
 /* Same for the last chained pair-GEMM launch: wait-time accounting of CTA 0 (see chain2_gemm.cu). */
 int msf_debug_chain_stamps(int64_t* out16);
+/* cta_group::2 probe (pair_gemm.cu): D[m, 256] = A[m, k] . B[256, k]^T, bf16 operands, fp32 D, one CTA pair per
+ * 256 rows.  Building block of the round-2 kernels; not used by the product path. */
+int msf_debug_pair_gemm(const void* a_bf16, const void* b_bf16, float* d, int64_t m, int64_t k, void* stream);
 /* Phase stamps of CTA 0 of the last input-projection launch (proj_gemm.cu). */
 int msf_debug_proj_stamps(int64_t* out16);
 /* HybridFusion.compute_adaptive_weights (src/fusion.py:429-479) stand-alone:
