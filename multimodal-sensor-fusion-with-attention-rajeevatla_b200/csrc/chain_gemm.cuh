@@ -60,6 +60,8 @@ bool chain_eligible(int H, int M);
 // Box height of map_w1 (rows of W1 one TMA load brings in): H for chain_kernel, H/2 for the
 // half-pair-pipelined chain2_kernel that chain_launch picks when hidden % 128 == 0.
 int chain_w1_box_rows(int H, int M);
+// Box height of map_w2: H, or H/2 for the CTA-pair kernel (each CTA of a pair stages half of every weight block).
+int chain_w2_box_rows(int H, int M);
 // Fills stages / items / row_tiles and launches.  Tensor maps must already be encoded (tc_encode_map).
 int chain_launch(ChainLaunch& L, cudaStream_t stream, const char* label);
 

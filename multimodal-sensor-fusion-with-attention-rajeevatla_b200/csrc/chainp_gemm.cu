@@ -1,14 +1,14 @@
-// chain_kernel: see chain_gemm.cuh.  One persistent CTA per SM, 12 warps:
+// chainp_kernel: the chained pair GEMMs of chain_gemm.cuh on CTA PAIRS (tcgen05 cta_group::2, hidden % 128 == 0).
 //
-//   warp 0 (one lane)  TMA producer : A1 / W1 k-blocks for GEMM1, then W2 k-blocks for GEMM2, through a smem ring
-//   warp 1 (one lane)  MMA issuer   : GEMM1 -> TMEM cols [0,H), GEMM2 (A = the staged intermediate) -> TMEM cols [H,2H)
-//   warp 2             TMEM allocator
-//   warp 3 (one lane)  TMA store    : intermediate / final tiles from the swizzled smem block to global memory
-//   warps 4..11        epilogue     : thread = accumulator row; tcgen05.ld, math, bf16, 128B-swizzled st.shared
-//
-// The smem block the epilogue writes is at once the K-major A operand of GEMM2 (read by tcgen05.mma
-// through a shared-memory descriptor) and the source box of the TMA store, so the intermediate is
-// produced exactly once.  All mbarrier waits are bounded (trap instead of hanging the GPU).
+// A cluster of two CTAs takes two consecutive 128-window tiles of one outer modality.  Each CTA stages its own A tile
+// and HALF of every weight block (H/2 of its H rows); the leader CTA issues tcgen05.mma.cta_group::2 (M = 256 over the
+// pair), which reads the B halves from both CTAs' shared memory — per SM the operand traffic through shared memory
+// drops from (128 + H)·32 B to (128 + H/2)·32 B per k-step, which is what bounds the single-CTA kernels
+// (profiles/README.md).  Everything else is chain_kernel's scheme, per CTA and on its own rows: GEMM1 -> TMEM [0,H),
+// epilogue1 -> bf16 staging block (= A operand of GEMM2 and TMA-store source), GEMM2 -> TMEM [H,2H), final epilogue.
+// Cross-CTA signalling: TMA completion bytes of both CTAs are counted on the leader's "full" barriers, MMA completion
+// is multicast to both CTAs' barriers (tcgen05.commit ... multicast::cluster), and the epilogue warps of both CTAs
+// arrive on the leader's barriers (16 arrivals) before the leader may overwrite TMEM or read the staging blocks.
 #include "chain_gemm.cuh"
 
 #include <stdlib.h>
@@ -20,12 +20,14 @@ namespace msf {
 namespace {
 
 constexpr int CH_THREADS = 384;
+constexpr uint32_t CP_PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address: the pair's leader
 constexpr int CH_EPI_WARPS = 8;
 constexpr int CH_MAX_STAGES = 4;
 constexpr uint32_t CH_A_BYTES = 128 * 64 * 2;  // one K-block of the A operand: 128 rows x 64 bf16
 constexpr size_t CH_SMEM_LIMIT = 232448;
 
-__host__ __device__ constexpr uint32_t ch_b_bytes(int H) { return (uint32_t)H * 64 * 2; }
+// one k-block of a weight HALF: H/2 rows x 64 bf16
+__host__ __device__ constexpr uint32_t ch_b_bytes(int H) { return (uint32_t)(H / 2) * 64 * 2; }
 
 struct Raw16 {
   uint4 lo, hi;
@@ -64,8 +66,51 @@ __device__ __forceinline__ void st_swizzled16(unsigned char* blk, int trow, int 
   }
 }
 
+__device__ __forceinline__ uint32_t cp_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cp_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are counted on the LEADER CTA's mbarrier (issued by both CTAs of the pair)
+__device__ __forceinline__ void cp_tma_load(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar & CP_PEER_MASK)
+      : "memory");
+}
+__device__ __forceinline__ void cp_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// arrive on the same barrier offset in BOTH CTAs once the MMAs issued so far have completed
+__device__ __forceinline__ void cp_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((unsigned short)3)
+               : "memory");
+}
+// arrive on the LEADER CTA's copy of a barrier (from either CTA)
+__device__ __forceinline__ void cp_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & CP_PEER_MASK) : "memory");
+}
+
+// wait-time accounting of cluster 0's leader CTA (clock64 cycles), same slots as chain2_gemm.cu
+__device__ long long g_chainp_stamps[16];
+#define CP_T0() const long long _t0 = clock64()
+#define CP_ACC(i) do { dbg_acc[(i) & 3] += clock64() - _t0; } while (0)
+#define CP_FLUSH(i) do { if (blockIdx.x == 0) g_chainp_stamps[i] = dbg_acc[(i) & 3]; } while (0)
+#define CP_SET(i) do { if (blockIdx.x == 0) g_chainp_stamps[i] = clock64(); } while (0)
+
 template <int MODE>
-__global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_constant__ ChainLaunch L) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1)
+    chainp_kernel(const __grid_constant__ ChainLaunch L) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int H = L.H, KB = L.H >> 6, STAGES = L.stages, M = L.M;
@@ -83,13 +128,17 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
   const uint32_t acc_full = bar_base + 8u * (2 * CH_MAX_STAGES + 4);  // ACC complete (MMA -> epilogue)
   const uint32_t acc_empty = bar_base + 8u * (2 * CH_MAX_STAGES + 5); // ACC drained (epilogue -> MMA)
   const uint32_t out_ready = bar_base + 8u * (2 * CH_MAX_STAGES + 6); // final tile staged (epilogue -> store)
-  const uint32_t tmem_slot = bar_base + 8u * (2 * CH_MAX_STAGES + 7);
+  const uint32_t us_ready_l = bar_base + 8u * (2 * CH_MAX_STAGES + 7); // smem intermediate written, this CTA only (-> its store warp)
+  const uint32_t tmem_slot = bar_base + 8u * (2 * CH_MAX_STAGES + 8);
   const uint32_t off0 = smem_u32(smem_raw);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - off0));
-  float* bias_smem = reinterpret_cast<float*>(smem_raw + (bar_base + 8u * (2 * CH_MAX_STAGES + 8) - off0));  // 3 x 256
+  float* bias_smem = reinterpret_cast<float*>(smem_raw + (bar_base + 8u * (2 * CH_MAX_STAGES + 10) - off0));  // 3 x 256
   unsigned char* u_smem = smem_raw + (u_base - off0);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cp_ctarank();                  // 0 = leader of the pair
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int HW = H >> 1;
   const uint32_t tmem_cols = (2 * H <= 32) ? 32 : (2 * H <= 64) ? 64 : (2 * H <= 128) ? 128 : (2 * H <= 256) ? 256 : 512;
 
   if (warp == 0 && lane == 0) {
@@ -105,47 +154,50 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(u_full, 1);
-    mbar_init(u_empty, CH_EPI_WARPS);
-    mbar_init(us_ready, CH_EPI_WARPS);
+    mbar_init(u_empty, 2 * CH_EPI_WARPS);     // leader: epilogue warps of both CTAs
+    mbar_init(us_ready, 2 * CH_EPI_WARPS);    // leader: epilogue warps of both CTAs
+    mbar_init(us_ready_l, CH_EPI_WARPS);      // local: this CTA's store warp
     mbar_init(us_free, 2);
     mbar_init(acc_full, 1);
-    mbar_init(acc_empty, CH_EPI_WARPS);
+    mbar_init(acc_empty, 2 * CH_EPI_WARPS);   // leader: epilogue warps of both CTAs
     mbar_init(out_ready, CH_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols)
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols)
                  : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  cp_cluster_sync();   // both CTAs' barriers exist before anything is signalled across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   pdl_wait();
   pdl_launch();
+  long long dbg_acc[4] = {0, 0, 0, 0};
+  if (blockIdx.x == 0 && threadIdx.x == 0) g_chainp_stamps[0] = clock64();
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < L.items; item += gridDim.x) {
-        const int o = L.active[item % L.n_active], m0 = (item / L.n_active) * 128;
+      for (int item = cluster_id; item < L.items; item += n_clusters) {
+        const int o = L.active[item % L.n_active], m0 = (item / L.n_active) * 256 + (int)rank * 128;
         const int n = L.outer[o].n;
         for (int i = 0; i < n; ++i) {
           const int zin = L.outer[o].inner[i], zp = L.outer[o].pair[i];
-          for (int kb = 0; kb < KB; ++kb) {  // GEMM1 operands
+          for (int kb = 0; kb < KB; ++kb) {  // GEMM1 operands: own A rows, own half of the W1 rows
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            mbar_expect_tx(full_bar(stage), CH_A_BYTES + B_BYTES);
-            tma_load_3d(a_base + stage * CH_A_BYTES, &L.map_a1, kb * 64, m0, zin, full_bar(stage));
-            tma_load_3d(b_base + stage * B_BYTES, &L.map_w1, kb * 64, 0, zp, full_bar(stage));
+            if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * (CH_A_BYTES + B_BYTES));   // both CTAs' bytes
+            cp_tma_load(a_base + stage * CH_A_BYTES, &L.map_a1, kb * 64, m0, zin, full_bar(stage));
+            cp_tma_load(b_base + stage * B_BYTES, &L.map_w1, kb * 64, (int)rank * HW, zp, full_bar(stage));
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
-          for (int kb = 0; kb < KB; ++kb) {  // GEMM2: only the weights travel, A is already on chip
+          for (int kb = 0; kb < KB; ++kb) {  // GEMM2: only the weight halves travel, A is already on chip
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            mbar_expect_tx(full_bar(stage), B_BYTES);
-            tma_load_3d(b_base + stage * B_BYTES, &L.map_w2, kb * 64, 0, zp, full_bar(stage));
+            if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * B_BYTES);
+            cp_tma_load(b_base + stage * B_BYTES, &L.map_w2, kb * 64, (int)rank * HW, zp, full_bar(stage));
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -153,56 +205,59 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
     }
   } else if (warp == 1) {
     // =========================== MMA issuer =============================
-    if (lane == 0) {
-      const uint32_t idesc = instr_desc(H, false, false);
+    if (lane == 0 && rank == 0) {   // the leader CTA issues the pair's MMAs
+      // bf16 x bf16 -> fp32, K-major, N = H, M = 256 over the pair
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0, u_cnt = 0, item_cnt = 0;
-      for (int item = blockIdx.x; item < L.items; item += gridDim.x, ++item_cnt) {
+      for (int item = cluster_id; item < L.items; item += n_clusters, ++item_cnt) {
         const int n = L.outer[L.active[item % L.n_active]].n;
         mbar_wait(acc_empty, (item_cnt & 1u) ^ 1u);
         tc_fence_after();
         for (int i = 0; i < n; ++i, ++u_cnt) {
-          mbar_wait(u_empty, (u_cnt & 1u) ^ 1u);
+          { CP_T0(); mbar_wait(u_empty, (u_cnt & 1u) ^ 1u); CP_ACC(2); }
           tc_fence_after();
           for (int kb = 0; kb < KB; ++kb) {  // GEMM1 -> TMEM [0, H)
-            mbar_wait(full_bar(stage), phase);
+            { CP_T0(); mbar_wait(full_bar(stage), phase); CP_ACC(1); }
             tc_fence_after();
             const uint32_t a_addr = a_base + stage * CH_A_BYTES, b_addr = b_base + stage * B_BYTES;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              tc_mma_bf16(tmem_base, smem_desc(a_addr + k * 32, 16, 1024), smem_desc(b_addr + k * 32, 16, 1024), idesc,
-                          (kb > 0 || k > 0) ? 1u : 0u);
-            tc_commit(empty_bar(stage));
+              cp_mma(tmem_base, smem_desc(a_addr + k * 32, 16, 1024), smem_desc(b_addr + k * 32, 16, 1024), idesc,
+                     (kb > 0 || k > 0) ? 1u : 0u);
+            cp_commit(empty_bar(stage));
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
-          tc_commit(u_full);
-          mbar_wait(us_ready, u_cnt & 1u);  // the epilogue has staged the bf16 intermediate
+          cp_commit(u_full);
+          { CP_T0(); mbar_wait(us_ready, u_cnt & 1u); CP_ACC(3); }  // the epilogues have staged the bf16 intermediate
           tc_fence_after();
           for (int kb = 0; kb < KB; ++kb) {  // GEMM2 -> TMEM [H, 2H), A from the staged block
-            mbar_wait(full_bar(stage), phase);
+            { CP_T0(); mbar_wait(full_bar(stage), phase); CP_ACC(1); }
             tc_fence_after();
             const uint32_t a_addr = u_base + kb * CH_A_BYTES, b_addr = b_base + stage * B_BYTES;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              tc_mma_bf16(tmem_base + (uint32_t)H, smem_desc(a_addr + k * 32, 16, 1024),
-                          smem_desc(b_addr + k * 32, 16, 1024), idesc, (i > 0 || kb > 0 || k > 0) ? 1u : 0u);
-            tc_commit(empty_bar(stage));
+              cp_mma(tmem_base + (uint32_t)H, smem_desc(a_addr + k * 32, 16, 1024),
+                     smem_desc(b_addr + k * 32, 16, 1024), idesc, (i > 0 || kb > 0 || k > 0) ? 1u : 0u);
+            cp_commit(empty_bar(stage));
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
-          tc_commit(us_free);  // 1 of 2: GEMM2 no longer reads the staged block
+          cp_commit(us_free);  // 1 of 2 (in both CTAs): GEMM2 no longer reads the staged blocks
         }
-        tc_commit(acc_full);
+        cp_commit(acc_full);
       }
+      CP_FLUSH(1); CP_FLUSH(2); CP_FLUSH(3);
+      CP_SET(4);
     }
   } else if (warp == 3) {
     // =========================== TMA store ==============================
     if (lane == 0) {
       uint32_t u_cnt = 0, item_cnt = 0;
-      for (int item = blockIdx.x; item < L.items; item += gridDim.x, ++item_cnt) {
-        const int o = L.active[item % L.n_active], m0 = (item / L.n_active) * 128;
+      for (int item = cluster_id; item < L.items; item += n_clusters, ++item_cnt) {
+        const int o = L.active[item % L.n_active], m0 = (item / L.n_active) * 256 + (int)rank * 128;
         const int n = L.outer[o].n;
         for (int i = 0; i < n; ++i, ++u_cnt) {
-          mbar_wait(us_ready, u_cnt & 1u);
+          mbar_wait(us_ready_l, u_cnt & 1u);
           if (L.store1) {
             for (int kb = 0; kb < KB; ++kb)
               tma_store_3d(&L.map_out1, u_base + kb * CH_A_BYTES, kb * 64, m0, L.outer[o].pair[i]);
@@ -229,8 +284,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
     const int et = threadIdx.x - 128;
     const uint32_t lane_base = (uint32_t)(lq * 32) << 16;
     uint32_t u_cnt = 0, us_uses = 0, item_cnt = 0;
-    for (int item = blockIdx.x; item < L.items; item += gridDim.x, ++item_cnt) {
-      const int o = L.active[item % L.n_active], m0 = (item / L.n_active) * 128;
+    for (int item = cluster_id; item < L.items; item += n_clusters, ++item_cnt) {
+      const int o = L.active[item % L.n_active], m0 = (item / L.n_active) * 256 + (int)rank * 128;
       const int n = L.outer[o].n;
       const long long row = (long long)m0 + trow;
       const bool row_ok = row < L.rows;
@@ -248,9 +303,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
         float* gate_out = (MODE == 0 && L.gate_out) ? L.gate_out + ((long long)zp * L.rows + row) * L.heads : nullptr;
         const float* gate_in = (MODE == 1) ? L.gate_in + ((long long)zp * L.rows + row) * L.heads : nullptr;
 
-        mbar_wait(u_full, u_cnt & 1u);
+        { CP_T0(); mbar_wait(u_full, u_cnt & 1u); CP_ACC(5); }
         tc_fence_after();
-        mbar_wait(us_free, (us_uses & 1u) ^ 1u);
+        { CP_T0(); mbar_wait(us_free, (us_uses & 1u) ^ 1u); CP_ACC(6); }
+        const long long _tc = clock64();
         int cur_head = -1;
         float cur_gate = 0.0f;
 #pragma unroll 1
@@ -309,9 +365,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(u_empty);
-          mbar_arrive(us_ready);
+          cp_arrive_leader(u_empty);     // TMEM intermediate drained (leader may start the next GEMM1)
+          cp_arrive_leader(us_ready);    // staging block written (leader may start GEMM2)
+          mbar_arrive(us_ready_l);       // ... and this CTA's store warp may read it
         }
+        dbg_acc[3] += clock64() - _tc;
       }
 
       // ---- final epilogue over ACC ----
@@ -338,7 +396,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
       Raw16 nxt = ld_row16(aux_row + c_begin, row_ok), nxt2;
       if (MODE == 1) nxt2 = ld_row16(aux2_row + c_begin, row_ok);
 
-      mbar_wait(acc_full, item_cnt & 1u);
+      { CP_T0(); mbar_wait(acc_full, item_cnt & 1u); CP_ACC(8); }
       tc_fence_after();
       mbar_wait(us_free, (us_uses & 1u) ^ 1u);
       ++us_uses;
@@ -372,93 +430,70 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
       fence_async_smem();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(acc_empty);
+        cp_arrive_leader(acc_empty);
         mbar_arrive(out_ready);
       }
+      if (threadIdx.x == 128) { CP_FLUSH(5); CP_FLUSH(6); CP_FLUSH(7); CP_FLUSH(8); CP_SET(9); }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  cp_cluster_sync();   // neither CTA frees TMEM or exits while the pair's MMAs / the peer's signals are in flight
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
 
-size_t chain_fixed_smem() { return 1024 + 8 * (2 * CH_MAX_STAGES + 8) + 3 * 256 * 4; }
+size_t chainp_fixed_smem() { return 1024 + 8 * (2 * CH_MAX_STAGES + 10) + 3 * 256 * 4; }
 
 }  // namespace
 
-bool chain2_eligible(int H, int M);                                          // chain2_gemm.cu
-int chain2_launch(ChainLaunch& L, cudaStream_t stream, const char* label);
+bool chainp_eligible(int H, int M) { return H % 128 == 0 && H >= 128 && H <= 256 && M >= 1 && M <= MSF_MAX_MODALITIES; }
 
-bool chainp_eligible(int H, int M);                                          // chainp_gemm.cu (CTA pairs)
-int chainp_launch(ChainLaunch& L, cudaStream_t stream, const char* label);
-
-bool chain2p_eligible(int H, int M);                                         // chain2p_gemm.cu (CTA pairs, pipelined)
-int chain2p_launch(ChainLaunch& L, cudaStream_t stream, const char* label);
-
-// kernel choice: 2 = chain2_kernel, single CTA with the half-pair software pipeline (default for hidden % 128 == 0);
-// 1 = chain_kernel (every other hidden size, or MSF_CHAIN=v1).  The cta_group::2 variants are correct (same parity
-// tests) but not faster yet at B = 4096 — the epilogue, not the tensor pipe, is their critical path — and are opt-in:
-// MSF_CHAIN=pair2 -> 4 = chain2p_kernel (CTA pairs + pipeline), MSF_CHAIN=pair -> 3 = chainp_kernel (CTA pairs).
-static int chain_variant(int H, int M) {
-  const char* e = getenv("MSF_CHAIN");
-  if (getenv("MSF_CHAIN_V1") || (e && e[0] == 'v' && e[1] == '1')) return 1;
-  if (e && e[0] == 'p' && e[1] == 'a' && e[2] == 'i' && e[3] == 'r' && e[4] == '2') return chain2p_eligible(H, M) ? 4 : 1;
-  if (e && e[0] == 'p') return chainp_eligible(H, M) ? 3 : 1;
-  return chain2_eligible(H, M) ? 2 : 1;
-}
-int chain_w1_box_rows(int H, int M) {
-  const int v = chain_variant(H, M);
-  return v == 4 ? H / 4 : (v >= 2 ? H / 2 : H);
-}
-int chain_w2_box_rows(int H, int M) { return chain_variant(H, M) >= 3 ? H / 2 : H; }
-
-bool chain_eligible(int H, int M) { return H % 64 == 0 && H >= 64 && H <= 256 && M >= 1 && M <= MSF_MAX_MODALITIES; }
-
-int chain_launch(ChainLaunch& L, cudaStream_t stream, const char* label) {
-  MSF_REQUIRE(chain_eligible(L.H, L.M), "chain_gemm: hidden %d / modalities %d not supported", L.H, L.M);
-  MSF_REQUIRE(L.rows >= 1, "chain_gemm: empty batch");
-  const int variant = chain_variant(L.H, L.M);
-  if (variant == 4) return chain2p_launch(L, stream, label);
-  if (variant == 3) return chainp_launch(L, stream, label);
-  if (variant == 2) return chain2_launch(L, stream, label);
-  L.row_tiles = (int)ceil_div(L.rows, 128);
+int chainp_launch(ChainLaunch& L, cudaStream_t stream, const char* label) {
+  MSF_REQUIRE(chainp_eligible(L.H, L.M), "chainp_gemm: hidden %d / modalities %d not supported", L.H, L.M);
+  MSF_REQUIRE(L.rows >= 1, "chainp_gemm: empty batch");
   if (L.n_active <= 0) {   // default: every modality is an outer modality
     L.n_active = L.M;
     for (int m = 0; m < L.M; ++m) L.active[m] = (short)m;
   }
+  L.row_tiles = (int)ceil_div(L.rows, 256);          // 256-window tiles: one per CTA pair
   L.items = L.row_tiles * L.n_active;
   const size_t per_stage = CH_A_BYTES + ch_b_bytes(L.H);
   const size_t ublock = (size_t)(L.H / 64) * CH_A_BYTES;
-  int stages = (int)((CH_SMEM_LIMIT - chain_fixed_smem() - ublock) / per_stage);
+  int stages = (int)((CH_SMEM_LIMIT - chainp_fixed_smem() - ublock) / per_stage);
   if (stages > CH_MAX_STAGES) stages = CH_MAX_STAGES;
-  MSF_REQUIRE(stages >= 2, "chain_gemm: not enough shared memory for hidden %d", L.H);
+  MSF_REQUIRE(stages >= 2, "chainp_gemm: not enough shared memory for hidden %d", L.H);
   L.stages = stages;
-  const size_t smem = chain_fixed_smem() + ublock + (size_t)stages * per_stage;
+  const size_t smem = chainp_fixed_smem() + ublock + (size_t)stages * per_stage;
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
     MSF_CHECK_CUDA(cudaGetDevice(&dev));
     MSF_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int grid = L.items < sms ? L.items : sms;
+  const int clusters = L.items < sms / 2 ? L.items : sms / 2;
   if (prof_enabled()) {
     double pairs = 0.0;
     for (int o = 0; o < L.M; ++o) pairs += L.outer[o].n;
     prof_begin(label, 2.0 * 2.0 * (double)L.rows * L.H * L.H * pairs, stream);
   }
   if (L.mode == 0) {
-    MSF_CHECK_CUDA(cudaFuncSetAttribute(chain_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MSF_CHECK_CUDA(launch_pdl(chain_kernel<0>, dim3(grid), dim3(CH_THREADS), smem, stream, L));
+    MSF_CHECK_CUDA(cudaFuncSetAttribute(chainp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MSF_CHECK_CUDA(launch_pdl(chainp_kernel<0>, dim3(2 * clusters), dim3(CH_THREADS), smem, stream, L));
   } else {
-    MSF_CHECK_CUDA(cudaFuncSetAttribute(chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MSF_CHECK_CUDA(launch_pdl(chain_kernel<1>, dim3(grid), dim3(CH_THREADS), smem, stream, L));
+    MSF_CHECK_CUDA(cudaFuncSetAttribute(chainp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MSF_CHECK_CUDA(launch_pdl(chainp_kernel<1>, dim3(2 * clusters), dim3(CH_THREADS), smem, stream, L));
   }
   MSF_LAUNCH_CHECK();
   prof_end(stream);
+  return MSF_OK;
+}
+
+int chainp_debug_stamps(long long* out16) {
+  MSF_CHECK_CUDA(cudaDeviceSynchronize());
+  MSF_CHECK_CUDA(cudaMemcpyFromSymbol(out16, g_chainp_stamps, sizeof(long long) * 16));
   return MSF_OK;
 }
 

@@ -200,3 +200,25 @@ def test_projection_kernel_input_widths():
     for key, _, _ in plan.slots:
         got, ref = _slot(plan, grad, key).cpu(), sd[key].grad
         assert float((got - ref).abs().max()) <= 1e-2, key
+
+
+@pytest.mark.parametrize("variant", ["pair", "pair2", "v1"])
+def test_chain_kernel_variants_agree(variant, monkeypatch):
+    """The opt-in chain kernels — CTA pairs (tcgen05 cta_group::2: chainp_kernel, chain2p_kernel) and the
+    un-pipelined chain_kernel — against the default chain2_kernel on a train pass (ragged batch: 7 row tiles,
+    so the last CTA pair has an empty second tile)."""
+    ops, N, model, plan, arena, arena16, xs, mask, labels = _setup(800, seed=31)
+    kw = dict(precision=N.MSF_PREC_BF16, training=True, p=0.1, seed=5, offset=2, arena_bf16=arena16)
+    monkeypatch.delenv("MSF_CHAIN", raising=False)
+    ref = ops.fusion_train_pass_raw(plan, arena, xs, mask, labels, smoothing=0.05, **kw)
+    monkeypatch.setenv("MSF_CHAIN", variant)
+    got = ops.fusion_train_pass_raw(plan, arena, xs, mask, labels, smoothing=0.05, **kw)
+    monkeypatch.delenv("MSF_CHAIN")
+    torch.cuda.synchronize()
+    assert torch.isfinite(got[2]).all()
+    assert float((got[0] - ref[0]).abs().max()) <= 5e-4           # logits
+    assert abs(float(got[1]) - float(ref[1])) <= 1e-4             # loss
+    assert torch.equal(got[4], ref[4])                            # attention gates
+    scale = float(ref[2].abs().max())
+    assert float((got[2] - ref[2]).abs().max()) <= 2e-3 * scale + 1e-7
+    assert float((got[2] - ref[2]).norm()) <= 2e-2 * float(ref[2].norm())
