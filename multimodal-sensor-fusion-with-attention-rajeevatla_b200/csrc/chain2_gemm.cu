@@ -336,35 +336,48 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
         const long long _tc = clock64();
         int cur_head = -1;
         float cur_gate = 0.0f;
+        if ((L.head_dim & 15) == 0) {
+          // 32 accumulator columns per TMEM load / wait (half as many round trips as x16); every 16-column group
+          // lies inside one head
 #pragma unroll 1
-        for (int c = hc_begin; c < hc_end; c += 16) {
-          const int ca = b * HW + c;   // column of the full intermediate
-          uint32_t acc[16];
-          tmem_ld16_issue(tmem_base + lane_base + (uint32_t)(b * HW + c), acc);
-          tmem_wait16(acc);
-          float v[16];
-          if ((L.head_dim & 15) == 0) {  // the 16 columns lie inside one head
-            const int head = ca / L.head_dim;
-            if (head != cur_head) {
-              cur_head = head;
-              if (MODE == 0) {
-                cur_gate = (gate_mask != 0.0f) ? 1.0f : 0.0f;
-                if (drop.active) cur_gate *= drop1(drop, SITE_ATTN, sub, row, head);
-                if (gate_out != nullptr && row_ok && ca == head * L.head_dim) gate_out[head] = cur_gate;
-              } else {
-                cur_gate = row_ok ? __ldg(gate_in + head) : 0.0f;
-              }
-            }
+          for (int c = hc_begin; c < hc_end; c += 32) {
+            uint32_t acc[32];
+            tmem_ld32(tmem_base + lane_base + (uint32_t)(b * HW + c), acc);
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (MODE == 0) b4 = *reinterpret_cast<const float4*>(bias_s + c + 4 * q4);
-              v[4 * q4 + 0] = (__uint_as_float(acc[4 * q4 + 0]) + b4.x) * cur_gate;
-              v[4 * q4 + 1] = (__uint_as_float(acc[4 * q4 + 1]) + b4.y) * cur_gate;
-              v[4 * q4 + 2] = (__uint_as_float(acc[4 * q4 + 2]) + b4.z) * cur_gate;
-              v[4 * q4 + 3] = (__uint_as_float(acc[4 * q4 + 3]) + b4.w) * cur_gate;
+            for (int g16 = 0; g16 < 2; ++g16) {
+              const int cc = c + 16 * g16, ca = b * HW + cc;   // column of the full intermediate
+              const int head = L.head_shift >= 0 ? (ca >> L.head_shift) : ca / L.head_dim;
+              if (head != cur_head) {
+                cur_head = head;
+                if (MODE == 0) {
+                  cur_gate = (gate_mask != 0.0f) ? 1.0f : 0.0f;
+                  if (drop.active) cur_gate *= drop1(drop, SITE_ATTN, sub, row, head);
+                  if (gate_out != nullptr && row_ok && ca == head * L.head_dim) gate_out[head] = cur_gate;
+                } else {
+                  cur_gate = row_ok ? __ldg(gate_in + head) : 0.0f;
+                }
+              }
+              float v[16];
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) {
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (MODE == 0) b4 = *reinterpret_cast<const float4*>(bias_s + cc + 4 * q4);
+                v[4 * q4 + 0] = (__uint_as_float(acc[16 * g16 + 4 * q4 + 0]) + b4.x) * cur_gate;
+                v[4 * q4 + 1] = (__uint_as_float(acc[16 * g16 + 4 * q4 + 1]) + b4.y) * cur_gate;
+                v[4 * q4 + 2] = (__uint_as_float(acc[16 * g16 + 4 * q4 + 2]) + b4.z) * cur_gate;
+                v[4 * q4 + 3] = (__uint_as_float(acc[16 * g16 + 4 * q4 + 3]) + b4.w) * cur_gate;
+              }
+              st_swizzled16(ub, trow, cc, v);
             }
-          } else {  // narrow heads (head_dim not a multiple of 16): per-column gate
+          }
+        } else {
+#pragma unroll 1
+          for (int c = hc_begin; c < hc_end; c += 16) {   // narrow heads (head_dim not a multiple of 16): per-column gate
+            const int ca = b * HW + c;
+            uint32_t acc[16];
+            tmem_ld16_issue(tmem_base + lane_base + (uint32_t)(b * HW + c), acc);
+            tmem_wait16(acc);
+            float v[16];
 #pragma unroll 1
             for (int j = 0; j < 16; ++j) {
               const int head = (ca + j) / L.head_dim;
@@ -386,8 +399,8 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
               for (int jj = 0; jj < 16; ++jj)
                 if (jj == j) v[jj] = r;
             }
+            st_swizzled16(ub, trow, c, v);
           }
-          st_swizzled16(ub, trow, c, v);
         }
         tc_fence_before();
         fence_async_smem();

@@ -421,6 +421,9 @@ bool chain_eligible(int H, int M) { return H % 64 == 0 && H >= 64 && H <= 256 &&
 int chain_launch(ChainLaunch& L, cudaStream_t stream, const char* label) {
   MSF_REQUIRE(chain_eligible(L.H, L.M), "chain_gemm: hidden %d / modalities %d not supported", L.H, L.M);
   MSF_REQUIRE(L.rows >= 1, "chain_gemm: empty batch");
+  L.head_shift = -1;
+  for (int sft = 0; sft < 16; ++sft)
+    if ((1 << sft) == L.head_dim) L.head_shift = sft;
   const int variant = chain_variant(L.H, L.M);
   if (variant == 4) return chain2p_launch(L, stream, label);
   if (variant == 3) return chainp_launch(L, stream, label);

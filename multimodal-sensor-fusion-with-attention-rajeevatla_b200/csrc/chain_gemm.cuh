@@ -38,6 +38,7 @@ struct ChainLaunch {
   CUtensorMap map_a1, map_w1, map_w2, map_out1, map_out;
   int mode;            // 0 forward, 1 backward
   int M, H, heads, head_dim;
+  int head_shift;      // log2(head_dim) when it is a power of two, else -1 (set by chain_launch)
   int rows, row_tiles, items;
   int n_active;                    // outer modalities that get items (0: all M); absent queries of a uniform-mask
   short active[MSF_MAX_MODALITIES];  // inference pass are left out: the head never reads their aggregated token
