@@ -222,3 +222,29 @@ def test_chain_kernel_variants_agree(variant, monkeypatch):
     scale = float(ref[2].abs().max())
     assert float((got[2] - ref[2]).abs().max()) <= 2e-3 * scale + 1e-7
     assert float((got[2] - ref[2]).norm()) <= 2e-2 * float(ref[2].norm())
+
+
+def test_multi_tile_per_cta_train_pass(monkeypatch):
+    """B = 19 200 windows = 150 head tiles of 128 windows on 148 SMs (and 600 chain / projection items): every
+    persistent kernel of the train pass takes a second item on some CTAs (ring positions, barrier parities and
+    staging buffers carried from one item to the next).  Checked against the un-fused sequence."""
+    ops, N, model, plan, arena, arena16, xs, mask, labels = _setup(19200, seed=37)
+    kw = dict(precision=N.MSF_PREC_BF16, training=True, p=0.1, seed=8, offset=1, arena_bf16=arena16)
+    monkeypatch.delenv("MSF_NO_HEAD", raising=False)
+    logits, loss, grad, fw, gates = ops.fusion_train_pass_raw(plan, arena, xs, mask, labels, smoothing=0.05, **kw)
+    monkeypatch.setenv("MSF_NO_HEAD", "1")
+    monkeypatch.setenv("MSF_NO_PROJ", "1")
+    l2, fw2, g2, ws = ops.fusion_forward_raw(plan, arena, xs, mask, **kw)
+    loss2, dl = ops.cross_entropy(l2, labels, 0.05)
+    grad2, _ = ops.fusion_backward_raw(plan, arena, xs, mask, ws, dl, **kw)
+    monkeypatch.delenv("MSF_NO_HEAD")
+    monkeypatch.delenv("MSF_NO_PROJ")
+    torch.cuda.synchronize()
+    assert torch.isfinite(grad).all() and torch.isfinite(logits).all()
+    assert float((logits - l2).abs().max()) <= 5e-4
+    assert float((fw - fw2).abs().max()) <= 5e-6
+    assert torch.equal(gates, g2)
+    assert abs(float(loss) - float(loss2)) <= 1e-4
+    scale = float(grad2.abs().max())
+    assert float((grad - grad2).abs().max()) <= 2e-3 * scale + 1e-7
+    assert float((grad - grad2).norm()) <= 2e-2 * float(grad2.norm())
