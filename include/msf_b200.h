@@ -160,6 +160,9 @@ int msf_debug_chain_stamps(int64_t* out16);
 /* cta_group::2 probe (pair_gemm.cu): D[m, 256] = A[m, k] . B[256, k]^T, bf16 operands, fp32 D, one CTA pair per
  * 256 rows.  Building block of the round-2 kernels; not used by the product path. */
 int msf_debug_pair_gemm(const void* a_bf16, const void* b_bf16, float* d, int64_t m, int64_t k, void* stream);
+/* Issue-rate probe: `ctas` CTAs each issue reps x ksteps tcgen05.mma (M = 128, N = n, K = 16, operands resident in
+ * shared memory); cycles_out[0] = clock64 cycles CTA 0 needed.  Synchronises the stream. */
+int msf_debug_mma_rate(int32_t n, int32_t reps, int32_t ksteps, int32_t ctas, int64_t* cycles_out, void* stream);
 /* Phase stamps of CTA 0 of the last input-projection launch (proj_gemm.cu). */
 int msf_debug_proj_stamps(int64_t* out16);
 /* HybridFusion.compute_adaptive_weights (src/fusion.py:429-479) stand-alone:

@@ -171,3 +171,72 @@ extern "C" int msf_debug_pair_gemm(const void* a_bf16, const void* b_bf16, float
   MSF_LAUNCH_CHECK();
   return MSF_OK;
 }
+
+// ---------------------------------------------------------------------------
+// Issue-rate probe: one thread per CTA issues `reps` tcgen05.mma (M = 128, N = n, K = 16, bf16, both operands
+// resident in shared memory — no TMA, no epilogue) and reports clock64 cycles per MMA.  Separates what the
+// tensor pipe can do from what the chained kernels achieve (profiles/README.md).
+// ---------------------------------------------------------------------------
+namespace msf {
+namespace {
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int reps, int ksteps, long long* out) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = base, b_base = base + 4 * 16384, bar = b_base + 4 * 32768, slot = bar + 8;
+  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (slot - smem_u32(smem_raw)));
+  for (uint32_t i = threadIdx.x; i < (4 * 16384 + 4 * 32768) / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)))[i] = 0x3c003c00u;   // bf16 small values
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot_ptr;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = instr_desc(n, false, false);
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      const int st = r & 3;   // walk over 4 resident operand stages like a ring
+      for (int k = 0; k < ksteps; ++k)
+        tc_mma_bf16(tmem + (uint32_t)((r & 1) * 256), smem_desc(a_base + st * 16384 + k * 32, 16, 1024),
+                    smem_desc(b_base + st * 32768 + k * 32, 16, 1024), idesc, (k > 0) ? 1u : 0u);
+    }
+    tc_commit(bar);
+    mbar_wait(bar, 0u);
+    const long long t1 = clock64();
+    if (blockIdx.x == 0) out[0] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+}  // namespace
+}  // namespace msf
+
+extern "C" int msf_debug_mma_rate(int32_t n, int32_t reps, int32_t ksteps, int32_t ctas, int64_t* cycles_out, void* stream) {
+  using namespace msf;
+  MSF_REQUIRE(n >= 16 && n <= 256 && n % 16 == 0 && reps >= 1 && ksteps >= 1 && ksteps <= 4 && ctas >= 1 && cycles_out,
+              "msf_debug_mma_rate: bad arguments");
+  long long* dev = nullptr;
+  MSF_CHECK_CUDA(cudaMalloc(&dev, sizeof(long long)));
+  const size_t smem = 1024 + 4 * 16384 + 4 * 32768 + 64;
+  MSF_CHECK_CUDA(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mma_rate_kernel<<<ctas, 128, smem, (cudaStream_t)stream>>>(n, reps, ksteps, dev);
+  MSF_LAUNCH_CHECK();
+  MSF_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  long long v = 0;
+  MSF_CHECK_CUDA(cudaMemcpy(&v, dev, sizeof(v), cudaMemcpyDeviceToHost));
+  MSF_CHECK_CUDA(cudaFree(dev));
+  *cycles_out = v;
+  return MSF_OK;
+}

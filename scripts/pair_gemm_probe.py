@@ -32,3 +32,11 @@ for _ in range(20):
 e1.record(); torch.cuda.synchronize()
 us = e0.elapsed_time(e1) * 1e3 / 20
 print(f"pair gemm {M}x256x{K}: {us:.1f} us, {2.0 * M * 256 * K / us / 1e6:.0f} TFLOP/s on {M // 256 * 2} CTAs")
+
+# tensor-pipe issue rate with resident operands
+for ctas in (1, 148):
+    for n in (64, 128, 256):
+        c = ctypes.c_int64()
+        N.check(lib.msf_debug_mma_rate(n, 2000, 4, ctas, ctypes.byref(c), torch.cuda.current_stream().cuda_stream))
+        per = c.value / (2000 * 4)
+        print(f"mma rate: ctas={ctas} M=128 N={n} K=16: {per:.1f} cycles/MMA -> {128 * n * 16 * 2 / per * 1.965e9 * 148 / 1e12:.0f} TFLOP/s chip-equivalent")
