@@ -224,3 +224,39 @@ def test_train_stream_pipeline_equals_step_by_step():
         assert abs(a - b) <= 1e-3 * abs(a), out
     diff = (out["blocking"][1] - out["stream"][1]).abs()
     assert float(diff.max()) <= 1.01e-2 and float(diff.mean()) <= 1e-4
+
+
+def test_resident_slots_and_subset_inference():
+    """FusionEngine.add_resident_batch / train_step_slot (batches trained on in place, one captured graph per
+    slot) follow the copy-in path; FusionEngine.infer_subset (uniform-mask hint) equals infer with that mask."""
+    pkg = load_pkg()
+    engine = importlib.import_module(pkg.__name__ + ".engine")
+    data = [seeded_case(PAMAP2, 256, 4, 25, 512, seed=60 + i, device="cuda")[1:] for i in range(3)]
+    out = {}
+    for mode in ("copy", "slots"):
+        model, *_ = seeded_case(PAMAP2, 256, 4, 25, 512, seed=21, device="cuda")
+        eng = engine.FusionEngine(model, 512, precision="bf16", seed=5, use_graph=True)
+        if mode == "copy":
+            losses = [float(eng.train_step(f, m, y).item()) for f, m, y in data for _ in range(2)]
+        else:
+            slots = [eng.add_resident_batch({k: v.contiguous() for k, v in f.items()}, m, y) for f, m, y in data]
+            losses = [float(eng.train_step_slot(s).item()) for s in slots for _ in range(2)]
+        out[mode] = (losses, eng.arena.clone(), eng)
+    for a, b in zip(out["copy"][0], out["slots"][0]):
+        assert abs(a - b) <= 1e-3 * abs(a), out
+    assert float((out["copy"][1] - out["slots"][1]).abs().max()) <= 1.3e-2   # Adam sign flips of ~0 gradients
+    eng = out["slots"][2]
+    with pytest.raises(ValueError):
+        eng.add_resident_batch(data[0][0], data[0][1][:100], data[0][2])
+    feats = data[0][0]
+    for present in ([0], [1, 3], [0, 1, 2, 3]):
+        mask = torch.zeros(512, 4, device="cuda")
+        mask[:, present] = 1.0
+        l_ref, c_ref, p_ref = (t.clone() for t in eng.infer(feats, mask))
+        l_sub, c_sub, p_sub = (t.clone() for t in eng.infer_subset(feats, present))
+        assert float((l_sub - l_ref).abs().max()) <= 1e-5
+        assert torch.equal(p_sub, p_ref)
+        l_again = eng.infer_subset(None, present)[0]          # features kept in the static buffers
+        assert torch.equal(l_again, l_sub)
+    with pytest.raises(ValueError):
+        eng.infer_subset(feats, [])
