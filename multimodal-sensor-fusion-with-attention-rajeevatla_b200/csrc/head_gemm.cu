@@ -30,6 +30,9 @@ constexpr int HD_RS = MSF_MAX_MODALITIES;      // stride of the per-row scalar a
 constexpr int HD_NBAR = 2 * HD_MAX_STAGES + 4;
 
 __host__ __device__ constexpr uint32_t hd_ring_bytes(int H) { return (uint32_t)H * 64 * 2; }
+// the cross-entropy's logit staging tile [128][33] fp32 lives in k-blocks 1.. of the A block when the A block has at
+// least three k-blocks, else in its own region behind the per-row scalars
+__host__ __device__ constexpr int hd_zs_floats(int H) { return H >= 192 ? 0 : 128 * 33; }
 
 // CTAs that have finished; the last one reduces row_loss in a fixed order and resets the ticket
 __device__ unsigned int g_head_ticket = 0;
@@ -115,7 +118,7 @@ __device__ __forceinline__ float transpose_reduce8(float (&p)[8], int lane) {
 
 struct HeadSmem {
   unsigned char* ublk;
-  float *b1s, *b2s, *gws, *gbs, *rw, *rsoft, *rmk;
+  float *b1s, *b2s, *db2s, *gws, *gbs, *rw, *rsoft, *rmk;
 };
 
 // Sum / max over the (up to 4) modalities of a window: lane l holds modality (l >> 3) & 3.
@@ -293,7 +296,8 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_kernel(const __grid_consta
   S.ublk = smem_raw + (u_base - off0);
   S.b1s = fbase;
   S.b2s = S.b1s + H;
-  S.gws = S.b2s + 32;
+  S.db2s = S.b2s + 32;   // this CTA's share of the classifier.3 bias gradient
+  S.gws = S.db2s + 32;
   S.gbs = S.gws + M * H;
   S.rw = S.gbs + HD_RS;
   S.rsoft = S.rw + 128 * HD_RS;
@@ -336,6 +340,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_kernel(const __grid_consta
     const int et = threadIdx.x - 128;
     for (int e = et; e < H; e += 32 * HD_WORKERS) S.b1s[e] = __ldg(L.b1 + e);
     if (et < 32) S.b2s[et] = et < C ? __ldg(L.b2 + et) : 0.0f;
+    if (et < 32) S.db2s[et] = 0.0f;
     for (int e = et; e < M * H; e += 32 * HD_WORKERS) S.gws[e] = __ldg(L.gate_w[e / H] + e % H);
     if (et < HD_RS) S.gbs[et] = et < M ? __ldg(L.gate_b[et]) : 0.0f;
   }
@@ -547,76 +552,94 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_kernel(const __grid_consta
       publish();
       HD_STAMP(3);
 
-      // ---- E2: logits, softmax / cross-entropy (thread = window) ----
+      // ---- E2: logits, softmax / cross-entropy.  The warps that own the accumulator rows move the 32 logit
+      // columns (+ bias) to shared memory; then ALL worker warps share the arithmetic, 8 threads per window
+      // (4 columns each, reductions over the 8-lane group), 32 windows per pass. ----
       acquire();
       HD_STAMP(4);
+      float* zs = hd_zs_floats(H) ? S.rmk + 128 * HD_RS : reinterpret_cast<float*>(S.ublk + HD_A_BYTES);   // [tile rows][33]
       if (cg == 0 && warp_live) {
-        // three rolled passes over the 32 accumulator columns, 8 at a time (TMEM re-reads are cheap, code is not)
-        const uint32_t zaddr = tmem_base + lane_base + 256u;
-        float mx = -INFINITY, zsum = 0.0f;
-        int arg = 0;
-        bool has_nan = false;
-#pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {   // pass 1: logits out, max / arg-max / sum
-          uint32_t acc[8];
-          tmem_ld8(zaddr + (uint32_t)(ch * 8), acc);
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + lane_base + 256u, acc);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int c = ch * 8 + e;
-            const float z = __uint_as_float(acc[e]) + S.b2s[c];
-            if (c < C) {
-              if (row_ok) L.logits[row * C + c] = z;
-              has_nan |= (z != z);
-              if (z > mx) { mx = z; arg = c; }   // first max (torch.max tie rule)
-              zsum += z;
+        for (int c = 0; c < 32; ++c) zs[trow * 33 + c] = __uint_as_float(acc[c]) + S.b2s[c];
+      }
+      tc_fence_before();
+      workers_sync();
+      {
+        const int sub = lane & 7, c0 = sub * 4;           // this thread's 4 columns
+        const float off = L.smoothing / (float)C * L.grad_scale, hit = (1.0f - L.smoothing) * L.grad_scale;
+#pragma unroll 1
+        for (int r0 = 0; r0 < L.tile_rows; r0 += 32) {
+          const int r = r0 + wq * 4 + (lane >> 3);
+          const long long grow = (long long)m0 + r;
+          const bool ok = grow < L.rows;
+          float z[4];
+          float mx = -INFINITY, zsum = 0.0f;
+          int arg = c0;
+          bool has_nan = false;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            z[e] = zs[r * 33 + c0 + e];
+            if (c0 + e < C) {
+              if (ok) L.logits[grow * C + c0 + e] = z[e];
+              has_nan |= (z[e] != z[e]);
+              if (z[e] > mx) { mx = z[e]; arg = c0 + e; }   // first max inside the thread's columns
+              zsum += z[e];
             }
           }
-        }
-        const int y = (L.train && row_ok) ? (int)L.labels[row] : -1;
-        float se = 0.0f, zy = 0.0f;
-#pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {   // pass 2: sum of exp(z - max), the label's logit
-          uint32_t acc[8];
-          tmem_ld8(zaddr + (uint32_t)(ch * 8), acc);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int c = ch * 8 + e;
-            const float z = __uint_as_float(acc[e]) + S.b2s[c];
-            if (c == y) zy = z;
-            if (c < C) se += expf(z - mx);
+          for (int o = 1; o < 8; o <<= 1) {                    // over the window's 8 threads; ties -> lowest column
+            const float omx = __shfl_xor_sync(0xffffffffu, mx, o);
+            const int oarg = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (omx > mx || (omx == mx && oarg < arg)) { mx = omx; arg = oarg; }
+            zsum += __shfl_xor_sync(0xffffffffu, zsum, o);
+            has_nan |= (__shfl_xor_sync(0xffffffffu, has_nan ? 1 : 0, o) != 0);
           }
-        }
-        if (!L.train) {
-          if (L.conf != nullptr && row_ok) {   // eval.py:89-90; a NaN logit gives (NaN, 0) like torch.max
-            L.conf[row] = has_nan ? nanf("") : 1.0f / se;
-            L.pred[row] = has_nan ? 0 : arg;
-          }
-        } else {
-          const float lse = mx + logf(se);
-          if (row_ok) {
-            const float nll = lse - zy;
-            const float smooth = lse - zsum / (float)C;  // mean_c(-log p_c)
-            L.row_loss[row] = (1.0f - L.smoothing) * nll + L.smoothing * smooth;
-          }
-          const float inv = row_ok ? L.grad_scale / se : 0.0f, off = L.smoothing / (float)C * L.grad_scale;
-          const float hit = (1.0f - L.smoothing) * L.grad_scale;
-#pragma unroll 1
-          for (int ch = 0; ch < 4; ++ch) {   // pass 3: d logits -> A operand of G3 / global, column sums -> d b2
-            uint32_t acc[8];
-            tmem_ld8(zaddr + (uint32_t)(ch * 8), acc);
-            float dl[8];
+          const int y = (L.train && ok) ? (int)L.labels[grow] : -1;
+          float ex[4], se = 0.0f, zy = 0.0f;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int c = ch * 8 + e;
-              const float z = __uint_as_float(acc[e]) + S.b2s[c];
-              dl[e] = (c < C && row_ok) ? fmaf(expf(z - mx), inv, -(off + (c == y ? hit : 0.0f))) : 0.0f;
+          for (int e = 0; e < 4; ++e) {
+            ex[e] = (c0 + e < C) ? expf(z[e] - mx) : 0.0f;
+            se += ex[e];
+            if (c0 + e == y) zy = z[e];
+          }
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {
+            se += __shfl_xor_sync(0xffffffffu, se, o);
+            zy += __shfl_xor_sync(0xffffffffu, zy, o);
+          }
+          if (!L.train) {
+            if (L.conf != nullptr && ok && sub == 0) {   // eval.py:89-90; a NaN logit gives (NaN, 0) like torch.max
+              L.conf[grow] = has_nan ? nanf("") : 1.0f / se;
+              L.pred[grow] = has_nan ? 0 : arg;
             }
-            const uint4 pk = pack8(dl);
-            *reinterpret_cast<uint4*>(S.ublk + swz_off(trow, ch * 8)) = pk;   // k < 32 of the dlog A block
-            if (row_ok && ch * 8 < L.Cp) *reinterpret_cast<uint4*>(L.dlog + row * L.Cp + ch * 8) = pk;
-            const float colsum = transpose_reduce8(dl, lane);   // lane l: column ch*8 + ((l >> 2) & 7)
-            const int cc = ch * 8 + ((lane >> 2) & 7);
-            if ((lane & 3) == 0 && cc < C) atomicAdd(L.db2 + cc, colsum);
+          } else {
+            if (ok && sub == 0) {
+              const float lse = mx + logf(se);
+              const float nll = lse - zy, smooth = lse - zsum / (float)C;   // mean_c(-log p_c)
+              L.row_loss[grow] = (1.0f - L.smoothing) * nll + L.smoothing * smooth;
+            }
+            const float inv = ok ? L.grad_scale / se : 0.0f;
+            float dl[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              dl[e] = (c0 + e < C && ok) ? fmaf(ex[e], inv, -(off + (c0 + e == y ? hit : 0.0f))) : 0.0f;
+            uint2 pk;
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+            h2[0] = __floats2bfloat162_rn(dl[0], dl[1]);
+            h2[1] = __floats2bfloat162_rn(dl[2], dl[3]);
+            // A operand of G3 (k < 32): 8-byte half of the 16-byte swizzle chunk
+            *reinterpret_cast<uint2*>(S.ublk + swz_off(r, c0 & ~7) + ((c0 & 4) ? 8 : 0)) = pk;
+            if (ok && c0 < L.Cp) *reinterpret_cast<uint2*>(L.dlog + grow * L.Cp + c0) = pk;
+            // classifier.3 bias gradient: sum the warp's 4 windows into the CTA's shared-memory accumulators
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float cs = dl[e];
+              cs += __shfl_xor_sync(0xffffffffu, cs, 8);
+              cs += __shfl_xor_sync(0xffffffffu, cs, 16);
+              if (lane < 8 && c0 + e < C) atomicAdd(S.db2s + c0 + e, cs);
+            }
           }
         }
       }
@@ -672,6 +695,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_kernel(const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (L.train && (int)threadIdx.x < C) atomicAdd(L.db2 + threadIdx.x, S.db2s[threadIdx.x]);
   HD_STAMP(12);
   if (warp == 2) {
     tc_fence_after();
@@ -706,7 +730,9 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_kernel(const __grid_consta
   }
 }
 
-size_t head_float_smem(int H, int M) { return (size_t)(H + 32 + M * H + HD_RS + 3 * 128 * HD_RS) * 4; }
+size_t head_float_smem(int H, int M) {
+  return (size_t)(H + 64 + M * H + HD_RS + 3 * 128 * HD_RS + hd_zs_floats(H)) * 4;
+}
 
 }  // namespace
 

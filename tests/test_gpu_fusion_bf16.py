@@ -254,7 +254,7 @@ def test_resident_slots_and_subset_inference():
         mask[:, present] = 1.0
         l_ref, c_ref, p_ref = (t.clone() for t in eng.infer(feats, mask))
         l_sub, c_sub, p_sub = (t.clone() for t in eng.infer_subset(feats, present))
-        assert float((l_sub - l_ref).abs().max()) <= 1e-5
+        assert float((l_sub - l_ref).abs().max()) <= 5e-4   # bf16 rounding flips where the skipped tokens change the summation order
         assert torch.equal(p_sub, p_ref)
         l_again = eng.infer_subset(None, present)[0]          # features kept in the static buffers
         assert torch.equal(l_again, l_sub)
