@@ -13,14 +13,21 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libmsf_b200.so")
+# MSF_BUILD_VARIANT=timeline: a debug library with the per-kernel step timeline compiled in (msf_common.cuh),
+# built beside the product library as libmsf_b200_timeline.so (select it with MSF_B200_LIB)
+VARIANT = os.environ.get("MSF_BUILD_VARIANT", "")
+OBJ = os.path.join(HERE, "build" + ("_" + VARIANT if VARIANT else ""))
+LIB = os.path.join(HERE, "libmsf_b200" + ("_" + VARIANT if VARIANT else "") + ".so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr",
     "-Xptxas", "-v" if os.environ.get("MSF_PTXAS_V") else "-O3",
 ]
+if VARIANT == "timeline":
+    FLAGS.append("-DMSF_TIMELINE")
+elif VARIANT:
+    raise RuntimeError(f"unknown MSF_BUILD_VARIANT {VARIANT!r}")
 
 
 def _sources():

@@ -101,6 +101,26 @@ int make_layout(const msf_fusion_shape* s, Layout* L) {
 
 }  // namespace msf
 
+#ifdef MSF_TIMELINE
+namespace msf {
+struct TlEntry {
+  const char* tu;
+  tl_dump_fn fn;
+};
+static TlEntry* tl_entries() {
+  static TlEntry e[64];
+  return e;
+}
+static int& tl_count() {
+  static int n = 0;
+  return n;
+}
+void tl_register(const char* tu, tl_dump_fn fn) {
+  if (tl_count() < 64) tl_entries()[tl_count()++] = {tu, fn};
+}
+}  // namespace msf
+#endif
+
 extern "C" {
 
 int msf_abi_version(void) { return MSF_ABI_VERSION; }
@@ -217,5 +237,35 @@ int msf_memcpy_batch(void* const* dst, const void* const* src, const size_t* byt
       MSF_CHECK_CUDA(cudaMemcpyAsync(dst[i], src[i], bytes[i], cudaMemcpyDefault, (cudaStream_t)stream));
   return MSF_OK;
 }
+
+
+#ifdef MSF_TIMELINE
+// debug builds only (msf_common.cuh): prints every translation unit's step-timeline table and clears it
+int msf_debug_timeline(char* buf, size_t cap, int reset) {
+  size_t used = 0;
+  if (cap) buf[0] = 0;
+  for (int i = 0; i < msf::tl_count(); ++i) {
+    static unsigned long long t[32 + 1024];
+    if (msf::tl_entries()[i].fn(t, reset) != 0) return MSF_E_CUDA;
+    for (int k = 0; k < 4; ++k) {
+      if (t[k * 8 + 5] == 0) continue;
+      const char* tu = strrchr(msf::tl_entries()[i].tu, '/');
+      int n = snprintf(buf + used, cap - used, "%s#%d\t%llu\t%llu\t%llu\t%llu\t%llu\t%llu\n", tu ? tu + 1 : msf::tl_entries()[i].tu,
+                       k, t[k * 8 + 0], t[k * 8 + 1], t[k * 8 + 2], t[k * 8 + 3], t[k * 8 + 4], t[k * 8 + 5]);
+      if (n < 0 || (size_t)n >= cap - used) return MSF_E_INVALID;
+      used += (size_t)n;
+      if (t[32 + k * 256] == 0) continue;
+      n = snprintf(buf + used, cap - used, "%s#%d.cta", tu ? tu + 1 : msf::tl_entries()[i].tu, k);
+      used += (size_t)n;
+      for (int b = 0; b < 256 && t[32 + k * 256 + b] != 0; ++b) {
+        if (cap - used < 64) return MSF_E_INVALID;
+        used += (size_t)snprintf(buf + used, cap - used, "\t%llu:%llu", t[32 + k * 256 + b] >> 8, t[32 + k * 256 + b] & 255ull);
+      }
+      used += (size_t)snprintf(buf + used, cap - used, "\n");
+    }
+  }
+  return MSF_OK;
+}
+#endif
 
 }  // extern "C"

@@ -74,6 +74,7 @@ __device__ long long g_chain_stamps[16];
 
 template <int MODE>
 __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_constant__ ChainLaunch L) {
+  TL_KERNEL(MODE);
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t off0 = smem_u32(smem_raw);
   const uint32_t smem_base = (off0 + 1023u) & ~1023u;
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  pdl_wait();     // the prologue above overlapped the previous kernel; its outputs are visible from here on
+  pdl_wait();     TL_WAITED(MODE);  // the prologue above overlapped the previous kernel; its outputs are visible from here on
   pdl_launch();
   long long dbg_acc[4] = {0, 0, 0, 0};
   if (blockIdx.x == 0 && threadIdx.x == 0) g_chain_stamps[0] = clock64();

@@ -446,15 +446,18 @@ struct Colsum16Problem {
   const float* coef;
   int coef_ld;
   float* dst;
+  float* dst_more[MSF_MAX_MODALITIES];   // further destinations of the same sums (nullptr-terminated)
 };
 constexpr int COLSUM16_MAX = 48;
 struct Colsum16List {
   Colsum16Problem p[COLSUM16_MAX];
   int count;
   int rows_per_block;
+  int tag;   // which launch of the step (timeline builds)
 };
 
 __global__ void __launch_bounds__(256) colsum16_kernel(const __grid_constant__ Colsum16List list) {
+  TL_KERNEL(list.tag);
   const Colsum16Problem& P = list.p[blockIdx.y];
   const int r0 = blockIdx.x * list.rows_per_block;
   if (r0 >= P.rows) return;
@@ -495,13 +498,16 @@ __global__ void __launch_bounds__(256) colsum16_kernel(const __grid_constant__ C
       float t = 0.0f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-      if (t != 0.0f) atomicAdd(P.dst + col, t);
+      if (t != 0.0f) {
+        atomicAdd(P.dst + col, t);
+        for (int d = 0; d < MSF_MAX_MODALITIES && P.dst_more[d] != nullptr; ++d) atomicAdd(P.dst_more[d] + col, t);
+      }
     }
     __syncthreads();
   }
 }
 
-static int colsum16_launch(const Colsum16Problem* probs, int count, cudaStream_t st) {
+static int colsum16_launch(const Colsum16Problem* probs, int count, cudaStream_t st, int tag = 0) {
   int done = 0;
   while (done < count) {
     Colsum16List list;
@@ -512,6 +518,7 @@ static int colsum16_launch(const Colsum16Problem* probs, int count, cudaStream_t
       if (list.p[i].rows > max_rows) max_rows = list.p[i].rows;
     }
     list.count = n;
+    list.tag = tag;
     // ~4 waves of blocks over 148 SMs x 8 resident blocks
     int chunks = (int)ceil_div(148 * 8, n);
     if (chunks < 1) chunks = 1;
@@ -542,7 +549,7 @@ __global__ void copy_gates16_kernel(const float* __restrict__ src, float* __rest
 // which also works while the caller's stream is being captured into a CUDA graph.
 struct SideStream {
   cudaStream_t stream;
-  cudaEvent_t fork, join;
+  cudaEvent_t fork, fork2, join;
 };
 static int side_stream(SideStream** out) {
   static SideStream cache[16];
@@ -553,6 +560,7 @@ static int side_stream(SideStream** out) {
   if (!made[dev]) {
     MSF_CHECK_CUDA(cudaStreamCreateWithFlags(&cache[dev].stream, cudaStreamNonBlocking));
     MSF_CHECK_CUDA(cudaEventCreateWithFlags(&cache[dev].fork, cudaEventDisableTiming));
+    MSF_CHECK_CUDA(cudaEventCreateWithFlags(&cache[dev].fork2, cudaEventDisableTiming));
     MSF_CHECK_CUDA(cudaEventCreateWithFlags(&cache[dev].join, cudaEventDisableTiming));
     made[dev] = true;
   }
@@ -864,6 +872,39 @@ static int export_gates(const Layout& L, const msf_fusion_call* c, const WsBf16&
   return MSF_OK;
 }
 
+// Bias and gating-layer gradients that are (weighted) column sums of the head's outputs: classifier.0 bias (dH1),
+// the gating layers (ds, agg) and the out_proj biases (dS_q, the same sum for every key of query q).
+static int colsum_head(const Layout& L, const msf_fusion_call* c, const WsBf16& ws, cudaStream_t st, bool head_fused) {
+  const int64_t B = c->batch;
+  const int M = L.M, H = L.H, C = L.C;
+  const long long BH = (long long)B * H;
+  float* dW = c->grad_params;
+  Colsum16Problem cs[3 * MSF_MAX_MODALITIES + 2];
+  int nc = 0;
+  auto add = [&](const void* src, int f32, long long ld, int cols, const float* coef, int coef_ld, float* dst) {
+    Colsum16Problem p;
+    memset(&p, 0, sizeof(p));
+    p.src = src; p.src_f32 = f32; p.ld = ld; p.rows = (int)B; p.cols = cols;
+    p.coef = coef; p.coef_ld = coef_ld; p.dst = dst;
+    cs[nc++] = p;
+  };
+  if (!head_fused) add(c->grad_logits, 1, C, C, nullptr, 0, dW + L.cls_b2);
+  add(ws.dH1, 0, H, H, nullptr, 0, dW + L.cls_b1);
+  for (int q = 0; q < M; ++q) {
+    add(ws.agg + (long long)q * BH, 0, H, H, ws.ds + q, M, dW + L.gate_w[q]);   // d gate_w_q = sum_r ds[r,q] agg_q[r,:]
+    add(ws.ds + q, 1, M, 1, nullptr, 0, dW + L.gate_b[q]);
+    int nd = 0;
+    for (int k = 0; k < M; ++k) {
+      if (q == k || !L.has_pair(q, k)) continue;
+      float* dst = dW + L.pair_b(L.pair_index(q, k), 3);
+      if (nd == 0) add(ws.dS + (long long)q * BH, 0, H, H, nullptr, 0, dst);
+      else cs[nc - 1].dst_more[nd - 1] = dst;
+      ++nd;
+    }
+  }
+  return colsum16_launch(cs, nc, st);
+}
+
 static int backward_back(const Layout& L, const msf_fusion_call* c, const WsBf16& ws, const ArenaBf16& A,
                          cudaStream_t st, bool head_fused);
 
@@ -1029,35 +1070,28 @@ static int backward_back(const Layout& L, const msf_fusion_call* c, const WsBf16
     }
   }
 
-  // fork: the column sums only read activations that are complete at this point
+  // fork: the column sums only read activations that are complete at this point.  Those over the head's outputs
+  // were launched by the caller when the head is fused (colsum_head: they run under the chain kernel above).
   SideStream* side = nullptr;
   if ((rc = side_stream(&side))) return rc;
   MSF_CHECK_CUDA(cudaEventRecord(side->fork, st));
   MSF_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
-  // ---- bias and gating-layer gradients: (weighted) column sums ----
-  {
-    Colsum16Problem cs[2 * MSF_MAX_MODALITIES * MSF_MAX_MODALITIES + 4 * MSF_MAX_MODALITIES + 4];
+  if (!head_fused && (rc = colsum_head(L, c, ws, side->stream, false))) return rc;
+  {  // value_proj and projection biases: column sums of the chain's outputs
+    Colsum16Problem cs[MSF_MAX_MODALITIES * MSF_MAX_MODALITIES + MSF_MAX_MODALITIES];
     int nc = 0;
-    auto add = [&](const void* src, int f32, long long ld, int cols, const float* coef, int coef_ld, float* dst) {
+    auto add = [&](const bf16* src, float* dst) {
       Colsum16Problem p;
-      p.src = src; p.src_f32 = f32; p.ld = ld; p.rows = (int)B; p.cols = cols;
-      p.coef = coef; p.coef_ld = coef_ld; p.dst = dst;
+      memset(&p, 0, sizeof(p));
+      p.src = src; p.ld = H; p.rows = (int)B; p.cols = H; p.dst = dst;
       cs[nc++] = p;
     };
-    if (!head_fused) add(c->grad_logits, 1, C, C, nullptr, 0, dW + L.cls_b2);
-    add(ws.dH1, 0, H, H, nullptr, 0, dW + L.cls_b1);
     for (int q = 0; q < M; ++q) {
-      add(ws.agg + (long long)q * BH, 0, H, H, ws.ds + q, M, dW + L.gate_w[q]);   // d gate_w_q = sum_r ds[r,q] agg_q[r,:]
-      add(ws.ds + q, 1, M, 1, nullptr, 0, dW + L.gate_b[q]);
-      add(ws.dZ + (long long)q * BH, 0, H, H, nullptr, 0, dW + L.proj_b[q]);
-      for (int k = 0; k < M; ++k) {
-        if (q == k || !L.has_pair(q, k)) continue;
-        const int pi = L.pair_index(q, k);
-        add(ws.dS + (long long)q * BH, 0, H, H, nullptr, 0, dW + L.pair_b(pi, 3));
-        add(ws.dV + (long long)pi * BH, 0, H, H, nullptr, 0, dW + L.pair_b(pi, 2));
-      }
+      add(ws.dZ + (long long)q * BH, dW + L.proj_b[q]);
+      for (int k = 0; k < M; ++k)
+        if (q != k && L.has_pair(q, k)) add(ws.dV + (long long)L.pair_index(q, k) * BH, dW + L.pair_b(L.pair_index(q, k), 2));
     }
-    if ((rc = colsum16_launch(cs, nc, side->stream))) return rc;
+    if ((rc = colsum16_launch(cs, nc, side->stream, 1))) return rc;
   }
   // ---- all weight gradients: one MN-major launch, dW[out,in] = dY^T . X over the windows ----
   {
@@ -1159,6 +1193,13 @@ int fusion_bf16_train(const Layout& L, const msf_fusion_call* c, const int64_t* 
   hl.dlog = ws.dlog; hl.db2 = dW + L.cls_b2; hl.dS = ws.dS; hl.ds = ws.ds;
   if ((rc = launch_head(L, c, ws, A, hl, st, "HEAD gating+classifier+CE fwd/bwd"))) return rc;
   if ((rc = export_gates(L, c, ws, st))) return rc;
+  {  // the column sums over the head's outputs run beside the d-out -> d-value chain
+    SideStream* side = nullptr;
+    if ((rc = side_stream(&side))) return rc;
+    MSF_CHECK_CUDA(cudaEventRecord(side->fork2, st));
+    MSF_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork2, 0));
+    if ((rc = colsum_head(L, c, ws, side->stream, true))) return rc;
+  }
   return backward_back(L, c, ws, A, st, true);
 }
 

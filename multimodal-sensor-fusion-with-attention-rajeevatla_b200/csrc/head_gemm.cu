@@ -276,6 +276,7 @@ __device__ __forceinline__ void head_p5(const HeadLaunch& L, const HeadSmem& S, 
 __device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * HD_WORKERS) : "memory"); }
 
 __global__ void __launch_bounds__(HD_THREADS, 1) head_kernel(const __grid_constant__ HeadLaunch L) {
+  TL_KERNEL(0);
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t off0 = smem_u32(smem_raw);
   const uint32_t smem_base = (off0 + 1023u) & ~1023u;
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_kernel(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  pdl_wait();     // everything above (incl. the parameter rows, written >= 2 kernels ago) overlapped the previous kernel
+  pdl_wait();     TL_WAITED(0);  // everything above (incl. the parameter rows, written >= 2 kernels ago) overlapped the previous kernel
   pdl_launch();
 
   if (warp == 0) {

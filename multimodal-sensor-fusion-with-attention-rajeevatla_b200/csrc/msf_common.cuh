@@ -61,6 +61,73 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 bool pdl_enabled();
 
+// ---------------------------------------------------------------------------
+// Step timeline (debug builds only, -DMSF_TIMELINE): per kernel, the earliest CTA entry, the earliest / latest
+// return from pdl_wait() and the earliest / latest CTA end, in %globaltimer ns.  One table per translation
+// unit, registered with api.cu at load time; msf_debug_timeline() prints and clears them.
+// ---------------------------------------------------------------------------
+#ifdef MSF_TIMELINE
+static __device__ unsigned long long g_tl[4][8];
+static __device__ unsigned long long g_tl_cta[4][256];   // per CTA (grids of <= 256): end time << 8 | SM id
+__device__ __forceinline__ unsigned long long tl_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+struct TlScope {
+  int id;
+  __device__ __forceinline__ explicit TlScope(int i) : id(i) {
+    if (threadIdx.x == blockDim.x - 1 && threadIdx.y == 0) atomicMin(&g_tl[id][0], tl_now());
+  }
+  __device__ __forceinline__ ~TlScope() {
+    if (threadIdx.x == blockDim.x - 1 && threadIdx.y == 0) {
+      const unsigned long long t = tl_now();
+      atomicMin(&g_tl[id][3], t);
+      atomicMax(&g_tl[id][4], t);
+      atomicAdd(&g_tl[id][5], 1ull);
+      if (gridDim.x <= 256 && blockIdx.y == 0) {
+        unsigned int sm;
+        asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
+        g_tl_cta[id][blockIdx.x] = (t << 8) | (sm & 255u);
+      }
+    }
+  }
+};
+__device__ __forceinline__ void tl_waited(int id) {
+  if (threadIdx.x == blockDim.x - 1 && threadIdx.y == 0) {
+    const unsigned long long t = tl_now();
+    atomicMin(&g_tl[id][1], t);
+    atomicMax(&g_tl[id][2], t);
+  }
+}
+typedef int (*tl_dump_fn)(unsigned long long*, int);
+void tl_register(const char* tu, tl_dump_fn fn);
+static int tl_dump_local(unsigned long long* out, int reset) {
+  if (cudaMemcpyFromSymbol(out, g_tl, sizeof(unsigned long long) * 32) != cudaSuccess) return 1;
+  if (cudaMemcpyFromSymbol(out + 32, g_tl_cta, sizeof(unsigned long long) * 1024) != cudaSuccess) return 1;
+  if (reset) {
+    unsigned long long init[4][8];
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 8; ++j) init[i][j] = (j == 0 || j == 1 || j == 3) ? ~0ull : 0ull;
+    if (cudaMemcpyToSymbol(g_tl, init, sizeof(init)) != cudaSuccess) return 1;
+    static unsigned long long zeros[1024];
+    if (cudaMemcpyToSymbol(g_tl_cta, zeros, sizeof(zeros)) != cudaSuccess) return 1;
+  }
+  return 0;
+}
+namespace {
+struct TlRegistrar {
+  TlRegistrar() { tl_register(__BASE_FILE__, tl_dump_local); }
+};
+static TlRegistrar tl_registrar_instance;
+}  // namespace
+#define TL_KERNEL(id) TlScope tl_scope_(id)
+#define TL_WAITED(id) tl_waited(id)
+#else
+#define TL_KERNEL(id)
+#define TL_WAITED(id)
+#endif
+
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                                      Args&&... args) {

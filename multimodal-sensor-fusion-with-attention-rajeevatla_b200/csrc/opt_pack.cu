@@ -88,10 +88,12 @@ __global__ void __launch_bounds__(256, 4) opt_pack_kernel(const __grid_constant_
                                                           double* __restrict__ sq_norm,
                                                           unsigned long long* __restrict__ train_state,
                                                           bf16* __restrict__ arena) {
+  TL_KERNEL(0);
   __shared__ float tile[32][33];
   __shared__ double red[8];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   pdl_wait();
+  TL_WAITED(0);
   pdl_launch();
   unsigned long long dp_epoch = 0ull;
   double dp_total = 0.0;

@@ -34,6 +34,7 @@ __device__ long long g_proj_stamps[16];
 #define PJ_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 128) g_proj_stamps[i] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(PJ_THREADS, 1) proj_kernel(const __grid_constant__ ProjLaunch L) {
+  TL_KERNEL(0);
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t off0 = smem_u32(smem_raw);
   const uint32_t smem_base = (off0 + 1023u) & ~1023u;
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(PJ_THREADS, 1) proj_kernel(const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   pdl_wait();
+  TL_WAITED(0);
   pdl_launch();
   PJ_STAMP(1);
 

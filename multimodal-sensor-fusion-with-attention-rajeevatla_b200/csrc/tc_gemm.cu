@@ -359,6 +359,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiTile T, const float* bias
 // ---------------------------------------------------------------------------
 template <bool MN_MAJOR>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcLaunch L) {
+  TL_KERNEL(MN_MAJOR ? 1 : 0);
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // carve: [A stages][B stages][barriers][tmem base]
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  pdl_wait();     // prologue overlapped the previous kernel (programmatic dependent launch, msf_common.cuh)
+  pdl_wait();     TL_WAITED(MN_MAJOR ? 1 : 0);  // prologue overlapped the previous kernel (programmatic dependent launch, msf_common.cuh)
   pdl_launch();
 
   if (warp == 0) {
