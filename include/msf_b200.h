@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define MSF_ABI_VERSION 1
+#define MSF_ABI_VERSION 2
 #define MSF_MAX_MODALITIES 8
 
 enum {
@@ -93,6 +93,10 @@ typedef struct msf_fusion_call {
   const float* grad_logits;     /* (B, C)                                      */
   float* grad_params;           /* master layout, fully overwritten (dead q/k slots = 0) */
   float* grad_x[MSF_MAX_MODALITIES];   /* (B, D_m) or NULL                     */
+  double* grad_sq;              /* optional, msf_fusion_train_pass (fused BF16 path) only: receives the sum of
+                                   squares of grad_params as written (weight matrices: summed by the weight-gradient
+                                   GEMM's epilogue; bias / gating slots: by a small kernel beside it); see
+                                   MSF_OPT_NORM_GIVEN */
 } msf_fusion_call;
 
 /* ---- library ------------------------------------------------------------ */
@@ -144,6 +148,9 @@ int msf_fusion_backward(const msf_fusion_shape* shape, const msf_fusion_call* ca
 int msf_fusion_train_pass(const msf_fusion_shape* shape, const msf_fusion_call* call, const int64_t* labels,
                           float smoothing, float grad_scale, float* row_loss, float* loss_out,
                           float* grad_logits_scratch, int32_t flags, void* stream);
+/* 1 if msf_fusion_train_pass runs this shape / precision through the fused path (one head kernel, call->grad_sq
+ * honoured), 0 if it composes forward + cross-entropy + backward (call->grad_sq must then be NULL). */
+int msf_fusion_train_pass_is_fused(const msf_fusion_shape* shape, int32_t precision);
 /* Inference pass of src/eval.py:84-90: logits, then softmax -> max -> (confidence, prediction), with the
  * softmax fused into the classifier epilogue on the tensor-core path.
  * present_hint: 0, or the set of modalities (bit m) that call->mask marks present in EVERY row while all others
@@ -228,8 +235,12 @@ int msf_fusion_optimizer_step(const msf_fusion_shape* shape, float* params, cons
                               void* stream);
 /* The same step fused with what follows it in a bf16 training loop: every live parameter is updated, its
  * bf16 copy (and transposed copy) in the compute arena `params_bf16` rewritten from registers, and — if
- * advance_state != 0 — train_state {seed, offset, step} moved on by the last CTA (offset += 1, step += 1),
- * replacing msf_fusion_optimizer_step + msf_fusion_pack_bf16 + msf_train_state_advance. */
+ * advance_state & 1 — train_state {seed, offset, step} moved on by the last CTA (offset += 1, step += 1),
+ * replacing msf_fusion_optimizer_step + msf_fusion_pack_bf16 + msf_train_state_advance.
+ * advance_state & MSF_OPT_NORM_GIVEN: sq_norm points at TWO doubles and sq_norm[1] already holds the sum of
+ * squares of `grad` (msf_fusion_train_pass with call->grad_sq = sq_norm + 1 earlier on the same stream), so the
+ * pass over the gradient arena and its grid-wide barrier disappear.  sq_norm[0] receives the value used. */
+#define MSF_OPT_NORM_GIVEN 2
 int msf_fusion_optimizer_step_packed(const msf_fusion_shape* shape, float* params, const float* grad,
                                      float* exp_avg, float* exp_avg_sq, uint64_t* train_state, float lr,
                                      float beta1, float beta2, float eps, float weight_decay, float grad_scale,

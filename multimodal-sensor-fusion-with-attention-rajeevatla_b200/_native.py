@@ -10,7 +10,8 @@ from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int32, c_
 MSF_MAX_MODALITIES = 8
 MSF_PREC_F32, MSF_PREC_BF16 = 0, 1
 MSF_TRAIN_DEAD_SLOTS_ZERO = 1
-MSF_ABI_VERSION = 1
+MSF_OPT_NORM_GIVEN = 2
+MSF_ABI_VERSION = 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -52,6 +53,7 @@ class FusionCall(Structure):
         ("grad_logits", c_void_p),
         ("grad_params", c_void_p),
         ("grad_x", c_void_p * MSF_MAX_MODALITIES),
+        ("grad_sq", c_void_p),
     ]
 
 
@@ -92,6 +94,7 @@ PROTOTYPES = {
     "msf_fusion_backward": (c_int32, [POINTER(FusionShape), POINTER(FusionCall), c_void_p]),
     "msf_fusion_train_pass": (c_int32, [POINTER(FusionShape), POINTER(FusionCall), c_void_p, c_float, c_float,
                                         c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
+    "msf_fusion_train_pass_is_fused": (c_int32, [POINTER(FusionShape), c_int32]),
     "msf_fusion_infer_pass": (c_int32, [POINTER(FusionShape), POINTER(FusionCall), c_void_p, c_void_p, ctypes.c_uint32,
                                         c_void_p]),
     "msf_debug_head_stamps": (c_int32, [c_void_p]),

@@ -250,8 +250,8 @@ int msf_debug_timeline(char* buf, size_t cap, int reset) {
     for (int k = 0; k < 4; ++k) {
       if (t[k * 8 + 5] == 0) continue;
       const char* tu = strrchr(msf::tl_entries()[i].tu, '/');
-      int n = snprintf(buf + used, cap - used, "%s#%d\t%llu\t%llu\t%llu\t%llu\t%llu\t%llu\n", tu ? tu + 1 : msf::tl_entries()[i].tu,
-                       k, t[k * 8 + 0], t[k * 8 + 1], t[k * 8 + 2], t[k * 8 + 3], t[k * 8 + 4], t[k * 8 + 5]);
+      int n = snprintf(buf + used, cap - used, "%s#%d\t%llu\t%llu\t%llu\t%llu\t%llu\t%llu\t%llu\t%llu\n", tu ? tu + 1 : msf::tl_entries()[i].tu,
+                       k, t[k * 8 + 0], t[k * 8 + 1], t[k * 8 + 2], t[k * 8 + 3], t[k * 8 + 4], t[k * 8 + 5], t[k * 8 + 6], t[k * 8 + 7]);
       if (n < 0 || (size_t)n >= cap - used) return MSF_E_INVALID;
       used += (size_t)n;
       if (t[32 + k * 256] == 0) continue;

@@ -124,6 +124,7 @@ int msf_fusion_train_pass(const msf_fusion_shape* shape, const msf_fusion_call* 
   if (call->precision == MSF_PREC_BF16 && msf::fusion_bf16_head_fused(L))
     return msf::fusion_bf16_train(L, call, labels, smoothing, grad_scale, row_loss, loss_out, flags, (cudaStream_t)stream);
   // un-fused composition (fp32 parity path, shapes outside the head kernel): same three steps
+  MSF_REQUIRE(call->grad_sq == nullptr, "msf_fusion_train_pass: grad_sq needs the fused path (msf_fusion_train_pass_is_fused)");
   MSF_REQUIRE(grad_logits_scratch != nullptr, "msf_fusion_train_pass: this precision / shape needs grad_logits_scratch");
   if ((rc = msf_fusion_forward(shape, call, stream))) return rc;
   if ((rc = msf_cross_entropy(call->logits, labels, call->batch, L.C, smoothing, grad_scale, row_loss, loss_out,
@@ -132,6 +133,13 @@ int msf_fusion_train_pass(const msf_fusion_shape* shape, const msf_fusion_call* 
   msf_fusion_call back = *call;
   back.grad_logits = grad_logits_scratch;
   return msf_fusion_backward(shape, &back, stream);
+}
+
+int msf_fusion_train_pass_is_fused(const msf_fusion_shape* shape, int32_t precision) {
+  msf::Layout L;
+  int rc = msf::make_layout(shape, &L);
+  if (rc) return rc;
+  return (precision == MSF_PREC_BF16 && msf::fusion_bf16_head_fused(L)) ? 1 : 0;
 }
 
 int msf_fusion_infer_pass(const msf_fusion_shape* shape, const msf_fusion_call* call, float* conf, int64_t* pred,

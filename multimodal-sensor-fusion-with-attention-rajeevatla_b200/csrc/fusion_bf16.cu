@@ -507,6 +507,33 @@ __global__ void __launch_bounds__(256) colsum16_kernel(const __grid_constant__ C
   }
 }
 
+// sum of squares of the bias / gating-layer gradient slots -> msf_fusion_call.grad_sq (after the column sums
+// that fill them; the weight matrices' share comes from the weight-gradient GEMM's epilogue)
+struct VecSqList {
+  long long begin[2 * MSF_MAX_MODALITIES * MSF_MAX_MODALITIES + MSF_MAX_MODALITIES + 4];
+  int count[2 * MSF_MAX_MODALITIES * MSF_MAX_MODALITIES + MSF_MAX_MODALITIES + 4];
+  int n;
+};
+__global__ void __launch_bounds__(256) vec_sq_kernel(const __grid_constant__ VecSqList list, const float* __restrict__ g,
+                                                     double* __restrict__ sq_out) {
+  __shared__ double red[8];
+  const float* p = g + list.begin[blockIdx.x];
+  double sq = 0.0;
+  for (int e = threadIdx.x; e < list.count[blockIdx.x]; e += 256) {
+    const double x = (double)__ldcg(p + e);
+    sq += x * x;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    if (t != 0.0) atomicAdd(sq_out, t);
+  }
+}
+
 static int colsum16_launch(const Colsum16Problem* probs, int count, cudaStream_t st, int tag = 0) {
   int done = 0;
   while (done < count) {
@@ -1093,6 +1120,23 @@ static int backward_back(const Layout& L, const msf_fusion_call* c, const WsBf16
     }
     if ((rc = colsum16_launch(cs, nc, side->stream, 1))) return rc;
   }
+  if (head_fused && c->grad_sq != nullptr) {   // every bias / gating slot is complete on this stream now
+    VecSqList vl;
+    memset(&vl, 0, sizeof(vl));
+    auto seg = [&](long long begin, long long count) {
+      if (count > 0) { vl.begin[vl.n] = begin; vl.count[vl.n] = (int)count; ++vl.n; }
+    };
+    for (int m = 0; m < M; ++m) seg(L.proj_b[m], H);
+    for (int p = 0; p < pairs; ++p) {
+      seg(L.pair_b(p, 2), H);
+      seg(L.pair_b(p, 3), H);
+    }
+    seg(L.gate_w[0], L.cls_w1 - L.gate_w[0]);
+    seg(L.cls_b1, H);
+    seg(L.cls_b2, C);
+    vec_sq_kernel<<<vl.n, 256, 0, side->stream>>>(vl, dW, c->grad_sq);
+    MSF_LAUNCH_CHECK();
+  }
   // ---- all weight gradients: one MN-major launch, dW[out,in] = dY^T . X over the windows ----
   {
     const int bn = 128;
@@ -1112,6 +1156,7 @@ static int backward_back(const Layout& L, const msf_fusion_call* c, const WsBf16
       g.seg[0].b_map = bm; g.seg[0].b_z = bz;
       g.M = rows; g.N = cols; g.K = (int)B;
       g.C = dst; g.ldc = cols; g.c_bf16 = 0; g.epi = TC_EPI_STORE;
+      g.sq = head_fused ? c->grad_sq : nullptr;   // cleared by the head kernel of the same pass
       tb.add_problem(g);
     };
     wgrad(mapDlog, 0, mapHr, 0, C, H, dW + L.cls_w2);      // dW2 = dlogits^T Hr
@@ -1191,6 +1236,7 @@ int fusion_bf16_train(const Layout& L, const msf_fusion_call* c, const int64_t* 
   hl.labels = reinterpret_cast<const long long*>(labels);
   hl.smoothing = smoothing; hl.grad_scale = grad_scale; hl.row_loss = row_loss; hl.loss_out = loss_out;
   hl.dlog = ws.dlog; hl.db2 = dW + L.cls_b2; hl.dS = ws.dS; hl.ds = ws.ds;
+  hl.grad_sq = c->grad_sq;
   if ((rc = launch_head(L, c, ws, A, hl, st, "HEAD gating+classifier+CE fwd/bwd"))) return rc;
   if ((rc = export_gates(L, c, ws, st))) return rc;
   {  // the column sums over the head's outputs run beside the d-out -> d-value chain

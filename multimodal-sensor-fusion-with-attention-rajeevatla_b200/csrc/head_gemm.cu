@@ -351,6 +351,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_kernel(const __grid_consta
   const uint32_t tmem_base = *tmem_slot_ptr;
   pdl_wait();     TL_WAITED(0);  // everything above (incl. the parameter rows, written >= 2 kernels ago) overlapped the previous kernel
   pdl_launch();
+  if (L.grad_sq != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *L.grad_sq = 0.0;
 
   if (warp == 0) {
     // =========================== TMA producer ===========================

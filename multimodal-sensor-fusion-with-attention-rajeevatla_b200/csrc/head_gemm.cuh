@@ -49,6 +49,7 @@ struct HeadLaunch {
   float* loss_out;        // mean of row_loss (fixed-order reduction by the last CTA)
   __nv_bfloat16* dlog;    // (rows, Cp) bf16 d logits: operand of the classifier.3 weight gradient
   float* db2;             // += column sums of d logits
+  double* grad_sq;        // optional: cleared here for the weight-gradient GEMM later in the pass (msf_fusion_call.grad_sq)
   __nv_bfloat16* dS;      // [M][rows][H]
   float* ds;              // (rows, M) d loss / d gating score (operand of the gating-layer gradients)
   float inv_cnt[MSF_MAX_MODALITIES];

@@ -100,6 +100,9 @@ __device__ __forceinline__ void tl_waited(int id) {
     atomicMax(&g_tl[id][2], t);
   }
 }
+__device__ __forceinline__ void tl_mark(int id, int slot) {   // slot 6 or 7: latest time any CTA passed the mark
+  if (threadIdx.x == blockDim.x - 1 && threadIdx.y == 0) atomicMax(&g_tl[id][slot], tl_now());
+}
 typedef int (*tl_dump_fn)(unsigned long long*, int);
 void tl_register(const char* tu, tl_dump_fn fn);
 static int tl_dump_local(unsigned long long* out, int reset) {
@@ -123,9 +126,11 @@ static TlRegistrar tl_registrar_instance;
 }  // namespace
 #define TL_KERNEL(id) TlScope tl_scope_(id)
 #define TL_WAITED(id) tl_waited(id)
+#define TL_MARK(id, slot) tl_mark(id, slot)
 #else
 #define TL_KERNEL(id)
 #define TL_WAITED(id)
+#define TL_MARK(id, slot)
 #endif
 
 template <typename... KArgs, typename... Args>

@@ -34,7 +34,8 @@ struct OptList {
 struct OptCfg {
   float lr, beta1, beta2, eps, wd, grad_scale, max_norm;
   int advance;
-  int fold_norm;   // compute the gradient norm in this launch (needs all CTAs resident: grid barrier)
+  int fold_norm;   // 1: compute the gradient norm in this launch (needs all CTAs resident: grid barrier);
+                   // 2: sq_norm[1] already holds it (MSF_OPT_NORM_GIVEN): no norm phase, no barrier
   // data-parallel mode (after dp_reduce_kernel): the gradient is this rank's reduced arena, filled by peer
   // writes; wait for every rank's "slice reduced" flag, form the norm from the published partials and close
   // the communicator epoch at the end
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(256, 4) opt_pack_kernel(const __grid_constant_
       dp_total += __longlong_as_double((long long)ld_acquire_sys(c.dp_sig + SIG_NORM + r));
   }
 
-  if (!DP && c.fold_norm) {  // ---- phase 1: sum of g^2 over the live slots (dead slots hold exact zeros) ----
+  if (!DP && c.fold_norm == 1) {  // ---- phase 1: sum of g^2 over the live slots (dead slots hold exact zeros) ----
     double sq = 0.0;
     for (int unit = blockIdx.x; unit < list.total_units; unit += gridDim.x) {
       int ji = 0;
@@ -145,11 +146,15 @@ __global__ void __launch_bounds__(256, 4) opt_pack_kernel(const __grid_constant_
       for (int i = 0; i < 8; ++i) t += red[i];
       if (t != 0.0) atomicAdd(&g_opt_sq, t);
     }
+    TL_MARK(0, 6);   // norm phase done (before the barrier)
     opt_grid_barrier();
+    TL_MARK(0, 7);
   }
 
   // ---- phase 2: clip + AdamW + bf16 copies ----
-  const double sq_total = DP ? dp_total : (c.fold_norm ? *reinterpret_cast<volatile double*>(&g_opt_sq) : *sq_norm);
+  const double sq_total = DP ? dp_total
+                             : c.fold_norm == 2 ? __ldcg(sq_norm + 1)
+                             : c.fold_norm == 1 ? *reinterpret_cast<volatile double*>(&g_opt_sq) : *sq_norm;
   __shared__ AdamConsts ks;
   if (threadIdx.x == 0) {   // two fp64 pow() per CTA instead of per thread
     const double step = (double)train_state[2];
@@ -277,10 +282,12 @@ __global__ void __launch_bounds__(256, 4) opt_pack_kernel(const __grid_constant_
         if (sq_norm != nullptr) *sq_norm = sq_total;
         c.dp_sig[SIG_EPOCH] = dp_epoch;
         c.dp_sig[SIG_TIME + 5] = gtime();
-      } else if (c.fold_norm) {
+      } else if (c.fold_norm == 1) {
         *sq_norm = sq_total;
         g_opt_sq = 0.0;
         g_opt_barrier = 0;
+      } else if (c.fold_norm == 2) {
+        *sq_norm = sq_total;
       }
       if (c.advance) {   // {seed, offset + 1, step + 1}
         train_state[1] += 1ull;
@@ -342,8 +349,10 @@ static int build_jobs(const Layout& L, OptList& list) {
 
 int fusion_bf16_opt_pack(const Layout& L, float* params, const float* grad, float* exp_avg, float* exp_avg_sq,
                          uint64_t* train_state, float lr, float beta1, float beta2, float eps, float wd,
-                         float grad_scale, float max_norm, double* sq_norm, void* arena_v, int advance,
+                         float grad_scale, float max_norm, double* sq_norm, void* arena_v, int flags,
                          cudaStream_t st) {
+  const int advance = flags & 1;
+  const bool given = (flags & MSF_OPT_NORM_GIVEN) != 0;
   OptList list;
   int rc0 = build_jobs(L, list);
   if (rc0) return rc0;
@@ -357,10 +366,10 @@ int fusion_bf16_opt_pack(const Layout& L, float* params, const float* grad, floa
     MSF_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, opt_pack_kernel<false>, 256, 0));
     resident = sms * per_sm;
   }
-  const bool fold = resident >= 148 && !getenv("MSF_OPT_TWO_PASS");
+  const bool fold = given || (resident >= 148 && !getenv("MSF_OPT_TWO_PASS"));
   int rc = MSF_OK;
   if (!fold && (rc = fusion_live_sq_norm(L, grad, sq_norm, st))) return rc;
-  OptCfg c{lr, beta1, beta2, eps, wd, grad_scale, max_norm, advance, fold ? 1 : 0, nullptr, 0};
+  OptCfg c{lr, beta1, beta2, eps, wd, grad_scale, max_norm, advance, given ? 2 : fold ? 1 : 0, nullptr, 0};
   int grid = list.total_units < 1184 ? list.total_units : 1184;
   if (fold && grid > resident) grid = resident;
   MSF_CHECK_CUDA(launch_pdl(opt_pack_kernel<false>, dim3(grid), dim3(256), 0, st, list, c, params, grad, exp_avg,

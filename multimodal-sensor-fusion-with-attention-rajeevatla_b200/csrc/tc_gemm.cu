@@ -65,6 +65,7 @@ struct EpiTile {
   float* cell;
   float* h32;
   long long h_slice;
+  double* sq;
 };
 
 // 16 consecutive bf16 of one row, raw (two 16-byte loads) or zero when out of range.
@@ -206,6 +207,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiTile T, const float* bias
 
   int cur_head = -1;
   float cur_gate = 0.0f;
+  float sq = 0.0f;   // TC_EPI_STORE with T.sq: sum of squares of this thread's stored values
 #pragma unroll 1
   for (int g = 0;; ++g) {
     const int c = group_col(g);
@@ -300,6 +302,11 @@ __device__ __forceinline__ void epilogue_tile(const EpiTile T, const float* bias
       else r = a * mrow * dm[j];  // TC_EPI_DX
       v[j] = r;
     }
+    if (EPI == TC_EPI_STORE && T.sq != nullptr && row_ok) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j < gcols) sq = fmaf(v[j], v[j], sq);
+    }
 
     // results go to this warp's shared-memory staging rows first (row pitch padded by 16 B: conflict-free)
     {
@@ -319,6 +326,13 @@ __device__ __forceinline__ void epilogue_tile(const EpiTile T, const float* bias
           reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
       }
     }
+  }
+
+  if (EPI == TC_EPI_STORE && T.sq != nullptr) {   // one fp64 atomic per warp and tile
+    double s = (double)sq;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0 && s != 0.0) atomicAdd(T.sq, s);
   }
 
   // flush: the warp walks its 32 x (col_end - col_begin) block row by row, 16 bytes per lane, so every
@@ -498,7 +512,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       T.head_dim = P.head_dim; T.heads = P.heads; T.site = P.site; T.sub = P.sub; T.scale = P.scale;
       T.C = P.C; T.ldc = P.ldc; T.aux = P.aux; T.ld_aux = P.ld_aux; T.aux2 = P.aux2; T.ld_aux2 = P.ld_aux2;
       T.gate_out = P.gate_out; T.gate_in = P.gate_in; T.dbg = L.dbg;
-      T.cell = P.cell; T.h32 = P.h32; T.h_slice = P.h_slice;
+      T.cell = P.cell; T.h32 = P.h32; T.h_slice = P.h_slice; T.sq = P.sq;
       const bool has_acc = P.K > 0;
       const int acc = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);

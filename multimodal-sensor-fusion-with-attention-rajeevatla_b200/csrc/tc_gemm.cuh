@@ -72,6 +72,9 @@ struct TcProblem {
   float* cell;
   float* h32;
   long long h_slice;
+  // TC_EPI_STORE: if set, the sum of squares of everything this problem stores is added here (the weight-gradient
+  // GEMM hands the optimizer its share of the gradient norm)
+  double* sq;
 };
 
 struct TcLaunch {

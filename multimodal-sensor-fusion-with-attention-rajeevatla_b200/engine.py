@@ -94,7 +94,7 @@ class FusionEngine:
         self.dlogits = torch.zeros(B, plan.C, **f32)
         self.row_loss = torch.zeros(B, **f32)
         self.loss = torch.zeros(1, **f32)
-        self.sq_norm = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.sq_norm = torch.zeros(2, dtype=torch.float64, device=dev)   # [used by the optimizer, from the pass]
         self.conf = torch.zeros(B, **f32)
         self.pred = torch.zeros(B, dtype=torch.int64, device=dev)
         # {seed, offset, step}; step is 1-based when the optimizer kernel reads it
@@ -128,6 +128,12 @@ class FusionEngine:
         # GLOBAL batch: each rank scales by 1/(B*world), the gradient exchange sums.
         c = self._call(True, slot)
         c.logits, c.grad_params = self.logits.data_ptr(), self.grad.data_ptr()
+        # single GPU, fused pass: the kernels that write the gradients also sum their squares, so the optimizer
+        # launch needs no pass over the gradient arena before it can clip (MSF_OPT_NORM_GIVEN)
+        norm_given = (self.world == 1 and self.arena_bf16 is not None
+                     and lib.msf_fusion_train_pass_is_fused(ctypes_ref(self.plan.shape), self.prec) == 1)
+        if norm_given:
+            c.grad_sq = self.sq_norm.data_ptr() + 8
         N.check(lib.msf_fusion_train_pass(ctypes_ref(self.plan.shape), ctypes_ref(c),
                                           self._slots[slot][2].data_ptr(), self.smoothing,
                                           1.0 / (self.batch * self.world), self.row_loss.data_ptr(),
@@ -145,14 +151,14 @@ class FusionEngine:
                 return
             N.check(lib.msf_dp_optimizer_step(*args, st))
         else:
-            if self._nccl_step(lib, st):
+            if self._nccl_step(lib, st, norm_given):
                 return   # optimizer, bf16 re-pack and state advance were one launch
         if self.arena_bf16 is not None:
             N.check(lib.msf_fusion_pack_bf16(ctypes_ref(self.plan.shape), self.arena.data_ptr(),
                                              self.arena_bf16.data_ptr(), st))
         N.check(lib.msf_train_state_advance(self.state.data_ptr(), st))
 
-    def _nccl_step(self, lib, st) -> bool:
+    def _nccl_step(self, lib, st, norm_given: bool = False) -> bool:
         if self.world > 1:
             self._all_reduce_gradients()
         if self.arena_bf16 is not None:
@@ -160,7 +166,8 @@ class FusionEngine:
             N.check(lib.msf_fusion_optimizer_step_packed(
                 ctypes_ref(self.plan.shape), self.arena.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
                 self.exp_avg_sq.data_ptr(), self.state.data_ptr(), self.lr, self.betas[0], self.betas[1], self.eps,
-                self.wd, 1.0, self.max_norm, self.sq_norm.data_ptr(), self.arena_bf16.data_ptr(), 1, st))
+                self.wd, 1.0, self.max_norm, self.sq_norm.data_ptr(), self.arena_bf16.data_ptr(),
+                1 | (N.MSF_OPT_NORM_GIVEN if norm_given else 0), st))
             return True
         # global-norm clip + AdamW, skipping the dead q/k slots' moments (their gradients are exact zeros)
         N.check(lib.msf_fusion_optimizer_step(ctypes_ref(self.plan.shape), self.arena.data_ptr(),

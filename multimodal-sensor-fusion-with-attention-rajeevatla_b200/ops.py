@@ -214,9 +214,11 @@ def fusion_train_pass_raw(plan: FusionPlan, arena: torch.Tensor, xs: Sequence[to
                           mask: Optional[torch.Tensor], labels: torch.Tensor, *, smoothing: float = 0.0,
                           grad_scale: Optional[float] = None, precision: int = N.MSF_PREC_F32,
                           training: bool = True, p: float = 0.0, seed: int = 0, offset: int = 0,
-                          arena_bf16: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None):
+                          arena_bf16: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None,
+                          grad_sq: Optional[torch.Tensor] = None):
     """One msf_fusion_train_pass call: forward + CE(label smoothing) + backward.
-    Returns ``(logits, loss[1], grad_arena, fusion_weights, gates)``."""
+    Returns ``(logits, loss[1], grad_arena, fusion_weights, gates)``.  ``grad_sq`` (float64[1], fused path only)
+    receives the sum of squares of the gradient arena."""
     dev = arena.device
     B = xs[0].shape[0]
     if workspace is None:
@@ -232,6 +234,7 @@ def fusion_train_pass_raw(plan: FusionPlan, arena: torch.Tensor, xs: Sequence[to
     call = _make_call(plan, B, precision, training, p, seed, offset, arena, arena_bf16, xs, mask, workspace)
     call.logits, call.grad_params = _p(logits), _p(grad)
     call.fusion_weights, call.attn_gates = _p(fw), _p(gates)
+    call.grad_sq = _p(grad_sq)
     labels = labels.to(torch.int64).contiguous()
     scale = (1.0 / B) if grad_scale is None else grad_scale
     N.check(N.lib().msf_fusion_train_pass(ctypes.byref(plan.shape), ctypes.byref(call), _p(labels),
@@ -498,14 +501,19 @@ def fusion_optimizer_step(plan: FusionPlan, params, grad, exp_avg, exp_avg_sq, t
 def fusion_optimizer_step_packed(plan: FusionPlan, params, grad, exp_avg, exp_avg_sq, train_state, arena_bf16,
                                  lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-4, grad_scale=1.0,
                                  max_norm=0.0, sq_norm: Optional[torch.Tensor] = None,
-                                 advance: bool = True) -> torch.Tensor:
+                                 advance: bool = True, norm_given: bool = False) -> torch.Tensor:
     """``fusion_optimizer_step`` fused with the bf16 re-pack of the compute arena and the advance of
-    ``train_state`` (one launch instead of three)."""
+    ``train_state`` (one launch instead of three).  ``norm_given``: ``sq_norm`` is float64[2] and ``sq_norm[1]``
+    already holds the gradient square norm (``fusion_train_pass_raw(grad_sq=
+    sq_norm[1:])``), see MSF_OPT_NORM_GIVEN."""
     if sq_norm is None:
-        sq_norm = torch.zeros(1, dtype=torch.float64, device=params.device)
+        sq_norm = torch.zeros(2 if norm_given else 1, dtype=torch.float64, device=params.device)
+    if norm_given and sq_norm.numel() < 2:
+        raise ValueError("norm_given needs sq_norm with two elements")
     N.check(N.lib().msf_fusion_optimizer_step_packed(
         ctypes.byref(plan.shape), _p(params), _p(grad), _p(exp_avg), _p(exp_avg_sq), _p(train_state), lr, beta1,
-        beta2, eps, weight_decay, grad_scale, max_norm, _p(sq_norm), _p(arena_bf16), int(advance), _stream()))
+        beta2, eps, weight_decay, grad_scale, max_norm, _p(sq_norm), _p(arena_bf16),
+        int(advance) | (N.MSF_OPT_NORM_GIVEN if norm_given else 0), _stream()))
     return sq_norm
 
 

@@ -23,7 +23,7 @@ torch.cuda.synchronize()
 lib = pkg.lib()
 lib.msf_debug_timeline.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int]
 lib.msf_debug_timeline.restype = ctypes.c_int
-buf = ctypes.create_string_buffer(1 << 14)
+buf = ctypes.create_string_buffer(1 << 18)
 ORDER = ["proj_gemm.cu#0", "chain2_gemm.cu#0", "head_gemm.cu#0", "fusion_bf16.cu#0", "chain2_gemm.cu#1", "fusion_bf16.cu#1", "tc_gemm.cu#1",
          "opt_pack.cu#0"]
 for rep in range(3):
@@ -32,19 +32,30 @@ for rep in range(3):
     torch.cuda.synchronize()
     N.check(lib.msf_debug_timeline(buf, len(buf), 1))
     rows = {}
+    ctas = {}
     for line in buf.value.decode().splitlines():
         name, *v = line.split("\t")
-        rows[name] = [int(x) for x in v]
+        if name.endswith(".cta"):
+            ctas[name[:-4]] = [tuple(int(y) for y in x.split(":")) for x in v]
+        else:
+            rows[name] = [int(x) for x in v]
     t0 = min(v[0] for v in rows.values())
     print(f"--- step {rep}: kernel, CTAs | first entry | pdl_wait returned first..last | CTA end first..last (us)")
     prev_end = None
     for name in ORDER + sorted(set(rows) - set(ORDER)):
         if name not in rows:
             continue
-        e, w0, w1, d0, d1, n = rows[name]
+        e, w0, w1, d0, d1, n, k6, k7 = rows[name]
         us = lambda t: (t - t0) / 1e3
         waited = f"{us(w0):7.1f}..{us(w1):7.1f}" if w1 else "      (no wait)  "
         gap = "" if prev_end is None or not w1 else f"  wait-return after predecessor's last end: {us(w0) - prev_end:+.1f}"
         print(f"{name:20s} {n:4d} | {us(e):7.1f} | {waited} | {us(d0):7.1f}..{us(d1):7.1f}{gap}")
+        if k6 or k7:
+            print(f"{'':20s}      marks: {us(k6):7.1f} {us(k7):7.1f}")
         if not name.startswith("fusion_bf16.cu"):
             prev_end = us(d1)
+    if rep == 2:   # per-CTA end times of the last step: block index (SM id) in order of completion
+        for name in ORDER:
+            if name in ctas:
+                order = sorted(range(len(ctas[name])), key=lambda b: ctas[name][b][0])
+                print(name, "ends:", " ".join(f"{b}({ctas[name][b][1]}):{(ctas[name][b][0] - t0) / 1e3:.1f}" for b in order))

@@ -185,11 +185,12 @@ def test_packed_optimizer_step_equals_step_plus_pack():
     for key, off, shape in plan.slots:   # dead query/key slots carry exact-zero gradients
         if ".query_proj." in key or ".key_proj." in key:
             gr[off:off + int(np.prod(shape))] = 0.0
-    pb = pa.clone()
-    ma, va, mb, vb = (torch.zeros_like(pa) for _ in range(4))
+    pb, pc = pa.clone(), pa.clone()
+    ma, va, mb, vb, mc, vc = (torch.zeros_like(pa) for _ in range(6))
     sa = torch.tensor([7, 3, 1], dtype=torch.int64, device="cuda")
-    sb = sa.clone()
+    sb, sc = sa.clone(), sa.clone()
     a16 = plan.pack_bf16(pa)
+    c16 = a16.clone()
     for step in range(3):
         gstep = gr * (1.0 + 0.25 * step)
         ops.fusion_optimizer_step(plan, pa, gstep, ma, va, sa, lr=1e-3, weight_decay=1e-4, max_norm=1.0)
@@ -201,3 +202,14 @@ def test_packed_optimizer_step_equals_step_plus_pack():
         assert float((va - vb).abs().max()) <= 1e-12
         assert torch.equal(plan.pack_bf16(pb).view(torch.int16), a16.view(torch.int16))
         assert torch.equal(sa, sb)
+        # MSF_OPT_NORM_GIVEN: the square norm comes in through sq_norm[1] (in the train step the pass that wrote
+        # the gradients puts it there) and the launch has no norm phase
+        sq2 = torch.zeros(2, dtype=torch.float64, device="cuda")
+        sq2[1] = (gstep.double() ** 2).sum()
+        ops.fusion_optimizer_step_packed(plan, pc, gstep, mc, vc, sc, c16, lr=1e-3, weight_decay=1e-4, max_norm=1.0,
+                                         sq_norm=sq2, norm_given=True)
+        assert abs(float(sq2[0]) - float(sq)) <= 1e-9 * float(sq)
+        assert float((pb - pc).abs().max()) <= 1e-7 and float((mb - mc).abs().max()) <= 1e-9
+        assert float((vb - vc).abs().max()) <= 1e-12
+        assert torch.equal(plan.pack_bf16(pc).view(torch.int16), c16.view(torch.int16))
+        assert torch.equal(sb, sc)

@@ -199,6 +199,23 @@ def test_engine_bf16_tracks_fp32_engine():
     assert float((params["fp32"] - params["bf16"]).abs().max()) <= 6.1e-3  # 3 Adam steps of lr 1e-3: sign flips of ~0 grads
 
 
+def test_engine_step_clips_with_the_norm_of_its_own_gradients():
+    """Inside the captured train step the optimizer takes the gradient square norm from the pass that wrote the
+    gradients (msf_fusion_call.grad_sq -> MSF_OPT_NORM_GIVEN): after every step, what it used (sq_norm[0]) is the
+    square norm of the gradient arena, on resident batches and across graph replays."""
+    pkg = load_pkg()
+    engine = importlib.import_module(pkg.__name__ + ".engine")
+    model, feats, mask, labels = seeded_case(PAMAP2, 256, 4, 25, 512, seed=33, device="cuda")
+    eng = engine.FusionEngine(model, 512, precision="bf16", seed=5, use_graph=True, max_grad_norm=0.05)
+    eng.load_batch(feats, mask, labels)
+    for _ in range(6):
+        eng.train_step_resident()
+        torch.cuda.synchronize()
+        want = float((eng.grad.double() ** 2).sum())
+        assert want > 0.05 ** 2          # the clip is active
+        assert abs(float(eng.sq_norm[0]) - want) <= 1e-5 * want, (float(eng.sq_norm[0]), float(eng.sq_norm[1]), want)
+
+
 def test_train_stream_pipeline_equals_step_by_step():
     """The 2-slot pipelined host-facing loop (H2D of batch i+1 overlapping step i, loss read one step late)
     follows the blocking load_batch + train_step loop (bias gradients are fp32 atomic column sums, so two

@@ -248,3 +248,24 @@ def test_multi_tile_per_cta_train_pass(monkeypatch):
     scale = float(grad2.abs().max())
     assert float((grad - grad2).abs().max()) <= 2e-3 * scale + 1e-7
     assert float((grad - grad2).norm()) <= 2e-2 * float(grad2.norm())
+
+
+@pytest.mark.parametrize("batch", [384, 4096])
+def test_train_pass_reports_gradient_square_norm(batch):
+    """msf_fusion_call.grad_sq: the pass adds up the squares of everything it writes to grad_params (the weight
+    matrices in the weight-gradient GEMM's epilogue, the bias / gating slots in a small kernel beside it), so the
+    optimizer launch can clip without a pass over the arena (MSF_OPT_NORM_GIVEN).  The value is re-zeroed by every
+    pass, and an un-fused shape / precision refuses the request."""
+    ops, N, model, plan, arena, arena16, xs, mask, labels = _setup(batch, seed=9)
+    kw = dict(precision=N.MSF_PREC_BF16, training=True, p=0.1, seed=11, offset=3, arena_bf16=arena16)
+    sq = torch.full((1,), 123.0, dtype=torch.float64, device="cuda")   # stale content must not leak in
+    for _ in range(2):
+        _, _, grad, _, _ = ops.fusion_train_pass_raw(plan, arena, xs, mask, labels, smoothing=0.05, grad_sq=sq, **kw)
+    want = float((grad.double() ** 2).sum())
+    assert want > 0.0
+    assert abs(float(sq) - want) <= 1e-5 * want, (float(sq), want)   # fp32 partial sums per thread, fp64 across
+    assert N.lib().msf_fusion_train_pass_is_fused(plan.shape, N.MSF_PREC_BF16) == 1
+    assert N.lib().msf_fusion_train_pass_is_fused(plan.shape, N.MSF_PREC_F32) == 0
+    with pytest.raises(N.MsfError):
+        ops.fusion_train_pass_raw(plan, arena, xs, mask, labels, smoothing=0.05, grad_sq=sq,
+                                  precision=N.MSF_PREC_F32, training=False)
