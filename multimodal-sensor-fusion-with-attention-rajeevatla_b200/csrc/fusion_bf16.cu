@@ -534,6 +534,22 @@ __global__ void __launch_bounds__(256) vec_sq_kernel(const __grid_constant__ Vec
   }
 }
 
+// mean of the per-window losses in a fixed order (deterministic): one block beside the backward chain instead of a
+// serial tail on the head kernel's last CTA
+__global__ void __launch_bounds__(256) loss_mean_kernel(const float* __restrict__ row_loss, long long rows,
+                                                        float* __restrict__ loss_out) {
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < rows; i += 256) s += (double)__ldcg(row_loss + i);
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss_out[0] = (float)(sh[0] / (double)rows);
+}
+
 static int colsum16_launch(const Colsum16Problem* probs, int count, cudaStream_t st, int tag = 0) {
   int done = 0;
   while (done < count) {
@@ -553,9 +569,23 @@ static int colsum16_launch(const Colsum16Problem* probs, int count, cudaStream_t
     if (rpb < 64) rpb = 64;
     list.rows_per_block = rpb;
     if (max_rows > 0) {
-      dim3 grid((unsigned)ceil_div(max_rows, rpb), (unsigned)n);
-      colsum16_kernel<<<grid, 256, 0, st>>>(list);
-      MSF_LAUNCH_CHECK();
+      // Highest launch priority: the block scheduler hands out grids of one priority in launch order, and the
+      // tensor-core kernel launched ahead of this one (programmatic dependent launch) has blocks waiting for SMs its
+      // predecessor still holds -- without the priority these small blocks queue behind them instead of running
+      // on the idle SMs.  Set per launch so it also holds for the kernel node of a captured graph.
+      int least = 0, greatest = 0;
+      MSF_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+      cudaLaunchAttribute attr;
+      attr.id = cudaLaunchAttributePriority;
+      attr.val.priority = greatest;
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3((unsigned)ceil_div(max_rows, rpb), (unsigned)n);
+      cfg.blockDim = dim3(256);
+      cfg.stream = st;
+      cfg.attrs = &attr;
+      cfg.numAttrs = 1;
+      MSF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, colsum16_kernel, list));
     }
     done += n;
   }
@@ -585,7 +615,9 @@ static int side_stream(SideStream** out) {
   MSF_CHECK_CUDA(cudaGetDevice(&dev));
   MSF_REQUIRE(dev >= 0 && dev < 16, "device index %d out of range", dev);
   if (!made[dev]) {
-    MSF_CHECK_CUDA(cudaStreamCreateWithFlags(&cache[dev].stream, cudaStreamNonBlocking));
+    int least = 0, greatest = 0;   // see colsum16_launch: the side work must not queue behind pending tensor-core blocks
+    MSF_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    MSF_CHECK_CUDA(cudaStreamCreateWithPriority(&cache[dev].stream, cudaStreamNonBlocking, greatest));
     MSF_CHECK_CUDA(cudaEventCreateWithFlags(&cache[dev].fork, cudaEventDisableTiming));
     MSF_CHECK_CUDA(cudaEventCreateWithFlags(&cache[dev].fork2, cudaEventDisableTiming));
     MSF_CHECK_CUDA(cudaEventCreateWithFlags(&cache[dev].join, cudaEventDisableTiming));
@@ -1234,7 +1266,8 @@ int fusion_bf16_train(const Layout& L, const msf_fusion_call* c, const int64_t* 
   memset(&hl, 0, sizeof(hl));
   hl.train = 1; hl.store_acts = 1;
   hl.labels = reinterpret_cast<const long long*>(labels);
-  hl.smoothing = smoothing; hl.grad_scale = grad_scale; hl.row_loss = row_loss; hl.loss_out = loss_out;
+  hl.smoothing = smoothing; hl.grad_scale = grad_scale; hl.row_loss = row_loss;
+  hl.loss_out = nullptr;   // the mean is formed on the side stream below
   hl.dlog = ws.dlog; hl.db2 = dW + L.cls_b2; hl.dS = ws.dS; hl.ds = ws.ds;
   hl.grad_sq = c->grad_sq;
   if ((rc = launch_head(L, c, ws, A, hl, st, "HEAD gating+classifier+CE fwd/bwd"))) return rc;
@@ -1244,6 +1277,10 @@ int fusion_bf16_train(const Layout& L, const msf_fusion_call* c, const int64_t* 
     if ((rc = side_stream(&side))) return rc;
     MSF_CHECK_CUDA(cudaEventRecord(side->fork2, st));
     MSF_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork2, 0));
+    if (loss_out != nullptr) {
+      loss_mean_kernel<<<1, 256, 0, side->stream>>>(row_loss, c->batch, loss_out);
+      MSF_LAUNCH_CHECK();
+    }
     if ((rc = colsum_head(L, c, ws, side->stream, true))) return rc;
   }
   return backward_back(L, c, ws, A, st, true);

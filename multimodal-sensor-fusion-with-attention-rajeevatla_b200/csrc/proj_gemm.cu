@@ -35,6 +35,28 @@ __device__ long long g_proj_stamps[16];
 
 __global__ void __launch_bounds__(PJ_THREADS, 1) proj_kernel(const __grid_constant__ ProjLaunch L) {
   TL_KERNEL(0);
+  // The last L.zero_ctas CTAs of the grid only clear the gradient slots this train pass accumulates into: walking
+  // the range table costs microseconds of dependent constant-bank misses, which these CTAs spend on otherwise
+  // idle SMs while the others work.  Chunks of 4096 floats are dealt round-robin.
+  const int nwork = (int)gridDim.x - L.zero_ctas;
+  if ((int)blockIdx.x >= nwork) {
+    pdl_wait();     // the previous step's optimizer still reads these slots
+    pdl_launch();
+    const int me = (int)blockIdx.x - nwork;
+    int chunk = 0;
+    for (int i = 0; i < L.nzero; ++i) {
+      const ProjZeroRange R = L.zero[i];
+      const int per = (int)((R.count + 4095) >> 12);
+      for (int b = 0; b < R.batch; ++b)
+        for (int j = 0; j < per; ++j, ++chunk) {
+          if (chunk % L.zero_ctas != me) continue;
+          float* p = L.zero_base + R.begin + (long long)b * R.stride + ((long long)j << 12);
+          const int n = (int)min((long long)4096, R.count - ((long long)j << 12));
+          for (int e = threadIdx.x; e < n; e += PJ_THREADS) p[e] = 0.0f;
+        }
+    }
+    return;
+  }
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t off0 = smem_u32(smem_raw);
   const uint32_t smem_base = (off0 + 1023u) & ~1023u;
@@ -97,7 +119,7 @@ __global__ void __launch_bounds__(PJ_THREADS, 1) proj_kernel(const __grid_consta
     // =========================== TMA producer ===========================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int item = blockIdx.x; item < L.items; item += gridDim.x) {
+      for (int item = blockIdx.x; item < L.items; item += nwork) {
         const int m = L.active[item % L.n_active], KB = L.D[m] >> 6, m0 = (item / L.n_active) * 128;
         const uint32_t it_cur = it++;
         if (it_cur > 0) mbar_wait(tile_done, (it_cur - 1) & 1u);   // the staging tile in the weight area has been stored
@@ -118,7 +140,7 @@ __global__ void __launch_bounds__(PJ_THREADS, 1) proj_kernel(const __grid_consta
     if (lane == 0) {
       const uint32_t idesc = instr_desc(H, false, false);
       uint32_t it = 0;
-      for (int item = blockIdx.x; item < L.items; item += gridDim.x) {
+      for (int item = blockIdx.x; item < L.items; item += nwork) {
         const int KB = L.D[L.active[item % L.n_active]] >> 6;
         const uint32_t it_cur = it++;
         mbar_wait(w_full, it_cur & 1u);
@@ -136,7 +158,7 @@ __global__ void __launch_bounds__(PJ_THREADS, 1) proj_kernel(const __grid_consta
     // =========================== TMA store ==============================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int item = blockIdx.x; item < L.items; item += gridDim.x) {
+      for (int item = blockIdx.x; item < L.items; item += nwork) {
         const int m = L.active[item % L.n_active], m0 = (item / L.n_active) * 128, KB = L.D[m] >> 6;
         const uint32_t it_cur = it++;
         mbar_wait(a_ready, it_cur & 1u);
@@ -159,19 +181,8 @@ __global__ void __launch_bounds__(PJ_THREADS, 1) proj_kernel(const __grid_consta
     const int half = H >> 1, c_begin = cg * half;
     const uint32_t lane_base = (uint32_t)(lq * 32) << 16;
 
-    // gradient slots cleared by the first kernel of a train pass (a slice of the grid: the ranges are small)
-    if (L.nzero > 0 && blockIdx.x < 64) {
-      const long long nthreads = (long long)(gridDim.x < 64 ? gridDim.x : 64) * (32 * PJ_WORKERS);
-      const long long tid = blockIdx.x * (long long)(32 * PJ_WORKERS) + et;
-      for (int i = 0; i < L.nzero; ++i)
-        for (int b = 0; b < L.zero[i].batch; ++b) {
-          float* p = L.zero_base + L.zero[i].begin + (long long)b * L.zero[i].stride;
-          for (long long e = tid; e < L.zero[i].count; e += nthreads) p[e] = 0.0f;
-        }
-    }
-
     uint32_t it_next = 0;
-    for (int item = blockIdx.x; item < L.items; item += gridDim.x) {
+    for (int item = blockIdx.x; item < L.items; item += nwork) {
       const int m = L.active[item % L.n_active], m0 = (item / L.n_active) * 128, D = L.D[m], c8n = D >> 3;
       const uint32_t it = it_next++;
       if (it > 0) mbar_wait(tile_done, (it - 1) & 1u);   // previous tile's A block / staging / bias row are free
@@ -309,7 +320,9 @@ int proj_launch(ProjLaunch& L, cudaStream_t stream, const char* label) {
     MSF_CHECK_CUDA(cudaGetDevice(&dev));
     MSF_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int grid = L.items < sms ? L.items : sms;
+  const int nwork = L.items < sms ? L.items : sms;
+  L.zero_ctas = L.nzero > 0 ? 16 : 0;
+  const int grid = nwork + L.zero_ctas;
   if (prof_enabled()) {
     double fl = 0.0;
     for (int m = 0; m < L.M; ++m) fl += 2.0 * (double)L.rows * L.H * L.D[m];

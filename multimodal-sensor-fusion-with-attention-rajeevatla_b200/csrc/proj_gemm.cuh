@@ -36,6 +36,7 @@ struct ProjLaunch {
   // gradient slots to clear at the start of a train pass (first kernel of the step); see fusion_bf16.cu
   ProjZeroRange zero[PROJ_MAX_ZERO];
   int nzero;
+  int zero_ctas;            // CTAs at the end of the grid that only clear the ranges below (set by proj_launch)
   float* zero_base;
 };
 

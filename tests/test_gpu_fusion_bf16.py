@@ -216,6 +216,38 @@ def test_engine_step_clips_with_the_norm_of_its_own_gradients():
         assert abs(float(eng.sq_norm[0]) - want) <= 1e-5 * want, (float(eng.sq_norm[0]), float(eng.sq_norm[1]), want)
 
 
+@pytest.mark.parametrize("batch", [130, 512, 4096])
+def test_gradient_slots_are_cleared_every_step(batch):
+    """With lr = 0 and weight decay 0 the parameters never move, so every replay of the captured step must leave
+    the same gradients: a slot that is accumulated into (bias column sums, gating layers) or never written (dead
+    deleted pair modules) and not cleared by the step's first kernel would grow from step to step.  The live part
+    of the arena is poisoned before the first step."""
+    pkg = load_pkg()
+    engine = importlib.import_module(pkg.__name__ + ".engine")
+    model, feats, mask, labels = seeded_case(PAMAP2, 256, 4, 25, batch, seed=52, device="cuda")
+    eng = engine.FusionEngine(model, batch, precision="bf16", seed=5, use_graph=True, lr=0.0, weight_decay=0.0)
+    eng.p = 0.0
+    eng.load_batch(feats, mask, labels)
+    eng.grad.fill_(float("nan"))
+    for key, off, shape in eng.plan.slots:   # the engine promises these stay zero (MSF_TRAIN_DEAD_SLOTS_ZERO)
+        if ".query_proj." in key or ".key_proj." in key:
+            eng.grad[off:off + int(torch.Size(shape).numel())].zero_()
+    grads, losses = [], []
+    for _ in range(4):
+        losses.append(float(eng.train_step_resident().item()))
+        torch.cuda.synchronize()
+        grads.append(eng.grad.clone())
+    assert torch.isfinite(grads[0]).all()
+    scale = float(grads[0].abs().max())
+    for g, l in zip(grads[1:], losses[1:]):
+        assert abs(l - losses[0]) <= 1e-6 * abs(losses[0])
+        assert float((g - grads[0]).abs().max()) <= 1e-4 * scale   # fp32 atomic column sums: rounding only
+    for key, off, shape in eng.plan.slots:
+        if ".query_proj." in key or ".key_proj." in key:
+            n = int(torch.Size(shape).numel())
+            assert float(grads[-1][off:off + n].abs().max()) == 0.0, key
+
+
 def test_train_stream_pipeline_equals_step_by_step():
     """The 2-slot pipelined host-facing loop (H2D of batch i+1 overlapping step i, loss read one step late)
     follows the blocking load_batch + train_step loop (bias gradients are fp32 atomic column sums, so two
