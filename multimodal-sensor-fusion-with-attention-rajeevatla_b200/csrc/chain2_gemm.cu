@@ -136,7 +136,11 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   pdl_wait();     TL_WAITED(MODE);  // the prologue above overlapped the previous kernel; its outputs are visible from here on
-  pdl_launch();
+  // The forward chain lets its successor (the head kernel) become resident now.  The backward chain does not: its
+  // successor is the weight-gradient GEMM, whose early blocks would sit in pdl_wait() on the 20 SMs this grid
+  // leaves idle for the whole kernel, which is where the column sums beside it are meant to run; without the
+  // early trigger the successor's blocks arrive when this grid is about to drain (the MMA thread triggers below).
+  if (MODE != 1) pdl_launch();
   long long dbg_acc[4] = {0, 0, 0, 0};
   if (blockIdx.x == 0 && threadIdx.x == 0) g_chain_stamps[0] = clock64();
 
@@ -245,6 +249,12 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
         }
         tc_commit(acc_full);
       }
+#ifdef MSF_CHAIN_LATE_TRIGGER
+      // backward chain: every MMA of this CTA has been issued, only the last epilogue and its stores remain -- let
+      // the successor's blocks become resident now, so its launch latency is hidden without them holding SMs for
+      // the whole kernel (see the note at pdl_wait above)
+      if (MODE == 1) pdl_launch();
+#endif
       C2_FLUSH(1); C2_FLUSH(2); C2_FLUSH(3);
       C2_SET(4);
     }

@@ -449,6 +449,16 @@ struct Colsum16Problem {
   float* dst_more[MSF_MAX_MODALITIES];   // further destinations of the same sums (nullptr-terminated)
 };
 constexpr int COLSUM16_MAX = 48;
+#ifndef MSF_COLSUM_ROWS
+#define MSF_COLSUM_ROWS 8
+#endif
+constexpr int CS_ROWS = MSF_COLSUM_ROWS;   // rows per warp in flight
+// Dynamic shared memory the column-sum blocks ask for without using it: with it a block no longer fits beside a
+// resident tensor-core CTA (those leave less than one pipeline stage of shared memory free), so the column sums run
+// on the SMs the tensor-core grid leaves idle instead of taking issue slots and shared-memory bandwidth from it.
+#ifndef MSF_COLSUM_PAD
+#define MSF_COLSUM_PAD 40960
+#endif
 struct Colsum16List {
   Colsum16Problem p[COLSUM16_MAX];
   int count;
@@ -467,8 +477,36 @@ __global__ void __launch_bounds__(256) colsum16_kernel(const __grid_constant__ C
   for (int cbase = 0; cbase < P.cols; cbase += 256) {
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const int c = cbase + lane * 8;
-    if (c < P.cols) {
-      const bool vec = (c + 8 <= P.cols) && ((P.ld & 7) == 0);
+    const bool vec = (c + 8 <= P.cols) && ((P.ld & 7) == 0);
+    if (c < P.cols && vec && !P.src_f32) {
+      // bf16 rows, 16 bytes per lane: CS_ROWS rows per warp in flight (the block may be one of only a few on its SM)
+      const bf16* s0 = reinterpret_cast<const bf16*>(P.src) + c;
+      for (int rb = r0 + warp; rb < r1; rb += 8 * CS_ROWS) {
+        float kk[CS_ROWS];
+        uint4 raw[CS_ROWS];
+#pragma unroll
+        for (int u = 0; u < CS_ROWS; ++u) {
+          const int r = rb + 8 * u;
+          kk[u] = r < r1 ? (P.coef ? __ldg(P.coef + (long long)r * P.coef_ld) : 1.0f) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < CS_ROWS; ++u) {
+          raw[u] = make_uint4(0u, 0u, 0u, 0u);
+          if (kk[u] != 0.0f) raw[u] = __ldg(reinterpret_cast<const uint4*>(s0 + (long long)(rb + 8 * u) * P.ld));
+        }
+#pragma unroll
+        for (int u = 0; u < CS_ROWS; ++u) {
+          if (kk[u] == 0.0f) continue;   // zero-weight rows are never read (they may hold anything)
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(h[e]);
+            acc[2 * e] = fmaf(kk[u], f.x, acc[2 * e]);
+            acc[2 * e + 1] = fmaf(kk[u], f.y, acc[2 * e + 1]);
+          }
+        }
+      }
+    } else if (c < P.cols) {
       for (int r = r0 + warp; r < r1; r += 8) {
         const float k = P.coef ? __ldg(P.coef + (long long)r * P.coef_ld) : 1.0f;
         if (k == 0.0f) continue;
@@ -582,6 +620,7 @@ static int colsum16_launch(const Colsum16Problem* probs, int count, cudaStream_t
       memset(&cfg, 0, sizeof(cfg));
       cfg.gridDim = dim3((unsigned)ceil_div(max_rows, rpb), (unsigned)n);
       cfg.blockDim = dim3(256);
+      cfg.dynamicSmemBytes = MSF_COLSUM_PAD;
       cfg.stream = st;
       cfg.attrs = &attr;
       cfg.numAttrs = 1;

@@ -48,7 +48,7 @@ template <bool DP>
 __device__ __forceinline__ float4 ld_grad4(const float* p) {
   return DP ? ld_peer4(p) : __ldg(reinterpret_cast<const float4*>(p));
 }
-constexpr int OPT_VEC_UNIT = 1024, OPT_DEAD_UNIT = 4096;
+constexpr int OPT_VEC_UNIT = 1024, OPT_DEAD_UNIT = 2048;
 
 __device__ unsigned int g_opt_ticket = 0;
 __device__ unsigned int g_opt_barrier = 0;   // grid barrier between the norm phase and the update phase
@@ -311,8 +311,13 @@ static int build_jobs(const Layout& L, OptList& list) {
     list.total_units += J.batch * units;
     list.j[list.count++] = J;
   };
+  // Units are dealt to the CTAs round-robin in table order, so the table lists the heavy units first (matrix tiles:
+  // four fp32 arrays plus two bf16 copies per element), then the live vectors, and the light weight-decay-only
+  // units last: every CTA gets the same number of tiles (+-1) and the light units fill the remainder.
+  int want = 2;
   auto matrix = [&](long long begin, long long stride, int batch, int rows, int cols, size_t dst, int dst_ld,
                     size_t dstT, int dstT_ld, long long dst_batch) {
+    if (want != 2) return;
     OptJob J;
     memset(&J, 0, sizeof(J));
     J.kind = 2; J.begin = begin; J.batch_stride = stride; J.batch = batch; J.rows = rows; J.cols = cols;
@@ -320,6 +325,7 @@ static int build_jobs(const Layout& L, OptList& list) {
     push(J, ((rows + 31) / 32) * ((cols + 31) / 32));
   };
   auto vec = [&](long long begin, long long stride, int batch, long long count, int dead) {
+    if (want != (dead ? 1 : 0)) return;
     OptJob J;
     memset(&J, 0, sizeof(J));
     J.kind = dead ? 1 : 0; J.begin = begin; J.batch_stride = stride; J.batch = batch; J.rows = 1; J.cols = (int)count;
@@ -327,22 +333,26 @@ static int build_jobs(const Layout& L, OptList& list) {
     push(J, (int)((count + unit - 1) / unit));
   };
   const int pairs = L.num_pairs();
-  for (int m = 0; m < L.M; ++m) {
-    matrix(L.proj_w[m], 0, 1, L.H, L.D[m], A.wp[m], L.D[m], A.wpT[m], L.H, 0);
-    vec(L.proj_b[m], 0, 1, H, 0);
+  const int order[3] = {2, 0, 1};
+  for (int pass = 0; pass < 3; ++pass) {
+    want = order[pass];
+    for (int m = 0; m < L.M; ++m) {
+      matrix(L.proj_w[m], 0, 1, L.H, L.D[m], A.wp[m], L.D[m], A.wpT[m], L.H, 0);
+      vec(L.proj_b[m], 0, 1, H, 0);
+    }
+    if (pairs > 0) {
+      vec(L.pair_w(0, 0), L.pair_stride, pairs, 2 * (H * H + H), 1);   // query_proj + key_proj: dead
+      matrix(L.pair_w(0, 2), L.pair_stride, pairs, L.H, L.H, A.wv, L.H, A.wvT, L.H, H * H);
+      vec(L.pair_b(0, 2), L.pair_stride, pairs, H, 0);
+      matrix(L.pair_w(0, 3), L.pair_stride, pairs, L.H, L.H, A.wo, L.H, A.woT, L.H, H * H);
+      vec(L.pair_b(0, 3), L.pair_stride, pairs, H, 0);
+    }
+    vec(L.gate_w[0], 0, 1, L.cls_w1 - L.gate_w[0], 0);   // gating layers: M x (H weights + 1 bias), contiguous
+    matrix(L.cls_w1, 0, 1, L.H, L.H, A.w1, L.H, A.w1T, L.H, 0);
+    vec(L.cls_b1, 0, 1, H, 0);
+    matrix(L.cls_w2, 0, 1, L.C, L.H, A.w2, L.H, A.w2T, A.Cp, 0);   // w2T padding columns stay zero
+    vec(L.cls_b2, 0, 1, L.C, 0);
   }
-  if (pairs > 0) {
-    vec(L.pair_w(0, 0), L.pair_stride, pairs, 2 * (H * H + H), 1);   // query_proj + key_proj: dead
-    matrix(L.pair_w(0, 2), L.pair_stride, pairs, L.H, L.H, A.wv, L.H, A.wvT, L.H, H * H);
-    vec(L.pair_b(0, 2), L.pair_stride, pairs, H, 0);
-    matrix(L.pair_w(0, 3), L.pair_stride, pairs, L.H, L.H, A.wo, L.H, A.woT, L.H, H * H);
-    vec(L.pair_b(0, 3), L.pair_stride, pairs, H, 0);
-  }
-  vec(L.gate_w[0], 0, 1, L.cls_w1 - L.gate_w[0], 0);   // gating layers: M x (H weights + 1 bias), contiguous
-  matrix(L.cls_w1, 0, 1, L.H, L.H, A.w1, L.H, A.w1T, L.H, 0);
-  vec(L.cls_b1, 0, 1, H, 0);
-  matrix(L.cls_w2, 0, 1, L.C, L.H, A.w2, L.H, A.w2T, A.Cp, 0);   // w2T padding columns stay zero
-  vec(L.cls_b2, 0, 1, L.C, 0);
   MSF_REQUIRE(list.count <= OPT_MAX_JOBS, "opt_pack: job table overflow");
   return MSF_OK;
 }
