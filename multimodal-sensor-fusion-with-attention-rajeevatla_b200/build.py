@@ -24,7 +24,6 @@ FLAGS = [
     "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr",
     "-Xptxas", "-v" if os.environ.get("MSF_PTXAS_V") else "-O3",
 ]
-FLAGS += os.environ.get("MSF_NVCC_EXTRA", "").split()   # experiment builds (-DNAME=value); not used by build()
 if VARIANT == "timeline":
     FLAGS.append("-DMSF_TIMELINE")
 elif VARIANT:

@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
   // The forward chain lets its successor (the head kernel) become resident now.  The backward chain does not: its
   // successor is the weight-gradient GEMM, whose early blocks would sit in pdl_wait() on the 20 SMs this grid
   // leaves idle for the whole kernel, which is where the column sums beside it are meant to run; without the
-  // early trigger the successor's blocks arrive when this grid is about to drain (the MMA thread triggers below).
+  // trigger the successor starts when this grid has drained (a trigger from the MMA thread once its last MMA is
+  // issued hides the successor's launch latency but measured the same: 154.4 vs 154.6 us per step).
   if (MODE != 1) pdl_launch();
   long long dbg_acc[4] = {0, 0, 0, 0};
   if (blockIdx.x == 0 && threadIdx.x == 0) g_chain_stamps[0] = clock64();
@@ -249,12 +250,6 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
         }
         tc_commit(acc_full);
       }
-#ifdef MSF_CHAIN_LATE_TRIGGER
-      // backward chain: every MMA of this CTA has been issued, only the last epilogue and its stores remain -- let
-      // the successor's blocks become resident now, so its launch latency is hidden without them holding SMs for
-      // the whole kernel (see the note at pdl_wait above)
-      if (MODE == 1) pdl_launch();
-#endif
       C2_FLUSH(1); C2_FLUSH(2); C2_FLUSH(3);
       C2_SET(4);
     }

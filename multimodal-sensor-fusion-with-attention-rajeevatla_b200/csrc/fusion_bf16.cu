@@ -449,16 +449,11 @@ struct Colsum16Problem {
   float* dst_more[MSF_MAX_MODALITIES];   // further destinations of the same sums (nullptr-terminated)
 };
 constexpr int COLSUM16_MAX = 48;
-#ifndef MSF_COLSUM_ROWS
-#define MSF_COLSUM_ROWS 8
-#endif
-constexpr int CS_ROWS = MSF_COLSUM_ROWS;   // rows per warp in flight
+constexpr int CS_ROWS = 8;   // rows per warp in flight
 // Dynamic shared memory the column-sum blocks ask for without using it: with it a block no longer fits beside a
 // resident tensor-core CTA (those leave less than one pipeline stage of shared memory free), so the column sums run
 // on the SMs the tensor-core grid leaves idle instead of taking issue slots and shared-memory bandwidth from it.
-#ifndef MSF_COLSUM_PAD
-#define MSF_COLSUM_PAD 40960
-#endif
+constexpr int CS_PAD_BYTES = 40960;
 struct Colsum16List {
   Colsum16Problem p[COLSUM16_MAX];
   int count;
@@ -620,11 +615,12 @@ static int colsum16_launch(const Colsum16Problem* probs, int count, cudaStream_t
       memset(&cfg, 0, sizeof(cfg));
       cfg.gridDim = dim3((unsigned)ceil_div(max_rows, rpb), (unsigned)n);
       cfg.blockDim = dim3(256);
-      cfg.dynamicSmemBytes = MSF_COLSUM_PAD;
+      cfg.dynamicSmemBytes = CS_PAD_BYTES;
       cfg.stream = st;
       cfg.attrs = &attr;
       cfg.numAttrs = 1;
       MSF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, colsum16_kernel, list));
+      MSF_LAUNCH_CHECK();
     }
     done += n;
   }
