@@ -104,6 +104,7 @@ class FusionEngine:
         self._loss_ptr = {}          # slot -> where that slot's graph writes the mean loss (default: self.loss)
         self._infer_graph = None
         self._subset_graphs = {}
+        self._epoch_graphs = {}      # tuple of slots -> (graph over one step per slot, per-step losses)
         self._subset_masks = {}
         self._copy_stream = None
         self.launches_per_step = 0
@@ -311,6 +312,44 @@ class FusionEngine:
         """One optimizer step on the batch of input slot `slot` (see add_resident_batch)."""
         self._replay_train(slot)
         return self.loss
+
+    def train_slots(self, slots: Sequence[int]) -> torch.Tensor:
+        """One optimizer step per listed input slot, in order, as ONE graph launch (an epoch over batches that live
+        in HBM, `add_resident_batch`).  Inside the graph the first kernel of step i+1 is a programmatic dependent of
+        the optimizer launch of step i, exactly as in the eager stream order, so the gap between two graph launches
+        is paid once per call instead of once per step.  Returns the per-step mean losses (device tensor,
+        `len(slots)`); every step does the full work of `train_step_slot`."""
+        key = tuple(int(s) for s in slots)
+        if not key:
+            return torch.empty(0, dtype=torch.float32, device=self.dev)
+        if not self.use_graph:
+            out = torch.empty(len(key), dtype=torch.float32, device=self.dev)
+            for i, s in enumerate(key):
+                self._enqueue_train_step(s)
+                out[i:i + 1].copy_(self.loss)
+            return out
+        entry = self._epoch_graphs.get(key)
+        if entry is None:
+            losses = torch.zeros(len(key), dtype=torch.float32, device=self.dev)
+
+            def enqueue():
+                saved = dict(self._loss_ptr)
+                try:
+                    for i, s in enumerate(key):
+                        self._loss_ptr[s] = losses[i:i + 1].data_ptr()
+                        self._enqueue_train_step(s)
+                finally:
+                    self._loss_ptr = saved
+
+            snap = (self.arena.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(), self.state.clone())
+            graph = self._capture(enqueue)
+            for dst, src in zip((self.arena, self.exp_avg, self.exp_avg_sq, self.state), snap):
+                dst.copy_(src)
+            if self.arena_bf16 is not None:
+                self.arena_bf16.copy_(self.plan.pack_bf16(self.arena))
+            entry = self._epoch_graphs[key] = (graph, losses)
+        entry[0].replay()
+        return entry[1]
 
     def train_step_resident(self) -> torch.Tensor:
         """One optimizer step on the batch already in the static buffers.
