@@ -179,6 +179,52 @@ def fusion_case(ref_fusion, name, dims, hidden, heads, classes, batch, seed,
     _save(name, payload)
 
 
+def fusion_seeded_case(ref_fusion, name, dims, hidden, heads, classes, batch, seed, smoothing=0.05):
+    """Full-size shapes (BASELINE configs[1] / configs[4]): the state dict is too large for a fixture (13 MB / 240 MB),
+    so the fixture holds the construction seed instead -- `torch.manual_seed(seed)` followed by the constructor gives
+    the drop-in module the same parameters (same registration order and initialisers; the fixture's per-parameter sums
+    let a test check that) -- plus the inputs, the reference's outputs and compact views of its gradients
+    (norm, sum and the first 64 entries of every parameter gradient; the input gradients in full)."""
+    torch.manual_seed(seed)
+    gen = torch.Generator().manual_seed(seed + 1)
+    names = list(dims)
+    model = ref_fusion.HybridFusion(dims, hidden_dim=hidden, num_classes=classes, num_heads=heads, dropout=0.0)
+    feats = {m: torch.randn(batch, d, generator=gen) for m, d in dims.items()}
+    mask = _masks(batch, len(names), gen, with_float=False)
+    labels = torch.randint(0, classes, (batch,), generator=gen)
+    payload = {
+        "names": np.array(names), "dims": np.array([dims[m] for m in names], dtype=np.int64),
+        "heads": np.int64(heads), "classes": np.int64(classes), "hidden": np.int64(hidden),
+        "seed": np.int64(seed), "smoothing": np.float64(smoothing), "mask": _np(mask), "labels": _np(labels),
+    }
+    for m in names:
+        payload["x/" + m] = _np(feats[m])
+    for k, v in model.state_dict().items():
+        payload["sdsum/" + k] = np.float64(v.double().sum().item())
+    model.eval()
+    with torch.no_grad():
+        logits, info = model(feats, mask, return_attention=True)
+    payload["eval/logits"] = _np(logits)
+    payload["eval/fusion_weights"] = _np(info["fusion_weights"])
+    payload["eval/attn_stack"] = _np(torch.stack([info["attention_maps"][k].reshape(batch, heads)
+                                                  for k in sorted(info["attention_maps"])]))
+    payload["eval/attn_keys"] = np.array(sorted(info["attention_maps"]))
+    model.train()
+    xs = {m: feats[m].clone().requires_grad_(True) for m in names}
+    logits = model(xs, mask)
+    loss = F.cross_entropy(logits, labels, label_smoothing=smoothing)
+    loss.backward()
+    payload["train/loss"] = _np(loss)
+    for k, p in model.named_parameters():
+        g = p.grad.reshape(-1)
+        payload["gnorm/" + k] = np.float64(g.double().norm().item())
+        payload["gsum/" + k] = np.float64(g.double().sum().item())
+        payload["ghead/" + k] = _np(g[:64])
+    for m in names:
+        payload["gradx/" + m] = _np(xs[m].grad)
+    _save(name, payload)
+
+
 def attention_case(ref_attention, name, seed):
     """Generic CrossModalAttention (attention.py:68-146), q_len/k_len > 1."""
     torch.manual_seed(seed)
@@ -358,6 +404,12 @@ def main():
                 seed=13, delete_pairs=("a_to_b", "c_to_a"))
     # tensor-core eligible shape (hidden % 64 == 0), ragged batch vs a 128-row tile
     fusion_case(ref_fusion, "fusion_tc_shape.npz", {"imu": 64, "hr": 64}, 64, 4, 25, 130, seed=14)
+    # full-size shapes by construction seed: BASELINE configs[1] (PAMAP2) and configs[4] (scaled variant)
+    pamap_full = {"imu_hand": 128, "imu_chest": 128, "imu_ankle": 128, "heart_rate": 128}
+    fusion_seeded_case(ref_fusion, "fusion_config2_seeded.npz", pamap_full, 256, 4, 25, 48, seed=31)
+    scaled = {f"video_{i}": 256 for i in range(2)}
+    scaled.update({f"imu_{i}": 256 for i in range(6)})
+    fusion_seeded_case(ref_fusion, "fusion_config5_seeded.npz", scaled, 512, 8, 11, 24, seed=32)
     attention_case(ref_attention, "attention_generic.npz", seed=21)
     ece_case(ref_uncertainty, "ece_seeded.npz", seed=1234, n=20000, classes=25)
     survey_kat(ref_uncertainty)

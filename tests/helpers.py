@@ -32,6 +32,19 @@ def module_from_golden(g, device=None, dropout=None, precision="fp32"):
     return model
 
 
+def module_from_seed(g, device=None, precision="fp32"):
+    """Drop-in HybridFusion rebuilt from a seeded fixture (oracle/make_golden.py: fusion_seeded_case): same seed,
+    same constructor arguments -> the reference's parameters; the fixture's per-parameter sums are checked."""
+    dims = {m: int(d) for m, d in zip(g.names, g["dims"])}
+    torch.manual_seed(int(g["seed"]))
+    model = dropin_fusion.HybridFusion(dims, hidden_dim=int(g["hidden"]), num_classes=int(g["classes"]),
+                                       num_heads=int(g["heads"]), dropout=0.0)
+    for key, v in model.state_dict().items():
+        assert float(v.double().sum()) == float(g["sdsum/" + key]), key
+    model.precision = precision
+    return model if device is None else model.to(device)
+
+
 def seeded_case(dims, hidden, heads, classes, batch, seed, device="cpu", mask_p=0.8):
     """Random-init drop-in module + PAMAP2-shaped synthetic windows (SURVEY §8d config 2 recipe)."""
     torch.manual_seed(seed)

@@ -48,6 +48,52 @@ def test_fusion_eval_matches_reference(case):
     assert torch.allclose(conf, g.t("eval/conf"), atol=1e-7, rtol=0)
 
 
+SEEDED_CASES = ["fusion_config2_seeded.npz", "fusion_config5_seeded.npz"]
+
+
+@pytest.mark.parametrize("case", SEEDED_CASES)
+def test_full_size_shapes_match_reference(case):
+    """BASELINE configs[1] (M=4, D=128, H=256, 4 heads, 25 classes) and the scaled variant configs[4] (M=8, D=256,
+    H=512, 8 heads, 11 classes) at full width: the fixture holds the construction seed instead of the state dict
+    (same seed + same constructor = the reference's parameters, checked through per-parameter sums), the inputs and
+    the unmodified reference's logits, fusion weights, attention maps, loss and gradient views."""
+    from helpers import module_from_seed
+
+    g = Golden(case)
+    model = module_from_seed(g)
+    heads = int(g["heads"])
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    feats = {k: v.clone().requires_grad_(True) for k, v in g.group("x").items()}
+    mask = g.t("mask")
+    with torch.no_grad():
+        logits, info = fusion_oracle.hybrid_fusion_forward(sd, g.names, heads, feats, mask)
+    assert torch.allclose(logits, g.t("eval/logits"), atol=2e-6, rtol=0)
+    assert torch.allclose(info["fusion_weights"], g.t("eval/fusion_weights"), atol=1e-7, rtol=0)
+    keys = [str(k) for k in g["eval/attn_keys"]]
+    assert sorted(info["attention_maps"]) == keys
+    stack = torch.stack([info["attention_maps"][k].reshape(mask.shape[0], heads) for k in keys])
+    assert torch.equal(stack, g.t("eval/attn_stack"))
+    closed = fusion_oracle.hybrid_fusion_closed_form(
+        {k: v.detach().double() for k, v in sd.items()}, g.names, heads,
+        {k: v.detach().double() for k, v in feats.items()}, mask.double())
+    assert torch.allclose(closed.float(), g.t("eval/logits"), atol=4e-6, rtol=0)
+    # train mode (dropout 0): loss and gradients
+    logits, _ = fusion_oracle.hybrid_fusion_forward(sd, g.names, heads, feats, mask)
+    loss = fusion_oracle.cross_entropy_label_smoothing(logits, g.t("labels"), float(g["smoothing"]))
+    loss.backward()
+    assert abs(float(loss.detach()) - float(g["train/loss"])) <= 1e-6
+    for key, p in sd.items():
+        grad = torch.zeros_like(p).reshape(-1) if p.grad is None else p.grad.reshape(-1)
+        ref_norm = float(g["gnorm/" + key])
+        assert abs(float(grad.double().norm()) - ref_norm) <= 1e-5 * ref_norm + 1e-9, key
+        assert abs(float(grad.double().sum()) - float(g["gsum/" + key])) <= 1e-4 * ref_norm + 1e-9, key
+        assert torch.allclose(grad[:64], g.t("ghead/" + key), atol=1e-6 + 1e-4 * ref_norm, rtol=0), key
+        if ".query_proj." in key or ".key_proj." in key:
+            assert ref_norm == 0.0 and float(grad.abs().max()) == 0.0, key
+    for m, ref in g.group("gradx").items():
+        assert torch.allclose(feats[m].grad, ref, atol=1e-7, rtol=1e-4), m
+
+
 @pytest.mark.parametrize("case", FUSION_CASES)
 def test_fusion_closed_form_matches_reference(case):
     """q/k projections are dead, attention is a 0/1 gate."""
