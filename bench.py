@@ -223,6 +223,14 @@ def run_ours(args):
     ring = [synthetic_batch(torch, 1000 + 97 * rank + i, BATCH, device=dev) for i in range(ring_n)]
     in_bytes = sum(t.numel() * t.element_size() for t in ring[0][0]) + ring[0][1].numel() * 4 + ring[0][2].numel() * 8
     host = [synthetic_batch(torch, 5000 + 97 * rank + i, BATCH, pin=True) for i in range(4)]
+    if args.packed_host:   # the same batches in FusionEngine.pinned_batch() buffers: one transfer per batch
+        packed = []
+        for f, m, y in host:
+            pf, pm, py = eng.pinned_batch()
+            for dst, src in zip(pf + [pm, py], f + [m, y]):
+                dst.copy_(src)
+            packed.append((pf, pm, py))
+        host = packed
 
     def barrier():
         if world > 1:
@@ -667,6 +675,9 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("MSF_BENCH_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--packed-host", action="store_true",
+                    help="train workload, e2e leg: host batches in FusionEngine.pinned_batch() buffers (one H2D "
+                         "transfer per batch instead of six); not measured yet")
     ap.add_argument("--steps-per-graph", type=int, default=0,
                     help="train workload: steps captured into one graph launch (FusionEngine.train_slots); "
                          "0 = 8 on one GPU, 1 under data parallelism")

@@ -104,6 +104,7 @@ class FusionEngine:
         self._loss_ptr = {}          # slot -> where that slot's graph writes the mean loss (default: self.loss)
         self._infer_graph = None
         self._subset_graphs = {}
+        self._packed_slots = False   # set by pinned_batch(): train_stream's input slots as one buffer each
         self._epoch_graphs = {}      # tuple of slots -> (graph over one step per slot, per-step losses)
         self._subset_masks = {}
         self._copy_stream = None
@@ -250,6 +251,41 @@ class FusionEngine:
             fn()
         return graph
 
+    def _one_buffer_batch(self, host: bool):
+        """(features, mask, labels) as views of ONE allocation, laid out in the order load_batch copies them.  A host
+        batch from pinned_batch() and a train_stream input slot are then adjacent on both sides and msf_memcpy_batch
+        sends the whole batch as a single transfer."""
+        B, plan = self.batch, self.plan
+        sizes = [B * d * 4 for d in plan.dims] + [B * plan.M * 4, B * 8]
+        if any(sz % 16 for sz in sizes[:-1]):
+            return None   # a tensor would start off a 16-byte boundary (bulk copies, int64 labels): separate buffers
+        total = sum(sizes)
+        buf = (torch.zeros(total, dtype=torch.uint8).pin_memory() if host
+               else torch.zeros(total, dtype=torch.uint8, device=self.dev))
+        parts, off = [], 0
+        for sz in sizes:
+            parts.append(buf[off:off + sz])
+            off += sz
+        feats = [p.view(torch.float32).view(B, d) for p, d in zip(parts, plan.dims)]
+        mask = parts[-2].view(torch.float32).view(B, plan.M)
+        labels = parts[-1].view(torch.int64)
+        mask.fill_(1.0)
+        return feats, mask, labels
+
+    def pinned_batch(self):
+        """A host batch in page-locked memory shaped for this engine: ``(features list, mask, labels)``, views of one
+        pinned allocation in the engine's copy order.  Fill it (a DataLoader collate function can write straight
+        into it) and hand it to train_stream: it crosses PCIe as one transfer instead of one per tensor.  Call it
+        before the first train_stream (the stream's device slots are laid out to match when they are created)."""
+        if self._copy_stream is None:
+            self._packed_slots = True   # train_stream lays its two input slots out the same way (first call)
+        got = self._one_buffer_batch(host=True)
+        if got is None:
+            B, plan = self.batch, self.plan
+            got = ([torch.zeros(B, d).pin_memory() for d in plan.dims], torch.ones(B, plan.M).pin_memory(),
+                   torch.zeros(B, dtype=torch.int64).pin_memory())
+        return got
+
     # -- public API --------------------------------------------------------------------
     def load_batch(self, features: Dict[str, torch.Tensor] | Sequence[torch.Tensor],
                    mask: Optional[torch.Tensor], labels: Optional[torch.Tensor] = None, slot: int = 0) -> int:
@@ -380,9 +416,10 @@ class FusionEngine:
             f32 = dict(dtype=torch.float32, device=dev)
             self._stream_slots = []
             for s in range(2):
-                self._slots.append(([torch.zeros(self.batch, d, **f32) for d in self.plan.dims],
-                                    torch.ones(self.batch, self.plan.M, **f32),
-                                    torch.zeros(self.batch, dtype=torch.int64, device=dev)))
+                self._slots.append((self._one_buffer_batch(host=False) if self._packed_slots else None)
+                                   or ([torch.zeros(self.batch, d, **f32) for d in self.plan.dims],
+                                       torch.ones(self.batch, self.plan.M, **f32),
+                                       torch.zeros(self.batch, dtype=torch.int64, device=dev)))
                 self._train_graphs.append(None)
                 slot = len(self._slots) - 1
                 self._stream_slots.append(slot)
