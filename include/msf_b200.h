@@ -114,8 +114,7 @@ int msf_prof_enable(int32_t on);
 int msf_prof_report(char* buf, size_t cap);
 /* n asynchronous copies (cudaMemcpyDefault: host-pinned or device pointers) on one stream in one call:
  * the per-step host->device staging of a batch (M feature tensors, mask, labels) without per-tensor
- * framework dispatch on the host.  Consecutive entries that are adjacent in both source and destination are issued
- * as one transfer. */
+ * framework dispatch on the host. */
 int msf_memcpy_batch(void* const* dst, const void* const* src, const size_t* bytes, int32_t n, void* stream);
 /* sm count / compute capability of the current device; fails unless cc >= 10.0 */
 int msf_device_check(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);

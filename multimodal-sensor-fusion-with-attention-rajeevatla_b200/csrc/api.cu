@@ -232,20 +232,9 @@ int msf_fusion_param_offset(const msf_fusion_shape* shape, int32_t kind, int32_t
 
 int msf_memcpy_batch(void* const* dst, const void* const* src, const size_t* bytes, int32_t n, void* stream) {
   MSF_REQUIRE(dst && src && bytes && n >= 0, "msf_memcpy_batch: bad arguments");
-  // runs of copies that are adjacent on both sides (FusionEngine.pinned_batch / one-buffer input slots) go out as
-  // one transfer: a batch of six tensors then costs one DMA setup instead of six
-  for (int i = 0; i < n;) {
-    size_t total = bytes[i];
-    int j = i + 1;
-    while (j < n && static_cast<const char*>(src[j]) == static_cast<const char*>(src[i]) + total &&
-           static_cast<char*>(dst[j]) == static_cast<char*>(dst[i]) + total) {
-      total += bytes[j];
-      ++j;
-    }
-    if (total > 0)
-      MSF_CHECK_CUDA(cudaMemcpyAsync(dst[i], src[i], total, cudaMemcpyDefault, (cudaStream_t)stream));
-    i = j;
-  }
+  for (int i = 0; i < n; ++i)
+    if (bytes[i] > 0)
+      MSF_CHECK_CUDA(cudaMemcpyAsync(dst[i], src[i], bytes[i], cudaMemcpyDefault, (cudaStream_t)stream));
   return MSF_OK;
 }
 

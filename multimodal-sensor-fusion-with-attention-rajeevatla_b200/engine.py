@@ -253,7 +253,7 @@ class FusionEngine:
 
     def _one_buffer_batch(self, host: bool):
         """(features, mask, labels) as views of ONE allocation, laid out in the order load_batch copies them.  A host
-        batch from pinned_batch() and a train_stream input slot are then adjacent on both sides and msf_memcpy_batch
+        batch from pinned_batch() and a train_stream input slot are then adjacent on both sides and load_batch
         sends the whole batch as a single transfer."""
         B, plan = self.batch, self.plan
         sizes = [B * d * 4 for d in plan.dims] + [B * plan.M * 4, B * 8]
@@ -305,10 +305,21 @@ class FusionEngine:
                and (src.device.type != "cpu" or src.is_pinned()) for dst, src in pairs):
             # one library call issues all the asynchronous copies (no per-tensor dispatch on the host)
             import ctypes
-            n = len(pairs)
-            dsts = (ctypes.c_void_p * n)(*[dst.data_ptr() for dst, _ in pairs])
-            srcs = (ctypes.c_void_p * n)(*[src.data_ptr() for _, src in pairs])
-            sizes = (ctypes.c_size_t * n)(*[src.numel() * src.element_size() for _, src in pairs])
+            triples = [(dst.data_ptr(), src.data_ptr(), src.numel() * src.element_size()) for dst, src in pairs]
+            if self._packed_slots:
+                # pinned_batch() source and a one-buffer slot: runs adjacent on both sides go out as one transfer
+                merged = [triples[0]]
+                for d, s_, sz in triples[1:]:
+                    d0, s0, sz0 = merged[-1]
+                    if d == d0 + sz0 and s_ == s0 + sz0:
+                        merged[-1] = (d0, s0, sz0 + sz)
+                    else:
+                        merged.append((d, s_, sz))
+                triples = merged
+            n = len(triples)
+            dsts = (ctypes.c_void_p * n)(*[t[0] for t in triples])
+            srcs = (ctypes.c_void_p * n)(*[t[1] for t in triples])
+            sizes = (ctypes.c_size_t * n)(*[t[2] for t in triples])
             N.check(N.lib().msf_memcpy_batch(dsts, srcs, sizes, n, ops._stream()))
         else:
             for dst, src in pairs:
@@ -443,6 +454,13 @@ class FusionEngine:
             dst_tables.append(((ctypes.c_void_p * len(tens))(*[t.data_ptr() for t in tens]),
                                (ctypes.c_size_t * len(tens))(*[t.numel() * t.element_size() for t in tens]),
                                [(t.dtype, t.numel()) for t in tens]))
+        one_dst, one_size = (ctypes.c_void_p * 1)(), (ctypes.c_size_t * 1)()
+
+        def adjacent(tens):   # laid out back to back in this order (pinned_batch / one-buffer slots)
+            return all(b.data_ptr() == a.data_ptr() + a.numel() * a.element_size() for a, b in zip(tens, tens[1:]))
+
+        slot_adjacent = [self._packed_slots and adjacent(list(self._slots[s][0]) + list(self._slots[s][1:]))
+                         for s in self._stream_slots]
 
         def stage(batch, k):
             cs.wait_event(self._ev_done[k])      # no-op until the slot's first step has been recorded
@@ -453,8 +471,13 @@ class FusionEngine:
                     t.dtype == d and t.numel() == n and t.is_contiguous() and (t.device.type != "cpu" or t.is_pinned())
                     for t, (d, n) in zip(srcs, meta)):
                 # one library call issues every host->device copy of the batch on the copy stream
-                ptrs = (ctypes.c_void_p * len(srcs))(*[t.data_ptr() for t in srcs])
-                N.check(lib.msf_memcpy_batch(dsts, ptrs, sizes, len(srcs), cs_handle))
+                if slot_adjacent[k] and adjacent(srcs):   # the whole batch as one transfer
+                    one_dst[0], one_size[0] = dsts[0], sum(sizes)
+                    ptrs = (ctypes.c_void_p * 1)(srcs[0].data_ptr())
+                    N.check(lib.msf_memcpy_batch(one_dst, ptrs, one_size, 1, cs_handle))
+                else:
+                    ptrs = (ctypes.c_void_p * len(srcs))(*[t.data_ptr() for t in srcs])
+                    N.check(lib.msf_memcpy_batch(dsts, ptrs, sizes, len(srcs), cs_handle))
             else:
                 with torch.cuda.stream(cs):
                     self.load_batch(batch[0], batch[1], batch[2], slot=self._stream_slots[k])
