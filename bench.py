@@ -298,9 +298,9 @@ def run_ours(args):
     # otherwise paid every step (155.0 -> 150.7 us at 4, 149.8 at 24); 1 under data parallelism.  Still exactly
     # args.steps optimizer steps inside the timed region, each with the full work of a single step; what does not
     # fill a group runs as single-step launches.
-    G = args.steps_per_graph if args.steps_per_graph > 0 else (8 if world == 1 else 1)
+    G = args.steps_per_graph if args.steps_per_graph > 0 else (8 if world == 1 and args.steps >= 16 else 1)
     if ring_slots is None or ring_n % G:
-        G = 1
+        G = 1   # short runs (profiler passes with a handful of steps) and eager mode keep one step per launch
     if G > 1:
         def resident_group(j):
             first = (j * G) % ring_n
@@ -680,7 +680,7 @@ def main():
                          "transfer per batch instead of six); not measured yet")
     ap.add_argument("--steps-per-graph", type=int, default=0,
                     help="train workload: steps captured into one graph launch (FusionEngine.train_slots); "
-                         "0 = 8 on one GPU, 1 under data parallelism")
+                         "0 = 8 on one GPU when --steps >= 16, else 1")
     ap.add_argument("--no-mask-hint", action="store_true",
                     help="infer_sweep: run every subset through the dense path (per-row mask, no skipping)")
     ap.add_argument("--workload", default="train", choices=["train", "infer_sweep", "ece", "raw_infer"],
