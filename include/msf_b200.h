@@ -107,8 +107,11 @@ const char* msf_last_error(void);
 /* kernels launched by this library so far in this process (host-side counter) */
 uint64_t msf_launch_count(void);
 /* Per-launch timing of the tensor-core GEMM launches with CUDA events on the launching stream.
- * enable(1) clears earlier records and starts recording, enable(0) stops.  report() synchronises the
- * device and writes one line per launch label: "label\tlaunches\ttotal_ms\ttotal_flops\n".
+ * enable(1) clears earlier records and starts recording, enable(0) stops; enable(R > 1) additionally makes the
+ * chained pair-GEMM launches issue their (idempotent) kernel R times back to back inside one event bracket, so
+ * the average includes the prologue overlap of programmatic dependent launches and excludes the event records.
+ * report() synchronises the device and writes one line per launch label:
+ * "label\tlaunches\ttotal_ms\ttotal_flops\n".
  * Must not be enabled while the stream is being captured into a CUDA graph. */
 int msf_prof_enable(int32_t on);
 int msf_prof_report(char* buf, size_t cap);
@@ -162,14 +165,9 @@ int msf_fusion_infer_pass(const msf_fusion_shape* shape, const msf_fusion_call* 
 /* Debugging aid: clock64 stamps (SM cycles) of the phases of CTA 0 in the last fused head-kernel launch
  * (P0 start/end, then acquire/finish of E1..E4, P5 start/end).  Synchronises the device. */
 int msf_debug_head_stamps(int64_t* out16);
-/* Same for the last chained pair-GEMM launch: wait-time accounting of CTA 0 (see chain2_gemm.cu). */
+/* Same for the last chained pair-GEMM launch: wait-time accounting of CTA 0 (chain3_gemm.cu; compiled into the timeline build only,
+ * MSF_E_UNSUPPORTED otherwise; MSF_CHAIN=v2: chain2_gemm.cu). */
 int msf_debug_chain_stamps(int64_t* out16);
-/* cta_group::2 probe (pair_gemm.cu): D[m, 256] = A[m, k] . B[256, k]^T, bf16 operands, fp32 D, one CTA pair per
- * 256 rows.  Building block of the round-2 kernels; not used by the product path. */
-int msf_debug_pair_gemm(const void* a_bf16, const void* b_bf16, float* d, int64_t m, int64_t k, void* stream);
-/* Issue-rate probe: `ctas` CTAs each issue reps x ksteps tcgen05.mma (M = 128, N = n, K = 16, operands resident in
- * shared memory); cycles_out[0] = clock64 cycles CTA 0 needed.  Synchronises the stream. */
-int msf_debug_mma_rate(int32_t n, int32_t reps, int32_t ksteps, int32_t ctas, int64_t* cycles_out, void* stream);
 /* Phase stamps of CTA 0 of the last input-projection launch (proj_gemm.cu). */
 int msf_debug_proj_stamps(int64_t* out16);
 /* HybridFusion.compute_adaptive_weights (src/fusion.py:429-479) stand-alone:
@@ -270,7 +268,10 @@ int msf_dp_optimizer_step_packed(const msf_fusion_shape* shape, const msf_dp_com
                                  float* exp_avg, float* exp_avg_sq, uint64_t* train_state, float lr, float beta1,
                                  float beta2, float eps, float weight_decay, float grad_scale, float max_norm,
                                  void* params_bf16, int32_t advance_state, void* stream);
-/* train_state = DEVICE {seed, offset, step}: offset += 1, step += 1. */
+/* train_state = DEVICE {seed, offset, step[, lr bits]}: offset += 1, step += 1.
+ * Every optimizer entry point that takes a train_state accepts lr < 0: the learning rate is then the fp32 whose bits
+ * are the low word of train_state[3] (a fourth uint64 the caller owns and updates between launches), so a captured
+ * CUDA graph follows a learning-rate schedule (src/train.py:395-404) without being re-captured. */
 int msf_train_state_advance(uint64_t* train_state, void* stream);
 
 /* ---- dense layer (nn.Linear) on the fp32 FFMA path ------------------------- */

@@ -100,8 +100,6 @@ PROTOTYPES = {
     "msf_debug_head_stamps": (c_int32, [c_void_p]),
     "msf_debug_chain_stamps": (c_int32, [c_void_p]),
     "msf_debug_proj_stamps": (c_int32, [c_void_p]),
-    "msf_debug_mma_rate": (c_int32, [c_int32, c_int32, c_int32, c_int32, POINTER(c_int64), c_void_p]),
-    "msf_debug_pair_gemm": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "msf_adaptive_weights": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
                                        c_void_p, c_void_p]),
     "msf_dropout_mask": (c_int32, [c_uint64, c_uint64, c_int32, c_int32, c_int64, c_int64, c_float,

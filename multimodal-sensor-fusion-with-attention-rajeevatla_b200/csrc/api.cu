@@ -14,13 +14,16 @@ namespace {
 struct ProfRecord {
   const char* label;
   double flops;
+  int reps;
   cudaEvent_t start, stop;
 };
 bool g_prof_on = false;
+int g_prof_reps = 1;
 std::vector<ProfRecord> g_prof;
 }  // namespace
 
 bool prof_enabled() { return g_prof_on; }
+int prof_repeat() { return g_prof_on ? g_prof_reps : 1; }
 
 bool pdl_enabled() {
   static int on = -1;
@@ -31,11 +34,12 @@ bool pdl_enabled() {
   return on != 0;
 }
 
-void prof_begin(const char* label, double flops, cudaStream_t stream) {
+void prof_begin(const char* label, double flops, cudaStream_t stream, int reps) {
   if (!g_prof_on) return;
   ProfRecord r;
   r.label = label;
   r.flops = flops;
+  r.reps = reps < 1 ? 1 : reps;
   if (cudaEventCreate(&r.start) != cudaSuccess || cudaEventCreate(&r.stop) != cudaSuccess) return;
   cudaEventRecord(r.start, stream);
   g_prof.push_back(r);
@@ -142,6 +146,7 @@ int msf_prof_enable(int32_t on) {
   }
   msf::g_prof.clear();
   msf::g_prof_on = on != 0;
+  msf::g_prof_reps = on > 1 ? on : 1;
   return MSF_OK;
 }
 
@@ -160,9 +165,9 @@ int msf_prof_report(char* buf, size_t cap) {
       agg.push_back(Agg{r.label, 0, 0.0, 0.0});
       a = &agg.back();
     }
-    a->n += 1;
+    a->n += r.reps;
     a->ms += ms;
-    a->flops += r.flops;
+    a->flops += r.flops * r.reps;
   }
   std::string out;
   char line[256];

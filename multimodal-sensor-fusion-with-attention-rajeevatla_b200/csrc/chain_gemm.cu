@@ -393,28 +393,31 @@ size_t chain_fixed_smem() { return 1024 + 8 * (2 * CH_MAX_STAGES + 8) + 3 * 256 
 bool chain2_eligible(int H, int M);                                          // chain2_gemm.cu
 int chain2_launch(ChainLaunch& L, cudaStream_t stream, const char* label);
 
-bool chainp_eligible(int H, int M);                                          // chainp_gemm.cu (CTA pairs)
-int chainp_launch(ChainLaunch& L, cudaStream_t stream, const char* label);
+bool chain3_eligible(int H, int M, int head_dim);                             // chain3_gemm.cu (cluster weight multicast)
+int chain3_cluster(int H, long long rows);
+int chain3_launch(ChainLaunch& L, cudaStream_t stream, const char* label);
 
-bool chain2p_eligible(int H, int M);                                         // chain2p_gemm.cu (CTA pairs, pipelined)
-int chain2p_launch(ChainLaunch& L, cudaStream_t stream, const char* label);
-
-// kernel choice: 2 = chain2_kernel, single CTA with the half-pair software pipeline (default for hidden % 128 == 0);
-// 1 = chain_kernel (every other hidden size, or MSF_CHAIN=v1).  The cta_group::2 variants are correct (same parity
-// tests) but not faster yet at B = 4096 — the epilogue, not the tensor pipe, is their critical path — and are opt-in:
-// MSF_CHAIN=pair2 -> 4 = chain2p_kernel (CTA pairs + pipeline), MSF_CHAIN=pair -> 3 = chainp_kernel (CTA pairs).
-static int chain_variant(int H, int M) {
+// kernel choice: 5 = chain3_kernel (clusters sharing every weight fetch by TMA multicast, N = H MMAs, k-block
+// pipeline; default for hidden % 128 == 0 and head_dim % 16 == 0); 1 = chain_kernel (every other shape, or
+// MSF_CHAIN=v1).  The round-1 default stays selectable for A/B runs: MSF_CHAIN=v2 -> 2 = chain2_kernel (single
+// CTA, half-pair pipeline).
+static int chain_variant(int H, int M, int heads) {
   const char* e = getenv("MSF_CHAIN");
   if (getenv("MSF_CHAIN_V1") || (e && e[0] == 'v' && e[1] == '1')) return 1;
-  if (e && e[0] == 'p' && e[1] == 'a' && e[2] == 'i' && e[3] == 'r' && e[4] == '2') return chain2p_eligible(H, M) ? 4 : 1;
-  if (e && e[0] == 'p') return chainp_eligible(H, M) ? 3 : 1;
+  if (e && e[0] == 'v' && e[1] == '2') return chain2_eligible(H, M) ? 2 : 1;
+  if (heads >= 1 && H % heads == 0 && chain3_eligible(H, M, H / heads)) return 5;
   return chain2_eligible(H, M) ? 2 : 1;
 }
-int chain_w1_box_rows(int H, int M) {
-  const int v = chain_variant(H, M);
-  return v == 4 ? H / 4 : (v >= 2 ? H / 2 : H);
+int chain_w1_box_rows(int H, int M, int heads, long long rows) {
+  const int v = chain_variant(H, M, heads);
+  if (v == 5) return H / chain3_cluster(H, rows);
+  return v == 2 ? H / 2 : H;
 }
-int chain_w2_box_rows(int H, int M) { return chain_variant(H, M) >= 3 ? H / 2 : H; }
+int chain_w2_box_rows(int H, int M, int heads, long long rows) {
+  const int v = chain_variant(H, M, heads);
+  if (v == 5) return H / chain3_cluster(H, rows);
+  return H;
+}
 
 bool chain_eligible(int H, int M) { return H % 64 == 0 && H >= 64 && H <= 256 && M >= 1 && M <= MSF_MAX_MODALITIES; }
 
@@ -424,9 +427,8 @@ int chain_launch(ChainLaunch& L, cudaStream_t stream, const char* label) {
   L.head_shift = -1;
   for (int sft = 0; sft < 16; ++sft)
     if ((1 << sft) == L.head_dim) L.head_shift = sft;
-  const int variant = chain_variant(L.H, L.M);
-  if (variant == 4) return chain2p_launch(L, stream, label);
-  if (variant == 3) return chainp_launch(L, stream, label);
+  const int variant = chain_variant(L.H, L.M, L.heads);
+  if (variant == 5) return chain3_launch(L, stream, label);
   if (variant == 2) return chain2_launch(L, stream, label);
   L.row_tiles = (int)ceil_div(L.rows, 128);
   if (L.n_active <= 0) {   // default: every modality is an outer modality

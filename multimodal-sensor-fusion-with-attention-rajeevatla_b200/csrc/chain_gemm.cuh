@@ -44,6 +44,7 @@ struct ChainLaunch {
   short active[MSF_MAX_MODALITIES];  // inference pass are left out: the head never reads their aggregated token
   int store1;          // write epilogue1's result to global memory (needed by the backward pass)
   int stages;
+  int cluster;         // CTAs per cluster sharing one fetch of every weight block (chain3_kernel; set by chain_launch)
   ChainOuter outer[MSF_MAX_MODALITIES];
   const float* bias1[CHAIN_MAX_PAIRS];   // forward: value_proj bias per pair
   const float* bias2[CHAIN_MAX_PAIRS];   // forward: out_proj bias per pair (summed in the final epilogue)
@@ -58,11 +59,11 @@ struct ChainLaunch {
 };
 
 bool chain_eligible(int H, int M);
-// Box height of map_w1 (rows of W1 one TMA load brings in): H for chain_kernel, H/2 for the
-// half-pair-pipelined chain2_kernel that chain_launch picks when hidden % 128 == 0.
-int chain_w1_box_rows(int H, int M);
-// Box height of map_w2: H, or H/2 for the CTA-pair kernel (each CTA of a pair stages half of every weight block).
-int chain_w2_box_rows(int H, int M);
+// Box height of map_w1 / map_w2 (rows of a weight block one TMA load brings in) for the kernel chain_launch will
+// pick for this shape: H / cluster for chain3_kernel (every CTA of a cluster fetches one slice and multicasts it),
+// H for chain_kernel.
+int chain_w1_box_rows(int H, int M, int heads, long long rows);
+int chain_w2_box_rows(int H, int M, int heads, long long rows);
 // Fills stages / items / row_tiles and launches.  Tensor maps must already be encoded (tc_encode_map).
 int chain_launch(ChainLaunch& L, cudaStream_t stream, const char* label);
 

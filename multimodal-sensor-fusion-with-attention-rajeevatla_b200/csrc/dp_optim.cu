@@ -180,7 +180,8 @@ __global__ void __launch_bounds__(256) dp_adamw_kernel(const __grid_constant__ D
   const float sqrt_bc2 = (float)sqrt(1.0 - pow((double)c.beta2, step));
   float gs = c.grad_scale;
   if (c.max_norm > 0.0f) gs *= fminf(c.max_norm / ((float)sqrt(total) * c.grad_scale + 1e-6f), 1.0f);
-  const float step_size = c.lr / bc1, decay = 1.0f - c.lr * c.wd;
+  const float lr = resolve_lr(c.lr, reinterpret_cast<const unsigned long long*>(a.train_state));
+  const float step_size = lr / bc1, decay = 1.0f - lr * c.wd;
 
   const DpSeg sg = a.seg[blockIdx.y];
   const float* red = a.reds[a.rank];

@@ -769,8 +769,8 @@ static int forward_front(const Layout& L, const msf_fusion_call* c, const WsBf16
     C.store1 = 1;  // U is an operand of the out_proj weight gradient
     const int np = pairs > 0 ? pairs : 1;
     if ((rc = tc_encode_map(&C.map_a1, ws.P, B, H, H, M, BH, 64, 128))) return rc;
-    if ((rc = tc_encode_map(&C.map_w1, pairs > 0 ? (const void*)(W16 + A.wv) : (const void*)ws.P, H, H, H, np, (long long)H * H, 64, chain_w1_box_rows(H, M)))) return rc;
-    if ((rc = tc_encode_map(&C.map_w2, pairs > 0 ? (const void*)(W16 + A.wo) : (const void*)ws.P, H, H, H, np, (long long)H * H, 64, chain_w2_box_rows(H, M)))) return rc;
+    if ((rc = tc_encode_map(&C.map_w1, pairs > 0 ? (const void*)(W16 + A.wv) : (const void*)ws.P, H, H, H, np, (long long)H * H, 64, chain_w1_box_rows(H, M, L.heads, B)))) return rc;
+    if ((rc = tc_encode_map(&C.map_w2, pairs > 0 ? (const void*)(W16 + A.wo) : (const void*)ws.P, H, H, H, np, (long long)H * H, 64, chain_w2_box_rows(H, M, L.heads, B)))) return rc;
     if ((rc = tc_encode_map(&C.map_out1, ws.U, B, H, H, np, BH, 64, 128))) return rc;
     if ((rc = tc_encode_map(&C.map_out, ws.agg, B, H, H, M, BH, 64, 128))) return rc;
     for (int q = 0; q < M; ++q) {
@@ -1087,8 +1087,8 @@ static int backward_back(const Layout& L, const msf_fusion_call* c, const WsBf16
     C.store1 = 1;  // dV is an operand of the value_proj weight / bias gradients
     const int np = pairs > 0 ? pairs : 1;
     if ((rc = tc_encode_map(&C.map_a1, ws.dS, B, H, H, M, BH, 64, 128))) return rc;
-    if ((rc = tc_encode_map(&C.map_w1, pairs > 0 ? (const void*)(W16 + A.woT) : (const void*)ws.dS, H, H, H, np, (long long)H * H, 64, chain_w1_box_rows(H, M)))) return rc;
-    if ((rc = tc_encode_map(&C.map_w2, pairs > 0 ? (const void*)(W16 + A.wvT) : (const void*)ws.dS, H, H, H, np, (long long)H * H, 64, chain_w2_box_rows(H, M)))) return rc;
+    if ((rc = tc_encode_map(&C.map_w1, pairs > 0 ? (const void*)(W16 + A.woT) : (const void*)ws.dS, H, H, H, np, (long long)H * H, 64, chain_w1_box_rows(H, M, L.heads, B)))) return rc;
+    if ((rc = tc_encode_map(&C.map_w2, pairs > 0 ? (const void*)(W16 + A.wvT) : (const void*)ws.dS, H, H, H, np, (long long)H * H, 64, chain_w2_box_rows(H, M, L.heads, B)))) return rc;
     if ((rc = tc_encode_map(&C.map_out1, ws.dV, B, H, H, np, BH, 64, 128))) return rc;
     if ((rc = tc_encode_map(&C.map_out, ws.dZ, B, H, H, M, BH, 64, 128))) return rc;
     for (int k = 0; k < M; ++k) {

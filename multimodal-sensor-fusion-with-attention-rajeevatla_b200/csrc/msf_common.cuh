@@ -45,8 +45,12 @@ extern unsigned long long g_launch_count;
 
 // Optional per-launch timing with CUDA events on the launching stream (msf_prof_enable / msf_prof_report);
 // bench.py uses it to time the dominant kernel live.  Not usable while a stream is being captured.
+// msf_prof_enable(R > 1): launchers whose kernel is idempotent issue it R times back to back inside one event
+// bracket (prof_repeat()), so the average launch duration includes what a programmatic dependent launch hides
+// in the real step (the prologue under the predecessor's tail) and not the cost of the event records.
 bool prof_enabled();
-void prof_begin(const char* label, double flops, cudaStream_t stream);
+int prof_repeat();
+void prof_begin(const char* label, double flops, cudaStream_t stream, int reps = 1);
 void prof_end(cudaStream_t stream);
 
 // ---------------------------------------------------------------------------
@@ -263,5 +267,12 @@ __host__ __device__ __forceinline__ float drop1(const DropCfg& d, int site, int 
 }
 
 enum { SITE_INPUT = 0, SITE_PROJ = 1, SITE_ATTN = 2, SITE_CLS = 3 };
+
+// Learning rate of an optimizer launch: the host value, or (host value < 0) the float whose bits sit in the low
+// word of train_state[3] — a captured CUDA graph then follows a schedule without being re-captured
+// (msf_train_state_set_lr; src/train.py:395-404 steps a cosine schedule per epoch).
+__device__ __forceinline__ float resolve_lr(float lr, const unsigned long long* train_state) {
+  return (lr < 0.0f && train_state != nullptr) ? __uint_as_float((uint32_t)train_state[3]) : lr;
+}
 
 }  // namespace msf

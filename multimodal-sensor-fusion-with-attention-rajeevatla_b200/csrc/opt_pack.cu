@@ -166,8 +166,9 @@ __global__ void __launch_bounds__(256, 4) opt_pack_kernel(const __grid_constant_
       const float total = (float)sqrt(sq_total) * c.grad_scale;
       t.gs *= fminf(c.max_norm / (total + 1e-6f), 1.0f);
     }
-    t.step_size = c.lr / bc1;
-    t.decay = 1.0f - c.lr * c.wd;
+    const float lr = resolve_lr(c.lr, reinterpret_cast<const unsigned long long*>(train_state));
+    t.step_size = lr / bc1;
+    t.decay = 1.0f - lr * c.wd;
     t.beta1 = c.beta1; t.beta2 = c.beta2; t.ob1 = 1.0f - c.beta1; t.ob2 = 1.0f - c.beta2; t.eps = c.eps;
     ks = t;
   }

@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
     const float coef = max_norm / (total + 1e-6f);
     gs *= fminf(coef, 1.0f);
   }
+  lr = resolve_lr(lr, train_state);
   const float step_size = lr / bc1;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -153,7 +154,8 @@ __global__ void __launch_bounds__(256) seg_adamw_kernel(const __grid_constant__ 
     const float total = (float)sqrt(*sq_norm) * c.grad_scale;
     gs *= fminf(c.max_norm / (total + 1e-6f), 1.0f);
   }
-  const float step_size = c.lr / bc1, decay = 1.0f - c.lr * c.wd;
+  const float lr = resolve_lr(c.lr, train_state);
+  const float step_size = lr / bc1, decay = 1.0f - lr * c.wd;
   const long long stride = (long long)gridDim.x * blockDim.x, t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const bool vec = (sg.begin & 3) == 0;
   const long long n4 = vec ? (sg.count >> 2) : 0;

@@ -97,8 +97,13 @@ class FusionEngine:
         self.sq_norm = torch.zeros(2, dtype=torch.float64, device=dev)   # [used by the optimizer, from the pass]
         self.conf = torch.zeros(B, **f32)
         self.pred = torch.zeros(B, dtype=torch.int64, device=dev)
-        # {seed, offset, step}; step is 1-based when the optimizer kernel reads it
-        self.state = torch.tensor([seed, 0, 1], dtype=torch.int64, device=dev)
+        # {seed, offset, step, lr bits}; step is 1-based when the optimizer kernel reads it.  The learning rate lives
+        # on the device (low word of state[3], fp32 bits) and the optimizer launches are given lr = -1, so a captured
+        # graph follows set_lr() without being re-captured (the reference steps a cosine schedule per epoch,
+        # src/train.py:395-404).  Data-parallel replicas draw different dropout masks: the rank is folded in.
+        rank = torch.distributed.get_rank(process_group) if self.world > 1 else 0
+        self.state = torch.tensor([seed + 7919 * rank, 0, 1, 0], dtype=torch.int64, device=dev)
+        self.set_lr(lr)
         self._train_graph = None
         self._train_graphs = [None, None]
         self._loss_ptr = {}          # slot -> where that slot's graph writes the mean loss (default: self.loss)
@@ -109,6 +114,13 @@ class FusionEngine:
         self._subset_masks = {}
         self._copy_stream = None
         self.launches_per_step = 0
+
+    def set_lr(self, lr: float) -> None:
+        """Learning rate of every later optimizer step, captured graphs included (stream-ordered device write)."""
+        import struct
+        self.lr = float(lr)
+        bits = struct.unpack("<I", struct.pack("<f", self.lr))[0]
+        self.state[3:4].copy_(torch.tensor([bits], dtype=torch.int64), non_blocking=False)
 
     # -- enqueue helpers (all on the current stream) ---------------------------------
     def _call(self, training: bool, slot: int = 0) -> N.FusionCall:
@@ -146,7 +158,7 @@ class FusionEngine:
             # reduce-scatter + norm over NVLink peer memory, then clip + AdamW (+ bf16 re-pack + state advance
             # in the same launch on the tensor-core path) from the local reduced arena
             args = (ctypes_ref(self.plan.shape), ctypes_ref(self.dp_comm), self.arena.data_ptr(),
-                    self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.state.data_ptr(), self.lr,
+                    self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.state.data_ptr(), -1.0,
                     self.betas[0], self.betas[1], self.eps, self.wd, 1.0, self.max_norm)
             if self.arena_bf16 is not None:
                 N.check(lib.msf_dp_optimizer_step_packed(*args, self.arena_bf16.data_ptr(), 1, st))
@@ -167,14 +179,14 @@ class FusionEngine:
             # clip + AdamW + bf16 re-pack + train-state advance in one kernel
             N.check(lib.msf_fusion_optimizer_step_packed(
                 ctypes_ref(self.plan.shape), self.arena.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
-                self.exp_avg_sq.data_ptr(), self.state.data_ptr(), self.lr, self.betas[0], self.betas[1], self.eps,
+                self.exp_avg_sq.data_ptr(), self.state.data_ptr(), -1.0, self.betas[0], self.betas[1], self.eps,
                 self.wd, 1.0, self.max_norm, self.sq_norm.data_ptr(), self.arena_bf16.data_ptr(),
                 1 | (N.MSF_OPT_NORM_GIVEN if norm_given else 0), st))
             return True
         # global-norm clip + AdamW, skipping the dead q/k slots' moments (their gradients are exact zeros)
         N.check(lib.msf_fusion_optimizer_step(ctypes_ref(self.plan.shape), self.arena.data_ptr(),
                                               self.grad.data_ptr(), self.exp_avg.data_ptr(),
-                                              self.exp_avg_sq.data_ptr(), self.state.data_ptr(), self.lr,
+                                              self.exp_avg_sq.data_ptr(), self.state.data_ptr(), -1.0,
                                               self.betas[0], self.betas[1], self.eps, self.wd, 1.0, self.max_norm,
                                               self.sq_norm.data_ptr(), st))
         return False

@@ -24,7 +24,8 @@ lib = pkg.lib()
 lib.msf_debug_timeline.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int]
 lib.msf_debug_timeline.restype = ctypes.c_int
 buf = ctypes.create_string_buffer(1 << 18)
-ORDER = ["proj_gemm.cu#0", "chain2_gemm.cu#0", "head_gemm.cu#0", "fusion_bf16.cu#0", "chain2_gemm.cu#1", "fusion_bf16.cu#1", "tc_gemm.cu#1",
+CH = "chain2_gemm.cu" if os.environ.get("MSF_CHAIN") == "v2" else "chain3_gemm.cu"
+ORDER = ["proj_gemm.cu#0", CH + "#0", "head_gemm.cu#0", "fusion_bf16.cu#0", CH + "#1", "fusion_bf16.cu#1", "tc_gemm.cu#1",
          "opt_pack.cu#0"]
 for rep in range(3):
     N.check(lib.msf_debug_timeline(buf, len(buf), 1))   # clear

@@ -202,18 +202,25 @@ def test_projection_kernel_input_widths():
         assert float((got - ref).abs().max()) <= 1e-2, key
 
 
-@pytest.mark.parametrize("variant", ["pair", "pair2", "v1"])
-def test_chain_kernel_variants_agree(variant, monkeypatch):
-    """The opt-in chain kernels — CTA pairs (tcgen05 cta_group::2: chainp_kernel, chain2p_kernel) and the
-    un-pipelined chain_kernel — against the default chain2_kernel on a train pass (ragged batch: 7 row tiles,
-    so the last CTA pair has an empty second tile)."""
-    ops, N, model, plan, arena, arena16, xs, mask, labels = _setup(800, seed=31)
+@pytest.mark.parametrize("batch", [800, 4096])
+@pytest.mark.parametrize("variant,cluster", [("v1", None), ("v2", None), (None, "1"), (None, "2"), (None, "8")])
+def test_chain_kernel_variants_agree(variant, cluster, batch, monkeypatch):
+    """The default chain3_kernel (clusters of 4 CTAs sharing every weight fetch by TMA multicast) against the
+    un-pipelined chain_kernel, the round-1 chain2_kernel and its own other cluster sizes on a train pass.  B = 800 is
+    ragged: 7 row tiles, so a cluster has surplus CTAs running on out-of-range rows; B = 4096 is the benchmarked
+    shape (32 tiles = 8 full clusters of 4 per modality)."""
+    ops, N, model, plan, arena, arena16, xs, mask, labels = _setup(batch, seed=31)
     kw = dict(precision=N.MSF_PREC_BF16, training=True, p=0.1, seed=5, offset=2, arena_bf16=arena16)
     monkeypatch.delenv("MSF_CHAIN", raising=False)
+    monkeypatch.delenv("MSF_CHAIN_CLUSTER", raising=False)
     ref = ops.fusion_train_pass_raw(plan, arena, xs, mask, labels, smoothing=0.05, **kw)
-    monkeypatch.setenv("MSF_CHAIN", variant)
+    if variant is not None:
+        monkeypatch.setenv("MSF_CHAIN", variant)
+    if cluster is not None:
+        monkeypatch.setenv("MSF_CHAIN_CLUSTER", cluster)
     got = ops.fusion_train_pass_raw(plan, arena, xs, mask, labels, smoothing=0.05, **kw)
-    monkeypatch.delenv("MSF_CHAIN")
+    monkeypatch.delenv("MSF_CHAIN", raising=False)
+    monkeypatch.delenv("MSF_CHAIN_CLUSTER", raising=False)
     torch.cuda.synchronize()
     assert torch.isfinite(got[2]).all()
     assert float((got[0] - ref[0]).abs().max()) <= 5e-4           # logits
