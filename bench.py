@@ -45,7 +45,8 @@ def _peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             p = json.load(f)
-        return {"hbm_gbs": p["hbm_gbs"], "tflops": p["bf16_tflops_sustained"], "src": "measured (sustained)"}
+        return {"hbm_gbs": p["hbm_gbs"], "tflops": p["bf16_tflops_sustained"], "tflops_burst": p.get("bf16_tflops"),
+                "src": "measured (sustained)"}
     except Exception:  # noqa: BLE001 - profiling guide's stated fallback
         return {"hbm_gbs": 6650.0, "tflops": 1400.0, "src": "fallback"}
 
@@ -128,11 +129,15 @@ def oracle_cpu_throughput(torch, budget_s: float, warmup: int = 1, steps=None):
     def draw(shape):
         return (torch.rand(shape, generator=g) < keep).float() / keep
 
+    # dropout masks are drawn OUTSIDE the timed region (a pool of 4 sets, used in turn): the reference's
+    # bernoulli_ is one pass per site, three passes of torch.rand/compare/divide here would handicap the baseline
+    pool = [{"input": {m: draw((BATCH, d)) for m, d in DIMS.items()},
+             "proj": {m: draw((BATCH, HIDDEN)) for m in names},
+             "attn": {f"{q}_to_{k}": draw((BATCH, HEADS, 1, 1)) for q in names for k in names if q != k},
+             "cls": draw((BATCH, HIDDEN))} for _ in range(4)]
+
     def one_step(step):
-        drops = {"input": {m: draw((BATCH, d)) for m, d in DIMS.items()},
-                 "proj": {m: draw((BATCH, HIDDEN)) for m in names},
-                 "attn": {f"{q}_to_{k}": draw((BATCH, HEADS, 1, 1)) for q in names for k in names if q != k},
-                 "cls": draw((BATCH, HIDDEN))}
+        drops = pool[step % len(pool)]
         logits, _ = fusion_oracle.hybrid_fusion_forward(sd, names, HEADS, xs, mask, drops=drops)
         loss = fusion_oracle.cross_entropy_label_smoothing(logits, labels, SMOOTHING)
         grads = torch.autograd.grad(loss, list(sd.values()))
@@ -155,7 +160,8 @@ def oracle_cpu_throughput(torch, budget_s: float, warmup: int = 1, steps=None):
         i += 1
     med = statistics.median(times)
     return {"value": BATCH / med, "unit": "windows/s", "cores": cores, "kind": "port",
-            "sample": f"{len(times)} train steps of {BATCH} windows (oracle fp32 + autograd + AdamW), median",
+            "sample": f"{len(times)} train steps of {BATCH} windows (oracle fp32 + autograd + AdamW, dropout masks "
+                      f"pre-drawn outside the timed region), median; a reported baseline, not the target",
             "ms_per_step": med * 1e3}
 
 
@@ -182,7 +188,8 @@ def workload_config(n):
     return {"workload": "HybridFusion train step (BASELINE configs[1]): fwd + CE(ls 0.05) + bwd + clip + AdamW",
             "per_gpu_batch": BATCH, "global_batch": BATCH * n, "modalities": 4, "feature_dim": 128,
             "hidden": HIDDEN, "heads": HEADS, "classes": CLASSES, "dropout": DROPOUT,
-            "parallelism": f"dp{n} (batch-sharded, NCCL grad all-reduce)" if n > 1 else "single GPU"}
+            "parallelism": f"dp{n} (batch-sharded, replicated parameters, gradient exchange per step)" if n > 1
+                           else "single GPU"}
 
 
 def run_ours(args):
@@ -237,20 +244,30 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, min_seconds=0.5, max_repeats=400):
+        """`steps` calls of fn between two CUDA events on the launching stream (barrier + synchronize on both
+        sides, max over ranks), repeated until the timed regions add up to >= min_seconds so the clock sampler
+        sees the load; returns (median ms per call, repeats)."""
         for i in range(warmup):
             fn(i)
-        barrier()
-        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        start.record()
-        for i in range(steps):
-            fn(warmup + i)
-        stop.record()
-        barrier()
-        ms = torch.tensor([start.elapsed_time(stop)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)  # max over ranks
-        return float(ms) / steps
+        samples, total, k = [], 0.0, warmup
+        while True:
+            barrier()
+            start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            start.record()
+            for i in range(steps):
+                fn(k + i)
+            stop.record()
+            barrier()
+            k += steps
+            ms = torch.tensor([start.elapsed_time(stop)], device=dev)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)  # max over ranks
+            samples.append(float(ms) / steps)
+            total += float(ms)
+            if total >= min_seconds * 1e3 or len(samples) >= max_repeats:
+                break
+        return statistics.median(samples), len(samples)
 
     # every ring batch is an input slot of its own (its own captured graph): the step reads it in place
     ring_slots = [eng.add_resident_batch(*b) for b in ring] if not args.no_graph else None
@@ -271,18 +288,25 @@ def run_ours(args):
         for loss in eng.train_stream(host[i % len(host)] for i in range(first, first + n)):
             losses.append(loss)
 
-    def timed_e2e(steps, warmup):
+    def timed_e2e(steps, warmup, min_seconds=0.25, max_repeats=100):
         e2e_loop(0, warmup)
-        barrier()
-        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        start.record()
-        e2e_loop(warmup, steps)
-        stop.record()
-        barrier()
-        ms = torch.tensor([start.elapsed_time(stop)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms) / steps
+        samples, total, first = [], 0.0, warmup
+        while True:
+            barrier()
+            start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            start.record()
+            e2e_loop(first, steps)
+            stop.record()
+            barrier()
+            first += steps
+            ms = torch.tensor([start.elapsed_time(stop)], device=dev)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            samples.append(float(ms) / steps)
+            total += float(ms)
+            if total >= min_seconds * 1e3 or len(samples) >= max_repeats:
+                break
+        return statistics.median(samples), len(samples)
 
     mark("engine and batches built")
     warm = max(3, args.warmup)
@@ -294,11 +318,11 @@ def run_ours(args):
     per_step_launches = eng_launches(lib, before, eng)
     mark("launch count taken")
 
-    # Steps per graph launch (FusionEngine.train_slots): 8 on one GPU, where the gap between two graph launches is
-    # otherwise paid every step (155.0 -> 150.7 us at 4, 149.8 at 24); 1 under data parallelism.  Still exactly
-    # args.steps optimizer steps inside the timed region, each with the full work of a single step; what does not
-    # fill a group runs as single-step launches.
-    G = args.steps_per_graph if args.steps_per_graph > 0 else (8 if world == 1 and args.steps >= 16 else 1)
+    # Steps per graph launch (FusionEngine.train_slots): 8, so the gap between two graph launches is paid once per
+    # eight steps, at every N (the same way on one GPU and under data parallelism).  Still exactly args.steps
+    # optimizer steps inside every timed region, each with the full work of a single step; what does not fill a
+    # group runs as single-step launches.
+    G = args.steps_per_graph if args.steps_per_graph > 0 else (8 if args.steps >= 16 else 1)
     if ring_slots is None or ring_n % G:
         G = 1   # short runs (profiler passes with a handful of steps) and eager mode keep one step per launch
     if G > 1:
@@ -309,31 +333,78 @@ def run_ours(args):
         for j in range(ring_n // G):   # capture outside the timed region
             resident_group(j)
         torch.cuda.synchronize()
+    warm = max(3, args.warmup)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     if G > 1:
         groups, rest = divmod(args.steps, G)
-        warm_groups = -(-warm // G)
+        calls = groups + rest   # launches per timed region: `groups` graph launches of G steps + `rest` single steps
 
-        def launch(j):   # warm-up groups, then the timed groups, then the remaining single steps
-            if j < warm_groups + groups:
+        def launch(j):
+            if j % calls < groups:
                 resident_group(j)
             else:
                 resident_step(j)
 
-        ms = timed(launch, groups + rest, warm_groups) * (groups + rest) / args.steps
-        warm = warm_groups * G
+        ms_call, repeats = timed(launch, calls, -(-warm // G))
+        ms = ms_call * calls / args.steps
     else:
-        ms = timed(resident_step, args.steps, warm)
+        ms, repeats = timed(resident_step, args.steps, warm)
     clocks = sampler.stop() if rank == 0 else None
     mark("resident loop timed")
-    ms_e2e = timed_e2e(max(5, min(args.steps, 100)), 3)
+    ms_e2e, repeats_e2e = timed_e2e(max(5, min(args.steps, 100)), 3)
 
     mark("e2e loop timed")
     # every rank runs the profiled steps: the eager step contains the gradient all-reduce
     kern = profile_dominant_kernel(torch, pkg, eng, ring, ring_n)
     mark("kernel profile done")
+
+    # Data-parallel correctness, outside the timed region: every rank's parameter arena (fp32 master and the bf16
+    # compute copy) must be bit-identical after the run.  Compared as 64-bit checksums (max == min over ranks).
+    replicas_identical = None
+    if world > 1:
+        def checksum(t):
+            v = t.view(torch.int32).to(torch.int64)
+            return torch.stack([v.sum(), (v * torch.arange(1, v.numel() + 1, device=dev) % 1000003).sum()])
+        cs = checksum(eng.arena)
+        if eng.arena_bf16 is not None:
+            raw = eng.arena_bf16.view(torch.uint8)
+            cs = torch.cat([cs, checksum(raw[:raw.numel() // 4 * 4])])
+        hi, lo = cs.clone(), cs.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        replicas_identical = bool(torch.equal(hi, lo))
+    comm_used = eng.comm
+
+    # BASELINE configs[3] (SURVEY "Config 4"): STRONG scaling, global batch 32768 split over the N ranks
+    strong = None
+    if not args.no_strong and 32768 % world == 0:
+        per = 32768 // world
+        torch.manual_seed(0)
+        model_s = fusion.HybridFusion(DIMS, hidden_dim=HIDDEN, num_classes=CLASSES, num_heads=HEADS, dropout=DROPOUT)
+        eng_s = engine_mod.FusionEngine(model_s, per, precision=precision, label_smoothing=SMOOTHING,
+                                        max_grad_norm=1.0, seed=1234, use_graph=not args.no_graph)
+        n_ring = max(2, min(8, (160 << 20) // (per * 2072) + 1))     # > 126 MiB L2 of inputs in rotation
+        ring_s = [synthetic_batch(torch, 3000 + 97 * rank + i, per, device=dev) for i in range(n_ring)]
+        slots_s = [eng_s.add_resident_batch(*b) for b in ring_s] if not args.no_graph else None
+
+        def strong_step(i):
+            if slots_s is not None:
+                eng_s.train_step_slot(slots_s[i % n_ring])
+            else:
+                eng_s.load_batch(*ring_s[i % n_ring])
+                eng_s.train_step_resident()
+
+        for i in range(n_ring):
+            strong_step(i)
+        torch.cuda.synchronize()
+        ms_s, rep_s = timed(strong_step, max(4, min(args.steps, 20)), 3, min_seconds=0.2)
+        strong = {"global_batch": 32768, "per_gpu_batch": per, "ms_per_step": ms_s, "value": 32768 / (ms_s * 1e-3),
+                  "unit": "windows/s", "scaling": "strong", "steps": max(4, min(args.steps, 20)), "repeats": rep_s,
+                  "collective": eng_s.comm}
+        mark("strong-scaling record timed")
+        eng = eng_s   # finish() drops the graphs of the live engine
 
     def finish():
         """Leave without tearing the NCCL communicator down: destroy_process_group() blocks while CUDA
@@ -355,20 +426,30 @@ def run_ours(args):
     step_tflops = FLOP_TRAIN * BATCH / (ms * 1e-3) / 1e12  # per GPU, whole fused step
     line = {
         "metric": METRIC, "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps,
-        "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
-        "config": dict(workload_config(world), l2=f"inputs rotate through a ring of {ring_n} resident batches "
-                       f"({ring_n * in_bytes / 2**20:.0f} MiB > 126 MiB L2), read in place", cuda_graph=not args.no_graph,
-                       steps_per_graph_launch=G),
+        "config": workload_config(world),
+        "run": {"l2": f"inputs rotate through a ring of {ring_n} resident batches "
+                      f"({ring_n * in_bytes / 2**20:.0f} MiB > 126 MiB L2), read in place",
+                "cuda_graph": not args.no_graph, "steps_per_graph_launch": G, "warmup_done": max(warm, -(-warm // G) * G),
+                "repeats": repeats, "timed_region_ms": ms * args.steps * repeats,
+                "ms_per_step_is": "median over `repeats` timed regions of exactly `steps` steps each",
+                "collective": {"none": "none (single GPU)",
+                               "p2p": "fused NVLink peer-memory reduce-scatter + all-gather kernels (dp_optim.cu), no NCCL on the data path",
+                               "nccl": "ncclAllReduce of the flat fp32 gradient arena"}[comm_used]},
         "clocks": clocks,
         "e2e": {"value": BATCH * world / (ms_e2e * 1e-3), "unit": "windows/s", "h2d_bytes_per_step": in_bytes,
-                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e, "repeats": repeats_e2e,
                 "api": "FusionEngine.train_stream(host batches): 2-slot pipeline, H2D of batch i+1 overlaps step i"},
         "gpu_launches": per_step_launches * args.steps,
         "gpu_launches_per_step": per_step_launches,
         "roofline": roofline_entry(kern, peaks, step_tflops),
         "final_loss": losses[-1] if losses else None,
     }
+    if replicas_identical is not None:
+        line["replicas_identical"] = replicas_identical
+    if strong is not None:
+        line["strong_32768"] = strong
     if world == 1 and not args.no_cpu_baseline:
         cpu = oracle_cpu_throughput(torch, budget_s=12.0)
         line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -579,11 +660,15 @@ def run_ece(args):
     os.write(json_fd, (json.dumps(line) + "\n").encode())
 
 
-def profile_dominant_kernel(torch, pkg, eng, ring, ring_n, steps=12):
-    """Per-launch durations of the dominant kernel (tc_gemm_kernel: every dense contraction of the step),
-    measured live with CUDA events on the launching stream (msf_prof_*).  Eager launches, the same
-    ring of batches; a device-side sleep in front of each step lets the host queue the whole step
-    so the events bracket kernels, not launch gaps."""
+def profile_dominant_kernel(torch, pkg, eng, ring, ring_n, steps=12, chain_reps=16):
+    """Per-launch durations measured live with CUDA events on the launching stream (msf_prof_*), eager launches
+    over the same ring of batches; a device-side sleep in front of each step lets the host queue the whole step so
+    the events bracket kernels, not launch gaps.  Two passes: (1) every tensor-core launch bracketed on its own
+    (the event records serialise the step: no programmatic-dependent-launch overlap, so these are upper bounds);
+    (2) the dominant kernel, the chained pair GEMMs, issued `chain_reps` times back to back inside ONE bracket
+    (msf_prof_enable(R): the kernel only reads its operands and overwrites its outputs), so its average launch
+    duration includes the prologue overlap it has in the real step and excludes the event records.  Operands are
+    L2-resident in both, as in the step (they were written by the preceding kernel)."""
     import ctypes
     if eng.prec != pkg.native.MSF_PREC_BF16:
         return None
@@ -593,22 +678,30 @@ def profile_dominant_kernel(torch, pkg, eng, ring, ring_n, steps=12):
         eng.load_batch(*ring[i % ring_n])
         eng._enqueue_train_step()
     torch.cuda.synchronize()
-    pkg.native.check(lib.msf_prof_enable(1))
-    for i in range(steps):
-        eng.load_batch(*ring[(3 + i) % ring_n])
-        torch.cuda._sleep(3_000_000)
-        eng._enqueue_train_step()
-    buf = ctypes.create_string_buffer(1 << 16)
-    pkg.native.check(lib.msf_prof_report(buf, len(buf)))
-    pkg.native.check(lib.msf_prof_enable(0))
+
+    def one_pass(mode, n_steps):
+        pkg.native.check(lib.msf_prof_enable(mode))
+        for i in range(n_steps):
+            eng.load_batch(*ring[(3 + i) % ring_n])
+            torch.cuda._sleep(3_000_000)
+            eng._enqueue_train_step()
+        buf = ctypes.create_string_buffer(1 << 16)
+        pkg.native.check(lib.msf_prof_report(buf, len(buf)))
+        pkg.native.check(lib.msf_prof_enable(0))
+        rows = []
+        for line in buf.value.decode().splitlines():
+            label, n, ms, flops = line.split("\t")
+            rows.append({"launch": label, "launches": int(n), "us_per_launch": float(ms) * 1e3 / int(n),
+                         "gflop_per_launch": float(flops) / int(n) / 1e9})
+        return rows
+
+    rows = one_pass(1, steps)
+    chain_rows = [r for r in one_pass(chain_reps, 4) if "chain" in r["launch"]]
     for dst, src in zip((eng.arena, eng.exp_avg, eng.exp_avg_sq, eng.state), snap):
         dst.copy_(src)
-    rows = []
-    for line in buf.value.decode().splitlines():
-        label, n, ms, flops = line.split("\t")
-        rows.append({"launch": label, "launches": int(n), "us_per_launch": float(ms) * 1e3 / int(n),
-                     "gflop_per_launch": float(flops) / int(n) / 1e9})
-    return {"steps": steps, "rows": rows}
+    if eng.arena_bf16 is not None:
+        eng.arena_bf16.copy_(eng.plan.pack_bf16(eng.arena))
+    return {"steps": steps, "rows": rows, "chain_rows": chain_rows, "chain_reps": chain_reps}
 
 
 def roofline_entry(kern, peaks, step_tflops):
@@ -632,20 +725,29 @@ def roofline_entry(kern, peaks, step_tflops):
         n = sum(r["launches"] for r in rows)
         return us, gf, n
 
-    chain = [r for r in kern["rows"] if "chain" in r["launch"]] or kern["rows"]
+    chain = kern.get("chain_rows") or [r for r in kern["rows"] if "chain" in r["launch"]] or kern["rows"]
     us, gf, n = agg(chain)
     us_all, gf_all, n_all = agg(kern["rows"])
     achieved = gf * 1e9 / (us * 1e-6) / 1e12
     all_tf = gf_all * 1e9 / (us_all * 1e-6) / 1e12
-    return {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-            "frac": achieved / peaks["tflops"], "traffic": traffic, "peak_source": peaks["src"],
-            "kernel": "chain_kernel (tcgen05/TMEM/TMA chained pair GEMMs; %d launches per step)" % (n // kern["steps"]),
-            "avg_launch_us": us / n, "algorithmic_gflop_per_launch": gf / n,
-            "all_gemm_kernels": {"launches_per_step": n_all // kern["steps"], "achieved": all_tf,
-                                 "frac": all_tf / peaks["tflops"], "us_per_step": us_all / kern["steps"]},
-            "whole_step_tflops": step_tflops, "whole_step_frac": step_tflops / peaks["tflops"],
-            "per_launch": [{k: (round(v, 3) if isinstance(v, float) else v) for k, v in r.items()} | {
-                "launches": r["launches"] // kern["steps"]} for r in kern["rows"]]}
+    burst = peaks.get("tflops_burst")
+    out = {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+           "frac": achieved / peaks["tflops"], "traffic": traffic, "peak_source": peaks["src"],
+           "kernel": "chain3_kernel (tcgen05/TMEM/TMA chained pair GEMMs, weights multicast over a CTA cluster; "
+                     "2 launches per step)",
+           "avg_launch_us": us / n, "algorithmic_gflop_per_launch": gf / n,
+           "how": "CUDA events around %d back-to-back launches of each of the step's two chain launches, inside an "
+                  "eager train step (operands L2-resident as in the step)" % kern.get("chain_reps", 1),
+           "all_gemm_kernels": {"launches_per_step": n_all // kern["steps"], "achieved": all_tf,
+                                "frac": all_tf / peaks["tflops"], "us_per_step": us_all / kern["steps"],
+                                "how": "each launch bracketed by its own event pair (serialised: upper bounds)"},
+           "whole_step_tflops": step_tflops, "whole_step_frac": step_tflops / peaks["tflops"],
+           "per_launch": [{k: (round(v, 3) if isinstance(v, float) else v) for k, v in r.items()} | {
+               "launches": r["launches"] // kern["steps"]} for r in kern["rows"]]}
+    if burst:
+        out["frac_of_burst_peak"] = achieved / burst
+        out["whole_step_frac_of_burst_peak"] = step_tflops / burst
+    return out
 
 
 def eng_launches(lib, before, eng):
@@ -675,6 +777,8 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("MSF_BENCH_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true",
+                    help="skip the strong-scaling sub-record (BASELINE configs[3]: global batch 32768 split N ways)")
     ap.add_argument("--packed-host", action="store_true",
                     help="train workload, e2e leg: host batches in FusionEngine.pinned_batch() buffers (one H2D "
                          "transfer per batch instead of six); not measured yet")

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define MSF_ABI_VERSION 2
+#define MSF_ABI_VERSION 3
 #define MSF_MAX_MODALITIES 8
 
 enum {
@@ -97,7 +97,28 @@ typedef struct msf_fusion_call {
                                    squares of grad_params as written (weight matrices: summed by the weight-gradient
                                    GEMM's epilogue; bias / gating slots: by a small kernel beside it); see
                                    MSF_OPT_NORM_GIVEN */
+  /* Optional per-modality LayerNorm between the encoders and the fusion model (src/train.py:170-171,267-268:
+   * nn.LayerNorm(D_m) on every encoder output): x[m] are then the RAW encoder outputs and the projection kernel
+   * normalises each row in its input phase, y = (x - mean) * rstd * ln_weight + ln_bias (biased variance), before
+   * mask and dropout.  Both NULL for a modality = no LayerNorm there.  Only where
+   * msf_fusion_layer_norm_fused() says 1 (otherwise call msf_layer_norm_forward first and leave these NULL).
+   * grad_x[m] is then the gradient with respect to the NORMALISED rows: msf_layer_norm_backward turns it into the
+   * gradient with respect to x[m] and the gradients of ln_weight / ln_bias. */
+  const float* ln_weight[MSF_MAX_MODALITIES];
+  const float* ln_bias[MSF_MAX_MODALITIES];
+  float ln_eps;
 } msf_fusion_call;
+
+/* ---- per-modality LayerNorm (src/train.py:170-171,267-268) ------------------ */
+/* 1 if msf_fusion_forward / _train_pass / _infer_pass apply msf_fusion_call.ln_* inside the projection kernel for
+ * this shape and precision (tensor-core path, in_dims % 64 == 0), else 0. */
+int msf_fusion_layer_norm_fused(const msf_fusion_shape* shape, int32_t precision);
+/* y[rows, dim] = (x - mean) * rstd * gamma + beta per row (gamma / beta may be NULL), fp32, dim <= 512. */
+int msf_layer_norm_forward(const float* x, const float* gamma, const float* beta, float* y, int64_t rows, int32_t dim,
+                           float eps, void* stream);
+/* dx (may be NULL), dgamma, dbeta (may be NULL; overwritten) from dy and the forward input x. */
+int msf_layer_norm_backward(const float* x, const float* gamma, const float* dy, float* dx, float* dgamma, float* dbeta,
+                            int64_t rows, int32_t dim, float eps, void* stream);
 
 /* ---- library ------------------------------------------------------------ */
 int msf_abi_version(void);
@@ -167,7 +188,7 @@ int msf_fusion_infer_pass(const msf_fusion_shape* shape, const msf_fusion_call* 
 int msf_debug_head_stamps(int64_t* out16);
 /* Same for the last chained pair-GEMM launch: wait-time accounting of CTA 0 (chain3_gemm.cu; compiled into the timeline build only,
  * MSF_E_UNSUPPORTED otherwise; MSF_CHAIN=v2: chain2_gemm.cu). */
-int msf_debug_chain_stamps(int64_t* out16);
+int msf_debug_chain_stamps(int64_t* out32);   /* 32 entries (chain2_gemm.cu fills the first 16) */
 /* Phase stamps of CTA 0 of the last input-projection launch (proj_gemm.cu). */
 int msf_debug_proj_stamps(int64_t* out16);
 /* HybridFusion.compute_adaptive_weights (src/fusion.py:429-479) stand-alone:

@@ -11,7 +11,7 @@ MSF_MAX_MODALITIES = 8
 MSF_PREC_F32, MSF_PREC_BF16 = 0, 1
 MSF_TRAIN_DEAD_SLOTS_ZERO = 1
 MSF_OPT_NORM_GIVEN = 2
-MSF_ABI_VERSION = 2
+MSF_ABI_VERSION = 3
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -54,6 +54,9 @@ class FusionCall(Structure):
         ("grad_params", c_void_p),
         ("grad_x", c_void_p * MSF_MAX_MODALITIES),
         ("grad_sq", c_void_p),
+        ("ln_weight", c_void_p * MSF_MAX_MODALITIES),
+        ("ln_bias", c_void_p * MSF_MAX_MODALITIES),
+        ("ln_eps", c_float),
     ]
 
 
@@ -78,6 +81,10 @@ class LstmSeq(ctypes.Structure):  # msf_lstm_seq
 # name -> (restype, argtypes); every symbol include/msf_b200.h declares
 PROTOTYPES = {
     "msf_abi_version": (c_int32, []),
+    "msf_fusion_layer_norm_fused": (c_int32, [POINTER(FusionShape), c_int32]),
+    "msf_layer_norm_forward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p]),
+    "msf_layer_norm_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
+                                          c_float, c_void_p]),
     "msf_struct_sizes": (c_int32, [POINTER(c_int32), POINTER(c_int32)]),
     "msf_last_error": (c_char_p, []),
     "msf_launch_count": (c_uint64, []),

@@ -32,10 +32,15 @@ namespace {
 
 constexpr int C3_THREADS = 384;
 constexpr int C3_EPI_WARPS = 8;
-constexpr int C3_W_SLOTS = 4, C3_A_SLOTS = 3, C3_U_SLOTS = 3;
+#ifndef C3_CFG_W
+#define C3_CFG_W 4
+#define C3_CFG_A 3
+#define C3_CFG_U 3
+#endif
+constexpr int C3_W_SLOTS = C3_CFG_W, C3_A_SLOTS = C3_CFG_A, C3_U_SLOTS = C3_CFG_U;
 constexpr uint32_t C3_BLK = 128 * 64 * 2;  // one k-block of a 128-row operand: 128 rows x 64 bf16
 constexpr size_t C3_SMEM_LIMIT = 232448;
-constexpr int C3_NBAR = 2 * C3_W_SLOTS + 2 * C3_A_SLOTS + 2 * C3_U_SLOTS + 6;   // even: the bias row behind the barriers is read as float4
+constexpr int C3_NBAR = (2 * C3_W_SLOTS + 2 * C3_A_SLOTS + 3 * C3_U_SLOTS + 7 + 1) & ~1;   // even: the bias row behind the barriers is read as float4
 
 struct Ring {
   int slot, n;
@@ -100,6 +105,20 @@ __device__ __forceinline__ void c3_tmem_wait32(uint32_t (&r)[32]) {
                : "memory");
 }
 
+// 32 fp32 values of this thread's row -> 32 TMEM columns (complete after c3_tmem_wait_st)
+__device__ __forceinline__ void c3_tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void c3_tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 struct Raw32 {
   uint4 q[4];
 };
@@ -131,7 +150,8 @@ __device__ __forceinline__ void st_swz8(unsigned char* blk, int trow, int c8, co
 //  [7] epilogue: first block start  [8] epilogue: waits for ACC  [9] epilogue end  [10] W producer: waits for free slots
 //  [11] W producer end  [12] first operands landed (MMA thread)
 #ifdef MSF_TIMELINE
-__device__ long long g_chain3_stamps[16];
+__device__ long long g_chain3_stamps[32];
+#define C3_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 128 && item_cnt == 0) g_chain3_stamps[i] = clock64(); } while (0)
 #define C3_T0() const long long _t0 = clock64()
 #define C3_ACC(i) do { dbg_acc[(i) & 3] += clock64() - _t0; } while (0)
 #define C3_FLUSH(i) do { if (blockIdx.x == 0) g_chain3_stamps[i] = dbg_acc[(i) & 3]; } while (0)
@@ -141,15 +161,17 @@ __device__ long long g_chain3_stamps[16];
 #define C3_ACC(i)
 #define C3_FLUSH(i)
 #define C3_SET(i)
+#define C3_STAMP(i)
 #endif
 
-template <int MODE>
+template <int MODE, int KBT>
 __global__ void __launch_bounds__(C3_THREADS, 1) chain3_kernel(const __grid_constant__ ChainLaunch L) {
   TL_KERNEL(MODE);
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t off0 = smem_u32(smem_raw);
   const uint32_t base = (off0 + 1023u) & ~1023u;   // identical in every CTA of the cluster (same kernel, same layout)
-  const int H = L.H, KB = L.H >> 6, M = L.M, C = L.cluster;
+  constexpr int KB = KBT;                          // 64-column k-blocks of the hidden size: 2 or 4
+  const int H = L.H, M = L.M, C = L.cluster;
   const uint32_t WB = (uint32_t)H * 128u;           // one weight k-block: H rows x 64 bf16
   const uint32_t w_base = base;
   const uint32_t a_base = w_base + C3_W_SLOTS * WB;
@@ -161,8 +183,9 @@ __global__ void __launch_bounds__(C3_THREADS, 1) chain3_kernel(const __grid_cons
   auto empty_a = [&](int s) { return bar_base + 8u * (2 * C3_W_SLOTS + C3_A_SLOTS + s); };
   auto u_full = [&](int s) { return bar_base + 8u * (2 * C3_W_SLOTS + 2 * C3_A_SLOTS + s); };              // block written
   auto u_free = [&](int s) { return bar_base + 8u * (2 * C3_W_SLOTS + 2 * C3_A_SLOTS + C3_U_SLOTS + s); }; // block reusable
-  const uint32_t bar_misc = bar_base + 8u * (2 * C3_W_SLOTS + 2 * C3_A_SLOTS + 2 * C3_U_SLOTS);
-  const uint32_t t_full = bar_misc, t_empty = bar_misc + 8u, acc_full = bar_misc + 16u, acc_empty = bar_misc + 24u;
+  auto x_full = [&](int s) { return bar_base + 8u * (2 * C3_W_SLOTS + 2 * C3_A_SLOTS + 2 * C3_U_SLOTS + s); };            // aux block landed (TMA)
+  const uint32_t bar_misc = bar_base + 8u * (2 * C3_W_SLOTS + 2 * C3_A_SLOTS + 3 * C3_U_SLOTS);
+  const uint32_t t_full = bar_misc, t_empty = bar_misc + 8u, acc_full = bar_misc + 16u, acc_ready = bar_misc + 24u;
   const uint32_t tmem_slot = bar_misc + 32u;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - off0));
   float* bias_s = reinterpret_cast<float*>(smem_raw + (bar_base + 8u * C3_NBAR - off0));   // H floats, restaged per phase
@@ -175,6 +198,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) chain3_kernel(const __grid_cons
   const int tile_groups = (L.row_tiles + C - 1) / C;
   const int n_citems = tile_groups * L.n_active;    // cluster items: (tile group, outer modality)
   const uint32_t tmem_cols = (2 * H <= 256) ? 256u : 512u;
+  constexpr int NX = (MODE == 1 ? 2 : 1) * KBT;   // aux k-blocks per item: the aux tile (+ backward: the P tile)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&L.map_a1);
@@ -182,6 +206,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) chain3_kernel(const __grid_cons
     tma_prefetch_desc(&L.map_w2);
     tma_prefetch_desc(&L.map_out1);
     tma_prefetch_desc(&L.map_out);
+    if (MODE == 1) tma_prefetch_desc(&L.map_aux2);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C3_W_SLOTS; ++s) {
@@ -193,13 +218,14 @@ __global__ void __launch_bounds__(C3_THREADS, 1) chain3_kernel(const __grid_cons
       mbar_init(empty_a(s), 1);
     }
     for (int s = 0; s < C3_U_SLOTS; ++s) {
-      mbar_init(u_full(s), C3_EPI_WARPS);
+      mbar_init(u_full(s), C3_EPI_WARPS / 2);   // the 4 warps that own the block's k-block
       mbar_init(u_free(s), 2);              // GEMM2 (or the store warp a second time) + the store warp
+      mbar_init(x_full(s), 1);
     }
     mbar_init(t_full, 1);
     mbar_init(t_empty, C3_EPI_WARPS);
     mbar_init(acc_full, 1);
-    mbar_init(acc_empty, C3_EPI_WARPS);
+    mbar_init(acc_ready, C3_EPI_WARPS);   // ACC holds the item's aux tile (and the previous item's ACC has been read)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -305,7 +331,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) chain3_kernel(const __grid_cons
           }
           tc_commit(t_full);
         };
-        auto g2 = [&](bool first) {   // ACC (+)= staged block . W2[:, k-block]^T, N = H
+        auto g2 = [&]() {   // ACC += staged block . W2[:, k-block]^T, N = H (ACC starts as the item's aux tile)
           { C3_T0(); mbar_wait(u_full(u.slot), u.phase); C3_ACC(3); }
           { C3_T0(); mbar_wait(full_w(w.slot), w.phase); C3_ACC(1); }
           tc_fence_after();
@@ -313,7 +339,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) chain3_kernel(const __grid_cons
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             tc_mma_bf16(acc_addr, smem_desc(a_addr + k * 32, 16, 1024), smem_desc(b_addr + k * 32, 16, 1024), idesc,
-                        (first && k == 0) ? 0u : 1u);
+                        1u);
           free_w(w.slot);
           tc_commit(u_free(u.slot));   // 1 of 2: GEMM2 no longer reads the staging block
           w.next();
@@ -321,16 +347,17 @@ __global__ void __launch_bounds__(C3_THREADS, 1) chain3_kernel(const __grid_cons
         };
         for (int ci = cluster_id; ci < n_citems; ci += n_clusters, ++item_cnt) {
           const int n = L.outer[item_outer(ci)].n;
+          for (int x = 0; x < NX; ++x) u.next();      // the item's aux blocks pass through the staging ring first
           if (n > 0) {
             g1();
             for (int i = 0; i < n; ++i) {
-              if (i == 0) {   // ACC of the previous item has been drained
-                mbar_wait(acc_empty, (item_cnt & 1u) ^ 1u);
+              if (i == 0) {   // the epilogue warps have read the previous item's ACC and written this item's aux tile
+                mbar_wait(acc_ready, item_cnt & 1u);
                 tc_fence_after();
               }
-              for (int kb = 0; kb + 1 < KB; ++kb) g2(i == 0 && kb == 0);
+              for (int kb = 0; kb + 1 < KB; ++kb) g2();
               if (i + 1 < n) g1();      // T is drained before the last staging block is written
-              g2(i == 0 && KB == 1);
+              g2();
             }
           }
           tc_commit(acc_full);
@@ -343,14 +370,28 @@ __global__ void __launch_bounds__(C3_THREADS, 1) chain3_kernel(const __grid_cons
       // =========================== TMA store ================================
       if (lane == 0) {
         Ring u(C3_U_SLOTS);
+        uint32_t item_cnt = 0;
         int pend = -1, pend_times = 0;   // staging block whose store has been committed but not yet released
         auto release_pending = [&]() {
           for (int t = 0; t < pend_times; ++t) mbar_arrive(u_free(pend));
           pend = -1;
         };
-        for (int ci = cluster_id; ci < n_citems; ci += n_clusters) {
+        for (int ci = cluster_id; ci < n_citems; ci += n_clusters, ++item_cnt) {
           const int o = item_outer(ci), m0 = item_m0(ci);
           const ChainOuter& O = L.outer[o];
+          // the item's aux tile (forward P_q, backward dS_k, then P_k) streams through the staging ring: the
+          // epilogue warps move it into ACC / reduce it to ReLU bits while the first GEMM1 is being fetched
+          if (pend >= 0) { tma_store_wait_read(); release_pending(); }   // never wait for a slot this thread still holds
+          for (int x = 0; x < NX; ++x) {
+            mbar_wait(u_free(u.slot), u.phase ^ 1u);
+            mbar_expect_tx(x_full(u.slot), C3_BLK);
+            tma_load_3d(u_base + (uint32_t)u.slot * C3_BLK, (MODE == 1 && x >= KB) ? &L.map_aux2 : &L.map_a1,
+                        (x % KB) * 64, m0, o, x_full(u.slot));
+            u.next();
+          }
+          // A parity wait cannot tell "two phases ago": do not look at a slot's "written" barrier before the
+          // aux use of that slot has been closed by the epilogue warps (they do that before signalling acc_ready).
+          mbar_wait(acc_ready, item_cnt & 1u);
           for (int i = 0; i < O.n; ++i)
             for (int kb = 0; kb < KB; ++kb) {
               mbar_wait(u_full(u.slot), u.phase);
@@ -378,13 +419,21 @@ __global__ void __launch_bounds__(C3_THREADS, 1) chain3_kernel(const __grid_cons
       }
     } else if (warp >= 4) {
       // =========================== epilogue =================================
+      // Warp (lq, cg) owns rows [32 lq, 32 lq + 32) of the k-blocks kb = cg, cg + 2: whole 64-column staging blocks,
+      // so a block is signalled by 4 warps and every warp runs NB = KB / 2 block hand-offs per pass.  Everything a
+      // pass needs from global memory (attention gates, aux rows, ReLU masks) is fetched BEFORE the wait for the
+      // tensor pipe; the pass itself only touches TMEM, registers and shared memory.
+      constexpr int NB = KBT / 2;        // k-blocks per warp per pass
+      constexpr int NG = 2 * NB;         // 32-column groups per thread per pass
       const DropCfg drop = resolve_drop(L.drop);
       const int lq = warp & 3, cg = (warp - 4) >> 2;
       const int trow = lq * 32 + lane;                 // row inside the tile = TMEM lane
       const int et = (int)threadIdx.x - 128;
       const uint32_t lane_base = (uint32_t)(lq * 32) << 16;
-      const int c_off = cg * 32;                       // this thread's 32 columns inside every 64-column k-block
-      Ring u(C3_U_SLOTS);
+      auto grp_kb = [&](int j) { return cg + 2 * (j >> 1); };                  // k-block of group j
+      auto grp_col = [&](int j) { return grp_kb(j) * 64 + (j & 1) * 32; };     // first column of group j in the tile
+      uint32_t blk0 = 0;                 // staging blocks handed off before this pass (all roles count the same way)
+      uint32_t xpar = 0u;                // per staging slot: parity of its next aux-block (TMA) use
       uint32_t t_cnt = 0, item_cnt = 0;
       uint32_t r0[32], r1[32];
       for (int ci = cluster_id; ci < n_citems; ci += n_clusters, ++item_cnt) {
@@ -394,6 +443,72 @@ __global__ void __launch_bounds__(C3_THREADS, 1) chain3_kernel(const __grid_cons
         const long long row = (long long)m0 + trow;
         const bool row_ok = row < L.rows;
 
+        // ---- aux blocks: the item's aux tile (forward P_q, backward dS_k) goes straight into the ACC columns of
+        // TMEM (GEMM2 accumulates on top of it; the final pass needs no global loads), backward also the P tile,
+        // reduced to one ReLU bit per column.  The store warp streams them through the staging ring by TMA; a
+        // thread reads its row of a block with conflict-free 16-byte shared-memory loads (128B swizzle).  This
+        // thread's cells of ACC were last read by this thread (previous item's final pass): program order suffices.
+        uint32_t relu_bits[NG];
+#pragma unroll
+        for (int x = 0; x < NX; ++x) {
+          const uint32_t idx = blk0 + (uint32_t)x, slot = idx % C3_U_SLOTS;
+          const uint32_t par = (xpar >> slot) & 1u;
+          xpar ^= 1u << slot;
+          const int kb = x % KBT;
+          if ((kb & 1) != cg) continue;                 // the other column group's block
+          mbar_wait(x_full(slot), par);
+          const unsigned char* xb = u_smem + slot * C3_BLK + trow * 128;
+          uint4 ch[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) ch[c] = *reinterpret_cast<const uint4*>(xb + ((c ^ (trow & 7)) << 4));
+          if (x < KBT) {   // aux tile -> fp32 -> ACC columns [kb*64, kb*64 + 64)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+              for (int c8 = 0; c8 < 4; ++c8) {
+                const uint32_t w[4] = {ch[4 * h + c8].x, ch[4 * h + c8].y, ch[4 * h + c8].z, ch[4 * h + c8].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  r0[8 * c8 + 2 * e] = row_ok ? (w[e] << 16) : 0u;              // bf16 -> fp32 bit patterns
+                  r0[8 * c8 + 2 * e + 1] = row_ok ? (w[e] & 0xffff0000u) : 0u;
+                }
+              }
+              c3_tmem_st32(tmem_base + lane_base + (uint32_t)(H + kb * 64 + 32 * h), r0);
+            }
+          } else {         // P tile -> ReLU bits of groups 2*(kb>>1), 2*(kb>>1) + 1
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint32_t bits = 0u;
+#pragma unroll
+              for (int c8 = 0; c8 < 4; ++c8) {
+                const uint32_t w[4] = {ch[4 * h + c8].x, ch[4 * h + c8].y, ch[4 * h + c8].z, ch[4 * h + c8].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  bits |= (bf_lo(w[e]) > 0.0f ? 1u : 0u) << (8 * c8 + 2 * e);
+                  bits |= (bf_hi(w[e]) > 0.0f ? 1u : 0u) << (8 * c8 + 2 * e + 1);
+                }
+              }
+              relu_bits[2 * (kb >> 1) + h] = bits;
+            }
+          }
+          // the row has been consumed (its values were used above): once the block's four reader warps are
+          // through, the slot goes back to the ring (both arrivals: an aux block has no GEMM2 / store reader)
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + cg) : "memory");
+          if (lq == 0 && lane == 0) {
+            // every use of a slot completes one phase of BOTH its barriers (the ring positions of all roles carry
+            // one parity per lap): close the "written" phase nobody waits for, then free the slot
+            for (int t = 0; t < C3_EPI_WARPS / 2; ++t) mbar_arrive(u_full(slot));
+            mbar_arrive(u_free(slot));
+            mbar_arrive(u_free(slot));
+          }
+        }
+        blk0 += (uint32_t)NX;
+        c3_tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_ready);
+        C3_STAMP(16);
+
         for (int i = 0; i < n; ++i) {
           const int zp = O.pair[i];
           if (MODE == 0) {   // value_proj bias of this pair -> shared memory (overlaps GEMM1)
@@ -402,20 +517,19 @@ __global__ void __launch_bounds__(C3_THREADS, 1) chain3_kernel(const __grid_cons
             for (int e = et; e < H; e += 32 * C3_EPI_WARPS) bias_s[e] = bsrc ? __ldg(bsrc + e) : 0.0f;
             asm volatile("bar.sync 1, %0;" ::"n"(32 * C3_EPI_WARPS) : "memory");
           }
-          float gate_mask = 1.0f;
-          if (MODE == 0 && L.mask != nullptr && row_ok) gate_mask = __ldg(L.mask + row * M + O.mask_col[i]);
-          const int sub = O.sub[i];
-          float* gate_out = (MODE == 0 && L.gate_out) ? L.gate_out + ((long long)zp * L.rows + row) * L.heads : nullptr;
-          const float* gate_in = (MODE == 1) ? L.gate_in + ((long long)zp * L.rows + row) * L.heads : nullptr;
-          int cur_head = -1;
-          float cur_gate = 0.0f;
-
-          // one 64-column k-block of T (this thread: 32 columns) -> one staging block
-          auto block1 = [&](uint32_t (&acc)[32], int kb) {
-            float gate[2];
+          // attention gates of this thread's 16-column groups (a group lies inside one head), before the wait
+          float gate[2 * NG];
+          {
+            float gate_mask = 1.0f;
+            if (MODE == 0 && L.mask != nullptr && row_ok) gate_mask = __ldg(L.mask + row * M + O.mask_col[i]);
+            const int sub = O.sub[i];
+            float* gate_out = (MODE == 0 && L.gate_out) ? L.gate_out + ((long long)zp * L.rows + row) * L.heads : nullptr;
+            const float* gate_in = (MODE == 1) ? L.gate_in + ((long long)zp * L.rows + row) * L.heads : nullptr;
+            int cur_head = -1;
+            float cur_gate = 0.0f;
 #pragma unroll
-            for (int g16 = 0; g16 < 2; ++g16) {
-              const int ca = kb * 64 + c_off + 16 * g16;   // column of the intermediate; a 16-column group lies in one head
+            for (int g = 0; g < 2 * NG; ++g) {
+              const int ca = grp_col(g >> 1) + 16 * (g & 1);
               const int head = L.head_shift >= 0 ? (ca >> L.head_shift) : ca / L.head_dim;
               if (head != cur_head) {
                 cur_head = head;
@@ -427,19 +541,25 @@ __global__ void __launch_bounds__(C3_THREADS, 1) chain3_kernel(const __grid_cons
                   cur_gate = row_ok ? __ldg(gate_in + head) : 0.0f;
                 }
               }
-              gate[g16] = cur_gate;
+              gate[g] = cur_gate;
             }
-            { C3_T0(); mbar_wait(u_free(u.slot), u.phase ^ 1u); C3_ACC(6); }
-            unsigned char* ub = u_smem + (uint32_t)u.slot * C3_BLK;
+          }
+
+          // 32 columns of T (registers) -> half of a staging block
+          auto half1 = [&](uint32_t (&acc)[32], int j) {
+            const uint32_t idx = blk0 + (uint32_t)grp_kb(j), slot = idx % C3_U_SLOTS, phase = (idx / C3_U_SLOTS) & 1u;
+            if ((j & 1) == 0) { C3_T0(); mbar_wait(u_free(slot), phase ^ 1u); C3_ACC(6); }
+            unsigned char* ub = u_smem + slot * C3_BLK;
+            const int cb = grp_col(j);
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {
               float v[8];
               float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
               if (MODE == 0) {
-                b0 = *reinterpret_cast<const float4*>(bias_s + kb * 64 + c_off + 8 * c8);
-                b1 = *reinterpret_cast<const float4*>(bias_s + kb * 64 + c_off + 8 * c8 + 4);
+                b0 = *reinterpret_cast<const float4*>(bias_s + cb + 8 * c8);
+                b1 = *reinterpret_cast<const float4*>(bias_s + cb + 8 * c8 + 4);
               }
-              const float g = gate[c8 >> 1];
+              const float g = gate[2 * j + (c8 >> 1)];
               v[0] = (__uint_as_float(acc[8 * c8 + 0]) + b0.x) * g;
               v[1] = (__uint_as_float(acc[8 * c8 + 1]) + b0.y) * g;
               v[2] = (__uint_as_float(acc[8 * c8 + 2]) + b0.z) * g;
@@ -448,12 +568,13 @@ __global__ void __launch_bounds__(C3_THREADS, 1) chain3_kernel(const __grid_cons
               v[5] = (__uint_as_float(acc[8 * c8 + 5]) + b1.y) * g;
               v[6] = (__uint_as_float(acc[8 * c8 + 6]) + b1.z) * g;
               v[7] = (__uint_as_float(acc[8 * c8 + 7]) + b1.w) * g;
-              st_swz8(ub, trow, (c_off >> 3) + c8, v);
+              st_swz8(ub, trow, (j & 1) * 4 + c8, v);
             }
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(u_full(u.slot));
-            u.next();
+            if (j & 1) {   // the warp's rows of this block are complete
+              fence_async_smem();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(u_full(slot));
+            }
           };
 
           { C3_T0(); mbar_wait(t_full, t_cnt & 1u); C3_ACC(5); }
@@ -461,27 +582,34 @@ __global__ void __launch_bounds__(C3_THREADS, 1) chain3_kernel(const __grid_cons
           tc_fence_after();
 #ifdef MSF_TIMELINE
           if (threadIdx.x == 128 && t_cnt == 1) C3_SET(7);
+          if (i < 3) C3_STAMP(17 + 2 * i);
 #endif
-          const uint32_t t_col = tmem_base + lane_base + (uint32_t)c_off;
-          c3_tmem_ld32_issue(t_col, r0);
-#pragma unroll 1
-          for (int kb = 0; kb < KB; kb += 2) {   // KB is even (hidden % 128 == 0)
-            c3_tmem_wait32(r0);
-            c3_tmem_ld32_issue(t_col + (uint32_t)((kb + 1) * 64), r1);
-            block1(r0, kb);
-            c3_tmem_wait32(r1);
-            if (kb + 2 < KB) {
-              c3_tmem_ld32_issue(t_col + (uint32_t)((kb + 2) * 64), r0);
-            } else {   // T is in registers: GEMM1 of the next pair may overwrite it
+          const uint32_t t_col = tmem_base + lane_base;
+          c3_tmem_ld32_issue(t_col + (uint32_t)grp_col(0), r0);
+#pragma unroll
+          for (int j = 0; j < NG; ++j) {
+            if (j & 1) {
+              c3_tmem_wait32(r1);
+              if (j + 1 < NG) c3_tmem_ld32_issue(t_col + (uint32_t)grp_col(j + 1), r0);
+            } else {
+              c3_tmem_wait32(r0);
+              c3_tmem_ld32_issue(t_col + (uint32_t)grp_col(j + 1), r1);   // NG is even
+            }
+            if (j + 1 == NG) {   // T is in registers: GEMM1 of the next pair may overwrite it
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(t_empty);
             }
-            block1(r1, kb + 1);
+            if (j & 1) half1(r1, j);
+            else half1(r0, j);
           }
+          blk0 += (uint32_t)KBT;
+#ifdef MSF_TIMELINE
+          if (i < 3) C3_STAMP(18 + 2 * i);
+#endif
         }
 
-        // ---- final epilogue over ACC (columns [H, 2H) of TMEM), k-block by k-block through the staging ring ----
+        // ---- final epilogue over ACC (columns [H, 2H) of TMEM), through the same staging ring ----
         if (MODE == 0) {   // summed out_proj biases of this item -> shared memory
           asm volatile("bar.sync 1, %0;" ::"n"(32 * C3_EPI_WARPS) : "memory");
           for (int e = et; e < H; e += 32 * C3_EPI_WARPS) {
@@ -498,75 +626,58 @@ __global__ void __launch_bounds__(C3_THREADS, 1) chain3_kernel(const __grid_cons
           }
           asm volatile("bar.sync 1, %0;" ::"n"(32 * C3_EPI_WARPS) : "memory");
         }
-        const __nv_bfloat16* aux_row = L.aux + ((long long)o * L.rows + row) * H + c_off;
-        const __nv_bfloat16* aux2_row = (MODE == 1) ? L.aux2 + ((long long)o * L.rows + row) * H + c_off : nullptr;
         float rscale = 1.0f;
         if (MODE == 0) rscale = L.inv_cnt[o] * ((L.mask != nullptr && row_ok) ? __ldg(L.mask + row * M + o) : 1.0f);
-        Raw32 nxt = ld_row32(aux_row, row_ok), nxt2;
-        if (MODE == 1) nxt2 = ld_row32(aux2_row, row_ok);
-
-        auto block2 = [&](uint32_t (&acc)[32], int kb) {
-          const Raw32 cur = nxt;
-          Raw32 cur2;
-          if (MODE == 1) cur2 = nxt2;
-          const bool more = kb + 1 < KB;
-          nxt = ld_row32(aux_row + (kb + 1) * 64, row_ok && more);
-          if (MODE == 1) nxt2 = ld_row32(aux2_row + (kb + 1) * 64, row_ok && more);
-          { C3_T0(); mbar_wait(u_free(u.slot), u.phase ^ 1u); C3_ACC(6); }
-          unsigned char* ub = u_smem + (uint32_t)u.slot * C3_BLK;
+        auto half2 = [&](uint32_t (&acc)[32], int j) {
+          const uint32_t idx = blk0 + (uint32_t)grp_kb(j), slot = idx % C3_U_SLOTS, phase = (idx / C3_U_SLOTS) & 1u;
+          if ((j & 1) == 0) { C3_T0(); mbar_wait(u_free(slot), phase ^ 1u); C3_ACC(6); }
+          unsigned char* ub = u_smem + slot * C3_BLK;
+          const int cb = grp_col(j);
 #pragma unroll
           for (int c8 = 0; c8 < 4; ++c8) {
-            const uint32_t aw[4] = {cur.q[c8].x, cur.q[c8].y, cur.q[c8].z, cur.q[c8].w};
-            uint32_t aw2[4] = {0u, 0u, 0u, 0u};
-            if (MODE == 1) { aw2[0] = cur2.q[c8].x; aw2[1] = cur2.q[c8].y; aw2[2] = cur2.q[c8].z; aw2[3] = cur2.q[c8].w; }
             float v[8];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float a_lo = __uint_as_float(acc[8 * c8 + 2 * e]), a_hi = __uint_as_float(acc[8 * c8 + 2 * e + 1]);
               if (MODE == 0) {
-                const float2 bb = *reinterpret_cast<const float2*>(bias_s + kb * 64 + c_off + 8 * c8 + 2 * e);
-                v[2 * e] = rscale != 0.0f ? (a_lo + bb.x + bf_lo(aw[e])) * rscale : 0.0f;       // masked row: exact 0
-                v[2 * e + 1] = rscale != 0.0f ? (a_hi + bb.y + bf_hi(aw[e])) * rscale : 0.0f;
+                const float2 bb = *reinterpret_cast<const float2*>(bias_s + cb + 8 * c8 + 2 * e);
+                v[2 * e] = rscale != 0.0f ? (a_lo + bb.x) * rscale : 0.0f;       // masked row: exact 0
+                v[2 * e + 1] = rscale != 0.0f ? (a_hi + bb.y) * rscale : 0.0f;
               } else {
-                v[2 * e] = (a_lo + bf_lo(aw[e])) * (bf_lo(aw2[e]) > 0.0f ? L.scale : 0.0f);
-                v[2 * e + 1] = (a_hi + bf_hi(aw[e])) * (bf_hi(aw2[e]) > 0.0f ? L.scale : 0.0f);
+                const uint32_t bits = relu_bits[j] >> (8 * c8 + 2 * e);
+                v[2 * e] = a_lo * ((bits & 1u) ? L.scale : 0.0f);
+                v[2 * e + 1] = a_hi * ((bits & 2u) ? L.scale : 0.0f);
               }
             }
-            st_swz8(ub, trow, (c_off >> 3) + c8, v);
+            st_swz8(ub, trow, (j & 1) * 4 + c8, v);
           }
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(u_full(u.slot));
-          u.next();
+          if (j & 1) {
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(u_full(slot));
+          }
         };
 
-        { C3_T0(); mbar_wait(acc_full, item_cnt & 1u); C3_ACC(8); }
+        { C3_T0(); mbar_wait(acc_full, item_cnt & 1u); C3_ACC(8); }   // n == 0: committed without MMAs, ACC = aux
         tc_fence_after();
-        if (n > 0) {
-          const uint32_t a_col = tmem_base + lane_base + (uint32_t)(H + c_off);
-          c3_tmem_ld32_issue(a_col, r0);
-#pragma unroll 1
-          for (int kb = 0; kb < KB; kb += 2) {
-            c3_tmem_wait32(r0);
-            c3_tmem_ld32_issue(a_col + (uint32_t)((kb + 1) * 64), r1);
-            block2(r0, kb);
-            c3_tmem_wait32(r1);
-            if (kb + 2 < KB) {
-              c3_tmem_ld32_issue(a_col + (uint32_t)((kb + 2) * 64), r0);
-            } else {   // ACC is in registers: the next item's GEMM2 may overwrite it
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(acc_empty);
-            }
-            block2(r1, kb + 1);
-          }
-        } else {   // no pair module: nothing was accumulated
+        C3_STAMP(23);
+        {
+          const uint32_t a_col = tmem_base + lane_base + (uint32_t)H;
+          c3_tmem_ld32_issue(a_col + (uint32_t)grp_col(0), r0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r0[j] = 0u;
-          if (lane == 0) mbar_arrive(acc_empty);
-#pragma unroll 1
-          for (int kb = 0; kb < KB; ++kb) block2(r0, kb);
+          for (int j = 0; j < NG; ++j) {
+            if (j & 1) {
+              c3_tmem_wait32(r1);
+              if (j + 1 < NG) c3_tmem_ld32_issue(a_col + (uint32_t)grp_col(j + 1), r0);
+            } else {
+              c3_tmem_wait32(r0);
+              c3_tmem_ld32_issue(a_col + (uint32_t)grp_col(j + 1), r1);
+            }
+            if (j & 1) half2(r1, j);
+            else half2(r0, j);
+          }
         }
+        blk0 += (uint32_t)KBT;
 #ifdef MSF_TIMELINE
         if (threadIdx.x == 128) { C3_FLUSH(5); C3_FLUSH(6); C3_FLUSH(8); C3_SET(9); }
 #endif
@@ -618,7 +729,7 @@ cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, 
 }  // namespace
 
 bool chain3_eligible(int H, int M, int head_dim) {
-  return H % 128 == 0 && H >= 128 && H <= 256 && M >= 1 && M <= MSF_MAX_MODALITIES && head_dim >= 16 && head_dim % 16 == 0 &&
+  return (H == 128 || H == 256) && M >= 1 && M <= MSF_MAX_MODALITIES && head_dim >= 16 && head_dim % 16 == 0 &&
          chain3_smem(H) <= C3_SMEM_LIMIT;
 }
 
@@ -658,9 +769,10 @@ int chain3_launch(ChainLaunch& L, cudaStream_t stream, const char* label) {
     MSF_CHECK_CUDA(cudaGetDevice(&dev));
     MSF_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  // clusters of 4 strand some SMs of a GPC (B300_MICROARCH: 16 of 148): leave headroom so every cluster is resident
-  const int max_clusters = C == 1 ? sms : (C == 2 ? sms / 2 : (C == 4 ? (sms - 16) / 4 : (sms - 20) / 8));
-  const int clusters = n_citems < max_clusters ? n_citems : max_clusters;
+  // One cluster per (tile group, outer modality).  chain_launch only picks this kernel for launches of one wave:
+  // the item loops are written for persistent CTAs, but both carrying the ring / barrier state from one item to the
+  // next and launching more clusters than fit at once still fail on the device (chain_gemm.cu: chain_variant).
+  const int clusters = n_citems;
   const int grid = clusters * C;
   if (prof_enabled()) {
     double pairs = 0.0;
@@ -668,15 +780,12 @@ int chain3_launch(ChainLaunch& L, cudaStream_t stream, const char* label) {
     prof_begin(label, 2.0 * 2.0 * (double)L.rows * L.H * L.H * pairs, stream, prof_repeat());
   }
   // the kernel only reads its operands and overwrites its outputs: repeating it (profiling) changes nothing
-  for (int rep = prof_repeat(); rep > 0; --rep) {
-    if (L.mode == 0) {
-      MSF_CHECK_CUDA(cudaFuncSetAttribute(chain3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      MSF_CHECK_CUDA(launch_pdl_cluster(chain3_kernel<0>, dim3(grid), dim3(C3_THREADS), smem, stream, C, L));
-    } else {
-      MSF_CHECK_CUDA(cudaFuncSetAttribute(chain3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      MSF_CHECK_CUDA(launch_pdl_cluster(chain3_kernel<1>, dim3(grid), dim3(C3_THREADS), smem, stream, C, L));
-    }
-  }
+  void (*kern)(const ChainLaunch) = nullptr;
+  if (L.H == 256) kern = L.mode == 0 ? chain3_kernel<0, 4> : chain3_kernel<1, 4>;
+  else kern = L.mode == 0 ? chain3_kernel<0, 2> : chain3_kernel<1, 2>;
+  MSF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  for (int rep = prof_repeat(); rep > 0; --rep)
+    MSF_CHECK_CUDA(launch_pdl_cluster(kern, dim3(grid), dim3(C3_THREADS), smem, stream, C, L));
   MSF_LAUNCH_CHECK();
   prof_end(stream);
   return MSF_OK;
@@ -685,7 +794,7 @@ int chain3_launch(ChainLaunch& L, cudaStream_t stream, const char* label) {
 int chain3_debug_stamps(long long* out16) {
 #ifdef MSF_TIMELINE
   MSF_CHECK_CUDA(cudaDeviceSynchronize());
-  MSF_CHECK_CUDA(cudaMemcpyFromSymbol(out16, g_chain3_stamps, sizeof(long long) * 16));
+  MSF_CHECK_CUDA(cudaMemcpyFromSymbol(out16, g_chain3_stamps, sizeof(long long) * 32));
   return MSF_OK;
 #else
   (void)out16;

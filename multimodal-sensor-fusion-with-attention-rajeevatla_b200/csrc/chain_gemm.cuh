@@ -36,6 +36,8 @@ struct ChainOuter {
 
 struct ChainLaunch {
   CUtensorMap map_a1, map_w1, map_w2, map_out1, map_out;
+  CUtensorMap map_aux2;   // backward: the P stack (ReLU masks of the final epilogue), box 64 x 128 like map_a1; the
+                          // aux tile itself (forward P_q, backward dS_k) is read through map_a1 (same tensor)
   int mode;            // 0 forward, 1 backward
   int M, H, heads, head_dim;
   int head_shift;      // log2(head_dim) when it is a power of two, else -1 (set by chain_launch)

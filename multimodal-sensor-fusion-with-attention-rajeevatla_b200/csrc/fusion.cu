@@ -6,6 +6,7 @@
 namespace msf {
 size_t fusion_f32_workspace_bytes(const Layout& L, int64_t B);
 int fusion_f32_forward(const Layout& L, const msf_fusion_call* c, cudaStream_t st);
+bool proj_eligible(int H, int M, const int* D);
 int fusion_f32_backward(const Layout& L, const msf_fusion_call* c, cudaStream_t st);
 
 // tensor-core path (fusion_bf16.cu)
@@ -94,11 +95,24 @@ int msf_fusion_pack_bf16(const msf_fusion_shape* shape, const float* params, voi
   return msf::fusion_bf16_pack(L, params, params_bf16, (cudaStream_t)stream);
 }
 
+int msf_fusion_layer_norm_fused(const msf_fusion_shape* shape, int32_t precision) {
+  msf::Layout L;
+  int rc = msf::make_layout(shape, &L);
+  if (rc) return rc;
+  return (precision == MSF_PREC_BF16 && msf::fusion_bf16_eligible(L) && msf::proj_eligible(L.H, L.M, L.D) &&
+          !getenv("MSF_NO_PROJ")) ? 1 : 0;
+}
+
 int msf_fusion_forward(const msf_fusion_shape* shape, const msf_fusion_call* call, void* stream) {
   msf::Layout L;
   int rc = msf::make_layout(shape, &L);
   if (rc) return rc;
   if ((rc = msf::check_call(L, call, false))) return rc;
+  if (call->precision == MSF_PREC_F32)
+    for (int m = 0; m < L.M; ++m)
+      MSF_REQUIRE(call->ln_weight[m] == nullptr && call->ln_bias[m] == nullptr,
+                  "msf_fusion_call.ln_* is only applied on the tensor-core path (msf_fusion_layer_norm_fused): run "
+                  "msf_layer_norm_forward first");
   return call->precision == MSF_PREC_F32 ? msf::fusion_f32_forward(L, call, (cudaStream_t)stream)
                                          : msf::fusion_bf16_forward(L, call, (cudaStream_t)stream);
 }

@@ -700,11 +700,14 @@ static int forward_front(const Layout& L, const msf_fusion_call* c, const WsBf16
       pl.D[m] = L.D[m];
       pl.x[m] = c->x[m];
       pl.bias[m] = W + L.proj_b[m];
+      pl.ln_w[m] = c->ln_weight[m];
+      pl.ln_b[m] = c->ln_bias[m];
       if ((rc = tc_encode_map(&pl.map_w[m], W16 + A.wp[m], H, L.D[m], L.D[m], 1, 0, 64, H))) return rc;
       if ((rc = tc_encode_map(&pl.map_xt[m], ws.xt[m], B, L.D[m], L.D[m], 1, 0, 64, 128))) return rc;
     }
     if ((rc = tc_encode_map(&pl.map_p, ws.P, B, H, H, M, BH, 64, 128))) return rc;
     pl.mask = c->mask;
+    pl.ln_eps = c->ln_eps;
     pl.drop = drop;
     if (present_hint != 0u)
       for (int m = 0; m < M; ++m)
@@ -720,6 +723,10 @@ static int forward_front(const Layout& L, const msf_fusion_call* c, const WsBf16
     }
     if ((rc = proj_launch(pl, st, "F0+F1 input prep + projections"))) return rc;
   } else {
+  for (int m = 0; m < M; ++m)
+    MSF_REQUIRE(c->ln_weight[m] == nullptr && c->ln_bias[m] == nullptr,
+                "msf_fusion_call.ln_* is only applied by the fused projection kernel (msf_fusion_layer_norm_fused() == 0 "
+                "for this shape): run msf_layer_norm_forward first");
   {  // F0
     PrepArgs16 a;
     memset(&a, 0, sizeof(a));
@@ -1091,6 +1098,7 @@ static int backward_back(const Layout& L, const msf_fusion_call* c, const WsBf16
     if ((rc = tc_encode_map(&C.map_w2, pairs > 0 ? (const void*)(W16 + A.wvT) : (const void*)ws.dS, H, H, H, np, (long long)H * H, 64, chain_w2_box_rows(H, M, L.heads, B)))) return rc;
     if ((rc = tc_encode_map(&C.map_out1, ws.dV, B, H, H, np, BH, 64, 128))) return rc;
     if ((rc = tc_encode_map(&C.map_out, ws.dZ, B, H, H, M, BH, 64, 128))) return rc;
+    if ((rc = tc_encode_map(&C.map_aux2, ws.P, B, H, H, M, BH, 64, 128))) return rc;
     for (int k = 0; k < M; ++k) {
       ChainOuter& O = C.outer[k];
       for (int q = 0; q < M; ++q) {

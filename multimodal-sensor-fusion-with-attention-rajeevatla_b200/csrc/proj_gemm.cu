@@ -76,6 +76,9 @@ __global__ void __launch_bounds__(PJ_THREADS, 1) proj_kernel(const __grid_consta
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - off0));
   float* bias_s = reinterpret_cast<float*>(smem_raw + (bar_base + 8u * PJ_NBAR - off0));
   float* mask_s = bias_s + H;                // mask column of the tile's 128 windows
+  float* stat_s = mask_s + 128;              // LayerNorm: mean[128], rstd[128] of the tile's rows
+  float* lnw_s = stat_s + 256;               // LayerNorm weight / bias of the item's modality (PJ_MAX_KB * 64 each)
+  float* lnb_s = lnw_s + 64 * PJ_MAX_KB;
   const float* x_smem = reinterpret_cast<const float*>(smem_raw + (x_base - off0));
   const bool staged = L.x_area > 0;
   unsigned char* a_smem = smem_raw + (a_base - off0);
@@ -188,13 +191,58 @@ __global__ void __launch_bounds__(PJ_THREADS, 1) proj_kernel(const __grid_consta
       if (it > 0) mbar_wait(tile_done, (it - 1) & 1u);   // previous tile's A block / staging / bias row are free
       for (int e = et; e < H; e += 32 * PJ_WORKERS) bias_s[e] = L.bias[m] ? __ldg(L.bias[m] + e) : 0.0f;
       if (et < 128) mask_s[et] = (L.mask && (long long)m0 + et < L.rows) ? __ldg(L.mask + ((long long)m0 + et) * M + m) : 1.0f;
+      const bool ln = L.ln_w[m] != nullptr || L.ln_b[m] != nullptr;
+      if (ln)
+        for (int e = et; e < D; e += 32 * PJ_WORKERS) {
+          lnw_s[e] = L.ln_w[m] ? __ldg(L.ln_w[m] + e) : 1.0f;
+          lnb_s[e] = L.ln_b[m] ? __ldg(L.ln_b[m] + e) : 0.0f;
+        }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * PJ_WORKERS) : "memory");   // bias row / mask column visible
       PJ_STAMP(2);
       if (staged) mbar_wait(x_full, it & 1u);
       PJ_STAMP(3);
-
-      // ---- X phase: xt = bf16(drop0(x * mask)), 8 columns per thread and step ----
       const float* xm = L.x[m];
+      if (ln) {
+        // row statistics, one warp per 16 rows, the row in registers (float4 per lane and 128 columns): mean, then
+        // the centred sum of squares (biased variance, like nn.LayerNorm)
+        const int c4n = D >> 2;
+        const float inv_d = 1.0f / (float)D;
+#pragma unroll 1
+        for (int rr = 0; rr < 16; ++rr) {
+          const int r = (warp - 4) * 16 + rr;
+          const long long row = (long long)m0 + r;
+          float4 v[2];
+          float s = 0.0f;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int c4 = lane + 32 * i;
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c4 < c4n && row < L.rows)
+              v[i] = staged ? *reinterpret_cast<const float4*>(x_smem + r * D + c4 * 4)
+                            : __ldg(reinterpret_cast<const float4*>(xm + row * D) + c4);
+            s += v[i].x + v[i].y + v[i].z + v[i].w;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          const float mean = s * inv_d;
+          float q = 0.0f;
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+            if (lane + 32 * i < c4n) {
+              const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+              q += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+            }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+          if (lane == 0) {
+            stat_s[r] = mean;
+            stat_s[128 + r] = rsqrtf(q * inv_d + L.ln_eps);
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * PJ_WORKERS) : "memory");   // every row's statistics visible
+      }
+
+      // ---- X phase: xt = bf16(drop0(LN(x) * mask)), 8 columns per thread and step ----
 #pragma unroll 1
       for (int id = et; id < 128 * c8n; id += 32 * PJ_WORKERS) {
         const int r = id / c8n, c8 = id - r * c8n;
@@ -208,6 +256,15 @@ __global__ void __launch_bounds__(PJ_THREADS, 1) proj_kernel(const __grid_consta
           } else {
             a = __ldg(reinterpret_cast<const float4*>(xm + row * D + c8 * 8));
             b = __ldg(reinterpret_cast<const float4*>(xm + row * D + c8 * 8) + 1);
+          }
+          if (ln) {
+            const float mu = stat_s[r], rs = stat_s[128 + r];
+            const float4 g0 = *reinterpret_cast<const float4*>(lnw_s + c8 * 8), g1 = *reinterpret_cast<const float4*>(lnw_s + c8 * 8 + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(lnb_s + c8 * 8), b1 = *reinterpret_cast<const float4*>(lnb_s + c8 * 8 + 4);
+            a.x = (a.x - mu) * rs * g0.x + b0.x; a.y = (a.y - mu) * rs * g0.y + b0.y;
+            a.z = (a.z - mu) * rs * g0.z + b0.z; a.w = (a.w - mu) * rs * g0.w + b0.w;
+            b.x = (b.x - mu) * rs * g1.x + b1.x; b.y = (b.y - mu) * rs * g1.y + b1.y;
+            b.z = (b.z - mu) * rs * g1.z + b1.z; b.w = (b.w - mu) * rs * g1.w + b1.w;
           }
           const float mk = mask_s[r];
           float dm[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
@@ -309,7 +366,7 @@ int proj_launch(ProjLaunch& L, cudaStream_t stream, const char* label) {
   const size_t out_tile = (size_t)(L.H / 64) * PJ_A_BYTES;
   L.w_area = (int)((size_t)max_kb * L.H * 128 > out_tile ? (size_t)max_kb * L.H * 128 : out_tile);
   L.a_area = max_kb * (int)PJ_A_BYTES;
-  const size_t fixed = 1024 + 8 * PJ_NBAR + (size_t)(L.H + 128) * 4;
+  const size_t fixed = 1024 + 8 * PJ_NBAR + (size_t)(L.H + 128 + 256 + 2 * 64 * PJ_MAX_KB) * 4;
   L.x_area = 128 * max_d * 4;     // fp32 input tile staged by a bulk copy when it fits
   if (fixed + L.w_area + L.a_area + L.x_area > PJ_SMEM_LIMIT || getenv("MSF_PROJ_NO_STAGE")) L.x_area = 0;
   const size_t smem = fixed + L.w_area + L.a_area + L.x_area;

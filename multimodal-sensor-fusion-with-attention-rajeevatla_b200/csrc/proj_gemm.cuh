@@ -1,6 +1,8 @@
 // proj_kernel: the input side of HybridFusion.forward (src/fusion.py:364-374) in one launch per step:
 //
-//   xt_m = bf16(drop0(x_m * mask_m))            read as fp32 rows by the worker warps, written once into the
+//   xt_m = bf16(drop0(LN_m(x_m) * mask_m))      (LN_m: the optional LayerNorm train.py puts between encoder and
+//                                               fusion; row mean / variance while the fp32 tile is in shared memory)
+//                                               read as fp32 rows by the worker warps, written once into the
 //                                               128B-swizzled A block (and from there to global by TMA: the
 //                                               projection weight gradient needs it later)
 //   P_m  = drop1(relu(xt_m Wp_m^T + bp_m))      tcgen05.mma, A = that block, Wp_m by TMA, accumulator in TMEM
@@ -32,6 +34,11 @@ struct ProjLaunch {
   int n_active;                             // modalities that get items (0: all M); absent ones of a uniform-mask
   short active[MSF_MAX_MODALITIES];         // inference pass are left out
   const float* mask;                        // (rows, M) or nullptr
+  // optional per-modality LayerNorm of the input rows (src/train.py:170-171,267-268), applied in the input phase
+  // before mask and dropout: y = (x - mean) * rstd * ln_w + ln_b; both nullptr = none
+  const float* ln_w[MSF_MAX_MODALITIES];
+  const float* ln_b[MSF_MAX_MODALITIES];
+  float ln_eps;
   DropCfg drop;
   // gradient slots to clear at the start of a train pass (first kernel of the step); see fusion_bf16.cu
   ProjZeroRange zero[PROJ_MAX_ZERO];

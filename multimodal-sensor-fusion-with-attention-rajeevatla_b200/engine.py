@@ -123,10 +123,33 @@ class FusionEngine:
         self.state[3:4].copy_(torch.tensor([bits], dtype=torch.int64), non_blocking=False)
 
     # -- enqueue helpers (all on the current stream) ---------------------------------
+    def set_input_norms(self, norms) -> None:
+        """Per-modality ``nn.LayerNorm`` applied to the inputs inside the projection kernel of every later INFERENCE
+        pass (src/train.py:170-171,267-268: the LayerNorm between encoder and fusion): ``load_batch`` / ``infer`` are
+        then fed the raw encoder outputs.  ``norms``: mapping or sequence in ``plan.names`` order (None entries = no
+        LayerNorm for that modality); ``None`` switches it off.  Captured inference graphs are dropped."""
+        self._infer_graph, self._subset_graphs = None, {}
+        if norms is None:
+            self._ln, self._ln_eps = None, 1e-5
+            return
+        seq = [norms.get(m) if hasattr(norms, "get") else norms[i] for i, m in enumerate(self.plan.names)]
+        if not ops.layer_norm_fused(self.plan, self.prec):
+            raise N.MsfError("input LayerNorm is fused on the tensor-core path only (msf_fusion_layer_norm_fused)")
+        eps = {float(n.eps) for n in seq if n is not None}
+        if len(eps) > 1:
+            raise ValueError("the fused input LayerNorm takes one eps for all modalities")
+        put = lambda t: None if t is None else t.detach().to(device=self.dev, dtype=torch.float32).contiguous()  # noqa: E731
+        self._ln = [None if n is None else (put(n.weight), put(n.bias)) for n in seq]
+        self._ln_eps = eps.pop() if eps else 1e-5
+
     def _call(self, training: bool, slot: int = 0) -> N.FusionCall:
         x, mask, _ = self._slots[slot]
+        ln = getattr(self, "_ln", None)
+        if training and ln is not None:
+            raise N.MsfError("FusionEngine trains the fusion model only: input LayerNorm parameters belong to the "
+                             "caller's optimizer (use HybridFusion.forward(input_norms=...) / pipeline.EncodeFuse)")
         c = ops._make_call(self.plan, self.batch, self.prec, training and self.p > 0, self.p, 0, 0,
-                           self.arena, self.arena_bf16, x, mask, self.ws)
+                           self.arena, self.arena_bf16, x, mask, self.ws, ln=ln, ln_eps=getattr(self, "_ln_eps", 1e-5))
         c.rng_state = self.state.data_ptr()
         return c
 

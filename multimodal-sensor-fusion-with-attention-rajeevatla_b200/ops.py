@@ -153,10 +153,23 @@ def get_plan(names, dims, hidden, heads, classes, present) -> FusionPlan:
     return plan
 
 
+def layer_norm_fused(plan: "FusionPlan", precision: int) -> bool:
+    """True if the projection kernel applies msf_fusion_call.ln_* itself for this shape / precision."""
+    return N.lib().msf_fusion_layer_norm_fused(ctypes.byref(plan.shape), precision) == 1
+
+
 def _make_call(plan: FusionPlan, batch: int, precision: int, training: bool, p: float, seed: int,
                offset: int, arena: torch.Tensor, arena_bf16: Optional[torch.Tensor],
-               xs: Sequence[torch.Tensor], mask: Optional[torch.Tensor], ws: torch.Tensor) -> N.FusionCall:
+               xs: Sequence[torch.Tensor], mask: Optional[torch.Tensor], ws: torch.Tensor,
+               ln: Optional[Sequence[Optional[tuple]]] = None, ln_eps: float = 1e-5) -> N.FusionCall:
+    """``ln``: per modality ``(weight, bias)`` fp32 device tensors (either may be None) or None — the LayerNorm
+    train.py puts between encoder and fusion, applied inside the projection kernel (layer_norm_fused())."""
     c = N.FusionCall()
+    if ln is not None:
+        for i, wb in enumerate(ln):
+            if wb is not None:
+                c.ln_weight[i], c.ln_bias[i] = _p(wb[0]), _p(wb[1])
+        c.ln_eps = float(ln_eps)
     c.batch, c.precision, c.training, c.dropout_p = batch, precision, int(bool(training)), float(p)
     c.seed, c.offset = seed & (2**64 - 1), offset & (2**64 - 1)
     c.params, c.params_bf16 = _p(arena), _p(arena_bf16)
@@ -171,7 +184,7 @@ def fusion_forward_raw(plan: FusionPlan, arena: torch.Tensor, xs: Sequence[torch
                        mask: Optional[torch.Tensor], *, precision: int = N.MSF_PREC_F32,
                        training: bool = False, p: float = 0.0, seed: int = 0, offset: int = 0,
                        arena_bf16: Optional[torch.Tensor] = None, want_aux: bool = True,
-                       workspace: Optional[torch.Tensor] = None):
+                       workspace: Optional[torch.Tensor] = None, ln=None, ln_eps: float = 1e-5):
     """One msf_fusion_forward call on already-prepared device buffers."""
     dev = arena.device
     B = xs[0].shape[0]
@@ -179,7 +192,8 @@ def fusion_forward_raw(plan: FusionPlan, arena: torch.Tensor, xs: Sequence[torch
         workspace = torch.empty(plan.workspace_bytes(B, precision), dtype=torch.uint8, device=dev)
     logits = torch.empty(B, plan.C, dtype=torch.float32, device=dev)
     fw = gates = None
-    call = _make_call(plan, B, precision, training, p, seed, offset, arena, arena_bf16, xs, mask, workspace)
+    call = _make_call(plan, B, precision, training, p, seed, offset, arena, arena_bf16, xs, mask, workspace,
+                      ln=ln, ln_eps=ln_eps)
     call.logits = _p(logits)
     if want_aux:
         fw = torch.empty(B, plan.M, dtype=torch.float32, device=dev)
@@ -246,7 +260,7 @@ def fusion_train_pass_raw(plan: FusionPlan, arena: torch.Tensor, xs: Sequence[to
 def fusion_infer_pass_raw(plan: FusionPlan, arena: torch.Tensor, xs: Sequence[torch.Tensor],
                           mask: Optional[torch.Tensor], *, precision: int = N.MSF_PREC_F32,
                           arena_bf16: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None,
-                          present_hint: int = 0):
+                          present_hint: int = 0, ln=None, ln_eps: float = 1e-5):
     """One msf_fusion_infer_pass call: ``(logits, conf, pred)`` (src/eval.py:84-90).  ``present_hint``: bit set
     of the modalities a batch-uniform mask marks present (0 = no hint)."""
     dev = arena.device
@@ -256,7 +270,7 @@ def fusion_infer_pass_raw(plan: FusionPlan, arena: torch.Tensor, xs: Sequence[to
     logits = torch.empty(B, plan.C, dtype=torch.float32, device=dev)
     conf = torch.empty(B, dtype=torch.float32, device=dev)
     pred = torch.empty(B, dtype=torch.int64, device=dev)
-    call = _make_call(plan, B, precision, False, 0.0, 0, 0, arena, arena_bf16, xs, mask, workspace)
+    call = _make_call(plan, B, precision, False, 0.0, 0, 0, arena, arena_bf16, xs, mask, workspace, ln=ln, ln_eps=ln_eps)
     call.logits = _p(logits)
     N.check(N.lib().msf_fusion_infer_pass(ctypes.byref(plan.shape), ctypes.byref(call), _p(conf), _p(pred),
                                           int(present_hint), _stream()))
@@ -275,33 +289,104 @@ class HybridFusionFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, plan: FusionPlan, cfg: dict, mask: Optional[torch.Tensor], *tensors):
         M = plan.M
+        n_par = len(plan.slots)
         xs = [t.contiguous() for t in tensors[:M]]
-        params = [t.contiguous() for t in tensors[M:]]
+        params = [t.contiguous() for t in tensors[M:M + n_par]]
+        # optional fused input LayerNorm (cfg["ln"]): 2 * M trailing tensors, weight_m then bias_m (None = absent)
+        ln = None
+        if cfg.get("ln"):
+            extra = tensors[M + n_par:]
+            ln = [None if extra[m] is None and extra[M + m] is None else
+                  (None if extra[m] is None else extra[m].contiguous(),
+                   None if extra[M + m] is None else extra[M + m].contiguous()) for m in range(M)]
         precision = cfg["precision"]
         arena = plan.gather(params)
         arena_bf16 = plan.pack_bf16(arena) if precision == N.MSF_PREC_BF16 else None
         logits, fw, gates, ws = fusion_forward_raw(
             plan, arena, xs, mask, precision=precision, training=cfg["training"], p=cfg["p"],
-            seed=cfg["seed"], offset=cfg["offset"], arena_bf16=arena_bf16, want_aux=True)
+            seed=cfg["seed"], offset=cfg["offset"], arena_bf16=arena_bf16, want_aux=True, ln=ln,
+            ln_eps=cfg.get("ln_eps", 1e-5))
         ctx.plan, ctx.cfg, ctx.mask = plan, cfg, mask
-        ctx.saved = (arena, arena_bf16, xs, ws)
-        ctx.param_shapes = [t.shape for t in tensors[M:]]
+        ctx.saved = (arena, arena_bf16, xs, ws, ln)
+        ctx.param_shapes = [t.shape for t in tensors[M:M + n_par]]
         ctx.mark_non_differentiable(fw, gates)
         return logits, fw, gates
 
     @staticmethod
     def backward(ctx, grad_logits, _gfw, _ggates):
         plan, cfg = ctx.plan, ctx.cfg
-        arena, arena_bf16, xs, ws = ctx.saved
+        arena, arena_bf16, xs, ws, ln = ctx.saved
         M = plan.M
-        need_dx = ctx.needs_input_grad[3:3 + M]
+        n_par = len(plan.slots)
+        need_dx = list(ctx.needs_input_grad[3:3 + M])
+        need_ln = [False] * (2 * M)
+        if ln is not None:
+            need_ln = list(ctx.needs_input_grad[3 + M + n_par:3 + M + n_par + 2 * M])
+            for m in range(M):   # the LayerNorm gradients need the gradient with respect to the normalised rows
+                need_dx[m] = need_dx[m] or (ln[m] is not None and (need_ln[m] or need_ln[M + m]))
         g = grad_logits.to(torch.float32).contiguous()
         grad_arena, dxs = fusion_backward_raw(
             plan, arena, xs, ctx.mask, ws, g, precision=cfg["precision"], training=cfg["training"],
             p=cfg["p"], seed=cfg["seed"], offset=cfg["offset"], arena_bf16=arena_bf16, need_dx=need_dx)
         grads = [grad_arena[off:off + int(torch.Size(shape).numel())].view(shape)
                  for (_, off, _), shape in zip(plan.slots, ctx.param_shapes)]
-        return (None, None, None, *dxs, *grads)
+        ln_grads = []
+        if ln is not None:
+            dws, dbs = [None] * M, [None] * M
+            for m in range(M):
+                if ln[m] is None or dxs[m] is None:
+                    continue
+                # dxs[m] is the gradient with respect to the normalised rows (include/msf_b200.h: ln_*)
+                dxs[m], dws[m], dbs[m] = layer_norm_backward_raw(xs[m], ln[m][0], dxs[m], cfg.get("ln_eps", 1e-5))
+                if ln[m][0] is None:
+                    dws[m] = None
+                if ln[m][1] is None:
+                    dbs[m] = None
+            ln_grads = dws + dbs
+            dxs = [dx if ctx.needs_input_grad[3 + m] else None for m, dx in enumerate(dxs)]
+        return (None, None, None, *dxs, *grads, *ln_grads)
+
+
+def layer_norm_forward_raw(x: torch.Tensor, weight: Optional[torch.Tensor], bias: Optional[torch.Tensor],
+                           eps: float = 1e-5) -> torch.Tensor:
+    rows = x.numel() // x.shape[-1]
+    y = torch.empty_like(x)
+    N.check(N.lib().msf_layer_norm_forward(_p(x), _p(weight), _p(bias), _p(y), rows, x.shape[-1], float(eps), _stream()))
+    return y
+
+
+def layer_norm_backward_raw(x: torch.Tensor, weight: Optional[torch.Tensor], dy: torch.Tensor, eps: float = 1e-5):
+    """``(dx, dweight, dbias)`` of y = LayerNorm(x) given dy (msf_layer_norm_backward)."""
+    dim = x.shape[-1]
+    rows = x.numel() // dim
+    dx = torch.empty_like(x)
+    dw = torch.empty(dim, dtype=torch.float32, device=x.device)
+    db = torch.empty(dim, dtype=torch.float32, device=x.device)
+    N.check(N.lib().msf_layer_norm_backward(_p(x), _p(weight), _p(dy.contiguous()), _p(dx), _p(dw), _p(db), rows, dim,
+                                            float(eps), _stream()))
+    return dx, dw, db
+
+
+class LayerNormFunction(torch.autograd.Function):
+    """nn.LayerNorm over the last dimension on msf_layer_norm_* (src/train.py:170-171,267-268)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps: float):
+        x = x.contiguous()
+        ctx.save_for_backward(x, weight)
+        ctx.eps, ctx.has = eps, (weight is not None, bias is not None)
+        return layer_norm_forward_raw(x, weight, bias, eps)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        dx, dw, db = layer_norm_backward_raw(x, weight, gy.to(torch.float32), ctx.eps)
+        return dx, (dw if ctx.has[0] else None), (db if ctx.has[1] else None), None
+
+
+def layer_norm(x: torch.Tensor, weight: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+               eps: float = 1e-5) -> torch.Tensor:
+    return LayerNormFunction.apply(x, weight, bias, eps)
 
 
 def adaptive_weights(feats: Sequence[torch.Tensor], gate_w: Sequence[torch.Tensor],

@@ -180,8 +180,15 @@ class HybridFusion(nn.Module):
 
     # -- forward -------------------------------------------------------------------
     def forward(self, modality_features: Dict[str, torch.Tensor], modality_mask: Optional[torch.Tensor] = None,
-                return_attention: bool = False):
-        """``logits`` or ``(logits, {"attention_maps", "fusion_weights"})``."""
+                return_attention: bool = False, input_norms=None):
+        """``logits`` or ``(logits, {"attention_maps", "fusion_weights"})``.
+
+        ``input_norms`` (extension; the reference has no such argument): ``{modality: nn.LayerNorm}`` — the
+        per-modality LayerNorm ``train.MultimodalFusionModule`` applies to every encoder output before the fusion
+        model (train.py:170-171,267-268).  ``modality_features`` are then the raw encoder outputs; on the
+        tensor-core path the normalisation happens inside the projection kernel (no pass over the features in
+        between), elsewhere through ``ops.layer_norm``.  Gradients flow to the features and the LayerNorm
+        parameters either way."""
         if not self.modality_names:
             raise ValueError("No modalities configured for HybridFusion.")
         names = self.modality_names
@@ -207,9 +214,26 @@ class HybridFusion(nn.Module):
             "seed": int(torch.randint(0, 2**62, (1,)).item()) if training else 0,
             "offset": 0,
         }
+        ln_tensors = []
+        if input_norms:
+            norms = [input_norms.get(m) if hasattr(input_norms, "get") else input_norms[m] for m in names]
+            canonical = all(n is None or (isinstance(n, nn.LayerNorm) and len(n.normalized_shape) == 1) for n in norms)
+            eps = {float(n.eps) for n in norms if n is not None}
+            with torch.cuda.device(dev):
+                fused = canonical and len(eps) <= 1 and ops.layer_norm_fused(plan, cfg["precision"])
+            put = lambda t: None if t is None else t.to(device=dev, dtype=torch.float32)  # noqa: E731
+            if fused:
+                cfg["ln"], cfg["ln_eps"] = True, (eps.pop() if eps else 1e-5)
+                ln_tensors = [put(None if n is None else n.weight) for n in norms] + \
+                             [put(None if n is None else n.bias) for n in norms]
+            else:   # normalise first (msf_layer_norm_* kernels; any other module is simply called)
+                with torch.cuda.device(dev):
+                    xs = [x if n is None else
+                          (ops.layer_norm(x, put(n.weight), put(n.bias), float(n.eps)) if isinstance(n, nn.LayerNorm)
+                           and len(n.normalized_shape) == 1 else n(x)) for x, n in zip(xs, norms)]
         with torch.cuda.device(dev):
             logits, fusion_w, gates = ops.HybridFusionFunction.apply(
-                plan, cfg, mask, *xs, *self._slot_tensors(plan, dev))
+                plan, cfg, mask, *xs, *self._slot_tensors(plan, dev), *ln_tensors)
         logits = logits.to(device=home, dtype=out_dtype)
         if not return_attention:
             return logits

@@ -10,9 +10,11 @@ weight, fp32 accumulator) so the returned floats match.  Counts are bit-exact;
 bin means agree to ~1e-7 relative (the reference's fp32 summation order vs an
 exact fixed-point sum).
 
-The remaining helpers of the reference file (MC-dropout, temperature scaling,
-ensembles, uncertainty-weighted fusion) are outside the accelerated path
- and are not re-implemented here.
+The remaining helpers of the reference file (``MCDropoutUncertainty``,
+``UncertaintyWeightedFusion``, ``TemperatureScaling``, ``EnsembleUncertainty``;
+uncertainty.py:19-71,286-492) are outside the accelerated path (SURVEY.md §2 row
+12): they are provided as small tensor programs around the caller's models so
+that the module's public surface is complete.
 """
 from __future__ import annotations
 
@@ -133,21 +135,125 @@ class CalibrationMetrics:
         plt.close(fig)
 
 
-def compute_calibration_metrics(model: torch.nn.Module, dataloader, device: str = "cuda") -> Dict[str, float]:
+class MCDropoutUncertainty(torch.nn.Module):
+    """Monte-Carlo dropout (uncertainty.py:19-71): ``num_samples`` stochastic forward passes of ``model`` in
+    train mode; returns the mean logits and, per sample, the variance of the class probabilities across passes
+    averaged over the classes.  Not on the fusion hot path: plain tensor arithmetic around the wrapped model."""
+
+    def __init__(self, model: torch.nn.Module, num_samples: int = 10):
+        super().__init__()
+        self.model = model
+        self.num_samples = num_samples
+
+    def forward(self, *args, **kwargs) -> Tuple[torch.Tensor, torch.Tensor]:
+        restore_eval = not self.model.training
+        self.model.train()
+        with torch.no_grad():
+            draws = torch.stack([self.model(*args, **kwargs) for _ in range(self.num_samples)])
+        if restore_eval:
+            self.model.eval()
+        spread = torch.softmax(draws, dim=2).var(dim=0, unbiased=False).mean(dim=1)
+        return draws.mean(dim=0), spread
+
+
+class UncertaintyWeightedFusion(torch.nn.Module):
+    """Late fusion with weights proportional to ``1 / (uncertainty + epsilon)`` over the available modalities
+    (uncertainty.py:286-363), with HybridFusion's fallbacks: availability-uniform when every weight vanishes,
+    uniform over all modalities when nothing is available."""
+
+    def __init__(self, epsilon: float = 1e-6):
+        super().__init__()
+        self.epsilon = epsilon
+
+    def forward(self, modality_predictions: Dict[str, torch.Tensor], modality_uncertainties: Dict[str, torch.Tensor],
+                modality_mask: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        names = list(modality_predictions)
+        if not names:
+            raise ValueError("No modality predictions supplied for fusion.")
+        for name in names:
+            if name not in modality_uncertainties:
+                raise KeyError(f"Missing uncertainty for modality '{name}'.")
+        dev = modality_predictions[names[0]].device
+        avail = modality_mask.to(device=dev, dtype=torch.float32)
+        votes = torch.stack([modality_predictions[m].to(dev) for m in names], dim=1)           # (B, M, C)
+        trust = torch.stack([1.0 / (modality_uncertainties[m].to(dev) + self.epsilon) for m in names], dim=1) * avail
+        total, present = trust.sum(dim=1, keepdim=True), avail.sum(dim=1, keepdim=True)
+        fallback = torch.where(present > 0, avail / (present + 1e-8), torch.full_like(avail, 1.0 / len(names)))
+        weights = torch.where(total > 0, trust / (total + 1e-8), fallback)
+        return (votes * weights.unsqueeze(-1)).sum(dim=1), weights
+
+
+class TemperatureScaling(torch.nn.Module):
+    """Post-hoc calibration with one learned temperature, ``softmax(logits / T)`` (uncertainty.py:366-437;
+    Guo et al., ICML 2017).  ``calibrate`` fits T by L-BFGS on held-out logits, starting from 1 and keeping the
+    parameter on the logits' device (a meta / foreign-device parameter is re-created there)."""
+
+    def __init__(self):
+        super().__init__()
+        self.temperature = torch.nn.Parameter(torch.ones(1))
+
+    def forward(self, logits: torch.Tensor) -> torch.Tensor:
+        return logits / self.temperature
+
+    def calibrate(self, logits: torch.Tensor, labels: torch.Tensor, lr: float = 0.01, max_iter: int = 50) -> None:
+        logits, labels = logits.detach(), labels.detach().to(dtype=torch.long)
+        current = self.temperature
+        if current.device != logits.device:
+            moved = (torch.ones(current.shape, device=logits.device, dtype=current.dtype)
+                     if current.device.type == "meta" else current.detach().to(device=logits.device))
+            self.temperature = torch.nn.Parameter(moved)
+        self.temperature.data = torch.ones_like(self.temperature.data)
+        solver = torch.optim.LBFGS([self.temperature], lr=lr, max_iter=max_iter)
+
+        def objective():
+            solver.zero_grad()
+            value = torch.nn.functional.cross_entropy(self.forward(logits), labels)
+            value.backward()
+            return value
+
+        solver.step(objective)
+        self.temperature.data = self.temperature.data.clamp(min=1e-3)
+
+
+class EnsembleUncertainty:
+    """Mean class probabilities of several models and their spread (uncertainty.py:440-492)."""
+
+    def __init__(self, models):
+        self.models = list(models)
+        self.num_models = len(self.models)
+
+    def predict_with_uncertainty(self, inputs: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        if self.num_models == 0:
+            raise ValueError("Ensemble must contain at least one model.")
+        votes = []
+        with torch.no_grad():
+            for member in self.models:
+                resume_training = member.training
+                member.eval()
+                votes.append(torch.softmax(member(inputs), dim=1))
+                if resume_training:
+                    member.train()
+        votes = torch.stack(votes)
+        return votes.mean(dim=0), votes.var(dim=0, unbiased=False).mean(dim=1)
+
+
+def compute_calibration_metrics(model: torch.nn.Module, dataloader, device: str = "cpu") -> Dict[str, float]:
     """ECE / MCE / NLL / accuracy over a dataloader (uncertainty.py:495-553).
-    Confidences and predictions stay on the device; the bins are accumulated
-    batch by batch into one ``(3, 15)`` integer tensor instead of concatenating
-    the whole evaluation set on the host."""
+    The model runs on the device the caller names (``"cpu"`` by default, like the reference); only its logits and
+    the labels go to the current CUDA device, where softmax -> (confidence, prediction), the cross-entropy sum and
+    the binning run.  Confidences and predictions stay there; the bins are accumulated batch by batch into one
+    ``(3, 15)`` integer tensor instead of concatenating the whole evaluation set on the host."""
     model.eval()
-    dev = torch.device(device) if str(device).startswith("cuda") else ops.require_cuda("compute_calibration_metrics")
+    run_dev = torch.device(device)
+    dev = run_dev if run_dev.type == "cuda" else ops.require_cuda("compute_calibration_metrics")
     edges = torch.linspace(0.0, 1.0, steps=16).double().tolist()
     stats = None
     seen = hits = 0
     nll_sum = 0.0
     with torch.no_grad(), torch.cuda.device(dev):
         for inputs, labels in dataloader:
-            inputs, labels = inputs.to(dev), labels.to(dev)
-            logits = model(inputs).to(dev)
+            logits = model(inputs.to(run_dev)).to(dev)
+            labels = labels.to(dev)
             conf, pred = ops.softmax_conf_pred(logits)
             stats = ops.ece_bin(conf, pred, labels, edges, out=stats)
             loss, _ = ops.cross_entropy(logits, labels, smoothing=0.0)

@@ -20,7 +20,7 @@ for _ in range(10):
     eng.train_step_resident()
 torch.cuda.synchronize()
 lib = pkg.lib()
-out = (ctypes.c_int64 * 16)()
+out = (ctypes.c_int64 * 32)()
 N.check(lib.msf_debug_chain_stamps(out))
 v = list(out)
 clk = 1.965e3  # cycles per us at the maximum SM clock
@@ -36,3 +36,8 @@ print(f"  epilogue end                         {us(v[9] - t0):7.2f}")
 print(f"  epilogue waits: G1 {us(v[5]):6.2f}  free staging block {us(v[6]):6.2f}  ACC {us(v[8]):6.2f}"
       f"  -> working {us(v[9] - v[7] - v[5] - v[6] - v[8]):6.2f}")
 print(f"  W producer waits for free slots {us(v[10]):6.2f}, ends at {us(v[11] - t0):7.2f}")
+rel = lambda i: us(v[i] - t0) if v[i] else float("nan")
+print(f"  epilogue thread 128, first item: aux blocks in ACC / ReLU bits ready at {rel(16):7.2f}")
+for i in range(3):
+    print(f"    pass {i}: T ready {rel(17 + 2 * i):7.2f}  staged {rel(18 + 2 * i):7.2f}  ({us(v[18 + 2 * i] - v[17 + 2 * i]):5.2f} us)")
+print(f"    final pass: ACC ready {rel(23):7.2f}  end {rel(9):7.2f}  ({us(v[9] - v[23]):5.2f} us)")

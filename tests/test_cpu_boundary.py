@@ -36,8 +36,8 @@ def test_library_exports_every_declared_symbol(pkg):
 def test_struct_layout_matches_header(pkg):
     n = pkg.native
     assert ctypes.sizeof(n.FusionShape) == 4 * 4 + 4 * 8 + 8
-    # int32 x3, float, u64 x2, 2 ptr, 8 ptr, 3 ptr(+size_t), 3 ptr, 2 ptr, 8 ptr, 1 ptr
-    assert ctypes.sizeof(n.FusionCall) == 16 + 16 + 8 * (1 + 2 + 8 + 1 + 2 + 3 + 2 + 8 + 1)
+    # int32 x3, float, u64 x2, 2 ptr, 8 ptr, 3 ptr(+size_t), 3 ptr, 2 ptr, 8 ptr, 1 ptr, LayerNorm: 8 + 8 ptr, float (+pad)
+    assert ctypes.sizeof(n.FusionCall) == 16 + 16 + 8 * (1 + 2 + 8 + 1 + 2 + 3 + 2 + 8 + 1) + 8 * 16 + 8
 
 
 @pytest.mark.parametrize("case", ["fusion_tiny.npz", "fusion_pamap_small.npz", "fusion_missing_pair.npz"])
