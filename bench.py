@@ -364,6 +364,8 @@ def run_ours(args):
     # compute copy) must be bit-identical after the run.  Compared as 64-bit checksums (max == min over ranks).
     replicas_identical = None
     if world > 1:
+        eng.gather_parameters()   # sharded step: collect every weight tile from its owner first
+
         def checksum(t):
             v = t.view(torch.int32).to(torch.int64)
             return torch.stack([v.sum(), (v * torch.arange(1, v.numel() + 1, device=dev) % 1000003).sum()])
@@ -435,6 +437,10 @@ def run_ours(args):
                 "repeats": repeats, "timed_region_ms": ms * args.steps * repeats,
                 "ms_per_step_is": "median over `repeats` timed regions of exactly `steps` steps each",
                 "collective": {"none": "none (single GPU)",
+                               "zshard": "sharded optimizer over NVLink peer memory (opt_pack.cu: dpz_reduce_kernel + "
+                                         "opt_pack_kernel<.., true>): push-based reduce-scatter of the gradient tiles to "
+                                         "their owners, owner-side clip + AdamW, bf16 weights pushed to all ranks; no NCCL "
+                                         "on the data path",
                                "p2p": "fused NVLink peer-memory reduce-scatter + all-gather kernels (dp_optim.cu), no NCCL on the data path",
                                "nccl": "ncclAllReduce of the flat fp32 gradient arena"}[comm_used]},
         "clocks": clocks,
@@ -457,10 +463,37 @@ def run_ours(args):
     finish()
 
 
+FLOP_SWEEP_MASK_AWARE = 16854528 / 15.0   # live FLOPs per window-evaluation when absent modalities
+                                          # (their projections, pair GEMMs, query rows) are skipped: 1 123 635
+
+
+def _timed_repeats(torch, fn, steps, warmup, min_seconds=0.5, max_repeats=200):
+    """`steps` calls of fn between CUDA events, repeated until >= min_seconds are covered; median ms per call."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    samples, total = [], 0.0
+    while True:
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(steps):
+            fn()
+        stop.record()
+        torch.cuda.synchronize()
+        ms = start.elapsed_time(stop)
+        samples.append(ms / steps)
+        total += ms
+        if total >= min_seconds * 1e3 or len(samples) >= max_repeats:
+            break
+    return statistics.median(samples), len(samples)
+
+
 def run_infer_sweep(args):
     """BASELINE configs[2]: inference over all 15 missing-modality subsets (eval.py:342-348 order), batch
     65536 per subset, single GPU; logits -> softmax -> (conf, pred) -> 15-bin ECE statistics per subset.
-    Throughput = 15 * B window-evaluations / time (inputs resident; one CUDA graph per subset mask)."""
+    Throughput = 15 * B window-evaluations / time (inputs resident; one CUDA graph per subset mask).
+    `e2e`: the same sweep fed from pinned host features (copied once per sweep) with every subset's predictions and
+    bin statistics read back; `cpu_baseline`: the oracle's forward + softmax/argmax + binning on the host cores."""
     import itertools
     import torch
     torch.cuda.set_device(0)
@@ -475,7 +508,8 @@ def run_infer_sweep(args):
     torch.manual_seed(0)
     model = fusion.HybridFusion(DIMS, hidden_dim=HIDDEN, num_classes=CLASSES, num_heads=HEADS, dropout=DROPOUT).eval()
     eng = engine_mod.FusionEngine(model, B, precision=args.precision, use_graph=not args.no_graph)
-    feats, _, labels = synthetic_batch(torch, 1234, B, device=dev)
+    host_feats, _, host_labels = synthetic_batch(torch, 1234, B, pin=True)
+    feats, labels = [f.to(dev) for f in host_feats], host_labels.to(dev)
     names = list(DIMS)
     subsets = [c for r in range(1, len(names) + 1) for c in itertools.combinations(range(len(names)), r)]
     masks = []
@@ -485,9 +519,11 @@ def run_infer_sweep(args):
         masks.append(m)
     edges = torch.linspace(0, 1, 16).double().tolist()
     stats = torch.zeros(len(subsets), 3, 15, dtype=torch.int64, device=dev)
+    host_pred = torch.zeros(len(subsets), B, dtype=torch.int64).pin_memory()
+    host_stats = torch.zeros(len(subsets), 3, 15, dtype=torch.int64).pin_memory()
 
-    def sweep():
-        eng.load_batch(feats, masks[0], labels)      # the batch is copied once per sweep, the mask per subset
+    def sweep(src_feats=feats, readback=False):
+        eng.load_batch(src_feats, masks[0], labels)  # the batch is copied once per sweep, the mask per subset
         for i, sub in enumerate(subsets):
             if args.no_mask_hint:
                 eng.mask.copy_(masks[i], non_blocking=True)
@@ -495,34 +531,93 @@ def run_infer_sweep(args):
             else:
                 eng.infer_subset(None, sub)          # uniform mask: absent modalities' work is skipped
             eng.ece_bins(labels, edges, out=stats[i])
+            if readback:
+                host_pred[i].copy_(eng.pred, non_blocking=True)
+        if readback:
+            host_stats.copy_(stats, non_blocking=True)
 
-    for _ in range(max(3, args.warmup)):
-        sweep()
-    torch.cuda.synchronize()
     steps = max(1, min(args.steps, 50))
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(0)
+    sampler.start()
     stats.zero_()
-    start.record()
-    for _ in range(steps):
-        sweep()
-    stop.record()
-    torch.cuda.synchronize()
-    ms = start.elapsed_time(stop) / steps
+    ms, repeats = _timed_repeats(torch, sweep, steps, max(3, args.warmup))
+    clocks = sampler.stop()
+    total = int(stats[:, 0].sum().item())
+    stats.zero_()
+    ms_e2e, rep_e2e = _timed_repeats(torch, lambda: sweep(host_feats, True), max(1, min(steps, 10)), 2, min_seconds=0.3)
     evals = len(subsets) * B
     peaks = _peaks()
-    tf = FLOP_FWD * evals / (ms * 1e-3) / 1e12
+    per_eval = FLOP_FWD if args.no_mask_hint else FLOP_SWEEP_MASK_AWARE
+    tf = per_eval * evals / (ms * 1e-3) / 1e12
+    h2d = sum(f.numel() * 4 for f in host_feats)
     line = {"metric": METRIC, "value": evals / (ms * 1e-3), "unit": "windows/s", "n_gpus": 1, "steps": steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": "HybridFusion inference mask sweep (BASELINE configs[2]): 15 subsets x 65536 "
                                    "windows, fwd + softmax/argmax + ECE binning", "batch": B, "subsets": len(subsets),
-                       "mask_hint": not args.no_mask_hint,
-                       "l2": "inputs 34 MB per subset, workspace 1.7 GB >> 126 MiB L2"},
+                       "mask_hint": not args.no_mask_hint},
+            "run": {"l2": "inputs 34 MB per subset, workspace 1.7 GB >> 126 MiB L2", "repeats": repeats,
+                    "timed_region_ms": ms * steps * repeats, "a_step_is": "one sweep = 15 x 65536 window-evaluations"},
+            "clocks": clocks,
+            "e2e": {"value": evals / (ms_e2e * 1e-3), "unit": "windows/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": host_pred.numel() * 8 + host_stats.numel() * 8,
+                    "repeats": rep_e2e,
+                    "api": "FusionEngine.load_batch(pinned host features) once per sweep, infer_subset x 15, "
+                           "ece_bins; predictions and bin statistics of every subset copied back"},
+            "gpu_launches": None,
             "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": tf / peaks["tflops"], "traffic": None, "peak_source": peaks["src"],
-                         "kernel": "whole sweep, dense forward FLOPs (3 553 792 per window-evaluation)"},
-            "accuracy_bins_total": int(stats[:, 0].sum().item()) // steps}
+                         "kernel": "whole sweep; algorithmic FLOPs per window-evaluation: "
+                                   + ("3 553 792 (dense path: every subset runs the full forward)" if args.no_mask_hint else
+                                      "1 123 635 (mask-aware: only pairs with both modalities present, SURVEY 8d config 3)")},
+            "accuracy_bins_total": total // (steps * repeats)}
+    before = pkg.lib().msf_launch_count()
+    sweep()
+    torch.cuda.synchronize()
+    line["gpu_launches"] = int(pkg.lib().msf_launch_count() - before) if args.no_graph else None
+    line["gpu_launches_per_step"] = "45 forward-pass kernels (3 per subset, CUDA graphs) + 15 ece_bin_kernel"
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = _cpu_sweep_baseline(torch, subsets)
     os.write(json_fd, (json.dumps(line) + "\n").encode())
+
+
+def _cpu_sweep_baseline(torch, subsets, sample=8192):
+    """The reference arithmetic of the sweep on the host: oracle forward (eval mode) + softmax/max + 15-bin ECE
+    binning for every subset, on a bounded sample of windows."""
+    from oracle import ece_oracle, fusion_oracle
+    sys.path.insert(0, os.path.join(ROOT, PKG, "src"))
+    fusion = importlib.import_module("fusion")
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = fusion.HybridFusion(DIMS, hidden_dim=HIDDEN, num_classes=CLASSES, num_heads=HEADS, dropout=DROPOUT)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    names = list(DIMS)
+    feats, _, labels = synthetic_batch(torch, 1234, sample)
+    xs = dict(zip(names, feats))
+    edges = ece_oracle.linspace_f32(15).astype("float64")
+
+    def one_sweep():
+        with torch.no_grad():
+            for sub in subsets:
+                mask = torch.zeros(sample, len(names))
+                mask[:, list(sub)] = 1.0
+                zeroed = {m: (x if i in sub else torch.zeros_like(x)) for i, (m, x) in enumerate(xs.items())}  # eval.py:401-404
+                logits, _ = fusion_oracle.hybrid_fusion_forward(sd, names, HEADS, zeroed, mask)
+                conf, pred = fusion_oracle.softmax_conf_pred(logits)
+                ece_oracle.bin_masks(conf.numpy(), pred.numpy(), labels.numpy(), edges)
+
+    one_sweep()
+    times = []
+    t_end = time.perf_counter() + 12.0
+    while time.perf_counter() < t_end and len(times) < 20:
+        t0 = time.perf_counter()
+        one_sweep()
+        times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return {"value": len(subsets) * sample / med, "unit": "windows/s", "cores": cores, "kind": "port",
+            "sample": f"{len(times)} sweeps of 15 subsets x {sample} windows (oracle fp32 forward + softmax/max + numpy "
+                      f"binning), median; a reported baseline, not the target"}
 
 
 def run_raw_infer(args):
@@ -620,7 +715,10 @@ def run_raw_infer(args):
 
 def run_ece(args):
     """ECE / reliability binning kernel (uncertainty.py:84-171) on N = 2^28 samples resident in HBM:
-    20 B/sample (f32 conf + i64 pred + i64 label), HBM-bound; buffers (5.4 GB) >> L2."""
+    20 B/sample (f32 conf + i64 pred + i64 label), HBM-bound; buffers (5.4 GB) >> L2.  `e2e`: 2^25 samples from
+    pinned host memory through ops.ece_bin with the statistics read back (PCIe-bound by construction);
+    `cpu_baseline`: the C oracle (oracle/ece_oracle.c) on the host."""
+    import numpy as np
     import torch
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
@@ -635,28 +733,66 @@ def run_ece(args):
     label = torch.randint(0, CLASSES, (n,), device=dev, generator=g)
     edges = torch.linspace(0, 1, 16).double().tolist()
     out = torch.zeros(3, 15, dtype=torch.int64, device=dev)
-    for _ in range(max(3, args.warmup)):
-        ops.ece_bin(conf, pred, label, edges, out=out)
-    torch.cuda.synchronize()
     steps = max(1, min(args.steps, 20))
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(0)
+    sampler.start()
     out.zero_()
-    start.record()
-    for _ in range(steps):
-        ops.ece_bin(conf, pred, label, edges, out=out)
-    stop.record()
-    torch.cuda.synchronize()
-    ms = start.elapsed_time(stop) / steps
+    ms, repeats = _timed_repeats(torch, lambda: ops.ece_bin(conf, pred, label, edges, out=out), steps, max(3, args.warmup))
+    clocks = sampler.stop()
+    assert int(out[0].sum().item()) == n * (steps * repeats + max(3, args.warmup)), "every in-range confidence lands in exactly one bin"
+    # end to end: host buffers in, statistics out
+    ne = 1 << 25
+    h_conf, h_pred, h_label = (t[:ne].cpu().pin_memory() for t in (conf, pred, label))
+    d_conf, d_pred, d_label = (torch.empty_like(t[:ne]) for t in (conf, pred, label))
+    h_out = torch.zeros(3, 15, dtype=torch.int64).pin_memory()
+
+    def e2e():
+        d_conf.copy_(h_conf, non_blocking=True)
+        d_pred.copy_(h_pred, non_blocking=True)
+        d_label.copy_(h_label, non_blocking=True)
+        out.zero_()
+        ops.ece_bin(d_conf, d_pred, d_label, edges, out=out)
+        h_out.copy_(out, non_blocking=True)
+
+    ms_e2e, rep_e2e = _timed_repeats(torch, e2e, 3, 2, min_seconds=0.3)
     peaks = _peaks()
     gbs = 20.0 * n / (ms * 1e-3) / 1e9
-    assert int(out[0].sum().item()) == n * steps, "every in-range confidence lands in exactly one bin"
     line = {"metric": "samples/sec ECE / reliability binning", "value": n / (ms * 1e-3), "unit": "samples/s",
-            "n_gpus": 1, "steps": steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
+            "n_gpus": 1, "steps": steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32+i64", "data": "synthetic",
-            "config": {"workload": "ECE binning, 15 bins, N = 2^28 samples", "l2": "5.4 GB of inputs >> 126 MiB L2"},
+            "config": {"workload": "ECE binning, 15 bins, N = 2^28 samples"},
+            "run": {"l2": "5.4 GB of inputs >> 126 MiB L2", "repeats": repeats, "timed_region_ms": ms * steps * repeats},
+            "clocks": clocks,
+            "e2e": {"value": ne / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e, "samples": ne,
+                    "h2d_bytes_per_step": 20 * ne, "d2h_bytes_per_step": 3 * 15 * 8, "repeats": rep_e2e,
+                    "api": "ops.ece_bin on device copies of pinned host arrays (3 H2D copies), statistics copied back"},
+            "gpu_launches": steps, "gpu_launches_per_step": 1,
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["src"],
                          "kernel": "ece_bin_kernel, 20 algorithmic bytes per sample"}}
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            line["roofline"]["traffic"] = json.load(f).get("ece_bin_kernel_dram_bytes_per_launch")
+    except Exception:  # noqa: BLE001
+        pass
+    if not args.no_cpu_baseline:
+        from oracle import ece_oracle
+        ns = 1 << 24
+        c_np, p_np, l_np = (t[:ns].cpu().numpy() for t in (conf, pred, label))
+        e_np = np.asarray(edges, dtype=np.float64)
+        cores = os.cpu_count() or 1
+        ece_oracle.bin_masks_c(c_np, p_np, l_np, e_np, threads=cores)
+        times = []
+        t_end = time.perf_counter() + 10.0
+        while time.perf_counter() < t_end and len(times) < 30:
+            t0 = time.perf_counter()
+            cnt, _, _ = ece_oracle.bin_masks_c(c_np, p_np, l_np, e_np, threads=cores)
+            times.append(time.perf_counter() - t0)
+        assert int(np.asarray(cnt).sum()) == ns
+        med = statistics.median(times)
+        line["cpu_baseline"] = {"value": ns / med, "unit": "samples/s", "cores": cores, "kind": "port",
+                                "sample": f"{len(times)} passes over 2^24 samples, C oracle (oracle/ece_oracle.c: the "
+                                          f"reference's per-bin mask passes), {cores} threads, median"}
     os.write(json_fd, (json.dumps(line) + "\n").encode())
 
 
@@ -673,7 +809,7 @@ def profile_dominant_kernel(torch, pkg, eng, ring, ring_n, steps=12, chain_reps=
     if eng.prec != pkg.native.MSF_PREC_BF16:
         return None
     lib = pkg.lib()
-    snap = (eng.arena.clone(), eng.exp_avg.clone(), eng.exp_avg_sq.clone(), eng.state.clone())
+    snap = eng._snapshot()
     for i in range(3):
         eng.load_batch(*ring[i % ring_n])
         eng._enqueue_train_step()
@@ -697,10 +833,7 @@ def profile_dominant_kernel(torch, pkg, eng, ring, ring_n, steps=12, chain_reps=
 
     rows = one_pass(1, steps)
     chain_rows = [r for r in one_pass(chain_reps, 4) if "chain" in r["launch"]]
-    for dst, src in zip((eng.arena, eng.exp_avg, eng.exp_avg_sq, eng.state), snap):
-        dst.copy_(src)
-    if eng.arena_bf16 is not None:
-        eng.arena_bf16.copy_(eng.plan.pack_bf16(eng.arena))
+    eng._restore(snap)
     return {"steps": steps, "rows": rows, "chain_rows": chain_rows, "chain_reps": chain_reps}
 
 
@@ -756,15 +889,12 @@ def eng_launches(lib, before, eng):
     import torch
     if not eng.use_graph:
         return int(lib.msf_launch_count() - before)
-    snap = (eng.arena.clone(), eng.exp_avg.clone(), eng.exp_avg_sq.clone(), eng.state.clone())
+    snap = eng._snapshot()
     a = lib.msf_launch_count()
     eng._enqueue_train_step()
     torch.cuda.synchronize()
     n = int(lib.msf_launch_count() - a)
-    for dst, src in zip((eng.arena, eng.exp_avg, eng.exp_avg_sq, eng.state), snap):
-        dst.copy_(src)
-    if eng.arena_bf16 is not None:
-        eng.arena_bf16.copy_(eng.plan.pack_bf16(eng.arena))
+    eng._restore(snap)
     return n
 
 

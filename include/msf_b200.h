@@ -289,6 +289,34 @@ int msf_dp_optimizer_step_packed(const msf_fusion_shape* shape, const msf_dp_com
                                  float* exp_avg, float* exp_avg_sq, uint64_t* train_state, float lr, float beta1,
                                  float beta2, float eps, float weight_decay, float grad_scale, float max_norm,
                                  void* params_bf16, int32_t advance_state, void* stream);
+/* Sharded ("owner computes") data-parallel step for the tensor-core path: the master arena is cut into optimizer
+ * units (32 x 32 tiles of the weight matrices, 1024-element pieces of the vectors); live unit u belongs to rank
+ * u % world.  Two kernels over NVLink peer memory:
+ *   (1) every rank pushes its gradient values of the units it does not own into the owner's staging arena
+ *       (stages[owner] + rank * total + arena offset); after a cross-GPU flag barrier each owner sums its units over
+ *       the ranks in fixed rank order, IN PLACE in `grad`, and publishes their square norm;
+ *   (2) after the norm barrier each owner applies clip + AdamW to its units (master weights and Adam moments of a
+ *       unit live on its owner only), pushes the bf16 copy and transposed copy of every updated weight tile into
+ *       EVERY rank's compute arena and the updated vector slots (biases, gating layers: the forward kernels read
+ *       them from the fp32 master) into every rank's master arena; dead query / key slots are decayed by every
+ *       rank; the kernel ends when all ranks' pushes have landed.
+ * The redundant full-arena AdamW of msf_dp_optimizer_step_packed becomes 1/world of it, and the reduced gradients
+ * never travel: (world-1)/world x 4 bytes per live parameter cross NVLink twice per step, as before.
+ * All pointer tables are peer-mapped (symmetric memory), indexed by rank; params == comm->params[comm->rank].
+ * msf_dpz_owner_map fills owner[total] on the HOST: rank owning each master element's weights and moments,
+ * -1 for replicated elements, -2 - rank for vector slots (moments on the owner, value valid everywhere). */
+typedef struct msf_dpz_comm {
+  int32_t rank, world;
+  float* stages[MSF_DP_MAX_RANKS];       /* world x total floats each */
+  void* arenas_bf16[MSF_DP_MAX_RANKS];   /* compute arenas (msf_fusion_pack_bf16 layout) */
+  float* params[MSF_DP_MAX_RANKS];       /* master arenas */
+  uint64_t* sigs[MSF_DP_MAX_RANKS];      /* 64 x uint64 signal blocks, zero-initialised */
+} msf_dpz_comm;
+int msf_dpz_optimizer_step_packed(const msf_fusion_shape* shape, const msf_dpz_comm* comm, float* params, float* grad,
+                                  float* exp_avg, float* exp_avg_sq, uint64_t* train_state, float lr, float beta1,
+                                  float beta2, float eps, float weight_decay, float grad_scale, float max_norm,
+                                  int32_t advance_state, void* stream);
+int msf_dpz_owner_map(const msf_fusion_shape* shape, int32_t world, int8_t* owner_host);
 /* train_state = DEVICE {seed, offset, step[, lr bits]}: offset += 1, step += 1.
  * Every optimizer entry point that takes a train_state accepts lr < 0: the learning rate is then the fp32 whose bits
  * are the low word of train_state[3] (a fourth uint64 the caller owns and updates between launches), so a captured

@@ -71,6 +71,17 @@ class DpComm(Structure):
     ]
 
 
+class DpzComm(Structure):  # msf_dpz_comm
+    _fields_ = [
+        ("rank", c_int32),
+        ("world", c_int32),
+        ("stages", c_void_p * 8),
+        ("arenas_bf16", c_void_p * 8),
+        ("params", c_void_p * 8),
+        ("sigs", c_void_p * 8),
+    ]
+
+
 class LstmSeq(ctypes.Structure):  # msf_lstm_seq
     _fields_ = [
         ("x_bf16", c_void_p), ("w_hh", c_void_p), ("w_ih", c_void_p), ("bias", c_void_p),
@@ -81,6 +92,10 @@ class LstmSeq(ctypes.Structure):  # msf_lstm_seq
 # name -> (restype, argtypes); every symbol include/msf_b200.h declares
 PROTOTYPES = {
     "msf_abi_version": (c_int32, []),
+    "msf_dpz_optimizer_step_packed": (c_int32, [POINTER(FusionShape), POINTER(DpzComm), c_void_p, c_void_p, c_void_p,
+                                                c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_float, c_float,
+                                                c_float, c_int32, c_void_p]),
+    "msf_dpz_owner_map": (c_int32, [POINTER(FusionShape), c_int32, c_void_p]),
     "msf_fusion_layer_norm_fused": (c_int32, [POINTER(FusionShape), c_int32]),
     "msf_layer_norm_forward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p]),
     "msf_layer_norm_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,

@@ -255,6 +255,39 @@ static int dp_step(const msf_fusion_shape* shape, const msf_dp_comm* comm, float
                    float weight_decay, float grad_scale, float max_norm, void* params_bf16, int advance,
                    void* stream);
 
+namespace msf {
+int fusion_bf16_opt_pack_dpz(const Layout& L, const msf_dpz_comm* comm, float* params, float* grad, float* exp_avg,
+                             float* exp_avg_sq, uint64_t* train_state, float lr, float beta1, float beta2, float eps,
+                             float wd, float grad_scale, float max_norm, int advance, cudaStream_t st);
+int fusion_bf16_dpz_owner_map(const Layout& L, int world, signed char* owner_host);
+}
+
+extern "C" int msf_dpz_optimizer_step_packed(const msf_fusion_shape* shape, const msf_dpz_comm* comm, float* params,
+                                             float* grad, float* exp_avg, float* exp_avg_sq, uint64_t* train_state,
+                                             float lr, float beta1, float beta2, float eps, float weight_decay,
+                                             float grad_scale, float max_norm, int32_t advance_state, void* stream) {
+  msf::Layout L;
+  int rc = msf::make_layout(shape, &L);
+  if (rc) return rc;
+  MSF_REQUIRE(comm && params && grad && exp_avg && exp_avg_sq && train_state, "msf_dpz_optimizer_step_packed: null pointer");
+  MSF_REQUIRE(comm->world >= 1 && comm->world <= msf::DP_MAX_RANKS && comm->rank >= 0 && comm->rank < comm->world,
+              "msf_dpz_optimizer_step_packed: rank %d / world %d out of range", comm->rank, comm->world);
+  if (!msf::fusion_bf16_eligible(L)) {
+    msf::set_error("shape not eligible for the tensor-core path");
+    return MSF_E_UNSUPPORTED;
+  }
+  return msf::fusion_bf16_opt_pack_dpz(L, comm, params, grad, exp_avg, exp_avg_sq, train_state, lr, beta1, beta2, eps,
+                                       weight_decay, grad_scale, max_norm, advance_state, (cudaStream_t)stream);
+}
+
+extern "C" int msf_dpz_owner_map(const msf_fusion_shape* shape, int32_t world, int8_t* owner_host) {
+  msf::Layout L;
+  int rc = msf::make_layout(shape, &L);
+  if (rc) return rc;
+  MSF_REQUIRE(owner_host != nullptr && world >= 1 && world <= msf::DP_MAX_RANKS, "msf_dpz_owner_map: bad arguments");
+  return msf::fusion_bf16_dpz_owner_map(L, world, reinterpret_cast<signed char*>(owner_host));
+}
+
 extern "C" int msf_dp_optimizer_step(const msf_fusion_shape* shape, const msf_dp_comm* comm, float* params,
                                      float* exp_avg, float* exp_avg_sq, const uint64_t* train_state, float lr,
                                      float beta1, float beta2, float eps, float weight_decay, float grad_scale,

@@ -9,6 +9,7 @@ namespace msf {
 constexpr int SIG_DONE_B = 0;    // [p]: rank p has finished the backward pass of step s
 constexpr int SIG_DONE_R = 8;    // [p]: rank p has finished reducing its slice of step s
 constexpr int SIG_NORM = 16;     // [p]: square-norm of rank p's slice (double bits)
+constexpr int SIG_DONE_W = 24;   // [p]: rank p has pushed its share of the updated bf16 weights everywhere (sharded step)
 constexpr int SIG_ACC = 32;      // local accumulator of the slice norm (double)
 constexpr int SIG_TICKET = 33;   // local last-block ticket (reduce kernel)
 constexpr int SIG_TICKET2 = 34;  // local last-block ticket (reduce kernel, phase 2)

@@ -35,6 +35,7 @@ class FusionEngine:
                  process_group=None, use_graph: bool = True, device: Optional[torch.device] = None,
                  comm: str = "auto"):
         self.dev = device or ops.require_cuda("FusionEngine")
+        self.arena_bf16 = None
         self.model = model.to(self.dev)
         self.plan = model._plan()
         self.batch = int(batch)
@@ -64,24 +65,38 @@ class FusionEngine:
         # memory (msf_dp_optimizer_step), "nccl" = all-reduce then optimizer, "auto" = p2p when available
         self.comm, self.dp_comm = "none", None
         self.grad = None
-        if self.world > 1 and comm in ("auto", "p2p"):
-            try:
-                self._setup_peer_memory()
-                self.comm = "p2p"
-            except Exception as exc:  # noqa: BLE001 - symmetric memory is optional plumbing
-                if comm == "p2p":
-                    raise
-                import sys
-                print(f"msf_b200: peer-memory gradient exchange unavailable ({exc}); using NCCL", file=sys.stderr)
-        if self.world > 1 and self.comm != "p2p":
+        # "zshard": sharded optimizer over NVLink peer memory (msf_dpz_optimizer_step_packed, tensor-core path only):
+        # every rank reduces and updates only the optimizer units it owns and pushes their bf16 copies to all ranks;
+        # "auto" prefers it, then "p2p" (replicated AdamW from pushed reduced gradients), then NCCL.
+        want = [comm] if comm != "auto" else (["zshard", "p2p"] if self.prec == N.MSF_PREC_BF16 else ["p2p"])
+        if self.world > 1:
+            for mode in want:
+                if mode not in ("zshard", "p2p"):
+                    continue
+                try:
+                    if mode == "zshard":
+                        if self.prec != N.MSF_PREC_BF16:
+                            raise N.MsfError("the sharded step needs the tensor-core path")
+                        self._setup_sharded()
+                    else:
+                        self._setup_peer_memory()
+                    self.comm = mode
+                    break
+                except Exception as exc:  # noqa: BLE001 - symmetric memory is optional plumbing
+                    if comm == mode:
+                        raise
+                    import sys
+                    print(f"msf_b200: {mode} gradient exchange unavailable ({exc})", file=sys.stderr)
+        if self.world > 1 and self.comm == "none":
             self.comm = "nccl"
         if self.grad is None:
             self.grad = torch.zeros(plan.total, **f32)
         self.exp_avg = torch.zeros(plan.total, **f32)
         self.exp_avg_sq = torch.zeros(plan.total, **f32)
-        self.arena_bf16 = None
-        if self.prec == N.MSF_PREC_BF16:
+        if self.prec == N.MSF_PREC_BF16 and getattr(self, "arena_bf16", None) is None:
             self.arena_bf16 = plan.pack_bf16(self.arena)
+        elif self.prec != N.MSF_PREC_BF16:
+            self.arena_bf16 = None
         self.ws = torch.empty(plan.workspace_bytes(B, self.prec), dtype=torch.uint8, device=dev)
 
         # static I/O buffers (graph inputs / outputs).  Two input slots: the host-facing stream API
@@ -132,7 +147,8 @@ class FusionEngine:
         if norms is None:
             self._ln, self._ln_eps = None, 1e-5
             return
-        seq = [norms.get(m) if hasattr(norms, "get") else norms[i] for i, m in enumerate(self.plan.names)]
+        keyed = hasattr(norms, "keys")
+        seq = [(norms[m] if m in norms else None) if keyed else norms[i] for i, m in enumerate(self.plan.names)]
         if not ops.layer_norm_fused(self.plan, self.prec):
             raise N.MsfError("input LayerNorm is fused on the tensor-core path only (msf_fusion_layer_norm_fused)")
         eps = {float(n.eps) for n in seq if n is not None}
@@ -177,6 +193,12 @@ class FusionEngine:
                                           self._loss_ptr.get(slot, self.loss.data_ptr()), self.dlogits.data_ptr(),
                                           N.MSF_TRAIN_DEAD_SLOTS_ZERO,   # self.grad is zero-initialised and only
                                           st))                           # ever written by this entry point
+        if self.comm == "zshard":
+            N.check(lib.msf_dpz_optimizer_step_packed(
+                ctypes_ref(self.plan.shape), ctypes_ref(self.dp_comm), self.arena.data_ptr(), self.grad.data_ptr(),
+                self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.state.data_ptr(), -1.0, self.betas[0],
+                self.betas[1], self.eps, self.wd, 1.0, self.max_norm, 1, st))
+            return
         if self.comm == "p2p":
             # reduce-scatter + norm over NVLink peer memory, then clip + AdamW (+ bf16 re-pack + state advance
             # in the same launch on the tensor-core path) from the local reduced arena
@@ -241,6 +263,57 @@ class FusionEngine:
             comm.stages[r] = int(handles[3].buffer_ptrs[r])
         self._symm_handles = handles
         self.dp_comm = comm
+
+    def _setup_sharded(self) -> None:
+        """Master arena, compute arena, staging (world x arena) and signal block in symmetric memory; the module's
+        parameters are re-pointed into the symmetric master arena."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        group = self.pg if self.pg is not None else dist.group.WORLD
+        n, plan = self.plan.total, self.plan
+        arena = symm_mem.empty(n, dtype=torch.float32, device=self.dev)
+        arena.copy_(self.arena)
+        packed = plan.pack_bf16(arena)
+        arena16 = symm_mem.empty(packed.numel(), dtype=packed.dtype, device=self.dev)
+        arena16.copy_(packed)
+        self.zstage = symm_mem.empty(n * self.world, dtype=torch.float32, device=self.dev)
+        self.sig = symm_mem.empty(64, dtype=torch.int64, device=self.dev)
+        handles = [symm_mem.rendezvous(t, group) for t in (arena, arena16, self.zstage, self.sig)]
+        self.zstage.zero_()
+        self.sig.zero_()
+        own = dict(self.model.named_parameters())
+        with torch.no_grad():
+            for key, off, shape in plan.slots:
+                own[key].data = arena[off:off + own[key].numel()].view(shape)
+        self.arena, self.arena_bf16 = arena, arena16
+        torch.cuda.synchronize(self.dev)
+        dist.barrier(group)  # nobody signals into a block that is not zeroed yet
+        comm = N.DpzComm()
+        comm.rank, comm.world = dist.get_rank(group), self.world
+        for r in range(self.world):
+            comm.params[r] = int(handles[0].buffer_ptrs[r])
+            comm.arenas_bf16[r] = int(handles[1].buffer_ptrs[r])
+            comm.stages[r] = int(handles[2].buffer_ptrs[r])
+            comm.sigs[r] = int(handles[3].buffer_ptrs[r])
+        self._symm_handles = handles
+        self.dp_comm = comm
+        owner = torch.empty(n, dtype=torch.int8)
+        N.check(N.lib().msf_dpz_owner_map(ctypes_ref(plan.shape), self.world, owner.data_ptr()))
+        self._owner = owner.to(self.dev)
+        self._rank = comm.rank
+
+    def gather_parameters(self) -> None:
+        """Sharded step only: make the fp32 master arena (the module's parameters) complete on every rank — each
+        weight tile is copied from the rank that owns it (one all-reduce of the owned values; sums with zeros are
+        exact).  Call before reading parameters for a checkpoint / state_dict; a no-op in every other mode.  Adam
+        moments stay sharded (`exp_avg` / `exp_avg_sq` hold the owner's values for owned tiles)."""
+        if self.comm != "zshard":
+            return
+        mine = self._owner == self._rank
+        owned_anywhere = self._owner >= 0
+        buf = torch.where(mine, self.arena, torch.zeros_like(self.arena))
+        torch.distributed.all_reduce(buf, group=self.pg)
+        self.arena.copy_(torch.where(owned_anywhere, buf, self.arena))
 
     def _live_gradient_views(self):
         """Views of the gradient arena that can be non-zero: everything except the query/key projection
@@ -423,12 +496,9 @@ class FusionEngine:
                 finally:
                     self._loss_ptr = saved
 
-            snap = (self.arena.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(), self.state.clone())
+            snap = self._snapshot()
             graph = self._capture(enqueue)
-            for dst, src in zip((self.arena, self.exp_avg, self.exp_avg_sq, self.state), snap):
-                dst.copy_(src)
-            if self.arena_bf16 is not None:
-                self.arena_bf16.copy_(self.plan.pack_bf16(self.arena))
+            self._restore(snap)
             entry = self._epoch_graphs[key] = (graph, losses)
         entry[0].replay()
         return entry[1]
@@ -538,14 +608,28 @@ class FusionEngine:
         self._ev_done[pending].synchronize()
         yield float(loss_np[pending])
 
+    def _snapshot(self):
+        """Everything a train step changes.  The compute arena is saved as it is, not re-packed from the master:
+        under the sharded step a rank's master is only current for the tiles it owns."""
+        return tuple(t.clone() for t in (self.arena, self.exp_avg, self.exp_avg_sq, self.state)
+                     + ((self.arena_bf16,) if self.arena_bf16 is not None else ()))
+
+    def _restore(self, snap) -> None:
+        torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            torch.distributed.barrier(self.pg)   # no peer is still pushing into the arenas being restored
+        for dst, src in zip((self.arena, self.exp_avg, self.exp_avg_sq, self.state)
+                            + ((self.arena_bf16,) if self.arena_bf16 is not None else ()), snap):
+            dst.copy_(src)
+        torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            torch.distributed.barrier(self.pg)
+
     def _replay_train_capture_only(self, slot: int) -> None:
         """Capture the train graph over `slot` without leaving a net model update behind."""
-        snap = (self.arena.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(), self.state.clone())
+        snap = self._snapshot()
         self._train_graphs[slot] = self._capture(lambda: self._enqueue_train_step(slot))
-        for dst, src in zip((self.arena, self.exp_avg, self.exp_avg_sq, self.state), snap):
-            dst.copy_(src)
-        if self.arena_bf16 is not None:
-            self.arena_bf16.copy_(self.plan.pack_bf16(self.arena))
+        self._restore(snap)
         self._train_graph = self._train_graphs[0]
 
     def infer_resident(self):

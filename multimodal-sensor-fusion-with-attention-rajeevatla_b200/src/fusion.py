@@ -216,7 +216,7 @@ class HybridFusion(nn.Module):
         }
         ln_tensors = []
         if input_norms:
-            norms = [input_norms.get(m) if hasattr(input_norms, "get") else input_norms[m] for m in names]
+            norms = [input_norms[m] if m in input_norms else None for m in names]
             canonical = all(n is None or (isinstance(n, nn.LayerNorm) and len(n.normalized_shape) == 1) for n in norms)
             eps = {float(n.eps) for n in norms if n is not None}
             with torch.cuda.device(dev):

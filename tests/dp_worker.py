@@ -60,6 +60,33 @@ def main():
                                                    eng.arena_bf16.view(torch.int16)))
     out["bf16_state"] = eng.state.tolist()
     out["bf16_vs_fp32"] = float((mine16 - res["p2p"]).abs().max())
+    # sharded optimizer (msf_dpz_optimizer_step_packed): every rank reduces / updates only the tiles it owns and
+    # pushes their bf16 copies everywhere.  Same arithmetic as the replicated p2p step: after gather_parameters()
+    # the masters equal the p2p engine's bit for bit, and every rank's compute arena is the pack of those masters.
+    model, feats, mask, labels = seeded_case(PAMAP2, 256, 4, 25, GLOBAL_B, seed=31, device=dev)
+    engz = engine.FusionEngine(model, GLOBAL_B // world, precision="bf16", seed=9, use_graph=True, comm="zshard")
+    assert engz.comm == "zshard", engz.comm
+    engz.p = 0.0
+    for _ in range(STEPS):
+        engz.train_step(*shard)
+    torch.cuda.synchronize()
+    dist.barrier()
+    bf16_local = engz.arena_bf16.clone()
+    engz.gather_parameters()
+    torch.cuda.synchronize()
+    mz = engz.arena.clone()
+    other = [torch.empty_like(mz) for _ in range(world)]
+    dist.all_gather(other, mz)
+    out["zshard_replicas_identical"] = all(bool(torch.equal(o, mz)) for o in other)
+    other16 = [torch.empty_like(bf16_local) for _ in range(world)]
+    dist.all_gather(other16, bf16_local)
+    out["zshard_bf16_identical"] = all(bool(torch.equal(o.view(torch.int16), bf16_local.view(torch.int16))) for o in other16)
+    out["zshard_pack_consistent"] = bool(torch.equal(engz.plan.pack_bf16(engz.arena).view(torch.int16),
+                                                     bf16_local.view(torch.int16)))
+    out["zshard_vs_p2p"] = float((mz - mine16).abs().max())
+    out["zshard_state"] = engz.state.tolist()
+    out["zshard_module_param_is_arena_view"] = bool(
+        next(iter(engz.model.parameters())).data_ptr() == engz.arena.data_ptr())
     if rank == 0:
         model, feats, mask, labels = seeded_case(PAMAP2, 256, 4, 25, GLOBAL_B, seed=31, device=dev)
         start = torch.cat([p.detach().flatten() for p in model.parameters()]).clone()

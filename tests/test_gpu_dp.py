@@ -38,3 +38,11 @@ def test_peer_memory_step_matches_nccl_and_single_process():
     assert res["bf16_pack_consistent"], res     # the compute arena is exactly the pack of the updated parameters
     assert res["bf16_state"][2] >= 3 and res["bf16_state"][1] == res["bf16_state"][2] - 1, res
     assert res["bf16_vs_fp32"] <= 1.3e-2, res   # Adam turns sign flips of ~0 gradients into 2*lr per step
+    # sharded optimizer (msf_dpz_optimizer_step_packed): owner-computes, bf16 weights pushed to every rank
+    assert res["zshard_replicas_identical"], res          # masters agree once gathered from their owners
+    assert res["zshard_bf16_identical"], res              # every rank computes with the same bf16 weights
+    assert res["zshard_pack_consistent"], res             # ... which are exactly the pack of the masters
+    assert res["zshard_vs_p2p"] <= 2e-5, res              # same sums in the same rank order, same AdamW: the two
+                                                          # exchanges differ only where fp32 atomics order the bias sums
+    assert res["zshard_state"][2] == res["bf16_state"][2], res
+    assert res["zshard_module_param_is_arena_view"], res
