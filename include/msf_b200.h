@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define MSF_ABI_VERSION 3
+#define MSF_ABI_VERSION 4
 #define MSF_MAX_MODALITIES 8
 
 enum {
@@ -81,7 +81,7 @@ typedef struct msf_fusion_call {
                                    captured CUDA graph draws fresh masks on every replay */
   const float* params;          /* master arena, fp32                          */
   const void* params_bf16;      /* compute arena made by msf_fusion_pack_bf16 (BF16 precision) */
-  const float* x[MSF_MAX_MODALITIES];  /* (B, D_m) row-major fp32 encoder outputs */
+  const float* x[MSF_MAX_MODALITIES];  /* (B, D_m) row-major encoder outputs: fp32, or bf16 when x_bf16 != 0 */
   const float* mask;            /* (B, M) fp32 availability, or NULL = all ones */
   void* workspace;              /* msf_fusion_workspace_bytes(); forward fills it, backward reads it */
   size_t workspace_bytes;
@@ -107,6 +107,11 @@ typedef struct msf_fusion_call {
   const float* ln_weight[MSF_MAX_MODALITIES];
   const float* ln_bias[MSF_MAX_MODALITIES];
   float ln_eps;
+  /* nonzero: x[m] point to bf16 rows (B, D_m), 2 bytes per element.  The tensor-core path rounds the inputs to bf16
+   * anyway (xt = bf16(dropout(x * mask))), so features that cross PCIe as bf16 halve the host->device bytes of a
+   * step; only where the fused projection kernel runs (BF16 precision, in_dims % 64 == 0, <= 256), else
+   * MSF_E_UNSUPPORTED.  grad_x stays fp32. */
+  int32_t x_bf16;
 } msf_fusion_call;
 
 /* ---- per-modality LayerNorm (src/train.py:170-171,267-268) ------------------ */

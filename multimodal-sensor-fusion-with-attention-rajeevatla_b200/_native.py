@@ -11,7 +11,7 @@ MSF_MAX_MODALITIES = 8
 MSF_PREC_F32, MSF_PREC_BF16 = 0, 1
 MSF_TRAIN_DEAD_SLOTS_ZERO = 1
 MSF_OPT_NORM_GIVEN = 2
-MSF_ABI_VERSION = 3
+MSF_ABI_VERSION = 4
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -57,6 +57,7 @@ class FusionCall(Structure):
         ("ln_weight", c_void_p * MSF_MAX_MODALITIES),
         ("ln_bias", c_void_p * MSF_MAX_MODALITIES),
         ("ln_eps", c_float),
+        ("x_bf16", c_int32),
     ]
 
 

@@ -36,6 +36,10 @@ static int check_call(const Layout& L, const msf_fusion_call* c, bool backward) 
   for (int m = 0; m < L.M; ++m) MSF_REQUIRE(c->x[m] != nullptr, "null features for modality %d", m);
   MSF_REQUIRE(c->workspace != nullptr, "null workspace");
   if (!backward) MSF_REQUIRE(c->logits != nullptr, "null logits");
+  if (c->x_bf16 && c->precision != MSF_PREC_BF16) {
+    set_error("msf_fusion_call.x_bf16 needs BF16 precision (the fp32 parity path reads fp32 features)");
+    return MSF_E_UNSUPPORTED;
+  }
   if (c->precision == MSF_PREC_BF16) {
     MSF_REQUIRE(c->params_bf16 != nullptr, "BF16 precision needs params_bf16 (msf_fusion_pack_bf16)");
     if (!fusion_bf16_eligible(L)) {

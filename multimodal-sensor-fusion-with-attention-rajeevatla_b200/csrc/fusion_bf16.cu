@@ -23,6 +23,7 @@
 #include "head_gemm.cuh"
 #include "proj_gemm.cuh"
 #include "tc_gemm.cuh"
+#include "wg2_gemm.cuh"
 
 namespace msf {
 
@@ -707,6 +708,7 @@ static int forward_front(const Layout& L, const msf_fusion_call* c, const WsBf16
     }
     if ((rc = tc_encode_map(&pl.map_p, ws.P, B, H, H, M, BH, 64, 128))) return rc;
     pl.mask = c->mask;
+    pl.x_bf16 = c->x_bf16 != 0;
     pl.ln_eps = c->ln_eps;
     pl.drop = drop;
     if (present_hint != 0u)
@@ -723,6 +725,10 @@ static int forward_front(const Layout& L, const msf_fusion_call* c, const WsBf16
     }
     if ((rc = proj_launch(pl, st, "F0+F1 input prep + projections"))) return rc;
   } else {
+  if (c->x_bf16) {
+    set_error("msf_fusion_call.x_bf16 is only read by the fused projection kernel (in_dims %% 64 == 0, <= 256, hidden <= 256)");
+    return MSF_E_UNSUPPORTED;
+  }
   for (int m = 0; m < M; ++m)
     MSF_REQUIRE(c->ln_weight[m] == nullptr && c->ln_bias[m] == nullptr,
                 "msf_fusion_call.ln_* is only applied by the fused projection kernel (msf_fusion_layer_norm_fused() == 0 "
@@ -1213,7 +1219,37 @@ static int backward_back(const Layout& L, const msf_fusion_call* c, const WsBf16
     MSF_LAUNCH_CHECK();
   }
   // ---- all weight gradients: one MN-major launch, dW[out,in] = dY^T . X over the windows ----
-  {
+  bool wg_pairs = wg2_enabled() && wg2_shape_ok(H, H, dW + L.cls_w1) && wg2_shape_ok(H, H, dW + L.cls_w2) &&
+                  (pairs == 0 || (wg2_shape_ok(H, H, dW + L.pair_w(0, 2)) && L.pair_stride % 4 == 0 && (H * H + H) % 4 == 0));
+  for (int m = 0; m < M; ++m) wg_pairs = wg_pairs && wg2_shape_ok(L.D[m], L.D[m], dW + L.proj_w[m]);
+  wg_pairs = wg_pairs && 9 + M <= WG2_MAX_MAPS && 2 + 2 * pairs + M <= WG2_MAX_PROBLEMS;
+  if (wg_pairs) {   // CTA pairs, 256 x 256 tiles, the contraction split in two halves (wg2_gemm.cu)
+    Wg2Builder wb(B, st, "WG weight gradients");
+    const short mapDlog = (short)wb.add_map(ws.dlog, B, Cp, Cp, 1, 0);
+    const short mapHr = (short)wb.add_map(ws.Hr, B, H, H, 1, 0);
+    const short mapDH1 = (short)wb.add_map(ws.dH1, B, H, H, 1, 0);
+    const short mapFused = (short)wb.add_map(ws.fused, B, H, H, 1, 0);
+    const short mapDS = (short)wb.add_map(ws.dS, B, H, H, M, BH);
+    const short mapU = (short)wb.add_map(ws.U, B, H, H, pairs > 0 ? pairs : 1, BH);
+    const short mapDV = (short)wb.add_map(ws.dV, B, H, H, pairs > 0 ? pairs : 1, BH);
+    const short mapP = (short)wb.add_map(ws.P, B, H, H, M, BH);
+    const short mapDZ = (short)wb.add_map(ws.dZ, B, H, H, M, BH);
+    double* sq = head_fused ? c->grad_sq : nullptr;   // cleared by the head kernel of the same pass
+    for (int q = 0; q < M; ++q)   // the heavy tiles first
+      for (int k = 0; k < M; ++k) {
+        if (q == k || !L.has_pair(q, k)) continue;
+        const int pi = L.pair_index(q, k);
+        wb.add_problem(mapDS, q, mapU, pi, H, H, dW + L.pair_w(pi, 3), H, sq);    // dWo_qk = dS_q^T U_qk
+        wb.add_problem(mapDV, pi, mapP, k, H, H, dW + L.pair_w(pi, 2), H, sq);    // dWv_qk = dV_qk^T P_k
+      }
+    wb.add_problem(mapDH1, 0, mapFused, 0, H, H, dW + L.cls_w1, H, sq);           // dW1 = dH1^T fused
+    for (int m = 0; m < M; ++m) {
+      const short mapX = (short)wb.add_map(ws.xt[m], B, L.D[m], L.D[m], 1, 0);
+      wb.add_problem(mapDZ, m, mapX, 0, H, L.D[m], dW + L.proj_w[m], L.D[m], sq);  // dWp_m = dZ_m^T xt_m
+    }
+    wb.add_problem(mapDlog, 0, mapHr, 0, C, H, dW + L.cls_w2, H, sq);             // dW2 = dlogits^T Hr
+    if ((rc = wb.flush())) return rc;
+  } else {
     const int bn = 128;
     TcBuilder tb(true, bn, drop, st, "WG weight gradients");
     const short mapDlog = (short)tb.add_map(ws.dlog, B, Cp, Cp, 1, 0, 0);

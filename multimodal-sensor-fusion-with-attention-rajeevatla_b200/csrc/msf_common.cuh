@@ -107,6 +107,20 @@ __device__ __forceinline__ void tl_waited(int id) {
 __device__ __forceinline__ void tl_mark(int id, int slot) {   // slot 6 or 7: latest time any CTA passed the mark
   if (threadIdx.x == blockDim.x - 1 && threadIdx.y == 0) atomicMax(&g_tl[id][slot], tl_now());
 }
+// per-CTA mark under a kernel id of its own (one thread per CTA calls it once): shows up as "<tu>#<id>" with the
+// earliest / latest mark in the "CTA end" columns and every CTA's time in the .cta line
+__device__ __forceinline__ void tl_cta_mark(int id) {
+  const unsigned long long t = tl_now();
+  atomicMin(&g_tl[id][0], t);
+  atomicMin(&g_tl[id][3], t);
+  atomicMax(&g_tl[id][4], t);
+  atomicAdd(&g_tl[id][5], 1ull);
+  if (gridDim.x <= 256) {
+    unsigned int sm;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
+    g_tl_cta[id][blockIdx.x] = (t << 8) | (sm & 255u);
+  }
+}
 typedef int (*tl_dump_fn)(unsigned long long*, int);
 void tl_register(const char* tu, tl_dump_fn fn);
 static int tl_dump_local(unsigned long long* out, int reset) {
@@ -131,10 +145,12 @@ static TlRegistrar tl_registrar_instance;
 #define TL_KERNEL(id) TlScope tl_scope_(id)
 #define TL_WAITED(id) tl_waited(id)
 #define TL_MARK(id, slot) tl_mark(id, slot)
+#define TL_CTA_MARK(id) tl_cta_mark(id)
 #else
 #define TL_KERNEL(id)
 #define TL_WAITED(id)
 #define TL_MARK(id, slot)
+#define TL_CTA_MARK(id)
 #endif
 
 template <typename... KArgs, typename... Args>

@@ -30,6 +30,22 @@ __device__ __forceinline__ uint4 pj_pack8(const float (&v)[8]) {
   return pk;
 }
 
+// 8 consecutive input elements of a row as fp32, from fp32 or bf16 storage (shared or global memory)
+__device__ __forceinline__ void pj_load8(const void* base, long long elem, bool is_bf16, bool global, float4& a, float4& b) {
+  if (is_bf16) {
+    const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem);
+    const uint4 w = global ? __ldg(p) : *p;
+    a = make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xffff0000u), __uint_as_float(w.y << 16),
+                    __uint_as_float(w.y & 0xffff0000u));
+    b = make_float4(__uint_as_float(w.z << 16), __uint_as_float(w.z & 0xffff0000u), __uint_as_float(w.w << 16),
+                    __uint_as_float(w.w & 0xffff0000u));
+  } else {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem);
+    a = global ? __ldg(p) : p[0];
+    b = global ? __ldg(p + 1) : p[1];
+  }
+}
+
 __device__ long long g_proj_stamps[16];
 #define PJ_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 128) g_proj_stamps[i] = clock64(); } while (0)
 
@@ -128,10 +144,12 @@ __global__ void __launch_bounds__(PJ_THREADS, 1) proj_kernel(const __grid_consta
         if (it_cur > 0) mbar_wait(tile_done, (it_cur - 1) & 1u);   // the staging tile in the weight area has been stored
         if (staged) {   // the tile's fp32 rows are contiguous in global memory: one bulk copy
           const int nrows = (L.rows - m0) < 128 ? (L.rows - m0) : 128;
-          const uint32_t bytes = (uint32_t)nrows * (uint32_t)L.D[m] * 4u;
+          const uint32_t esz = L.x_bf16 ? 2u : 4u;
+          const uint32_t bytes = (uint32_t)nrows * (uint32_t)L.D[m] * esz;
           mbar_expect_tx(x_full, bytes);
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                       ::"r"(x_base), "l"(L.x[m] + (long long)m0 * L.D[m]), "r"(bytes), "r"(x_full)
+                       ::"r"(x_base), "l"(reinterpret_cast<const unsigned char*>(L.x[m]) + (long long)m0 * L.D[m] * esz),
+                         "r"(bytes), "r"(x_full)
                        : "memory");
         }
         mbar_expect_tx(w_full, (uint32_t)KB * WB);
@@ -205,33 +223,26 @@ __global__ void __launch_bounds__(PJ_THREADS, 1) proj_kernel(const __grid_consta
       if (ln) {
         // row statistics, one warp per 16 rows, the row in registers (float4 per lane and 128 columns): mean, then
         // the centred sum of squares (biased variance, like nn.LayerNorm)
-        const int c4n = D >> 2;
+        const int c8s = D >> 3;   // 8-column groups per row: lane l takes group l (D <= 256)
         const float inv_d = 1.0f / (float)D;
+        const bool xb = L.x_bf16 != 0;
 #pragma unroll 1
         for (int rr = 0; rr < 16; ++rr) {
           const int r = (warp - 4) * 16 + rr;
           const long long row = (long long)m0 + r;
-          float4 v[2];
-          float s = 0.0f;
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int c4 = lane + 32 * i;
-            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c4 < c4n && row < L.rows)
-              v[i] = staged ? *reinterpret_cast<const float4*>(x_smem + r * D + c4 * 4)
-                            : __ldg(reinterpret_cast<const float4*>(xm + row * D) + c4);
-            s += v[i].x + v[i].y + v[i].z + v[i].w;
-          }
+          float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+          const bool have = lane < c8s && row < L.rows;
+          if (have) pj_load8(staged ? (const void*)x_smem : (const void*)xm, (staged ? (long long)r : row) * D + lane * 8, xb, !staged, va, vb);
+          float s = va.x + va.y + va.z + va.w + vb.x + vb.y + vb.z + vb.w;
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
           const float mean = s * inv_d;
           float q = 0.0f;
-#pragma unroll
-          for (int i = 0; i < 2; ++i)
-            if (lane + 32 * i < c4n) {
-              const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
-              q += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
-            }
+          if (lane < c8s) {
+            const float a0 = va.x - mean, a1 = va.y - mean, a2 = va.z - mean, a3 = va.w - mean;
+            const float b0 = vb.x - mean, b1 = vb.y - mean, b2 = vb.z - mean, b3 = vb.w - mean;
+            q = a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3 + b0 * b0 + b1 * b1 + b2 * b2 + b3 * b3;
+          }
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
           if (lane == 0) {
@@ -250,13 +261,8 @@ __global__ void __launch_bounds__(PJ_THREADS, 1) proj_kernel(const __grid_consta
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (row < L.rows) {
           float4 a, b;
-          if (staged) {
-            a = *reinterpret_cast<const float4*>(x_smem + r * D + c8 * 8);
-            b = *reinterpret_cast<const float4*>(x_smem + r * D + c8 * 8 + 4);
-          } else {
-            a = __ldg(reinterpret_cast<const float4*>(xm + row * D + c8 * 8));
-            b = __ldg(reinterpret_cast<const float4*>(xm + row * D + c8 * 8) + 1);
-          }
+          pj_load8(staged ? (const void*)x_smem : (const void*)xm, (staged ? (long long)r : row) * D + c8 * 8, L.x_bf16 != 0,
+                   !staged, a, b);
           if (ln) {
             const float mu = stat_s[r], rs = stat_s[128 + r];
             const float4 g0 = *reinterpret_cast<const float4*>(lnw_s + c8 * 8), g1 = *reinterpret_cast<const float4*>(lnw_s + c8 * 8 + 4);

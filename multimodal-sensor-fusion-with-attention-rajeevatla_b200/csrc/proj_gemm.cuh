@@ -29,7 +29,8 @@ struct ProjLaunch {
   int M, H, rows, row_tiles, items;
   int w_area, a_area, x_area;               // shared-memory carve-up in bytes (set by proj_launch)
   int D[MSF_MAX_MODALITIES];
-  const float* x[MSF_MAX_MODALITIES];       // (rows, D_m) fp32
+  const float* x[MSF_MAX_MODALITIES];       // (rows, D_m) fp32, or bf16 rows when x_bf16
+  int x_bf16;
   const float* bias[MSF_MAX_MODALITIES];    // (H)
   int n_active;                             // modalities that get items (0: all M); absent ones of a uniform-mask
   short active[MSF_MAX_MODALITIES];         // inference pass are left out

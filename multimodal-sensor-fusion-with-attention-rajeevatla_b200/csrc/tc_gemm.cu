@@ -14,6 +14,7 @@
 #include <stdlib.h>
 
 #include "tc_ptx.cuh"
+#include "wg2_gemm.cuh"
 
 namespace msf {
 
@@ -738,6 +739,15 @@ extern "C" int msf_gemm_bf16(const void* a, const void* b, void* d, int32_t d_is
                              const float* bias, int32_t relu, void* stream) {
   MSF_REQUIRE(a && b && d && m >= 1 && n >= 1 && k >= 1, "msf_gemm_bf16: bad arguments");
   MSF_REQUIRE(m < (1ll << 31) && n < (1ll << 31) && k < (1ll << 31), "msf_gemm_bf16: dimension too large");
+  if (mn_major && !d_is_bf16 && bias == nullptr && !relu && msf::wg2_enabled() && msf::wg2_shape_ok((int)n, ldd, d)) {
+    // weight-gradient shape: CTA pairs, 256 x 256 tiles, contraction split in two halves (wg2_gemm.cu)
+    msf::Wg2Builder wb(k, (cudaStream_t)stream, "wg2_gemm");
+    const short am = (short)wb.add_map(a, k, m, lda, 1, 0), bm = (short)wb.add_map(b, k, n, ldb, 1, 0);
+    if (am < 0 || bm < 0) return wb.status;
+    int rc = wb.add_problem(am, 0, bm, 0, (int)m, (int)n, static_cast<float*>(d), ldd, nullptr);
+    if (rc) return rc;
+    return wb.flush();
+  }
   int bn = n > 128 ? 256 : n > 64 ? 128 : 64;
   if (!d_is_bf16 && bn > 128) bn = 128;  // fp32 tiles are staged in shared memory: 128 x 128 x 4 B
   if (!mn_major && n <= 32) bn = 32;

@@ -33,8 +33,16 @@ class FusionEngine:
                  weight_decay: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
                  label_smoothing: float = 0.05, max_grad_norm: float = 1.0, seed: int = 1234,
                  process_group=None, use_graph: bool = True, device: Optional[torch.device] = None,
-                 comm: str = "auto"):
+                 comm: str = "auto", feature_dtype: torch.dtype = torch.float32):
+        """``feature_dtype=torch.bfloat16`` (tensor-core path): the input slots hold the features as bf16 rows
+        (msf_fusion_call.x_bf16) — the projection kernel rounds them to bf16 anyway, and a host batch that is
+        already bf16 (``pinned_batch()``) crosses PCIe with half the bytes."""
         self.dev = device or ops.require_cuda("FusionEngine")
+        if feature_dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("feature_dtype must be torch.float32 or torch.bfloat16")
+        if feature_dtype == torch.bfloat16 and precision != "bf16":
+            raise N.MsfError("bf16 features need the tensor-core path (precision='bf16')")
+        self.feature_dtype = feature_dtype
         self.arena_bf16 = None
         self.model = model.to(self.dev)
         self.plan = model._plan()
@@ -102,7 +110,7 @@ class FusionEngine:
         # static I/O buffers (graph inputs / outputs).  Two input slots: the host-facing stream API
         # (train_stream) copies batch i+1 into one slot on a copy stream while the graph captured over the
         # other slot computes batch i; the resident API uses slot 0 only.
-        self._slots = [([torch.zeros(B, d, **f32) for d in plan.dims], torch.ones(B, plan.M, **f32),
+        self._slots = [([torch.zeros(B, d, dtype=feature_dtype, device=dev) for d in plan.dims], torch.ones(B, plan.M, **f32),
                         torch.zeros(B, dtype=torch.int64, device=dev)) for _ in range(2)]
         self.x, self.mask, self.labels = self._slots[0]
         self.logits = torch.zeros(B, plan.C, **f32)
@@ -364,7 +372,8 @@ class FusionEngine:
         batch from pinned_batch() and a train_stream input slot are then adjacent on both sides and load_batch
         sends the whole batch as a single transfer."""
         B, plan = self.batch, self.plan
-        sizes = [B * d * 4 for d in plan.dims] + [B * plan.M * 4, B * 8]
+        fsz = 2 if self.feature_dtype == torch.bfloat16 else 4
+        sizes = [B * d * fsz for d in plan.dims] + [B * plan.M * 4, B * 8]
         if any(sz % 16 for sz in sizes[:-1]):
             return None   # a tensor would start off a 16-byte boundary (bulk copies, int64 labels): separate buffers
         total = sum(sizes)
@@ -374,7 +383,7 @@ class FusionEngine:
         for sz in sizes:
             parts.append(buf[off:off + sz])
             off += sz
-        feats = [p.view(torch.float32).view(B, d) for p, d in zip(parts, plan.dims)]
+        feats = [p.view(self.feature_dtype).view(B, d) for p, d in zip(parts, plan.dims)]
         mask = parts[-2].view(torch.float32).view(B, plan.M)
         labels = parts[-1].view(torch.int64)
         mask.fill_(1.0)
@@ -390,7 +399,7 @@ class FusionEngine:
         got = self._one_buffer_batch(host=True)
         if got is None:
             B, plan = self.batch, self.plan
-            got = ([torch.zeros(B, d).pin_memory() for d in plan.dims], torch.ones(B, plan.M).pin_memory(),
+            got = ([torch.zeros(B, d, dtype=self.feature_dtype).pin_memory() for d in plan.dims], torch.ones(B, plan.M).pin_memory(),
                    torch.zeros(B, dtype=torch.int64).pin_memory())
         return got
 
@@ -414,8 +423,11 @@ class FusionEngine:
             # one library call issues all the asynchronous copies (no per-tensor dispatch on the host)
             import ctypes
             triples = [(dst.data_ptr(), src.data_ptr(), src.numel() * src.element_size()) for dst, src in pairs]
-            if self._packed_slots:
-                # pinned_batch() source and a one-buffer slot: runs adjacent on both sides go out as one transfer
+            one_alloc = lambda ts: len({t.untyped_storage().data_ptr() for t in ts}) == 1   # noqa: E731
+            if self._packed_slots and one_alloc([d for d, _ in pairs]) and one_alloc([s_ for _, s_ in pairs]):
+                # pinned_batch() source and a one-buffer slot (views of ONE allocation on each side — tensors of
+                # separate allocations that merely sit next to each other must not be merged): runs adjacent on both
+                # sides go out as one transfer
                 merged = [triples[0]]
                 for d, s_, sz in triples[1:]:
                     d0, s0, sz0 = merged[-1]
@@ -450,8 +462,11 @@ class FusionEngine:
         B = self.batch
         xs = []
         for f, d in zip(feats, self.plan.dims):
-            if f.device != self.dev or f.dtype != torch.float32 or tuple(f.shape) != (B, d) or not f.is_contiguous():
-                raise ValueError("resident features must be contiguous fp32 (batch, in_dim) tensors on the engine's device")
+            ok_dtype = f.dtype == feats[0].dtype and (f.dtype == torch.float32 or (
+                f.dtype == torch.bfloat16 and self.prec == N.MSF_PREC_BF16))
+            if f.device != self.dev or not ok_dtype or tuple(f.shape) != (B, d) or not f.is_contiguous():
+                raise ValueError("resident features must be contiguous fp32 (or, on the tensor-core path, bf16) "
+                                 "(batch, in_dim) tensors on the engine's device, all of one dtype")
             xs.append(f)
         msk = torch.ones(B, self.plan.M, dtype=torch.float32, device=self.dev) if mask is None else mask
         if msk.device != self.dev or msk.dtype != torch.float32 or tuple(msk.shape) != (B, self.plan.M) \
@@ -533,7 +548,8 @@ class FusionEngine:
             self._stream_slots = []
             for s in range(2):
                 self._slots.append((self._one_buffer_batch(host=False) if self._packed_slots else None)
-                                   or ([torch.zeros(self.batch, d, **f32) for d in self.plan.dims],
+                                   or ([torch.zeros(self.batch, d, dtype=self.feature_dtype, device=dev)
+                                        for d in self.plan.dims],
                                        torch.ones(self.batch, self.plan.M, **f32),
                                        torch.zeros(self.batch, dtype=torch.int64, device=dev)))
                 self._train_graphs.append(None)
@@ -561,8 +577,9 @@ class FusionEngine:
                                [(t.dtype, t.numel()) for t in tens]))
         one_dst, one_size = (ctypes.c_void_p * 1)(), (ctypes.c_size_t * 1)()
 
-        def adjacent(tens):   # laid out back to back in this order (pinned_batch / one-buffer slots)
-            return all(b.data_ptr() == a.data_ptr() + a.numel() * a.element_size() for a, b in zip(tens, tens[1:]))
+        def adjacent(tens):   # views of one allocation laid out back to back in this order (pinned_batch / one-buffer slots)
+            return (len({t.untyped_storage().data_ptr() for t in tens}) == 1 and
+                    all(b.data_ptr() == a.data_ptr() + a.numel() * a.element_size() for a, b in zip(tens, tens[1:])))
 
         slot_adjacent = [self._packed_slots and adjacent(list(self._slots[s][0]) + list(self._slots[s][1:]))
                          for s in self._stream_slots]

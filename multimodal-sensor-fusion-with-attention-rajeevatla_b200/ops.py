@@ -175,6 +175,11 @@ def _make_call(plan: FusionPlan, batch: int, precision: int, training: bool, p: 
     c.params, c.params_bf16 = _p(arena), _p(arena_bf16)
     for i, x in enumerate(xs):
         c.x[i] = _p(x)
+    kinds = {x.dtype for x in xs}
+    if kinds == {torch.bfloat16}:
+        c.x_bf16 = 1      # features stored as bf16 rows (msf_fusion_call.x_bf16)
+    elif kinds != {torch.float32}:
+        raise N.MsfError(f"features must be all float32 or all bfloat16, got {sorted(str(k) for k in kinds)}")
     c.mask = _p(mask)
     c.workspace, c.workspace_bytes = _p(ws), ws.numel()
     return c

@@ -24,8 +24,9 @@ lib = pkg.lib()
 lib.msf_debug_timeline.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int]
 lib.msf_debug_timeline.restype = ctypes.c_int
 buf = ctypes.create_string_buffer(1 << 18)
-CH = "chain2_gemm.cu" if os.environ.get("MSF_CHAIN") == "v2" else "chain3_gemm.cu"
-ORDER = ["proj_gemm.cu#0", CH + "#0", "head_gemm.cu#0", "fusion_bf16.cu#0", CH + "#1", "fusion_bf16.cu#1", "tc_gemm.cu#1",
+CH = "chain3_gemm.cu" if os.environ.get("MSF_CHAIN") == "v3" else "chain2_gemm.cu"
+WG = "tc_gemm.cu#1" if os.environ.get("MSF_WG") == "v1" else "wg2_gemm.cu#0"
+ORDER = ["proj_gemm.cu#0", CH + "#0", "head_gemm.cu#0", "fusion_bf16.cu#0", CH + "#1", "fusion_bf16.cu#1", WG,
          "opt_pack.cu#0"]
 for rep in range(3):
     N.check(lib.msf_debug_timeline(buf, len(buf), 1))   # clear
@@ -55,7 +56,7 @@ for rep in range(3):
             print(f"{'':20s}      marks: {us(k6):7.1f} {us(k7):7.1f}")
         if not name.startswith("fusion_bf16.cu"):
             prev_end = us(d1)
-    if rep == 2:   # per-CTA end times of the last step: block index (SM id) in order of completion
+    if rep == 2 and os.environ.get("MSF_TL_CTAS"):   # per-CTA end times of the last step: block index (SM id) in order of completion
         for name in ORDER:
             if name in ctas:
                 order = sorted(range(len(ctas[name])), key=lambda b: ctas[name][b][0])

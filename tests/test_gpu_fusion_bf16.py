@@ -372,3 +372,84 @@ def test_pinned_batch_crosses_as_one_transfer_and_trains_the_same():
         assert abs(a - b) <= 1e-3 * abs(a), out
     diff = (out["separate"][1] - out["packed"][1]).abs()
     assert float(diff.max()) <= 1.01e-2 and float(diff.mean()) <= 1e-4   # as test_train_stream_pipeline_equals_step_by_step
+
+
+@pytest.mark.parametrize("batch", [300, 4096])
+def test_bf16_features_equal_fp32_features_of_the_same_values(batch):
+    """msf_fusion_call.x_bf16: features stored as bf16 rows give bit-identical logits and weight gradients to fp32
+    rows holding the same (bf16-representable) values — the projection kernel only changes how it reads them —
+    and stay within the bf16 tolerance of the oracle on the un-rounded features."""
+    pkg, ops = load_pkg(), _ops()
+    N = pkg.native
+    model, feats, mask, labels = seeded_case(PAMAP2, 256, 4, 25, batch, seed=91, device="cuda")
+    plan = model._plan()
+    own = dict(model.named_parameters())
+    arena = plan.gather([own[k].detach() for k, _, _ in plan.slots])
+    a16 = plan.pack_bf16(arena)
+    x16 = [feats[m].to(torch.bfloat16).contiguous() for m in plan.names]
+    x32 = [x.float().contiguous() for x in x16]
+    kw = dict(smoothing=0.05, precision=N.MSF_PREC_BF16, training=True, p=0.1, seed=11, arena_bf16=a16)
+    got = {}
+    for name, xs in (("bf16", x16), ("fp32", x32)):
+        logits, loss, grad, fw, gates = ops.fusion_train_pass_raw(plan, arena, xs, mask, labels, **kw)
+        got[name] = (logits.clone(), float(loss), grad.clone(), fw.clone())
+    assert torch.equal(got["bf16"][0], got["fp32"][0])
+    assert torch.equal(got["bf16"][3], got["fp32"][3])
+    # weight-gradient GEMMs and their split halves are bit-reproducible; bias column sums are fp32 atomics
+    assert _maxabs(got["bf16"][2], got["fp32"][2]) <= 1e-5
+    # eval mode against the oracle on the ORIGINAL fp32 features: the extra input rounding stays inside 1e-2
+    logits_eval, _, _, _ = ops.fusion_forward_raw(plan, arena, x16, mask, precision=N.MSF_PREC_BF16, arena_bf16=a16)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    ref, _ = fusion_oracle.hybrid_fusion_forward(sd, list(PAMAP2), 4, {k: v.cpu() for k, v in feats.items()}, mask.cpu())
+    assert _maxabs(logits_eval, ref) <= TOL
+
+
+def test_bf16_features_are_refused_off_the_fused_projection_kernel():
+    pkg, ops = load_pkg(), _ops()
+    N = pkg.native
+    model, feats, mask, labels = seeded_case(PAMAP2, 256, 4, 25, 64, seed=92, device="cuda")
+    plan = model._plan()
+    own = dict(model.named_parameters())
+    arena = plan.gather([own[k].detach() for k, _, _ in plan.slots])
+    x16 = [feats[m].to(torch.bfloat16).contiguous() for m in plan.names]
+    with pytest.raises(pkg.MsfError):     # fp32 parity path reads fp32 features
+        ops.fusion_forward_raw(plan, arena, x16, mask, precision=N.MSF_PREC_F32)
+    mixed = [x16[0]] + [feats[m].contiguous() for m in plan.names[1:]]
+    with pytest.raises(pkg.MsfError):     # one dtype for all modalities
+        ops.fusion_forward_raw(plan, arena, mixed, mask, precision=N.MSF_PREC_BF16, arena_bf16=plan.pack_bf16(arena))
+
+
+def test_engine_streams_bf16_host_batches():
+    """FusionEngine(feature_dtype=bfloat16): pinned bf16 host batches (half the PCIe bytes) through train_stream follow
+    an fp32-feature engine fed the same rounded values; resident fp32 batches still train on the same engine."""
+    pkg = load_pkg()
+    engine = importlib.import_module(pkg.__name__ + ".engine")
+    raw = [seeded_case(PAMAP2, 256, 4, 25, 512, seed=60 + i, device="cpu")[1:] for i in range(5)]
+    out = {}
+    for mode in ("fp32", "bf16", "bf16-packed"):
+        model, *_ = seeded_case(PAMAP2, 256, 4, 25, 512, seed=21, device="cuda")
+        fd = torch.float32 if mode == "fp32" else torch.bfloat16
+        eng = engine.FusionEngine(model, 512, precision="bf16", seed=5, use_graph=True, feature_dtype=fd)
+        batches, moved = [], 0
+        for feats, mask, labels in raw:
+            f16 = [f.to(torch.bfloat16) for f in feats.values()]
+            if mode == "bf16-packed":
+                pf, pm, py = eng.pinned_batch()
+                assert pf[0].dtype == torch.bfloat16 and pf[1].data_ptr() == pf[0].data_ptr() + pf[0].numel() * 2
+                for dst, src in zip(pf + [pm, py], f16 + [mask, labels]):
+                    dst.copy_(src)
+                batches.append((pf, pm, py))
+            else:
+                fs = [(f if mode == "bf16" else f.float()).pin_memory() for f in f16]
+                batches.append((fs, mask.pin_memory(), labels.pin_memory()))
+            moved = sum(t.numel() * t.element_size() for t in batches[-1][0])
+        out[mode] = (list(eng.train_stream(iter(batches))), eng.arena.clone(), moved)
+        if mode == "bf16":   # a resident fp32 batch on the same engine
+            slot = eng.add_resident_batch([f.cuda() for f in raw[0][0].values()], raw[0][1].cuda(), raw[0][2].cuda())
+            assert torch.isfinite(eng.train_step_slot(slot)).all()
+    assert out["bf16"][2] * 2 == out["fp32"][2]
+    for mode in ("bf16", "bf16-packed"):
+        for a, b in zip(out["fp32"][0], out[mode][0]):
+            assert abs(a - b) <= 1e-3 * abs(a), out
+        diff = (out["fp32"][1] - out[mode][1]).abs()
+        assert float(diff.max()) <= 1.01e-2 and float(diff.mean()) <= 1e-4   # as test_train_stream_pipeline_equals_step_by_step

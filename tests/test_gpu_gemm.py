@@ -49,6 +49,9 @@ def test_k_major_matches_fp32_reference(m, n, k, out):
 MN_MAJOR = [  # k (contraction = windows), m, n
     (64, 64, 64), (4096, 256, 256), (4096, 256, 128), (1000, 256, 256), (4096, 32, 256), (333, 128, 64),
     (8192, 256, 128),
+    # CTA-pair kernel (wg2_gemm.cu, n % 128 == 0): several 256 x 256 tiles, ragged m, a 128-wide last column tile,
+    # contraction of 3 / 1 k-blocks (uneven halves / no split)
+    (4096, 512, 512), (4096, 704, 384), (130, 256, 128), (64, 256, 256), (2048, 25, 256),
 ]
 
 
@@ -61,6 +64,15 @@ def test_mn_major_matches_fp32_reference(k, m, n):
     got = ops.gemm_bf16(a, b, mn_major=True)
     assert got.shape == (m, n)
     assert float((got - ref).abs().max()) <= 2e-4 * k ** 0.5 * max(1.0, float(ref.abs().max()) / 64)
+
+
+def test_split_contraction_is_bit_reproducible():
+    """The two halves of a split contraction meet in the destination in either order (wg2_gemm.cu): same bits every run."""
+    ops = _ops()
+    a, b = _rand((4096, 256), 6), _rand((4096, 256), 7)
+    first = ops.gemm_bf16(a, b, mn_major=True).clone()
+    for _ in range(20):
+        assert torch.equal(ops.gemm_bf16(a, b, mn_major=True), first)
 
 
 def test_rejects_misaligned_operands():
