@@ -298,7 +298,7 @@ int msf_dp_optimizer_step_packed(const msf_fusion_shape* shape, const msf_dp_com
  * units (32 x 32 tiles of the weight matrices, 1024-element pieces of the vectors); live unit u belongs to rank
  * u % world.  Two kernels over NVLink peer memory:
  *   (1) every rank pushes its gradient values of the units it does not own into the owner's staging arena
- *       (stages[owner] + rank * total + arena offset); after a cross-GPU flag barrier each owner sums its units over
+ *       (stages[owner] + rank * stride + arena offset, stride = total rounded up to a multiple of 4 floats); after a cross-GPU flag barrier each owner sums its units over
  *       the ranks in fixed rank order, IN PLACE in `grad`, and publishes their square norm;
  *   (2) after the norm barrier each owner applies clip + AdamW to its units (master weights and Adam moments of a
  *       unit live on its owner only), pushes the bf16 copy and transposed copy of every updated weight tile into
@@ -312,7 +312,7 @@ int msf_dp_optimizer_step_packed(const msf_fusion_shape* shape, const msf_dp_com
  * -1 for replicated elements, -2 - rank for vector slots (moments on the owner, value valid everywhere). */
 typedef struct msf_dpz_comm {
   int32_t rank, world;
-  float* stages[MSF_DP_MAX_RANKS];       /* world x total floats each */
+  float* stages[MSF_DP_MAX_RANKS];       /* world x ((total + 3) / 4 * 4) floats each */
   void* arenas_bf16[MSF_DP_MAX_RANKS];   /* compute arenas (msf_fusion_pack_bf16 layout) */
   float* params[MSF_DP_MAX_RANKS];       /* master arenas */
   uint64_t* sigs[MSF_DP_MAX_RANKS];      /* 64 x uint64 signal blocks, zero-initialised */

@@ -54,7 +54,7 @@ struct ZCfg {
                                    // to every rank, the forward kernels read them from the fp32 master
   float* stages[8];                // peer-mapped staging arenas: world x total floats, [contributor][arena offset]
   unsigned long long* sigs[8];     // peer-mapped signal blocks
-  long long total;                 // master-arena elements
+  long long total;                 // stride of a staging arena's per-contributor slices: master-arena elements rounded up to 4
 };
 
 template <bool DP>
@@ -597,7 +597,8 @@ int fusion_bf16_opt_pack_dpz(const Layout& L, const msf_dpz_comm* comm, float* p
   if (rc) return rc;
   ZCfg z;
   memset(&z, 0, sizeof(z));
-  z.rank = comm->rank; z.world = comm->world; z.total = L.total;
+  z.rank = comm->rank; z.world = comm->world;
+  z.total = (L.total + 3) & ~3ll;   // stride between the contributors' slices of a staging arena: keeps float4 groups aligned
   for (int r = 0; r < comm->world; ++r) {
     MSF_REQUIRE(comm->stages[r] && comm->arenas_bf16[r] && comm->params[r] && comm->sigs[r],
                 "msf_dpz_optimizer_step_packed: null peer pointer (rank %d)", r);

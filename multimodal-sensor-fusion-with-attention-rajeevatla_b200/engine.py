@@ -284,7 +284,7 @@ class FusionEngine:
         packed = plan.pack_bf16(arena)
         arena16 = symm_mem.empty(packed.numel(), dtype=packed.dtype, device=self.dev)
         arena16.copy_(packed)
-        self.zstage = symm_mem.empty(n * self.world, dtype=torch.float32, device=self.dev)
+        self.zstage = symm_mem.empty((n + 3) // 4 * 4 * self.world, dtype=torch.float32, device=self.dev)   # slices 16-byte aligned
         self.sig = symm_mem.empty(64, dtype=torch.int64, device=self.dev)
         handles = [symm_mem.rendezvous(t, group) for t in (arena, arena16, self.zstage, self.sig)]
         self.zstage.zero_()
