@@ -316,6 +316,14 @@ typedef struct msf_dpz_comm {
   void* arenas_bf16[MSF_DP_MAX_RANKS];   /* compute arenas (msf_fusion_pack_bf16 layout) */
   float* params[MSF_DP_MAX_RANKS];       /* master arenas */
   uint64_t* sigs[MSF_DP_MAX_RANKS];      /* 64 x uint64 signal blocks, zero-initialised */
+  /* Optional NVLink multicast (NVLS) addresses, all three or none: the address that stands for the same offset in
+   * EVERY rank's gradient arena (`grad` of each rank's call must be its own window of it), compute arena and master
+   * arena.  With them the owner of a unit reads its gradient already summed over the ranks by the switch
+   * (multimem.ld_reduce: nothing is pushed into `stages`, which may then be NULL) and delivers every updated
+   * weight to all ranks with one multimem.st instead of one store per rank. */
+  const float* mc_grad;
+  void* mc_arena_bf16;
+  float* mc_params;
 } msf_dpz_comm;
 int msf_dpz_optimizer_step_packed(const msf_fusion_shape* shape, const msf_dpz_comm* comm, float* params, float* grad,
                                   float* exp_avg, float* exp_avg_sq, uint64_t* train_state, float lr, float beta1,

@@ -80,6 +80,9 @@ class DpzComm(Structure):  # msf_dpz_comm
         ("arenas_bf16", c_void_p * 8),
         ("params", c_void_p * 8),
         ("sigs", c_void_p * 8),
+        ("mc_grad", c_void_p),
+        ("mc_arena_bf16", c_void_p),
+        ("mc_params", c_void_p),
     ]
 
 

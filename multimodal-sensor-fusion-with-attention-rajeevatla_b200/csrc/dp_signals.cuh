@@ -44,6 +44,26 @@ __device__ __forceinline__ float ld_peer1(const float* p) {
   return v;
 }
 
+// NVLink multicast (NVLS): one address that stands for the same offset in every rank's buffer.  A load-reduce is
+// answered by the switch with the sum over the ranks' copies; a store is delivered to every rank's copy.
+__device__ __forceinline__ float4 mm_ld_reduce4(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ float mm_ld_reduce1(const float* mc) {
+  float v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(v) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ void mm_st_f32(float* mc, float v) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc), "f"(v) : "memory");
+}
+__device__ __forceinline__ void mm_st_bf16x4(void* mc, uint2 v) {   // 4 bf16 = 8 bytes
+  asm volatile("multimem.st.relaxed.sys.global.v2.bf16x2 [%0], {%1, %2};" ::"l"(mc), "r"(v.x), "r"(v.y) : "memory");
+}
+
 // every thread of the block returns once all ranks have published `epoch` in words [base, base + world)
 __device__ __forceinline__ void wait_all(const unsigned long long* sig, int base, int world, unsigned long long epoch) {
   if ((int)threadIdx.x < world) {

@@ -54,6 +54,11 @@ struct ZCfg {
                                    // to every rank, the forward kernels read them from the fp32 master
   float* stages[8];                // peer-mapped staging arenas: world x total floats, [contributor][arena offset]
   unsigned long long* sigs[8];     // peer-mapped signal blocks
+  // optional NVLink multicast addresses of the ranks' gradient / compute / master arenas (all three or none): the
+  // owner then reads a unit's gradient summed by the switch (no staging pushes) and stores updated weights once
+  const float* mc_grad;
+  bf16* mc_arena;
+  float* mc_params;
   long long total;                 // stride of a staging arena's per-contributor slices: master-arena elements rounded up to 4
 };
 
@@ -227,8 +232,10 @@ __global__ void __launch_bounds__(256, 4) opt_pack_kernel(const __grid_constant_
           __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
           h[0] = __floats2bfloat162_rn(x.x, x.y);
           h[1] = __floats2bfloat162_rn(x.z, x.w);
-          for (int d = 0; d < ndst; ++d)
-            *reinterpret_cast<uint2*>((Z ? z.arenas[d] : arena) + dst_off + (long long)r * J.dst_ld + cc) = pk;
+          if (Z && z.mc_arena != nullptr) mm_st_bf16x4(z.mc_arena + dst_off + (long long)r * J.dst_ld + cc, pk);
+          else
+            for (int d = 0; d < ndst; ++d)
+              *reinterpret_cast<uint2*>((Z ? z.arenas[d] : arena) + dst_off + (long long)r * J.dst_ld + cc) = pk;
         }
         const int lr = threadIdx.x >> 3, lc = (threadIdx.x & 7) * 4;
         tile[lr][lc] = x.x; tile[lr][lc + 1] = x.y; tile[lr][lc + 2] = x.z; tile[lr][lc + 3] = x.w;
@@ -241,8 +248,10 @@ __global__ void __launch_bounds__(256, 4) opt_pack_kernel(const __grid_constant_
             __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
             h[0] = __floats2bfloat162_rn(tile[sr][sc], tile[sr + 1][sc]);
             h[1] = __floats2bfloat162_rn(tile[sr + 2][sc], tile[sr + 3][sc]);
-            for (int d = 0; d < ndst; ++d)
-              *reinterpret_cast<uint2*>((Z ? z.arenas[d] : arena) + dstT_off + (long long)tcn * J.dstT_ld + tr) = pk;
+            if (Z && z.mc_arena != nullptr) mm_st_bf16x4(z.mc_arena + dstT_off + (long long)tcn * J.dstT_ld + tr, pk);
+            else
+              for (int d = 0; d < ndst; ++d)
+                *reinterpret_cast<uint2*>((Z ? z.arenas[d] : arena) + dstT_off + (long long)tcn * J.dstT_ld + tr) = pk;
           }
         }
         __syncthreads();
@@ -278,7 +287,9 @@ __global__ void __launch_bounds__(256, 4) opt_pack_kernel(const __grid_constant_
         float mm = m[ee], vv = v[ee];
         const float x = adam_elem(k, ld_grad<DP>(g + ee), mm, vv, p[ee]);
         m[ee] = mm; v[ee] = vv;
-        if (Z) {
+        if (Z && z.mc_params != nullptr) {
+          mm_st_f32(z.mc_params + ee, x);
+        } else if (Z) {
           for (int d = 0; d < ndst; ++d) z.params[d][ee] = x;   // every rank's forward reads these from the master
         } else {
           p[ee] = x;
@@ -303,10 +314,14 @@ __global__ void __launch_bounds__(256, 4) opt_pack_kernel(const __grid_constant_
   // the last CTA to finish publishes the norm, resets the launch-scoped globals and moves the train state on
   {
     __shared__ bool last;
-    if (Z) __threadfence_system();   // this block's pushed bf16 weights are visible system-wide before it reports in
-    else __threadfence();
+    // one fence per block, by the thread that reports in, after the block barrier (fences are cumulative: the
+    // other threads' writes are ordered before it through the barrier)
     __syncthreads();
-    if (threadIdx.x == 0) last = (atomicAdd(&g_opt_ticket, 1u) == gridDim.x - 1);
+    if (threadIdx.x == 0) {
+      if (Z) __threadfence_system();   // this block's pushed bf16 weights are visible system-wide before it reports in
+      else __threadfence();
+      last = (atomicAdd(&g_opt_ticket, 1u) == gridDim.x - 1);
+    }
     __syncthreads();
     if (Z && last) {   // "my share of the compute arena has landed everywhere", then wait for everybody else's
       if ((int)threadIdx.x < z.world) {
@@ -391,7 +406,7 @@ __global__ void __launch_bounds__(256, 4) dpz_reduce_kernel(const __grid_constan
   };
 
   // ---- phase 1: my values of the units other ranks own -> their staging arenas ----
-  for (int unit = blockIdx.x; unit < list.live_units; unit += gridDim.x) {
+  for (int unit = blockIdx.x; z.mc_grad == nullptr && unit < list.live_units; unit += gridDim.x) {
     const int owner = unit % z.world;
     if (owner == z.rank) continue;
     int local;
@@ -426,16 +441,22 @@ __global__ void __launch_bounds__(256, 4) dpz_reduce_kernel(const __grid_constan
     unit_elems(J, local, base, [&](long long e, int w) {
       if (w == 4) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int pr = 0; pr < z.world; ++pr) {
-          const float4 gg = (pr == z.rank) ? *reinterpret_cast<const float4*>(grad + e)
-                                           : ld_peer4(stage + (long long)pr * z.total + e);
-          acc.x += gg.x; acc.y += gg.y; acc.z += gg.z; acc.w += gg.w;
+        if (z.mc_grad != nullptr) {
+          acc = mm_ld_reduce4(z.mc_grad + e);   // summed over the ranks' arenas by the switch
+        } else {
+          for (int pr = 0; pr < z.world; ++pr) {
+            const float4 gg = (pr == z.rank) ? *reinterpret_cast<const float4*>(grad + e)
+                                             : ld_peer4(stage + (long long)pr * z.total + e);
+            acc.x += gg.x; acc.y += gg.y; acc.z += gg.z; acc.w += gg.w;
+          }
         }
         *reinterpret_cast<float4*>(grad + e) = acc;
         sq += (double)acc.x * acc.x + (double)acc.y * acc.y + (double)acc.z * acc.z + (double)acc.w * acc.w;
       } else {
         float acc = 0.0f;
-        for (int pr = 0; pr < z.world; ++pr) acc += (pr == z.rank) ? grad[e] : ld_peer1(stage + (long long)pr * z.total + e);
+        if (z.mc_grad != nullptr) acc = mm_ld_reduce1(z.mc_grad + e);
+        else
+          for (int pr = 0; pr < z.world; ++pr) acc += (pr == z.rank) ? grad[e] : ld_peer1(stage + (long long)pr * z.total + e);
         grad[e] = acc;
         sq += (double)acc * acc;
       }
@@ -600,7 +621,7 @@ int fusion_bf16_opt_pack_dpz(const Layout& L, const msf_dpz_comm* comm, float* p
   z.rank = comm->rank; z.world = comm->world;
   z.total = (L.total + 3) & ~3ll;   // stride between the contributors' slices of a staging arena: keeps float4 groups aligned
   for (int r = 0; r < comm->world; ++r) {
-    MSF_REQUIRE(comm->stages[r] && comm->arenas_bf16[r] && comm->params[r] && comm->sigs[r],
+    MSF_REQUIRE((comm->stages[r] || comm->mc_grad) && comm->arenas_bf16[r] && comm->params[r] && comm->sigs[r],
                 "msf_dpz_optimizer_step_packed: null peer pointer (rank %d)", r);
     z.stages[r] = comm->stages[r];
     z.arenas[r] = reinterpret_cast<bf16*>(comm->arenas_bf16[r]);
@@ -608,6 +629,11 @@ int fusion_bf16_opt_pack_dpz(const Layout& L, const msf_dpz_comm* comm, float* p
     z.sigs[r] = reinterpret_cast<unsigned long long*>(comm->sigs[r]);
   }
   MSF_REQUIRE(params == comm->params[comm->rank], "msf_dpz_optimizer_step_packed: params must be this rank's entry of comm->params");
+  const int n_mc = (comm->mc_grad != nullptr) + (comm->mc_arena_bf16 != nullptr) + (comm->mc_params != nullptr);
+  MSF_REQUIRE(n_mc == 0 || n_mc == 3, "msf_dpz_optimizer_step_packed: give all three multicast addresses or none");
+  z.mc_grad = comm->mc_grad;
+  z.mc_arena = reinterpret_cast<bf16*>(comm->mc_arena_bf16);
+  z.mc_params = comm->mc_params;
   // Every block waits inside the kernels for the peers' flags, which depend on ALL blocks of every rank: both
   // grids must be co-resident (occupancy 4 x SMs of 256 threads) or the ranks deadlock.
   static int resident = -1;

@@ -282,10 +282,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG2_THREADS, 1)
       __syncwarp();
       if (lane == 0) wg2_arrive_leader(acc_empty);
       if (active) {
-        if (sender) {          // publish the partial sums
-          __threadfence();
-          __syncwarp();
-          if (lane == 0) atomicExch(flag, 1u);
+        if (sender) {          // publish the partial sums: one fence, by the signalling lane, after the warp barrier
+          __syncwarp();        // (fences are cumulative; a fence per lane is a MEMBAR per warp for nothing)
+          if (lane == 0) {
+            __threadfence();
+            atomicExch(flag, 1u);
+          }
         } else {
           if (combine && lane == 0) *flag = 0u;   // ready for the next launch
           if (sqp != nullptr) {

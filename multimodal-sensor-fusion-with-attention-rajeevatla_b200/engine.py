@@ -286,14 +286,16 @@ class FusionEngine:
         arena16.copy_(packed)
         self.zstage = symm_mem.empty((n + 3) // 4 * 4 * self.world, dtype=torch.float32, device=self.dev)   # slices 16-byte aligned
         self.sig = symm_mem.empty(64, dtype=torch.int64, device=self.dev)
-        handles = [symm_mem.rendezvous(t, group) for t in (arena, arena16, self.zstage, self.sig)]
+        grad = symm_mem.empty(n, dtype=torch.float32, device=self.dev)
+        handles = [symm_mem.rendezvous(t, group) for t in (arena, arena16, self.zstage, self.sig, grad)]
         self.zstage.zero_()
         self.sig.zero_()
+        grad.zero_()
         own = dict(self.model.named_parameters())
         with torch.no_grad():
             for key, off, shape in plan.slots:
                 own[key].data = arena[off:off + own[key].numel()].view(shape)
-        self.arena, self.arena_bf16 = arena, arena16
+        self.arena, self.arena_bf16, self.grad = arena, arena16, grad
         torch.cuda.synchronize(self.dev)
         dist.barrier(group)  # nobody signals into a block that is not zeroed yet
         comm = N.DpzComm()
@@ -303,6 +305,19 @@ class FusionEngine:
             comm.arenas_bf16[r] = int(handles[1].buffer_ptrs[r])
             comm.stages[r] = int(handles[2].buffer_ptrs[r])
             comm.sigs[r] = int(handles[3].buffer_ptrs[r])
+        # NVLink multicast (NVLS) windows of the gradient / compute / master arenas, opt-in (MSF_DP_MULTICAST=1): the
+        # owner of a unit reads its gradient summed by the switch and stores every updated weight once for all ranks.
+        # Measured: 194 vs 186 us/step at 2 GPUs, 200 vs 203 at 8 — the push path stays the default (fixed-order sums)
+        import os
+        mc = [int(getattr(handles[i], "multicast_ptr", 0) or 0) for i in (4, 1, 0)]
+        local_ok = all(int(handles[i].buffer_ptrs[comm.rank]) == t.data_ptr()
+                       for i, t in ((4, grad), (1, arena16), (0, arena)))
+        self.multicast = all(mc) and local_ok and os.environ.get("MSF_DP_MULTICAST", "0") == "1"
+        flag = torch.tensor([int(self.multicast)], device=self.dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)   # every rank takes the same path
+        self.multicast = bool(int(flag.item()))
+        if self.multicast:
+            comm.mc_grad, comm.mc_arena_bf16, comm.mc_params = mc
         self._symm_handles = handles
         self.dp_comm = comm
         owner = torch.empty(n, dtype=torch.int8)
