@@ -616,7 +616,12 @@ static int colsum16_launch(const Colsum16Problem* probs, int count, cudaStream_t
       memset(&cfg, 0, sizeof(cfg));
       cfg.gridDim = dim3((unsigned)ceil_div(max_rows, rpb), (unsigned)n);
       cfg.blockDim = dim3(256);
-      cfg.dynamicSmemBytes = CS_PAD_BYTES;
+      // tag 0 runs beside the backward chain kernel (shared-memory bound: keep these blocks off its SMs with a
+      // shared-memory request that does not fit beside a chain CTA); tag 1 runs beside the weight-gradient CTA
+      // pairs, which wait on the L2 and leave their SMs' issue slots and shared-memory port idle: no padding, the
+      // blocks spread over all SMs (MSF_CS_PAD=1 pads both)
+      static const bool pad_all = getenv("MSF_CS_PAD") != nullptr;
+      cfg.dynamicSmemBytes = (tag == 0 || pad_all) ? CS_PAD_BYTES : 0;
       cfg.stream = st;
       cfg.attrs = &attr;
       cfg.numAttrs = 1;
