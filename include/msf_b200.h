@@ -386,6 +386,25 @@ typedef struct msf_lstm_seq {
 } msf_lstm_seq;
 int msf_lstm_forward(const msf_lstm_seq* seqs, int32_t n, int64_t batch, int32_t steps, int32_t hidden, void* stream);
 
+/* ---- BatchNorm1d -> ReLU -> Dropout behind a Linear layer (src/encoders.py:339-397, BatchNorm at :374-375) ----- */
+/* out = dropout(relu((y - mean) * invstd * gamma + beta)) over y (rows x cols, row-major fp32: the Linear output).
+ * training != 0: batch statistics (biased variance; fp64 column sums), running_mean / running_var moved on like
+ * nn.BatchNorm1d (momentum, unbiased variance; either may be NULL), Philox dropout keyed by `seed`;
+ * training == 0: the running statistics, no dropout.  gamma / beta may be NULL (affine=False), relu == 0 skips the
+ * ReLU.  save_mean / save_invstd (cols floats each) receive what the backward pass needs; scratch = 2 * cols
+ * doubles, ZERO on entry, zero again on return (reusable across calls on one stream).  rows == 1 in training mode
+ * is refused like PyTorch does. */
+int msf_bn_act_forward(const float* y, float* out, int64_t rows, int32_t cols, const float* gamma, const float* beta,
+                       float* running_mean, float* running_var, float momentum, float eps, int32_t training,
+                       int32_t relu, float dropout_p, uint64_t seed, float* save_mean, float* save_invstd,
+                       double* scratch, void* stream);
+/* Gradients of the above: dy (rows x cols) with respect to the Linear output, dgamma / dbeta (cols, may be NULL).
+ * `out` is the forward result: the ReLU / dropout gate is recovered from out != 0. */
+int msf_bn_act_backward(const float* dout, const float* y, const float* out, int64_t rows, int32_t cols,
+                        const float* gamma, const float* save_mean, const float* save_invstd, int32_t training,
+                        int32_t relu, float dropout_p, float* dy, float* dgamma, float* dbeta, double* scratch,
+                        void* stream);
+
 /* ---- tensor-core GEMM building block (encoder/attention projections) ------ */
 /* bf16 operands, fp32 accumulate in TMEM via tcgen05.mma, operands staged by TMA
  * into 128B-swizzled shared memory; D is fp32 or bf16 row-major (ldd elements).

@@ -394,6 +394,50 @@ def layer_norm(x: torch.Tensor, weight: Optional[torch.Tensor] = None, bias: Opt
     return LayerNormFunction.apply(x, weight, bias, eps)
 
 
+class BatchNormActFunction(torch.autograd.Function):
+    """``dropout(relu(batch_norm(y)))`` behind a Linear layer on msf_bn_act_* (src/encoders.py:374-377)."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, running_mean, running_var, momentum, eps, training, relu, p, seed):
+        y = y.contiguous()
+        rows, cols = y.shape
+        out = torch.empty_like(y)
+        mean = torch.empty(cols, dtype=torch.float32, device=y.device)
+        invstd = torch.empty(cols, dtype=torch.float32, device=y.device)
+        scratch = torch.zeros(2 * cols, dtype=torch.float64, device=y.device)
+        N.check(N.lib().msf_bn_act_forward(_p(y), _p(out), rows, cols, _p(gamma), _p(beta), _p(running_mean),
+                                           _p(running_var), float(momentum), float(eps), int(training), int(relu),
+                                           float(p), seed & (2**64 - 1), _p(mean), _p(invstd), _p(scratch), _stream()))
+        ctx.save_for_backward(y, out, gamma, mean, invstd)
+        ctx.cfg = (int(training), int(relu), float(p), gamma is not None, beta is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        y, out, gamma, mean, invstd = ctx.saved_tensors
+        training, relu, p, has_g, has_b = ctx.cfg
+        rows, cols = y.shape
+        dy = torch.empty_like(y)
+        dg = torch.empty(cols, dtype=torch.float32, device=y.device) if has_g else None
+        db = torch.empty(cols, dtype=torch.float32, device=y.device) if has_b else None
+        scratch = torch.zeros(2 * cols, dtype=torch.float64, device=y.device)
+        N.check(N.lib().msf_bn_act_backward(_p(gout.to(torch.float32).contiguous()), _p(y), _p(out), rows, cols, _p(gamma),
+                                            _p(mean), _p(invstd), training, relu, p, _p(dy), _p(dg), _p(db), _p(scratch),
+                                            _stream()))
+        return dy, dg, db, None, None, None, None, None, None, None, None
+
+
+def batch_norm_act(y: torch.Tensor, weight, bias, running_mean, running_var, momentum: float, eps: float,
+                   use_batch_stats: bool, relu: bool = True, p: float = 0.0) -> torch.Tensor:
+    """``dropout_p(relu(batch_norm(y)))`` for a 2-D fp32 CUDA tensor through msf_bn_act_* (differentiable in ``y``,
+    ``weight``, ``bias``).  ``use_batch_stats``: normalise with the batch statistics and, if running tensors are
+    given, move them on (nn.BatchNorm1d training mode); otherwise normalise with the running statistics.  ``p`` > 0
+    draws a fresh Philox dropout mask (only with batch statistics, i.e. in training mode)."""
+    seed = int(torch.randint(0, 2**62, (1,)).item()) if (use_batch_stats and p > 0.0) else 0
+    return BatchNormActFunction.apply(y, weight, bias, running_mean, running_var, momentum, eps, use_batch_stats, relu,
+                                      p if use_batch_stats else 0.0, seed)
+
+
 def adaptive_weights(feats: Sequence[torch.Tensor], gate_w: Sequence[torch.Tensor],
                      gate_b: Sequence[torch.Tensor], mask: torch.Tensor) -> torch.Tensor:
     """HybridFusion.compute_adaptive_weights (src/fusion.py:429-479) on the tail kernel."""

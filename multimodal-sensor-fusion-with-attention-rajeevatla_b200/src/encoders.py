@@ -77,11 +77,52 @@ def _rnn_fp32(rnn: nn.Module, inp):
         return rnn(inp)
 
 
+def _bn_act(bn: nn.BatchNorm1d, y: torch.Tensor, relu: bool, drop: Optional[nn.Dropout]) -> torch.Tensor:
+    """``Dropout(ReLU(BatchNorm1d(y)))`` as one fused forward (and one fused backward) on msf_bn_act_*
+    (encoders.py:374-377 of the reference).  Statistics, running-average update and ``num_batches_tracked`` follow
+    nn.BatchNorm1d; under data parallelism they are per process, as in the reference (no SyncBatchNorm)."""
+    home, dtype = y.device, y.dtype
+    dev = home if home.type == "cuda" else ops.require_cuda("SimpleMLPEncoder batch norm")
+    put = lambda t: None if t is None else t.to(device=dev, dtype=torch.float32)  # noqa: E731
+    training = bn.training
+    use_batch = training or not bn.track_running_stats or bn.running_mean is None
+    momentum = bn.momentum
+    if training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+        if momentum is None:   # cumulative moving average
+            momentum = 1.0 / float(bn.num_batches_tracked)
+    momentum = 0.0 if momentum is None else float(momentum)
+    update = training and bn.track_running_stats and bn.running_mean is not None
+    rm = rv = None
+    if update or not use_batch:
+        rm, rv = put(bn.running_mean), put(bn.running_var)
+        if update and rm.data_ptr() != bn.running_mean.data_ptr():
+            rm, rv = rm.clone(), rv.clone()
+    p = float(drop.p) if (drop is not None and drop.training) else 0.0
+    with torch.cuda.device(dev):
+        out = ops.batch_norm_act(put(y), put(bn.weight), put(bn.bias), rm, rv, momentum, bn.eps, use_batch, relu, p)
+    if update and rm.data_ptr() != bn.running_mean.data_ptr():   # staged copies: hand the moved-on statistics back
+        with torch.no_grad():
+            bn.running_mean.copy_(rm)
+            bn.running_var.copy_(rv)
+    return out.to(device=home, dtype=dtype)
+
+
 def _run_sequential(seq: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
-    """An ``nn.Sequential`` with its Linear layers on the kernels; ``Linear -> ReLU`` pairs are fused."""
+    """An ``nn.Sequential`` with its Linear layers on the kernels; ``Linear -> ReLU`` pairs are fused, and
+    ``BatchNorm1d [-> ReLU] [-> Dropout]`` behind a Linear runs as one fused kernel sequence (_bn_act)."""
     mods = list(seq)
     i = 0
     while i < len(mods):
+        if isinstance(mods[i], nn.BatchNorm1d) and x.dim() == 2:
+            j = i + 1
+            relu = j < len(mods) and isinstance(mods[j], nn.ReLU)
+            j += 1 if relu else 0
+            drop = mods[j] if j < len(mods) and isinstance(mods[j], nn.Dropout) and not mods[j].inplace else None
+            j += 1 if drop is not None else 0
+            x = _bn_act(mods[i], x, relu, drop)
+            i = j
+            continue
         fuse = isinstance(mods[i], nn.Linear) and i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
         x = _dense(mods[i], x, relu=fuse)
         i += 2 if fuse else 1

@@ -393,6 +393,82 @@ def encoder_cases():
     _save("encoders_small.npz", payload)
 
 
+def frame_and_temporal_cases():
+    """FrameEncoder (all three poolings, frame masks incl. a fully masked clip) of src/encoders.py:211-336 and
+    TemporalAttention / PairwiseModalityAttention of src/attention.py:149-281,284-372 of the unmodified reference:
+    eval-mode outputs and dropout-free training gradients.  A file of its own (frame_temporal_small.npz) so the older
+    fixtures regenerate bit-identically."""
+    sys.path.insert(0, REF_SRC)
+    import attention as ref_att  # noqa
+    import encoders as ref_enc  # noqa
+    assert ref_enc.__file__.startswith(REF_SRC) and ref_att.__file__.startswith(REF_SRC)
+    sys.path.pop(0)
+    gen = torch.Generator().manual_seed(51)
+    payload = {}
+    B, T, F_in, H, D = 5, 9, 24, 32, 16
+    frames = torch.randn(B, T, F_in, generator=gen)
+    mask = torch.ones(B, T)
+    mask[1, 4:] = 0
+    mask[2, 0] = 0
+    mask[3, :] = 0          # a clip with no valid frame
+    payload["frame/x"], payload["frame/mask"] = _np(frames), _np(mask)
+    w = torch.linspace(-1, 1, D).unsqueeze(0)
+    for pool in ("attention", "average", "max"):
+        torch.manual_seed(52)
+        enc = ref_enc.FrameEncoder(F_in, hidden_dim=H, output_dim=D, temporal_pooling=pool, dropout=0.0)
+        enc.eval()
+        for k, v in enc.state_dict().items():
+            payload[f"frame/{pool}/sd/{k}"] = _np(v)
+        payload[f"frame/{pool}/out"] = _np(enc(frames))
+        payload[f"frame/{pool}/out_mask"] = _np(enc(frames, mask))
+        enc.train()
+        xg = frames.clone().requires_grad_(True)
+        (enc(xg, mask) * w).sum().backward()
+        payload[f"frame/{pool}/gradx"] = _np(xg.grad)
+        for k, prm in enc.named_parameters():
+            payload[f"frame/{pool}/grad/{k}"] = _np(prm.grad)
+    # TemporalAttention: self-attention over the time steps of one modality
+    torch.manual_seed(53)
+    ta = ref_att.TemporalAttention(F_in, hidden_dim=H, num_heads=4, dropout=0.0)
+    ta.eval()
+    for k, v in ta.state_dict().items():
+        payload[f"temporal/sd/{k}"] = _np(v)
+    tmask = mask.clone()
+    tmask[3, :2] = 1        # the reference's softmax over an all-masked row is NaN-cleaned; keep one such row out
+    payload["temporal/mask"] = _np(tmask)
+    out, wts = ta(frames)
+    payload["temporal/out"], payload["temporal/weights"] = _np(out), _np(wts)
+    out_m, wts_m = ta(frames, tmask)
+    payload["temporal/out_mask"], payload["temporal/weights_mask"] = _np(out_m), _np(wts_m)
+    payload["temporal/pooled"] = _np(ta.pool_sequence(frames, wts_m))
+    ta.train()
+    xg = frames.clone().requires_grad_(True)
+    o, _ = ta(xg, tmask)
+    (o * torch.linspace(-1, 1, H).view(1, 1, H)).sum().backward()
+    payload["temporal/gradx"] = _np(xg.grad)
+    for k, prm in ta.named_parameters():
+        payload[f"temporal/grad/{k}"] = _np(prm.grad)
+    # PairwiseModalityAttention over three modality embeddings
+    dims = {"video": 12, "imu": 20, "hr": 8}
+    torch.manual_seed(54)
+    pa = ref_att.PairwiseModalityAttention(dims, hidden_dim=H, num_heads=4, dropout=0.0)
+    pa.eval()
+    for k, v in pa.state_dict().items():
+        payload[f"pairwise/sd/{k}"] = _np(v)
+    feats = {m: torch.randn(B, d, generator=gen) for m, d in dims.items()}
+    mmask = torch.tensor([[1, 1, 1], [1, 0, 1], [0, 1, 1], [1, 1, 0], [1, 0, 0]], dtype=torch.float32)
+    for m, t in feats.items():
+        payload[f"pairwise/x/{m}"] = _np(t)
+    payload["pairwise/mask"] = _np(mmask)
+    got = pa(feats, mmask)
+    attended, maps = got if isinstance(got, tuple) else (got, {})
+    for m, t in attended.items():
+        payload[f"pairwise/out/{m}"] = _np(t)
+    for key, t in maps.items():
+        payload[f"pairwise/map/{key}"] = _np(t)
+    _save("frame_temporal_small.npz", payload)
+
+
 def main():
     ref_fusion, ref_attention, ref_uncertainty = _import_reference()
     # the reference's own test configuration (tests/test_fusion.py:50-80)
@@ -414,6 +490,7 @@ def main():
     ece_case(ref_uncertainty, "ece_seeded.npz", seed=1234, n=20000, classes=25)
     survey_kat(ref_uncertainty)
     encoder_cases()
+    frame_and_temporal_cases()
 
 
 if __name__ == "__main__":

@@ -103,3 +103,65 @@ def test_tensor_core_lstm_matches_oracle(batch, steps, feat, hidden):
     enc.precision = "fp32"
     with torch.no_grad():
         assert _maxabs(enc(x.cuda()), ref_out) <= 2e-4
+
+
+@pytest.mark.parametrize("pool", ["attention", "average", "max"])
+def test_frame_encoder_matches_reference_golden(pool):
+    """FrameEncoder (src/encoders.py:211-336) against the unmodified reference: all three temporal poolings, with and
+    without a frame mask (one clip has no valid frame at all), outputs and dropout-free training gradients."""
+    g = Golden("frame_temporal_small.npz")
+    enc = dropin_encoders.FrameEncoder(24, hidden_dim=32, output_dim=16, temporal_pooling=pool, dropout=0.0)
+    enc.load_state_dict(g.group(f"frame/{pool}/sd"))
+    enc = enc.cuda().eval()
+    x, mask = g.t("frame/x").cuda(), g.t("frame/mask").cuda()
+    assert _maxabs(enc(x), g.t(f"frame/{pool}/out")) <= TOL
+    assert _maxabs(enc(x, mask), g.t(f"frame/{pool}/out_mask")) <= TOL
+    enc.train()
+    xg = x.clone().requires_grad_(True)
+    (enc(xg, mask) * torch.linspace(-1, 1, 16, device="cuda").unsqueeze(0)).sum().backward()
+    assert _maxabs(xg.grad, g.t(f"frame/{pool}/gradx")) <= TOL
+    grads = dict(enc.named_parameters())
+    for key, ref in g.group(f"frame/{pool}/grad").items():
+        got = grads[key].grad
+        got = torch.zeros_like(grads[key]) if got is None else got
+        assert _maxabs(got, ref) <= 5 * TOL, key
+
+
+@pytest.mark.parametrize("rows,cols", [(10, 24), (300, 256), (4096, 130)])
+@pytest.mark.parametrize("p", [0.0, 0.3])
+def test_fused_batch_norm_relu_dropout_matches_torch(rows, cols, p):
+    """msf_bn_act_* (BatchNorm1d -> ReLU -> Dropout of SimpleMLPEncoder, src/encoders.py:374-377) against plain
+    PyTorch fp32 on the same input: batch statistics, running-average update, eval mode, and the backward pass with
+    the dropout mask the kernel drew injected into the reference."""
+    import importlib
+    from conftest import load_pkg
+    ops = importlib.import_module(load_pkg().__name__ + ".ops")
+    gen = torch.Generator().manual_seed(rows + cols)
+    y = (torch.randn(rows, cols, generator=gen) * 2.0 + 0.5).cuda().requires_grad_(True)
+    bn = torch.nn.BatchNorm1d(cols).cuda()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.uniform_(-0.3, 0.3)
+    ref_bn = torch.nn.BatchNorm1d(cols).cuda()
+    ref_bn.load_state_dict(bn.state_dict())
+    drop = torch.nn.Dropout(p)
+    wvec = torch.linspace(-1, 1, cols, device="cuda").unsqueeze(0)
+    out = dropin_encoders._bn_act(bn, y, True, drop)
+    keep = (out != 0).float() if p > 0 else None
+    (out * wvec).sum().backward()
+    y2 = y.detach().clone().requires_grad_(True)
+    ref = torch.relu(ref_bn(y2))
+    if p > 0:
+        live = ref > 0
+        frac = float(keep[live].mean())
+        assert abs(frac - (1 - p)) < 0.05, frac            # Bernoulli(1 - p) over the live units
+        ref = ref * keep / (1 - p)
+    (ref * wvec).sum().backward()
+    assert _maxabs(out, ref) <= 2e-5
+    assert _maxabs(y.grad, y2.grad) <= 2e-5
+    assert _maxabs(bn.weight.grad, ref_bn.weight.grad) <= 2e-4 * max(1.0, rows / 300)
+    assert _maxabs(bn.bias.grad, ref_bn.bias.grad) <= 2e-4 * max(1.0, rows / 300)
+    assert _maxabs(bn.running_mean, ref_bn.running_mean) <= 1e-6 and _maxabs(bn.running_var, ref_bn.running_var) <= 1e-5
+    assert int(bn.num_batches_tracked) == 1
+    bn.eval(), ref_bn.eval(), drop.eval()
+    assert _maxabs(dropin_encoders._bn_act(bn, y.detach(), True, drop), torch.relu(ref_bn(y.detach()))) <= 2e-5
