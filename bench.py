@@ -35,9 +35,27 @@ PKG = "multimodal-sensor-fusion-with-attention-rajeevatla_b200"
 DIMS = {"imu_hand": 128, "imu_chest": 128, "imu_ankle": 128, "heart_rate": 128}
 HIDDEN, HEADS, CLASSES, BATCH, DROPOUT, SMOOTHING = 256, 4, 25, 4096, 0.1, 0.05
 # live-path FLOPs per window: forward 3 553 792, train step 3x
-FLOP_FWD = sum(2 * d * HIDDEN for d in DIMS.values()) + 4 * HIDDEN * HIDDEN * 12 + 2 * HIDDEN * 4 \
-    + 2 * HIDDEN * HIDDEN + 2 * HIDDEN * CLASSES
+def _flop_fwd():
+    m = len(DIMS)
+    return sum(2 * d * HIDDEN for d in DIMS.values()) + 4 * HIDDEN * HIDDEN * m * (m - 1) + 2 * HIDDEN * m \
+        + 2 * HIDDEN * HIDDEN + 2 * HIDDEN * CLASSES
+
+
+FLOP_FWD = _flop_fwd()
 FLOP_TRAIN = 3 * FLOP_FWD
+SHAPE = "pamap2"
+
+
+def use_scaled_shape():
+    """BASELINE configs[4] (SURVEY config 5): 8 modalities of width 256 (2 video + 6 IMU), hidden 512, 8 heads,
+    11 classes (config/base.yaml:57-65).  Outside the fused kernels (M > 4, H > 256): grouped tcgen05 GEMM launches."""
+    global DIMS, HIDDEN, HEADS, CLASSES, FLOP_FWD, FLOP_TRAIN, SHAPE
+    DIMS = {f"video_{i}": 256 for i in range(2)}
+    DIMS.update({f"imu_{i}": 256 for i in range(6)})
+    HIDDEN, HEADS, CLASSES = 512, 8, 11
+    FLOP_FWD = _flop_fwd()
+    FLOP_TRAIN = 3 * FLOP_FWD
+    SHAPE = "scaled"
 METRIC = "windows/sec HybridFusion fwd+bwd & inference at 1/2/4/8 B200; % of HBM/TC roofline"
 
 
@@ -185,8 +203,12 @@ def run_reference(args):
 
 
 def workload_config(n):
-    return {"workload": "HybridFusion train step (BASELINE configs[1]): fwd + CE(ls 0.05) + bwd + clip + AdamW",
-            "per_gpu_batch": BATCH, "global_batch": BATCH * n, "modalities": 4, "feature_dim": 128,
+    what = ("HybridFusion train step (BASELINE configs[1]): fwd + CE(ls 0.05) + bwd + clip + AdamW" if SHAPE == "pamap2" else
+            "HybridFusion train step, scaled variant (BASELINE configs[4]: 8 modalities, d_model 512, 8 heads): fwd + "
+            "CE(ls 0.05) + bwd + clip + AdamW")
+    return {"workload": what,
+            "per_gpu_batch": BATCH, "global_batch": BATCH * n, "modalities": len(DIMS),
+            "feature_dim": next(iter(DIMS.values())),
             "hidden": HIDDEN, "heads": HEADS, "classes": CLASSES, "dropout": DROPOUT,
             "parallelism": f"dp{n} (batch-sharded, replicated parameters, gradient exchange per step)" if n > 1
                            else "single GPU"}
@@ -225,6 +247,9 @@ def run_ours(args):
     # host-facing leg: features cross PCIe as bf16 by default (the tensor-core path rounds them to bf16 anyway:
     # msf_fusion_call.x_bf16); the resident ring below stays fp32
     host_bf16 = args.host_dtype == "bf16" and precision == "bf16"
+    if host_bf16:   # bf16 features are read by the fused projection kernel only (msf_fusion_call.x_bf16)
+        ops_mod = importlib.import_module(PKG + ".ops")
+        host_bf16 = ops_mod.layer_norm_fused(model._plan(), pkg.native.MSF_PREC_BF16)
     eng = engine_mod.FusionEngine(model, BATCH, precision=precision, label_smoothing=SMOOTHING,
                                   max_grad_norm=1.0, seed=1234, use_graph=not args.no_graph,
                                   feature_dtype=torch.bfloat16 if host_bf16 else torch.float32)
@@ -876,8 +901,11 @@ def roofline_entry(kern, peaks, step_tflops):
     burst = peaks.get("tflops_burst")
     out = {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
            "frac": achieved / peaks["tflops"], "traffic": traffic, "peak_source": peaks["src"],
-           "kernel": "chain3_kernel (tcgen05/TMEM/TMA chained pair GEMMs, weights multicast over a CTA cluster; "
-                     "2 launches per step)",
+           "kernel": ("chain3_kernel (chained pair GEMMs, weights multicast over a CTA cluster; 2 launches per step)"
+                      if os.environ.get("MSF_CHAIN") == "v3" else
+                      "chain2_kernel (tcgen05/TMEM/TMA chained pair GEMMs value_proj -> out_proj and their mirror "
+                      "backward, half-pair software pipeline; 2 launches per step)") if SHAPE == "pamap2" else
+                     "tc_gemm_kernel grouped launches of the pair projections (shape outside the chained kernel)",
            "avg_launch_us": us / n, "algorithmic_gflop_per_launch": gf / n,
            "how": "CUDA events around %d back-to-back launches of each of the step's two chain launches, inside an "
                   "eager train step (operands L2-resident as in the step)" % kern.get("chain_reps", 1),
@@ -930,10 +958,15 @@ def main():
                          "0 = 8 on one GPU when --steps >= 16, else 1")
     ap.add_argument("--no-mask-hint", action="store_true",
                     help="infer_sweep: run every subset through the dense path (per-row mask, no skipping)")
+    ap.add_argument("--shape", default="pamap2", choices=["pamap2", "scaled"],
+                    help="train workload: pamap2 = BASELINE configs[1] (4 x 128 -> hidden 256), scaled = BASELINE "
+                         "configs[4] (8 modalities x 256 -> hidden 512, 8 heads, 11 classes)")
     ap.add_argument("--workload", default="train", choices=["train", "infer_sweep", "ece", "raw_infer"],
                     help="train = the benchmark proper (BASELINE configs[1]); the other two print extra evidence "
                          "lines for configs[2] and the ECE binning kernel (single GPU)")
     args = ap.parse_args()
+    if args.shape == "scaled":
+        use_scaled_shape()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "infer_sweep":

@@ -330,6 +330,12 @@ int msf_dpz_optimizer_step_packed(const msf_fusion_shape* shape, const msf_dpz_c
                                   float beta2, float eps, float weight_decay, float grad_scale, float max_norm,
                                   int32_t advance_state, void* stream);
 int msf_dpz_owner_map(const msf_fusion_shape* shape, int32_t world, int8_t* owner_host);
+/* Gradient accumulation over micro-batches (config/base.yaml:75 accumulate_grad_batches, src/train.py:519-521):
+ * acc[i] = (first ? 0 : acc[i]) + grad[i] over n floats; if both are given, *loss_acc = (first ? 0 : *loss_acc) +
+ * loss_scale * *loss (the mean micro-batch loss).  Each micro-batch's pass scales its gradient by
+ * 1 / (batch * micro_batches) (grad_scale of msf_fusion_train_pass), so the sum is the mean over the whole step. */
+int msf_grad_accumulate(float* acc, const float* grad, int64_t n, float* loss_acc, const float* loss, float loss_scale,
+                        int32_t first, void* stream);
 /* train_state = DEVICE {seed, offset, step[, lr bits]}: offset += 1, step += 1.
  * Every optimizer entry point that takes a train_state accepts lr < 0: the learning rate is then the fp32 whose bits
  * are the low word of train_state[3] (a fourth uint64 the caller owns and updates between launches), so a captured

@@ -168,6 +168,7 @@ PROTOTYPES = {
                                               c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                               c_void_p, c_void_p]),
     "msf_lstm_forward": (c_int32, [POINTER(LstmSeq), c_int32, c_int64, c_int32, c_int32, c_void_p]),
+    "msf_grad_accumulate": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_float, c_int32, c_void_p]),
     "msf_bn_act_forward": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                      c_float, c_int32, c_int32, c_float, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "msf_bn_act_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int32,

@@ -381,3 +381,42 @@ int msf_dropout_mask(uint64_t seed, uint64_t offset, int32_t site, int32_t sub, 
 }
 
 }  // extern "C"
+
+
+// Gradient accumulation over micro-batches (config/base.yaml:75, src/train.py:519-521): acc = (first ? 0 : acc) + grad,
+// and the running mean of the micro-batch losses beside it.
+namespace msf {
+namespace {
+__global__ void grad_accumulate_kernel(float* __restrict__ acc, const float* __restrict__ grad, long long n, int first,
+                                       float* __restrict__ loss_acc, const float* __restrict__ loss, float loss_scale) {
+  const long long n4 = n >> 2;
+  const bool vec = ((reinterpret_cast<uintptr_t>(acc) | reinterpret_cast<uintptr_t>(grad)) & 15) == 0;
+  const long long stride = (long long)gridDim.x * blockDim.x, tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vec) {
+    for (long long i = tid; i < n4; i += stride) {
+      float4 g = __ldg(reinterpret_cast<const float4*>(grad) + i);
+      if (!first) {
+        const float4 a = reinterpret_cast<const float4*>(acc)[i];
+        g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w;
+      }
+      reinterpret_cast<float4*>(acc)[i] = g;
+    }
+    for (long long i = (n4 << 2) + tid; i < n; i += stride) acc[i] = (first ? 0.0f : acc[i]) + __ldg(grad + i);
+  } else {
+    for (long long i = tid; i < n; i += stride) acc[i] = (first ? 0.0f : acc[i]) + __ldg(grad + i);
+  }
+  if (tid == 0 && loss_acc != nullptr && loss != nullptr) *loss_acc = (first ? 0.0f : *loss_acc) + loss_scale * *loss;
+}
+}  // namespace
+}  // namespace msf
+
+extern "C" int msf_grad_accumulate(float* acc, const float* grad, int64_t n, float* loss_acc, const float* loss,
+                                   float loss_scale, int32_t first, void* stream) {
+  using namespace msf;
+  MSF_REQUIRE(acc && grad && n >= 1, "msf_grad_accumulate: bad arguments");
+  const long long blocks = ceil_div(n >> 2, 256);
+  grad_accumulate_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks > 1184 ? 1184 : blocks), 256, 0, (cudaStream_t)stream>>>(
+      acc, grad, n, first, loss_acc, loss, loss_scale);
+  MSF_LAUNCH_CHECK();
+  return MSF_OK;
+}

@@ -183,24 +183,35 @@ class FusionEngine:
         N.check(N.lib().msf_fusion_forward(ctypes_ref(self.plan.shape), ctypes_ref(c), ops._stream()))
 
     def _enqueue_train_step(self, slot: int = 0) -> None:
+        norm_given = self._enqueue_pass(slot)
+        self._enqueue_optimizer(norm_given)
+
+    def _enqueue_pass(self, slot: int = 0, grad: Optional[torch.Tensor] = None, micro_batches: int = 1) -> bool:
+        """Forward + CE(label smoothing) + backward of one batch as one enqueue (msf_fusion_train_pass); the gradient
+        arena (``grad`` or self.grad) is overwritten.  Returns whether the pass also produced the gradient square norm."""
         lib = N.lib()
         st = ops._stream()
-        # forward + CE(label smoothing) + backward as one enqueue (msf_fusion_train_pass).  Mean over the
-        # GLOBAL batch: each rank scales by 1/(B*world), the gradient exchange sums.
+        # Mean over the GLOBAL batch (times the micro-batches of an accumulated step): each rank scales by
+        # 1/(B*world*micro_batches), the gradient exchange / accumulation sums.
         c = self._call(True, slot)
-        c.logits, c.grad_params = self.logits.data_ptr(), self.grad.data_ptr()
+        c.logits, c.grad_params = self.logits.data_ptr(), (self.grad if grad is None else grad).data_ptr()
         # single GPU, fused pass: the kernels that write the gradients also sum their squares, so the optimizer
         # launch needs no pass over the gradient arena before it can clip (MSF_OPT_NORM_GIVEN)
-        norm_given = (self.world == 1 and self.arena_bf16 is not None
-                     and lib.msf_fusion_train_pass_is_fused(ctypes_ref(self.plan.shape), self.prec) == 1)
+        norm_given = (self.world == 1 and self.arena_bf16 is not None and grad is None
+                      and lib.msf_fusion_train_pass_is_fused(ctypes_ref(self.plan.shape), self.prec) == 1)
         if norm_given:
             c.grad_sq = self.sq_norm.data_ptr() + 8
         N.check(lib.msf_fusion_train_pass(ctypes_ref(self.plan.shape), ctypes_ref(c),
                                           self._slots[slot][2].data_ptr(), self.smoothing,
-                                          1.0 / (self.batch * self.world), self.row_loss.data_ptr(),
+                                          1.0 / (self.batch * self.world * micro_batches), self.row_loss.data_ptr(),
                                           self._loss_ptr.get(slot, self.loss.data_ptr()), self.dlogits.data_ptr(),
-                                          N.MSF_TRAIN_DEAD_SLOTS_ZERO,   # self.grad is zero-initialised and only
-                                          st))                           # ever written by this entry point
+                                          N.MSF_TRAIN_DEAD_SLOTS_ZERO if grad is None else 0,   # self.grad is zero-
+                                          st))                  # initialised and only ever written by this entry point
+        return norm_given
+
+    def _enqueue_optimizer(self, norm_given: bool) -> None:
+        lib = N.lib()
+        st = ops._stream()
         if self.comm == "zshard":
             N.check(lib.msf_dpz_optimizer_step_packed(
                 ctypes_ref(self.plan.shape), ctypes_ref(self.dp_comm), self.arena.data_ptr(), self.grad.data_ptr(),
@@ -542,6 +553,30 @@ class FusionEngine:
     def train_step(self, features, mask, labels) -> torch.Tensor:
         self.load_batch(features, mask, labels)
         return self.train_step_resident()
+
+    def train_step_accumulated(self, micro_batches) -> torch.Tensor:
+        """One optimizer step over several micro-batches (config/base.yaml:75 ``accumulate_grad_batches``,
+        src/train.py:519-521): every micro-batch (features, mask, labels), each of the engine's batch size, runs
+        forward + backward with its loss scaled by 1 / len(micro_batches); the gradients are summed on the device
+        (msf_grad_accumulate) and clipped / applied once.  Returns the mean of the micro-batch losses (device)."""
+        micro_batches = list(micro_batches)
+        k = len(micro_batches)
+        if k == 0:
+            raise ValueError("train_step_accumulated needs at least one micro-batch")
+        if getattr(self, "_grad_micro", None) is None:
+            self._grad_micro = torch.zeros_like(self.grad)
+            self._loss_acc = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        lib, n = N.lib(), self.plan.total
+        for i, (f, m, y) in enumerate(micro_batches):
+            self.load_batch(f, m, y)
+            self._enqueue_pass(0, grad=self._grad_micro, micro_batches=k)
+            N.check(lib.msf_grad_accumulate(self.grad.data_ptr(), self._grad_micro.data_ptr(), n,
+                                            self._loss_acc.data_ptr(), self.loss.data_ptr(), 1.0 / k, int(i == 0),
+                                            ops._stream()))
+            if i + 1 < k:
+                self.state[1] += 1   # the next micro-batch draws fresh dropout masks (Philox offset; stream-ordered)
+        self._enqueue_optimizer(False)
+        return self._loss_acc
 
     def train_stream(self, batches):
         """Host-facing training loop: `batches` yields (features, mask, labels) on the host (pinned memory

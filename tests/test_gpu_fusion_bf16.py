@@ -453,3 +453,33 @@ def test_engine_streams_bf16_host_batches():
             assert abs(a - b) <= 1e-3 * abs(a), out
         diff = (out["fp32"][1] - out[mode][1]).abs()
         assert float(diff.max()) <= 1.01e-2 and float(diff.mean()) <= 1e-4   # as test_train_stream_pipeline_equals_step_by_step
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_accumulated_step_equals_one_large_batch(precision):
+    """FusionEngine.train_step_accumulated (accumulate_grad_batches, config/base.yaml:75): two micro-batches of 256
+    windows give the gradient — and, dropout off, the optimizer step — of the 512-window batch they were cut from."""
+    pkg = load_pkg()
+    engine = importlib.import_module(pkg.__name__ + ".engine")
+    out = {}
+    for mode in ("whole", "micro"):
+        model, feats, mask, labels = seeded_case(PAMAP2, 256, 4, 25, 512, seed=33, device="cuda")
+        B = 512 if mode == "whole" else 256
+        eng = engine.FusionEngine(model, B, precision=precision, seed=5, use_graph=False)
+        eng.p = 0.0
+        losses = []
+        for _ in range(3):
+            if mode == "whole":
+                losses.append(float(eng.train_step(feats, mask, labels).item()))
+            else:
+                halves = [({k: v[s] for k, v in feats.items()}, mask[s], labels[s]) for s in (slice(0, 256), slice(256, 512))]
+                losses.append(float(eng.train_step_accumulated(halves).item()))
+        torch.cuda.synchronize()
+        out[mode] = (losses, eng.arena.clone(), eng.grad.clone(), int(eng.state[2].item()))
+    assert out["whole"][3] == out["micro"][3] == 4          # three optimizer steps either way (1-based counter)
+    for a, b in zip(out["whole"][0], out["micro"][0]):
+        assert abs(a - b) <= (1e-5 if precision == "fp32" else 1e-3) * abs(a), out
+    gdiff = (out["whole"][2] - out["micro"][2]).abs()
+    assert float(gdiff.max()) <= (2e-6 if precision == "fp32" else 2e-4)     # last step's (clipped-scale) gradient
+    diff = (out["whole"][1] - out["micro"][1]).abs()
+    assert float(diff.max()) <= 1.01e-2 and float(diff.mean()) <= 1e-4   # Adam sign flips of ~0 gradients
