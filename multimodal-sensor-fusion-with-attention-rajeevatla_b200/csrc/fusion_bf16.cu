@@ -1227,7 +1227,7 @@ static int backward_back(const Layout& L, const msf_fusion_call* c, const WsBf16
   bool wg_pairs = wg2_enabled() && wg2_shape_ok(H, H, dW + L.cls_w1) && wg2_shape_ok(H, H, dW + L.cls_w2) &&
                   (pairs == 0 || (wg2_shape_ok(H, H, dW + L.pair_w(0, 2)) && L.pair_stride % 4 == 0 && (H * H + H) % 4 == 0));
   for (int m = 0; m < M; ++m) wg_pairs = wg_pairs && wg2_shape_ok(L.D[m], L.D[m], dW + L.proj_w[m]);
-  wg_pairs = wg_pairs && 9 + M <= WG2_MAX_MAPS && 2 + 2 * pairs + M <= WG2_MAX_PROBLEMS;
+  wg_pairs = wg_pairs && 9 + M <= WG2_MAX_MAPS;   // more than WG2_MAX_PROBLEMS problems go out as several launches
   if (wg_pairs) {   // CTA pairs, 256 x 256 tiles, the contraction split in two halves (wg2_gemm.cu)
     Wg2Builder wb(B, st, "WG weight gradients");
     const short mapDlog = (short)wb.add_map(ws.dlog, B, Cp, Cp, 1, 0);

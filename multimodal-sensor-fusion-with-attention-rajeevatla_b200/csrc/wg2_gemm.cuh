@@ -10,7 +10,7 @@
 namespace msf {
 
 constexpr int WG2_MAX_PROBLEMS = 40;
-constexpr int WG2_MAX_MAPS = 16;
+constexpr int WG2_MAX_MAPS = 24;
 constexpr int WG2_MAX_FLAG_TILES = 96;   // split launches keep one ticket word per (tile, CTA rank, epilogue warp)
 
 struct Wg2Problem {

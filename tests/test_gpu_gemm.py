@@ -52,6 +52,7 @@ MN_MAJOR = [  # k (contraction = windows), m, n
     # CTA-pair kernel (wg2_gemm.cu, n % 128 == 0): several 256 x 256 tiles, ragged m, a 128-wide last column tile,
     # contraction of 3 / 1 k-blocks (uneven halves / no split)
     (4096, 512, 512), (4096, 704, 384), (130, 256, 128), (64, 256, 256), (2048, 25, 256),
+    (512, 2560, 2560),   # 100 tiles on 74 CTA pairs: no split, clusters loop over several tiles
 ]
 
 
