@@ -219,6 +219,11 @@ int msf_arena_scatter(const int64_t* table, int32_t n_tensors, int64_t total, co
 int msf_cross_entropy(const float* logits, const int64_t* labels, int64_t batch, int32_t classes,
                       float smoothing, float grad_scale, float* row_loss, float* loss_out,
                       float* grad_logits, void* stream);
+/* Rows handed to msf_cross_entropy whose label was outside [0, classes) since the last reset (synchronises the
+ * device).  Such rows never index the logits: they are treated as having no target class.  The fused head kernel
+ * (msf_fusion_train_pass) compares class indices instead of indexing, so it cannot read out of bounds either;
+ * FusionEngine.load_batch validates host labels before they are copied. */
+int msf_bad_label_count(int64_t* count, int32_t reset);
 int msf_softmax_conf_pred(const float* logits, int64_t batch, int32_t classes, float* conf,
                           int64_t* pred, void* stream);
 
@@ -233,6 +238,16 @@ int msf_softmax_conf_pred(const float* logits, int64_t batch, int32_t classes, f
 int msf_ece_bin(const float* conf, const int64_t* pred, const int64_t* label, int64_t n,
                 const double* edges, int32_t num_bins, int64_t* count, int64_t* correct,
                 uint64_t* conf_sum_q32, void* stream);
+/* Evaluation epilogue in one pass over the logits (src/eval.py:39-130, src/uncertainty.py:495-553): per window
+ * softmax -> (confidence, first arg-max) and NLL = lse - logit[label]; ACCUMULATED (all integer, order-independent,
+ * shards merge with one integer all-reduce) into
+ *   confusion[classes * classes]  counts of (label, prediction): accuracy and macro-F1 follow from it
+ *   scalars[3]                    {windows seen, sum of NLL in Q24 fixed point, windows whose label is outside [0, C)}
+ *   bins[3 * num_bins]            ECE / reliability bins as msf_ece_bin: count, correct, confidence sum (Q32)
+ * conf / pred (batch each) may be NULL.  Windows with an out-of-range label only count in scalars[0] and scalars[2]. */
+int msf_eval_accumulate(const float* logits, const int64_t* labels, int64_t batch, int32_t classes,
+                        const double* edges, int32_t num_bins, float* conf, int64_t* pred, int64_t* confusion,
+                        int64_t* scalars, int64_t* bins, void* stream);
 
 /* ---- optimizer (src/train.py:378-382,416-430) ------------------------------ */
 /* sq_norm[0] += sum(g^2) (double); zero it first. */

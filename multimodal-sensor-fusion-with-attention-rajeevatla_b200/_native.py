@@ -168,6 +168,9 @@ PROTOTYPES = {
                                               c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                               c_void_p, c_void_p]),
     "msf_lstm_forward": (c_int32, [POINTER(LstmSeq), c_int32, c_int64, c_int32, c_int32, c_void_p]),
+    "msf_eval_accumulate": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, POINTER(ctypes.c_double), c_int32, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "msf_bad_label_count": (c_int32, [POINTER(c_int64), c_int32]),
     "msf_grad_accumulate": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_float, c_int32, c_void_p]),
     "msf_bn_act_forward": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                      c_float, c_int32, c_int32, c_float, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p]),

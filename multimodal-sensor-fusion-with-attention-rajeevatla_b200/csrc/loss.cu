@@ -24,6 +24,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 // deterministic) and resets the ticket, so the mean needs no second launch
 __device__ unsigned int g_ce_ticket = 0;
 
+__device__ unsigned long long g_bad_labels = 0ull;   // rows whose label was outside [0, C) since the last reset
+
 __device__ void ce_rows(const float* __restrict__ logits, const int64_t* __restrict__ labels, long long B, int C,
                         float smoothing, float grad_scale, float* __restrict__ row_loss, float* __restrict__ grad) {
   const int lane = threadIdx.x & 31;
@@ -42,9 +44,14 @@ __device__ void ce_rows(const float* __restrict__ logits, const int64_t* __restr
   for (int c = lane; c < C; c += 32) se += expf(__ldg(z + c) - mx);
   se = warp_sum(se);
   const float lse = mx + logf(se);
-  const int y = (int)labels[row];
+  // a label outside [0, C) (e.g. an ignore_index of -100) must not index the logits: the row is treated as having
+  // no target class (loss = lse, gradient = softmax - smoothing / C) and counted (msf_bad_label_count)
+  const long long y64 = labels[row];
+  const bool y_ok = y64 >= 0 && y64 < (long long)C;
+  const int y = y_ok ? (int)y64 : -1;
+  if (lane == 0 && !y_ok) atomicAdd(&g_bad_labels, 1ull);
   if (lane == 0 && row_loss) {
-    const float nll = lse - __ldg(z + y);
+    const float nll = lse - (y_ok ? __ldg(z + y) : 0.0f);
     const float smooth = lse - zsum / (float)C;  // mean_c(-log p_c)
     row_loss[row] = (1.0f - smoothing) * nll + smoothing * smooth;
   }
@@ -154,3 +161,17 @@ int msf_softmax_conf_pred(const float* logits, int64_t batch, int32_t classes, f
 }
 
 }  // extern "C"
+
+
+extern "C" int msf_bad_label_count(int64_t* count, int32_t reset) {
+  using namespace msf;
+  MSF_REQUIRE(count != nullptr, "msf_bad_label_count: null output");
+  unsigned long long v = 0ull;
+  MSF_CHECK_CUDA(cudaMemcpyFromSymbol(&v, g_bad_labels, sizeof(v)));
+  if (reset) {
+    const unsigned long long zero = 0ull;
+    MSF_CHECK_CUDA(cudaMemcpyToSymbol(g_bad_labels, &zero, sizeof(zero)));
+  }
+  *count = (int64_t)v;
+  return MSF_OK;
+}

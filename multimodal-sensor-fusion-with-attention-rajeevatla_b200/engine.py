@@ -442,6 +442,10 @@ class FusionEngine:
         else:
             pairs.append((msk, mask))
         if labels is not None:
+            if labels.device.type == "cpu" and labels.numel():   # a host batch: cheap to check before it is copied
+                lo, hi = int(labels.min()), int(labels.max())
+                if lo < 0 or hi >= self.plan.C:
+                    raise IndexError(f"Target {lo if lo < 0 else hi} is out of bounds.")   # F.cross_entropy's message
             pairs.append((lab, labels))
         moved = sum(src.numel() * src.element_size() for _, src in pairs if src.device.type == "cpu")
         if all(src.dtype == dst.dtype and src.is_contiguous() and src.numel() == dst.numel()
@@ -738,6 +742,16 @@ class FusionEngine:
                 self._subset_graphs[bits] = self._capture(lambda: self._enqueue_inference(bits))
             self._subset_graphs[bits].replay()
         return self.logits, self.conf, self.pred
+
+    def eval_update(self, labels: torch.Tensor, stats: Optional["ops.EvalStats"] = None) -> "ops.EvalStats":
+        """Fold the last inference pass (self.logits) and its labels into device-side evaluation statistics
+        (confusion counts -> accuracy / macro-F1, NLL sum, ECE bins: ops.EvalStats, msf_eval_accumulate) — the
+        per-batch body of evaluate_model (src/eval.py:39-130) without host round trips.  Under data parallelism call
+        ``stats.all_reduce()`` once at the end (integer sums)."""
+        if stats is None:
+            stats = ops.EvalStats(self.plan.C, device=self.dev)
+        stats.update(self.logits, labels)
+        return stats
 
     def ece_bins(self, labels: torch.Tensor, edges: Sequence[float], out=None) -> torch.Tensor:
         """Shard-local binning of the last inference, then one integer all-reduce

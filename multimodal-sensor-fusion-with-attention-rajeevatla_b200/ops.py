@@ -583,6 +583,61 @@ def ece_bin(conf: torch.Tensor, pred: torch.Tensor, label: torch.Tensor, edges: 
     return out
 
 
+class EvalStats:
+    """Device-side accumulators of msf_eval_accumulate: confusion matrix, NLL sum, ECE bins.  ``update(logits,
+    labels)`` adds one batch in a single pass over the logits; ``metrics()`` reads the few integers back and returns
+    what evaluate_model / compute_calibration_metrics report (src/eval.py:39-130, src/uncertainty.py:495-553):
+    accuracy, f1_macro (sklearn's macro average with zero_division=0 over the classes seen in labels or
+    predictions), loss (mean NLL per window), ece, mce, num_samples."""
+
+    def __init__(self, classes: int, num_bins: int = 15, device=None):
+        self.dev = device or require_cuda("EvalStats")
+        self.C, self.nb = int(classes), int(num_bins)
+        self.edges = torch.linspace(0.0, 1.0, self.nb + 1).double().tolist()   # fp32 linspace edges, uncertainty.py:113
+        self.confusion = torch.zeros(self.C, self.C, dtype=torch.int64, device=self.dev)
+        self.scalars = torch.zeros(3, dtype=torch.int64, device=self.dev)
+        self.bins = torch.zeros(3, self.nb, dtype=torch.int64, device=self.dev)
+
+    def reset(self) -> None:
+        self.confusion.zero_()
+        self.scalars.zero_()
+        self.bins.zero_()
+
+    def update(self, logits: torch.Tensor, labels: torch.Tensor, conf: Optional[torch.Tensor] = None,
+               pred: Optional[torch.Tensor] = None) -> None:
+        logits = logits.detach().to(device=self.dev, dtype=torch.float32).contiguous()
+        labels = labels.detach().to(device=self.dev, dtype=torch.int64).contiguous()
+        assert logits.dim() == 2 and logits.shape[1] == self.C and labels.numel() == logits.shape[0]
+        e = (ctypes.c_double * (self.nb + 1))(*self.edges)
+        N.check(N.lib().msf_eval_accumulate(_p(logits), _p(labels), logits.shape[0], self.C, e, self.nb, _p(conf), _p(pred),
+                                            _p(self.confusion), _p(self.scalars), _p(self.bins), _stream()))
+
+    def all_reduce(self, group=None) -> None:
+        """Shard-local statistics -> global ones: integer sums, exact in any order."""
+        for t in (self.confusion, self.scalars, self.bins):
+            torch.distributed.all_reduce(t, group=group)
+
+    def metrics(self) -> Dict[str, float]:
+        cm = self.confusion.cpu().double()
+        seen, nll_q24, bad = (int(v) for v in self.scalars.cpu().tolist())
+        n = int(cm.sum().item())
+        tp = cm.diag()
+        support, predicted = cm.sum(1), cm.sum(0)
+        present = (support + predicted) > 0
+        denom = support + predicted
+        f1 = torch.where(denom > 0, 2.0 * tp / denom.clamp_min(1.0), torch.zeros_like(tp))
+        count, correct, csum = (self.bins[i].cpu().double() for i in range(3))
+        csum = csum / 4294967296.0
+        gap = torch.where(count > 0, (csum / count.clamp_min(1.0) - correct / count.clamp_min(1.0)).abs(), torch.zeros_like(count))
+        total = float(count.sum().item())
+        return {"accuracy": float(tp.sum().item()) / max(n, 1),
+                "f1_macro": float(f1[present].mean().item()) if bool(present.any()) else 0.0,
+                "loss": (nll_q24 / 16777216.0) / max(n, 1),
+                "ece": float((gap * count).sum().item()) / max(total, 1.0),
+                "mce": float(gap.max().item()) if total > 0 else 0.0,
+                "num_samples": seen, "out_of_range_labels": bad}
+
+
 def grad_sq_norm(grad: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     if out is None:
         out = torch.zeros(1, dtype=torch.float64, device=grad.device)

@@ -246,32 +246,19 @@ def compute_calibration_metrics(model: torch.nn.Module, dataloader, device: str 
     model.eval()
     run_dev = torch.device(device)
     dev = run_dev if run_dev.type == "cuda" else ops.require_cuda("compute_calibration_metrics")
-    edges = torch.linspace(0.0, 1.0, steps=16).double().tolist()
     stats = None
-    seen = hits = 0
-    nll_sum = 0.0
     with torch.no_grad(), torch.cuda.device(dev):
         for inputs, labels in dataloader:
             logits = model(inputs.to(run_dev)).to(dev)
-            labels = labels.to(dev)
-            conf, pred = ops.softmax_conf_pred(logits)
-            stats = ops.ece_bin(conf, pred, labels, edges, out=stats)
-            loss, _ = ops.cross_entropy(logits, labels, smoothing=0.0)
-            nll_sum += float(loss.item()) * labels.numel()
-            hits += int((pred == labels).sum().item())
-            seen += labels.numel()
+            if stats is None:
+                stats = ops.EvalStats(logits.shape[1], num_bins=15, device=dev)
+            # one pass over the logits per batch (msf_eval_accumulate): softmax -> (confidence, prediction), NLL, the
+            # confusion counts and the bins, all accumulated on the device; nothing is read back until the end
+            stats.update(logits, labels)
     if stats is None:
         raise ValueError("Dataloader produced no batches to evaluate.")
-    host = stats.cpu().numpy()
-    ece = torch.zeros(1, dtype=torch.float32)
-    mce = torch.zeros(1, dtype=torch.float32)
-    for n, hit, q in zip(host[0].tolist(), host[1].tolist(), host[2].astype(np.uint64).tolist()):
-        if n == 0:
-            continue
-        err = torch.abs(torch.tensor(hit / n, dtype=torch.float32) - torch.tensor(q / _Q32 / n, dtype=torch.float32))
-        ece += (n / seen) * err
-        mce = torch.max(mce, err)
-    return {"ece": float(ece.item()), "mce": float(mce.item()), "nll": nll_sum / seen, "accuracy": hits / seen}
+    m = stats.metrics()
+    return {"ece": m["ece"], "mce": m["mce"], "nll": m["loss"], "accuracy": m["accuracy"]}
 
 
 def main(save_path: Path | str = "test_reliability.png", num_samples: int = 1000,

@@ -213,3 +213,63 @@ def test_packed_optimizer_step_equals_step_plus_pack():
         assert float((vb - vc).abs().max()) <= 1e-12
         assert torch.equal(plan.pack_bf16(pc).view(torch.int16), c16.view(torch.int16))
         assert torch.equal(sb, sc)
+
+
+@pytest.mark.parametrize("n,classes", [(1000, 25), (65536, 25), (777, 40), (64, 3)])
+def test_eval_epilogue_matches_host_metrics(n, classes):
+    """msf_eval_accumulate (ops.EvalStats): accuracy, macro-F1 (sklearn's definition, zero_division=0), mean NLL and
+    ECE / MCE from ONE pass over the logits, against the reference's host recipe (src/eval.py:89-112) on the same
+    logits — integer accumulators: counts exact, NLL to fp32 rounding; two half-batches merge to the same integers."""
+    import importlib
+    from conftest import load_pkg
+    ops = importlib.import_module(load_pkg().__name__ + ".ops")
+    g = torch.Generator().manual_seed(n + classes)
+    logits = torch.randn(n, classes, generator=g) * 3.0
+    labels = torch.randint(0, classes, (n,), generator=g)
+    if classes > 10:
+        labels[labels == 7] = 8          # a class that never occurs in the labels
+        logits[:, 5] -= 100.0            # ... and one that is never predicted
+    st = ops.EvalStats(classes)
+    conf = torch.empty(n, device="cuda")
+    pred = torch.empty(n, dtype=torch.int64, device="cuda")
+    st.update(logits.cuda(), labels.cuda(), conf=conf, pred=pred)
+    m = st.metrics()
+    probs = torch.softmax(logits.double(), 1)
+    rconf, rpred = probs.max(1)
+    assert torch.equal(pred.cpu(), rpred)
+    assert float((conf.cpu().double() - rconf).abs().max()) <= 1e-6
+    assert m["num_samples"] == n and m["out_of_range_labels"] == 0
+    assert abs(m["accuracy"] - float((rpred == labels).double().mean())) < 1e-12
+    nll = float(torch.nn.functional.cross_entropy(logits.double(), labels))
+    assert abs(m["loss"] - nll) <= 2e-6 * max(1.0, nll)
+    f1s = []
+    for c in range(classes):     # sklearn f1_score(average="macro", zero_division=0) over labels seen in either vector
+        tp = int(((rpred == c) & (labels == c)).sum()); fp = int(((rpred == c) & (labels != c)).sum())
+        fn = int(((rpred != c) & (labels == c)).sum())
+        if tp + fp + fn == 0:
+            continue
+        f1s.append(2 * tp / (2 * tp + fp + fn))
+    assert abs(m["f1_macro"] - sum(f1s) / len(f1s)) < 1e-12
+    two = ops.EvalStats(classes)
+    half = n // 2
+    two.update(logits[:half].cuda(), labels[:half].cuda())
+    two.update(logits[half:].cuda(), labels[half:].cuda())
+    assert torch.equal(two.confusion, st.confusion) and torch.equal(two.bins, st.bins)
+    assert torch.equal(two.scalars, st.scalars)
+    # the bins are those of the stand-alone binning kernel on the same (conf, pred, label)
+    edges = torch.linspace(0, 1, 16).double().tolist()
+    bins = ops.ece_bin(conf, pred, labels.cuda(), edges)
+    assert torch.equal(bins, st.bins)
+
+
+def test_eval_epilogue_counts_out_of_range_labels():
+    import importlib
+    from conftest import load_pkg
+    ops = importlib.import_module(load_pkg().__name__ + ".ops")
+    logits = torch.randn(32, 5, device="cuda")
+    labels = torch.randint(0, 5, (32,), device="cuda")
+    labels[4], labels[9] = -100, 5
+    st = ops.EvalStats(5)
+    st.update(logits, labels)
+    m = st.metrics()
+    assert m["num_samples"] == 32 and m["out_of_range_labels"] == 2 and int(st.confusion.sum()) == 30

@@ -197,3 +197,35 @@ def test_c_abi_rejects_bad_calls():
         ops.FusionPlan(["a", "b"], [8, 8], 10, 4, 3, [])
     with pytest.raises(pkg.MsfError, match="not eligible|params_bf16"):
         ops.fusion_forward_raw(plan, arena, xs, None, precision=pkg.native.MSF_PREC_BF16)
+
+
+def test_out_of_range_labels_never_index_the_logits():
+    """A label outside [0, C) (an ignore_index of -100, a class id >= C) must not read out of bounds: the stand-alone
+    CE kernel treats the row as having no target class and counts it; the engine refuses a host batch that holds one."""
+    import importlib
+    import ctypes
+    pkg = load_pkg()
+    ops = importlib.import_module(pkg.__name__ + ".ops")
+    engine = importlib.import_module(pkg.__name__ + ".engine")
+    lib = pkg.lib()
+    n = ctypes.c_int64()
+    pkg.native.check(lib.msf_bad_label_count(ctypes.byref(n), 1))
+    logits = torch.randn(64, 25, device="cuda")
+    labels = torch.randint(0, 25, (64,), device="cuda")
+    labels[3], labels[40] = -100, 25
+    loss, grad = ops.cross_entropy(logits, labels, smoothing=0.0)
+    assert torch.isfinite(loss).all() and torch.isfinite(grad).all()
+    ok = torch.ones(64, dtype=torch.bool, device="cuda")
+    ok[3] = ok[40] = False
+    ref = torch.nn.functional.cross_entropy(logits[ok], labels[ok], reduction="sum")
+    lse = torch.logsumexp(logits[~ok], dim=1).sum()     # rows without a target class contribute their lse
+    assert abs(float(loss) * 64 - float(ref + lse)) <= 1e-3
+    pkg.native.check(lib.msf_bad_label_count(ctypes.byref(n), 1))
+    assert n.value == 2
+    from helpers import PAMAP2, seeded_case
+    model, feats, mask, labels = seeded_case(PAMAP2, 256, 4, 25, 64, seed=3, device="cpu")
+    eng = engine.FusionEngine(model, 64, precision="fp32", use_graph=False)
+    bad = labels.clone()
+    bad[5] = 25
+    with pytest.raises(IndexError):
+        eng.load_batch(feats, mask, bad)
