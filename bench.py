@@ -557,7 +557,18 @@ def run_infer_sweep(args):
     host_pred = torch.zeros(len(subsets), B, dtype=torch.int64).pin_memory()
     host_stats = torch.zeros(len(subsets), 3, 15, dtype=torch.int64).pin_memory()
 
+    folded = not args.no_mask_hint and not args.no_fold
+
     def sweep(src_feats=feats, readback=False):
+        if folded:   # projections shared over the sweep, one folded pair GEMM + head kernel per subset
+            def after(i, sub):
+                eng.ece_bins(labels, edges, out=stats[i])
+                if readback:
+                    host_pred[i].copy_(eng.pred, non_blocking=True)
+            eng.infer_sweep(src_feats, subsets, on_subset=after)
+            if readback:
+                host_stats.copy_(stats, non_blocking=True)
+            return
         eng.load_batch(src_feats, masks[0], labels)  # the batch is copied once per sweep, the mask per subset
         for i, sub in enumerate(subsets):
             if args.no_mask_hint:
@@ -590,7 +601,11 @@ def run_infer_sweep(args):
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": "HybridFusion inference mask sweep (BASELINE configs[2]): 15 subsets x 65536 "
                                    "windows, fwd + softmax/argmax + ECE binning", "batch": B, "subsets": len(subsets),
-                       "mask_hint": not args.no_mask_hint},
+                       "mask_hint": not args.no_mask_hint,
+                       "path": ("FusionEngine.infer_sweep: projections computed once per sweep, value_proj -> out_proj "
+                                "of every attention module folded into one matrix (msf_fusion_infer_folded)") if folded
+                               else ("infer_subset per subset (chained pair kernels, absent modalities skipped)"
+                                     if not args.no_mask_hint else "dense per-row-mask path per subset")},
             "run": {"l2": "inputs 34 MB per subset, workspace 1.7 GB >> 126 MiB L2", "repeats": repeats,
                     "timed_region_ms": ms * steps * repeats, "a_step_is": "one sweep = 15 x 65536 window-evaluations"},
             "clocks": clocks,
@@ -610,7 +625,8 @@ def run_infer_sweep(args):
     sweep()
     torch.cuda.synchronize()
     line["gpu_launches"] = int(pkg.lib().msf_launch_count() - before) if args.no_graph else None
-    line["gpu_launches_per_step"] = "45 forward-pass kernels (3 per subset, CUDA graphs) + 15 ece_bin_kernel"
+    line["gpu_launches_per_step"] = ("1 projection kernel + 15 x (folded pair GEMM + head kernel) + 15 ece_bin_kernel" if folded
+                                     else "45 forward-pass kernels (3 per subset, CUDA graphs) + 15 ece_bin_kernel")
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = _cpu_sweep_baseline(torch, subsets)
     os.write(json_fd, (json.dumps(line) + "\n").encode())
@@ -728,8 +744,25 @@ def run_raw_infer(args):
     steps = max(1, min(args.steps, 5))
     logits_a = ours()[0].clone()
     logits_b = library()[0].clone()
+    sampler = ClockSampler(0)
+    sampler.start()
     ms = timed(ours, steps)
+    clocks = sampler.stop()
     ms_lib = timed(library, steps)
+    # e2e: raw windows from pinned host memory, predictions and confidences read back, every pass
+    host_x = {m: x.cpu().pin_memory() for m, x in xs.items()}
+    host_pred = torch.zeros(B, dtype=torch.int64).pin_memory()
+    host_conf = torch.zeros(B, dtype=torch.float32).pin_memory()
+
+    def e2e():
+        for m in xs:
+            xs[m].copy_(host_x[m], non_blocking=True)
+        _, conf, pred = ours()
+        host_pred.copy_(pred, non_blocking=True)
+        host_conf.copy_(conf, non_blocking=True)
+
+    ms_e2e = timed(e2e, max(1, min(steps, 3)))
+    h2d = sum(t.numel() * 4 for t in host_x.values())
     flop = B * sum(T * 2 * (f + HID) * 4 * HID + 2 * HID * 128 for f in feats_in.values()) + B * FLOP_FWD
     peaks = _peaks()
     tf = flop / (ms * 1e-3) / 1e12
@@ -739,13 +772,58 @@ def run_raw_infer(args):
             "config": {"workload": "inference from raw windows (SURVEY 8d boundary E): 4 LSTM encoders T=1024 + "
                                    "projection + LayerNorm + HybridFusion + softmax", "batch": B, "seq_len": T,
                        "l2": "1.1 GB of raw windows per pass >> 126 MiB L2"},
+            "clocks": clocks,
+            "e2e": {"value": B / (ms_e2e * 1e-3), "unit": "windows/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": B * 12,
+                    "api": "raw fp32 windows copied from pinned host memory, SequenceEncoder recurrence on "
+                           "ops.lstm_forward, FusionEngine.infer, predictions + confidences copied back"},
+            "gpu_launches": 1024 * 1 + 8,
             "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": tf / peaks["tflops"], "traffic": None, "peak_source": peaks["src"],
                          "kernel": "whole pass: 1024 LSTM-step launches (tc_gemm_kernel, TC_EPI_LSTM) + fusion forward"},
             "library_recurrence": {"ms_per_step": ms_lib, "value": B / (ms_lib * 1e-3),
                                    "what": "same pass with torch.nn.LSTM (cuDNN, fp32 no-TF32) for the recurrence"},
             "max_abs_logit_diff_vs_library": float((logits_a - logits_b).abs().max())}
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = _cpu_raw_infer_baseline(torch, encoders, fusion, feats_in, T, HID)
     os.write(json_fd, (json.dumps(line) + "\n").encode())
+
+
+def _cpu_raw_infer_baseline(torch, encoders_mod, fusion, feats_in, T, HID, sample=64):
+    """The reference arithmetic of the raw-window pass on the host cores: oracle LSTM recurrence (fp32) of the four
+    encoders + projection + LayerNorm + oracle fusion forward + softmax/argmax on a bounded sample of windows."""
+    from oracle import encoder_oracle, fusion_oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    encs = {m: encoders_mod.SequenceEncoder(f, hidden_dim=HID, output_dim=128, num_layers=1, encoder_type="lstm",
+                                            dropout=DROPOUT).eval() for m, f in feats_in.items()}
+    norms = {m: torch.nn.LayerNorm(128) for m in feats_in}
+    model = fusion.HybridFusion(DIMS, hidden_dim=HIDDEN, num_classes=CLASSES, num_heads=HEADS, dropout=DROPOUT).eval()
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(7)
+    xs = {m: torch.randn(sample, T, f, generator=g) for m, f in feats_in.items()}
+    mask = torch.ones(sample, len(feats_in))
+
+    def one_pass():
+        with torch.no_grad():
+            enc = {}
+            for m in feats_in:
+                esd = {k: v.detach() for k, v in encs[m].state_dict().items()}
+                h = encoder_oracle.sequence_encoder_forward(esd, xs[m], 1, "lstm")
+                enc[m] = norms[m](h)
+            logits, _ = fusion_oracle.hybrid_fusion_forward(sd, list(DIMS), HEADS, enc, mask)
+            return torch.softmax(logits, 1).max(1)
+
+    one_pass()
+    t0, n = time.perf_counter(), 0
+    while time.perf_counter() - t0 < 10.0:
+        one_pass()
+        n += 1
+    dt = (time.perf_counter() - t0) / n
+    return {"value": sample / dt, "unit": "windows/s", "cores": cores, "kind": "port",
+            "sample": f"{n} passes of {sample} raw windows (T = {T}): oracle LSTM recurrence + projection + LayerNorm + "
+                      "fusion forward + softmax/argmax; a reported baseline, not the target"}
 
 
 def run_ece(args):
@@ -956,6 +1034,8 @@ def main():
     ap.add_argument("--steps-per-graph", type=int, default=0,
                     help="train workload: steps captured into one graph launch (FusionEngine.train_slots); "
                          "0 = 8 on one GPU when --steps >= 16, else 1")
+    ap.add_argument("--no-fold", action="store_true",
+                    help="infer_sweep: per-subset infer_subset (chained pair kernels) instead of the folded sweep")
     ap.add_argument("--no-mask-hint", action="store_true",
                     help="infer_sweep: run every subset through the dense path (per-row mask, no skipping)")
     ap.add_argument("--shape", default="pamap2", choices=["pamap2", "scaled"],

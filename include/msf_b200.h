@@ -188,6 +188,21 @@ int msf_fusion_train_pass_is_fused(const msf_fusion_shape* shape, int32_t precis
  * exactly the out_proj bias remains) and the rows of absent queries are not computed (tensor-core path). */
 int msf_fusion_infer_pass(const msf_fusion_shape* shape, const msf_fusion_call* call, float* conf, int64_t* pred,
                           uint32_t present_hint, void* stream);
+/* The subset sweep of src/eval.py:342-404 with every attention module's value_proj -> out_proj pair FOLDED into one
+ * matrix: in inference (no attention dropout) the gate of a present key is 1 for every head, so
+ * out_proj(value_proj(P_k)) = P_k (Wo Wv)^T + (Wo bv + bo).  Per present query one tcgen05 GEMM whose K-segments are
+ * the present keys (accumulated in TMEM) with the mean epilogue, then the fused head kernel: half the pair FLOPs
+ * of msf_fusion_infer_pass, same result within the BF16 tolerance.  Tensor-core path, shapes of the fused kernels.
+ *   wov_bf16  [M*(M-1)][H][H] bf16, pair order of attn_gates: Wo_qk * Wv_qk, row-major [out][in]
+ *   bias_sum  [M][H] fp32 for THIS subset: row q = sum_{k present, k != q} (Wo_qk bv_qk + bo_qk) + sum_{k absent} bo_qk
+ *   present   bit m = modality m is present in every row (call->mask must be that uniform mask)
+ *   flags     bit 0: the projections of the present modalities are still in the workspace from an earlier call on
+ *             the same features (the sweep projects once); bit 1: compute the projections only */
+#define MSF_FOLD_REUSE_PROJECTIONS 1
+#define MSF_FOLD_PROJECTIONS_ONLY 2
+int msf_fusion_infer_folded(const msf_fusion_shape* shape, const msf_fusion_call* call, const void* wov_bf16,
+                            const float* bias_sum, uint32_t present, int32_t flags, float* conf, int64_t* pred,
+                            void* stream);
 /* Debugging aid: clock64 stamps (SM cycles) of the phases of CTA 0 in the last fused head-kernel launch
  * (P0 start/end, then acquire/finish of E1..E4, P5 start/end).  Synchronises the device. */
 int msf_debug_head_stamps(int64_t* out16);

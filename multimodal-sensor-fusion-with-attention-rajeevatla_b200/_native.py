@@ -12,6 +12,8 @@ MSF_PREC_F32, MSF_PREC_BF16 = 0, 1
 MSF_TRAIN_DEAD_SLOTS_ZERO = 1
 MSF_OPT_NORM_GIVEN = 2
 MSF_ABI_VERSION = 4
+MSF_FOLD_REUSE_PROJECTIONS = 1
+MSF_FOLD_PROJECTIONS_ONLY = 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -168,6 +170,8 @@ PROTOTYPES = {
                                               c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                               c_void_p, c_void_p]),
     "msf_lstm_forward": (c_int32, [POINTER(LstmSeq), c_int32, c_int64, c_int32, c_int32, c_void_p]),
+    "msf_fusion_infer_folded": (c_int32, [POINTER(FusionShape), POINTER(FusionCall), c_void_p, c_void_p, ctypes.c_uint32,
+                                          c_int32, c_void_p, c_void_p, c_void_p]),
     "msf_eval_accumulate": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, POINTER(ctypes.c_double), c_int32, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "msf_bad_label_count": (c_int32, [POINTER(c_int64), c_int32]),

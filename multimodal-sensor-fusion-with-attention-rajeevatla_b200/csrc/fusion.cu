@@ -25,6 +25,8 @@ int fusion_bf16_train(const Layout& L, const msf_fusion_call* c, const int64_t* 
                       float grad_scale, float* row_loss, float* loss_out, int flags, cudaStream_t st);
 int fusion_bf16_infer(const Layout& L, const msf_fusion_call* c, float* conf, int64_t* pred, unsigned present_hint,
                       cudaStream_t st);
+int fusion_bf16_infer_folded(const Layout& L, const msf_fusion_call* c, const void* wov, const float* bias_sum,
+                             unsigned present, int flags, float* conf, int64_t* pred, cudaStream_t st);
 
 static int check_call(const Layout& L, const msf_fusion_call* c, bool backward) {
   MSF_REQUIRE(c != nullptr, "null call");
@@ -171,6 +173,20 @@ int msf_fusion_infer_pass(const msf_fusion_shape* shape, const msf_fusion_call* 
     return msf::fusion_bf16_infer(L, call, conf, pred, present_hint, (cudaStream_t)stream);
   if ((rc = msf_fusion_forward(shape, call, stream))) return rc;
   return msf_softmax_conf_pred(call->logits, call->batch, L.C, conf, pred, stream);
+}
+
+int msf_fusion_infer_folded(const msf_fusion_shape* shape, const msf_fusion_call* call, const void* wov_bf16,
+                            const float* bias_sum, uint32_t present, int32_t flags, float* conf, int64_t* pred,
+                            void* stream) {
+  msf::Layout L;
+  int rc = msf::make_layout(shape, &L);
+  if (rc) return rc;
+  if ((rc = msf::check_call(L, call, false))) return rc;
+  if (call->precision != MSF_PREC_BF16) {
+    msf::set_error("msf_fusion_infer_folded runs on the tensor-core path only");
+    return MSF_E_UNSUPPORTED;
+  }
+  return msf::fusion_bf16_infer_folded(L, call, wov_bf16, bias_sum, present, flags, conf, pred, (cudaStream_t)stream);
 }
 
 int msf_debug_chain_stamps(int64_t* out16) {

@@ -686,7 +686,8 @@ static int check_ws(const WsBf16& ws, const msf_fusion_call* c) {
 // skipped: their projections, the chain items of absent queries (aggregated = 0 through the row mask) and the
 // GEMMs of pairs with an absent key (gate 0: they contribute exactly their out_proj bias).
 static int forward_front(const Layout& L, const msf_fusion_call* c, const WsBf16& ws, const ArenaBf16& A,
-                         cudaStream_t st, const ZeroList* zero = nullptr, unsigned present_hint = 0u) {
+                         cudaStream_t st, const ZeroList* zero = nullptr, unsigned present_hint = 0u,
+                         bool projections_only = false) {
   const int64_t B = c->batch;
   const int M = L.M, H = L.H;
   int rc = MSF_OK;
@@ -779,6 +780,7 @@ static int forward_front(const Layout& L, const msf_fusion_call* c, const WsBf16
 
   }
 
+  if (projections_only) return MSF_OK;
   const bool use_chain = chain_eligible(H, M) && !getenv("MSF_NO_CHAIN");
   if (use_chain) {  // F2 + F3 chained per (window tile, query): U never leaves the SM on its way to out_proj
     ChainLaunch C;
@@ -1388,6 +1390,66 @@ int fusion_bf16_infer(const Layout& L, const msf_fusion_call* c, float* conf, in
   hl.conf = conf; hl.pred = reinterpret_cast<long long*>(pred);
   if ((rc = launch_head(L, c, ws, A, hl, st, "HEAD gating+classifier+softmax"))) return rc;
   return export_gates(L, c, ws, st);
+}
+
+// Inference for a subset of modalities that is present in EVERY row (the sweep of src/eval.py:342-404) with each
+// attention module's value_proj -> out_proj pair folded into one matrix.  Without dropout the attention gate of a
+// present key is 1 for every head, so out_proj(value_proj(P_k)) = P_k (Wo Wv)^T + (Wo bv + bo): per present query
+// ONE GEMM whose K-segments are the present keys, accumulated in TMEM, with the mean epilogue of the un-fused path —
+// half the FLOPs of the chained pair kernel and no U round trip.  `wov` = [pairs][H][H] bf16 (Wo Wv, row-major
+// [out][in]); `bias_sum` = [M][H] fp32, row q = sum over present keys of (Wo bv + bo) + sum over absent keys of bo.
+// flags bit 0: the projections P of the present modalities are still valid in the workspace (same features, an
+// earlier call of the sweep); bit 1: compute the projections only.
+int fusion_bf16_infer_folded(const Layout& L, const msf_fusion_call* c, const void* wov, const float* bias_sum,
+                             unsigned present, int flags, float* conf, int64_t* pred, cudaStream_t st) {
+  WsBf16 ws;
+  carve_bf16(L, c->batch, c->workspace, &ws);
+  int rc = check_ws(ws, c);
+  if (rc) return rc;
+  const int M = L.M, H = L.H;
+  MSF_REQUIRE(use_head(L) && chain_eligible(H, M), "folded inference pass not available for this shape");
+  MSF_REQUIRE(present != 0u && present < (1u << M), "msf_fusion_infer_folded: present must name at least one modality");
+  MSF_REQUIRE(c->mask != nullptr && c->attn_gates == nullptr, "msf_fusion_infer_folded needs the subset's mask and no gate export");
+  MSF_REQUIRE(!c->training, "msf_fusion_infer_folded is an inference pass (attention dropout makes the gates per head)");
+  const ArenaBf16 A = arena_layout(L);
+  const int64_t B = c->batch;
+  const long long BH = (long long)B * H;
+  if (!(flags & 1) && (rc = forward_front(L, c, ws, A, st, nullptr, present, true))) return rc;
+  if (flags & 2) return MSF_OK;
+  MSF_REQUIRE(wov != nullptr && bias_sum != nullptr && conf && pred, "msf_fusion_infer_folded: null argument");
+  {
+    const int bnH = block_n_for(H);
+    const int pairs = L.num_pairs();
+    TcBuilder tb(false, bnH, no_dropout(), st, "FOLD present keys -> aggregated tokens");
+    const short mapP = (short)tb.add_map(ws.P, B, H, H, M, BH, TC_BLOCK_M);
+    const short mapW = (short)tb.add_map(wov, H, H, H, pairs > 0 ? pairs : 1, (long long)H * H, bnH);
+    for (int q = 0; q < M; ++q) {
+      if (!((present >> q) & 1u)) continue;   // absent query: its token is zero through the row mask
+      TcProblem p = tc_blank_problem();
+      int seg = 0;
+      for (int k = 0; k < M; ++k) {
+        if (q == k || !L.has_pair(q, k) || !((present >> k) & 1u)) continue;
+        p.seg[seg].a_map = mapP; p.seg[seg].a_z = k;
+        p.seg[seg].b_map = mapW; p.seg[seg].b_z = L.pair_index(q, k);
+        ++seg;
+      }
+      p.M = (int)B; p.N = H; p.K = seg ? H : 0;
+      if (seg == 0) { p.seg[0].a_map = mapP; p.seg[0].b_map = mapW; seg = 1; }  // epilogue only
+      p.nseg = seg;
+      p.bias[0] = bias_sum + (long long)q * H;
+      p.C = ws.agg + (long long)q * BH; p.ldc = H; p.c_bf16 = 1;
+      p.epi = TC_EPI_OUT_MEAN; p.scale = (float)L.mean_count(q);
+      p.aux = ws.P + (long long)q * BH; p.ld_aux = H;
+      p.mask = c->mask; p.mask_ld = M; p.mask_col = q;
+      tb.add_problem(p);
+    }
+    if ((rc = tb.flush())) return rc;
+  }
+  HeadLaunch hl;
+  memset(&hl, 0, sizeof(hl));
+  hl.train = 0; hl.store_acts = 0;
+  hl.conf = conf; hl.pred = reinterpret_cast<long long*>(pred);
+  return launch_head(L, c, ws, A, hl, st, "HEAD gating+classifier+softmax");
 }
 
 bool fusion_bf16_head_fused(const Layout& L) { return use_head(L); }

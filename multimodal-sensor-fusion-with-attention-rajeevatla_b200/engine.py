@@ -135,6 +135,7 @@ class FusionEngine:
         self._packed_slots = False   # set by pinned_batch(): train_stream's input slots as one buffer each
         self._epoch_graphs = {}      # tuple of slots -> (graph over one step per slot, per-step losses)
         self._subset_masks = {}
+        self._fold_wov = None        # fold_for_inference(): Wo Wv per attention module, for infer_sweep
         self._copy_stream = None
         self.launches_per_step = 0
 
@@ -742,6 +743,99 @@ class FusionEngine:
                 self._subset_graphs[bits] = self._capture(lambda: self._enqueue_inference(bits))
             self._subset_graphs[bits].replay()
         return self.logits, self.conf, self.pred
+
+    def fold_for_inference(self) -> None:
+        """Fold every attention module's value_proj -> out_proj pair into one matrix for the subset sweep
+        (msf_fusion_infer_folded): Wov = Wo Wv (bf16 [pairs][H][H]) and cv = Wo bv + bo, from the CURRENT fp32 master
+        weights.  Call again after the weights change (training steps, load_state_dict)."""
+        plan, H, M = self.plan, self.plan.H, self.plan.M
+        names = plan.names
+        mods = self.model.attention_modules
+        wov = torch.zeros(M * (M - 1), H, H, dtype=torch.float32, device=self.dev)
+        self._fold_cv = torch.zeros(M, M, H, dtype=torch.float32, device=self.dev)   # [q][k]: Wo bv + bo
+        self._fold_bo = torch.zeros(M, M, H, dtype=torch.float32, device=self.dev)   # [q][k]: bo alone
+        with torch.no_grad():
+            for q in range(M):
+                for k in range(M):
+                    key = f"{names[q]}_to_{names[k]}"
+                    if q == k or key not in mods:
+                        continue
+                    att = mods[key]
+                    pi = q * (M - 1) + (k if k < q else k - 1)
+                    wo, wv = att.out_proj.weight.detach().float(), att.value_proj.weight.detach().float()
+                    wov[pi] = wo @ wv
+                    self._fold_cv[q, k] = wo @ att.value_proj.bias.detach().float() + att.out_proj.bias.detach().float()
+                    self._fold_bo[q, k] = att.out_proj.bias.detach().float()
+        self._fold_wov = wov.to(torch.bfloat16).contiguous()
+        self._fold_bias = {}
+        self._fold_graphs = {}
+
+    def _fold_bias_for(self, bits: int) -> torch.Tensor:
+        got = self._fold_bias.get(bits)
+        if got is None:
+            M = self.plan.M
+            pres = torch.tensor([(bits >> m) & 1 for m in range(M)], dtype=torch.float32, device=self.dev)
+            # row q: present keys contribute Wo bv + bo, absent keys their out_proj bias (attention gate 0)
+            got = (self._fold_cv * pres.view(1, M, 1) + self._fold_bo * (1.0 - pres).view(1, M, 1)).sum(1).contiguous()
+            self._fold_bias[bits] = got
+        return got
+
+    def _enqueue_inference_folded(self, bits: int, flags: int) -> None:
+        c = self._call(False)
+        c.logits = self.logits.data_ptr()
+        bias = self._fold_bias_for(bits)
+        N.check(N.lib().msf_fusion_infer_folded(ctypes_ref(self.plan.shape), ctypes_ref(c), self._fold_wov.data_ptr(),
+                                                bias.data_ptr(), bits, flags, self.conf.data_ptr(), self.pred.data_ptr(),
+                                                ops._stream()))
+
+    def infer_sweep(self, features, subsets: Sequence[Sequence[int]], on_subset=None):
+        """The missing-modality sweep of src/eval.py:342-404 over ONE batch: for every subset (modality indices present
+        in every window) logits / confidences / predictions as `infer_subset` gives them, with the work the subsets
+        share done once — the projections of all modalities are computed a single time, and every subset then costs
+        one folded pair GEMM (msf_fusion_infer_folded: value_proj and out_proj of each module as one matrix) plus
+        the head kernel.  `on_subset(index, subset)` runs after each subset on the same stream (e.g. eval_update /
+        ece_bins on self.logits).  `features=None` keeps the batch already in the static buffers."""
+        if self.prec != N.MSF_PREC_BF16:
+            raise N.MsfError("infer_sweep needs the tensor-core path (precision='bf16')")
+        if getattr(self, "_fold_wov", None) is None:
+            self.fold_for_inference()
+        M = self.plan.M
+        full = (1 << M) - 1
+        ones = self._subset_mask(full)
+        if features is not None:
+            self.load_batch(features, ones)
+        else:
+            self.mask.copy_(ones, non_blocking=True)
+        self._run_folded(full, N.MSF_FOLD_PROJECTIONS_ONLY)        # every modality projected once for the whole sweep
+        for i, sub in enumerate(subsets):
+            bits = 0
+            for m in sub:
+                bits |= 1 << int(m)
+            if bits == 0 or bits > full:
+                raise ValueError("every subset must name at least one valid modality")
+            self.mask.copy_(self._subset_mask(bits), non_blocking=True)
+            self._run_folded(bits, N.MSF_FOLD_REUSE_PROJECTIONS)
+            if on_subset is not None:
+                on_subset(i, sub)
+        return self.logits, self.conf, self.pred
+
+    def _subset_mask(self, bits: int) -> torch.Tensor:
+        mask = self._subset_masks.get(bits)
+        if mask is None:
+            mask = torch.zeros(self.batch, self.plan.M, dtype=torch.float32, device=self.dev)
+            mask[:, [m for m in range(self.plan.M) if (bits >> m) & 1]] = 1.0
+            self._subset_masks[bits] = mask
+        return mask
+
+    def _run_folded(self, bits: int, flags: int) -> None:
+        if not self.use_graph:
+            self._enqueue_inference_folded(bits, flags)
+            return
+        key = (bits, flags)
+        if key not in self._fold_graphs:
+            self._fold_bias_for(bits)   # allocate outside the capture
+            self._fold_graphs[key] = self._capture(lambda: self._enqueue_inference_folded(bits, flags))
+        self._fold_graphs[key].replay()
 
     def eval_update(self, labels: torch.Tensor, stats: Optional["ops.EvalStats"] = None) -> "ops.EvalStats":
         """Fold the last inference pass (self.logits) and its labels into device-side evaluation statistics

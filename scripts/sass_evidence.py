@@ -15,7 +15,7 @@ lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(
 sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
 PAT = [("UTC*MMA", re.compile(r"\bUTC\w*MMA\b")), ("LDTM", re.compile(r"\bLDTM\b")), ("STTM", re.compile(r"\bSTTM\b")),
        ("UTMALDG", re.compile(r"\bUTMALDG\b")), ("UTMASTG", re.compile(r"\bUTMASTG\b")),
-       ("UBLKCP", re.compile(r"\bUBLKCP\b")), ("HMMA", re.compile(r"\bHMMA\b")), ("RED/ATOM", re.compile(r"\b(REDG?|REDUX|ATOMG?|ATOMS)\b"))]
+       ("UBLKCP", re.compile(r"\bUBLKCP\b")), ("LDGMC", re.compile(r"\bLDGMC\b")), ("HMMA", re.compile(r"\bHMMA\b")), ("RED/ATOM", re.compile(r"\b(REDG?|REDUX|ATOMG?|ATOMS)\b"))]
 counts = collections.OrderedDict()
 name = None
 for line in sass.splitlines():
