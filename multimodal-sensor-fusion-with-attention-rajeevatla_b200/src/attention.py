@@ -32,7 +32,7 @@ from typing import Dict, Mapping, Optional, Sequence, Tuple
 import torch
 import torch.nn as nn
 
-_HERE = os.path.dirname(os.path.abspath(__file__))
+_HERE = os.path.dirname(os.path.realpath(__file__))   # realpath: src/ may be reached through a symlink
 _ROOT = os.path.dirname(os.path.dirname(_HERE))
 if _ROOT not in sys.path:
     sys.path.insert(0, _ROOT)
@@ -243,11 +243,12 @@ def visualize_attention(attention_weights, modality_names: Sequence[str], save_p
     plt.close(fig)
 
 
-# Simple test
 if __name__ == "__main__":
+    # Simple test
     print("Testing attention mechanisms...")
+    print("\nTesting CrossModalAttention...")
     try:
-        layer = CrossModalAttention(query_dim=512, key_dim=64)
+        layer = CrossModalAttention(query_dim=512, key_dim=64, hidden_dim=256, num_heads=4)
         a, b = torch.randn(4, 512), torch.randn(4, 64)
         out, w = layer(a, b, b)
         assert out.shape == (4, 256)
@@ -256,3 +257,14 @@ if __name__ == "__main__":
         print("✗ CrossModalAttention not implemented yet")
     except Exception as err:  # noqa: BLE001
         print(f"✗ CrossModalAttention error: {err}")
+    print("\nTesting TemporalAttention...")
+    try:
+        steps = TemporalAttention(128, 256, 4)
+        seq = torch.randn(4, 10, 128)
+        attended_seq, w = steps(seq)
+        assert attended_seq.shape == (4, 10, 256)
+        print(f"✓ TemporalAttention working! Output shape: {attended_seq.shape}")
+    except NotImplementedError:
+        print("✗ TemporalAttention not implemented yet")
+    except Exception as err:  # noqa: BLE001
+        print(f"✗ TemporalAttention error: {err}")

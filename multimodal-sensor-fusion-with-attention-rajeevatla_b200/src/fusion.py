@@ -29,10 +29,10 @@ import torch.nn as nn
 
 from attention import CrossModalAttention
 
-_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.realpath(__file__))))
 if _ROOT not in sys.path:
     sys.path.insert(0, _ROOT)
-_pkg = importlib.import_module(os.path.basename(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+_pkg = importlib.import_module(os.path.basename(os.path.dirname(os.path.dirname(os.path.realpath(__file__)))))
 ops = importlib.import_module(_pkg.__name__ + ".ops")
 
 

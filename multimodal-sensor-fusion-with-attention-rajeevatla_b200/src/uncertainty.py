@@ -27,7 +27,7 @@ from typing import Any, Dict, Tuple
 import numpy as np
 import torch
 
-_HERE = os.path.dirname(os.path.abspath(__file__))
+_HERE = os.path.dirname(os.path.realpath(__file__))   # realpath: src/ may be reached through a symlink
 _ROOT = os.path.dirname(os.path.dirname(_HERE))
 if _ROOT not in sys.path:
     sys.path.insert(0, _ROOT)
