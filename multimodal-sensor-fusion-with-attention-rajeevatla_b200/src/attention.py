@@ -221,7 +221,7 @@ def visualize_attention(attention_weights, modality_names: Sequence[str], save_p
         grid = grid.unsqueeze(0)
     while grid.dim() > 2:
         grid = grid.mean(dim=0)
-    values = grid.numpy()
+    values = np.atleast_2d(grid.numpy())    # a backend that hands back a squeezed vector still draws one row
     rows, cols = values.shape
     fig, ax = plt.subplots(figsize=(4 + 0.5 * cols, 4))
     image = ax.imshow(values, cmap="viridis", aspect="auto")
