@@ -401,13 +401,16 @@ int msf_attention_core_backward(const float* q, const float* k, const float* v, 
 
 /* ---- LSTM recurrence of SequenceEncoder (src/encoders.py:54-65,135-166) ------ */
 /* nn.LSTM(F, H, num_layers=1, batch_first=True) forward over T steps with zero initial state, bf16 operands /
- * fp32 accumulate and state, one grouped tensor-core launch per time step for up to MSF_LSTM_MAX_SEQS encoders
- * of the same batch, length and hidden size.  Operand layouts (prepared once per model / batch by the caller):
+ * fp32 accumulate and state, for up to MSF_LSTM_MAX_SEQS encoders of the same batch, length and hidden size.
+ * hidden <= 256: ONE persistent launch over all time steps (lstm_seq.cu: a cluster of hidden/64 CTAs per share of the
+ * windows, its W_hh / W_ih columns resident in shared memory, h exchanged through the L2 with one cluster barrier
+ * per step); otherwise one grouped tensor-core launch per time step.  Operand layouts (prepared once per model / batch by the caller):
  *   x_bf16  [T][B][64]        bf16, time-major, the F <= 64 features zero-padded to 64 columns
  *   w_hh    [H/64][4H][64]    bf16: row 4u+g = gate g (i,f,g,o) of hidden unit u, columns split into 64-wide k-blocks
  *   w_ih    [4H][64]          bf16: same row order, F columns zero-padded to 64
  *   bias    [4H]              fp32: bias_ih + bias_hh in the same row order
- *   h_a,h_b [H/64][B][64]     bf16 scratch; h_a holds h_0 (zeros);  cell [B][H] fp32: c_0 in (zeros), c_T out
+ *   h_a,h_b [H/64][B][64]     bf16 scratch; h_a holds h_0 (zeros);  cell B*H fp32: zeros on entry (c_0), scratch
+ *                             afterwards (c_T in an implementation-defined order)
  *   h_out   [B][H]            fp32: h_T (what SequenceEncoder feeds to its projection) */
 #define MSF_LSTM_MAX_SEQS 4
 typedef struct msf_lstm_seq {

@@ -12,6 +12,11 @@
 
 #include "tc_gemm.cuh"
 
+namespace msf {
+bool lstm_seq_eligible(int hidden, int n, long long batch, int sms);   // lstm_seq.cu: one persistent launch
+int lstm_seq_launch(const msf_lstm_seq* seqs, int n, long long batch, int steps, int hidden, cudaStream_t st);
+}  // namespace msf
+
 extern "C" int msf_lstm_forward(const msf_lstm_seq* seqs, int32_t n, int64_t batch, int32_t steps, int32_t hidden,
                                 void* stream) {
   using namespace msf;
@@ -21,6 +26,16 @@ extern "C" int msf_lstm_forward(const msf_lstm_seq* seqs, int32_t n, int64_t bat
   const int KBH = hidden / 64;
   MSF_REQUIRE(KBH + 1 <= TC_MAX_SEG, "msf_lstm_forward: hidden %d needs too many K-segments", hidden);
   cudaStream_t st = (cudaStream_t)stream;
+  {   // hidden <= 256: the whole sequence as one persistent launch, weights resident in shared memory (lstm_seq.cu);
+      // MSF_LSTM_STEPS=1 keeps the launch-per-step path below
+    static int sms = 0;
+    if (sms == 0) {
+      int dev = 0;
+      MSF_CHECK_CUDA(cudaGetDevice(&dev));
+      MSF_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    if (lstm_seq_eligible(hidden, n, batch, sms)) return lstm_seq_launch(seqs, n, batch, steps, hidden, st);
+  }
   const long long B = batch, N4 = 4LL * hidden, slice = B * 64;
   // two launch descriptions: even steps read h_a / write h_b, odd steps the other way round
   TcBuilder even(false, 256, no_dropout(), st, "LSTM step"), odd(false, 256, no_dropout(), st, "LSTM step");

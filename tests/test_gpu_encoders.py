@@ -77,12 +77,21 @@ def test_frame_encoder_shapes_and_masking():
     assert torch.allclose(enc(frames2, mask)[0], out[0], atol=1e-6)
 
 
-@pytest.mark.parametrize("batch,steps,feat,hidden", [(5, 7, 17, 64), (300, 96, 17, 256), (130, 1024, 1, 256)])
-def test_tensor_core_lstm_matches_oracle(batch, steps, feat, hidden):
-    """msf_lstm_forward (bf16 operands, fp32 accumulate / state, one tcgen05 launch per step) against the
+@pytest.mark.parametrize("batch,steps,feat,hidden", [(5, 7, 17, 64), (300, 96, 17, 256), (130, 1024, 1, 256),
+                                                      (2500, 33, 17, 256), (700, 20, 64, 128), (129, 12, 17, 384)])
+@pytest.mark.parametrize("path", ["sequence", "steps"])
+def test_tensor_core_lstm_matches_oracle(batch, steps, feat, hidden, path, monkeypatch):
+    """msf_lstm_forward (bf16 operands, fp32 accumulate / state) against the fp32 CPU oracle — both implementations:
+    "sequence" = ONE persistent launch over all steps, a cluster of hidden / 64 CTAs with the weights resident in
+    shared memory (lstm_seq.cu; hidden <= 256, several window tiles per cluster at batch 2500), "steps" = one grouped
+    tcgen05 launch per step (lstm.cu, also what hidden 384 takes) against the
     fp32 CPU oracle of the reference's nn.LSTM call (src/encoders.py:135-166).  Tolerance of the bf16
     path (BASELINE north_star): max-abs <= 1e-2 on h_T and on the encoder output."""
     from oracle import encoder_oracle
+    if path == "steps":
+        monkeypatch.setenv("MSF_LSTM_STEPS", "1")
+    elif hidden > 256:
+        pytest.skip("the persistent kernel covers hidden <= 256")
     torch.manual_seed(3)
     enc = dropin_encoders.SequenceEncoder(feat, hidden_dim=hidden, output_dim=128, num_layers=1, encoder_type="lstm",
                                           dropout=0.0).eval()
