@@ -23,6 +23,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cuda_fp16.h>
+
 #include "tc_gemm.cuh"
 #include "tc_ptx.cuh"
 
@@ -69,6 +71,14 @@ __device__ __forceinline__ float ls_tanh(float x) {
   return y;
 }
 __device__ __forceinline__ float ls_sigmoid(float x) { return fmaf(0.5f, ls_tanh(0.5f * x), 0.5f); }
+// Two activations per MUFU operation: tanh.approx.f16x2 on a packed pair (fp16 in / out: 2^-11 relative, the size of
+// the bf16 rounding h gets every step anyway).  The cell state itself stays fp32.
+__device__ __forceinline__ float2 ls_tanh2(float lo, float hi) {
+  __half2 p = __floats2half2_rn(lo, hi);
+  uint32_t r, in = *reinterpret_cast<uint32_t*>(&p);
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(r) : "r"(in));
+  return __half22float2(*reinterpret_cast<__half2*>(&r));
+}
 // Cell state: fp32, one 128-window tile after the other; inside a full tile unit-group-major ([H/4][128][4]) so that a
 // warp's access (32 windows x 4 units) is one contiguous 512-byte run; a ragged last tile stays window-major.
 __device__ __forceinline__ long long ls_cell_index(int tile, int r, int u, int H, bool ragged) {
@@ -129,7 +139,9 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
   }
   if (warp >= 4) {
     const int et = threadIdx.x - 128;
-    if (et < 256) bias_s[et] = L.bias[seq] ? __ldg(L.bias[seq] + rank * 256 + et) : 0.0f;
+    // gate order i, f, g, o per unit; sigmoid(x) = 0.5 + 0.5 tanh(x / 2): the input and output gates' and the forget
+    // gate's pre-activations are halved on the way in (acc * 0.5 + bias / 2), so their bias is stored halved
+    if (et < 256) bias_s[et] = (L.bias[seq] ? __ldg(L.bias[seq] + rank * 256 + et) : 0.0f) * ((et & 3) == 2 ? 1.0f : 0.5f);
   }
   tc_fence_before();
   __syncthreads();
@@ -164,16 +176,26 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
     if (warp == 0) {
       // ===== TMA producer: [h_{t-1} | x_t] of every tile of this cluster =====
       if (lane == 0) {
+        // per tile: x_t first (it does not depend on the previous step: the first tile's x_t was requested before the
+        // step barrier, at the end of the previous step), then the k-blocks of h_{t-1}
+        auto load_x = [&](int tt, int i) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), LS_A_BYTES);
+          tma_load_3d(ring_base + stage * LS_A_BYTES, &M.x, 0, (slot + i * L.cps) * 128, tt, full_bar(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        };
+        if (t == 0) load_x(0, 0);
         for (int i = 0; i < my_tiles; ++i) {
           const int row0 = (slot + i * L.cps) * 128;
-          for (int kb = 0; kb < NKB; ++kb) {
+          if (i > 0) load_x(t, i);
+          for (int kb = 0; kb < KBH; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             mbar_expect_tx(full_bar(stage), LS_A_BYTES);
-            if (kb < KBH) tma_load_3d(ring_base + stage * LS_A_BYTES, &M.h[par], 0, row0, kb, full_bar(stage));
-            else tma_load_3d(ring_base + stage * LS_A_BYTES, &M.x, 0, row0, t, full_bar(stage));
+            tma_load_3d(ring_base + stage * LS_A_BYTES, &M.h[par], 0, row0, kb, full_bar(stage));
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
+        if (t + 1 < L.steps) load_x(t + 1, 0);
         if (stamp) g_ls_stamps[0] += clock64() - t_step;
       }
     } else if (warp == 1) {
@@ -184,14 +206,15 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
           mbar_wait(acc_empty(acc), ((cnt >> 1) & 1u) ^ 1u);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
-          for (int kb = 0; kb < NKB; ++kb) {
+          for (int kk = 0; kk < NKB; ++kk) {
+            const int kb = kk == 0 ? KBH : kk - 1;   // the producer's order: x_t, then the k-blocks of h_{t-1}
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
             const uint32_t a_addr = ring_base + stage * LS_A_BYTES, b_addr = w_base + kb * LS_W_BYTES;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               tc_mma_bf16(d_tmem, smem_desc(a_addr + k * 32, 16, 1024), smem_desc(b_addr + k * 32, 16, 1024), idesc,
-                          (kb > 0 || k > 0) ? 1u : 0u);
+                          (kk > 0 || k > 0) ? 1u : 0u);
             tc_commit(empty_bar(stage));
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
@@ -229,16 +252,21 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
           tmem_ld16_issue(taddr + (uint32_t)(16 * g), a);
           tmem_wait16(a);
           const float cp[4] = {cprev[g].x, cprev[g].y, cprev[g].z, cprev[g].w};
-          float cn[4], hn[4];
+          float cn[4], hn[4], go[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cg * 64 + 16 * g + 4 * j);
-            const float gi = ls_sigmoid(__uint_as_float(a[4 * j + 0]) + b4.x);
-            const float gf = ls_sigmoid(__uint_as_float(a[4 * j + 1]) + b4.y);
-            const float gg = ls_tanh(__uint_as_float(a[4 * j + 2]) + b4.z);
-            const float go = ls_sigmoid(__uint_as_float(a[4 * j + 3]) + b4.w);
-            cn[j] = gf * cp[j] + gi * gg;
-            hn[j] = go * ls_tanh(cn[j]);
+            const float2 t_if = ls_tanh2(fmaf(__uint_as_float(a[4 * j + 0]), 0.5f, b4.x), fmaf(__uint_as_float(a[4 * j + 1]), 0.5f, b4.y));
+            const float2 t_go = ls_tanh2(__uint_as_float(a[4 * j + 2]) + b4.z, fmaf(__uint_as_float(a[4 * j + 3]), 0.5f, b4.w));
+            const float gi = fmaf(0.5f, t_if.x, 0.5f), gf = fmaf(0.5f, t_if.y, 0.5f);
+            go[j] = fmaf(0.5f, t_go.y, 0.5f);
+            cn[j] = fmaf(gf, cp[j], gi * t_go.x);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; j += 2) {
+            const float2 tc = ls_tanh2(cn[j], cn[j + 1]);
+            hn[j] = go[j] * tc.x;
+            hn[j + 1] = go[j + 1] * tc.y;
           }
           const int u0 = ubase + 4 * g;
           if (cell_io)
