@@ -411,7 +411,10 @@ int msf_attention_core_backward(const float* q, const float* k, const float* v, 
  *   bias    [4H]              fp32: bias_ih + bias_hh in the same row order
  *   h_a,h_b [H/64][B][64]     bf16 scratch; h_a holds h_0 (zeros);  cell B*H fp32: zeros on entry (c_0), scratch
  *                             afterwards (c_T in an implementation-defined order)
- *   h_out   [B][H]            fp32: h_T (what SequenceEncoder feeds to its projection) */
+ *   h_out   [B][H]            fp32: h_T (what SequenceEncoder feeds to its projection)
+ *   lengths [B] int32 or NULL  valid steps per window (1..T): the state of a window stops after its last valid step,
+ *                             as with pack_padded_sequence (src/encoders.py:140-152); h_out is then the state at that
+ *                             step.  Persistent kernel only (hidden <= 256), MSF_E_UNSUPPORTED otherwise. */
 #define MSF_LSTM_MAX_SEQS 4
 typedef struct msf_lstm_seq {
   const void* x_bf16;
@@ -422,6 +425,7 @@ typedef struct msf_lstm_seq {
   void* h_b;
   float* cell;
   float* h_out;
+  const int32_t* lengths;
 } msf_lstm_seq;
 int msf_lstm_forward(const msf_lstm_seq* seqs, int32_t n, int64_t batch, int32_t steps, int32_t hidden, void* stream);
 

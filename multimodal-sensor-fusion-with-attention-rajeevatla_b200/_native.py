@@ -91,7 +91,7 @@ class DpzComm(Structure):  # msf_dpz_comm
 class LstmSeq(ctypes.Structure):  # msf_lstm_seq
     _fields_ = [
         ("x_bf16", c_void_p), ("w_hh", c_void_p), ("w_ih", c_void_p), ("bias", c_void_p),
-        ("h_a", c_void_p), ("h_b", c_void_p), ("cell", c_void_p), ("h_out", c_void_p),
+        ("h_a", c_void_p), ("h_b", c_void_p), ("cell", c_void_p), ("h_out", c_void_p), ("lengths", c_void_p),
     ]
 
 

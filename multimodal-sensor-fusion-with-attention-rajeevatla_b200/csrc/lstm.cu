@@ -35,6 +35,11 @@ extern "C" int msf_lstm_forward(const msf_lstm_seq* seqs, int32_t n, int64_t bat
       MSF_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
     if (lstm_seq_eligible(hidden, n, batch, sms)) return lstm_seq_launch(seqs, n, batch, steps, hidden, st);
+    for (int i = 0; i < n; ++i)
+      if (seqs[i].lengths != nullptr) {
+        set_error("msf_lstm_forward: per-window lengths need the persistent kernel (hidden <= 256, MSF_LSTM_STEPS unset)");
+        return MSF_E_UNSUPPORTED;
+      }
   }
   const long long B = batch, N4 = 4LL * hidden, slice = B * 64;
   // two launch descriptions: even steps read h_a / write h_b, odd steps the other way round

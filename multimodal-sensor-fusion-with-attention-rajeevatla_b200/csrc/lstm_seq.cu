@@ -49,6 +49,7 @@ struct LstmSeqLaunch {
   void* hbuf[MSF_LSTM_MAX_SEQS][2];
   float* cell[MSF_LSTM_MAX_SEQS];
   float* h_out[MSF_LSTM_MAX_SEQS];
+  const int* lengths[MSF_LSTM_MAX_SEQS];   // valid steps per window, or nullptr (all steps)
   int n, rows, steps, hidden, kbh, cs, cps, row_tiles, stages;
   int dbg;   // MSF_LSTM_DBG: 1 no async-proxy fence, 2 no __threadfence, 8 no cell-state traffic, 16 stamps
   long long h_slice;
@@ -226,7 +227,9 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
       // ===== epilogue: LSTM cell on this CTA's 64 hidden units (16 per warp: 64 accumulator columns) =====
       __nv_bfloat16* h_next = reinterpret_cast<__nv_bfloat16*>(L.hbuf[seq][par ^ 1]);
       float* cellp = L.cell[seq];
-      float* h32 = (t == L.steps - 1) ? L.h_out[seq] : nullptr;
+      const __nv_bfloat16* h_prev = reinterpret_cast<const __nv_bfloat16*>(L.hbuf[seq][par]);
+      const int* lens = L.lengths[seq];
+      float* h32 = L.h_out[seq];
       for (int i = 0; i < my_tiles; ++i, ++cnt) {
         const int acc = (int)(cnt & 1u);
         const int tile = slot + i * L.cps;
@@ -235,7 +238,11 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
         const bool ragged = (tile + 1) * 128 > L.rows;
         const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)acc * 256u + (uint32_t)(cg * 64);
         const int ubase = rank * 64 + cg * 16;   // first hidden unit of this thread's 16
-        const bool cell_io = row_ok && !(L.dbg & 8);
+        // pack_padded_sequence semantics: a window's state stops after its last valid step (src/encoders.py:140-152)
+        const int len = (lens != nullptr && row_ok) ? __ldg(lens + row) : L.steps;
+        const bool live = t < len;           // this step still belongs to the window
+        const bool last_live = t == len - 1;  // its final hidden state is the one of this step
+        const bool cell_io = row_ok && live && !(L.dbg & 8);
         // the previous cell state is fetched before the accumulator is ready
         float4 cprev[4];
 #pragma unroll
@@ -274,14 +281,21 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
           __nv_bfloat162 p0 = __floats2bfloat162_rn(hn[0], hn[1]), p1 = __floats2bfloat162_rn(hn[2], hn[3]);
           hp[2 * g] = *reinterpret_cast<uint32_t*>(&p0);
           hp[2 * g + 1] = *reinterpret_cast<uint32_t*>(&p1);
-          if (h32 != nullptr && row_ok)
+          if (last_live && row_ok)
             *reinterpret_cast<float4*>(h32 + (long long)row * H + u0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
         }
         tc_fence_before();
         if (row_ok) {   // k-block (ubase >> 6) = this CTA's rank of [H/64][B][64]
-          uint4* dst = reinterpret_cast<uint4*>(h_next + (long long)(ubase >> 6) * L.h_slice + (long long)row * 64 + (ubase & 63));
-          dst[0] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-          dst[1] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+          const long long off = (long long)(ubase >> 6) * L.h_slice + (long long)row * 64 + (ubase & 63);
+          uint4* dst = reinterpret_cast<uint4*>(h_next + off);
+          if (live) {
+            dst[0] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+            dst[1] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+          } else {   // finished window: carry its hidden state forward unchanged
+            const uint4* src = reinterpret_cast<const uint4*>(h_prev + off);
+            dst[0] = src[0];
+            dst[1] = src[1];
+          }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty(acc));
@@ -370,6 +384,7 @@ int lstm_seq_launch(const msf_lstm_seq* seqs, int n, long long batch, int steps,
     L.bias[i] = S.bias;
     L.hbuf[i][0] = S.h_a; L.hbuf[i][1] = S.h_b;
     L.cell[i] = S.cell; L.h_out[i] = S.h_out;
+    L.lengths[i] = S.lengths;
   }
   const size_t fixed = 1024 + LS_BIAS_OFF + 256 * 4 + 64;
   const size_t weights = (size_t)(L.kbh + 1) * LS_W_BYTES;

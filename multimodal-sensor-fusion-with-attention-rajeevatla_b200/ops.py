@@ -739,10 +739,13 @@ def lstm_pack_input(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def lstm_forward(xs: Sequence[torch.Tensor], packed: Sequence[tuple], hidden: int) -> List[torch.Tensor]:
+def lstm_forward(xs: Sequence[torch.Tensor], packed: Sequence[tuple], hidden: int,
+                 lengths: Optional[Sequence[Optional[torch.Tensor]]] = None) -> List[torch.Tensor]:
     """``h_T`` (fp32, (B, hidden)) of up to 4 single-layer LSTM encoders over packed inputs ``xs``
     (``lstm_pack_input``) with packed weights (``lstm_pack_weights``): one tensor-core launch per time step
-    for all of them (msf_lstm_forward)."""
+    for all of them (msf_lstm_forward); hidden <= 256: one persistent launch over all steps.  ``lengths``: per
+    encoder an integer tensor (B,) of valid steps (1..T) or None — the state stops after a window's last valid step,
+    as ``pack_padded_sequence`` makes nn.LSTM do (src/encoders.py:140-152)."""
     require_cuda("lstm_forward")
     n = len(xs)
     T, B, _ = xs[0].shape
@@ -759,6 +762,12 @@ def lstm_forward(xs: Sequence[torch.Tensor], packed: Sequence[tuple], hidden: in
         outs.append(h_out)
         seqs[i].x_bf16, seqs[i].w_hh, seqs[i].w_ih, seqs[i].bias = _p(x), _p(w_hh), _p(w_ih), _p(bias)
         seqs[i].h_a, seqs[i].h_b, seqs[i].cell, seqs[i].h_out = _p(h_a), _p(h_b), _p(cell), _p(h_out)
+        if lengths is not None and lengths[i] is not None:
+            ln = lengths[i].to(device=dev, dtype=torch.int32).contiguous()
+            if ln.numel() != B or int(ln.min()) < 1 or int(ln.max()) > T:
+                raise N.MsfError(f"lengths must be {B} integers in [1, {T}]")
+            keep.append(ln)
+            seqs[i].lengths = _p(ln)
     N.check(N.lib().msf_lstm_forward(seqs, n, B, T, hidden, _stream()))
     for t in keep:   # the launches are asynchronous: keep the scratch alive on this stream
         t.record_stream(torch.cuda.current_stream(dev))

@@ -54,20 +54,24 @@ def _dense(layer: nn.Module, x: torch.Tensor, relu: bool = False) -> torch.Tenso
 def _lstm_tensor_core_ok(enc, sequence: torch.Tensor, lengths) -> bool:
     """The hand-written recurrence (msf_lstm_forward: bf16 operands, fp32 state, <= 1e-2) is used for
     inference when the caller opted into bf16 (``encoder.precision = "bf16"`` or MSF_PRECISION=bf16):
-    single-layer LSTM, no packing, CUDA input, hidden % 64 == 0, input_dim <= 64, no gradient wanted."""
+    single-layer LSTM, CUDA input, hidden % 64 == 0, input_dim <= 64, no gradient wanted; per-window ``lengths``
+    (the reference packs ragged windows, src/encoders.py:140-152) on the persistent kernel (hidden <= 256)."""
     prec = getattr(enc, "precision", None) or os.environ.get("MSF_PRECISION", "fp32")
     rnn = enc.rnn
-    return (prec == "bf16" and enc.encoder_type == "lstm" and lengths is None and sequence.is_cuda
+    if lengths is not None and rnn.hidden_size > 256:
+        return False   # per-window lengths: persistent kernel only (lstm_seq.cu)
+    return (prec == "bf16" and enc.encoder_type == "lstm" and sequence.is_cuda
             and isinstance(rnn, nn.LSTM) and rnn.num_layers == 1 and not rnn.bidirectional and rnn.proj_size == 0
             and rnn.hidden_size % 64 == 0 and rnn.input_size <= 64
             and not (torch.is_grad_enabled() and (sequence.requires_grad or any(p.requires_grad for p in rnn.parameters()))))
 
 
-def _lstm_tensor_core(rnn: nn.LSTM, sequence: torch.Tensor) -> torch.Tensor:
+def _lstm_tensor_core(rnn: nn.LSTM, sequence: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
     packed = ops.lstm_pack_weights(rnn.weight_ih_l0, rnn.weight_hh_l0, getattr(rnn, "bias_ih_l0", None),
                                    getattr(rnn, "bias_hh_l0", None))
     with torch.cuda.device(sequence.device):
-        return ops.lstm_forward([ops.lstm_pack_input(sequence.to(torch.float32))], [packed], rnn.hidden_size)[0]
+        return ops.lstm_forward([ops.lstm_pack_input(sequence.to(torch.float32))], [packed], rnn.hidden_size,
+                                None if lengths is None else [lengths])[0]
 
 
 def _rnn_fp32(rnn: nn.Module, inp):
@@ -173,7 +177,7 @@ class SequenceEncoder(nn.Module):
             if self.rnn is None:
                 raise RuntimeError("RNN module not initialized.")
             if _lstm_tensor_core_ok(self, sequence, lengths):
-                last = _lstm_tensor_core(self.rnn, sequence).to(sequence.dtype)
+                last = _lstm_tensor_core(self.rnn, sequence, lengths).to(sequence.dtype)
                 return _dense(self.projection, self.dropout_layer(last))
             if lengths is not None:  # ragged windows: pack, like encoders.py:141-156
                 lens = lengths.to(device=sequence.device).to(torch.int64).cpu()

@@ -114,6 +114,40 @@ def test_tensor_core_lstm_matches_oracle(batch, steps, feat, hidden, path, monke
         assert _maxabs(enc(x.cuda()), ref_out) <= 2e-4
 
 
+@pytest.mark.parametrize("batch,steps,feat,hidden", [(37, 9, 17, 64), (300, 40, 17, 256), (2500, 21, 3, 128)])
+def test_tensor_core_lstm_ragged_windows(batch, steps, feat, hidden):
+    """Per-window ``lengths`` on the persistent kernel: the state of a window stops after its last valid step, which
+    is what the reference's pack_padded_sequence call does (src/encoders.py:140-152); against the fp32 CPU oracle
+    (oracle/encoder_oracle.py:lstm_last_hidden with lengths), max-abs <= 1e-2.  Steps behind a window's length must
+    not influence it at all (bit-identical result when they are overwritten)."""
+    from oracle import encoder_oracle
+    torch.manual_seed(5)
+    enc = dropin_encoders.SequenceEncoder(feat, hidden_dim=hidden, output_dim=128, num_layers=1, encoder_type="lstm",
+                                          dropout=0.0).eval()
+    gen = torch.Generator().manual_seed(6)
+    x = torch.randn(batch, steps, feat, generator=gen)
+    lengths = torch.randint(1, steps + 1, (batch,), generator=gen)
+    lengths[0], lengths[-1] = steps, 1
+    sd = {k: v.detach().clone() for k, v in enc.state_dict().items()}
+    ref_h = encoder_oracle.lstm_last_hidden(sd, "rnn", x, 1, lengths)
+    ref_out = ref_h @ sd["projection.weight"].t() + sd["projection.bias"]
+    enc = enc.cuda()
+    enc.precision = "bf16"
+    with torch.no_grad():
+        h = dropin_encoders._lstm_tensor_core(enc.rnn, x.cuda(), lengths.cuda())
+        out = enc(x.cuda(), lengths.cuda())
+        x2 = x.clone()
+        for b in range(batch):
+            x2[b, int(lengths[b]):] = 50.0
+        h2 = dropin_encoders._lstm_tensor_core(enc.rnn, x2.cuda(), lengths.cuda())
+    assert torch.isfinite(h).all()
+    assert _maxabs(h, ref_h) <= 1e-2
+    assert _maxabs(out, ref_out) <= 1e-2
+    assert torch.equal(h, h2)
+    with pytest.raises(Exception):
+        dropin_encoders._lstm_tensor_core(enc.rnn, x.cuda(), torch.zeros(batch, dtype=torch.int64))
+
+
 @pytest.mark.parametrize("pool", ["attention", "average", "max"])
 def test_frame_encoder_matches_reference_golden(pool):
     """FrameEncoder (src/encoders.py:211-336) against the unmodified reference: all three temporal poolings, with and
