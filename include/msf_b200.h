@@ -426,8 +426,33 @@ typedef struct msf_lstm_seq {
   float* cell;
   float* h_out;
   const int32_t* lengths;
+  /* training mode (all NULL for inference): set by the caller of msf_lstm_forward when msf_lstm_backward follows */
+  void* h_all;           /* [T+1][B][H] bf16: hidden state BEFORE step t at [t]; [0] zeros on entry (h_a, h_b, cell unused) */
+  void* gates;           /* [T][B][4H] bf16, columns 4u+g: gate activations after the forward pass, gradients of the
+                            gate pre-activations after the backward pass (in place) */
+  float* c_all;          /* [T][B*H] fp32: cell state after every step (implementation-defined order inside a step) */
+  /* msf_lstm_backward only */
+  const void* w_hh_t;    /* [H][4H] bf16: recurrent weights transposed, w_hh_t[n][4u+g] = weight_hh[g*H+u][n] */
+  const float* d_h_out;  /* [B][H] fp32: gradient of the loss with respect to h_out */
+  float* dc;             /* [B*H] fp32 scratch, ZERO on entry */
+  float* partial;        /* fp32 scratch, msf_lstm_backward_scratch_bytes() */
+  float* d_w_ih;         /* [4H][F] fp32, nn.LSTM row order (gate-major): gradient of weight_ih_l0 */
+  float* d_w_hh;         /* [4H][H] fp32: gradient of weight_hh_l0 */
+  float* d_bias;         /* [4H]    fp32: gradient of bias_ih_l0 (= that of bias_hh_l0) */
 } msf_lstm_seq;
 int msf_lstm_forward(const msf_lstm_seq* seqs, int32_t n, int64_t batch, int32_t steps, int32_t hidden, void* stream);
+
+/* Backward pass of the recurrence (training mode of SequenceEncoder, src/encoders.py:135-166 under autograd): given
+ * d_h_out and what msf_lstm_forward kept (h_all, gates, c_all), ONE persistent launch walks the steps backwards
+ * (lstm_bwd.cu: d h_{t-1} = d a_t W_hh on tcgen05 with this CTA's rows of W_hh^T resident in shared memory, the cell
+ * backward in the epilogue, d a_t written over the gate activations), then the weight gradients
+ * d W_hh = sum_t d a_t^T h_{t-1}, d W_ih = sum_t d a_t^T x_t are tensor-core GEMMs contracting over (t, window), split
+ * over chunks of steps, and one reduction kernel sums the chunks into nn.LSTM's layout.  The bias gradient is the
+ * column `features` of d W_ih: the caller stores 1.0 in column `features` of x_bf16 (features <= 63) whose weight
+ * column is zero.  No gradient with respect to x (the encoders' inputs are data).  hidden <= 256. */
+int msf_lstm_backward_scratch_bytes(int64_t batch, int32_t steps, int32_t hidden, size_t* bytes);
+int msf_lstm_backward(const msf_lstm_seq* seqs, int32_t n, int64_t batch, int32_t steps, int32_t hidden,
+                      int32_t features, void* stream);
 
 /* ---- BatchNorm1d -> ReLU -> Dropout behind a Linear layer (src/encoders.py:339-397, BatchNorm at :374-375) ----- */
 /* out = dropout(relu((y - mean) * invstd * gamma + beta)) over y (rows x cols, row-major fp32: the Linear output).

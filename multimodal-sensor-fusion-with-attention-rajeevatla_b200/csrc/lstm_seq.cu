@@ -50,6 +50,10 @@ struct LstmSeqLaunch {
   float* cell[MSF_LSTM_MAX_SEQS];
   float* h_out[MSF_LSTM_MAX_SEQS];
   const int* lengths[MSF_LSTM_MAX_SEQS];   // valid steps per window, or nullptr (all steps)
+  // training mode (SAVE): hbuf[.][0] = h_all [T+1][B][H] (m[.].h[0] over it), every step's gate activations and cell
+  // state are kept for the backward pass (lstm_bwd.cu)
+  __nv_bfloat16* gates[MSF_LSTM_MAX_SEQS];   // [T][B][4H] bf16, columns gate-interleaved (4u + {i,f,g,o})
+  float* c_all[MSF_LSTM_MAX_SEQS];           // [T][B*H] fp32, each step in the cell layout below
   int n, rows, steps, hidden, kbh, cs, cps, row_tiles, stages;
   int dbg;   // MSF_LSTM_DBG: 1 no async-proxy fence, 2 no __threadfence, 8 no cell-state traffic, 16 stamps
   long long h_slice;
@@ -91,6 +95,7 @@ __device__ __forceinline__ long long ls_cell_index(int tile, int r, int u, int H
 // [2] -> accumulators complete (epilogue warp 4 sees the last tile), [3] -> epilogue done, [4] -> cluster barrier passed
 __device__ long long g_ls_stamps[8];
 
+template <bool SAVE>
 __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_constant__ LstmSeqLaunch L) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t off0 = smem_u32(smem_raw);
@@ -118,7 +123,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&M.x);
     tma_prefetch_desc(&M.h[0]);
-    tma_prefetch_desc(&M.h[1]);
+    if (!SAVE) tma_prefetch_desc(&M.h[1]);
     tma_prefetch_desc(&M.whh);
     tma_prefetch_desc(&M.wih);
   }
@@ -192,7 +197,8 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
           for (int kb = 0; kb < KBH; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             mbar_expect_tx(full_bar(stage), LS_A_BYTES);
-            tma_load_3d(ring_base + stage * LS_A_BYTES, &M.h[par], 0, row0, kb, full_bar(stage));
+            if (SAVE) tma_load_3d(ring_base + stage * LS_A_BYTES, &M.h[0], kb * 64, row0, t, full_bar(stage));
+            else tma_load_3d(ring_base + stage * LS_A_BYTES, &M.h[par], 0, row0, kb, full_bar(stage));
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -225,9 +231,15 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
       }
     } else if (warp >= 4) {
       // ===== epilogue: LSTM cell on this CTA's 64 hidden units (16 per warp: 64 accumulator columns) =====
-      __nv_bfloat16* h_next = reinterpret_cast<__nv_bfloat16*>(L.hbuf[seq][par ^ 1]);
-      float* cellp = L.cell[seq];
-      const __nv_bfloat16* h_prev = reinterpret_cast<const __nv_bfloat16*>(L.hbuf[seq][par]);
+      const long long BH = (long long)L.rows * L.hidden;
+      __nv_bfloat16* h_next = SAVE ? reinterpret_cast<__nv_bfloat16*>(L.hbuf[seq][0]) + (long long)(t + 1) * BH
+                                   : reinterpret_cast<__nv_bfloat16*>(L.hbuf[seq][par ^ 1]);
+      const __nv_bfloat16* h_prev = SAVE ? reinterpret_cast<const __nv_bfloat16*>(L.hbuf[seq][0]) + (long long)t * BH
+                                         : reinterpret_cast<const __nv_bfloat16*>(L.hbuf[seq][par]);
+      // SAVE: c_{t-1} is read from step t-1's slice (zeros at t = 0) and c_t goes to step t's
+      float* cellp = SAVE ? L.c_all[seq] + (long long)t * BH : L.cell[seq];
+      const float* cell_prev = SAVE ? cellp - BH : cellp;
+      __nv_bfloat16* gates_t = SAVE ? L.gates[seq] + (long long)t * BH * 4 : nullptr;
       const int* lens = L.lengths[seq];
       float* h32 = L.h_out[seq];
       for (int i = 0; i < my_tiles; ++i, ++cnt) {
@@ -247,8 +259,9 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
         float4 cprev[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g)
-          cprev[g] = cell_io ? *reinterpret_cast<const float4*>(cellp + ls_cell_index(tile, r, ubase + 4 * g, H, ragged))
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
+          cprev[g] = (cell_io && !(SAVE && t == 0))
+                         ? *reinterpret_cast<const float4*>(cell_prev + ls_cell_index(tile, r, ubase + 4 * g, H, ragged))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
         mbar_wait(acc_full(acc), (cnt >> 1) & 1u);
         tc_fence_after();
         if (stamp && warp == 4 && i == my_tiles - 1) g_ls_stamps[2] += clock64() - t_step;
@@ -260,6 +273,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
           tmem_wait16(a);
           const float cp[4] = {cprev[g].x, cprev[g].y, cprev[g].z, cprev[g].w};
           float cn[4], hn[4], go[4];
+          uint32_t gs[8];   // SAVE: the 16 gate activations of these 4 units as bf16 pairs (i,f | g,o per unit)
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cg * 64 + 16 * g + 4 * j);
@@ -268,6 +282,11 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
             const float gi = fmaf(0.5f, t_if.x, 0.5f), gf = fmaf(0.5f, t_if.y, 0.5f);
             go[j] = fmaf(0.5f, t_go.y, 0.5f);
             cn[j] = fmaf(gf, cp[j], gi * t_go.x);
+            if (SAVE) {
+              __nv_bfloat162 s0 = __floats2bfloat162_rn(gi, gf), s1 = __floats2bfloat162_rn(t_go.x, go[j]);
+              gs[2 * j] = *reinterpret_cast<uint32_t*>(&s0);
+              gs[2 * j + 1] = *reinterpret_cast<uint32_t*>(&s1);
+            }
           }
 #pragma unroll
           for (int j = 0; j < 4; j += 2) {
@@ -278,6 +297,11 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
           const int u0 = ubase + 4 * g;
           if (cell_io)
             *reinterpret_cast<float4*>(cellp + ls_cell_index(tile, r, u0, H, ragged)) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+          if (SAVE && cell_io) {
+            uint4* gd = reinterpret_cast<uint4*>(gates_t + (long long)row * 4 * H + 4 * u0);
+            gd[0] = make_uint4(gs[0], gs[1], gs[2], gs[3]);
+            gd[1] = make_uint4(gs[4], gs[5], gs[6], gs[7]);
+          }
           __nv_bfloat162 p0 = __floats2bfloat162_rn(hn[0], hn[1]), p1 = __floats2bfloat162_rn(hn[2], hn[3]);
           hp[2 * g] = *reinterpret_cast<uint32_t*>(&p0);
           hp[2 * g + 1] = *reinterpret_cast<uint32_t*>(&p1);
@@ -286,7 +310,8 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
         }
         tc_fence_before();
         if (row_ok) {   // k-block (ubase >> 6) = this CTA's rank of [H/64][B][64]
-          const long long off = (long long)(ubase >> 6) * L.h_slice + (long long)row * 64 + (ubase & 63);
+          const long long off = SAVE ? (long long)row * H + ubase
+                                     : (long long)(ubase >> 6) * L.h_slice + (long long)row * 64 + (ubase & 63);
           uint4* dst = reinterpret_cast<uint4*>(h_next + off);
           if (live) {
             dst[0] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
@@ -372,18 +397,30 @@ int lstm_seq_launch(const msf_lstm_seq* seqs, int n, long long batch, int steps,
   if (cps > L.row_tiles) cps = L.row_tiles;
   L.cps = cps;
   int rc;
+  const bool save = seqs[0].gates != nullptr;   // training mode: keep what the backward pass needs (lstm_bwd.cu)
   for (int i = 0; i < n; ++i) {
     const msf_lstm_seq& S = seqs[i];
-    MSF_REQUIRE(S.x_bf16 && S.w_hh && S.w_ih && S.bias && S.h_a && S.h_b && S.cell && S.h_out,
-                "msf_lstm_forward: null pointer in sequence %d", i);
+    MSF_REQUIRE(S.x_bf16 && S.w_hh && S.w_ih && S.bias && S.h_out, "msf_lstm_forward: null pointer in sequence %d", i);
+    MSF_REQUIRE((S.gates != nullptr) == save, "msf_lstm_forward: training buffers in some sequences only");
     if ((rc = tc_encode_map(&L.m[i].x, S.x_bf16, B, 64, 64, steps, slice, 64, 128))) return rc;
-    if ((rc = tc_encode_map(&L.m[i].h[0], S.h_a, B, 64, 64, L.kbh, slice, 64, 128))) return rc;
-    if ((rc = tc_encode_map(&L.m[i].h[1], S.h_b, B, 64, 64, L.kbh, slice, 64, 128))) return rc;
+    if (save) {
+      MSF_REQUIRE(S.h_all && S.c_all, "msf_lstm_forward: training mode needs h_all, gates and c_all (sequence %d)", i);
+      if ((rc = tc_encode_map(&L.m[i].h[0], S.h_all, B, hidden, hidden, steps + 1, B * hidden, 64, 128))) return rc;
+      L.m[i].h[1] = L.m[i].h[0];
+      L.hbuf[i][0] = S.h_all; L.hbuf[i][1] = S.h_all;
+      L.gates[i] = static_cast<__nv_bfloat16*>(S.gates);
+      L.c_all[i] = S.c_all;
+    } else {
+      MSF_REQUIRE(S.h_a && S.h_b && S.cell, "msf_lstm_forward: null pointer in sequence %d", i);
+      if ((rc = tc_encode_map(&L.m[i].h[0], S.h_a, B, 64, 64, L.kbh, slice, 64, 128))) return rc;
+      if ((rc = tc_encode_map(&L.m[i].h[1], S.h_b, B, 64, 64, L.kbh, slice, 64, 128))) return rc;
+      L.hbuf[i][0] = S.h_a; L.hbuf[i][1] = S.h_b;
+      L.cell[i] = S.cell;
+    }
     if ((rc = tc_encode_map(&L.m[i].whh, S.w_hh, N4, 64, 64, L.kbh, N4 * 64, 64, 256))) return rc;
     if ((rc = tc_encode_map(&L.m[i].wih, S.w_ih, N4, 64, 64, 1, 0, 64, 256))) return rc;
     L.bias[i] = S.bias;
-    L.hbuf[i][0] = S.h_a; L.hbuf[i][1] = S.h_b;
-    L.cell[i] = S.cell; L.h_out[i] = S.h_out;
+    L.h_out[i] = S.h_out;
     L.lengths[i] = S.lengths;
   }
   const size_t fixed = 1024 + LS_BIAS_OFF + 256 * 4 + 64;
@@ -395,9 +432,9 @@ int lstm_seq_launch(const msf_lstm_seq* seqs, int n, long long batch, int steps,
   const size_t smem = fixed + weights + (size_t)stages * LS_A_BYTES;
   const int grid = n * cps * L.cs;
   if (prof_enabled()) prof_begin("LSTM sequence", 2.0 * (double)B * (hidden + 64) * 4.0 * hidden * steps * n, st);
-  MSF_CHECK_CUDA(cudaFuncSetAttribute(lstm_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (L.cs > 8) MSF_CHECK_CUDA(cudaFuncSetAttribute(lstm_seq_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  MSF_CHECK_CUDA(ls_launch(lstm_seq_kernel, dim3(grid), dim3(LS_THREADS), smem, st, L.cs, L));
+  auto kernel = save ? lstm_seq_kernel<true> : lstm_seq_kernel<false>;
+  MSF_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MSF_CHECK_CUDA(ls_launch(kernel, dim3(grid), dim3(LS_THREADS), smem, st, L.cs, L));
   MSF_LAUNCH_CHECK();
   prof_end(st);
   if (L.dbg & 16) {

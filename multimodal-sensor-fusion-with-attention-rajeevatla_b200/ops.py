@@ -731,11 +731,17 @@ def lstm_pack_weights(weight_ih: torch.Tensor, weight_hh: torch.Tensor, bias_ih:
     return w_hh, w_ih.to(torch.bfloat16).contiguous(), bias
 
 
-def lstm_pack_input(x: torch.Tensor) -> torch.Tensor:
-    """(B, T, F) fp32 windows -> time-major bf16 [T][B][64] with the features zero-padded to 64 columns."""
+def lstm_pack_input(x: torch.Tensor, ones_column: bool = False) -> torch.Tensor:
+    """(B, T, F) fp32 windows -> time-major bf16 [T][B][64] with the features zero-padded to 64 columns.
+    ``ones_column``: column F carries 1.0 (its weight column is zero), so that the weight-gradient GEMM of
+    msf_lstm_backward yields the bias gradient as column F of d W_ih."""
     B, T, F = x.shape
     out = torch.zeros(T, B, 64, dtype=torch.bfloat16, device=x.device)
     out[:, :, :F] = x.detach().transpose(0, 1)
+    if ones_column:
+        if F > 63:
+            raise N.MsfError("the LSTM training path needs input_dim <= 63")
+        out[:, :, F] = 1.0
     return out
 
 
@@ -772,3 +778,114 @@ def lstm_forward(xs: Sequence[torch.Tensor], packed: Sequence[tuple], hidden: in
     for t in keep:   # the launches are asynchronous: keep the scratch alive on this stream
         t.record_stream(torch.cuda.current_stream(dev))
     return outs
+
+
+class LstmTape:
+    """What msf_lstm_forward keeps in training mode for msf_lstm_backward (one encoder)."""
+
+    def __init__(self, x_packed, packed, w_hh_t, h_all, gates, c_all, h_out, lengths, features, hidden):
+        self.x, self.packed, self.w_hh_t = x_packed, packed, w_hh_t
+        self.h_all, self.gates, self.c_all, self.h_out = h_all, gates, c_all, h_out
+        self.lengths, self.features, self.hidden = lengths, features, hidden
+
+
+def lstm_pack_weights_t(weight_hh: torch.Tensor) -> torch.Tensor:
+    """weight_hh_l0 (4H, H) -> the backward operand of msf_lstm_backward: [H][4H] bf16 with
+    ``out[n][4u+g] = weight_hh[g*H+u][n]`` (gate-interleaved columns, like the gate buffers)."""
+    H4, H = weight_hh.shape
+    inter = weight_hh.detach().to(torch.float32).view(4, H, H).permute(1, 0, 2).reshape(4 * H, H)
+    return inter.t().contiguous().to(torch.bfloat16)
+
+
+def lstm_train_forward(xs: Sequence[torch.Tensor], weights: Sequence[tuple], hidden: int,
+                       lengths: Optional[Sequence[Optional[torch.Tensor]]] = None) -> List[LstmTape]:
+    """Training-mode forward of up to 4 single-layer LSTM encoders (msf_lstm_forward with the training buffers set):
+    ``xs`` are (B, T, F) fp32 windows, ``weights`` per encoder ``(weight_ih, weight_hh, bias_ih, bias_hh)`` as
+    nn.LSTM holds them.  One persistent launch; the returned tapes hold ``h_out`` (B, hidden) fp32 and what
+    ``lstm_backward`` needs: h_{t-1} (bf16), the gate activations (bf16) and the cell states (fp32) of every step."""
+    require_cuda("lstm_train_forward")
+    n = len(xs)
+    B, T, _ = xs[0].shape
+    dev = xs[0].device
+    seqs = (N.LstmSeq * n)()
+    tapes = []
+    for i, (x, (w_ih, w_hh, b_ih, b_hh)) in enumerate(zip(xs, weights)):
+        F = x.shape[2]
+        xp = lstm_pack_input(x.to(torch.float32), ones_column=True)
+        packed = lstm_pack_weights(w_ih, w_hh, b_ih, b_hh)
+        h_all = torch.empty(T + 1, B, hidden, dtype=torch.bfloat16, device=dev)
+        h_all[0].zero_()
+        gates = torch.empty(T, B, 4 * hidden, dtype=torch.bfloat16, device=dev)
+        c_all = torch.empty(T, B * hidden, dtype=torch.float32, device=dev)
+        h_out = torch.empty(B, hidden, dtype=torch.float32, device=dev)
+        ln = None
+        if lengths is not None and lengths[i] is not None:
+            ln = lengths[i].to(device=dev, dtype=torch.int32).contiguous()
+            if ln.numel() != B or int(ln.min()) < 1 or int(ln.max()) > T:
+                raise N.MsfError(f"lengths must be {B} integers in [1, {T}]")
+            seqs[i].lengths = _p(ln)
+        seqs[i].x_bf16, seqs[i].w_hh, seqs[i].w_ih, seqs[i].bias = _p(xp), _p(packed[0]), _p(packed[1]), _p(packed[2])
+        seqs[i].h_all, seqs[i].gates, seqs[i].c_all, seqs[i].h_out = _p(h_all), _p(gates), _p(c_all), _p(h_out)
+        tapes.append(LstmTape(xp, packed, lstm_pack_weights_t(w_hh), h_all, gates, c_all, h_out, ln, F, hidden))
+    N.check(N.lib().msf_lstm_forward(seqs, n, B, T, hidden, _stream()))
+    return tapes
+
+
+def lstm_backward(tapes: Sequence[LstmTape], d_h_out: Sequence[torch.Tensor]):
+    """Gradients of the recurrences recorded by ``lstm_train_forward``: per encoder ``(d weight_ih, d weight_hh,
+    d bias)`` in nn.LSTM's layout (``d bias`` is the gradient of bias_ih and of bias_hh alike).  Overwrites the
+    tapes' gate buffers (msf_lstm_backward): a tape can be walked backwards once."""
+    require_cuda("lstm_backward")
+    n = len(tapes)
+    T1, B, hidden = tapes[0].h_all.shape
+    T = T1 - 1
+    dev = tapes[0].h_all.device
+    nbytes = ctypes.c_size_t(0)
+    N.check(N.lib().msf_lstm_backward_scratch_bytes(B, T, hidden, ctypes.byref(nbytes)))
+    seqs = (N.LstmSeq * n)()
+    keep, outs = [], []
+    feats = {tp.features for tp in tapes}
+    if len(feats) != 1:   # one `features` argument per call: encoders of different width go in separate calls
+        raise N.MsfError("lstm_backward: encoders of one call must share input_dim")
+    for i, (tp, dh) in enumerate(zip(tapes, d_h_out)):
+        if tp.gates is None:
+            raise N.MsfError("lstm_backward: this tape was already walked backwards")
+        dh = dh.to(device=dev, dtype=torch.float32).contiguous()
+        dc = torch.zeros(B * hidden, dtype=torch.float32, device=dev)
+        partial = torch.empty(nbytes.value // 4, dtype=torch.float32, device=dev)
+        d_w_ih = torch.empty(4 * hidden, tp.features, dtype=torch.float32, device=dev)
+        d_w_hh = torch.empty(4 * hidden, hidden, dtype=torch.float32, device=dev)
+        d_b = torch.empty(4 * hidden, dtype=torch.float32, device=dev)
+        keep += [dh, dc, partial]
+        outs.append((d_w_ih, d_w_hh, d_b))
+        q = seqs[i]
+        q.x_bf16, q.h_all, q.gates, q.c_all, q.w_hh_t = _p(tp.x), _p(tp.h_all), _p(tp.gates), _p(tp.c_all), _p(tp.w_hh_t)
+        q.d_h_out, q.dc, q.partial = _p(dh), _p(dc), _p(partial)
+        q.d_w_ih, q.d_w_hh, q.d_bias = _p(d_w_ih), _p(d_w_hh), _p(d_b)
+        if tp.lengths is not None:
+            q.lengths = _p(tp.lengths)
+    N.check(N.lib().msf_lstm_backward(seqs, n, B, T, hidden, tapes[0].features, _stream()))
+    for tp in tapes:
+        keep += [tp.x, tp.h_all, tp.gates, tp.c_all, tp.w_hh_t] + ([tp.lengths] if tp.lengths is not None else [])
+        tp.gates = None
+    for t in keep:   # asynchronous launches: keep the buffers alive on this stream
+        t.record_stream(torch.cuda.current_stream(dev))
+    return outs
+
+
+class LstmLastHidden(torch.autograd.Function):
+    """``h_T = LSTM(x)`` of one single-layer nn.LSTM with gradients for its four parameters (none for ``x``: the
+    encoders' inputs are data): msf_lstm_forward in training mode + msf_lstm_backward."""
+
+    @staticmethod
+    def forward(ctx, x, weight_ih, weight_hh, bias_ih, bias_hh, lengths):
+        tape = lstm_train_forward([x], [(weight_ih, weight_hh, bias_ih, bias_hh)], weight_hh.shape[1],
+                                  None if lengths is None else [lengths])[0]
+        ctx.tape = tape
+        ctx.has_bias = bias_ih is not None, bias_hh is not None
+        return tape.h_out
+
+    @staticmethod
+    def backward(ctx, d_h):
+        d_w_ih, d_w_hh, d_b = lstm_backward([ctx.tape], [d_h])[0]
+        return (None, d_w_ih, d_w_hh, d_b if ctx.has_bias[0] else None, d_b.clone() if ctx.has_bias[1] else None, None)

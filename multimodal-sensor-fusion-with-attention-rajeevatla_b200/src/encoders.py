@@ -52,24 +52,36 @@ def _dense(layer: nn.Module, x: torch.Tensor, relu: bool = False) -> torch.Tenso
 
 
 def _lstm_tensor_core_ok(enc, sequence: torch.Tensor, lengths) -> bool:
-    """The hand-written recurrence (msf_lstm_forward: bf16 operands, fp32 state, <= 1e-2) is used for
-    inference when the caller opted into bf16 (``encoder.precision = "bf16"`` or MSF_PRECISION=bf16):
-    single-layer LSTM, CUDA input, hidden % 64 == 0, input_dim <= 64, no gradient wanted; per-window ``lengths``
-    (the reference packs ragged windows, src/encoders.py:140-152) on the persistent kernel (hidden <= 256)."""
+    """The hand-written recurrence (msf_lstm_forward / msf_lstm_backward: bf16 operands, fp32 state, <= 1e-2) is used
+    when the caller opted into bf16 (``encoder.precision = "bf16"`` or MSF_PRECISION=bf16): single-layer LSTM, CUDA
+    input, hidden % 64 == 0, input_dim <= 64; per-window ``lengths`` (the reference packs ragged windows,
+    src/encoders.py:140-152) on the persistent kernel (hidden <= 256).  With gradients wanted for the LSTM's
+    parameters it runs in training mode (hidden <= 256, input_dim <= 63); a gradient with respect to the input
+    sequence is not provided (the encoders' inputs are data) and keeps the library recurrence."""
     prec = getattr(enc, "precision", None) or os.environ.get("MSF_PRECISION", "fp32")
     rnn = enc.rnn
+    if not (prec == "bf16" and enc.encoder_type == "lstm" and sequence.is_cuda
+            and isinstance(rnn, nn.LSTM) and rnn.num_layers == 1 and not rnn.bidirectional and rnn.proj_size == 0
+            and rnn.hidden_size % 64 == 0 and rnn.input_size <= 64):
+        return False
+    if _lstm_wants_grad(rnn):
+        return not sequence.requires_grad and rnn.hidden_size <= 256 and rnn.input_size <= 63
     if lengths is not None and rnn.hidden_size > 256:
         return False   # per-window lengths: persistent kernel only (lstm_seq.cu)
-    return (prec == "bf16" and enc.encoder_type == "lstm" and sequence.is_cuda
-            and isinstance(rnn, nn.LSTM) and rnn.num_layers == 1 and not rnn.bidirectional and rnn.proj_size == 0
-            and rnn.hidden_size % 64 == 0 and rnn.input_size <= 64
-            and not (torch.is_grad_enabled() and (sequence.requires_grad or any(p.requires_grad for p in rnn.parameters()))))
+    return not (torch.is_grad_enabled() and sequence.requires_grad)
+
+
+def _lstm_wants_grad(rnn: nn.Module) -> bool:
+    return torch.is_grad_enabled() and any(p.requires_grad for p in rnn.parameters())
 
 
 def _lstm_tensor_core(rnn: nn.LSTM, sequence: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
-    packed = ops.lstm_pack_weights(rnn.weight_ih_l0, rnn.weight_hh_l0, getattr(rnn, "bias_ih_l0", None),
-                                   getattr(rnn, "bias_hh_l0", None))
     with torch.cuda.device(sequence.device):
+        if _lstm_wants_grad(rnn):   # training: the tape of the forward pass feeds msf_lstm_backward
+            return ops.LstmLastHidden.apply(sequence.detach(), rnn.weight_ih_l0, rnn.weight_hh_l0,
+                                            getattr(rnn, "bias_ih_l0", None), getattr(rnn, "bias_hh_l0", None), lengths)
+        packed = ops.lstm_pack_weights(rnn.weight_ih_l0, rnn.weight_hh_l0, getattr(rnn, "bias_ih_l0", None),
+                                       getattr(rnn, "bias_hh_l0", None))
         return ops.lstm_forward([ops.lstm_pack_input(sequence.to(torch.float32))], [packed], rnn.hidden_size,
                                 None if lengths is None else [lengths])[0]
 

@@ -148,6 +148,53 @@ def test_tensor_core_lstm_ragged_windows(batch, steps, feat, hidden):
         dropin_encoders._lstm_tensor_core(enc.rnn, x.cuda(), torch.zeros(batch, dtype=torch.int64))
 
 
+def _relerr(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("batch,steps,feat,hidden,ragged", [(5, 7, 17, 64, False), (300, 40, 17, 256, False),
+                                                             (130, 300, 1, 256, False), (2500, 21, 3, 128, True),
+                                                             (260, 33, 17, 256, True)])
+def test_tensor_core_lstm_training_matches_oracle(batch, steps, feat, hidden, ragged):
+    """Training mode of the hand-written recurrence (msf_lstm_forward with the training buffers + msf_lstm_backward:
+    persistent backward kernel, weight gradients on the grouped tensor-core GEMM) against autograd through the fp32
+    CPU oracle of the reference's nn.LSTM call (src/encoders.py:135-166; ragged windows :140-152).  Loss = a fixed
+    linear functional of the encoder output (LSTM -> dropout(p=0) -> projection).  bf16 tolerance: output max-abs
+    <= 1e-2; every gradient within 1e-2 max-abs of the oracle's after scaling by the oracle gradient's largest entry,
+    and within 5 % in the Frobenius norm."""
+    from oracle import encoder_oracle
+    torch.manual_seed(7)
+    enc = dropin_encoders.SequenceEncoder(feat, hidden_dim=hidden, output_dim=128, num_layers=1, encoder_type="lstm",
+                                          dropout=0.0).train()
+    gen = torch.Generator().manual_seed(8)
+    x = torch.randn(batch, steps, feat, generator=gen)
+    lengths = None
+    if ragged:
+        lengths = torch.randint(1, steps + 1, (batch,), generator=gen)
+        lengths[0], lengths[-1] = steps, 1
+    probe = torch.randn(batch, 128, generator=gen) / batch
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in enc.state_dict().items()}
+    ref_out = encoder_oracle.sequence_encoder_forward(sd, x, 1, "lstm", lengths)
+    (ref_out * probe).sum().backward()
+    enc = enc.cuda()
+    enc.precision = "bf16"
+    out = enc(x.cuda(), None if lengths is None else lengths.cuda())
+    assert out.requires_grad
+    (out * probe.cuda()).sum().backward()
+    assert _maxabs(out, ref_out) <= 1e-2
+    for name, p in enc.named_parameters():
+        ref = sd[name].grad
+        assert p.grad is not None and torch.isfinite(p.grad).all(), name
+        scale = float(ref.abs().max())
+        assert _maxabs(p.grad, ref) <= 1e-2 * max(scale, 1e-6), name
+        assert _relerr(p.grad, ref) <= 5e-2, name
+    # a second pass accumulates into .grad like autograd does
+    out2 = enc(x.cuda(), None if lengths is None else lengths.cuda())
+    (out2 * probe.cuda()).sum().backward()
+    assert _relerr(enc.rnn.weight_hh_l0.grad, 2 * sd["rnn.weight_hh_l0"].grad) <= 5e-2
+
+
 @pytest.mark.parametrize("pool", ["attention", "average", "max"])
 def test_frame_encoder_matches_reference_golden(pool):
     """FrameEncoder (src/encoders.py:211-336) against the unmodified reference: all three temporal poolings, with and
