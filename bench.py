@@ -674,8 +674,9 @@ def _cpu_sweep_baseline(torch, subsets, sample=8192):
 def run_raw_infer(args):
     """Boundary E of SURVEY.md §8d: inference from RAW windows — 4 single-layer LSTM SequenceEncoders
     (T = 1024; F = 17, 17, 17, 1; hidden 256) -> Linear(256, 128) -> LayerNorm -> HybridFusion -> softmax/argmax,
-    B = 4096 windows on one GPU.  The recurrence runs on msf_lstm_forward (one tcgen05 launch per time step for
-    the four encoders); the same pass with the library (cuDNN) recurrence is timed beside it."""
+    B = 4096 windows on one GPU.  The recurrence runs on msf_lstm_forward (ONE persistent tcgen05 launch over all
+    time steps for the four encoders, lstm_seq.cu); the same pass with the library (cuDNN) recurrence is timed
+    beside it."""
     import torch
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
@@ -706,7 +707,7 @@ def run_raw_infer(args):
             enc_out = [norms[m](encoders._dense(encs[m].projection, h)) for m, h in zip(feats_in, hs)]
         return eng.infer(enc_out, mask)
 
-    # the 1024 step launches are captured once into a CUDA graph over static packed-input buffers
+    # the recurrence launch is captured once into a CUDA graph over static packed-input buffers
     static_x = [ops.lstm_pack_input(x) for x in xs.values()]
     side = torch.cuda.Stream(device=dev)
     side.wait_stream(torch.cuda.current_stream(dev))
@@ -749,6 +750,11 @@ def run_raw_infer(args):
     ms = timed(ours, steps)
     clocks = sampler.stop()
     ms_lib = timed(library, steps)
+    ms_lstm = timed(lstm_graph.replay, steps)   # the recurrence launch alone
+    lstm_flop = B * sum(T * 2 * (f + HID) * 4 * HID for f in feats_in.values())
+    lstm_only = {"ms": ms_lstm, "tflops": lstm_flop / (ms_lstm * 1e-3) / 1e12,
+                 "frac": lstm_flop / (ms_lstm * 1e-3) / 1e12 / _peaks()["tflops"],
+                 "us_per_time_step": ms_lstm * 1e3 / T}
     # e2e: raw windows from pinned host memory, predictions and confidences read back, every pass
     host_x = {m: x.cpu().pin_memory() for m, x in xs.items()}
     host_pred = torch.zeros(B, dtype=torch.int64).pin_memory()
@@ -777,10 +783,12 @@ def run_raw_infer(args):
                     "d2h_bytes_per_step": B * 12,
                     "api": "raw fp32 windows copied from pinned host memory, SequenceEncoder recurrence on "
                            "ops.lstm_forward, FusionEngine.infer, predictions + confidences copied back"},
-            "gpu_launches": 1024 * 1 + 8,
+            "gpu_launches": (1 if HID <= 256 and not os.environ.get("MSF_LSTM_STEPS") else T) + 8,
             "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": tf / peaks["tflops"], "traffic": None, "peak_source": peaks["src"],
-                         "kernel": "whole pass: 1024 LSTM-step launches (tc_gemm_kernel, TC_EPI_LSTM) + fusion forward"},
+                         "kernel": "whole pass: lstm_seq_kernel (one persistent launch over the 1024 steps of the 4 "
+                                   "encoders; MSF_LSTM_STEPS=1: one tc_gemm_kernel launch per step) + fusion forward",
+                         "lstm_kernel": lstm_only},
             "library_recurrence": {"ms_per_step": ms_lib, "value": B / (ms_lib * 1e-3),
                                    "what": "same pass with torch.nn.LSTM (cuDNN, fp32 no-TF32) for the recurrence"},
             "max_abs_logit_diff_vs_library": float((logits_a - logits_b).abs().max())}
@@ -824,6 +832,171 @@ def _cpu_raw_infer_baseline(torch, encoders_mod, fusion, feats_in, T, HID, sampl
     return {"value": sample / dt, "unit": "windows/s", "cores": cores, "kind": "port",
             "sample": f"{n} passes of {sample} raw windows (T = {T}): oracle LSTM recurrence + projection + LayerNorm + "
                       "fusion forward + softmax/argmax; a reported baseline, not the target"}
+
+
+def run_raw_train(args):
+    """Training pass of the four LSTM SequenceEncoders from RAW windows (the first "next" row of SURVEY.md §8f; the
+    reference's nn.LSTM call under autograd, src/encoders.py:135-166): forward in training mode (msf_lstm_forward
+    keeping h / gates / cell states) + backward (msf_lstm_backward: persistent backward kernel + weight-gradient
+    GEMMs), B = 4096 windows, T = --seq-len steps, one GPU.  The library (cuDNN fp32) forward + backward of the same
+    encoders is timed beside it; gradients of both are compared."""
+    import torch
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    importlib.import_module(PKG)
+    ops = importlib.import_module(PKG + ".ops")
+    sys.path.insert(0, os.path.join(ROOT, PKG, "src"))
+    encoders = importlib.import_module("encoders")
+    B, T, HID = BATCH, args.seq_len, 256
+    feats_in = {"imu_hand": 17, "imu_chest": 17, "imu_ankle": 17, "heart_rate": 1}
+    torch.manual_seed(0)
+    encs = {m: encoders.SequenceEncoder(f, hidden_dim=HID, output_dim=128, num_layers=1, encoder_type="lstm",
+                                        dropout=0.0).to(dev).train() for m, f in feats_in.items()}
+    g = torch.Generator(device=dev).manual_seed(1234)
+    xs = [torch.randn(B, T, f, device=dev, generator=g) for f in feats_in.values()]
+    d_h = [torch.randn(B, HID, device=dev, generator=g) / B for _ in feats_in]
+    weights = [(e.rnn.weight_ih_l0, e.rnn.weight_hh_l0, e.rnn.bias_ih_l0, e.rnn.bias_hh_l0) for e in encs.values()]
+
+    def ours():
+        tapes = ops.lstm_train_forward(xs, weights, HID)
+        return ops.lstm_backward(tapes, d_h)
+
+    def library():
+        grads = []
+        for e, x, d in zip(encs.values(), xs, d_h):
+            for p in e.rnn.parameters():
+                p.grad = None
+            h = encoders._rnn_fp32(e.rnn, x)[1][0][-1]
+            (h * d).sum().backward()
+            grads.append((e.rnn.weight_ih_l0.grad, e.rnn.weight_hh_l0.grad, e.rnn.bias_ih_l0.grad))
+        return grads
+
+    def timed(fn, steps):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(steps):
+            fn()
+        stop.record()
+        torch.cuda.synchronize()
+        return start.elapsed_time(stop) / steps
+
+    steps = max(1, min(args.steps, 5))
+    ga = ours()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    ms = timed(ours, steps)
+    clocks = sampler.stop()
+    # where the pass spends its time: forward launch, backward recurrence, weight-gradient GEMMs
+    tapes = ops.lstm_train_forward(xs, weights, HID)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev[0].record()
+    tapes = ops.lstm_train_forward(xs, weights, HID)
+    ev[1].record()
+    ops.lstm_backward(tapes, d_h)
+    ev[2].record()
+    torch.cuda.synchronize()
+    ms_fwd, ms_bwd = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+    del tapes
+    # per-launch durations (msf_prof_*: CUDA events around every tensor-core launch of one pass)
+    import ctypes
+    nat = importlib.import_module(PKG + "._native")
+    nat.check(nat.lib().msf_prof_enable(1))
+    ours()
+    buf = ctypes.create_string_buffer(1 << 16)
+    nat.check(nat.lib().msf_prof_report(buf, len(buf)))
+    nat.check(nat.lib().msf_prof_enable(0))
+    launches = []
+    for row in buf.value.decode().splitlines():
+        label, cnt, msr, fl = row.split("\t")
+        launches.append({"launch": label, "launches": int(cnt), "ms": float(msr),
+                         "tflops": float(fl) / (float(msr) * 1e-3) / 1e12 if float(msr) > 0 else None})
+    rel = None
+    ms_lib = None
+    try:
+        torch.cuda.empty_cache()
+        gb = library()
+        rel = max(float((a[k] - b[k]).norm() / b[k].norm()) for a, b in zip(ga, gb) for k in range(3))
+        ms_lib = timed(library, max(1, min(steps, 2)))
+    except torch.cuda.OutOfMemoryError:
+        pass
+    fwd_flop = B * sum(T * 2 * (f + HID) * 4 * HID for f in feats_in.values())
+    bwd_flop = B * sum(T * (2 * 4 * HID * HID + 2 * 4 * HID * (HID + 64)) for f in feats_in.values())
+    peaks = _peaks()
+    tf = (fwd_flop + bwd_flop) / (ms * 1e-3) / 1e12
+    host_x = [x.cpu().pin_memory() for x in xs]
+    host_g = [[torch.empty_like(t, device="cpu").pin_memory() for t in trip] for trip in ga]
+
+    def e2e():
+        for x, hx in zip(xs, host_x):
+            x.copy_(hx, non_blocking=True)
+        grads = ours()
+        for trip, htrip in zip(grads, host_g):
+            for t, ht in zip(trip, htrip):
+                ht.copy_(t, non_blocking=True)
+
+    ms_e2e = timed(e2e, max(1, min(steps, 3)))
+    line = {"metric": METRIC, "value": B / (ms * 1e-3), "unit": "windows/s", "n_gpus": 1, "steps": steps, "warmup": 2,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": "training pass of the 4 LSTM encoders from raw windows (SURVEY 8f): forward with tape + "
+                                   "backward incl. weight gradients", "batch": B, "seq_len": T, "hidden": HID,
+                       "l2": f"{sum(x.numel() for x in xs) * 4 / 1e9:.2f} GB of raw windows and "
+                             f"{B * T * HID * (8 + 4 + 2) * 4 / 1e9:.1f} GB of tape per pass >> 126 MiB L2"},
+            "clocks": clocks,
+            "e2e": {"value": B / (ms_e2e * 1e-3), "unit": "windows/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": sum(t.numel() * 4 for t in host_x),
+                    "d2h_bytes_per_step": sum(t.numel() * 4 for trip in host_g for t in trip),
+                    "api": "raw fp32 windows copied from pinned host memory, ops.lstm_train_forward + ops.lstm_backward, "
+                           "all parameter gradients copied back"},
+            "gpu_launches": 2 + 3 * len(feats_in),
+            "phases_ms": {"forward (lstm_seq_kernel<true>, incl. input / weight packing)": ms_fwd,
+                          "backward (lstm_bwd_kernel + weight-gradient GEMMs + reduction)": ms_bwd},
+            "per_launch": launches,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                         "frac": tf / peaks["tflops"], "traffic": None, "peak_source": peaks["src"],
+                         "kernel": "whole pass: lstm_seq_kernel<true> + lstm_bwd_kernel + tc_gemm_kernel<true> (weight gradients)"},
+            "library_recurrence": None if ms_lib is None else {
+                "ms_per_step": ms_lib, "value": B / (ms_lib * 1e-3),
+                "what": "torch.nn.LSTM forward + autograd backward (cuDNN, fp32 no-TF32) of the same 4 encoders"},
+            "max_rel_gradient_diff_vs_library": rel}
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = _cpu_raw_train_baseline(torch, encoders, feats_in, T, HID)
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
+
+
+def _cpu_raw_train_baseline(torch, encoders_mod, feats_in, T, HID, sample=32):
+    """The reference arithmetic of the same pass on the host cores: oracle LSTM recurrence (fp32) of the four encoders
+    forward + autograd backward on a bounded sample of windows."""
+    from oracle import encoder_oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    encs = {m: encoders_mod.SequenceEncoder(f, hidden_dim=HID, output_dim=128, num_layers=1, encoder_type="lstm",
+                                            dropout=0.0).train() for m, f in feats_in.items()}
+    g = torch.Generator().manual_seed(7)
+    xs = {m: torch.randn(sample, T, f, generator=g) for m, f in feats_in.items()}
+
+    def one_pass():
+        for m in feats_in:
+            sd = {k: v.detach().clone().requires_grad_(True) for k, v in encs[m].state_dict().items()}
+            encoder_oracle.lstm_last_hidden(sd, "rnn", xs[m], 1).sum().backward()
+
+    one_pass()
+    t0, n = time.perf_counter(), 0
+    while time.perf_counter() - t0 < 10.0:
+        one_pass()
+        n += 1
+    dt = (time.perf_counter() - t0) / n
+    return {"value": sample / dt, "unit": "windows/s", "cores": cores, "kind": "port",
+            "sample": f"{n} passes of {sample} raw windows (T = {T}): oracle LSTM recurrence of the 4 encoders, forward + "
+                      "autograd backward; a reported baseline, not the target"}
 
 
 def run_ece(args):
@@ -1041,7 +1214,8 @@ def main():
     ap.add_argument("--shape", default="pamap2", choices=["pamap2", "scaled"],
                     help="train workload: pamap2 = BASELINE configs[1] (4 x 128 -> hidden 256), scaled = BASELINE "
                          "configs[4] (8 modalities x 256 -> hidden 512, 8 heads, 11 classes)")
-    ap.add_argument("--workload", default="train", choices=["train", "infer_sweep", "ece", "raw_infer"],
+    ap.add_argument("--seq-len", type=int, default=1024, help="raw_train: time steps per window")
+    ap.add_argument("--workload", default="train", choices=["train", "infer_sweep", "ece", "raw_infer", "raw_train"],
                     help="train = the benchmark proper (BASELINE configs[1]); the other two print extra evidence "
                          "lines for configs[2] and the ECE binning kernel (single GPU)")
     args = ap.parse_args()
@@ -1055,6 +1229,8 @@ def main():
         run_ece(args)
     elif args.workload == "raw_infer":
         run_raw_infer(args)
+    elif args.workload == "raw_train":
+        run_raw_train(args)
     else:
         run_ours(args)
 

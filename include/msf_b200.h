@@ -426,19 +426,29 @@ typedef struct msf_lstm_seq {
   float* cell;
   float* h_out;
   const int32_t* lengths;
-  /* training mode (all NULL for inference): set by the caller of msf_lstm_forward when msf_lstm_backward follows */
-  void* h_all;           /* [T+1][B][H] bf16: hidden state BEFORE step t at [t]; [0] zeros on entry (h_a, h_b, cell unused) */
+  /* stacked layers / training mode (all NULL for single-layer inference) */
+  void* h_all;           /* [T+1][B][H] bf16: hidden state BEFORE step t at [t]; [0] zeros on entry (h_a, h_b unused):
+                            every hidden state is kept — the next layer's input, the backward pass's operand */
+  const void* z_in;      /* layers above the first: [T][B][4H] bf16, columns 4u+g: in_t W_ih^T of every step, computed
+                            beforehand by one GEMM (msf_gemm_bf16); replaces x_bf16 / w_ih; may be `gates` itself */
+  /* training mode: set by the caller of msf_lstm_forward when msf_lstm_backward follows (cell unused) */
   void* gates;           /* [T][B][4H] bf16, columns 4u+g: gate activations after the forward pass, gradients of the
                             gate pre-activations after the backward pass (in place) */
   float* c_all;          /* [T][B*H] fp32: cell state after every step (implementation-defined order inside a step) */
   /* msf_lstm_backward only */
   const void* w_hh_t;    /* [H][4H] bf16: recurrent weights transposed, w_hh_t[n][4u+g] = weight_hh[g*H+u][n] */
-  const float* d_h_out;  /* [B][H] fp32: gradient of the loss with respect to h_out */
+  const float* d_h_out;  /* [B][H] fp32: gradient of the loss with respect to h_out (NULL for a layer below the top) */
+  const void* d_h_all;   /* [T][B][H] bf16 or NULL: gradient with respect to EVERY step's hidden state, from the layer
+                            above (d a of that layer times its W_ih, through the inter-layer dropout mask) */
   float* dc;             /* [B*H] fp32 scratch, ZERO on entry */
   float* partial;        /* fp32 scratch, msf_lstm_backward_scratch_bytes() */
   float* d_w_ih;         /* [4H][F] fp32, nn.LSTM row order (gate-major): gradient of weight_ih_l0 */
   float* d_w_hh;         /* [4H][H] fp32: gradient of weight_hh_l0 */
   float* d_bias;         /* [4H]    fp32: gradient of bias_ih_l0 (= that of bias_hh_l0) */
+  int32_t features;      /* F = input_dim of this layer: 1..63 for the first layer, H for the layers above */
+  int32_t in_cols;       /* row length of x_bf16 in msf_lstm_backward: 0 for the first layer (64 padded columns); H for a layer above,
+                            whose x_bf16 is the [T][B][H] input the forward GEMM read (no ones column: the bias gradient
+                            is a column sum of d a) */
 } msf_lstm_seq;
 int msf_lstm_forward(const msf_lstm_seq* seqs, int32_t n, int64_t batch, int32_t steps, int32_t hidden, void* stream);
 
@@ -451,8 +461,12 @@ int msf_lstm_forward(const msf_lstm_seq* seqs, int32_t n, int64_t batch, int32_t
  * column `features` of d W_ih: the caller stores 1.0 in column `features` of x_bf16 (features <= 63) whose weight
  * column is zero.  No gradient with respect to x (the encoders' inputs are data).  hidden <= 256. */
 int msf_lstm_backward_scratch_bytes(int64_t batch, int32_t steps, int32_t hidden, size_t* bytes);
-int msf_lstm_backward(const msf_lstm_seq* seqs, int32_t n, int64_t batch, int32_t steps, int32_t hidden,
-                      int32_t features, void* stream);
+int msf_lstm_backward(const msf_lstm_seq* seqs, int32_t n, int64_t batch, int32_t steps, int32_t hidden, void* stream);
+/* Inter-layer dropout of a stacked nn.LSTM in training mode: out = in * m over rows x cols bf16 (cols % 8 == 0), m the
+ * library's Philox multipliers (0 or 1/(1-p)) of site 4, sub = layer (msf_dropout_mask(seed, offset, 4, layer, ...)
+ * returns the same ones); in == out is allowed.  Forward: the input of layer `layer`; backward: its gradient. */
+int msf_lstm_dropout(const void* in_bf16, void* out_bf16, int64_t rows, int32_t cols, float p, uint64_t seed,
+                     uint64_t offset, int32_t layer, void* stream);
 
 /* ---- BatchNorm1d -> ReLU -> Dropout behind a Linear layer (src/encoders.py:339-397, BatchNorm at :374-375) ----- */
 /* out = dropout(relu((y - mean) * invstd * gamma + beta)) over y (rows x cols, row-major fp32: the Linear output).

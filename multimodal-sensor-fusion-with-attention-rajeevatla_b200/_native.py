@@ -93,8 +93,9 @@ class LstmSeq(ctypes.Structure):  # msf_lstm_seq
         ("x_bf16", c_void_p), ("w_hh", c_void_p), ("w_ih", c_void_p), ("bias", c_void_p),
         ("h_a", c_void_p), ("h_b", c_void_p), ("cell", c_void_p), ("h_out", c_void_p), ("lengths", c_void_p),
         # training mode
-        ("h_all", c_void_p), ("gates", c_void_p), ("c_all", c_void_p), ("w_hh_t", c_void_p), ("d_h_out", c_void_p),
+        ("h_all", c_void_p), ("z_in", c_void_p), ("gates", c_void_p), ("c_all", c_void_p), ("w_hh_t", c_void_p), ("d_h_out", c_void_p), ("d_h_all", c_void_p),
         ("dc", c_void_p), ("partial", c_void_p), ("d_w_ih", c_void_p), ("d_w_hh", c_void_p), ("d_bias", c_void_p),
+        ("features", c_int32), ("in_cols", c_int32),
     ]
 
 
@@ -173,7 +174,8 @@ PROTOTYPES = {
                                               c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                               c_void_p, c_void_p]),
     "msf_lstm_forward": (c_int32, [POINTER(LstmSeq), c_int32, c_int64, c_int32, c_int32, c_void_p]),
-    "msf_lstm_backward": (c_int32, [POINTER(LstmSeq), c_int32, c_int64, c_int32, c_int32, c_int32, c_void_p]),
+    "msf_lstm_backward": (c_int32, [POINTER(LstmSeq), c_int32, c_int64, c_int32, c_int32, c_void_p]),
+    "msf_lstm_dropout": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_float, c_uint64, c_uint64, c_int32, c_void_p]),
     "msf_lstm_backward_scratch_bytes": (c_int32, [c_int64, c_int32, c_int32, POINTER(ctypes.c_size_t)]),
     "msf_fusion_infer_folded": (c_int32, [POINTER(FusionShape), POINTER(FusionCall), c_void_p, c_void_p, ctypes.c_uint32,
                                           c_int32, c_void_p, c_void_p, c_void_p]),

@@ -48,9 +48,11 @@ struct LstmBwdLaunch {
   __nv_bfloat16* gates[MSF_LSTM_MAX_SEQS];
   const float* c_all[MSF_LSTM_MAX_SEQS];
   float* dc[MSF_LSTM_MAX_SEQS];
-  const float* d_h_out[MSF_LSTM_MAX_SEQS];
+  const float* d_h_out[MSF_LSTM_MAX_SEQS];          // gradient of the last valid hidden state, or nullptr
+  const __nv_bfloat16* dh_all[MSF_LSTM_MAX_SEQS];   // [T][B][H] gradient of every step's hidden state (from the layer above), or nullptr
   const int* lengths[MSF_LSTM_MAX_SEQS];
   int n, rows, steps, hidden, kb4, cs, cps, row_tiles, stages;
+  int dbg;   // MSF_LSTM_DBG: 16 = cycle stamps of CTA 0, 8 = no gate / cell traffic in the epilogue (timing only)
 };
 
 __device__ __forceinline__ uint32_t lb_ctarank() {
@@ -78,6 +80,10 @@ __device__ __forceinline__ uint32_t lb_pack(float a, float b) {
   __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&p);
 }
+
+// cycles of CTA 0 summed over the steps (dbg & 16): [0] step start -> producer done, [1] -> MMAs issued,
+// [2] -> first accumulator complete, [3] -> last accumulator complete, [4] -> epilogue done, [5] -> barrier passed
+__device__ long long g_lb_stamps[8];
 
 __global__ void __launch_bounds__(LB_THREADS, 1) lstm_bwd_kernel(const __grid_constant__ LstmBwdLaunch L) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -149,6 +155,8 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_bwd_kernel(const __grid_co
 #pragma unroll 1
   for (int s = 0; s < L.steps; ++s) {
     const int t = L.steps - 1 - s;
+    const bool stamp = (L.dbg & 16) && blockIdx.x == 0 && lane == 0;
+    const long long t_step = stamp ? clock64() : 0;
     if (warp == 0) {
       // ===== TMA producer: d a_{t+1} of every tile of this cluster (nothing at the last time step) =====
       if (lane == 0 && s > 0) {
@@ -161,6 +169,7 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_bwd_kernel(const __grid_co
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
+        if (stamp) g_lb_stamps[0] += clock64() - t_step;
       }
     } else if (warp == 1) {
       // ===== MMA issuer: d h_t (recurrent part) = d a_{t+1} W_hh restricted to this CTA's 64 units =====
@@ -183,6 +192,7 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_bwd_kernel(const __grid_co
           }
           tc_commit(acc_full(acc));
         }
+        if (stamp) g_lb_stamps[1] += clock64() - t_step;
       }
     } else if (warp >= 4) {
       // ===== epilogue: cell backward on this CTA's 64 hidden units (16 per warp column group) =====
@@ -191,6 +201,7 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_bwd_kernel(const __grid_co
       const float* c_p = c_t - BH;   // step t - 1 (not read at t = 0: c_{-1} = 0)
       float* dcp = L.dc[seq];
       const float* dho = L.d_h_out[seq];
+      const __nv_bfloat16* dha = L.dh_all[seq] != nullptr ? L.dh_all[seq] + (long long)t * BH : nullptr;
       const int* lens = L.lengths[seq];
       for (int i = 0; i < my_tiles; ++i) {
         const int tile = slot + i * L.cps;
@@ -200,7 +211,7 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_bwd_kernel(const __grid_co
         const int ubase = rank * 64 + cg * 16;   // first hidden unit of this thread's 16
         const int len = (lens != nullptr && row_ok) ? __ldg(lens + row) : L.steps;
         const bool live = row_ok && t < len;      // the window took this step in the forward pass
-        const bool ext = row_ok && t == len - 1;  // h_out of the window is h_t
+        const bool ext = row_ok && dho != nullptr && t == len - 1;  // h_out of the window is h_t
         uint32_t a[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) a[j] = 0u;
@@ -208,6 +219,8 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_bwd_kernel(const __grid_co
           const int acc = (int)(cnt & 1u);
           mbar_wait(acc_full(acc), (cnt >> 1) & 1u);
           tc_fence_after();
+          if (stamp && warp == 4 && i == 0) g_lb_stamps[2] += clock64() - t_step;
+          if (stamp && warp == 4 && i == my_tiles - 1) g_lb_stamps[3] += clock64() - t_step;
           const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)acc * LB_ACC_COLS + (uint32_t)(cg * 16);
           tmem_ld16_issue(taddr, a);
           tmem_wait16(a);
@@ -220,14 +233,18 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_bwd_kernel(const __grid_co
         for (int g = 0; g < 4; ++g) {
           const int u0 = ubase + 4 * g;
           uint4* gp = reinterpret_cast<uint4*>(gates_t + (long long)row * 4 * H + 4 * u0);
-          if (live) {
+          if (live && !(L.dbg & 8)) {
             const long long idx = lb_cell_index(tile, r, u0, H, ragged);
             const uint4 g0 = gp[0], g1 = gp[1];
             const float4 ct4 = *reinterpret_cast<const float4*>(c_t + idx);
             const float4 cp4 = t > 0 ? *reinterpret_cast<const float4*>(c_p + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
             const float4 dc4 = *reinterpret_cast<const float4*>(dcp + idx);
-            const float4 ex4 = ext ? __ldg(reinterpret_cast<const float4*>(dho + (long long)row * H + u0))
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 ex4 = ext ? __ldg(reinterpret_cast<const float4*>(dho + (long long)row * H + u0))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (dha != nullptr) {   // this step's hidden state also fed the layer above
+              const uint2 e2 = __ldg(reinterpret_cast<const uint2*>(dha + (long long)row * H + u0));
+              ex4.x += lb_lo(e2.x); ex4.y += lb_hi(e2.x); ex4.z += lb_lo(e2.y); ex4.w += lb_hi(e2.y);
+            }
             const uint32_t gw[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
             const float ct[4] = {ct4.x, ct4.y, ct4.z, ct4.w}, cp[4] = {cp4.x, cp4.y, cp4.z, cp4.w};
             const float dcv[4] = {dc4.x, dc4.y, dc4.z, dc4.w}, ex[4] = {ex4.x, ex4.y, ex4.z, ex4.w};
@@ -259,9 +276,11 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_bwd_kernel(const __grid_co
       // d a_t is read back by TMA (async proxy) in the next step, by every CTA of the cluster
       asm volatile("fence.proxy.async.global;" ::: "memory");
       __threadfence();
+      if (stamp && warp == 4) g_lb_stamps[4] += clock64() - t_step;
     }
     __syncwarp();
     lb_cluster_sync();   // d a_t of the cluster's tiles is complete and visible
+    if (stamp && warp == 4) g_lb_stamps[5] += clock64() - t_step;
   }
 
   tc_fence_before();
@@ -274,20 +293,61 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_bwd_kernel(const __grid_co
 
 // d W_hh / d W_ih / d bias = sum over the chunks of partial[chunk][4u+g][0..H) / [H..H+F) / [H+F], rows back in
 // nn.LSTM's gate-major order (row g*H + u); fixed summation order.
-__global__ void lstm_wgrad_reduce_kernel(const float* __restrict__ partial, int chunks, int H, int F, float* __restrict__ d_w_ih,
-                                         float* __restrict__ d_w_hh, float* __restrict__ d_bias) {
-  const int ld = H + 64;
+__global__ void lstm_wgrad_reduce_kernel(const float* __restrict__ partial, int chunks, int H, int F, int in_cols,
+                                         const float* __restrict__ bias_partial, int bias_blocks,
+                                         float* __restrict__ d_w_ih, float* __restrict__ d_w_hh, float* __restrict__ d_bias) {
+  const int ld = H + in_cols;
   const long long per_chunk = 4LL * H * ld;
   const long long total = 4LL * H * (H + F + 1);
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int row = (int)(e / (H + F + 1)), col = (int)(e % (H + F + 1));   // row = 4u + g
-    const float* src = partial + (long long)row * ld + col;
     float sum = 0.0f;
-    for (int c = 0; c < chunks; ++c) sum += src[(long long)c * per_chunk];
+    if (col == H + F && bias_partial != nullptr) {   // no ones column in this layer's input: column sums of d a
+      for (int b = 0; b < bias_blocks; ++b) sum += bias_partial[(long long)b * 4 * H + row];
+    } else {
+      const float* src = partial + (long long)row * ld + col;
+      for (int c = 0; c < chunks; ++c) sum += src[(long long)c * per_chunk];
+    }
     const int dst_row = (row & 3) * H + (row >> 2);
     if (col < H) d_w_hh[(long long)dst_row * H + col] = sum;
     else if (col < H + F) d_w_ih[(long long)dst_row * F + (col - H)] = sum;
     else d_bias[dst_row] = sum;
+  }
+}
+
+// Column sums of d a ([rows][4H] bf16) for the bias gradient of the layers above the first: block b adds rows
+// b, b + grid, ... (thread = 4 adjacent columns) into bias_partial[b][4H]; the reduction kernel sums the blocks.
+constexpr int LB_COLSUM_BLOCKS = 592;
+__global__ void __launch_bounds__(256) lstm_colsum_kernel(const __nv_bfloat16* __restrict__ da, long long rows, int cols,
+                                                          float* __restrict__ bias_partial) {
+  const int c0 = threadIdx.x * 4;
+  if (c0 >= cols) return;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(da + r * cols + c0));
+    acc[0] += lb_lo(v.x); acc[1] += lb_hi(v.x); acc[2] += lb_lo(v.y); acc[3] += lb_hi(v.y);
+  }
+  *reinterpret_cast<float4*>(bias_partial + (long long)blockIdx.x * cols + c0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+}
+
+// Inter-layer dropout of a stacked nn.LSTM (training mode, src/encoders.py:54-65: dropout between the layers):
+// out = in * mask with the library's Philox multipliers (site 4, sub = layer), 8 elements per thread.
+constexpr int SITE_LSTM_LAYER = 4;
+__global__ void lstm_dropout_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, long long rows,
+                                    int cols, DropCfg d, int layer) {
+  const int c8n = cols >> 3;
+  const long long total = rows * c8n;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long row = e / c8n;
+    const int c8 = (int)(e % c8n);
+    float m[8];
+    drop8(d, SITE_LSTM_LAYER, layer, row, c8, m);
+    const uint4 v = *reinterpret_cast<const uint4*>(in + row * cols + c8 * 8);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = lb_pack(lb_lo(w[j]) * m[2 * j], lb_hi(w[j]) * m[2 * j + 1]);
+    *reinterpret_cast<uint4*>(out + row * cols + c8 * 8) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -331,7 +391,7 @@ int lb_sm_count(int* sms) {
 // The contraction over (t, window) is cut into chunks of whole time steps: enough chunks for two waves of tiles,
 // at most 32 (problems per launch) and at most one per step.
 void lb_chunking(int steps, int hidden, int sms, int* steps_per_chunk, int* chunks) {
-  const int tiles_per_chunk = (4 * hidden / 128) * ((hidden + 127) / 128 + 1);
+  const int tiles_per_chunk = (4 * hidden / 128) * 2 * ((hidden + 127) / 128);
   int want = (2 * sms + tiles_per_chunk - 1) / tiles_per_chunk;
   if (want > 16) want = 16;
   if (want > steps) want = steps;
@@ -352,17 +412,16 @@ extern "C" int msf_lstm_backward_scratch_bytes(int64_t batch, int32_t steps, int
   if (rc) return rc;
   int spc, chunks;
   lb_chunking(steps, hidden, sms, &spc, &chunks);
-  *bytes = (size_t)chunks * 4 * hidden * (hidden + 64) * sizeof(float);
+  *bytes = ((size_t)chunks * 4 * hidden * 2 * hidden + (size_t)LB_COLSUM_BLOCKS * 4 * hidden) * sizeof(float);
   return MSF_OK;
 }
 
 extern "C" int msf_lstm_backward(const msf_lstm_seq* seqs, int32_t n, int64_t batch, int32_t steps, int32_t hidden,
-                                 int32_t features, void* stream) {
+                                 void* stream) {
   using namespace msf;
   MSF_REQUIRE(seqs != nullptr && n >= 1 && n <= MSF_LSTM_MAX_SEQS, "msf_lstm_backward: 1..%d sequences per call", MSF_LSTM_MAX_SEQS);
   MSF_REQUIRE(batch >= 1 && batch < (1 << 24) && steps >= 1, "msf_lstm_backward: bad batch / steps");
   MSF_REQUIRE(hidden % 64 == 0 && hidden >= 64 && hidden <= 256, "msf_lstm_backward: hidden %d (needs a multiple of 64, <= 256)", hidden);
-  MSF_REQUIRE(features >= 1 && features <= 63, "msf_lstm_backward: features %d (1..63: column `features` of x carries the ones of the bias gradient)", features);
   cudaStream_t st = (cudaStream_t)stream;
   int sms = 0, rc = lb_sm_count(&sms);
   if (rc) return rc;
@@ -371,21 +430,31 @@ extern "C" int msf_lstm_backward(const msf_lstm_seq* seqs, int32_t n, int64_t ba
   memset(&L, 0, sizeof(L));
   L.n = n; L.rows = (int)B; L.steps = steps; L.hidden = hidden; L.kb4 = (int)(N4 / 64); L.cs = hidden / 64;
   L.row_tiles = (int)ceil_div(B, 128);
+  { const char* e = getenv("MSF_LSTM_DBG"); L.dbg = e ? atoi(e) : 0; }
   MSF_REQUIRE(sms / L.cs >= n, "msf_lstm_backward: %d sequences need %d clusters of %d CTAs", n, n, L.cs);
   int cps = (sms / L.cs) / n;
   if (cps > L.row_tiles) cps = L.row_tiles;
   L.cps = cps;
   for (int i = 0; i < n; ++i) {
     const msf_lstm_seq& S = seqs[i];
-    MSF_REQUIRE(S.x_bf16 && S.h_all && S.gates && S.c_all && S.w_hh_t && S.d_h_out && S.dc && S.partial && S.d_w_ih &&
-                    S.d_w_hh && S.d_bias,
+    MSF_REQUIRE(S.x_bf16 && S.h_all && S.gates && S.c_all && S.w_hh_t && (S.d_h_out || S.d_h_all) && S.dc && S.partial &&
+                    S.d_w_ih && S.d_w_hh && S.d_bias,
                 "msf_lstm_backward: null pointer in sequence %d", i);
+    MSF_REQUIRE(S.in_cols == 0 || S.in_cols == hidden,
+                "msf_lstm_backward: in_cols %d (0 for the first layer, hidden for the layers above)", S.in_cols);
+    if (S.in_cols != 0) {
+      MSF_REQUIRE(S.features == hidden, "msf_lstm_backward: a stacked layer has features == hidden");
+    } else {
+      MSF_REQUIRE(S.features >= 1 && S.features <= 63,
+                  "msf_lstm_backward: features %d (1..63: column `features` of x carries the ones of the bias gradient)", S.features);
+    }
     if ((rc = tc_encode_map(&L.m[i].da, S.gates, B, N4, N4, steps, B * N4, 64, 128))) return rc;
     if ((rc = tc_encode_map(&L.m[i].wt, S.w_hh_t, H, N4, N4, 1, 0, 64, 64))) return rc;
     L.gates[i] = static_cast<__nv_bfloat16*>(S.gates);
     L.c_all[i] = S.c_all;
     L.dc[i] = S.dc;
     L.d_h_out[i] = S.d_h_out;
+    L.dh_all[i] = static_cast<const __nv_bfloat16*>(S.d_h_all);
     L.lengths[i] = S.lengths;
   }
   const size_t fixed = 1024 + 8 * LB_NBAR + 64;
@@ -401,15 +470,28 @@ extern "C" int msf_lstm_backward(const msf_lstm_seq* seqs, int32_t n, int64_t ba
   MSF_CHECK_CUDA(lb_launch(lstm_bwd_kernel, dim3(grid), dim3(LB_THREADS), smem, st, L.cs, L));
   MSF_LAUNCH_CHECK();
   prof_end(st);
+  if (L.dbg & 16) {
+    MSF_CHECK_CUDA(cudaStreamSynchronize(st));
+    long long v[8];
+    MSF_CHECK_CUDA(cudaMemcpyFromSymbol(v, g_lb_stamps, sizeof(v)));
+    fprintf(stderr, "lstm_bwd CTA 0, cycles per step: producer done %lld, MMAs issued %lld, first accumulator %lld, last "
+                    "accumulator %lld, epilogue done %lld, barrier passed %lld (tiles per cluster %d, stages %d)\n",
+            v[0] / steps, v[1] / steps, v[2] / steps, v[3] / steps, v[4] / steps, v[5] / steps,
+            (int)ceil_div(L.row_tiles, cps), stages);
+    memset(v, 0, sizeof(v));
+    MSF_CHECK_CUDA(cudaMemcpyToSymbol(g_lb_stamps, v, sizeof(v)));
+  }
 
   // ---- weight gradients: contraction over (t, window), chunks of whole steps -> fp32 partial sums ----
   int spc, chunks;
   lb_chunking(steps, hidden, sms, &spc, &chunks);
   const int full = steps / spc, rem = steps - full * spc;   // `full` chunks of spc steps (+ one of `rem`)
-  const long long rows_c = (long long)spc * B, ld_p = H + 64, per_chunk = N4 * ld_p;
+  const long long rows_c = (long long)spc * B;
   MSF_REQUIRE(rows_c < (1ll << 31), "msf_lstm_backward: chunk of %lld rows too long", rows_c);
   for (int i = 0; i < n; ++i) {
     const msf_lstm_seq& S = seqs[i];
+    const bool stacked = S.in_cols != 0;   // input = the layer below's hidden states, no ones column
+    const long long IC = stacked ? H : 64, ld_p = H + IC, per_chunk = N4 * ld_p;
     TcBuilder tb(true, 128, no_dropout(), st, "LSTM weight gradients");
     const __nv_bfloat16* da = static_cast<const __nv_bfloat16*>(S.gates);
     const __nv_bfloat16* hh = static_cast<const __nv_bfloat16*>(S.h_all);
@@ -418,13 +500,13 @@ extern "C" int msf_lstm_backward(const msf_lstm_seq* seqs, int32_t n, int64_t ba
     if (full > 0) {
       m_a = (short)tb.add_map(da, rows_c, N4, N4, full, rows_c * N4, 0);
       m_h = (short)tb.add_map(hh, rows_c, H, H, full, rows_c * H, 0);
-      m_x = (short)tb.add_map(xx, rows_c, 64, 64, full, rows_c * 64, 0);
+      m_x = (short)tb.add_map(xx, rows_c, IC, IC, full, rows_c * IC, 0);
     }
     if (rem > 0) {
       const long long done = (long long)full * rows_c;
       r_a = (short)tb.add_map(da + done * N4, (long long)rem * B, N4, N4, 1, 0, 0);
       r_h = (short)tb.add_map(hh + done * H, (long long)rem * B, H, H, 1, 0, 0);
-      r_x = (short)tb.add_map(xx + done * 64, (long long)rem * B, 64, 64, 1, 0, 0);
+      r_x = (short)tb.add_map(xx + done * IC, (long long)rem * B, IC, IC, 1, 0, 0);
     }
     if (tb.status) return tb.status;
     for (int c = 0; c < chunks; ++c) {
@@ -437,7 +519,7 @@ extern "C" int msf_lstm_backward(const msf_lstm_seq* seqs, int32_t n, int64_t ba
         p.seg[0].b_z = tail ? 0 : c;
         p.nseg = 1;
         p.M = (int)N4;
-        p.N = which == 0 ? hidden : 64;
+        p.N = which == 0 ? hidden : (int)IC;
         p.K = (int)(tail ? (long long)rem * B : rows_c);
         p.C = S.partial + (long long)c * per_chunk + (which == 0 ? 0 : H);
         p.ldc = ld_p;
@@ -447,10 +529,32 @@ extern "C" int msf_lstm_backward(const msf_lstm_seq* seqs, int32_t n, int64_t ba
       }
     }
     if ((rc = tb.flush())) return rc;
-    const long long total = N4 * (H + features + 1);
-    lstm_wgrad_reduce_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(S.partial, chunks, hidden, features, S.d_w_ih,
-                                                                           S.d_w_hh, S.d_bias);
+    float* bias_partial = nullptr;
+    if (stacked) {
+      bias_partial = S.partial + (size_t)chunks * per_chunk;
+      lstm_colsum_kernel<<<LB_COLSUM_BLOCKS, 256, 0, st>>>(da, (long long)steps * B, (int)N4, bias_partial);
+      MSF_LAUNCH_CHECK();
+    }
+    const long long total = N4 * (H + S.features + 1);
+    lstm_wgrad_reduce_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(
+        S.partial, chunks, hidden, S.features, (int)IC, bias_partial, LB_COLSUM_BLOCKS, S.d_w_ih, S.d_w_hh, S.d_bias);
     MSF_LAUNCH_CHECK();
   }
+  return MSF_OK;
+}
+
+extern "C" int msf_lstm_dropout(const void* in_bf16, void* out_bf16, int64_t rows, int32_t cols, float p, uint64_t seed,
+                                uint64_t offset, int32_t layer, void* stream) {
+  using namespace msf;
+  MSF_REQUIRE(in_bf16 && out_bf16 && rows >= 0 && cols >= 8 && cols % 8 == 0 && p >= 0.0f && p < 1.0f,
+              "msf_lstm_dropout: bad arguments (cols %d must be a multiple of 8)", cols);
+  if (rows == 0) return MSF_OK;
+  DropCfg d;
+  d.seed = seed; d.offset = offset; d.p = p; d.scale = 1.0f / (1.0f - p); d.active = 1; d.state = nullptr;
+  long long blocks = ceil_div(rows * (cols / 8), 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  lstm_dropout_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      static_cast<const __nv_bfloat16*>(in_bf16), static_cast<__nv_bfloat16*>(out_bf16), rows, cols, d, layer);
+  MSF_LAUNCH_CHECK();
   return MSF_OK;
 }

@@ -50,10 +50,16 @@ struct LstmSeqLaunch {
   float* cell[MSF_LSTM_MAX_SEQS];
   float* h_out[MSF_LSTM_MAX_SEQS];
   const int* lengths[MSF_LSTM_MAX_SEQS];   // valid steps per window, or nullptr (all steps)
-  // training mode (SAVE): hbuf[.][0] = h_all [T+1][B][H] (m[.].h[0] over it), every step's gate activations and cell
-  // state are kept for the backward pass (lstm_bwd.cu)
+  // HALL (template): hbuf[.][0] = h_all [T+1][B][H] (m[.].h[0] over it): every hidden state is kept — the input of the
+  // next layer and of the backward pass.  Training mode (gates != nullptr): every step's gate activations and cell
+  // state are kept as well (lstm_bwd.cu)
   __nv_bfloat16* gates[MSF_LSTM_MAX_SEQS];   // [T][B][4H] bf16, columns gate-interleaved (4u + {i,f,g,o})
   float* c_all[MSF_LSTM_MAX_SEQS];           // [T][B*H] fp32, each step in the cell layout below
+  // layers above the first: the input's share of the gate pre-activations, z_t = in_t W_ih^T, computed beforehand by
+  // one GEMM over all steps ([T][B][4H] bf16, same column order; may be the `gates` buffer itself: read, then
+  // overwritten in place).  Then there is no x / W_ih k-block (nkbx = 0).
+  const __nv_bfloat16* zin[MSF_LSTM_MAX_SEQS];
+  int nkbx;
   int n, rows, steps, hidden, kbh, cs, cps, row_tiles, stages;
   int dbg;   // MSF_LSTM_DBG: 1 no async-proxy fence, 2 no __threadfence, 8 no cell-state traffic, 16 stamps
   long long h_slice;
@@ -100,7 +106,8 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t off0 = smem_u32(smem_raw);
   const uint32_t base = (off0 + 1023u) & ~1023u;
-  const int KBH = L.kbh, NKB = L.kbh + 1, STAGES = L.stages;
+  const int KBH = L.kbh, NKB = L.kbh + L.nkbx, STAGES = L.stages;
+  const bool HASX = L.nkbx != 0;
   const uint32_t w_base = base;                                    // NKB weight k-blocks, resident
   const uint32_t ring_base = w_base + (uint32_t)NKB * LS_W_BYTES;  // A k-blocks
   const uint32_t bar_base = ring_base + (uint32_t)STAGES * LS_A_BYTES;
@@ -121,11 +128,11 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
   const LstmSeqMaps& M = L.m[seq];
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&M.x);
+    if (HASX) tma_prefetch_desc(&M.x);
     tma_prefetch_desc(&M.h[0]);
     if (!SAVE) tma_prefetch_desc(&M.h[1]);
     tma_prefetch_desc(&M.whh);
-    tma_prefetch_desc(&M.wih);
+    if (HASX) tma_prefetch_desc(&M.wih);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -164,7 +171,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
   if (warp == 0 && lane == 0) {   // this CTA's 256 gate columns of W_hh and W_ih: resident for the whole sequence
     mbar_expect_tx(w_full, (uint32_t)NKB * LS_W_BYTES);
     for (int kb = 0; kb < KBH; ++kb) tma_load_3d(w_base + kb * LS_W_BYTES, &M.whh, 0, rank * 256, kb, w_full);
-    tma_load_3d(w_base + KBH * LS_W_BYTES, &M.wih, 0, rank * 256, 0, w_full);
+    if (HASX) tma_load_3d(w_base + KBH * LS_W_BYTES, &M.wih, 0, rank * 256, 0, w_full);
   }
   if (warp == 1 && lane == 0) {
     mbar_wait(w_full, 0u);
@@ -190,10 +197,10 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
           tma_load_3d(ring_base + stage * LS_A_BYTES, &M.x, 0, (slot + i * L.cps) * 128, tt, full_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         };
-        if (t == 0) load_x(0, 0);
+        if (HASX && t == 0) load_x(0, 0);
         for (int i = 0; i < my_tiles; ++i) {
           const int row0 = (slot + i * L.cps) * 128;
-          if (i > 0) load_x(t, i);
+          if (HASX && i > 0) load_x(t, i);
           for (int kb = 0; kb < KBH; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             mbar_expect_tx(full_bar(stage), LS_A_BYTES);
@@ -202,7 +209,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
-        if (t + 1 < L.steps) load_x(t + 1, 0);
+        if (HASX && t + 1 < L.steps) load_x(t + 1, 0);
         if (stamp) g_ls_stamps[0] += clock64() - t_step;
       }
     } else if (warp == 1) {
@@ -214,7 +221,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
           for (int kk = 0; kk < NKB; ++kk) {
-            const int kb = kk == 0 ? KBH : kk - 1;   // the producer's order: x_t, then the k-blocks of h_{t-1}
+            const int kb = !HASX ? kk : kk == 0 ? KBH : kk - 1;   // the producer's order: x_t, then the k-blocks of h_{t-1}
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
             const uint32_t a_addr = ring_base + stage * LS_A_BYTES, b_addr = w_base + kb * LS_W_BYTES;
@@ -236,10 +243,12 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
                                    : reinterpret_cast<__nv_bfloat16*>(L.hbuf[seq][par ^ 1]);
       const __nv_bfloat16* h_prev = SAVE ? reinterpret_cast<const __nv_bfloat16*>(L.hbuf[seq][0]) + (long long)t * BH
                                          : reinterpret_cast<const __nv_bfloat16*>(L.hbuf[seq][par]);
-      // SAVE: c_{t-1} is read from step t-1's slice (zeros at t = 0) and c_t goes to step t's
-      float* cellp = SAVE ? L.c_all[seq] + (long long)t * BH : L.cell[seq];
-      const float* cell_prev = SAVE ? cellp - BH : cellp;
-      __nv_bfloat16* gates_t = SAVE ? L.gates[seq] + (long long)t * BH * 4 : nullptr;
+      // training mode: c_{t-1} is read from step t-1's slice (zeros at t = 0) and c_t goes to step t's
+      const bool tape = SAVE && L.gates[seq] != nullptr;
+      float* cellp = tape ? L.c_all[seq] + (long long)t * BH : L.cell[seq];
+      const float* cell_prev = tape ? cellp - BH : cellp;
+      __nv_bfloat16* gates_t = tape ? L.gates[seq] + (long long)t * BH * 4 : nullptr;
+      const __nv_bfloat16* zin_t = L.zin[seq] != nullptr ? L.zin[seq] + (long long)t * BH * 4 : nullptr;
       const int* lens = L.lengths[seq];
       float* h32 = L.h_out[seq];
       for (int i = 0; i < my_tiles; ++i, ++cnt) {
@@ -259,7 +268,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
         float4 cprev[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g)
-          cprev[g] = (cell_io && !(SAVE && t == 0))
+          cprev[g] = (cell_io && !(tape && t == 0))
                          ? *reinterpret_cast<const float4*>(cell_prev + ls_cell_index(tile, r, ubase + 4 * g, H, ragged))
                          : make_float4(0.f, 0.f, 0.f, 0.f);
         mbar_wait(acc_full(acc), (cnt >> 1) & 1u);
@@ -269,8 +278,22 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint32_t a[16];
+          uint4 z0 = make_uint4(0u, 0u, 0u, 0u), z1 = z0;
+          if (zin_t != nullptr && cell_io) {   // the input's share of these 16 pre-activations
+            const uint4* zp = reinterpret_cast<const uint4*>(zin_t + (long long)row * 4 * H + 4 * (ubase + 4 * g));
+            z0 = zp[0];
+            z1 = zp[1];
+          }
           tmem_ld16_issue(taddr + (uint32_t)(16 * g), a);
           tmem_wait16(a);
+          if (zin_t != nullptr) {
+            const uint32_t zw[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              a[2 * e] = __float_as_uint(__uint_as_float(a[2 * e]) + __uint_as_float(zw[e] << 16));
+              a[2 * e + 1] = __float_as_uint(__uint_as_float(a[2 * e + 1]) + __uint_as_float(zw[e] & 0xffff0000u));
+            }
+          }
           const float cp[4] = {cprev[g].x, cprev[g].y, cprev[g].z, cprev[g].w};
           float cn[4], hn[4], go[4];
           uint32_t gs[8];   // SAVE: the 16 gate activations of these 4 units as bf16 pairs (i,f | g,o per unit)
@@ -282,7 +305,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
             const float gi = fmaf(0.5f, t_if.x, 0.5f), gf = fmaf(0.5f, t_if.y, 0.5f);
             go[j] = fmaf(0.5f, t_go.y, 0.5f);
             cn[j] = fmaf(gf, cp[j], gi * t_go.x);
-            if (SAVE) {
+            if (tape) {
               __nv_bfloat162 s0 = __floats2bfloat162_rn(gi, gf), s1 = __floats2bfloat162_rn(t_go.x, go[j]);
               gs[2 * j] = *reinterpret_cast<uint32_t*>(&s0);
               gs[2 * j + 1] = *reinterpret_cast<uint32_t*>(&s1);
@@ -297,7 +320,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
           const int u0 = ubase + 4 * g;
           if (cell_io)
             *reinterpret_cast<float4*>(cellp + ls_cell_index(tile, r, u0, H, ragged)) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-          if (SAVE && cell_io) {
+          if (tape && cell_io) {
             uint4* gd = reinterpret_cast<uint4*>(gates_t + (long long)row * 4 * H + 4 * u0);
             gd[0] = make_uint4(gs[0], gs[1], gs[2], gs[3]);
             gd[1] = make_uint4(gs[4], gs[5], gs[6], gs[7]);
@@ -397,19 +420,32 @@ int lstm_seq_launch(const msf_lstm_seq* seqs, int n, long long batch, int steps,
   if (cps > L.row_tiles) cps = L.row_tiles;
   L.cps = cps;
   int rc;
-  const bool save = seqs[0].gates != nullptr;   // training mode: keep what the backward pass needs (lstm_bwd.cu)
+  const bool save = seqs[0].h_all != nullptr;   // every hidden state kept ([T+1][B][H]): lower layers, training mode
+  const bool zin = seqs[0].z_in != nullptr;     // layers above the first: the input's share comes precomputed
+  L.nkbx = zin ? 0 : 1;
   for (int i = 0; i < n; ++i) {
     const msf_lstm_seq& S = seqs[i];
-    MSF_REQUIRE(S.x_bf16 && S.w_hh && S.w_ih && S.bias && S.h_out, "msf_lstm_forward: null pointer in sequence %d", i);
-    MSF_REQUIRE((S.gates != nullptr) == save, "msf_lstm_forward: training buffers in some sequences only");
-    if ((rc = tc_encode_map(&L.m[i].x, S.x_bf16, B, 64, 64, steps, slice, 64, 128))) return rc;
+    MSF_REQUIRE(S.w_hh && S.bias && S.h_out, "msf_lstm_forward: null pointer in sequence %d", i);
+    MSF_REQUIRE((S.h_all != nullptr) == save && (S.z_in != nullptr) == zin,
+                "msf_lstm_forward: the sequences of one call must use the same mode (h_all / z_in)");
+    MSF_REQUIRE(S.gates == nullptr || (S.h_all && S.c_all),
+                "msf_lstm_forward: training mode needs h_all, gates and c_all (sequence %d)", i);
+    if (zin) {
+      L.zin[i] = static_cast<const __nv_bfloat16*>(S.z_in);
+      L.m[i].x = L.m[i].wih = CUtensorMap{};
+    } else {
+      MSF_REQUIRE(S.x_bf16 && S.w_ih, "msf_lstm_forward: null pointer in sequence %d", i);
+      if ((rc = tc_encode_map(&L.m[i].x, S.x_bf16, B, 64, 64, steps, slice, 64, 128))) return rc;
+      if ((rc = tc_encode_map(&L.m[i].wih, S.w_ih, N4, 64, 64, 1, 0, 64, 256))) return rc;
+    }
     if (save) {
-      MSF_REQUIRE(S.h_all && S.c_all, "msf_lstm_forward: training mode needs h_all, gates and c_all (sequence %d)", i);
       if ((rc = tc_encode_map(&L.m[i].h[0], S.h_all, B, hidden, hidden, steps + 1, B * hidden, 64, 128))) return rc;
       L.m[i].h[1] = L.m[i].h[0];
       L.hbuf[i][0] = S.h_all; L.hbuf[i][1] = S.h_all;
       L.gates[i] = static_cast<__nv_bfloat16*>(S.gates);
       L.c_all[i] = S.c_all;
+      MSF_REQUIRE(S.gates != nullptr || S.cell != nullptr, "msf_lstm_forward: null cell buffer in sequence %d", i);
+      L.cell[i] = S.cell;
     } else {
       MSF_REQUIRE(S.h_a && S.h_b && S.cell, "msf_lstm_forward: null pointer in sequence %d", i);
       if ((rc = tc_encode_map(&L.m[i].h[0], S.h_a, B, 64, 64, L.kbh, slice, 64, 128))) return rc;
@@ -418,20 +454,19 @@ int lstm_seq_launch(const msf_lstm_seq* seqs, int n, long long batch, int steps,
       L.cell[i] = S.cell;
     }
     if ((rc = tc_encode_map(&L.m[i].whh, S.w_hh, N4, 64, 64, L.kbh, N4 * 64, 64, 256))) return rc;
-    if ((rc = tc_encode_map(&L.m[i].wih, S.w_ih, N4, 64, 64, 1, 0, 64, 256))) return rc;
     L.bias[i] = S.bias;
     L.h_out[i] = S.h_out;
     L.lengths[i] = S.lengths;
   }
   const size_t fixed = 1024 + LS_BIAS_OFF + 256 * 4 + 64;
-  const size_t weights = (size_t)(L.kbh + 1) * LS_W_BYTES;
+  const size_t weights = (size_t)(L.kbh + L.nkbx) * LS_W_BYTES;
   int stages = (int)((LS_SMEM_LIMIT - fixed - weights) / LS_A_BYTES);
   if (stages > LS_MAX_STAGES) stages = LS_MAX_STAGES;
   MSF_REQUIRE(stages >= 2, "lstm_seq: not enough shared memory for hidden %d", hidden);
   L.stages = stages;
   const size_t smem = fixed + weights + (size_t)stages * LS_A_BYTES;
   const int grid = n * cps * L.cs;
-  if (prof_enabled()) prof_begin("LSTM sequence", 2.0 * (double)B * (hidden + 64) * 4.0 * hidden * steps * n, st);
+  if (prof_enabled()) prof_begin("LSTM sequence", 2.0 * (double)B * (hidden + 64 * L.nkbx) * 4.0 * hidden * steps * n, st);
   auto kernel = save ? lstm_seq_kernel<true> : lstm_seq_kernel<false>;
   MSF_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   MSF_CHECK_CUDA(ls_launch(kernel, dim3(grid), dim3(LS_THREADS), smem, st, L.cs, L));

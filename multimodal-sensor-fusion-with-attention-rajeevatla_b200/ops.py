@@ -781,20 +781,98 @@ def lstm_forward(xs: Sequence[torch.Tensor], packed: Sequence[tuple], hidden: in
 
 
 class LstmTape:
-    """What msf_lstm_forward keeps in training mode for msf_lstm_backward (one encoder)."""
+    """What msf_lstm_forward keeps in training mode for msf_lstm_backward (one layer of one encoder): the layer's
+    input as the weight-gradient GEMM reads it (``inp``: [T][B][64] padded windows with the ones column for the first
+    layer, the [T][B][H] (dropped-out) hidden states of the layer below otherwise), h_{t-1} / gate activations / cell
+    states of every step, and the transposed weights of the backward GEMMs."""
 
-    def __init__(self, x_packed, packed, w_hh_t, h_all, gates, c_all, h_out, lengths, features, hidden):
-        self.x, self.packed, self.w_hh_t = x_packed, packed, w_hh_t
+    def __init__(self, inp, in_cols, features, w_hh_t, w_ih_t, h_all, gates, c_all, h_out, lengths, hidden, layer=0,
+                 drop=None):
+        self.inp, self.in_cols, self.features = inp, in_cols, features
+        self.w_hh_t, self.w_ih_t = w_hh_t, w_ih_t
         self.h_all, self.gates, self.c_all, self.h_out = h_all, gates, c_all, h_out
-        self.lengths, self.features, self.hidden = lengths, features, hidden
+        self.lengths, self.hidden, self.layer, self.drop = lengths, hidden, layer, drop
 
 
-def lstm_pack_weights_t(weight_hh: torch.Tensor) -> torch.Tensor:
-    """weight_hh_l0 (4H, H) -> the backward operand of msf_lstm_backward: [H][4H] bf16 with
-    ``out[n][4u+g] = weight_hh[g*H+u][n]`` (gate-interleaved columns, like the gate buffers)."""
-    H4, H = weight_hh.shape
-    inter = weight_hh.detach().to(torch.float32).view(4, H, H).permute(1, 0, 2).reshape(4 * H, H)
-    return inter.t().contiguous().to(torch.bfloat16)
+def _lstm_interleave(w: torch.Tensor, hidden: int) -> torch.Tensor:
+    """(4H, K) rows in nn.LSTM's gate-major order -> rows 4u+g (fp32)."""
+    return w.detach().to(torch.float32).view(4, hidden, -1).permute(1, 0, 2).reshape(4 * hidden, -1)
+
+
+def lstm_pack_weights_t(weight: torch.Tensor) -> torch.Tensor:
+    """weight_hh (4H, H) or an upper layer's weight_ih (4H, H) -> the operand of the backward GEMMs: [K][4H] bf16
+    with ``out[n][4u+g] = weight[g*H+u][n]`` (gate-interleaved columns, like the gate buffers)."""
+    return _lstm_interleave(weight, weight.shape[0] // 4).t().contiguous().to(torch.bfloat16)
+
+
+def lstm_pack_upper(weight_ih, weight_hh, bias_ih, bias_hh):
+    """Parameters of a layer above the first -> (w_hh k-blocked [H/64][4H][64], w_ih [4H][H] for the input GEMM, bias
+    [4H]), rows gate-interleaved, bf16 / fp32."""
+    H = weight_hh.shape[1]
+    if H % 64 != 0:
+        raise N.MsfError(f"msf_lstm_forward needs hidden % 64 == 0 (got {H})")
+    w_hh = _lstm_interleave(weight_hh, H).view(4 * H, H // 64, 64).permute(1, 0, 2).contiguous().to(torch.bfloat16)
+    w_ih = _lstm_interleave(weight_ih, H).contiguous().to(torch.bfloat16)
+    bias = torch.zeros(4 * H, dtype=torch.float32, device=weight_hh.device)
+    for b in (bias_ih, bias_hh):
+        if b is not None:
+            bias = bias + b.detach().to(torch.float32)
+    return w_hh, w_ih, bias.view(4, H).t().reshape(4 * H).contiguous()
+
+
+def _lstm_lengths(lengths, B, T, dev):
+    if lengths is None:
+        return None
+    ln = lengths.to(device=dev, dtype=torch.int32).contiguous()
+    if ln.numel() != B or int(ln.min()) < 1 or int(ln.max()) > T:
+        raise N.MsfError(f"lengths must be {B} integers in [1, {T}]")
+    return ln
+
+
+def lstm_forward_stack(x: torch.Tensor, layers: Sequence[tuple], hidden: int,
+                       lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``h_n[-1]`` of a stacked nn.LSTM in inference mode (src/encoders.py:54-65,135-166 with num_layers >= 1):
+    ``x`` (B, T, F) fp32, ``layers`` = per layer ``(weight_ih, weight_hh, bias_ih, bias_hh)``.  Every layer is one
+    persistent launch (msf_lstm_forward); a layer above the first gets the input's share of its gate
+    pre-activations from ONE tensor-core GEMM over all steps of the layer below (msf_gemm_bf16 -> z_in)."""
+    require_cuda("lstm_forward_stack")
+    B, T, F = x.shape
+    dev = x.device
+    ln = _lstm_lengths(lengths, B, T, dev)
+    prev, h_out = None, None
+    for l, w in enumerate(layers):
+        last = l == len(layers) - 1
+        seqs = (N.LstmSeq * 1)()
+        q = seqs[0]
+        keep = []
+        if l == 0:
+            w_hh, w_ih, bias = lstm_pack_weights(*w)
+            xp = lstm_pack_input(x.to(torch.float32))
+            q.x_bf16, q.w_ih = _p(xp), _p(w_ih)
+            keep += [xp, w_ih]
+        else:
+            w_hh, w_ih, bias = lstm_pack_upper(*w)
+            z = gemm_bf16(prev[1:].view(T * B, hidden), w_ih, out_dtype=torch.bfloat16)
+            q.z_in = _p(z)
+            keep += [z]
+        h_out = torch.empty(B, hidden, dtype=torch.float32, device=dev)
+        cell = torch.zeros(B, hidden, dtype=torch.float32, device=dev)
+        q.w_hh, q.bias, q.cell, q.h_out = _p(w_hh), _p(bias), _p(cell), _p(h_out)
+        if ln is not None:
+            q.lengths = _p(ln)
+        if last:
+            h_a = torch.zeros(hidden // 64, B, 64, dtype=torch.bfloat16, device=dev)
+            h_b = torch.zeros(hidden // 64, B, 64, dtype=torch.bfloat16, device=dev)
+            q.h_a, q.h_b = _p(h_a), _p(h_b)
+            keep += [h_a, h_b]
+        else:
+            h_all = torch.empty(T + 1, B, hidden, dtype=torch.bfloat16, device=dev)
+            h_all[0].zero_()
+            q.h_all = _p(h_all)
+        N.check(N.lib().msf_lstm_forward(seqs, 1, B, T, hidden, _stream()))
+        prev = None if last else h_all
+        del keep
+    return h_out
 
 
 def lstm_train_forward(xs: Sequence[torch.Tensor], weights: Sequence[tuple], hidden: int,
@@ -808,7 +886,7 @@ def lstm_train_forward(xs: Sequence[torch.Tensor], weights: Sequence[tuple], hid
     B, T, _ = xs[0].shape
     dev = xs[0].device
     seqs = (N.LstmSeq * n)()
-    tapes = []
+    tapes, keep = [], []
     for i, (x, (w_ih, w_hh, b_ih, b_hh)) in enumerate(zip(xs, weights)):
         F = x.shape[2]
         xp = lstm_pack_input(x.to(torch.float32), ones_column=True)
@@ -818,23 +896,69 @@ def lstm_train_forward(xs: Sequence[torch.Tensor], weights: Sequence[tuple], hid
         gates = torch.empty(T, B, 4 * hidden, dtype=torch.bfloat16, device=dev)
         c_all = torch.empty(T, B * hidden, dtype=torch.float32, device=dev)
         h_out = torch.empty(B, hidden, dtype=torch.float32, device=dev)
-        ln = None
-        if lengths is not None and lengths[i] is not None:
-            ln = lengths[i].to(device=dev, dtype=torch.int32).contiguous()
-            if ln.numel() != B or int(ln.min()) < 1 or int(ln.max()) > T:
-                raise N.MsfError(f"lengths must be {B} integers in [1, {T}]")
+        ln = _lstm_lengths(None if lengths is None else lengths[i], B, T, dev)
+        if ln is not None:
             seqs[i].lengths = _p(ln)
         seqs[i].x_bf16, seqs[i].w_hh, seqs[i].w_ih, seqs[i].bias = _p(xp), _p(packed[0]), _p(packed[1]), _p(packed[2])
         seqs[i].h_all, seqs[i].gates, seqs[i].c_all, seqs[i].h_out = _p(h_all), _p(gates), _p(c_all), _p(h_out)
-        tapes.append(LstmTape(xp, packed, lstm_pack_weights_t(w_hh), h_all, gates, c_all, h_out, ln, F, hidden))
+        keep.append(packed)
+        tapes.append(LstmTape(xp, 0, F, lstm_pack_weights_t(w_hh), None, h_all, gates, c_all, h_out, ln, hidden))
     N.check(N.lib().msf_lstm_forward(seqs, n, B, T, hidden, _stream()))
     return tapes
 
 
-def lstm_backward(tapes: Sequence[LstmTape], d_h_out: Sequence[torch.Tensor]):
-    """Gradients of the recurrences recorded by ``lstm_train_forward``: per encoder ``(d weight_ih, d weight_hh,
-    d bias)`` in nn.LSTM's layout (``d bias`` is the gradient of bias_ih and of bias_hh alike).  Overwrites the
-    tapes' gate buffers (msf_lstm_backward): a tape can be walked backwards once."""
+def lstm_train_forward_stack(x: torch.Tensor, layers: Sequence[tuple], hidden: int,
+                             lengths: Optional[torch.Tensor] = None, dropout_p: float = 0.0, seed: int = 0,
+                             offset: int = 0) -> List[LstmTape]:
+    """Training-mode forward of ONE stacked nn.LSTM (num_layers = len(layers)): one tape per layer, bottom first;
+    ``tapes[-1].h_out`` is ``h_n[-1]``.  Between the layers nn.LSTM's dropout (p = ``dropout_p``) is applied with the
+    library's Philox multipliers (msf_lstm_dropout: site 4, sub = layer, keyed by ``seed`` / ``offset``).  A layer
+    above the first reads the input's share of its pre-activations from one GEMM over all steps, written straight
+    into its gate buffer (z_in == gates: read, then overwritten in place by the activations)."""
+    require_cuda("lstm_train_forward_stack")
+    B, T, F = x.shape
+    dev = x.device
+    ln = _lstm_lengths(lengths, B, T, dev)
+    tapes: List[LstmTape] = []
+    for l, w in enumerate(layers):
+        if l == 0:
+            tp = lstm_train_forward([x], [w], hidden, None if ln is None else [ln])[0]
+            tapes.append(tp)
+            continue
+        below = tapes[-1].h_all[1:].view(T * B, hidden)
+        drop = None
+        if dropout_p > 0.0:
+            inp = torch.empty_like(below)
+            N.check(N.lib().msf_lstm_dropout(_p(below), _p(inp), T * B, hidden, float(dropout_p), seed & (2**64 - 1),
+                                             offset & (2**64 - 1), l, _stream()))
+            drop = (float(dropout_p), seed, offset)
+        else:
+            inp = below
+        w_hh, w_ih, bias = lstm_pack_upper(*w)
+        gates = gemm_bf16(inp, w_ih, out_dtype=torch.bfloat16).view(T, B, 4 * hidden)
+        h_all = torch.empty(T + 1, B, hidden, dtype=torch.bfloat16, device=dev)
+        h_all[0].zero_()
+        c_all = torch.empty(T, B * hidden, dtype=torch.float32, device=dev)
+        h_out = torch.empty(B, hidden, dtype=torch.float32, device=dev)
+        seqs = (N.LstmSeq * 1)()
+        q = seqs[0]
+        q.w_hh, q.bias, q.z_in, q.gates = _p(w_hh), _p(bias), _p(gates), _p(gates)
+        q.h_all, q.c_all, q.h_out = _p(h_all), _p(c_all), _p(h_out)
+        if ln is not None:
+            q.lengths = _p(ln)
+        N.check(N.lib().msf_lstm_forward(seqs, 1, B, T, hidden, _stream()))
+        tapes.append(LstmTape(inp, hidden, hidden, lstm_pack_weights_t(w[1]), lstm_pack_weights_t(w[0]), h_all, gates,
+                              c_all, h_out, ln, hidden, layer=l, drop=drop))
+    return tapes
+
+
+def lstm_backward(tapes: Sequence[LstmTape], d_h_out: Sequence[Optional[torch.Tensor]],
+                  d_h_all: Optional[Sequence[Optional[torch.Tensor]]] = None, release: bool = True):
+    """Gradients of the recurrences recorded by ``lstm_train_forward`` (one layer each, up to 4 per call): per tape
+    ``(d weight_ih, d weight_hh, d bias)`` in nn.LSTM's layout (``d bias`` is the gradient of bias_ih and of bias_hh
+    alike).  ``d_h_out[i]``: gradient of the tape's ``h_out`` or None; ``d_h_all[i]``: [T][B][H] bf16 gradient of
+    every step's hidden state (from the layer above) or None.  Overwrites the tapes' gate buffers with the gradients
+    of the gate pre-activations (msf_lstm_backward): a tape can be walked backwards once."""
     require_cuda("lstm_backward")
     n = len(tapes)
     T1, B, hidden = tapes[0].h_all.shape
@@ -844,48 +968,76 @@ def lstm_backward(tapes: Sequence[LstmTape], d_h_out: Sequence[torch.Tensor]):
     N.check(N.lib().msf_lstm_backward_scratch_bytes(B, T, hidden, ctypes.byref(nbytes)))
     seqs = (N.LstmSeq * n)()
     keep, outs = [], []
-    feats = {tp.features for tp in tapes}
-    if len(feats) != 1:   # one `features` argument per call: encoders of different width go in separate calls
-        raise N.MsfError("lstm_backward: encoders of one call must share input_dim")
-    for i, (tp, dh) in enumerate(zip(tapes, d_h_out)):
+    for i, tp in enumerate(tapes):
         if tp.gates is None:
             raise N.MsfError("lstm_backward: this tape was already walked backwards")
-        dh = dh.to(device=dev, dtype=torch.float32).contiguous()
         dc = torch.zeros(B * hidden, dtype=torch.float32, device=dev)
         partial = torch.empty(nbytes.value // 4, dtype=torch.float32, device=dev)
         d_w_ih = torch.empty(4 * hidden, tp.features, dtype=torch.float32, device=dev)
         d_w_hh = torch.empty(4 * hidden, hidden, dtype=torch.float32, device=dev)
         d_b = torch.empty(4 * hidden, dtype=torch.float32, device=dev)
-        keep += [dh, dc, partial]
+        keep += [dc, partial]
         outs.append((d_w_ih, d_w_hh, d_b))
         q = seqs[i]
-        q.x_bf16, q.h_all, q.gates, q.c_all, q.w_hh_t = _p(tp.x), _p(tp.h_all), _p(tp.gates), _p(tp.c_all), _p(tp.w_hh_t)
-        q.d_h_out, q.dc, q.partial = _p(dh), _p(dc), _p(partial)
-        q.d_w_ih, q.d_w_hh, q.d_bias = _p(d_w_ih), _p(d_w_hh), _p(d_b)
+        q.x_bf16, q.h_all, q.gates, q.c_all, q.w_hh_t = _p(tp.inp), _p(tp.h_all), _p(tp.gates), _p(tp.c_all), _p(tp.w_hh_t)
+        q.dc, q.partial = _p(dc), _p(partial)
+        q.d_w_ih, q.d_w_hh, q.d_bias, q.features, q.in_cols = _p(d_w_ih), _p(d_w_hh), _p(d_b), tp.features, tp.in_cols
+        if d_h_out[i] is not None:
+            dh = d_h_out[i].to(device=dev, dtype=torch.float32).contiguous()
+            keep.append(dh)
+            q.d_h_out = _p(dh)
+        if d_h_all is not None and d_h_all[i] is not None:
+            da = d_h_all[i]
+            assert da.dtype == torch.bfloat16 and da.is_contiguous() and da.numel() == T * B * hidden
+            keep.append(da)
+            q.d_h_all = _p(da)
         if tp.lengths is not None:
             q.lengths = _p(tp.lengths)
-    N.check(N.lib().msf_lstm_backward(seqs, n, B, T, hidden, tapes[0].features, _stream()))
-    for tp in tapes:
-        keep += [tp.x, tp.h_all, tp.gates, tp.c_all, tp.w_hh_t] + ([tp.lengths] if tp.lengths is not None else [])
-        tp.gates = None
-    for t in keep:   # asynchronous launches: keep the buffers alive on this stream
-        t.record_stream(torch.cuda.current_stream(dev))
+    N.check(N.lib().msf_lstm_backward(seqs, n, B, T, hidden, _stream()))
+    if release:
+        for tp in tapes:
+            tp.gates = None
     return outs
 
 
+def lstm_backward_stack(tapes: Sequence[LstmTape], d_h_out: torch.Tensor):
+    """Backward pass through the tapes of ``lstm_train_forward_stack`` (top layer first): per layer
+    ``(d weight_ih, d weight_hh, d bias)``, bottom first.  Between two layers the gradient of the lower layer's hidden
+    states is one GEMM over all steps (d a of the upper layer times its W_ih) through the same dropout mask."""
+    grads: List[Optional[tuple]] = [None] * len(tapes)
+    d_all = None
+    for l in reversed(range(len(tapes))):
+        tp = tapes[l]
+        T1, B, hidden = tp.h_all.shape
+        grads[l] = lstm_backward([tp], [d_h_out if l == len(tapes) - 1 else None], [d_all], release=False)[0]
+        if l > 0:
+            d_all = gemm_bf16(tp.gates.view((T1 - 1) * B, 4 * hidden), tp.w_ih_t, out_dtype=torch.bfloat16)
+            if tp.drop is not None:
+                p, seed, offset = tp.drop
+                N.check(N.lib().msf_lstm_dropout(_p(d_all), _p(d_all), (T1 - 1) * B, hidden, p, seed & (2**64 - 1),
+                                                 offset & (2**64 - 1), l, _stream()))
+        tp.gates = tp.c_all = tp.h_all = tp.inp = None
+    return grads
+
+
 class LstmLastHidden(torch.autograd.Function):
-    """``h_T = LSTM(x)`` of one single-layer nn.LSTM with gradients for its four parameters (none for ``x``: the
-    encoders' inputs are data): msf_lstm_forward in training mode + msf_lstm_backward."""
+    """``h_n[-1] = LSTM(x)`` of one (stacked) nn.LSTM with gradients for its parameters (none for ``x``: the
+    encoders' inputs are data): msf_lstm_forward in training mode + msf_lstm_backward per layer.  ``params`` are
+    (weight_ih, weight_hh, bias_ih, bias_hh) of every layer, flattened, bottom layer first."""
 
     @staticmethod
-    def forward(ctx, x, weight_ih, weight_hh, bias_ih, bias_hh, lengths):
-        tape = lstm_train_forward([x], [(weight_ih, weight_hh, bias_ih, bias_hh)], weight_hh.shape[1],
-                                  None if lengths is None else [lengths])[0]
-        ctx.tape = tape
-        ctx.has_bias = bias_ih is not None, bias_hh is not None
-        return tape.h_out
+    def forward(ctx, x, lengths, dropout_p, seed, *params):
+        layers = [tuple(params[4 * l:4 * l + 4]) for l in range(len(params) // 4)]
+        tapes = lstm_train_forward_stack(x, layers, layers[0][1].shape[1], lengths, dropout_p, seed)
+        ctx.tapes = tapes
+        ctx.has = [p is not None for p in params]
+        return tapes[-1].h_out
 
     @staticmethod
     def backward(ctx, d_h):
-        d_w_ih, d_w_hh, d_b = lstm_backward([ctx.tape], [d_h])[0]
-        return (None, d_w_ih, d_w_hh, d_b if ctx.has_bias[0] else None, d_b.clone() if ctx.has_bias[1] else None, None)
+        grads = lstm_backward_stack(ctx.tapes, d_h)
+        ctx.tapes = None
+        flat = []
+        for (d_w_ih, d_w_hh, d_b) in grads:
+            flat += [d_w_ih, d_w_hh, d_b, d_b.clone()]
+        return (None, None, None, None, *[g if has else None for g, has in zip(flat, ctx.has)])

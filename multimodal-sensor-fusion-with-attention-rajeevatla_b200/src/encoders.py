@@ -53,35 +53,51 @@ def _dense(layer: nn.Module, x: torch.Tensor, relu: bool = False) -> torch.Tenso
 
 def _lstm_tensor_core_ok(enc, sequence: torch.Tensor, lengths) -> bool:
     """The hand-written recurrence (msf_lstm_forward / msf_lstm_backward: bf16 operands, fp32 state, <= 1e-2) is used
-    when the caller opted into bf16 (``encoder.precision = "bf16"`` or MSF_PRECISION=bf16): single-layer LSTM, CUDA
-    input, hidden % 64 == 0, input_dim <= 64; per-window ``lengths`` (the reference packs ragged windows,
-    src/encoders.py:140-152) on the persistent kernel (hidden <= 256).  With gradients wanted for the LSTM's
-    parameters it runs in training mode (hidden <= 256, input_dim <= 63); a gradient with respect to the input
+    when the caller opted into bf16 (``encoder.precision = "bf16"`` or MSF_PRECISION=bf16): uni-directional LSTM of
+    any depth, CUDA input, hidden % 64 == 0, input_dim <= 64; per-window ``lengths`` (the reference packs ragged
+    windows, src/encoders.py:140-152), stacked layers and the training mode (gradients wanted for the LSTM's
+    parameters; input_dim <= 63) on the persistent kernels (hidden <= 256).  A gradient with respect to the input
     sequence is not provided (the encoders' inputs are data) and keeps the library recurrence."""
     prec = getattr(enc, "precision", None) or os.environ.get("MSF_PRECISION", "fp32")
     rnn = enc.rnn
     if not (prec == "bf16" and enc.encoder_type == "lstm" and sequence.is_cuda
-            and isinstance(rnn, nn.LSTM) and rnn.num_layers == 1 and not rnn.bidirectional and rnn.proj_size == 0
+            and isinstance(rnn, nn.LSTM) and not rnn.bidirectional and rnn.proj_size == 0
             and rnn.hidden_size % 64 == 0 and rnn.input_size <= 64):
         return False
+    if torch.is_grad_enabled() and sequence.requires_grad:
+        return False
+    persistent = rnn.hidden_size <= 256 and not os.environ.get("MSF_LSTM_STEPS")
     if _lstm_wants_grad(rnn):
-        return not sequence.requires_grad and rnn.hidden_size <= 256 and rnn.input_size <= 63
-    if lengths is not None and rnn.hidden_size > 256:
-        return False   # per-window lengths: persistent kernel only (lstm_seq.cu)
-    return not (torch.is_grad_enabled() and sequence.requires_grad)
+        return persistent and rnn.input_size <= 63
+    if lengths is not None or rnn.num_layers > 1:
+        return persistent
+    return True
 
 
 def _lstm_wants_grad(rnn: nn.Module) -> bool:
     return torch.is_grad_enabled() and any(p.requires_grad for p in rnn.parameters())
 
 
-def _lstm_tensor_core(rnn: nn.LSTM, sequence: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+def _lstm_layers(rnn: nn.LSTM):
+    return [tuple(getattr(rnn, f"{name}_l{l}", None) for name in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"))
+            for l in range(rnn.num_layers)]
+
+
+def _lstm_tensor_core(rnn: nn.LSTM, sequence: torch.Tensor, lengths: Optional[torch.Tensor] = None,
+                      seed: Optional[int] = None) -> torch.Tensor:
+    """``h_n[-1]`` of ``rnn`` on the hand-written kernels.  Training mode (gradients wanted): nn.LSTM's inter-layer
+    dropout is drawn from the library's Philox stream keyed by ``seed`` (default: one draw from torch's generator)."""
+    layers = _lstm_layers(rnn)
     with torch.cuda.device(sequence.device):
-        if _lstm_wants_grad(rnn):   # training: the tape of the forward pass feeds msf_lstm_backward
-            return ops.LstmLastHidden.apply(sequence.detach(), rnn.weight_ih_l0, rnn.weight_hh_l0,
-                                            getattr(rnn, "bias_ih_l0", None), getattr(rnn, "bias_hh_l0", None), lengths)
-        packed = ops.lstm_pack_weights(rnn.weight_ih_l0, rnn.weight_hh_l0, getattr(rnn, "bias_ih_l0", None),
-                                       getattr(rnn, "bias_hh_l0", None))
+        if _lstm_wants_grad(rnn):   # training: the tapes of the forward pass feed msf_lstm_backward
+            p = float(rnn.dropout) if (rnn.training and rnn.num_layers > 1) else 0.0
+            if seed is None:
+                seed = int(torch.randint(0, 2**62, (1,)).item()) if p > 0.0 else 0
+            flat = [t for layer in layers for t in layer]
+            return ops.LstmLastHidden.apply(sequence.detach(), lengths, p, int(seed), *flat)
+        if rnn.num_layers > 1:
+            return ops.lstm_forward_stack(sequence, layers, rnn.hidden_size, lengths)
+        packed = ops.lstm_pack_weights(*layers[0])
         return ops.lstm_forward([ops.lstm_pack_input(sequence.to(torch.float32))], [packed], rnn.hidden_size,
                                 None if lengths is None else [lengths])[0]
 
@@ -189,7 +205,8 @@ class SequenceEncoder(nn.Module):
             if self.rnn is None:
                 raise RuntimeError("RNN module not initialized.")
             if _lstm_tensor_core_ok(self, sequence, lengths):
-                last = _lstm_tensor_core(self.rnn, sequence, lengths).to(sequence.dtype)
+                last = _lstm_tensor_core(self.rnn, sequence, lengths,
+                                         getattr(self, "lstm_dropout_seed", None)).to(sequence.dtype)
                 return _dense(self.projection, self.dropout_layer(last))
             if lengths is not None:  # ragged windows: pack, like encoders.py:141-156
                 lens = lengths.to(device=sequence.device).to(torch.int64).cpu()

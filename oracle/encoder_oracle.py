@@ -21,8 +21,11 @@ StateDict = Mapping[str, torch.Tensor]
 
 
 def lstm_last_hidden(sd: StateDict, prefix: str, x: torch.Tensor, num_layers: int,
-                     lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """``h_n[-1]`` of a ``batch_first`` multi-layer LSTM (eval mode / no inter-layer dropout).
+                     lengths: Optional[torch.Tensor] = None,
+                     layer_masks: Optional[Mapping[int, torch.Tensor]] = None) -> torch.Tensor:
+    """``h_n[-1]`` of a ``batch_first`` multi-layer LSTM.  Eval mode by default; ``layer_masks[l]`` (B, T, H) are the
+    multipliers (0 or 1/(1-p)) of nn.LSTM's training-mode dropout on the INPUT of layer l >= 1 (the outputs of layer
+    l-1; encoders.py:54-65 passes ``dropout`` to nn.LSTM), injected so that both sides use the same draws.
 
     With ``lengths`` the state of row b stops updating after ``lengths[b]`` steps, which is what
     ``pack_padded_sequence`` does (encoders.py:141-156); encoders.py:160-164 takes ``hidden[0][-1]``.
@@ -50,6 +53,8 @@ def lstm_last_hidden(sd: StateDict, prefix: str, x: torch.Tensor, num_layers: in
             h, c = h_new, c_new
             outs.append(h)
         inp = torch.stack(outs, dim=1)
+        if layer_masks is not None and (layer + 1) in layer_masks:
+            inp = inp * layer_masks[layer + 1].to(x.dtype)
     return h
 
 
@@ -81,13 +86,14 @@ def gru_last_hidden(sd: StateDict, prefix: str, x: torch.Tensor, num_layers: int
 
 
 def sequence_encoder_forward(sd: StateDict, x: torch.Tensor, num_layers: int, encoder_type: str = "lstm",
-                             lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+                             lengths: Optional[torch.Tensor] = None,
+                             layer_masks: Optional[Mapping[int, torch.Tensor]] = None) -> torch.Tensor:
     """``SequenceEncoder.forward`` for the rnn variants in eval mode (encoders.py:115-166):
     last hidden state of the top layer -> (dropout = identity) -> ``projection``."""
     if x.dim() != 3:
         raise ValueError(f"Expected 3D input sequence, got shape {x.shape}")
     if encoder_type == "lstm":
-        final = lstm_last_hidden(sd, "rnn", x, num_layers, lengths)
+        final = lstm_last_hidden(sd, "rnn", x, num_layers, lengths, layer_masks)
     elif encoder_type == "gru":
         final = gru_last_hidden(sd, "rnn", x, num_layers)
     else:

@@ -195,6 +195,76 @@ def test_tensor_core_lstm_training_matches_oracle(batch, steps, feat, hidden, ra
     assert _relerr(enc.rnn.weight_hh_l0.grad, 2 * sd["rnn.weight_hh_l0"].grad) <= 5e-2
 
 
+@pytest.mark.parametrize("batch,steps,feat,hidden,layers,ragged", [(37, 9, 17, 64, 2, False), (300, 40, 17, 256, 2, True),
+                                                                    (130, 25, 1, 128, 3, False), (2500, 12, 17, 256, 2, False)])
+def test_tensor_core_lstm_stacked_inference(batch, steps, feat, hidden, layers, ragged):
+    """Stacked nn.LSTM (the reference's default num_layers = 2, src/encoders.py:54-65) in inference mode: every layer
+    one persistent launch, the input's share of an upper layer's pre-activations from one GEMM over all steps;
+    against the fp32 CPU oracle (pinned on the 2-layer golden fixture), max-abs <= 1e-2."""
+    from oracle import encoder_oracle
+    torch.manual_seed(9)
+    enc = dropin_encoders.SequenceEncoder(feat, hidden_dim=hidden, output_dim=128, num_layers=layers, encoder_type="lstm",
+                                          dropout=0.1).eval()
+    gen = torch.Generator().manual_seed(10)
+    x = torch.randn(batch, steps, feat, generator=gen)
+    lengths = None
+    if ragged:
+        lengths = torch.randint(1, steps + 1, (batch,), generator=gen)
+        lengths[0], lengths[-1] = steps, 1
+    sd = {k: v.detach().clone() for k, v in enc.state_dict().items()}
+    ref_out = encoder_oracle.sequence_encoder_forward(sd, x, layers, "lstm", lengths)
+    enc = enc.cuda()
+    enc.precision = "bf16"
+    with torch.no_grad():
+        out = enc(x.cuda(), None if lengths is None else lengths.cuda())
+    assert torch.isfinite(out).all()
+    assert _maxabs(out, ref_out) <= 1e-2
+
+
+@pytest.mark.parametrize("batch,steps,feat,hidden,layers,p,ragged", [(37, 9, 17, 64, 2, 0.0, False),
+                                                                      (300, 40, 17, 256, 2, 0.1, False),
+                                                                      (260, 33, 17, 256, 2, 0.1, True),
+                                                                      (130, 25, 3, 128, 3, 0.2, False)])
+def test_tensor_core_lstm_stacked_training(batch, steps, feat, hidden, layers, p, ragged):
+    """Stacked LSTM in training mode: per layer msf_lstm_forward (tape) / msf_lstm_backward, between the layers one
+    GEMM each way and nn.LSTM's inter-layer dropout with the library's Philox multipliers, which are injected into the
+    oracle (msf_dropout_mask site 4).  Gradients of every layer's parameters against autograd through the oracle:
+    max-abs <= 1e-2 of the oracle gradient's largest entry, Frobenius <= 5 %."""
+    from oracle import encoder_oracle
+    pkg_ops = dropin_encoders.ops
+    torch.manual_seed(11)
+    enc = dropin_encoders.SequenceEncoder(feat, hidden_dim=hidden, output_dim=128, num_layers=layers, encoder_type="lstm",
+                                          dropout=p).train()
+    enc.dropout_layer.p = 0.0   # the dropout on the last hidden state draws from torch's generator: not under test
+    gen = torch.Generator().manual_seed(12)
+    x = torch.randn(batch, steps, feat, generator=gen)
+    lengths = None
+    if ragged:
+        lengths = torch.randint(1, steps + 1, (batch,), generator=gen)
+        lengths[0], lengths[-1] = steps, 1
+    probe = torch.randn(batch, 128, generator=gen) / batch
+    seed = 4242
+    masks = None
+    if p > 0.0:
+        masks = {l: pkg_ops.dropout_mask(seed, 0, 4, l, steps * batch, hidden, p).view(steps, batch, hidden)
+                 .permute(1, 0, 2).cpu() for l in range(1, layers)}
+        assert 0.5 * p < float((masks[1] == 0).float().mean()) < 1.5 * p
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in enc.state_dict().items()}
+    ref_out = encoder_oracle.sequence_encoder_forward(sd, x, layers, "lstm", lengths, masks)
+    (ref_out * probe).sum().backward()
+    enc = enc.cuda()
+    enc.precision = "bf16"
+    enc.lstm_dropout_seed = seed
+    out = enc(x.cuda(), None if lengths is None else lengths.cuda())
+    (out * probe.cuda()).sum().backward()
+    assert _maxabs(out, ref_out) <= 1e-2
+    for name, prm in enc.named_parameters():
+        ref = sd[name].grad
+        assert prm.grad is not None and torch.isfinite(prm.grad).all(), name
+        assert _maxabs(prm.grad, ref) <= 1e-2 * max(float(ref.abs().max()), 1e-6), name
+        assert _relerr(prm.grad, ref) <= 5e-2, name
+
+
 @pytest.mark.parametrize("pool", ["attention", "average", "max"])
 def test_frame_encoder_matches_reference_golden(pool):
     """FrameEncoder (src/encoders.py:211-336) against the unmodified reference: all three temporal poolings, with and
