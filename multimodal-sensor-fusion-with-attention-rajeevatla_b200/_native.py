@@ -95,7 +95,7 @@ class LstmSeq(ctypes.Structure):  # msf_lstm_seq
         # training mode
         ("h_all", c_void_p), ("z_in", c_void_p), ("gates", c_void_p), ("c_all", c_void_p), ("w_hh_t", c_void_p), ("d_h_out", c_void_p), ("d_h_all", c_void_p),
         ("dc", c_void_p), ("partial", c_void_p), ("d_w_ih", c_void_p), ("d_w_hh", c_void_p), ("d_bias", c_void_p),
-        ("features", c_int32), ("in_cols", c_int32),
+        ("features", c_int32), ("in_cols", c_int32), ("cell_type", c_int32),
     ]
 
 

@@ -36,8 +36,8 @@ extern "C" int msf_lstm_forward(const msf_lstm_seq* seqs, int32_t n, int64_t bat
     }
     if (lstm_seq_eligible(hidden, n, batch, sms)) return lstm_seq_launch(seqs, n, batch, steps, hidden, st);
     for (int i = 0; i < n; ++i)
-      if (seqs[i].lengths != nullptr || seqs[i].h_all != nullptr || seqs[i].z_in != nullptr) {
-        set_error("msf_lstm_forward: per-window lengths, stacked layers and the training mode need the persistent kernel (hidden <= 256, MSF_LSTM_STEPS unset)");
+      if (seqs[i].lengths != nullptr || seqs[i].h_all != nullptr || seqs[i].z_in != nullptr || seqs[i].cell_type != 0) {
+        set_error("msf_lstm_forward: per-window lengths, stacked layers, the GRU cell and the training mode need the persistent kernel (hidden <= 256, MSF_LSTM_STEPS unset)");
         return MSF_E_UNSUPPORTED;
       }
   }

@@ -101,7 +101,12 @@ __device__ __forceinline__ long long ls_cell_index(int tile, int r, int u, int H
 // [2] -> accumulators complete (epilogue warp 4 sees the last tile), [3] -> epilogue done, [4] -> cluster barrier passed
 __device__ long long g_ls_stamps[8];
 
-template <bool SAVE>
+// GRU (nn.GRU, gate order r, z, n; src/encoders.py:66-72): the same kernel with the four accumulator columns of a unit
+// holding (r, z, n_x, n_h) — the weight rows are packed so that column n_x only receives the input's share of the
+// candidate gate and n_h only the recurrent share (ops.gru_pack_weights) — and the cell
+//     r = s(a_r + b_r), z = s(a_z + b_z), n = tanh(a_nx + b_in + r (a_nh + b_hn)), h_t = n + z (h_{t-1} - n)
+// with h kept in fp32 in the `cell` buffer.  Inference only (no tape).
+template <bool SAVE, bool GRU>
 __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_constant__ LstmSeqLaunch L) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t off0 = smem_u32(smem_raw);
@@ -154,7 +159,9 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
     const int et = threadIdx.x - 128;
     // gate order i, f, g, o per unit; sigmoid(x) = 0.5 + 0.5 tanh(x / 2): the input and output gates' and the forget
     // gate's pre-activations are halved on the way in (acc * 0.5 + bias / 2), so their bias is stored halved
-    if (et < 256) bias_s[et] = (L.bias[seq] ? __ldg(L.bias[seq] + rank * 256 + et) : 0.0f) * ((et & 3) == 2 ? 1.0f : 0.5f);
+    // (GRU: r and z are the sigmoid gates, the two halves of the candidate gate are not halved)
+    const bool halved = GRU ? (et & 3) < 2 : (et & 3) != 2;
+    if (et < 256) bias_s[et] = (L.bias[seq] ? __ldg(L.bias[seq] + rank * 256 + et) : 0.0f) * (halved ? 0.5f : 1.0f);
   }
   tc_fence_before();
   __syncthreads();
@@ -244,7 +251,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
       const __nv_bfloat16* h_prev = SAVE ? reinterpret_cast<const __nv_bfloat16*>(L.hbuf[seq][0]) + (long long)t * BH
                                          : reinterpret_cast<const __nv_bfloat16*>(L.hbuf[seq][par]);
       // training mode: c_{t-1} is read from step t-1's slice (zeros at t = 0) and c_t goes to step t's
-      const bool tape = SAVE && L.gates[seq] != nullptr;
+      const bool tape = SAVE && !GRU && L.gates[seq] != nullptr;
       float* cellp = tape ? L.c_all[seq] + (long long)t * BH : L.cell[seq];
       const float* cell_prev = tape ? cellp - BH : cellp;
       __nv_bfloat16* gates_t = tape ? L.gates[seq] + (long long)t * BH * 4 : nullptr;
@@ -300,6 +307,15 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cg * 64 + 16 * g + 4 * j);
+            if (GRU) {   // cp = h_{t-1} (fp32), cn = hn = h_t
+              const float2 t_rz = ls_tanh2(fmaf(__uint_as_float(a[4 * j + 0]), 0.5f, b4.x), fmaf(__uint_as_float(a[4 * j + 1]), 0.5f, b4.y));
+              const float gr = fmaf(0.5f, t_rz.x, 0.5f), gz = fmaf(0.5f, t_rz.y, 0.5f);
+              const float nn = ls_tanh(fmaf(gr, __uint_as_float(a[4 * j + 3]) + b4.w, __uint_as_float(a[4 * j + 2]) + b4.z));
+              cn[j] = fmaf(gz, cp[j] - nn, nn);
+              hn[j] = cn[j];
+              go[j] = 0.0f;
+              continue;
+            }
             const float2 t_if = ls_tanh2(fmaf(__uint_as_float(a[4 * j + 0]), 0.5f, b4.x), fmaf(__uint_as_float(a[4 * j + 1]), 0.5f, b4.y));
             const float2 t_go = ls_tanh2(__uint_as_float(a[4 * j + 2]) + b4.z, fmaf(__uint_as_float(a[4 * j + 3]), 0.5f, b4.w));
             const float gi = fmaf(0.5f, t_if.x, 0.5f), gf = fmaf(0.5f, t_if.y, 0.5f);
@@ -312,7 +328,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
             }
           }
 #pragma unroll
-          for (int j = 0; j < 4; j += 2) {
+          for (int j = 0; j < 4 && !GRU; j += 2) {
             const float2 tc = ls_tanh2(cn[j], cn[j + 1]);
             hn[j] = go[j] * tc.x;
             hn[j + 1] = go[j + 1] * tc.y;
@@ -467,7 +483,14 @@ int lstm_seq_launch(const msf_lstm_seq* seqs, int n, long long batch, int steps,
   const size_t smem = fixed + weights + (size_t)stages * LS_A_BYTES;
   const int grid = n * cps * L.cs;
   if (prof_enabled()) prof_begin("LSTM sequence", 2.0 * (double)B * (hidden + 64 * L.nkbx) * 4.0 * hidden * steps * n, st);
-  auto kernel = save ? lstm_seq_kernel<true> : lstm_seq_kernel<false>;
+  const bool gru = seqs[0].cell_type == 1;
+  for (int i = 0; i < n; ++i) {
+    MSF_REQUIRE(seqs[i].cell_type == seqs[0].cell_type && (seqs[i].cell_type == 0 || seqs[i].cell_type == 1),
+                "msf_lstm_forward: cell_type 0 (LSTM) or 1 (GRU), the same for all sequences of a call");
+    MSF_REQUIRE(!(gru && seqs[i].gates != nullptr), "msf_lstm_forward: the training mode covers the LSTM cell only");
+  }
+  auto kernel = gru ? (save ? lstm_seq_kernel<true, true> : lstm_seq_kernel<false, true>)
+                    : (save ? lstm_seq_kernel<true, false> : lstm_seq_kernel<false, false>);
   MSF_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   MSF_CHECK_CUDA(ls_launch(kernel, dim3(grid), dim3(LS_THREADS), smem, st, L.cs, L));
   MSF_LAUNCH_CHECK();

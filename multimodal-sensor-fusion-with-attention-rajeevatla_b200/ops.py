@@ -745,8 +745,24 @@ def lstm_pack_input(x: torch.Tensor, ones_column: bool = False) -> torch.Tensor:
     return out
 
 
+def gru_as_four_gates(weight_ih, weight_hh, bias_ih, bias_hh):
+    """nn.GRU layer parameters (gate order r, z, n; (3H, .)) -> the four-gate form the recurrence kernel takes with
+    ``cell_type = 1`` (msf_lstm_seq): gates (r, z, n_x, n_h) with W_ih's n_h rows and W_hh's n_x rows zero, so that the
+    input's and the recurrent share of the candidate gate arrive in separate accumulator columns.  The result goes
+    through the LSTM packers (lstm_pack_weights / lstm_pack_upper)."""
+    H = weight_hh.shape[1]
+    w_ih, w_hh = weight_ih.detach().to(torch.float32), weight_hh.detach().to(torch.float32)
+    zi, zh = torch.zeros_like(w_ih[:H]), torch.zeros_like(w_hh[:H])
+    w_ih4 = torch.cat([w_ih[:2 * H], w_ih[2 * H:], zi], 0)
+    w_hh4 = torch.cat([w_hh[:2 * H], zh, w_hh[2 * H:]], 0)
+    zb = torch.zeros(H, dtype=torch.float32, device=w_hh.device)
+    b_ih = torch.zeros(3 * H, dtype=torch.float32, device=w_hh.device) if bias_ih is None else bias_ih.detach().float()
+    b_hh = torch.zeros(3 * H, dtype=torch.float32, device=w_hh.device) if bias_hh is None else bias_hh.detach().float()
+    return w_ih4, w_hh4, torch.cat([b_ih[:2 * H], b_ih[2 * H:], zb], 0), torch.cat([b_hh[:2 * H], zb, b_hh[2 * H:]], 0)
+
+
 def lstm_forward(xs: Sequence[torch.Tensor], packed: Sequence[tuple], hidden: int,
-                 lengths: Optional[Sequence[Optional[torch.Tensor]]] = None) -> List[torch.Tensor]:
+                 lengths: Optional[Sequence[Optional[torch.Tensor]]] = None, cell: str = "lstm") -> List[torch.Tensor]:
     """``h_T`` (fp32, (B, hidden)) of up to 4 single-layer LSTM encoders over packed inputs ``xs``
     (``lstm_pack_input``) with packed weights (``lstm_pack_weights``): one tensor-core launch per time step
     for all of them (msf_lstm_forward); hidden <= 256: one persistent launch over all steps.  ``lengths``: per
@@ -768,6 +784,7 @@ def lstm_forward(xs: Sequence[torch.Tensor], packed: Sequence[tuple], hidden: in
         outs.append(h_out)
         seqs[i].x_bf16, seqs[i].w_hh, seqs[i].w_ih, seqs[i].bias = _p(x), _p(w_hh), _p(w_ih), _p(bias)
         seqs[i].h_a, seqs[i].h_b, seqs[i].cell, seqs[i].h_out = _p(h_a), _p(h_b), _p(cell), _p(h_out)
+        seqs[i].cell_type = 1 if cell == "gru" else 0
         if lengths is not None and lengths[i] is not None:
             ln = lengths[i].to(device=dev, dtype=torch.int32).contiguous()
             if ln.numel() != B or int(ln.min()) < 1 or int(ln.max()) > T:
@@ -830,11 +847,12 @@ def _lstm_lengths(lengths, B, T, dev):
 
 
 def lstm_forward_stack(x: torch.Tensor, layers: Sequence[tuple], hidden: int,
-                       lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+                       lengths: Optional[torch.Tensor] = None, cell: str = "lstm") -> torch.Tensor:
     """``h_n[-1]`` of a stacked nn.LSTM in inference mode (src/encoders.py:54-65,135-166 with num_layers >= 1):
     ``x`` (B, T, F) fp32, ``layers`` = per layer ``(weight_ih, weight_hh, bias_ih, bias_hh)``.  Every layer is one
     persistent launch (msf_lstm_forward); a layer above the first gets the input's share of its gate
-    pre-activations from ONE tensor-core GEMM over all steps of the layer below (msf_gemm_bf16 -> z_in)."""
+    pre-activations from ONE tensor-core GEMM over all steps of the layer below (msf_gemm_bf16 -> z_in).
+    ``cell="gru"``: nn.GRU layers (src/encoders.py:66-72), passed through ``gru_as_four_gates``."""
     require_cuda("lstm_forward_stack")
     B, T, F = x.shape
     dev = x.device
@@ -845,6 +863,9 @@ def lstm_forward_stack(x: torch.Tensor, layers: Sequence[tuple], hidden: int,
         seqs = (N.LstmSeq * 1)()
         q = seqs[0]
         keep = []
+        if cell == "gru":
+            w = gru_as_four_gates(*w)
+            q.cell_type = 1
         if l == 0:
             w_hh, w_ih, bias = lstm_pack_weights(*w)
             xp = lstm_pack_input(x.to(torch.float32))
@@ -856,8 +877,8 @@ def lstm_forward_stack(x: torch.Tensor, layers: Sequence[tuple], hidden: int,
             q.z_in = _p(z)
             keep += [z]
         h_out = torch.empty(B, hidden, dtype=torch.float32, device=dev)
-        cell = torch.zeros(B, hidden, dtype=torch.float32, device=dev)
-        q.w_hh, q.bias, q.cell, q.h_out = _p(w_hh), _p(bias), _p(cell), _p(h_out)
+        state = torch.zeros(B, hidden, dtype=torch.float32, device=dev)   # c (LSTM) / h (GRU) in fp32
+        q.w_hh, q.bias, q.cell, q.h_out = _p(w_hh), _p(bias), _p(state), _p(h_out)
         if ln is not None:
             q.lengths = _p(ln)
         if last:

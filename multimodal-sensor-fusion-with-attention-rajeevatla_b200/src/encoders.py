@@ -56,20 +56,21 @@ def _lstm_tensor_core_ok(enc, sequence: torch.Tensor, lengths) -> bool:
     when the caller opted into bf16 (``encoder.precision = "bf16"`` or MSF_PRECISION=bf16): uni-directional LSTM of
     any depth, CUDA input, hidden % 64 == 0, input_dim <= 64; per-window ``lengths`` (the reference packs ragged
     windows, src/encoders.py:140-152), stacked layers and the training mode (gradients wanted for the LSTM's
-    parameters; input_dim <= 63) on the persistent kernels (hidden <= 256).  A gradient with respect to the input
-    sequence is not provided (the encoders' inputs are data) and keeps the library recurrence."""
+    parameters; input_dim <= 63) on the persistent kernels (hidden <= 256).  GRU encoders (src/encoders.py:66-72): the
+    same kernels in inference (hidden <= 256).  A gradient with respect to the input sequence is not provided (the
+    encoders' inputs are data) and keeps the library recurrence, as does GRU training."""
     prec = getattr(enc, "precision", None) or os.environ.get("MSF_PRECISION", "fp32")
     rnn = enc.rnn
-    if not (prec == "bf16" and enc.encoder_type == "lstm" and sequence.is_cuda
-            and isinstance(rnn, nn.LSTM) and not rnn.bidirectional and rnn.proj_size == 0
+    if not (prec == "bf16" and enc.encoder_type in ("lstm", "gru") and sequence.is_cuda
+            and isinstance(rnn, (nn.LSTM, nn.GRU)) and not rnn.bidirectional and getattr(rnn, "proj_size", 0) == 0
             and rnn.hidden_size % 64 == 0 and rnn.input_size <= 64):
         return False
     if torch.is_grad_enabled() and sequence.requires_grad:
         return False
     persistent = rnn.hidden_size <= 256 and not os.environ.get("MSF_LSTM_STEPS")
     if _lstm_wants_grad(rnn):
-        return persistent and rnn.input_size <= 63
-    if lengths is not None or rnn.num_layers > 1:
+        return persistent and rnn.input_size <= 63 and isinstance(rnn, nn.LSTM)
+    if lengths is not None or rnn.num_layers > 1 or isinstance(rnn, nn.GRU):
         return persistent
     return True
 
@@ -78,12 +79,12 @@ def _lstm_wants_grad(rnn: nn.Module) -> bool:
     return torch.is_grad_enabled() and any(p.requires_grad for p in rnn.parameters())
 
 
-def _lstm_layers(rnn: nn.LSTM):
+def _lstm_layers(rnn: nn.Module):
     return [tuple(getattr(rnn, f"{name}_l{l}", None) for name in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"))
             for l in range(rnn.num_layers)]
 
 
-def _lstm_tensor_core(rnn: nn.LSTM, sequence: torch.Tensor, lengths: Optional[torch.Tensor] = None,
+def _lstm_tensor_core(rnn: nn.Module, sequence: torch.Tensor, lengths: Optional[torch.Tensor] = None,
                       seed: Optional[int] = None) -> torch.Tensor:
     """``h_n[-1]`` of ``rnn`` on the hand-written kernels.  Training mode (gradients wanted): nn.LSTM's inter-layer
     dropout is drawn from the library's Philox stream keyed by ``seed`` (default: one draw from torch's generator)."""
@@ -95,8 +96,9 @@ def _lstm_tensor_core(rnn: nn.LSTM, sequence: torch.Tensor, lengths: Optional[to
                 seed = int(torch.randint(0, 2**62, (1,)).item()) if p > 0.0 else 0
             flat = [t for layer in layers for t in layer]
             return ops.LstmLastHidden.apply(sequence.detach(), lengths, p, int(seed), *flat)
-        if rnn.num_layers > 1:
-            return ops.lstm_forward_stack(sequence, layers, rnn.hidden_size, lengths)
+        if rnn.num_layers > 1 or isinstance(rnn, nn.GRU):
+            return ops.lstm_forward_stack(sequence, layers, rnn.hidden_size, lengths,
+                                          "gru" if isinstance(rnn, nn.GRU) else "lstm")
         packed = ops.lstm_pack_weights(*layers[0])
         return ops.lstm_forward([ops.lstm_pack_input(sequence.to(torch.float32))], [packed], rnn.hidden_size,
                                 None if lengths is None else [lengths])[0]

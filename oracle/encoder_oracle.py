@@ -58,8 +58,10 @@ def lstm_last_hidden(sd: StateDict, prefix: str, x: torch.Tensor, num_layers: in
     return h
 
 
-def gru_last_hidden(sd: StateDict, prefix: str, x: torch.Tensor, num_layers: int) -> torch.Tensor:
-    """``h_n[-1]`` of a ``batch_first`` multi-layer GRU (gate order r, z, n)."""
+def gru_last_hidden(sd: StateDict, prefix: str, x: torch.Tensor, num_layers: int,
+                    lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``h_n[-1]`` of a ``batch_first`` multi-layer GRU (gate order r, z, n); with ``lengths`` the state of row b
+    stops after ``lengths[b]`` steps (pack_padded_sequence, encoders.py:141-156)."""
     B, T, _ = x.shape
     inp = x
     h = None
@@ -79,7 +81,11 @@ def gru_last_hidden(sd: StateDict, prefix: str, x: torch.Tensor, num_layers: int
             r = torch.sigmoid(i_r + h_r)
             z = torch.sigmoid(i_z + h_z)
             n = torch.tanh(i_n + r * h_n)
-            h = (1 - z) * n + z * h
+            h_new = (1 - z) * n + z * h
+            if lengths is not None:
+                live = (t < lengths).to(x.dtype).unsqueeze(1)
+                h_new = live * h_new + (1 - live) * h
+            h = h_new
             outs.append(h)
         inp = torch.stack(outs, dim=1)
     return h
@@ -95,7 +101,7 @@ def sequence_encoder_forward(sd: StateDict, x: torch.Tensor, num_layers: int, en
     if encoder_type == "lstm":
         final = lstm_last_hidden(sd, "rnn", x, num_layers, lengths, layer_masks)
     elif encoder_type == "gru":
-        final = gru_last_hidden(sd, "rnn", x, num_layers)
+        final = gru_last_hidden(sd, "rnn", x, num_layers, lengths)
     else:
         raise ValueError(f"Unsupported encoder type: {encoder_type}")
     return final @ sd["projection.weight"].to(x.dtype).t() + sd["projection.bias"].to(x.dtype)
