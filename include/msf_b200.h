@@ -471,6 +471,24 @@ int msf_lstm_backward(const msf_lstm_seq* seqs, int32_t n, int64_t batch, int32_
 int msf_lstm_dropout(const void* in_bf16, void* out_bf16, int64_t rows, int32_t cols, float p, uint64_t seed,
                      uint64_t offset, int32_t layer, void* stream);
 
+/* fp32 parity path of the same recurrence (lstm_f32.cu: FFMA GEMMs + pointwise cell kernels, one launch pair per time
+ * step), ONE LAYER per call, forward and backward incl. the gradient with respect to the input: what SequenceEncoder
+ * runs by default (precision "fp32", max-abs <= 1e-5 against the reference's nn.LSTM).  Time-major contiguous layouts:
+ *   x [T][B][in_dim];  h_seq, c_seq [T+1][B][H]: slice t = state BEFORE step t, slice 0 ZERO on entry;  gates [T][B][4H],
+ *   nn.LSTM's gate-major columns (i | f | g | o): activations after forward, d pre-activations after backward (in place)
+ *   w_ih [4H][in_dim], w_hh [4H][H], b_ih / b_hh [4H] or NULL: nn.LSTM's own parameter tensors
+ *   lengths [B] int32 or NULL: a window's state stands still from step lengths[b] on (pack_padded_sequence)
+ *   forward scratch: B*4H floats;  backward scratch: 3*B*H floats
+ *   d_h_last [B][H] or NULL: gradient of the state after a window's last valid step;  d_h_seq [T][B][H] or NULL: gradient
+ *   of every step's hidden state (from the layer above);  d_x [T][B][in_dim] or NULL;  d_bias [4H] or NULL (= d b_ih = d b_hh) */
+int msf_lstm_f32_forward(const float* x, int32_t in_dim, const float* w_ih, const float* w_hh, const float* b_ih,
+                         const float* b_hh, const int32_t* lengths, int64_t batch, int32_t steps, int32_t hidden,
+                         float* h_seq, float* c_seq, float* gates, float* scratch, void* stream);
+int msf_lstm_f32_backward(const float* x, int32_t in_dim, const float* w_ih, const float* w_hh, const int32_t* lengths,
+                          int64_t batch, int32_t steps, int32_t hidden, const float* h_seq, const float* c_seq,
+                          float* gates, const float* d_h_last, const float* d_h_seq, float* scratch, float* d_x,
+                          float* d_w_ih, float* d_w_hh, float* d_bias, void* stream);
+
 /* ---- BatchNorm1d -> ReLU -> Dropout behind a Linear layer (src/encoders.py:339-397, BatchNorm at :374-375) ----- */
 /* out = dropout(relu((y - mean) * invstd * gamma + beta)) over y (rows x cols, row-major fp32: the Linear output).
  * training != 0: batch statistics (biased variance; fp64 column sums), running_mean / running_var moved on like

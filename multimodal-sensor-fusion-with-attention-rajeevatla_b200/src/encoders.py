@@ -104,6 +104,25 @@ def _lstm_tensor_core(rnn: nn.Module, sequence: torch.Tensor, lengths: Optional[
                                 None if lengths is None else [lengths])[0]
 
 
+def _lstm_fp32_ok(enc, sequence: torch.Tensor) -> bool:
+    """The default (fp32) precision of an LSTM encoder on a CUDA input runs the recurrence on the library's own fp32
+    kernels (msf_lstm_f32_forward / _backward: FFMA GEMMs + cell kernels, <= 1e-5 of the reference, gradients for the
+    parameters and the input), any depth, with or without ``lengths``.  MSF_LSTM_LIBRARY=1 keeps torch.nn.LSTM."""
+    rnn = enc.rnn
+    return (enc.encoder_type == "lstm" and sequence.is_cuda and isinstance(rnn, nn.LSTM) and not rnn.bidirectional
+            and rnn.proj_size == 0 and not os.environ.get("MSF_LSTM_LIBRARY"))
+
+
+def _lstm_fp32(rnn: nn.LSTM, sequence: torch.Tensor, lengths: Optional[torch.Tensor] = None,
+               seed: Optional[int] = None) -> torch.Tensor:
+    p = float(rnn.dropout) if (rnn.training and rnn.num_layers > 1) else 0.0
+    if seed is None:
+        seed = int(torch.randint(0, 2**62, (1,)).item()) if p > 0.0 else 0
+    flat = [t for layer in _lstm_layers(rnn) for t in layer]
+    with torch.cuda.device(sequence.device):
+        return ops.LstmLastHiddenF32.apply(sequence, lengths, p, int(seed), *flat)
+
+
 def _rnn_fp32(rnn: nn.Module, inp):
     """Run the library recurrence in true fp32: cuDNN's RNN kernels default to TF32, which is
     ~1e-4 away from the reference's CPU arithmetic."""
@@ -209,6 +228,9 @@ class SequenceEncoder(nn.Module):
             if _lstm_tensor_core_ok(self, sequence, lengths):
                 last = _lstm_tensor_core(self.rnn, sequence, lengths,
                                          getattr(self, "lstm_dropout_seed", None)).to(sequence.dtype)
+                return _dense(self.projection, self.dropout_layer(last))
+            if _lstm_fp32_ok(self, sequence):
+                last = _lstm_fp32(self.rnn, sequence, lengths, getattr(self, "lstm_dropout_seed", None)).to(sequence.dtype)
                 return _dense(self.projection, self.dropout_layer(last))
             if lengths is not None:  # ragged windows: pack, like encoders.py:141-156
                 lens = lengths.to(device=sequence.device).to(torch.int64).cpu()
