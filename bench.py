@@ -893,7 +893,6 @@ def run_raw_train(args):
     ms = timed(ours, steps)
     clocks = sampler.stop()
     # where the pass spends its time: forward launch, backward recurrence, weight-gradient GEMMs
-    tapes = ops.lstm_train_forward(xs, weights, HID)
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     ev[0].record()

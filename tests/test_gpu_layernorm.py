@@ -145,3 +145,48 @@ def test_encode_fuse_pipeline_matches_reference_wiring():
     assert out.shape == (50, 7)
     with pytest.raises(ValueError, match="only available for HybridFusion"):
         late(feats, mask, return_attention=True)
+
+
+def test_encode_fuse_trains_from_raw_windows_through_the_recurrence_kernels():
+    """Boundary E in training mode: raw windows -> 2-layer LSTM SequenceEncoders (msf_lstm_forward in training mode,
+    msf_lstm_backward) -> LayerNorm -> HybridFusion (tensor-core path) -> cross entropy, one backward pass through the
+    drop-in modules.  Logits and the gradients that reach the LSTM parameters of every encoder are compared with the
+    same wiring on the CPU (oracle encoders -> layer_norm -> fusion oracle -> autograd), bf16 tolerance."""
+    pkg = load_pkg()
+    pipeline = importlib.import_module(pkg.__name__ + ".pipeline")
+    import encoders as dropin_encoders
+    import fusion as dropin_fusion
+    torch.manual_seed(21)
+    feats_in = {"imu_hand": 17, "imu_chest": 17, "heart_rate": 1}
+    B, T = 96, 20
+    encs = torch.nn.ModuleDict({m: dropin_encoders.SequenceEncoder(f, hidden_dim=64, output_dim=64, num_layers=2,
+                                                                   encoder_type="lstm", dropout=0.0)
+                                for m, f in feats_in.items()})
+    norms = torch.nn.ModuleDict({m: torch.nn.LayerNorm(64) for m in feats_in})
+    fus = dropin_fusion.HybridFusion({m: 64 for m in feats_in}, hidden_dim=64, num_classes=7, num_heads=4, dropout=0.0)
+    gen = torch.Generator().manual_seed(22)
+    xs = {m: torch.randn(B, T, f, generator=gen) for m, f in feats_in.items()}
+    mask = (torch.rand(B, 3, generator=gen) < 0.85).float()
+    labels = torch.randint(0, 7, (B,), generator=gen)
+    # reference wiring on the CPU with autograd through the oracles
+    enc_sd = {m: {k: v.detach().clone().requires_grad_(True) for k, v in encs[m].state_dict().items()} for m in feats_in}
+    cpu = {m: encoder_oracle.sequence_encoder_forward(enc_sd[m], xs[m], 2, "lstm") for m in feats_in}
+    cpu = {m: torch.nn.functional.layer_norm(x, (64,), norms[m].weight.detach(), norms[m].bias.detach(), 1e-5)
+           for m, x in cpu.items()}
+    sd = {k: v.detach().clone() for k, v in fus.state_dict().items()}
+    ref_logits, _ = fusion_oracle.hybrid_fusion_forward(sd, list(feats_in), 4, cpu, mask)
+    torch.nn.functional.cross_entropy(ref_logits, labels).backward()
+    # the drop-in on the device
+    for e in encs.values():
+        e.precision = "bf16"
+    fus.precision = "bf16"
+    model = pipeline.EncodeFuse(encs, fus, norms).cuda().train()
+    logits = model({m: x.cuda() for m, x in xs.items()}, mask.cuda())
+    torch.nn.functional.cross_entropy(logits, labels.cuda()).backward()
+    assert _maxabs(logits, ref_logits) <= 2e-2
+    for m in feats_in:
+        for name, prm in encs[m].rnn.named_parameters():
+            ref = enc_sd[m]["rnn." + name].grad
+            assert prm.grad is not None and torch.isfinite(prm.grad).all(), (m, name)
+            err = float((prm.grad.cpu().double() - ref.double()).norm() / ref.double().norm().clamp_min(1e-30))
+            assert err <= 0.1, (m, name, err)
