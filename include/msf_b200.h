@@ -445,7 +445,7 @@ typedef struct msf_lstm_seq {
   float* d_w_ih;         /* [4H][F] fp32, nn.LSTM row order (gate-major): gradient of weight_ih_l0 */
   float* d_w_hh;         /* [4H][H] fp32: gradient of weight_hh_l0 */
   float* d_bias;         /* [4H]    fp32: gradient of bias_ih_l0 (= that of bias_hh_l0) */
-  int32_t features;      /* F = input_dim of this layer: 1..63 for the first layer, H for the layers above */
+  int32_t features;      /* F = input_dim of this layer: 1..64 for the first layer, H for the layers above */
   int32_t in_cols;       /* row length of x_bf16 in msf_lstm_backward: 0 for the first layer (64 padded columns); H for a layer above,
                             whose x_bf16 is the [T][B][H] input the forward GEMM read (no ones column: the bias gradient
                             is a column sum of d a) */
@@ -462,7 +462,7 @@ int msf_lstm_forward(const msf_lstm_seq* seqs, int32_t n, int64_t batch, int32_t
  * d W_hh = sum_t d a_t^T h_{t-1}, d W_ih = sum_t d a_t^T x_t are tensor-core GEMMs contracting over (t, window), split
  * over chunks of steps, and one reduction kernel sums the chunks into nn.LSTM's layout.  The bias gradient is the
  * column `features` of d W_ih: the caller stores 1.0 in column `features` of x_bf16 (features <= 63) whose weight
- * column is zero.  No gradient with respect to x (the encoders' inputs are data).  hidden <= 256. */
+ * column is zero (features == 64, and the layers above the first: a fixed-order column sum of d a instead).  No gradient with respect to x (the encoders' inputs are data).  hidden <= 256. */
 int msf_lstm_backward_scratch_bytes(int64_t batch, int32_t steps, int32_t hidden, size_t* bytes);
 int msf_lstm_backward(const msf_lstm_seq* seqs, int32_t n, int64_t batch, int32_t steps, int32_t hidden, void* stream);
 /* Inter-layer dropout of a stacked nn.LSTM in training mode: out = in * m over rows x cols bf16 (cols % 8 == 0), m the

@@ -445,8 +445,7 @@ extern "C" int msf_lstm_backward(const msf_lstm_seq* seqs, int32_t n, int64_t ba
     if (S.in_cols != 0) {
       MSF_REQUIRE(S.features == hidden, "msf_lstm_backward: a stacked layer has features == hidden");
     } else {
-      MSF_REQUIRE(S.features >= 1 && S.features <= 63,
-                  "msf_lstm_backward: features %d (1..63: column `features` of x carries the ones of the bias gradient)", S.features);
+      MSF_REQUIRE(S.features >= 1 && S.features <= 64, "msf_lstm_backward: features %d (1..64)", S.features);
     }
     if ((rc = tc_encode_map(&L.m[i].da, S.gates, B, N4, N4, steps, B * N4, 64, 128))) return rc;
     if ((rc = tc_encode_map(&L.m[i].wt, S.w_hh_t, H, N4, N4, 1, 0, 64, 64))) return rc;
@@ -530,7 +529,7 @@ extern "C" int msf_lstm_backward(const msf_lstm_seq* seqs, int32_t n, int64_t ba
     }
     if ((rc = tb.flush())) return rc;
     float* bias_partial = nullptr;
-    if (stacked) {
+    if (stacked || S.features == 64) {   // no spare column for the ones of the bias gradient: column sums of d a
       bias_partial = S.partial + (size_t)chunks * per_chunk;
       lstm_colsum_kernel<<<LB_COLSUM_BLOCKS, 256, 0, st>>>(da, (long long)steps * B, (int)N4, bias_partial);
       MSF_LAUNCH_CHECK();

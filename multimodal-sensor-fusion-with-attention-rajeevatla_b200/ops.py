@@ -738,9 +738,7 @@ def lstm_pack_input(x: torch.Tensor, ones_column: bool = False) -> torch.Tensor:
     B, T, F = x.shape
     out = torch.zeros(T, B, 64, dtype=torch.bfloat16, device=x.device)
     out[:, :, :F] = x.detach().transpose(0, 1)
-    if ones_column:
-        if F > 63:
-            raise N.MsfError("the LSTM training path needs input_dim <= 63")
+    if ones_column and F < 64:   # F == 64: no spare column, msf_lstm_backward sums the columns of d a instead
         out[:, :, F] = 1.0
     return out
 

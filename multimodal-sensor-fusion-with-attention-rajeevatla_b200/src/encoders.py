@@ -56,7 +56,7 @@ def _lstm_tensor_core_ok(enc, sequence: torch.Tensor, lengths) -> bool:
     when the caller opted into bf16 (``encoder.precision = "bf16"`` or MSF_PRECISION=bf16): uni-directional LSTM of
     any depth, CUDA input, hidden % 64 == 0, input_dim <= 64; per-window ``lengths`` (the reference packs ragged
     windows, src/encoders.py:140-152), stacked layers and the training mode (gradients wanted for the LSTM's
-    parameters; input_dim <= 63) on the persistent kernels (hidden <= 256).  GRU encoders (src/encoders.py:66-72): the
+    parameters) on the persistent kernels (hidden <= 256).  GRU encoders (src/encoders.py:66-72): the
     same kernels in inference (hidden <= 256).  A gradient with respect to the input sequence is not provided (the
     encoders' inputs are data) and keeps the library recurrence, as does GRU training."""
     prec = getattr(enc, "precision", None) or os.environ.get("MSF_PRECISION", "fp32")
@@ -69,7 +69,7 @@ def _lstm_tensor_core_ok(enc, sequence: torch.Tensor, lengths) -> bool:
         return False
     persistent = rnn.hidden_size <= 256 and not os.environ.get("MSF_LSTM_STEPS")
     if _lstm_wants_grad(rnn):
-        return persistent and rnn.input_size <= 63 and isinstance(rnn, nn.LSTM)
+        return persistent and isinstance(rnn, nn.LSTM)
     if lengths is not None or rnn.num_layers > 1 or isinstance(rnn, nn.GRU):
         return persistent
     return True

@@ -43,3 +43,25 @@ for row in buf.value.decode().splitlines():
     label, cnt, ms, fl = row.split("\t")
     print(f"B={B} T={T}: {label}: {cnt} launches, {float(ms):.3f} ms, {float(ms) * 1e3 / T:.2f} us per time step, "
           f"{float(fl) / (float(ms) * 1e-3) / 1e12:.0f} TFLOP/s (MSF_LSTM_DBG={os.environ.get('MSF_LSTM_DBG', '')})")
+
+# one stacked encoder (the reference's default num_layers = 2): inference and training pass through the layer-wise path
+LAYERS = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+if LAYERS > 1:
+    rnn = torch.nn.LSTM(17, H, num_layers=LAYERS, batch_first=True, dropout=0.1).to(dev)
+    layers = [tuple(getattr(rnn, f"{n}_l{l}") for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")) for l in range(LAYERS)]
+    x = xs[0]
+
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    ms_inf = timed(lambda: ops.lstm_forward_stack(x, layers, H))
+    ms_trn = timed(lambda: ops.lstm_backward_stack(ops.lstm_train_forward_stack(x, layers, H, None, 0.1, 7), d_h[0]))
+    print(f"B={B} T={T}: one {LAYERS}-layer encoder: inference {ms_inf:.2f} ms, training pass (forward + backward) {ms_trn:.2f} ms")

@@ -224,7 +224,8 @@ def test_tensor_core_lstm_stacked_inference(batch, steps, feat, hidden, layers, 
 @pytest.mark.parametrize("batch,steps,feat,hidden,layers,p,ragged", [(37, 9, 17, 64, 2, 0.0, False),
                                                                       (300, 40, 17, 256, 2, 0.1, False),
                                                                       (260, 33, 17, 256, 2, 0.1, True),
-                                                                      (130, 25, 3, 128, 3, 0.2, False)])
+                                                                      (130, 25, 3, 128, 3, 0.2, False),
+                                                                      (200, 30, 64, 256, 2, 0.1, False)])
 def test_tensor_core_lstm_stacked_training(batch, steps, feat, hidden, layers, p, ragged):
     """Stacked LSTM in training mode: per layer msf_lstm_forward (tape) / msf_lstm_backward, between the layers one
     GEMM each way and nn.LSTM's inter-layer dropout with the library's Philox multipliers, which are injected into the
