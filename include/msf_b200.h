@@ -126,6 +126,11 @@ int msf_layer_norm_backward(const float* x, const float* gamma, const float* dy,
                             int64_t rows, int32_t dim, float eps, void* stream);
 
 /* ---- library ------------------------------------------------------------ */
+/* Concurrency: every call enqueues on the caller's stream and returns.  The optimizer kernels
+ * (msf_fusion_optimizer_step*, msf_dp*_optimizer_step*) and msf_cross_entropy keep their grid-wide ticket / barrier words
+ * in process-global device variables: launches of these entry points must not run CONCURRENTLY on one device (two
+ * streams, two engines in one process) — serialise them on one stream or with events.  One process per GPU, as
+ * the drop-in and the engine use the library, satisfies this by construction. */
 int msf_abi_version(void);
 /* sizeof(msf_fusion_shape), sizeof(msf_fusion_call) as compiled, for binding self-checks */
 int msf_struct_sizes(int32_t* shape_bytes, int32_t* call_bytes);

@@ -351,9 +351,25 @@ static int dp_step(const msf_fusion_shape* shape, const msf_dp_comm* comm, float
   cudaStream_t st = (cudaStream_t)stream;
   // Every block waits inside the kernel for the peers' flags, and those depend on ALL blocks of every rank
   // having pushed: the grid must be co-resident (148 SMs x 8 blocks of 256 threads) or the ranks deadlock.
+  // The bound comes from the device this call runs on (occupancy x SM count), not from a fixed part.
+  static int resident[64] = {0};   // co-resident blocks of dp_reduce_kernel per device
+  int dev = 0;
+  MSF_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && resident[dev] == 0) {
+    int per_sm = 0, sms = 0;
+    MSF_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, msf::dp_reduce_kernel, 256, 0));
+    MSF_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    resident[dev] = per_sm * sms;
+  }
+  const int cap = (dev >= 0 && dev < 64) ? resident[dev] : 0;
+  if (cap < 1) {
+    msf::set_error("msf_dp_optimizer_step: the exchange kernel cannot be made co-resident on this device");
+    return MSF_E_UNSUPPORTED;
+  }
   long long blocks = msf::ceil_div(msf::ceil_div(a.n_live, 4), 256);
-  if (blocks < 148) blocks = 148;
-  if (blocks > 592) blocks = 592;
+  const long long lo = cap < 148 ? cap : 148, hi = cap < 592 ? cap : 592;
+  if (blocks < lo) blocks = lo;
+  if (blocks > hi) blocks = hi;
   msf::dp_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
   MSF_LAUNCH_CHECK();
   if (params_bf16 != nullptr) {   // clip + AdamW + bf16 re-pack + state advance in one launch
