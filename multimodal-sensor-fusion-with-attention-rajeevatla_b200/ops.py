@@ -844,54 +844,71 @@ def _lstm_lengths(lengths, B, T, dev):
     return ln
 
 
+def lstm_forward_stack_group(xs: Sequence[torch.Tensor], layers_list: Sequence[Sequence[tuple]], hidden: int,
+                             lengths_list: Optional[Sequence[Optional[torch.Tensor]]] = None,
+                             cell: str = "lstm") -> List[torch.Tensor]:
+    """``h_n[-1]`` of up to 4 stacked nn.LSTM / nn.GRU encoders of the same depth, hidden size, batch and length in
+    inference mode (src/encoders.py:54-72,135-166): ``xs[i]`` (B, T, F_i) fp32, ``layers_list[i]`` = per layer
+    ``(weight_ih, weight_hh, bias_ih, bias_hh)``.  Every LAYER is one persistent launch for all encoders
+    (msf_lstm_forward, n sequences); a layer above the first gets the input's share of its gate pre-activations from
+    ONE tensor-core GEMM per encoder over all steps of the layer below (msf_gemm_bf16 -> z_in).
+    ``cell="gru"``: nn.GRU layers (src/encoders.py:66-72), passed through ``gru_as_four_gates``."""
+    require_cuda("lstm_forward_stack_group")
+    n = len(xs)
+    B, T, _ = xs[0].shape
+    dev = xs[0].device
+    depth = len(layers_list[0])
+    if any(len(ls) != depth for ls in layers_list) or any(tuple(x.shape[:2]) != (B, T) for x in xs):
+        raise N.MsfError("lstm_forward_stack_group: the encoders of one call share depth, batch and length")
+    lns = [_lstm_lengths(None if lengths_list is None else lengths_list[i], B, T, dev) for i in range(n)]
+    prev: List[Optional[torch.Tensor]] = [None] * n
+    h_outs: List[torch.Tensor] = []
+    for l in range(depth):
+        last = l == depth - 1
+        seqs = (N.LstmSeq * n)()
+        keep, h_outs, h_alls = [], [], []
+        for i in range(n):
+            q, w = seqs[i], layers_list[i][l]
+            if cell == "gru":
+                w = gru_as_four_gates(*w)
+                q.cell_type = 1
+            if l == 0:
+                w_hh, w_ih, bias = lstm_pack_weights(*w)
+                xp = lstm_pack_input(xs[i].to(torch.float32))
+                q.x_bf16, q.w_ih = _p(xp), _p(w_ih)
+                keep += [xp, w_ih]
+            else:
+                w_hh, w_ih, bias = lstm_pack_upper(*w)
+                z = gemm_bf16(prev[i][1:].view(T * B, hidden), w_ih, out_dtype=torch.bfloat16)
+                q.z_in = _p(z)
+                keep += [z]
+            h_out = torch.empty(B, hidden, dtype=torch.float32, device=dev)
+            state = torch.zeros(B, hidden, dtype=torch.float32, device=dev)   # c (LSTM) / h (GRU) in fp32
+            q.w_hh, q.bias, q.cell, q.h_out = _p(w_hh), _p(bias), _p(state), _p(h_out)
+            keep += [w_hh, bias, state]
+            h_outs.append(h_out)
+            if lns[i] is not None:
+                q.lengths = _p(lns[i])
+            if last:
+                h_a = torch.zeros(hidden // 64, B, 64, dtype=torch.bfloat16, device=dev)
+                h_b = torch.zeros(hidden // 64, B, 64, dtype=torch.bfloat16, device=dev)
+                q.h_a, q.h_b = _p(h_a), _p(h_b)
+                keep += [h_a, h_b]
+            else:
+                h_all = torch.empty(T + 1, B, hidden, dtype=torch.bfloat16, device=dev)
+                h_all[0].zero_()
+                q.h_all = _p(h_all)
+                h_alls.append(h_all)
+        N.check(N.lib().msf_lstm_forward(seqs, n, B, T, hidden, _stream()))
+        prev = h_alls if not last else [None] * n
+        del keep
+    return h_outs
+
+
 def lstm_forward_stack(x: torch.Tensor, layers: Sequence[tuple], hidden: int,
                        lengths: Optional[torch.Tensor] = None, cell: str = "lstm") -> torch.Tensor:
-    """``h_n[-1]`` of a stacked nn.LSTM in inference mode (src/encoders.py:54-65,135-166 with num_layers >= 1):
-    ``x`` (B, T, F) fp32, ``layers`` = per layer ``(weight_ih, weight_hh, bias_ih, bias_hh)``.  Every layer is one
-    persistent launch (msf_lstm_forward); a layer above the first gets the input's share of its gate
-    pre-activations from ONE tensor-core GEMM over all steps of the layer below (msf_gemm_bf16 -> z_in).
-    ``cell="gru"``: nn.GRU layers (src/encoders.py:66-72), passed through ``gru_as_four_gates``."""
-    require_cuda("lstm_forward_stack")
-    B, T, F = x.shape
-    dev = x.device
-    ln = _lstm_lengths(lengths, B, T, dev)
-    prev, h_out = None, None
-    for l, w in enumerate(layers):
-        last = l == len(layers) - 1
-        seqs = (N.LstmSeq * 1)()
-        q = seqs[0]
-        keep = []
-        if cell == "gru":
-            w = gru_as_four_gates(*w)
-            q.cell_type = 1
-        if l == 0:
-            w_hh, w_ih, bias = lstm_pack_weights(*w)
-            xp = lstm_pack_input(x.to(torch.float32))
-            q.x_bf16, q.w_ih = _p(xp), _p(w_ih)
-            keep += [xp, w_ih]
-        else:
-            w_hh, w_ih, bias = lstm_pack_upper(*w)
-            z = gemm_bf16(prev[1:].view(T * B, hidden), w_ih, out_dtype=torch.bfloat16)
-            q.z_in = _p(z)
-            keep += [z]
-        h_out = torch.empty(B, hidden, dtype=torch.float32, device=dev)
-        state = torch.zeros(B, hidden, dtype=torch.float32, device=dev)   # c (LSTM) / h (GRU) in fp32
-        q.w_hh, q.bias, q.cell, q.h_out = _p(w_hh), _p(bias), _p(state), _p(h_out)
-        if ln is not None:
-            q.lengths = _p(ln)
-        if last:
-            h_a = torch.zeros(hidden // 64, B, 64, dtype=torch.bfloat16, device=dev)
-            h_b = torch.zeros(hidden // 64, B, 64, dtype=torch.bfloat16, device=dev)
-            q.h_a, q.h_b = _p(h_a), _p(h_b)
-            keep += [h_a, h_b]
-        else:
-            h_all = torch.empty(T + 1, B, hidden, dtype=torch.bfloat16, device=dev)
-            h_all[0].zero_()
-            q.h_all = _p(h_all)
-        N.check(N.lib().msf_lstm_forward(seqs, 1, B, T, hidden, _stream()))
-        prev = None if last else h_all
-        del keep
-    return h_out
+    """``lstm_forward_stack_group`` for one encoder."""
+    return lstm_forward_stack_group([x], [layers], hidden, None if lengths is None else [lengths], cell)[0]
 
 
 def lstm_train_forward(xs: Sequence[torch.Tensor], weights: Sequence[tuple], hidden: int,
@@ -926,49 +943,66 @@ def lstm_train_forward(xs: Sequence[torch.Tensor], weights: Sequence[tuple], hid
     return tapes
 
 
+def lstm_train_forward_stack_group(xs: Sequence[torch.Tensor], layers_list: Sequence[Sequence[tuple]], hidden: int,
+                                   lengths_list: Optional[Sequence[Optional[torch.Tensor]]] = None,
+                                   dropout_p: float = 0.0, seeds: Optional[Sequence[int]] = None) -> List[List[LstmTape]]:
+    """Training-mode forward of up to 4 stacked nn.LSTM encoders of the same depth / hidden size / batch / length:
+    per encoder one tape per layer, bottom first (``tapes[i][-1].h_out`` is ``h_n[-1]`` of encoder i); every layer is
+    ONE persistent launch for all encoders.  Between the layers nn.LSTM's dropout (p = ``dropout_p``) is applied with
+    the library's Philox multipliers (msf_lstm_dropout: site 4, sub = layer, keyed by ``seeds[i]``).  A layer above the
+    first reads the input's share of its pre-activations from one GEMM over all steps, written straight into its gate
+    buffer (z_in == gates: read, then overwritten in place by the activations)."""
+    require_cuda("lstm_train_forward_stack_group")
+    n = len(xs)
+    B, T, _ = xs[0].shape
+    dev = xs[0].device
+    depth = len(layers_list[0])
+    if any(len(ls) != depth for ls in layers_list) or any(tuple(x.shape[:2]) != (B, T) for x in xs):
+        raise N.MsfError("lstm_train_forward_stack_group: the encoders of one call share depth, batch and length")
+    seeds = list(seeds) if seeds is not None else [0] * n
+    lns = [_lstm_lengths(None if lengths_list is None else lengths_list[i], B, T, dev) for i in range(n)]
+    tapes = [[tp] for tp in lstm_train_forward(xs, [ls[0] for ls in layers_list], hidden, lns)]
+    for l in range(1, depth):
+        seqs = (N.LstmSeq * n)()
+        keep, new = [], []
+        for i in range(n):
+            w = layers_list[i][l]
+            below = tapes[i][-1].h_all[1:].view(T * B, hidden)
+            drop = None
+            if dropout_p > 0.0:
+                inp = torch.empty_like(below)
+                N.check(N.lib().msf_lstm_dropout(_p(below), _p(inp), T * B, hidden, float(dropout_p),
+                                                 seeds[i] & (2**64 - 1), 0, l, _stream()))
+                drop = (float(dropout_p), seeds[i], 0)
+            else:
+                inp = below
+            w_hh, w_ih, bias = lstm_pack_upper(*w)
+            gates = gemm_bf16(inp, w_ih, out_dtype=torch.bfloat16).view(T, B, 4 * hidden)
+            h_all = torch.empty(T + 1, B, hidden, dtype=torch.bfloat16, device=dev)
+            h_all[0].zero_()
+            c_all = torch.empty(T, B * hidden, dtype=torch.float32, device=dev)
+            h_out = torch.empty(B, hidden, dtype=torch.float32, device=dev)
+            q = seqs[i]
+            q.w_hh, q.bias, q.z_in, q.gates = _p(w_hh), _p(bias), _p(gates), _p(gates)
+            q.h_all, q.c_all, q.h_out = _p(h_all), _p(c_all), _p(h_out)
+            if lns[i] is not None:
+                q.lengths = _p(lns[i])
+            keep += [w_hh, bias]
+            new.append(LstmTape(inp, hidden, hidden, lstm_pack_weights_t(w[1]), lstm_pack_weights_t(w[0]), h_all, gates,
+                                c_all, h_out, lns[i], hidden, layer=l, drop=drop))
+        N.check(N.lib().msf_lstm_forward(seqs, n, B, T, hidden, _stream()))
+        for i in range(n):
+            tapes[i].append(new[i])
+        del keep
+    return tapes
+
+
 def lstm_train_forward_stack(x: torch.Tensor, layers: Sequence[tuple], hidden: int,
                              lengths: Optional[torch.Tensor] = None, dropout_p: float = 0.0, seed: int = 0,
                              offset: int = 0) -> List[LstmTape]:
-    """Training-mode forward of ONE stacked nn.LSTM (num_layers = len(layers)): one tape per layer, bottom first;
-    ``tapes[-1].h_out`` is ``h_n[-1]``.  Between the layers nn.LSTM's dropout (p = ``dropout_p``) is applied with the
-    library's Philox multipliers (msf_lstm_dropout: site 4, sub = layer, keyed by ``seed`` / ``offset``).  A layer
-    above the first reads the input's share of its pre-activations from one GEMM over all steps, written straight
-    into its gate buffer (z_in == gates: read, then overwritten in place by the activations)."""
-    require_cuda("lstm_train_forward_stack")
-    B, T, F = x.shape
-    dev = x.device
-    ln = _lstm_lengths(lengths, B, T, dev)
-    tapes: List[LstmTape] = []
-    for l, w in enumerate(layers):
-        if l == 0:
-            tp = lstm_train_forward([x], [w], hidden, None if ln is None else [ln])[0]
-            tapes.append(tp)
-            continue
-        below = tapes[-1].h_all[1:].view(T * B, hidden)
-        drop = None
-        if dropout_p > 0.0:
-            inp = torch.empty_like(below)
-            N.check(N.lib().msf_lstm_dropout(_p(below), _p(inp), T * B, hidden, float(dropout_p), seed & (2**64 - 1),
-                                             offset & (2**64 - 1), l, _stream()))
-            drop = (float(dropout_p), seed, offset)
-        else:
-            inp = below
-        w_hh, w_ih, bias = lstm_pack_upper(*w)
-        gates = gemm_bf16(inp, w_ih, out_dtype=torch.bfloat16).view(T, B, 4 * hidden)
-        h_all = torch.empty(T + 1, B, hidden, dtype=torch.bfloat16, device=dev)
-        h_all[0].zero_()
-        c_all = torch.empty(T, B * hidden, dtype=torch.float32, device=dev)
-        h_out = torch.empty(B, hidden, dtype=torch.float32, device=dev)
-        seqs = (N.LstmSeq * 1)()
-        q = seqs[0]
-        q.w_hh, q.bias, q.z_in, q.gates = _p(w_hh), _p(bias), _p(gates), _p(gates)
-        q.h_all, q.c_all, q.h_out = _p(h_all), _p(c_all), _p(h_out)
-        if ln is not None:
-            q.lengths = _p(ln)
-        N.check(N.lib().msf_lstm_forward(seqs, 1, B, T, hidden, _stream()))
-        tapes.append(LstmTape(inp, hidden, hidden, lstm_pack_weights_t(w[1]), lstm_pack_weights_t(w[0]), h_all, gates,
-                              c_all, h_out, ln, hidden, layer=l, drop=drop))
-    return tapes
+    """``lstm_train_forward_stack_group`` for one encoder (``offset`` is kept for callers of the first version: 0)."""
+    return lstm_train_forward_stack_group([x], [layers], hidden, None if lengths is None else [lengths], dropout_p,
+                                          [seed])[0]
 
 
 def lstm_backward(tapes: Sequence[LstmTape], d_h_out: Sequence[Optional[torch.Tensor]],
@@ -1019,24 +1053,63 @@ def lstm_backward(tapes: Sequence[LstmTape], d_h_out: Sequence[Optional[torch.Te
     return outs
 
 
-def lstm_backward_stack(tapes: Sequence[LstmTape], d_h_out: torch.Tensor):
-    """Backward pass through the tapes of ``lstm_train_forward_stack`` (top layer first): per layer
+def lstm_backward_stack_group(tapes_list: Sequence[Sequence[LstmTape]], d_h_outs: Sequence[torch.Tensor]):
+    """Backward pass through the tapes of ``lstm_train_forward_stack_group`` (top layer first, every layer ONE
+    persistent launch + the weight-gradient GEMMs for all encoders): per encoder and layer
     ``(d weight_ih, d weight_hh, d bias)``, bottom first.  Between two layers the gradient of the lower layer's hidden
     states is one GEMM over all steps (d a of the upper layer times its W_ih) through the same dropout mask."""
-    grads: List[Optional[tuple]] = [None] * len(tapes)
-    d_all = None
-    for l in reversed(range(len(tapes))):
-        tp = tapes[l]
-        T1, B, hidden = tp.h_all.shape
-        grads[l] = lstm_backward([tp], [d_h_out if l == len(tapes) - 1 else None], [d_all], release=False)[0]
-        if l > 0:
-            d_all = gemm_bf16(tp.gates.view((T1 - 1) * B, 4 * hidden), tp.w_ih_t, out_dtype=torch.bfloat16)
-            if tp.drop is not None:
-                p, seed, offset = tp.drop
-                N.check(N.lib().msf_lstm_dropout(_p(d_all), _p(d_all), (T1 - 1) * B, hidden, p, seed & (2**64 - 1),
-                                                 offset & (2**64 - 1), l, _stream()))
-        tp.gates = tp.c_all = tp.h_all = tp.inp = None
+    n, depth = len(tapes_list), len(tapes_list[0])
+    grads: List[List[Optional[tuple]]] = [[None] * depth for _ in range(n)]
+    d_all: List[Optional[torch.Tensor]] = [None] * n
+    for l in reversed(range(depth)):
+        tps = [tapes_list[i][l] for i in range(n)]
+        T1, B, hidden = tps[0].h_all.shape
+        out = lstm_backward(tps, [d_h_outs[i] if l == depth - 1 else None for i in range(n)], d_all, release=False)
+        for i in range(n):
+            grads[i][l] = out[i]
+            tp = tps[i]
+            if l > 0:
+                d_all[i] = gemm_bf16(tp.gates.view((T1 - 1) * B, 4 * hidden), tp.w_ih_t, out_dtype=torch.bfloat16)
+                if tp.drop is not None:
+                    p, seed, offset = tp.drop
+                    N.check(N.lib().msf_lstm_dropout(_p(d_all[i]), _p(d_all[i]), (T1 - 1) * B, hidden, p,
+                                                     seed & (2**64 - 1), offset & (2**64 - 1), l, _stream()))
+            tp.gates = tp.c_all = tp.h_all = tp.inp = None
     return grads
+
+
+def lstm_backward_stack(tapes: Sequence[LstmTape], d_h_out: torch.Tensor):
+    """``lstm_backward_stack_group`` for one encoder."""
+    return lstm_backward_stack_group([tapes], [d_h_out])[0]
+
+
+class LstmLastHiddenGroup(torch.autograd.Function):
+    """``h_n[-1]`` of up to 4 (stacked) nn.LSTM encoders of the same depth / hidden size / batch / length in one go,
+    with gradients for their parameters: every layer of the forward and of the backward pass is ONE persistent launch
+    for all encoders.  ``tensors`` = the n input sequences, then the parameters (weight_ih, weight_hh, bias_ih,
+    bias_hh per layer, bottom first) of encoder 0, encoder 1, ...  Returns n tensors (B, hidden)."""
+
+    @staticmethod
+    def forward(ctx, n, depth, lengths_list, dropout_p, seeds, *tensors):
+        xs, params = tensors[:n], tensors[n:]
+        layers_list = [[tuple(params[(i * depth + l) * 4:(i * depth + l) * 4 + 4]) for l in range(depth)] for i in range(n)]
+        hidden = layers_list[0][0][1].shape[1]
+        tapes = lstm_train_forward_stack_group(xs, layers_list, hidden, lengths_list, dropout_p, seeds)
+        ctx.tapes, ctx.n = tapes, n
+        ctx.has = [p is not None for p in params]
+        return tuple(tp[-1].h_out for tp in tapes)
+
+    @staticmethod
+    def backward(ctx, *d_hs):
+        outs = [tp[-1].h_out for tp in ctx.tapes]
+        d_hs = [torch.zeros_like(o) if d is None else d for d, o in zip(d_hs, outs)]
+        grads = lstm_backward_stack_group(ctx.tapes, d_hs)
+        ctx.tapes = None
+        flat = []
+        for per_encoder in grads:
+            for (d_w_ih, d_w_hh, d_b) in per_encoder:
+                flat += [d_w_ih, d_w_hh, d_b, d_b.clone()]
+        return (None, None, None, None, None, *([None] * ctx.n), *[g if has else None for g, has in zip(flat, ctx.has)])
 
 
 class LstmLastHiddenF32(torch.autograd.Function):

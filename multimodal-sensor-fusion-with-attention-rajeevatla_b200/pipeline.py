@@ -38,11 +38,32 @@ class EncodeFuse(nn.Module):
     def _fuses_norms(self) -> bool:
         return type(self.fusion_model).__name__ == "HybridFusion" and hasattr(self.fusion_model, "_plan")
 
+    def _encode(self, features: Mapping[str, torch.Tensor]):
+        """``{m: encoders[m](features[m])}`` in ``encoders`` order (train.py:261-269).  Recurrent encoders on the
+        tensor-core path that agree in cell, depth, hidden size, batch and length (``SequenceEncoder.group_key``) are
+        run together, up to 4 per launch (``SequenceEncoder.forward_group``): the three IMU encoders and the heart-rate
+        encoder of the PAMAP2 configuration share every launch of the recurrence."""
+        todo = [(m, enc) for m, enc in self.encoders.items() if m in features]
+        out, groups = {}, {}
+        for m, enc in todo:
+            key_fn = getattr(enc, "group_key", None)
+            key = key_fn(features[m]) if callable(key_fn) else None
+            if key is not None:
+                groups.setdefault((type(enc), key), []).append(m)
+        for (cls, _), names in groups.items():
+            for i in range(0, len(names), 4):
+                chunk = names[i:i + 4]
+                if len(chunk) < 2:
+                    continue
+                res = cls.forward_group([self.encoders[m] for m in chunk], [features[m] for m in chunk])
+                out.update(dict(zip(chunk, res)))
+        return {m: out[m] if m in out else enc(features[m]) for m, enc in todo}
+
     def forward(self, features: Mapping[str, torch.Tensor], mask: Optional[torch.Tensor] = None,
                 return_attention: bool = False):
         if return_attention and type(self.fusion_model).__name__ != "HybridFusion":
             raise ValueError("Attention information is only available for HybridFusion.")
-        encoded = {m: enc(features[m]) for m, enc in self.encoders.items() if m in features}
+        encoded = self._encode(features)
         norms = {m: self.layer_norms[m] for m in encoded if self.use_layer_norm and m in self.layer_norms}
         kwargs = {}
         if norms and self._fuses_norms():

@@ -265,6 +265,41 @@ class SequenceEncoder(nn.Module):
 
         raise ValueError(f"Unsupported encoder type: {self.encoder_type}")
 
+    # ---- several recurrent encoders in one go (pipeline.EncodeFuse) -------------------------------------------
+    def group_key(self, sequence: torch.Tensor):
+        """Encoders whose keys are equal (and not None) can share the launches of the tensor-core recurrence: same
+        cell, depth, hidden size, batch, length, mode.  None: this encoder runs by itself."""
+        if (self.encoder_type not in ("lstm", "gru") or self.rnn is None or sequence.dim() != 3
+                or not _lstm_tensor_core_ok(self, sequence, None)):
+            return None
+        rnn = self.rnn
+        return (type(rnn).__name__, rnn.num_layers, rnn.hidden_size, tuple(sequence.shape[:2]), str(sequence.device),
+                _lstm_wants_grad(rnn), bool(rnn.training), float(rnn.dropout))
+
+    @staticmethod
+    def forward_group(encoders, sequences):
+        """``[enc(seq) for enc, seq in zip(encoders, sequences)]`` for up to 4 encoders with equal ``group_key``: every
+        layer of the recurrence (forward and, in training mode, backward) is ONE persistent launch for all of them
+        (ops.lstm_forward_stack_group / ops.LstmLastHiddenGroup) instead of one per encoder."""
+        n = len(encoders)
+        rnn0 = encoders[0].rnn
+        layers_list = [_lstm_layers(e.rnn) for e in encoders]
+        with torch.cuda.device(sequences[0].device):
+            if _lstm_wants_grad(rnn0):
+                p = float(rnn0.dropout) if (rnn0.training and rnn0.num_layers > 1) else 0.0
+                seeds = []
+                for e in encoders:
+                    seed = getattr(e, "lstm_dropout_seed", None)
+                    seeds.append(int(seed) if seed is not None else
+                                 (int(torch.randint(0, 2**62, (1,)).item()) if p > 0.0 else 0))
+                flat = [t for layers in layers_list for layer in layers for t in layer]
+                lasts = ops.LstmLastHiddenGroup.apply(n, rnn0.num_layers, None, p, seeds,
+                                                      *[s.detach() for s in sequences], *flat)
+            else:
+                lasts = ops.lstm_forward_stack_group(list(sequences), layers_list, rnn0.hidden_size, None,
+                                                     "gru" if isinstance(rnn0, nn.GRU) else "lstm")
+        return [_dense(e.projection, e.dropout_layer(h.to(s.dtype))) for e, h, s in zip(encoders, lasts, sequences)]
+
 
 class FrameEncoder(nn.Module):
     """Frame-feature encoder with attention / average / max temporal pooling (encoders.py:211-336)."""

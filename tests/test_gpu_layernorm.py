@@ -190,3 +190,14 @@ def test_encode_fuse_trains_from_raw_windows_through_the_recurrence_kernels():
             assert prm.grad is not None and torch.isfinite(prm.grad).all(), (m, name)
             err = float((prm.grad.cpu().double() - ref.double()).norm() / ref.double().norm().clamp_min(1e-30))
             assert err <= 0.1, (m, name, err)
+    # inference through the same grouped launches, and group == one encoder at a time (rows are independent)
+    model.eval()
+    with torch.no_grad():
+        dev_x = {m: x.cuda() for m, x in xs.items()}
+        eval_logits = model(dev_x, mask.cuda())
+        names = list(feats_in)
+        grouped = dropin_encoders.SequenceEncoder.forward_group([encs[m] for m in names], [dev_x[m] for m in names])
+        for m, g in zip(names, grouped):
+            assert encs[m].group_key(dev_x[m]) is not None
+            assert torch.equal(g, encs[m](dev_x[m])), m
+    assert _maxabs(eval_logits, ref_logits) <= 2e-2
