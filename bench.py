@@ -768,6 +768,22 @@ def run_raw_infer(args):
         host_conf.copy_(conf, non_blocking=True)
 
     ms_e2e = timed(e2e, max(1, min(steps, 3)))
+    # the same pass through the module-level drop-in (pipeline.EncodeFuse: SequenceEncoder modules grouped into one
+    # launch of the recurrence, LayerNorm inside the projection kernel, HybridFusion module on the tensor-core path)
+    import copy
+    pipeline = importlib.import_module(PKG + ".pipeline")
+    for e in encs.values():
+        e.precision = "bf16"
+    fus_mod = copy.deepcopy(model).to(dev).eval()
+    fus_mod.precision = "bf16"
+    glue = pipeline.EncodeFuse(encs, fus_mod, norms).eval()
+
+    def module_pass():
+        with torch.no_grad():
+            return glue(xs, mask)
+
+    mod_logits = module_pass().clone()
+    ms_mod = timed(module_pass, steps)
     h2d = sum(t.numel() * 4 for t in host_x.values())
     flop = B * sum(T * 2 * (f + HID) * 4 * HID + 2 * HID * 128 for f in feats_in.values()) + B * FLOP_FWD
     peaks = _peaks()
@@ -791,6 +807,10 @@ def run_raw_infer(args):
                          "lstm_kernel": lstm_only},
             "library_recurrence": {"ms_per_step": ms_lib, "value": B / (ms_lib * 1e-3),
                                    "what": "same pass with torch.nn.LSTM (cuDNN, fp32 no-TF32) for the recurrence"},
+            "module_api": {"ms_per_step": ms_mod, "value": B / (ms_mod * 1e-3),
+                           "what": "pipeline.EncodeFuse(SequenceEncoder x 4, LayerNorm, HybridFusion)(raw windows, mask) "
+                                   "in eval mode, precision bf16: the drop-in modules a caller of train.py / eval.py uses",
+                           "max_abs_logit_diff_vs_engine": float((mod_logits - logits_a).abs().max())},
             "max_abs_logit_diff_vs_library": float((logits_a - logits_b).abs().max())}
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = _cpu_raw_infer_baseline(torch, encoders, fusion, feats_in, T, HID)
@@ -941,6 +961,38 @@ def run_raw_train(args):
                 ht.copy_(t, non_blocking=True)
 
     ms_e2e = timed(e2e, max(1, min(steps, 3)))
+    # the whole model from raw windows through the module-level drop-in, as train.py's training_step wires it
+    # (train.py:233-291,302-324): encoders (grouped launches of the recurrence) -> projection -> LayerNorm ->
+    # HybridFusion -> cross entropy -> backward to every parameter
+    module_api = None
+    try:
+        torch.cuda.empty_cache()
+        pipeline = importlib.import_module(PKG + ".pipeline")
+        fusion = importlib.import_module("fusion")
+        for e in encs.values():
+            e.precision = "bf16"
+        fus_mod = fusion.HybridFusion(DIMS, hidden_dim=HIDDEN, num_classes=CLASSES, num_heads=HEADS, dropout=DROPOUT).to(dev)
+        fus_mod.precision = "bf16"
+        norms = {m: torch.nn.LayerNorm(128).to(dev) for m in feats_in}
+        glue = pipeline.EncodeFuse(encs, fus_mod, norms).train()
+        feats = dict(zip(feats_in, xs))
+        mask = torch.ones(B, len(feats_in), device=dev)
+        labels = torch.randint(0, CLASSES, (B,), device=dev, generator=g)
+
+        def module_step():
+            for prm in glue.parameters():
+                prm.grad = None
+            loss = torch.nn.functional.cross_entropy(glue(feats, mask), labels, label_smoothing=SMOOTHING)
+            loss.backward()
+            return loss
+
+        ms_mod = timed(module_step, max(1, min(steps, 3)))
+        module_api = {"ms_per_step": ms_mod, "value": B / (ms_mod * 1e-3),
+                      "what": "pipeline.EncodeFuse(SequenceEncoder x 4, LayerNorm, HybridFusion) in training mode, precision "
+                              "bf16: forward + cross entropy + backward to every parameter through the drop-in modules",
+                      "final_loss": float(module_step().detach())}
+    except torch.cuda.OutOfMemoryError:
+        pass
     line = {"metric": METRIC, "value": B / (ms * 1e-3), "unit": "windows/s", "n_gpus": 1, "steps": steps, "warmup": 2,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
@@ -964,7 +1016,7 @@ def run_raw_train(args):
             "library_recurrence": None if ms_lib is None else {
                 "ms_per_step": ms_lib, "value": B / (ms_lib * 1e-3),
                 "what": "torch.nn.LSTM forward + autograd backward (cuDNN, fp32 no-TF32) of the same 4 encoders"},
-            "max_rel_gradient_diff_vs_library": rel}
+            "max_rel_gradient_diff_vs_library": rel, "module_api": module_api}
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = _cpu_raw_train_baseline(torch, encoders, feats_in, T, HID)
     os.write(json_fd, (json.dumps(line) + "\n").encode())

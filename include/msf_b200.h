@@ -494,6 +494,19 @@ int msf_lstm_f32_backward(const float* x, int32_t in_dim, const float* w_ih, con
                           float* gates, const float* d_h_last, const float* d_h_seq, float* scratch, float* d_x,
                           float* d_w_ih, float* d_w_hh, float* d_bias, void* stream);
 
+/* The GRU cell of SequenceEncoder (src/encoders.py:66-72: nn.GRU, gate order r | z | n) on the same fp32 kernels, one
+ * layer per call, same conventions as msf_lstm_f32_*: gates is [T][B][4H] ((r | z | n | h-share of the candidate gate)
+ * after the forward pass; the gradient of the input's share of the pre-activations in its first 3H columns after the
+ * backward pass), dzh [T][B][3H] receives the gradient of the recurrent share.  w_ih [3H][in_dim], w_hh [3H][H], biases
+ * [3H] or NULL.  forward scratch: B*3H floats; backward scratch: 2*B*H floats. */
+int msf_gru_f32_forward(const float* x, int32_t in_dim, const float* w_ih, const float* w_hh, const float* b_ih,
+                        const float* b_hh, const int32_t* lengths, int64_t batch, int32_t steps, int32_t hidden,
+                        float* h_seq, float* gates, float* scratch, void* stream);
+int msf_gru_f32_backward(const float* x, int32_t in_dim, const float* w_ih, const float* w_hh, const int32_t* lengths,
+                         int64_t batch, int32_t steps, int32_t hidden, const float* h_seq, float* gates, float* dzh,
+                         const float* d_h_last, const float* d_h_seq, float* scratch, float* d_x, float* d_w_ih,
+                         float* d_w_hh, float* d_b_ih, float* d_b_hh, void* stream);
+
 /* ---- BatchNorm1d -> ReLU -> Dropout behind a Linear layer (src/encoders.py:339-397, BatchNorm at :374-375) ----- */
 /* out = dropout(relu((y - mean) * invstd * gamma + beta)) over y (rows x cols, row-major fp32: the Linear output).
  * training != 0: batch statistics (biased variance; fp64 column sums), running_mean / running_var moved on like

@@ -1113,17 +1113,19 @@ class LstmLastHiddenGroup(torch.autograd.Function):
 
 
 class LstmLastHiddenF32(torch.autograd.Function):
-    """``h_n[-1]`` of a (stacked) nn.LSTM on the fp32 parity kernels (msf_lstm_f32_forward / _backward, one call per
-    layer), with gradients for every parameter AND the input sequence.  ``params``: (weight_ih, weight_hh, bias_ih,
-    bias_hh) per layer, flattened, bottom first.  Training-mode inter-layer dropout (``dropout_p`` > 0): the library's
-    Philox multipliers of site 4 (msf_dropout_mask), keyed by ``seed``."""
+    """``h_n[-1]`` of a (stacked) nn.LSTM or nn.GRU (``cell`` = "lstm" / "gru") on the fp32 parity kernels
+    (msf_lstm_f32_* / msf_gru_f32_*, one call per layer), with gradients for every parameter AND the input sequence.
+    ``params``: (weight_ih, weight_hh, bias_ih, bias_hh) per layer, flattened, bottom first.  Training-mode
+    inter-layer dropout (``dropout_p`` > 0): the library's Philox multipliers of site 4 (msf_dropout_mask), keyed by
+    ``seed``."""
 
     @staticmethod
-    def forward(ctx, x, lengths, dropout_p, seed, *params):
+    def forward(ctx, x, lengths, dropout_p, seed, cell, *params):
         require_cuda("LstmLastHiddenF32")
         B, T, _ = x.shape
         dev = x.device
         n_layers = len(params) // 4
+        gru = cell == "gru"
         ln = _lstm_lengths(lengths, B, T, dev)
         inp = x.detach().to(torch.float32).transpose(0, 1).contiguous()   # time-major [T][B][F]
         layers = []
@@ -1136,25 +1138,28 @@ class LstmLastHiddenF32(torch.autograd.Function):
                 mask = dropout_mask(seed, 0, 4, l, T * B, H, dropout_p, dev).view(T, B, H)
                 inp = inp * mask
             h_seq = torch.empty(T + 1, B, H, dtype=torch.float32, device=dev)
-            c_seq = torch.empty(T + 1, B, H, dtype=torch.float32, device=dev)
             h_seq[0].zero_()
-            c_seq[0].zero_()
             gates = torch.empty(T, B, 4 * H, dtype=torch.float32, device=dev)
             scratch = torch.empty(B * 4 * H, dtype=torch.float32, device=dev)
-            N.check(N.lib().msf_lstm_f32_forward(_p(inp), inp.shape[2], _p(w_ih), _p(w_hh), _p(b_ih), _p(b_hh), _p(ln), B, T, H,
-                                                 _p(h_seq), _p(c_seq), _p(gates), _p(scratch), _stream()))
+            if gru:
+                c_seq = None
+                N.check(N.lib().msf_gru_f32_forward(_p(inp), inp.shape[2], _p(w_ih), _p(w_hh), _p(b_ih), _p(b_hh), _p(ln), B, T,
+                                                    H, _p(h_seq), _p(gates), _p(scratch), _stream()))
+            else:
+                c_seq = torch.empty(T + 1, B, H, dtype=torch.float32, device=dev)
+                c_seq[0].zero_()
+                N.check(N.lib().msf_lstm_f32_forward(_p(inp), inp.shape[2], _p(w_ih), _p(w_hh), _p(b_ih), _p(b_hh), _p(ln), B,
+                                                     T, H, _p(h_seq), _p(c_seq), _p(gates), _p(scratch), _stream()))
             layers.append((inp, w_ih, w_hh, h_seq, c_seq, gates, mask))
             inp = h_seq[1:]
-        ctx.layers, ctx.ln = layers, ln
+        ctx.layers, ctx.ln, ctx.gru = layers, ln, gru
         ctx.has = [p is not None for p in params]
         ctx.want_dx = x.requires_grad
-        if ln is None:
-            return layers[-1][3][T].clone()
         return layers[-1][3][T].clone()   # finished windows carry their state: slice T holds every window's last state
 
     @staticmethod
     def backward(ctx, d_h):
-        layers, ln = ctx.layers, ctx.ln
+        layers, ln, gru = ctx.layers, ctx.ln, ctx.gru
         T1, B, H = layers[0][3].shape
         T = T1 - 1
         dev = d_h.device
@@ -1168,19 +1173,29 @@ class LstmLastHiddenF32(torch.autograd.Function):
             need_dx = l > 0 or ctx.want_dx
             dx = torch.empty(T, B, F, dtype=torch.float32, device=dev) if need_dx else None
             d_w_ih, d_w_hh = torch.empty_like(w_ih), torch.empty_like(w_hh)
-            d_b = torch.empty(4 * H, dtype=torch.float32, device=dev)
             scratch = torch.empty(3 * B * H, dtype=torch.float32, device=dev)
-            N.check(N.lib().msf_lstm_f32_backward(_p(inp), F, _p(w_ih), _p(w_hh), _p(ln), B, T, H, _p(h_seq), _p(c_seq),
-                                                  _p(gates), _p(d_last if l == len(layers) - 1 else None), _p(d_seq),
-                                                  _p(scratch), _p(dx), _p(d_w_ih), _p(d_w_hh), _p(d_b), _stream()))
-            flat[4 * l:4 * l + 4] = [d_w_ih, d_w_hh, d_b, d_b.clone()]
+            top = d_last if l == len(layers) - 1 else None
+            if gru:
+                d_b_ih = torch.empty(3 * H, dtype=torch.float32, device=dev)
+                d_b_hh = torch.empty(3 * H, dtype=torch.float32, device=dev)
+                dzh = torch.empty(T, B, 3 * H, dtype=torch.float32, device=dev)
+                N.check(N.lib().msf_gru_f32_backward(_p(inp), F, _p(w_ih), _p(w_hh), _p(ln), B, T, H, _p(h_seq), _p(gates),
+                                                     _p(dzh), _p(top), _p(d_seq), _p(scratch), _p(dx), _p(d_w_ih), _p(d_w_hh),
+                                                     _p(d_b_ih), _p(d_b_hh), _stream()))
+                flat[4 * l:4 * l + 4] = [d_w_ih, d_w_hh, d_b_ih, d_b_hh]
+            else:
+                d_b = torch.empty(4 * H, dtype=torch.float32, device=dev)
+                N.check(N.lib().msf_lstm_f32_backward(_p(inp), F, _p(w_ih), _p(w_hh), _p(ln), B, T, H, _p(h_seq), _p(c_seq),
+                                                      _p(gates), _p(top), _p(d_seq), _p(scratch), _p(dx), _p(d_w_ih),
+                                                      _p(d_w_hh), _p(d_b), _stream()))
+                flat[4 * l:4 * l + 4] = [d_w_ih, d_w_hh, d_b, d_b.clone()]
             if l > 0:
                 d_seq = dx if mask is None else dx * mask
             else:
                 d_x = dx
         ctx.layers = None
         gx = None if d_x is None else d_x.transpose(0, 1).contiguous()
-        return (gx, None, None, None, *[g if has else None for g, has in zip(flat, ctx.has)])
+        return (gx, None, None, None, None, *[g if has else None for g, has in zip(flat, ctx.has)])
 
 
 class LstmLastHidden(torch.autograd.Function):

@@ -105,22 +105,22 @@ def _lstm_tensor_core(rnn: nn.Module, sequence: torch.Tensor, lengths: Optional[
 
 
 def _lstm_fp32_ok(enc, sequence: torch.Tensor) -> bool:
-    """The default (fp32) precision of an LSTM encoder on a CUDA input runs the recurrence on the library's own fp32
-    kernels (msf_lstm_f32_forward / _backward: FFMA GEMMs + cell kernels, <= 1e-5 of the reference, gradients for the
-    parameters and the input), any depth, with or without ``lengths``.  MSF_LSTM_LIBRARY=1 keeps torch.nn.LSTM."""
+    """The default (fp32) precision of an LSTM / GRU encoder on a CUDA input runs the recurrence on the library's own
+    fp32 kernels (msf_lstm_f32_* / msf_gru_f32_*: FFMA GEMMs + cell kernels, <= 1e-5 of the reference, gradients for the
+    parameters and the input), any depth, with or without ``lengths``.  MSF_LSTM_LIBRARY=1 keeps torch.nn.LSTM / GRU."""
     rnn = enc.rnn
-    return (enc.encoder_type == "lstm" and sequence.is_cuda and isinstance(rnn, nn.LSTM) and not rnn.bidirectional
-            and rnn.proj_size == 0 and not os.environ.get("MSF_LSTM_LIBRARY"))
+    return (enc.encoder_type in ("lstm", "gru") and sequence.is_cuda and isinstance(rnn, (nn.LSTM, nn.GRU))
+            and not rnn.bidirectional and getattr(rnn, "proj_size", 0) == 0 and not os.environ.get("MSF_LSTM_LIBRARY"))
 
 
-def _lstm_fp32(rnn: nn.LSTM, sequence: torch.Tensor, lengths: Optional[torch.Tensor] = None,
+def _lstm_fp32(rnn: nn.Module, sequence: torch.Tensor, lengths: Optional[torch.Tensor] = None,
                seed: Optional[int] = None) -> torch.Tensor:
     p = float(rnn.dropout) if (rnn.training and rnn.num_layers > 1) else 0.0
     if seed is None:
         seed = int(torch.randint(0, 2**62, (1,)).item()) if p > 0.0 else 0
     flat = [t for layer in _lstm_layers(rnn) for t in layer]
     with torch.cuda.device(sequence.device):
-        return ops.LstmLastHiddenF32.apply(sequence, lengths, p, int(seed), *flat)
+        return ops.LstmLastHiddenF32.apply(sequence, lengths, p, int(seed), "gru" if isinstance(rnn, nn.GRU) else "lstm", *flat)
 
 
 def _rnn_fp32(rnn: nn.Module, inp):

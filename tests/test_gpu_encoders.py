@@ -1,5 +1,6 @@
 """Drop-in encoders (src/encoders.py) on the GPU against golden vectors from the reference encoders:
-the Linear layers run on msf_linear_*, the recurrence on PyTorch's LSTM/GRU.  fp32, max-abs <= 1e-5."""
+the Linear layers run on msf_linear_*, the LSTM / GRU recurrences on msf_lstm_f32_* / msf_gru_f32_* (fp32, max-abs <= 1e-5)
+and, with precision = "bf16", on the persistent tensor-core kernels (max-abs <= 1e-2)."""
 import sys
 
 import pytest
@@ -296,30 +297,37 @@ def test_tensor_core_gru_matches_oracle(batch, steps, feat, hidden, layers, ragg
     assert enc.rnn.weight_hh_l0.grad is not None
 
 
-def test_fp32_lstm_runs_on_library_kernels_and_matches_reference_golden(monkeypatch):
-    """The default (fp32) LSTM encoder on a CUDA input does not touch torch.nn.LSTM / cuDNN: the recurrence runs on
-    msf_lstm_f32_forward / _backward (lstm_f32.cu).  Against the unmodified reference's 2-layer golden fixture
-    (outputs with and without lengths, gradients of every parameter and of the input): max-abs <= 1e-5 (5e-5 on the
-    gradients, as for the other fp32 encoder tests)."""
+@pytest.mark.parametrize("kind", ["lstm", "gru"])
+def test_fp32_lstm_runs_on_library_kernels_and_matches_reference_golden(kind, monkeypatch):
+    """The default (fp32) LSTM / GRU encoder on a CUDA input does not touch torch.nn.LSTM / nn.GRU / cuDNN: the
+    recurrence runs on msf_lstm_f32_* / msf_gru_f32_* (lstm_f32.cu).  Against the unmodified reference's 2-layer golden
+    fixtures (outputs, for the LSTM also with lengths; gradients of every parameter and of the input): max-abs <= 1e-5
+    (5e-5 on the gradients, as for the other fp32 encoder tests)."""
     g = Golden("encoders_small.npz")
 
     def no_library(*a, **k):
         raise AssertionError("the fp32 LSTM path must not call the library recurrence")
 
     monkeypatch.setattr(dropin_encoders, "_rnn_fp32", no_library)
-    enc = dropin_encoders.SequenceEncoder(17, hidden_dim=32, output_dim=16, num_layers=2, encoder_type="lstm", dropout=0.0)
-    enc.load_state_dict(g.group("lstm/sd"))
+    enc = dropin_encoders.SequenceEncoder(17, hidden_dim=32, output_dim=16, num_layers=2, encoder_type=kind, dropout=0.0)
+    enc.load_state_dict(g.group(f"{kind}/sd"))
     enc = enc.cuda().eval()
     x = g.t("seq/x").cuda()
-    assert _maxabs(enc(x), g.t("lstm/out")) <= TOL
-    assert _maxabs(enc(x, g.t("seq/lengths")), g.t("lstm/out_lengths")) <= TOL
+    assert _maxabs(enc(x), g.t(f"{kind}/out")) <= TOL
+    if kind == "lstm":
+        assert _maxabs(enc(x, g.t("seq/lengths")), g.t("lstm/out_lengths")) <= TOL
+    else:   # ragged windows of the GRU: against the oracle (the fixture holds none)
+        from oracle import encoder_oracle
+        sd = {k: v.detach().cpu() for k, v in enc.state_dict().items()}
+        ref = encoder_oracle.sequence_encoder_forward(sd, g.t("seq/x"), 2, "gru", g.t("seq/lengths"))
+        assert _maxabs(enc(x, g.t("seq/lengths")), ref) <= TOL
     enc.train()
     xg = x.clone().requires_grad_(True)
     out = enc(xg)
     (out * torch.linspace(-1, 1, 16, device="cuda").unsqueeze(0)).sum().backward()
-    assert _maxabs(xg.grad, g.t("lstm/gradx")) <= 5 * TOL
+    assert _maxabs(xg.grad, g.t(f"{kind}/gradx")) <= 5 * TOL
     grads = dict(enc.named_parameters())
-    for key, ref in g.group("lstm/grad").items():
+    for key, ref in g.group(f"{kind}/grad").items():
         assert _maxabs(grads[key].grad, ref) <= 5 * TOL, key
 
 
