@@ -454,9 +454,11 @@ typedef struct msf_lstm_seq {
   int32_t in_cols;       /* row length of x_bf16 in msf_lstm_backward: 0 for the first layer (64 padded columns); H for a layer above,
                             whose x_bf16 is the [T][B][H] input the forward GEMM read (no ones column: the bias gradient
                             is a column sum of d a) */
-  int32_t cell_type;     /* 0 = LSTM; 1 = GRU (msf_lstm_forward only, no training mode): the four columns of a unit are
-                            (r, z, n_x, n_h) — w_ih row 4u+3 and w_hh row 4u+2 are zero, bias = (b_ir + b_hr, b_iz + b_hz,
-                            b_in, b_hn) — and `cell` holds h in fp32 (zeros on entry) */
+  int32_t cell_type;     /* 0 = LSTM; 1 = GRU: the four columns of a unit are (r, z, n_x, n_h) — w_ih row 4u+3 and w_hh row
+                            4u+2 are zero, bias = (b_ir + b_hr, b_iz + b_hz, b_in, b_hn) — and `cell` holds h in fp32 (zeros
+                            on entry, also in training mode; c_all is unused).  Training mode keeps (r, z, n, a_nh + b_hn)
+                            in `gates`; msf_lstm_backward returns the gradients in the same four-gate row order
+                            (d_w_ih rows of n_h and d_w_hh rows of n_x are meaningless; d_bias = (d b_r, d b_z, d b_in, d b_hn)) */
 } msf_lstm_seq;
 int msf_lstm_forward(const msf_lstm_seq* seqs, int32_t n, int64_t batch, int32_t steps, int32_t hidden, void* stream);
 

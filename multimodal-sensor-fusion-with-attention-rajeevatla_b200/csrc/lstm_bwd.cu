@@ -47,6 +47,7 @@ struct LstmBwdLaunch {
   LstmBwdMaps m[MSF_LSTM_MAX_SEQS];
   __nv_bfloat16* gates[MSF_LSTM_MAX_SEQS];
   const float* c_all[MSF_LSTM_MAX_SEQS];
+  const __nv_bfloat16* h_all[MSF_LSTM_MAX_SEQS];    // GRU: h_{t-1} of every step
   float* dc[MSF_LSTM_MAX_SEQS];
   const float* d_h_out[MSF_LSTM_MAX_SEQS];          // gradient of the last valid hidden state, or nullptr
   const __nv_bfloat16* dh_all[MSF_LSTM_MAX_SEQS];   // [T][B][H] gradient of every step's hidden state (from the layer above), or nullptr
@@ -85,6 +86,10 @@ __device__ __forceinline__ uint32_t lb_pack(float a, float b) {
 // [2] -> first accumulator complete, [3] -> last accumulator complete, [4] -> epilogue done, [5] -> barrier passed
 __device__ long long g_lb_stamps[8];
 
+// GRU = true: the cell backward of nn.GRU (forward kernel with cell_type 1: columns (r, z, n_x, n_h) per unit, the tape
+// holds (r, z, n, a_nh + b_hn)):  d n = d h (1-z)(1-n^2),  d z = d h (h_{t-1} - n) z(1-z),  d r = d n (a_nh + b_hn) r(1-r),
+// d a = (d r, d z, d n, d n r), and d h_{t-1} gets d h z directly (carried in fp32 in the `dc` buffer) beside d a W_hh.
+template <bool GRU>
 __global__ void __launch_bounds__(LB_THREADS, 1) lstm_bwd_kernel(const __grid_constant__ LstmBwdLaunch L) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t off0 = smem_u32(smem_raw);
@@ -197,8 +202,9 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_bwd_kernel(const __grid_co
     } else if (warp >= 4) {
       // ===== epilogue: cell backward on this CTA's 64 hidden units (16 per warp column group) =====
       __nv_bfloat16* gates_t = L.gates[seq] + (long long)t * BH * 4;
-      const float* c_t = L.c_all[seq] + (long long)t * BH;
-      const float* c_p = c_t - BH;   // step t - 1 (not read at t = 0: c_{-1} = 0)
+      const float* c_t = GRU ? nullptr : L.c_all[seq] + (long long)t * BH;
+      const float* c_p = GRU ? nullptr : c_t - BH;   // step t - 1 (not read at t = 0: c_{-1} = 0)
+      const __nv_bfloat16* h_p = GRU ? L.h_all[seq] + (long long)t * BH : nullptr;   // h_{t-1}
       float* dcp = L.dc[seq];
       const float* dho = L.d_h_out[seq];
       const __nv_bfloat16* dha = L.dh_all[seq] != nullptr ? L.dh_all[seq] + (long long)t * BH : nullptr;
@@ -236,8 +242,6 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_bwd_kernel(const __grid_co
           if (live && !(L.dbg & 8)) {
             const long long idx = lb_cell_index(tile, r, u0, H, ragged);
             const uint4 g0 = gp[0], g1 = gp[1];
-            const float4 ct4 = *reinterpret_cast<const float4*>(c_t + idx);
-            const float4 cp4 = t > 0 ? *reinterpret_cast<const float4*>(c_p + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
             const float4 dc4 = *reinterpret_cast<const float4*>(dcp + idx);
             float4 ex4 = ext ? __ldg(reinterpret_cast<const float4*>(dho + (long long)row * H + u0))
                              : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -246,23 +250,41 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_bwd_kernel(const __grid_co
               ex4.x += lb_lo(e2.x); ex4.y += lb_hi(e2.x); ex4.z += lb_lo(e2.y); ex4.w += lb_hi(e2.y);
             }
             const uint32_t gw[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-            const float ct[4] = {ct4.x, ct4.y, ct4.z, ct4.w}, cp[4] = {cp4.x, cp4.y, cp4.z, cp4.w};
             const float dcv[4] = {dc4.x, dc4.y, dc4.z, dc4.w}, ex[4] = {ex4.x, ex4.y, ex4.z, ex4.w};
             uint32_t out[8];
             float dcn[4];
+            if (GRU) {
+              const uint2 hp2 = *reinterpret_cast<const uint2*>(h_p + (long long)row * H + u0);
+              const float hp[4] = {lb_lo(hp2.x), lb_hi(hp2.x), lb_lo(hp2.y), lb_hi(hp2.y)};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float gi = lb_lo(gw[2 * j]), gf = lb_hi(gw[2 * j]), gg = lb_lo(gw[2 * j + 1]), go = lb_hi(gw[2 * j + 1]);
-              const float dh = __uint_as_float(a[4 * g + j]) + ex[j];
-              const float tc = lb_tanh(ct[j]);
-              const float dcs = fmaf(dh * go, 1.0f - tc * tc, dcv[j]);
-              const float dai = dcs * gg * gi * (1.0f - gi);
-              const float daf = dcs * cp[j] * gf * (1.0f - gf);
-              const float dag = dcs * gi * (1.0f - gg * gg);
-              const float dao = dh * tc * go * (1.0f - go);
-              dcn[j] = dcs * gf;
-              out[2 * j] = lb_pack(dai, daf);
-              out[2 * j + 1] = lb_pack(dag, dao);
+              for (int j = 0; j < 4; ++j) {
+                const float gr = lb_lo(gw[2 * j]), gz = lb_hi(gw[2 * j]), gn = lb_lo(gw[2 * j + 1]), hn = lb_hi(gw[2 * j + 1]);
+                const float dh = __uint_as_float(a[4 * g + j]) + ex[j] + dcv[j];   // dcv: d h_{t+1} z_{t+1}, the direct path
+                const float dn = dh * (1.0f - gz) * (1.0f - gn * gn);
+                const float dz = dh * (hp[j] - gn) * gz * (1.0f - gz);
+                const float dr = dn * hn * gr * (1.0f - gr);
+                dcn[j] = dh * gz;
+                out[2 * j] = lb_pack(dr, dz);
+                out[2 * j + 1] = lb_pack(dn, dn * gr);
+              }
+            } else {
+              const float4 ct4 = *reinterpret_cast<const float4*>(c_t + idx);
+              const float4 cp4 = t > 0 ? *reinterpret_cast<const float4*>(c_p + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+              const float ct[4] = {ct4.x, ct4.y, ct4.z, ct4.w}, cp[4] = {cp4.x, cp4.y, cp4.z, cp4.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float gi = lb_lo(gw[2 * j]), gf = lb_hi(gw[2 * j]), gg = lb_lo(gw[2 * j + 1]), go = lb_hi(gw[2 * j + 1]);
+                const float dh = __uint_as_float(a[4 * g + j]) + ex[j];
+                const float tc = lb_tanh(ct[j]);
+                const float dcs = fmaf(dh * go, 1.0f - tc * tc, dcv[j]);
+                const float dai = dcs * gg * gi * (1.0f - gi);
+                const float daf = dcs * cp[j] * gf * (1.0f - gf);
+                const float dag = dcs * gi * (1.0f - gg * gg);
+                const float dao = dh * tc * go * (1.0f - go);
+                dcn[j] = dcs * gf;
+                out[2 * j] = lb_pack(dai, daf);
+                out[2 * j + 1] = lb_pack(dag, dao);
+              }
             }
             *reinterpret_cast<float4*>(dcp + idx) = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
             gp[0] = make_uint4(out[0], out[1], out[2], out[3]);
@@ -437,9 +459,11 @@ extern "C" int msf_lstm_backward(const msf_lstm_seq* seqs, int32_t n, int64_t ba
   L.cps = cps;
   for (int i = 0; i < n; ++i) {
     const msf_lstm_seq& S = seqs[i];
-    MSF_REQUIRE(S.x_bf16 && S.h_all && S.gates && S.c_all && S.w_hh_t && (S.d_h_out || S.d_h_all) && S.dc && S.partial &&
-                    S.d_w_ih && S.d_w_hh && S.d_bias,
+    MSF_REQUIRE(S.x_bf16 && S.h_all && S.gates && (S.c_all || S.cell_type == 1) && S.w_hh_t && (S.d_h_out || S.d_h_all) &&
+                    S.dc && S.partial && S.d_w_ih && S.d_w_hh && S.d_bias,
                 "msf_lstm_backward: null pointer in sequence %d", i);
+    MSF_REQUIRE(S.cell_type == seqs[0].cell_type && (S.cell_type == 0 || S.cell_type == 1),
+                "msf_lstm_backward: cell_type 0 (LSTM) or 1 (GRU), the same for all sequences of a call");
     MSF_REQUIRE(S.in_cols == 0 || S.in_cols == hidden,
                 "msf_lstm_backward: in_cols %d (0 for the first layer, hidden for the layers above)", S.in_cols);
     if (S.in_cols != 0) {
@@ -451,6 +475,7 @@ extern "C" int msf_lstm_backward(const msf_lstm_seq* seqs, int32_t n, int64_t ba
     if ((rc = tc_encode_map(&L.m[i].wt, S.w_hh_t, H, N4, N4, 1, 0, 64, 64))) return rc;
     L.gates[i] = static_cast<__nv_bfloat16*>(S.gates);
     L.c_all[i] = S.c_all;
+    L.h_all[i] = static_cast<const __nv_bfloat16*>(S.h_all);
     L.dc[i] = S.dc;
     L.d_h_out[i] = S.d_h_out;
     L.dh_all[i] = static_cast<const __nv_bfloat16*>(S.d_h_all);
@@ -465,8 +490,9 @@ extern "C" int msf_lstm_backward(const msf_lstm_seq* seqs, int32_t n, int64_t ba
   const size_t smem = fixed + weights + (size_t)stages * LB_A_BYTES;
   const int grid = n * cps * L.cs;
   if (prof_enabled()) prof_begin("LSTM sequence backward", 2.0 * (double)B * H * 4.0 * H * (steps - 1) * n, st);
-  MSF_CHECK_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  MSF_CHECK_CUDA(lb_launch(lstm_bwd_kernel, dim3(grid), dim3(LB_THREADS), smem, st, L.cs, L));
+  auto kernel = seqs[0].cell_type == 1 ? lstm_bwd_kernel<true> : lstm_bwd_kernel<false>;
+  MSF_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MSF_CHECK_CUDA(lb_launch(kernel, dim3(grid), dim3(LB_THREADS), smem, st, L.cs, L));
   MSF_LAUNCH_CHECK();
   prof_end(st);
   if (L.dbg & 16) {

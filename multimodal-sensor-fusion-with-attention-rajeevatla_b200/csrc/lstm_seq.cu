@@ -105,7 +105,7 @@ __device__ long long g_ls_stamps[8];
 // holding (r, z, n_x, n_h) — the weight rows are packed so that column n_x only receives the input's share of the
 // candidate gate and n_h only the recurrent share (ops.gru_pack_weights) — and the cell
 //     r = s(a_r + b_r), z = s(a_z + b_z), n = tanh(a_nx + b_in + r (a_nh + b_hn)), h_t = n + z (h_{t-1} - n)
-// with h kept in fp32 in the `cell` buffer.  Inference only (no tape).
+// with h kept in fp32 in the `cell` buffer.  Training mode keeps (r, z, n, a_nh + b_hn) per unit in the gate buffer.
 template <bool SAVE, bool GRU>
 __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_constant__ LstmSeqLaunch L) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -251,9 +251,10 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
       const __nv_bfloat16* h_prev = SAVE ? reinterpret_cast<const __nv_bfloat16*>(L.hbuf[seq][0]) + (long long)t * BH
                                          : reinterpret_cast<const __nv_bfloat16*>(L.hbuf[seq][par]);
       // training mode: c_{t-1} is read from step t-1's slice (zeros at t = 0) and c_t goes to step t's
-      const bool tape = SAVE && !GRU && L.gates[seq] != nullptr;
-      float* cellp = tape ? L.c_all[seq] + (long long)t * BH : L.cell[seq];
-      const float* cell_prev = tape ? cellp - BH : cellp;
+      const bool tape = SAVE && L.gates[seq] != nullptr;
+      // (GRU: the fp32 hidden state stays in place in `cell` also in training mode; the tape holds h as bf16 in h_all)
+      float* cellp = (tape && !GRU) ? L.c_all[seq] + (long long)t * BH : L.cell[seq];
+      const float* cell_prev = (tape && !GRU) ? cellp - BH : cellp;
       __nv_bfloat16* gates_t = tape ? L.gates[seq] + (long long)t * BH * 4 : nullptr;
       const __nv_bfloat16* zin_t = L.zin[seq] != nullptr ? L.zin[seq] + (long long)t * BH * 4 : nullptr;
       const int* lens = L.lengths[seq];
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
         float4 cprev[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g)
-          cprev[g] = (cell_io && !(tape && t == 0))
+          cprev[g] = (cell_io && !(tape && !GRU && t == 0))
                          ? *reinterpret_cast<const float4*>(cell_prev + ls_cell_index(tile, r, ubase + 4 * g, H, ragged))
                          : make_float4(0.f, 0.f, 0.f, 0.f);
         mbar_wait(acc_full(acc), (cnt >> 1) & 1u);
@@ -314,6 +315,11 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
               cn[j] = fmaf(gz, cp[j] - nn, nn);
               hn[j] = cn[j];
               go[j] = 0.0f;
+              if (tape) {   // (r, z, n, recurrent share of the candidate gate incl. its bias)
+                __nv_bfloat162 s0 = __floats2bfloat162_rn(gr, gz), s1 = __floats2bfloat162_rn(nn, __uint_as_float(a[4 * j + 3]) + b4.w);
+                gs[2 * j] = *reinterpret_cast<uint32_t*>(&s0);
+                gs[2 * j + 1] = *reinterpret_cast<uint32_t*>(&s1);
+              }
               continue;
             }
             const float2 t_if = ls_tanh2(fmaf(__uint_as_float(a[4 * j + 0]), 0.5f, b4.x), fmaf(__uint_as_float(a[4 * j + 1]), 0.5f, b4.y));
@@ -444,8 +450,8 @@ int lstm_seq_launch(const msf_lstm_seq* seqs, int n, long long batch, int steps,
     MSF_REQUIRE(S.w_hh && S.bias && S.h_out, "msf_lstm_forward: null pointer in sequence %d", i);
     MSF_REQUIRE((S.h_all != nullptr) == save && (S.z_in != nullptr) == zin,
                 "msf_lstm_forward: the sequences of one call must use the same mode (h_all / z_in)");
-    MSF_REQUIRE(S.gates == nullptr || (S.h_all && S.c_all),
-                "msf_lstm_forward: training mode needs h_all, gates and c_all (sequence %d)", i);
+    MSF_REQUIRE(S.gates == nullptr || (S.h_all && (S.cell_type == 1 ? S.cell != nullptr : S.c_all != nullptr)),
+                "msf_lstm_forward: training mode needs h_all, gates and c_all (GRU: cell) (sequence %d)", i);
     if (zin) {
       L.zin[i] = static_cast<const __nv_bfloat16*>(S.z_in);
       L.m[i].x = L.m[i].wih = CUtensorMap{};
@@ -487,7 +493,6 @@ int lstm_seq_launch(const msf_lstm_seq* seqs, int n, long long batch, int steps,
   for (int i = 0; i < n; ++i) {
     MSF_REQUIRE(seqs[i].cell_type == seqs[0].cell_type && (seqs[i].cell_type == 0 || seqs[i].cell_type == 1),
                 "msf_lstm_forward: cell_type 0 (LSTM) or 1 (GRU), the same for all sequences of a call");
-    MSF_REQUIRE(!(gru && seqs[i].gates != nullptr), "msf_lstm_forward: the training mode covers the LSTM cell only");
   }
   auto kernel = gru ? (save ? lstm_seq_kernel<true, true> : lstm_seq_kernel<false, true>)
                     : (save ? lstm_seq_kernel<true, false> : lstm_seq_kernel<false, false>);

@@ -802,7 +802,8 @@ class LstmTape:
     states of every step, and the transposed weights of the backward GEMMs."""
 
     def __init__(self, inp, in_cols, features, w_hh_t, w_ih_t, h_all, gates, c_all, h_out, lengths, hidden, layer=0,
-                 drop=None):
+                 drop=None, cell="lstm"):
+        self.cell = cell
         self.inp, self.in_cols, self.features = inp, in_cols, features
         self.w_hh_t, self.w_ih_t = w_hh_t, w_ih_t
         self.h_all, self.gates, self.c_all, self.h_out = h_all, gates, c_all, h_out
@@ -912,7 +913,7 @@ def lstm_forward_stack(x: torch.Tensor, layers: Sequence[tuple], hidden: int,
 
 
 def lstm_train_forward(xs: Sequence[torch.Tensor], weights: Sequence[tuple], hidden: int,
-                       lengths: Optional[Sequence[Optional[torch.Tensor]]] = None) -> List[LstmTape]:
+                       lengths: Optional[Sequence[Optional[torch.Tensor]]] = None, cell: str = "lstm") -> List[LstmTape]:
     """Training-mode forward of up to 4 single-layer LSTM encoders (msf_lstm_forward with the training buffers set):
     ``xs`` are (B, T, F) fp32 windows, ``weights`` per encoder ``(weight_ih, weight_hh, bias_ih, bias_hh)`` as
     nn.LSTM holds them.  One persistent launch; the returned tapes hold ``h_out`` (B, hidden) fp32 and what
@@ -926,11 +927,17 @@ def lstm_train_forward(xs: Sequence[torch.Tensor], weights: Sequence[tuple], hid
     for i, (x, (w_ih, w_hh, b_ih, b_hh)) in enumerate(zip(xs, weights)):
         F = x.shape[2]
         xp = lstm_pack_input(x.to(torch.float32), ones_column=True)
+        if cell == "gru":   # nn.GRU: four-gate form (r, z, n_x, n_h), fp32 hidden state in `cell`, no cell-state tape
+            w_ih, w_hh, b_ih, b_hh = gru_as_four_gates(w_ih, w_hh, b_ih, b_hh)
+            seqs[i].cell_type = 1
+            state = torch.zeros(B * hidden, dtype=torch.float32, device=dev)
+            seqs[i].cell = _p(state)
+            keep.append(state)
         packed = lstm_pack_weights(w_ih, w_hh, b_ih, b_hh)
         h_all = torch.empty(T + 1, B, hidden, dtype=torch.bfloat16, device=dev)
         h_all[0].zero_()
         gates = torch.empty(T, B, 4 * hidden, dtype=torch.bfloat16, device=dev)
-        c_all = torch.empty(T, B * hidden, dtype=torch.float32, device=dev)
+        c_all = None if cell == "gru" else torch.empty(T, B * hidden, dtype=torch.float32, device=dev)
         h_out = torch.empty(B, hidden, dtype=torch.float32, device=dev)
         ln = _lstm_lengths(None if lengths is None else lengths[i], B, T, dev)
         if ln is not None:
@@ -938,14 +945,15 @@ def lstm_train_forward(xs: Sequence[torch.Tensor], weights: Sequence[tuple], hid
         seqs[i].x_bf16, seqs[i].w_hh, seqs[i].w_ih, seqs[i].bias = _p(xp), _p(packed[0]), _p(packed[1]), _p(packed[2])
         seqs[i].h_all, seqs[i].gates, seqs[i].c_all, seqs[i].h_out = _p(h_all), _p(gates), _p(c_all), _p(h_out)
         keep.append(packed)
-        tapes.append(LstmTape(xp, 0, F, lstm_pack_weights_t(w_hh), None, h_all, gates, c_all, h_out, ln, hidden))
+        tapes.append(LstmTape(xp, 0, F, lstm_pack_weights_t(w_hh), None, h_all, gates, c_all, h_out, ln, hidden, cell=cell))
     N.check(N.lib().msf_lstm_forward(seqs, n, B, T, hidden, _stream()))
     return tapes
 
 
 def lstm_train_forward_stack_group(xs: Sequence[torch.Tensor], layers_list: Sequence[Sequence[tuple]], hidden: int,
                                    lengths_list: Optional[Sequence[Optional[torch.Tensor]]] = None,
-                                   dropout_p: float = 0.0, seeds: Optional[Sequence[int]] = None) -> List[List[LstmTape]]:
+                                   dropout_p: float = 0.0, seeds: Optional[Sequence[int]] = None,
+                                   cell: str = "lstm") -> List[List[LstmTape]]:
     """Training-mode forward of up to 4 stacked nn.LSTM encoders of the same depth / hidden size / batch / length:
     per encoder one tape per layer, bottom first (``tapes[i][-1].h_out`` is ``h_n[-1]`` of encoder i); every layer is
     ONE persistent launch for all encoders.  Between the layers nn.LSTM's dropout (p = ``dropout_p``) is applied with
@@ -961,7 +969,7 @@ def lstm_train_forward_stack_group(xs: Sequence[torch.Tensor], layers_list: Sequ
         raise N.MsfError("lstm_train_forward_stack_group: the encoders of one call share depth, batch and length")
     seeds = list(seeds) if seeds is not None else [0] * n
     lns = [_lstm_lengths(None if lengths_list is None else lengths_list[i], B, T, dev) for i in range(n)]
-    tapes = [[tp] for tp in lstm_train_forward(xs, [ls[0] for ls in layers_list], hidden, lns)]
+    tapes = [[tp] for tp in lstm_train_forward(xs, [ls[0] for ls in layers_list], hidden, lns, cell)]
     for l in range(1, depth):
         seqs = (N.LstmSeq * n)()
         keep, new = [], []
@@ -976,20 +984,26 @@ def lstm_train_forward_stack_group(xs: Sequence[torch.Tensor], layers_list: Sequ
                 drop = (float(dropout_p), seeds[i], 0)
             else:
                 inp = below
+            q = seqs[i]
+            if cell == "gru":
+                w = gru_as_four_gates(*w)
+                q.cell_type = 1
+                state = torch.zeros(B * hidden, dtype=torch.float32, device=dev)
+                q.cell = _p(state)
+                keep.append(state)
             w_hh, w_ih, bias = lstm_pack_upper(*w)
             gates = gemm_bf16(inp, w_ih, out_dtype=torch.bfloat16).view(T, B, 4 * hidden)
             h_all = torch.empty(T + 1, B, hidden, dtype=torch.bfloat16, device=dev)
             h_all[0].zero_()
-            c_all = torch.empty(T, B * hidden, dtype=torch.float32, device=dev)
+            c_all = None if cell == "gru" else torch.empty(T, B * hidden, dtype=torch.float32, device=dev)
             h_out = torch.empty(B, hidden, dtype=torch.float32, device=dev)
-            q = seqs[i]
             q.w_hh, q.bias, q.z_in, q.gates = _p(w_hh), _p(bias), _p(gates), _p(gates)
             q.h_all, q.c_all, q.h_out = _p(h_all), _p(c_all), _p(h_out)
             if lns[i] is not None:
                 q.lengths = _p(lns[i])
             keep += [w_hh, bias]
             new.append(LstmTape(inp, hidden, hidden, lstm_pack_weights_t(w[1]), lstm_pack_weights_t(w[0]), h_all, gates,
-                                c_all, h_out, lns[i], hidden, layer=l, drop=drop))
+                                c_all, h_out, lns[i], hidden, layer=l, drop=drop, cell=cell))
         N.check(N.lib().msf_lstm_forward(seqs, n, B, T, hidden, _stream()))
         for i in range(n):
             tapes[i].append(new[i])
@@ -1002,7 +1016,7 @@ def lstm_train_forward_stack(x: torch.Tensor, layers: Sequence[tuple], hidden: i
                              offset: int = 0) -> List[LstmTape]:
     """``lstm_train_forward_stack_group`` for one encoder (``offset`` is kept for callers of the first version: 0)."""
     return lstm_train_forward_stack_group([x], [layers], hidden, None if lengths is None else [lengths], dropout_p,
-                                          [seed])[0]
+                                          [seed], "lstm")[0]
 
 
 def lstm_backward(tapes: Sequence[LstmTape], d_h_out: Sequence[Optional[torch.Tensor]],
@@ -1035,6 +1049,7 @@ def lstm_backward(tapes: Sequence[LstmTape], d_h_out: Sequence[Optional[torch.Te
         q.x_bf16, q.h_all, q.gates, q.c_all, q.w_hh_t = _p(tp.inp), _p(tp.h_all), _p(tp.gates), _p(tp.c_all), _p(tp.w_hh_t)
         q.dc, q.partial = _p(dc), _p(partial)
         q.d_w_ih, q.d_w_hh, q.d_bias, q.features, q.in_cols = _p(d_w_ih), _p(d_w_hh), _p(d_b), tp.features, tp.in_cols
+        q.cell_type = 1 if tp.cell == "gru" else 0
         if d_h_out[i] is not None:
             dh = d_h_out[i].to(device=dev, dtype=torch.float32).contiguous()
             keep.append(dh)
@@ -1090,11 +1105,12 @@ class LstmLastHiddenGroup(torch.autograd.Function):
     bias_hh per layer, bottom first) of encoder 0, encoder 1, ...  Returns n tensors (B, hidden)."""
 
     @staticmethod
-    def forward(ctx, n, depth, lengths_list, dropout_p, seeds, *tensors):
+    def forward(ctx, n, depth, lengths_list, dropout_p, seeds, cell, *tensors):
         xs, params = tensors[:n], tensors[n:]
+        ctx.cell = cell
         layers_list = [[tuple(params[(i * depth + l) * 4:(i * depth + l) * 4 + 4]) for l in range(depth)] for i in range(n)]
         hidden = layers_list[0][0][1].shape[1]
-        tapes = lstm_train_forward_stack_group(xs, layers_list, hidden, lengths_list, dropout_p, seeds)
+        tapes = lstm_train_forward_stack_group(xs, layers_list, hidden, lengths_list, dropout_p, seeds, cell)
         ctx.tapes, ctx.n = tapes, n
         ctx.has = [p is not None for p in params]
         return tuple(tp[-1].h_out for tp in tapes)
@@ -1108,8 +1124,13 @@ class LstmLastHiddenGroup(torch.autograd.Function):
         flat = []
         for per_encoder in grads:
             for (d_w_ih, d_w_hh, d_b) in per_encoder:
-                flat += [d_w_ih, d_w_hh, d_b, d_b.clone()]
-        return (None, None, None, None, None, *([None] * ctx.n), *[g if has else None for g, has in zip(flat, ctx.has)])
+                if ctx.cell == "gru":   # four-gate rows (r | z | n_x | n_h) back to nn.GRU's (r | z | n)
+                    H = d_w_hh.shape[1]
+                    flat += [torch.cat([d_w_ih[:2 * H], d_w_ih[2 * H:3 * H]], 0), torch.cat([d_w_hh[:2 * H], d_w_hh[3 * H:]], 0),
+                             torch.cat([d_b[:2 * H], d_b[2 * H:3 * H]], 0), torch.cat([d_b[:2 * H], d_b[3 * H:]], 0)]
+                else:
+                    flat += [d_w_ih, d_w_hh, d_b, d_b.clone()]
+        return (None, None, None, None, None, None, *([None] * ctx.n), *[g if has else None for g, has in zip(flat, ctx.has)])
 
 
 class LstmLastHiddenF32(torch.autograd.Function):
@@ -1198,24 +1219,12 @@ class LstmLastHiddenF32(torch.autograd.Function):
         return (gx, None, None, None, None, *[g if has else None for g, has in zip(flat, ctx.has)])
 
 
-class LstmLastHidden(torch.autograd.Function):
-    """``h_n[-1] = LSTM(x)`` of one (stacked) nn.LSTM with gradients for its parameters (none for ``x``: the
-    encoders' inputs are data): msf_lstm_forward in training mode + msf_lstm_backward per layer.  ``params`` are
-    (weight_ih, weight_hh, bias_ih, bias_hh) of every layer, flattened, bottom layer first."""
+class LstmLastHidden:
+    """``h_n[-1]`` of ONE (stacked) nn.LSTM / nn.GRU with gradients for its parameters (none for ``x``: the encoders'
+    inputs are data): ``LstmLastHiddenGroup`` with one encoder.  ``params`` are (weight_ih, weight_hh, bias_ih, bias_hh)
+    of every layer, flattened, bottom layer first."""
 
     @staticmethod
-    def forward(ctx, x, lengths, dropout_p, seed, *params):
-        layers = [tuple(params[4 * l:4 * l + 4]) for l in range(len(params) // 4)]
-        tapes = lstm_train_forward_stack(x, layers, layers[0][1].shape[1], lengths, dropout_p, seed)
-        ctx.tapes = tapes
-        ctx.has = [p is not None for p in params]
-        return tapes[-1].h_out
-
-    @staticmethod
-    def backward(ctx, d_h):
-        grads = lstm_backward_stack(ctx.tapes, d_h)
-        ctx.tapes = None
-        flat = []
-        for (d_w_ih, d_w_hh, d_b) in grads:
-            flat += [d_w_ih, d_w_hh, d_b, d_b.clone()]
-        return (None, None, None, None, *[g if has else None for g, has in zip(flat, ctx.has)])
+    def apply(x, lengths, dropout_p, seed, *params, cell: str = "lstm"):
+        return LstmLastHiddenGroup.apply(1, len(params) // 4, None if lengths is None else [lengths], dropout_p, [seed],
+                                         cell, x, *params)[0]

@@ -57,8 +57,8 @@ def _lstm_tensor_core_ok(enc, sequence: torch.Tensor, lengths) -> bool:
     any depth, CUDA input, hidden % 64 == 0, input_dim <= 64; per-window ``lengths`` (the reference packs ragged
     windows, src/encoders.py:140-152), stacked layers and the training mode (gradients wanted for the LSTM's
     parameters) on the persistent kernels (hidden <= 256).  GRU encoders (src/encoders.py:66-72): the
-    same kernels in inference (hidden <= 256).  A gradient with respect to the input sequence is not provided (the
-    encoders' inputs are data) and keeps the library recurrence, as does GRU training."""
+    same kernels (hidden <= 256), inference and training.  A gradient with respect to the input sequence is not provided
+    on this path (the encoders' inputs are data): such a call takes the fp32 kernels (_lstm_fp32)."""
     prec = getattr(enc, "precision", None) or os.environ.get("MSF_PRECISION", "fp32")
     rnn = enc.rnn
     if not (prec == "bf16" and enc.encoder_type in ("lstm", "gru") and sequence.is_cuda
@@ -69,7 +69,7 @@ def _lstm_tensor_core_ok(enc, sequence: torch.Tensor, lengths) -> bool:
         return False
     persistent = rnn.hidden_size <= 256 and not os.environ.get("MSF_LSTM_STEPS")
     if _lstm_wants_grad(rnn):
-        return persistent and isinstance(rnn, nn.LSTM)
+        return persistent
     if lengths is not None or rnn.num_layers > 1 or isinstance(rnn, nn.GRU):
         return persistent
     return True
@@ -95,7 +95,8 @@ def _lstm_tensor_core(rnn: nn.Module, sequence: torch.Tensor, lengths: Optional[
             if seed is None:
                 seed = int(torch.randint(0, 2**62, (1,)).item()) if p > 0.0 else 0
             flat = [t for layer in layers for t in layer]
-            return ops.LstmLastHidden.apply(sequence.detach(), lengths, p, int(seed), *flat)
+            return ops.LstmLastHidden.apply(sequence.detach(), lengths, p, int(seed), *flat,
+                                            cell="gru" if isinstance(rnn, nn.GRU) else "lstm")
         if rnn.num_layers > 1 or isinstance(rnn, nn.GRU):
             return ops.lstm_forward_stack(sequence, layers, rnn.hidden_size, lengths,
                                           "gru" if isinstance(rnn, nn.GRU) else "lstm")
@@ -294,6 +295,7 @@ class SequenceEncoder(nn.Module):
                                  (int(torch.randint(0, 2**62, (1,)).item()) if p > 0.0 else 0))
                 flat = [t for layers in layers_list for layer in layers for t in layer]
                 lasts = ops.LstmLastHiddenGroup.apply(n, rnn0.num_layers, None, p, seeds,
+                                                      "gru" if isinstance(rnn0, nn.GRU) else "lstm",
                                                       *[s.detach() for s in sequences], *flat)
             else:
                 lasts = ops.lstm_forward_stack_group(list(sequences), layers_list, rnn0.hidden_size, None,

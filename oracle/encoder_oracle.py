@@ -59,7 +59,8 @@ def lstm_last_hidden(sd: StateDict, prefix: str, x: torch.Tensor, num_layers: in
 
 
 def gru_last_hidden(sd: StateDict, prefix: str, x: torch.Tensor, num_layers: int,
-                    lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    lengths: Optional[torch.Tensor] = None,
+                    layer_masks: Optional[Mapping[int, torch.Tensor]] = None) -> torch.Tensor:
     """``h_n[-1]`` of a ``batch_first`` multi-layer GRU (gate order r, z, n); with ``lengths`` the state of row b
     stops after ``lengths[b]`` steps (pack_padded_sequence, encoders.py:141-156)."""
     B, T, _ = x.shape
@@ -88,6 +89,8 @@ def gru_last_hidden(sd: StateDict, prefix: str, x: torch.Tensor, num_layers: int
             h = h_new
             outs.append(h)
         inp = torch.stack(outs, dim=1)
+        if layer_masks is not None and (layer + 1) in layer_masks:   # nn.GRU's training-mode inter-layer dropout, injected
+            inp = inp * layer_masks[layer + 1].to(x.dtype)
     return h
 
 
@@ -101,7 +104,7 @@ def sequence_encoder_forward(sd: StateDict, x: torch.Tensor, num_layers: int, en
     if encoder_type == "lstm":
         final = lstm_last_hidden(sd, "rnn", x, num_layers, lengths, layer_masks)
     elif encoder_type == "gru":
-        final = gru_last_hidden(sd, "rnn", x, num_layers, lengths)
+        final = gru_last_hidden(sd, "rnn", x, num_layers, lengths, layer_masks)
     else:
         raise ValueError(f"Unsupported encoder type: {encoder_type}")
     return final @ sd["projection.weight"].to(x.dtype).t() + sd["projection.bias"].to(x.dtype)

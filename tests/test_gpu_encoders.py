@@ -227,7 +227,8 @@ def test_tensor_core_lstm_stacked_inference(batch, steps, feat, hidden, layers, 
                                                                       (260, 33, 17, 256, 2, 0.1, True),
                                                                       (130, 25, 3, 128, 3, 0.2, False),
                                                                       (200, 30, 64, 256, 2, 0.1, False)])
-def test_tensor_core_lstm_stacked_training(batch, steps, feat, hidden, layers, p, ragged):
+@pytest.mark.parametrize("kind", ["lstm", "gru"])
+def test_tensor_core_lstm_stacked_training(batch, steps, feat, hidden, layers, p, ragged, kind):
     """Stacked LSTM in training mode: per layer msf_lstm_forward (tape) / msf_lstm_backward, between the layers one
     GEMM each way and nn.LSTM's inter-layer dropout with the library's Philox multipliers, which are injected into the
     oracle (msf_dropout_mask site 4).  Gradients of every layer's parameters against autograd through the oracle:
@@ -235,7 +236,7 @@ def test_tensor_core_lstm_stacked_training(batch, steps, feat, hidden, layers, p
     from oracle import encoder_oracle
     pkg_ops = dropin_encoders.ops
     torch.manual_seed(11)
-    enc = dropin_encoders.SequenceEncoder(feat, hidden_dim=hidden, output_dim=128, num_layers=layers, encoder_type="lstm",
+    enc = dropin_encoders.SequenceEncoder(feat, hidden_dim=hidden, output_dim=128, num_layers=layers, encoder_type=kind,
                                           dropout=p).train()
     enc.dropout_layer.p = 0.0   # the dropout on the last hidden state draws from torch's generator: not under test
     gen = torch.Generator().manual_seed(12)
@@ -252,7 +253,7 @@ def test_tensor_core_lstm_stacked_training(batch, steps, feat, hidden, layers, p
                  .permute(1, 0, 2).cpu() for l in range(1, layers)}
         assert 0.5 * p < float((masks[1] == 0).float().mean()) < 1.5 * p
     sd = {k: v.detach().clone().requires_grad_(True) for k, v in enc.state_dict().items()}
-    ref_out = encoder_oracle.sequence_encoder_forward(sd, x, layers, "lstm", lengths, masks)
+    ref_out = encoder_oracle.sequence_encoder_forward(sd, x, layers, kind, lengths, masks)
     (ref_out * probe).sum().backward()
     enc = enc.cuda()
     enc.precision = "bf16"
@@ -291,10 +292,6 @@ def test_tensor_core_gru_matches_oracle(batch, steps, feat, hidden, layers, ragg
         out = enc(x.cuda(), None if lengths is None else lengths.cuda())
     assert torch.isfinite(out).all()
     assert _maxabs(out, ref_out) <= 1e-2
-    # training keeps the library recurrence and still produces gradients
-    enc.train()
-    enc(x[:8].cuda()).sum().backward()
-    assert enc.rnn.weight_hh_l0.grad is not None
 
 
 @pytest.mark.parametrize("kind", ["lstm", "gru"])
