@@ -59,6 +59,15 @@ def use_scaled_shape():
 METRIC = "windows/sec HybridFusion fwd+bwd & inference at 1/2/4/8 B200; % of HBM/TC roofline"
 
 
+def _lstm_traffic(key, steps):
+    """DRAM bytes of one recurrence launch from the ncu capture (profiles/traffic.json: per time step), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)["lstm_kernels_dram_bytes_per_time_step"][key] * steps
+    except Exception:  # noqa: BLE001 - optional ncu-derived figure
+        return None
+
+
 def _peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -752,7 +761,8 @@ def run_raw_infer(args):
     ms_lib = timed(library, steps)
     ms_lstm = timed(lstm_graph.replay, steps)   # the recurrence launch alone
     lstm_flop = B * sum(T * 2 * (f + HID) * 4 * HID for f in feats_in.values())
-    lstm_only = {"ms": ms_lstm, "tflops": lstm_flop / (ms_lstm * 1e-3) / 1e12,
+    lstm_only = {"ms": ms_lstm, "traffic": _lstm_traffic("lstm_seq_kernel_inference", T),
+                 "tflops": lstm_flop / (ms_lstm * 1e-3) / 1e12,
                  "frac": lstm_flop / (ms_lstm * 1e-3) / 1e12 / _peaks()["tflops"],
                  "us_per_time_step": ms_lstm * 1e3 / T}
     # e2e: raw windows from pinned host memory, predictions and confidences read back, every pass
@@ -801,7 +811,7 @@ def run_raw_infer(args):
                            "ops.lstm_forward, FusionEngine.infer, predictions + confidences copied back"},
             "gpu_launches": (1 if HID <= 256 and not os.environ.get("MSF_LSTM_STEPS") else T) + 8,
             "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                         "frac": tf / peaks["tflops"], "traffic": None, "peak_source": peaks["src"],
+                         "frac": tf / peaks["tflops"], "traffic": _lstm_traffic("lstm_seq_kernel_inference", T), "peak_source": peaks["src"],
                          "kernel": "whole pass: lstm_seq_kernel (one persistent launch over the 1024 steps of the 4 "
                                    "encoders; MSF_LSTM_STEPS=1: one tc_gemm_kernel launch per step) + fusion forward",
                          "lstm_kernel": lstm_only},
@@ -1011,7 +1021,7 @@ def run_raw_train(args):
                           "backward (lstm_bwd_kernel + weight-gradient GEMMs + reduction)": ms_bwd},
             "per_launch": launches,
             "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                         "frac": tf / peaks["tflops"], "traffic": None, "peak_source": peaks["src"],
+                         "frac": tf / peaks["tflops"], "traffic": (_lstm_traffic("lstm_seq_kernel_training", T) or 0) + (_lstm_traffic("lstm_bwd_kernel", T) or 0) or None, "peak_source": peaks["src"],
                          "kernel": "whole pass: lstm_seq_kernel<true> + lstm_bwd_kernel + tc_gemm_kernel<true> (weight gradients)"},
             "library_recurrence": None if ms_lib is None else {
                 "ms_per_step": ms_lib, "value": B / (ms_lib * 1e-3),
