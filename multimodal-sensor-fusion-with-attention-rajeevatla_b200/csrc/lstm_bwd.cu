@@ -39,6 +39,8 @@ constexpr uint32_t LB_W_BYTES = 64 * 64 * 2;    // one k-block of this CTA's row
 constexpr size_t LB_SMEM_LIMIT = 232448;
 constexpr int LB_NBAR = 2 * LB_MAX_STAGES + 5;
 constexpr int LB_ACC_COLS = 64;                 // accumulator: 128 windows x 64 hidden units
+constexpr int LB_DC_COL0 = 2 * LB_ACC_COLS;     // behind the two accumulators: the carried d c of up to LB_DC_TILES tiles
+constexpr int LB_DC_TILES = (512 - LB_DC_COL0) / 64;
 
 struct LstmBwdMaps {
   CUtensorMap da, wt;
@@ -53,7 +55,9 @@ struct LstmBwdLaunch {
   const __nv_bfloat16* dh_all[MSF_LSTM_MAX_SEQS];   // [T][B][H] gradient of every step's hidden state (from the layer above), or nullptr
   const int* lengths[MSF_LSTM_MAX_SEQS];
   int n, rows, steps, hidden, kb4, cs, cps, row_tiles, stages;
-  int dbg;   // MSF_LSTM_DBG: 16 = cycle stamps of CTA 0, 8 = no gate / cell traffic in the epilogue (timing only)
+  int dc_tmem;   // 1: d c (GRU: the direct d h z path) lives in TMEM columns [128, 128 + 64 tiles) instead of `dc`
+  int dbg;   // MSF_LSTM_DBG: 16 = cycle stamps of CTA 0, 8 = no gate / cell traffic in the epilogue (timing only),
+             // 4 = keep d c in global memory
 };
 
 __device__ __forceinline__ uint32_t lb_ctarank() {
@@ -130,7 +134,7 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_bwd_kernel(const __grid_co
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(2u * LB_ACC_COLS) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -239,10 +243,17 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_bwd_kernel(const __grid_co
         for (int g = 0; g < 4; ++g) {
           const int u0 = ubase + 4 * g;
           uint4* gp = reinterpret_cast<uint4*>(gates_t + (long long)row * 4 * H + 4 * u0);
+          // the carried d c of these 4 units: a TMEM scratch column group of this thread's lane (warp-collective
+          // access: outside the per-window branch), or the global `dc` buffer
+          const uint32_t dc_taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(LB_DC_COL0 + i * 64 + cg * 16 + 4 * g);
+          uint32_t dct[4] = {0u, 0u, 0u, 0u};
+          if (L.dc_tmem && s > 0) tmem_ld4(dc_taddr, dct);
           if (live && !(L.dbg & 8)) {
             const long long idx = lb_cell_index(tile, r, u0, H, ragged);
             const uint4 g0 = gp[0], g1 = gp[1];
-            const float4 dc4 = *reinterpret_cast<const float4*>(dcp + idx);
+            const float4 dc4 = L.dc_tmem ? make_float4(__uint_as_float(dct[0]), __uint_as_float(dct[1]), __uint_as_float(dct[2]),
+                                                       __uint_as_float(dct[3]))
+                                         : *reinterpret_cast<const float4*>(dcp + idx);
             float4 ex4 = ext ? __ldg(reinterpret_cast<const float4*>(dho + (long long)row * H + u0))
                              : make_float4(0.f, 0.f, 0.f, 0.f);
             if (dha != nullptr) {   // this step's hidden state also fed the layer above
@@ -286,15 +297,22 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_bwd_kernel(const __grid_co
                 out[2 * j + 1] = lb_pack(dag, dao);
               }
             }
-            *reinterpret_cast<float4*>(dcp + idx) = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
+            if (L.dc_tmem) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dct[j] = __float_as_uint(dcn[j]);
+            } else {
+              *reinterpret_cast<float4*>(dcp + idx) = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
+            }
             gp[0] = make_uint4(out[0], out[1], out[2], out[3]);
             gp[1] = make_uint4(out[4], out[5], out[6], out[7]);
           } else if (row_ok) {   // a step behind the window's length: no gradient through it
             gp[0] = make_uint4(0u, 0u, 0u, 0u);
             gp[1] = make_uint4(0u, 0u, 0u, 0u);
           }
+          if (L.dc_tmem) tmem_st4(dc_taddr, dct);   // (unchanged for a window that did not take this step)
         }
       }
+      if (L.dc_tmem) tmem_st_wait();
       // d a_t is read back by TMA (async proxy) in the next step, by every CTA of the cluster
       asm volatile("fence.proxy.async.global;" ::: "memory");
       __threadfence();
@@ -309,7 +327,7 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_bwd_kernel(const __grid_co
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * LB_ACC_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -457,6 +475,7 @@ extern "C" int msf_lstm_backward(const msf_lstm_seq* seqs, int32_t n, int64_t ba
   int cps = (sms / L.cs) / n;
   if (cps > L.row_tiles) cps = L.row_tiles;
   L.cps = cps;
+  L.dc_tmem = (ceil_div(L.row_tiles, cps) <= LB_DC_TILES && !(L.dbg & 4)) ? 1 : 0;
   for (int i = 0; i < n; ++i) {
     const msf_lstm_seq& S = seqs[i];
     MSF_REQUIRE(S.x_bf16 && S.h_all && S.gates && (S.c_all || S.cell_type == 1) && S.w_hh_t && (S.d_h_out || S.d_h_all) &&
