@@ -461,6 +461,8 @@ typedef struct msf_lstm_seq {
                             (d_w_ih rows of n_h and d_w_hh rows of n_x are meaningless; d_bias = (d b_r, d b_z, d b_in, d b_hn)) */
 } msf_lstm_seq;
 int msf_lstm_forward(const msf_lstm_seq* seqs, int32_t n, int64_t batch, int32_t steps, int32_t hidden, void* stream);
+/* sizeof(msf_lstm_seq) as compiled, for binding self-checks */
+int msf_lstm_seq_bytes(void);
 
 /* Backward pass of the recurrence (training mode of SequenceEncoder, src/encoders.py:135-166 under autograd): given
  * d_h_out and what msf_lstm_forward kept (h_all, gates, c_all), ONE persistent launch walks the steps backwards

@@ -174,6 +174,7 @@ PROTOTYPES = {
                                               c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                               c_void_p, c_void_p]),
     "msf_lstm_forward": (c_int32, [POINTER(LstmSeq), c_int32, c_int64, c_int32, c_int32, c_void_p]),
+    "msf_lstm_seq_bytes": (c_int32, []),
     "msf_lstm_backward": (c_int32, [POINTER(LstmSeq), c_int32, c_int64, c_int32, c_int32, c_void_p]),
     "msf_lstm_f32_forward": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
                                        c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -227,6 +228,9 @@ def lib():
         if (a.value, b.value) != (ctypes.sizeof(FusionShape), ctypes.sizeof(FusionCall)):
             raise MsfError(f"struct layout mismatch: library {(a.value, b.value)}, binding "
                            f"{(ctypes.sizeof(FusionShape), ctypes.sizeof(FusionCall))}")
+        if handle.msf_lstm_seq_bytes() != ctypes.sizeof(LstmSeq):
+            raise MsfError(f"struct layout mismatch: msf_lstm_seq is {handle.msf_lstm_seq_bytes()} bytes in the library, "
+                           f"{ctypes.sizeof(LstmSeq)} in the binding")
         _LIB = handle
     return _LIB
 

@@ -135,6 +135,8 @@ int msf_struct_sizes(int32_t* shape_bytes, int32_t* call_bytes) {
   return MSF_OK;
 }
 
+int msf_lstm_seq_bytes(void) { return (int)sizeof(msf_lstm_seq); }
+
 uint64_t msf_launch_count(void) { return msf::g_launch_count; }
 
 const char* msf_last_error(void) { return msf::g_err; }
