@@ -59,6 +59,40 @@ def use_scaled_shape():
 METRIC = "windows/sec HybridFusion fwd+bwd & inference at 1/2/4/8 B200; % of HBM/TC roofline"
 
 
+class HostPipeline:
+    """Two device slots for a list of input tensors fed from pinned host memory on a copy stream: the copy of batch
+    i+1 overlaps the pass over batch i (what FusionEngine.train_stream does for the fusion step).  next() returns the
+    device tensors of the batch to process now (the compute stream already waits for its copy); release() marks them
+    consumed, so that the slot may be overwritten."""
+
+    def __init__(self, torch, host_tensors, device):
+        self.torch, self.host = torch, host_tensors
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.slots = [[torch.empty(t.shape, dtype=t.dtype, device=device) for t in host_tensors] for _ in range(2)]
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.free = [torch.cuda.Event() for _ in range(2)]
+        self.i = 0
+        self._issue(0)
+
+    def _issue(self, k):
+        torch = self.torch
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.free[k])
+            for dst, src in zip(self.slots[k], self.host):
+                dst.copy_(src, non_blocking=True)
+            self.ready[k].record(self.copy_stream)
+
+    def next(self):
+        k = self.i & 1
+        self._issue(k ^ 1)
+        self.torch.cuda.current_stream().wait_event(self.ready[k])
+        return self.slots[k]
+
+    def release(self):
+        self.free[self.i & 1].record(self.torch.cuda.current_stream())
+        self.i += 1
+
+
 def _lstm_traffic(key, steps):
     """DRAM bytes of one recurrence launch from the ncu capture (profiles/traffic.json: per time step), or None."""
     try:
@@ -728,9 +762,11 @@ def run_raw_infer(args):
     with torch.cuda.graph(lstm_graph, stream=side):
         static_h = ops.lstm_forward(static_x, packed_w, HID)
 
-    def ours():
-        for dst, x in zip(static_x, xs.values()):                           # bf16, time-major, padded: part of the pass
+    def ours(src=None, after_pack=None):
+        for dst, x in zip(static_x, src if src is not None else xs.values()):   # bf16, time-major, padded: part of the pass
             dst[:, :, :x.shape[2]] = x.transpose(0, 1)
+        if after_pack is not None:
+            after_pack()
         lstm_graph.replay()
         return tail(static_h)
 
@@ -770,14 +806,15 @@ def run_raw_infer(args):
     host_pred = torch.zeros(B, dtype=torch.int64).pin_memory()
     host_conf = torch.zeros(B, dtype=torch.float32).pin_memory()
 
+    pipe = HostPipeline(torch, list(host_x.values()), dev)
+
     def e2e():
-        for m in xs:
-            xs[m].copy_(host_x[m], non_blocking=True)
-        _, conf, pred = ours()
+        _, conf, pred = ours(pipe.next(), pipe.release)
         host_pred.copy_(pred, non_blocking=True)
         host_conf.copy_(conf, non_blocking=True)
 
-    ms_e2e = timed(e2e, max(1, min(steps, 3)))
+    ms_e2e = timed(e2e, max(3, steps))
+    del pipe
     # the same pass through the module-level drop-in (pipeline.EncodeFuse: SequenceEncoder modules grouped into one
     # launch of the recurrence, LayerNorm inside the projection kernel, HybridFusion module on the tensor-core path)
     import copy
@@ -807,8 +844,9 @@ def run_raw_infer(args):
             "clocks": clocks,
             "e2e": {"value": B / (ms_e2e * 1e-3), "unit": "windows/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": B * 12,
-                    "api": "raw fp32 windows copied from pinned host memory, SequenceEncoder recurrence on "
-                           "ops.lstm_forward, FusionEngine.infer, predictions + confidences copied back"},
+                    "api": "raw fp32 windows copied from pinned host memory (2-slot pipeline on a copy stream: the copy of "
+                           "pass i+1 overlaps pass i), SequenceEncoder recurrence on ops.lstm_forward, FusionEngine.infer, "
+                           "predictions + confidences copied back, every pass"},
             "gpu_launches": (1 if HID <= 256 and not os.environ.get("MSF_LSTM_STEPS") else T) + 8,
             "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": tf / peaks["tflops"], "traffic": _lstm_traffic("lstm_seq_kernel_inference", T), "peak_source": peaks["src"],
@@ -889,8 +927,10 @@ def run_raw_train(args):
     d_h = [torch.randn(B, HID, device=dev, generator=g) / B for _ in feats_in]
     weights = [(e.rnn.weight_ih_l0, e.rnn.weight_hh_l0, e.rnn.bias_ih_l0, e.rnn.bias_hh_l0) for e in encs.values()]
 
-    def ours():
-        tapes = ops.lstm_train_forward(xs, weights, HID)
+    def ours(src=None, after_pack=None):
+        tapes = ops.lstm_train_forward(src if src is not None else xs, weights, HID)
+        if after_pack is not None:
+            after_pack()   # the raw windows are consumed (packed into the recurrence's operand layout)
         return ops.lstm_backward(tapes, d_h)
 
     def library():
@@ -962,15 +1002,16 @@ def run_raw_train(args):
     host_x = [x.cpu().pin_memory() for x in xs]
     host_g = [[torch.empty_like(t, device="cpu").pin_memory() for t in trip] for trip in ga]
 
+    pipe = HostPipeline(torch, host_x, dev)
+
     def e2e():
-        for x, hx in zip(xs, host_x):
-            x.copy_(hx, non_blocking=True)
-        grads = ours()
+        grads = ours(pipe.next(), pipe.release)
         for trip, htrip in zip(grads, host_g):
             for t, ht in zip(trip, htrip):
                 ht.copy_(t, non_blocking=True)
 
-    ms_e2e = timed(e2e, max(1, min(steps, 3)))
+    ms_e2e = timed(e2e, max(3, steps))
+    del pipe
     # the whole model from raw windows through the module-level drop-in, as train.py's training_step wires it
     # (train.py:233-291,302-324): encoders (grouped launches of the recurrence) -> projection -> LayerNorm ->
     # HybridFusion -> cross entropy -> backward to every parameter
@@ -1014,8 +1055,9 @@ def run_raw_train(args):
             "e2e": {"value": B / (ms_e2e * 1e-3), "unit": "windows/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": sum(t.numel() * 4 for t in host_x),
                     "d2h_bytes_per_step": sum(t.numel() * 4 for trip in host_g for t in trip),
-                    "api": "raw fp32 windows copied from pinned host memory, ops.lstm_train_forward + ops.lstm_backward, "
-                           "all parameter gradients copied back"},
+                    "api": "raw fp32 windows copied from pinned host memory (2-slot pipeline on a copy stream: the copy of "
+                           "pass i+1 overlaps pass i), ops.lstm_train_forward + ops.lstm_backward, all parameter gradients "
+                           "copied back, every pass"},
             "gpu_launches": 2 + 3 * len(feats_in),
             "phases_ms": {"forward (lstm_seq_kernel<true>, incl. input / weight packing)": ms_fwd,
                           "backward (lstm_bwd_kernel + weight-gradient GEMMs + reduction)": ms_bwd},
