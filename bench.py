@@ -1263,9 +1263,7 @@ def roofline_entry(kern, peaks, step_tflops):
     burst = peaks.get("tflops_burst")
     out = {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
            "frac": achieved / peaks["tflops"], "traffic": traffic, "peak_source": peaks["src"],
-           "kernel": ("chain3_kernel (chained pair GEMMs, weights multicast over a CTA cluster; 2 launches per step)"
-                      if os.environ.get("MSF_CHAIN") == "v3" else
-                      "chain2_kernel (tcgen05/TMEM/TMA chained pair GEMMs value_proj -> out_proj and their mirror "
+           "kernel": ("chain2_kernel (tcgen05/TMEM/TMA chained pair GEMMs value_proj -> out_proj and their mirror "
                       "backward, half-pair software pipeline; 2 launches per step)") if SHAPE == "pamap2" else
                      "tc_gemm_kernel grouped launches of the pair projections (shape outside the chained kernel)",
            "avg_launch_us": us / n, "algorithmic_gflop_per_launch": gf / n,

@@ -26,9 +26,6 @@ FLAGS = [
 ]
 if VARIANT == "timeline":
     FLAGS.append("-DMSF_TIMELINE")
-elif VARIANT.startswith("c3_"):   # chain3 ring-depth experiments: c3_<W>_<A>_<U> (timeline stamps compiled in)
-    w, a, u = VARIANT.split("_")[1:4]
-    FLAGS += ["-DMSF_TIMELINE", f"-DC3_CFG_W={w}", f"-DC3_CFG_A={a}", f"-DC3_CFG_U={u}"]
 elif VARIANT:
     raise RuntimeError(f"unknown MSF_BUILD_VARIANT {VARIANT!r}")
 

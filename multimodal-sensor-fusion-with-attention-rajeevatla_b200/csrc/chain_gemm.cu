@@ -393,42 +393,19 @@ size_t chain_fixed_smem() { return 1024 + 8 * (2 * CH_MAX_STAGES + 8) + 3 * 256 
 bool chain2_eligible(int H, int M);                                          // chain2_gemm.cu
 int chain2_launch(ChainLaunch& L, cudaStream_t stream, const char* label);
 
-bool chain3_eligible(int H, int M, int head_dim);                             // chain3_gemm.cu (cluster weight multicast)
-int chain3_cluster(int H, long long rows);
-int chain3_launch(ChainLaunch& L, cudaStream_t stream, const char* label);
-
-// kernel choice.  2 = chain2_kernel (single CTA, half-pair pipeline): the default for hidden % 128 == 0.
-// 5 = chain3_kernel (clusters sharing every weight fetch by TMA multicast, N = H MMAs, k-block pipeline, aux tile
-// preloaded into TMEM): opt-in with MSF_CHAIN=v3, and only for launches that fit one wave of clusters.  Measured
-// on the B = 4096 train step it is correct for cluster sizes 1 / 2 / 4 / 8 but slower (30 vs 24 us per launch: with
-// one item per CTA both kernels are bound by L2 -> SM latency, and 224 KB of shared memory cannot hold the next
-// GEMM1's operands while the current pair drains, see profiles/README.md), and launches of more than one wave hit
-// a rare cross-CTA race (1 cluster of 256 hung at B = 32 768) that is not understood yet.
-// 1 = chain_kernel (every other shape, or MSF_CHAIN=v1).
+// kernel choice.  2 = chain2_kernel (single CTA, half-pair pipeline): the default for hidden % 128 == 0;
+// 1 = chain_kernel (every other shape, or MSF_CHAIN=v1).  (A cluster variant that shared every weight fetch by TMA
+// multicast, chain3_kernel, measured slower at B = 4096 — 30 vs 24 us per launch — and was removed.)
 static int chain_variant(int H, int M, int heads, long long rows) {
   const char* e = getenv("MSF_CHAIN");
   if (getenv("MSF_CHAIN_V1") || (e && e[0] == 'v' && e[1] == '1')) return 1;
-  if (e && e[0] == 'v' && e[1] == '3' && heads >= 1 && H % heads == 0 && chain3_eligible(H, M, H / heads)) {
-    static int sms = 0;
-    if (sms == 0) {
-      int dev = 0;
-      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-        sms = 148;
-    }
-    const int C = chain3_cluster(H, rows);
-    const long long ctas = ceil_div(ceil_div(rows < 1 ? 1 : rows, 128), C) * C * M;
-    if (ctas <= sms - (C >= 4 ? 16 : 0)) return 5;
-  }
   return chain2_eligible(H, M) ? 2 : 1;
 }
 int chain_w1_box_rows(int H, int M, int heads, long long rows) {
-  const int v = chain_variant(H, M, heads, rows);
-  if (v == 5) return H / chain3_cluster(H, rows);
-  return v == 2 ? H / 2 : H;
+  return chain_variant(H, M, heads, rows) == 2 ? H / 2 : H;
 }
 int chain_w2_box_rows(int H, int M, int heads, long long rows) {
-  const int v = chain_variant(H, M, heads, rows);
-  if (v == 5) return H / chain3_cluster(H, rows);
+  (void)M; (void)heads; (void)rows;
   return H;
 }
 
@@ -441,7 +418,6 @@ int chain_launch(ChainLaunch& L, cudaStream_t stream, const char* label) {
   for (int sft = 0; sft < 16; ++sft)
     if ((1 << sft) == L.head_dim) L.head_shift = sft;
   const int variant = chain_variant(L.H, L.M, L.heads, L.rows);
-  if (variant == 5) return chain3_launch(L, stream, label);
   if (variant == 2) return chain2_launch(L, stream, label);
   L.row_tiles = (int)ceil_div(L.rows, 128);
   if (L.n_active <= 0) {   // default: every modality is an outer modality

@@ -46,7 +46,7 @@ struct ChainLaunch {
   short active[MSF_MAX_MODALITIES];  // inference pass are left out: the head never reads their aggregated token
   int store1;          // write epilogue1's result to global memory (needed by the backward pass)
   int stages;
-  int cluster;         // CTAs per cluster sharing one fetch of every weight block (chain3_kernel; set by chain_launch)
+  int cluster;         // unused (the cluster variant of the kernel is gone); kept so that the launch record keeps its layout
   ChainOuter outer[MSF_MAX_MODALITIES];
   const float* bias1[CHAIN_MAX_PAIRS];   // forward: value_proj bias per pair
   const float* bias2[CHAIN_MAX_PAIRS];   // forward: out_proj bias per pair (summed in the final epilogue)
@@ -62,7 +62,7 @@ struct ChainLaunch {
 
 bool chain_eligible(int H, int M);
 // Box height of map_w1 / map_w2 (rows of a weight block one TMA load brings in) for the kernel chain_launch will
-// pick for this shape: H / cluster for chain3_kernel (every CTA of a cluster fetches one slice and multicasts it),
+// pick for this shape: H / 2 (map_w1) for chain2_kernel,
 // H for chain_kernel.
 int chain_w1_box_rows(int H, int M, int heads, long long rows);
 int chain_w2_box_rows(int H, int M, int heads, long long rows);

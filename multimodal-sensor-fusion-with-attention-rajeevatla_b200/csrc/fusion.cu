@@ -19,7 +19,6 @@ int fusion_bf16_backward(const Layout& L, const msf_fusion_call* c, cudaStream_t
 bool fusion_bf16_head_fused(const Layout& L);
 int head_debug_stamps(long long* out16);
 int chain_debug_stamps(long long* out16);
-int chain3_debug_stamps(long long* out16);
 int proj_debug_stamps(long long* out16);
 int fusion_bf16_train(const Layout& L, const msf_fusion_call* c, const int64_t* labels, float smoothing,
                       float grad_scale, float* row_loss, float* loss_out, int flags, cudaStream_t st);
@@ -191,8 +190,6 @@ int msf_fusion_infer_folded(const msf_fusion_shape* shape, const msf_fusion_call
 
 int msf_debug_chain_stamps(int64_t* out16) {
   MSF_REQUIRE(out16 != nullptr, "msf_debug_chain_stamps: null output");
-  const char* e = getenv("MSF_CHAIN");   // default: chain3_kernel (timeline builds); MSF_CHAIN=v2: chain2_kernel
-  if (e == nullptr) return msf::chain3_debug_stamps(reinterpret_cast<long long*>(out16));
   return msf::chain_debug_stamps(reinterpret_cast<long long*>(out16));
 }
 

@@ -24,7 +24,7 @@ lib = pkg.lib()
 lib.msf_debug_timeline.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int]
 lib.msf_debug_timeline.restype = ctypes.c_int
 buf = ctypes.create_string_buffer(1 << 18)
-CH = "chain3_gemm.cu" if os.environ.get("MSF_CHAIN") == "v3" else "chain2_gemm.cu"
+CH = "chain2_gemm.cu"
 WG = "tc_gemm.cu#1" if os.environ.get("MSF_WG") == "v1" else "wg2_gemm.cu#0"
 ORDER = ["proj_gemm.cu#0", CH + "#0", "head_gemm.cu#0", "fusion_bf16.cu#0", CH + "#1", "fusion_bf16.cu#1", WG,
          "opt_pack.cu#0"]

@@ -203,12 +203,10 @@ def test_projection_kernel_input_widths():
 
 
 @pytest.mark.parametrize("batch", [800, 4096])
-@pytest.mark.parametrize("variant,cluster", [("v1", None), ("v3", None), ("v3", "1"), ("v3", "2"), ("v3", "8")])
+@pytest.mark.parametrize("variant,cluster", [("v1", None)])
 def test_chain_kernel_variants_agree(variant, cluster, batch, monkeypatch):
-    """chain2_kernel (the default at these batch sizes) against the un-pipelined chain_kernel and chain3_kernel
-    (clusters of 1 / 2 / 4 / 8 CTAs sharing every weight fetch by TMA multicast; the default when CTAs get several
-    items) on a train pass.  B = 800 is ragged: 7 row tiles, so a cluster has surplus CTAs running on
-    out-of-range rows; B = 4096 is the benchmarked shape (32 tiles = 8 full clusters of 4 per modality)."""
+    """chain2_kernel (the default at these batch sizes: half-pair software pipeline) against the un-pipelined
+    chain_kernel on a train pass.  B = 800 is ragged (7 row tiles); B = 4096 is the benchmarked shape."""
     ops, N, model, plan, arena, arena16, xs, mask, labels = _setup(batch, seed=31)
     kw = dict(precision=N.MSF_PREC_BF16, training=True, p=0.1, seed=5, offset=2, arena_bf16=arena16)
     monkeypatch.delenv("MSF_CHAIN", raising=False)
