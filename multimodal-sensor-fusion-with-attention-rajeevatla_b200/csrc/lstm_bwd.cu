@@ -222,6 +222,30 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_bwd_kernel(const __grid_co
         const int len = (lens != nullptr && row_ok) ? __ldg(lens + row) : L.steps;
         const bool live = row_ok && t < len;      // the window took this step in the forward pass
         const bool ext = row_ok && dho != nullptr && t == len - 1;  // h_out of the window is h_t
+        // What the forward pass kept for these windows does not depend on this step's MMAs: the loads of two of the
+        // thread's four unit groups are issued BEFORE the wait for the accumulator (one DRAM round trip hidden behind
+        // the tile's operand loads and MMAs), the other two right after the first two are consumed.
+        struct Kept {
+          uint32_t g[8];    // gate activations of 4 units
+          float4 ct, cp;    // c_t, c_{t-1}            (LSTM)
+          uint2 hp;         // h_{t-1} as bf16         (GRU)
+        };
+        const bool use = live && !(L.dbg & 8);
+        auto load_kept = [&](int g, Kept& K) {
+          if (!use) return;
+          const int u0 = ubase + 4 * g;
+          ld_global_v8(gates_t + (long long)row * 4 * H + 4 * u0, K.g);
+          if (GRU) {
+            K.hp = *reinterpret_cast<const uint2*>(h_p + (long long)row * H + u0);
+          } else {
+            const long long idx = lb_cell_index(tile, r, u0, H, ragged);
+            K.ct = *reinterpret_cast<const float4*>(c_t + idx);
+            K.cp = t > 0 ? *reinterpret_cast<const float4*>(c_p + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        };
+        Kept K0, K1;
+        load_kept(0, K0);
+        load_kept(1, K1);
         uint32_t a[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) a[j] = 0u;
@@ -239,18 +263,16 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_bwd_kernel(const __grid_co
           if (lane == 0) mbar_arrive(acc_empty(acc));   // the accumulator is in registers: the next tile may use it
           ++cnt;
         }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        auto cell_backward = [&](int g, const Kept& K) {
           const int u0 = ubase + 4 * g;
-          uint4* gp = reinterpret_cast<uint4*>(gates_t + (long long)row * 4 * H + 4 * u0);
+          __nv_bfloat16* gp = gates_t + (long long)row * 4 * H + 4 * u0;
           // the carried d c of these 4 units: a TMEM scratch column group of this thread's lane (warp-collective
           // access: outside the per-window branch), or the global `dc` buffer
           const uint32_t dc_taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(LB_DC_COL0 + i * 64 + cg * 16 + 4 * g);
           uint32_t dct[4] = {0u, 0u, 0u, 0u};
           if (L.dc_tmem && s > 0) tmem_ld4(dc_taddr, dct);
-          if (live && !(L.dbg & 8)) {
+          if (use) {
             const long long idx = lb_cell_index(tile, r, u0, H, ragged);
-            const uint4 g0 = gp[0], g1 = gp[1];
             const float4 dc4 = L.dc_tmem ? make_float4(__uint_as_float(dct[0]), __uint_as_float(dct[1]), __uint_as_float(dct[2]),
                                                        __uint_as_float(dct[3]))
                                          : *reinterpret_cast<const float4*>(dcp + idx);
@@ -260,13 +282,12 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_bwd_kernel(const __grid_co
               const uint2 e2 = __ldg(reinterpret_cast<const uint2*>(dha + (long long)row * H + u0));
               ex4.x += lb_lo(e2.x); ex4.y += lb_hi(e2.x); ex4.z += lb_lo(e2.y); ex4.w += lb_hi(e2.y);
             }
-            const uint32_t gw[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const uint32_t (&gw)[8] = K.g;
             const float dcv[4] = {dc4.x, dc4.y, dc4.z, dc4.w}, ex[4] = {ex4.x, ex4.y, ex4.z, ex4.w};
             uint32_t out[8];
             float dcn[4];
             if (GRU) {
-              const uint2 hp2 = *reinterpret_cast<const uint2*>(h_p + (long long)row * H + u0);
-              const float hp[4] = {lb_lo(hp2.x), lb_hi(hp2.x), lb_lo(hp2.y), lb_hi(hp2.y)};
+              const float hp[4] = {lb_lo(K.hp.x), lb_hi(K.hp.x), lb_lo(K.hp.y), lb_hi(K.hp.y)};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float gr = lb_lo(gw[2 * j]), gz = lb_hi(gw[2 * j]), gn = lb_lo(gw[2 * j + 1]), hn = lb_hi(gw[2 * j + 1]);
@@ -279,9 +300,7 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_bwd_kernel(const __grid_co
                 out[2 * j + 1] = lb_pack(dn, dn * gr);
               }
             } else {
-              const float4 ct4 = *reinterpret_cast<const float4*>(c_t + idx);
-              const float4 cp4 = t > 0 ? *reinterpret_cast<const float4*>(c_p + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
-              const float ct[4] = {ct4.x, ct4.y, ct4.z, ct4.w}, cp[4] = {cp4.x, cp4.y, cp4.z, cp4.w};
+              const float ct[4] = {K.ct.x, K.ct.y, K.ct.z, K.ct.w}, cp[4] = {K.cp.x, K.cp.y, K.cp.z, K.cp.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float gi = lb_lo(gw[2 * j]), gf = lb_hi(gw[2 * j]), gg = lb_lo(gw[2 * j + 1]), go = lb_hi(gw[2 * j + 1]);
@@ -303,14 +322,20 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_bwd_kernel(const __grid_co
             } else {
               *reinterpret_cast<float4*>(dcp + idx) = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
             }
-            gp[0] = make_uint4(out[0], out[1], out[2], out[3]);
-            gp[1] = make_uint4(out[4], out[5], out[6], out[7]);
+            st_global_v8(gp, out);
           } else if (row_ok) {   // a step behind the window's length: no gradient through it
-            gp[0] = make_uint4(0u, 0u, 0u, 0u);
-            gp[1] = make_uint4(0u, 0u, 0u, 0u);
+            const uint32_t zero[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            st_global_v8(gp, zero);
           }
           if (L.dc_tmem) tmem_st4(dc_taddr, dct);   // (unchanged for a window that did not take this step)
-        }
+        };
+        Kept K2;
+        load_kept(2, K2);   // in flight while groups 0 and 1 are computed
+        cell_backward(0, K0);
+        load_kept(3, K0);   // (group 0's registers are free again)
+        cell_backward(1, K1);
+        cell_backward(2, K2);
+        cell_backward(3, K0);
       }
       if (L.dc_tmem) tmem_st_wait();
       // d a_t is read back by TMA (async proxy) in the next step, by every CTA of the cluster

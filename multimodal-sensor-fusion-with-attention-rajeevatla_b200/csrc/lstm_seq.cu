@@ -286,16 +286,12 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint32_t a[16];
-          uint4 z0 = make_uint4(0u, 0u, 0u, 0u), z1 = z0;
-          if (zin_t != nullptr && cell_io) {   // the input's share of these 16 pre-activations
-            const uint4* zp = reinterpret_cast<const uint4*>(zin_t + (long long)row * 4 * H + 4 * (ubase + 4 * g));
-            z0 = zp[0];
-            z1 = zp[1];
-          }
+          uint32_t zw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+          if (zin_t != nullptr && cell_io)   // the input's share of these 16 pre-activations
+            ld_global_v8(zin_t + (long long)row * 4 * H + 4 * (ubase + 4 * g), zw);
           tmem_ld16_issue(taddr + (uint32_t)(16 * g), a);
           tmem_wait16(a);
           if (zin_t != nullptr) {
-            const uint32_t zw[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               a[2 * e] = __float_as_uint(__uint_as_float(a[2 * e]) + __uint_as_float(zw[e] << 16));
@@ -342,11 +338,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
           const int u0 = ubase + 4 * g;
           if (cell_io)
             *reinterpret_cast<float4*>(cellp + ls_cell_index(tile, r, u0, H, ragged)) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-          if (tape && cell_io) {
-            uint4* gd = reinterpret_cast<uint4*>(gates_t + (long long)row * 4 * H + 4 * u0);
-            gd[0] = make_uint4(gs[0], gs[1], gs[2], gs[3]);
-            gd[1] = make_uint4(gs[4], gs[5], gs[6], gs[7]);
-          }
+          if (tape && cell_io) st_global_v8(gates_t + (long long)row * 4 * H + 4 * u0, gs);
           __nv_bfloat162 p0 = __floats2bfloat162_rn(hn[0], hn[1]), p1 = __floats2bfloat162_rn(hn[2], hn[3]);
           hp[2 * g] = *reinterpret_cast<uint32_t*>(&p0);
           hp[2 * g + 1] = *reinterpret_cast<uint32_t*>(&p1);
@@ -357,14 +349,12 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_kernel(const __grid_co
         if (row_ok) {   // k-block (ubase >> 6) = this CTA's rank of [H/64][B][64]
           const long long off = SAVE ? (long long)row * H + ubase
                                      : (long long)(ubase >> 6) * L.h_slice + (long long)row * 64 + (ubase & 63);
-          uint4* dst = reinterpret_cast<uint4*>(h_next + off);
           if (live) {
-            dst[0] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-            dst[1] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+            st_global_v8(h_next + off, hp);
           } else {   // finished window: carry its hidden state forward unchanged
-            const uint4* src = reinterpret_cast<const uint4*>(h_prev + off);
-            dst[0] = src[0];
-            dst[1] = src[1];
+            uint32_t carry[8];
+            ld_global_v8(h_prev + off, carry);
+            st_global_v8(h_next + off, carry);
           }
         }
         __syncwarp();

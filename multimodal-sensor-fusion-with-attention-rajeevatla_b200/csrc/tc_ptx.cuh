@@ -136,6 +136,20 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4])
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// 256-bit global accesses (sm_100: LDG.256 / STG.256): one full 32-byte sector per thread and request instead of two
+// half-sector requests.  The address must be 32-byte aligned.
+__device__ __forceinline__ void ld_global_v8(const void* p, uint32_t (&r)[8]) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p)
+               : "memory");
+}
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&r)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
 // ---------------------------------------------------------------------------
 // descriptors
 // ---------------------------------------------------------------------------
