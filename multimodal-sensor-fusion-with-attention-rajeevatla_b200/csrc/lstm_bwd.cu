@@ -228,21 +228,22 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_bwd_kernel(const __grid_co
         struct Kept {
           uint32_t g[8];    // gate activations of 4 units
           float4 ct, cp;    // c_t, c_{t-1}            (LSTM)
-          uint2 hp;         // h_{t-1} as bf16         (GRU)
         };
         const bool use = live && !(L.dbg & 8);
         auto load_kept = [&](int g, Kept& K) {
           if (!use) return;
           const int u0 = ubase + 4 * g;
           ld_global_v8(gates_t + (long long)row * 4 * H + 4 * u0, K.g);
-          if (GRU) {
-            K.hp = *reinterpret_cast<const uint2*>(h_p + (long long)row * H + u0);
-          } else {
+          if (!GRU) {
             const long long idx = lb_cell_index(tile, r, u0, H, ragged);
             K.ct = *reinterpret_cast<const float4*>(c_t + idx);
             K.cp = t > 0 ? *reinterpret_cast<const float4*>(c_p + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         };
+        // 16 units x bf16 = one 32-byte sector per thread: h_{t-1} (GRU) and the gradient from the layer above
+        uint32_t hpv[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}, dhv[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        if (GRU && use) ld_global_v8(h_p + (long long)row * H + ubase, hpv);
+        if (dha != nullptr && use) ld_global_v8(dha + (long long)row * H + ubase, dhv);
         Kept K0, K1;
         load_kept(0, K0);
         load_kept(1, K1);
@@ -279,15 +280,14 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_bwd_kernel(const __grid_co
             float4 ex4 = ext ? __ldg(reinterpret_cast<const float4*>(dho + (long long)row * H + u0))
                              : make_float4(0.f, 0.f, 0.f, 0.f);
             if (dha != nullptr) {   // this step's hidden state also fed the layer above
-              const uint2 e2 = __ldg(reinterpret_cast<const uint2*>(dha + (long long)row * H + u0));
-              ex4.x += lb_lo(e2.x); ex4.y += lb_hi(e2.x); ex4.z += lb_lo(e2.y); ex4.w += lb_hi(e2.y);
+              ex4.x += lb_lo(dhv[2 * g]); ex4.y += lb_hi(dhv[2 * g]); ex4.z += lb_lo(dhv[2 * g + 1]); ex4.w += lb_hi(dhv[2 * g + 1]);
             }
             const uint32_t (&gw)[8] = K.g;
             const float dcv[4] = {dc4.x, dc4.y, dc4.z, dc4.w}, ex[4] = {ex4.x, ex4.y, ex4.z, ex4.w};
             uint32_t out[8];
             float dcn[4];
             if (GRU) {
-              const float hp[4] = {lb_lo(K.hp.x), lb_hi(K.hp.x), lb_lo(K.hp.y), lb_hi(K.hp.y)};
+              const float hp[4] = {lb_lo(hpv[2 * g]), lb_hi(hpv[2 * g]), lb_lo(hpv[2 * g + 1]), lb_hi(hpv[2 * g + 1])};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float gr = lb_lo(gw[2 * j]), gz = lb_hi(gw[2 * j]), gn = lb_lo(gw[2 * j + 1]), hn = lb_hi(gw[2 * j + 1]);
