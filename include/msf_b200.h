@@ -530,6 +530,21 @@ int msf_bn_act_backward(const float* dout, const float* y, const float* out, int
                         int32_t relu, float dropout_p, float* dy, float* dgamma, float* dbeta, double* scratch,
                         void* stream);
 
+/* ---- temporal pooling of FrameEncoder (src/encoders.py:258-336) -------------------------------- */
+/* x (B, T, H) fp32 frame features, mask (B, T) fp32 or NULL (0 = frame absent).  mode 0: attention pooling — scores
+ * s_t = x_t . w + bias (w: H floats, bias: 1 float or NULL), masked softmax over the frames (a clip without a valid
+ * frame pools to zeros, like the reference's nan_to_num), pooled = sum_t p_t x_t; mode 1: (masked) average; mode 2:
+ * (masked) maximum.  pooled (B, H).  weights (B, T) receives p_t (modes 0 / 1), argmax (B, H) int32 the frame of the
+ * maximum (mode 2, -1 for a clip without a valid frame): the tape of the backward pass.  One block per clip, the clip
+ * is read once from DRAM.  T <= 8192. */
+int msf_frame_pool_forward(const float* x, const float* mask, const float* w, const float* bias, int64_t batch,
+                           int32_t frames, int32_t hidden, int32_t mode, float* pooled, float* weights, int32_t* argmax,
+                           void* stream);
+/* dx (B, T, H); mode 0 also dw (H) and db (1, may be NULL); scratch: (B * H + B) floats (mode 0). */
+int msf_frame_pool_backward(const float* x, const float* w, const float* weights, const int32_t* argmax,
+                            const float* d_pooled, int64_t batch, int32_t frames, int32_t hidden, int32_t mode, float* dx,
+                            float* dw, float* db, float* scratch, void* stream);
+
 /* ---- tensor-core GEMM building block (encoder/attention projections) ------ */
 /* bf16 operands, fp32 accumulate in TMEM via tcgen05.mma, operands staged by TMA
  * into 128B-swizzled shared memory; D is fp32 or bf16 row-major (ldd elements).

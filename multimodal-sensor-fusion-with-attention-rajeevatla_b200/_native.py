@@ -186,6 +186,10 @@ PROTOTYPES = {
     "msf_gru_f32_backward": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_void_p]),
+    "msf_frame_pool_forward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p,
+                                         c_void_p, c_void_p, c_void_p]),
+    "msf_frame_pool_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32,
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "msf_lstm_dropout": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_float, c_uint64, c_uint64, c_int32, c_void_p]),
     "msf_lstm_backward_scratch_bytes": (c_int32, [c_int64, c_int32, c_int32, POINTER(ctypes.c_size_t)]),
     "msf_fusion_infer_folded": (c_int32, [POINTER(FusionShape), POINTER(FusionCall), c_void_p, c_void_p, ctypes.c_uint32,

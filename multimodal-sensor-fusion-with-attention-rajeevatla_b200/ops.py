@@ -394,6 +394,56 @@ def layer_norm(x: torch.Tensor, weight: Optional[torch.Tensor] = None, bias: Opt
     return LayerNormFunction.apply(x, weight, bias, eps)
 
 
+class FramePoolFunction(torch.autograd.Function):
+    """Temporal pooling of FrameEncoder (src/encoders.py:258-336) on msf_frame_pool_*: ``mode`` 0 attention (scores
+    ``x . w + b``, masked softmax over the frames, weighted sum), 1 (masked) average, 2 (masked) maximum."""
+
+    @staticmethod
+    def forward(ctx, x, mask, w, b, mode: int):
+        x = x.to(torch.float32).contiguous()
+        B, T, H = x.shape
+        dev = x.device
+        m = None if mask is None else mask.detach().to(device=dev, dtype=torch.float32).expand(B, T).contiguous()
+        wv = None if w is None else w.detach().to(torch.float32).reshape(-1).contiguous()
+        bv = None if b is None else b.detach().to(torch.float32).reshape(-1).contiguous()
+        pooled = torch.empty(B, H, dtype=torch.float32, device=dev)
+        weights = torch.empty(B, T, dtype=torch.float32, device=dev) if mode != 2 else None
+        argmax = torch.empty(B, H, dtype=torch.int32, device=dev) if mode == 2 else None
+        N.check(N.lib().msf_frame_pool_forward(_p(x), _p(m), _p(wv), _p(bv), B, T, H, mode, _p(pooled), _p(weights),
+                                               _p(argmax), _stream()))
+        ctx.save_for_backward(x, wv, weights, argmax)
+        ctx.mode, ctx.has = mode, (w is not None, b is not None)
+        ctx.w_shape = None if w is None else w.shape
+        ctx.b_shape = None if b is None else b.shape
+        return pooled
+
+    @staticmethod
+    def backward(ctx, d_pooled):
+        x, wv, weights, argmax = ctx.saved_tensors
+        B, T, H = x.shape
+        dev = x.device
+        dp = d_pooled.to(torch.float32).contiguous()
+        dx = torch.empty_like(x)
+        dw = db = scratch = None
+        if ctx.mode == 0:
+            dw = torch.empty(H, dtype=torch.float32, device=dev)
+            db = torch.empty(1, dtype=torch.float32, device=dev)
+            scratch = torch.empty(B * H + B, dtype=torch.float32, device=dev)
+        N.check(N.lib().msf_frame_pool_backward(_p(x), _p(wv), _p(weights), _p(argmax), _p(dp), B, T, H, ctx.mode, _p(dx),
+                                                _p(dw), _p(db), _p(scratch), _stream()))
+        gw = dw.reshape(ctx.w_shape) if (ctx.mode == 0 and ctx.has[0]) else None
+        gb = db.reshape(ctx.b_shape) if (ctx.mode == 0 and ctx.has[1]) else None
+        return dx, None, gw, gb, None
+
+
+def frame_pool(x: torch.Tensor, mask: Optional[torch.Tensor], mode: str, weight: Optional[torch.Tensor] = None,
+               bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``(B, T, H) -> (B, H)``: ``mode`` "attention" (``weight`` (1, H) / ``bias`` (1,) of the scoring layer),
+    "average" or "max", with an optional frame mask (B, T)."""
+    require_cuda("frame_pool")
+    return FramePoolFunction.apply(x, mask, weight, bias, {"attention": 0, "average": 1, "max": 2}[mode])
+
+
 class BatchNormActFunction(torch.autograd.Function):
     """``dropout(relu(batch_norm(y)))`` behind a Linear layer on msf_bn_act_* (src/encoders.py:374-377)."""
 
