@@ -17,6 +17,10 @@
 //   * the epilogue warps turn d h_t of their 16 units into d a_t and write it OVER the gate activations of step t:
 //     the same buffer is the next step's A operand and, afterwards, the A operand of the weight-gradient GEMMs.
 //   * d a_t of a tile is produced by all CTAs of the cluster and consumed by all of them: one cluster barrier per step.
+//   * the carried d c (fp32; GRU: the direct d h_t z_t path) of a thread's windows lives in TMEM columns behind the two
+//     accumulators (tcgen05.ld / tcgen05.st, up to 6 tiles per cluster), not in global memory; the tape is read and d a
+//     written with one 256-bit access per 32-byte sector (thread = window: a warp touches 32 different rows), and two
+//     of a thread's four unit groups are requested before it waits for the tile's accumulator.
 //
 // After the recurrence:  d W_hh = sum_t d a_t^T h_{t-1},  d W_ih = sum_t d a_t^T x_t  run on the grouped tensor-core GEMM
 // (tc_gemm_kernel<true>: contraction over (t, window)), split over chunks of steps into fp32 partial sums that

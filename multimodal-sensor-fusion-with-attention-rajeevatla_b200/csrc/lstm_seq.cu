@@ -18,6 +18,11 @@
 //     time step (h travels through global memory / the L2 and comes back by TMA; the writers fence the async proxy
 //     before they arrive).  No grid-wide synchronisation, no per-step launch.
 //
+// Training mode and stacked layers (template SAVE): h_t of every step is kept ([T+1][B][H]), with `gates` set also the
+// gate activations (bf16, 256-bit stores: one full sector per thread and group of 4 units) and c_t (fp32) — the tape of
+// lstm_bwd.cu; a layer above the first reads the input's share of its pre-activations (z_in, one GEMM over all steps)
+// from the gate buffer in place.  Template GRU: the GRU cell on the same machinery (see below).
+//
 // Roles per CTA: warp 0 lane 0 TMA producer, warp 1 lane 0 MMA issuer, warp 2 TMEM allocator, warps 4..11 epilogue.
 // Every mbarrier wait is bounded.
 #include <stdlib.h>
