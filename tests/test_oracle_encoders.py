@@ -44,6 +44,47 @@ def test_lstm_lengths_stop_the_state():
     assert _maxabs(out, g.t("lstm/out_lengths")) <= TOL
 
 
+@pytest.mark.parametrize("kind", ["lstm", "gru"])
+def test_ragged_windows_match_the_reference_call(kind):
+    """The reference packs ragged windows (src/encoders.py:140-156: pack_padded_sequence -> nn.LSTM / nn.GRU -> h_n[-1]).
+    The oracle's ``lengths`` handling (state stands still after a window's last valid step), which the GPU parity tests
+    lean on for both cells, is held to exactly that call sequence of PyTorch's own CPU recurrence here."""
+    torch.manual_seed(51)
+    rnn = (nn.LSTM if kind == "lstm" else nn.GRU)(5, 12, num_layers=2, batch_first=True)
+    x = torch.randn(9, 11, 5)
+    lengths = torch.tensor([11, 1, 4, 7, 11, 2, 9, 3, 6])
+    packed = nn.utils.rnn.pack_padded_sequence(x, lengths, batch_first=True, enforce_sorted=False)
+    with torch.no_grad():
+        _, hidden = rnn(packed)
+    ref = (hidden[0] if kind == "lstm" else hidden)[-1]
+    sd = {"rnn." + k: v.detach() for k, v in rnn.state_dict().items()}
+    fn = encoder_oracle.lstm_last_hidden if kind == "lstm" else encoder_oracle.gru_last_hidden
+    assert _maxabs(fn(sd, "rnn", x, 2, lengths), ref) <= TOL
+
+
+@pytest.mark.parametrize("kind", ["lstm", "gru"])
+def test_injected_inter_layer_dropout_is_applied_to_the_upper_layers_input(kind):
+    """``layer_masks`` (the training-mode dropout nn.LSTM / nn.GRU applies between layers, injected so that the GPU
+    kernels' Philox draws and the oracle agree): equal to running the layers one by one through PyTorch's own
+    single-layer recurrences with the mask multiplied in between."""
+    torch.manual_seed(52)
+    cls = nn.LSTM if kind == "lstm" else nn.GRU
+    rnn = cls(5, 12, num_layers=2, batch_first=True)
+    x = torch.randn(7, 9, 5)
+    mask = (torch.rand(7, 9, 12) > 0.3).float() / 0.7
+    lower, upper = cls(5, 12, batch_first=True), cls(12, 12, batch_first=True)
+    lower.load_state_dict({k[:-1] + "0": v for k, v in rnn.state_dict().items() if k.endswith("l0")})
+    upper.load_state_dict({k[:-1] + "0": v for k, v in rnn.state_dict().items() if k.endswith("l1")})
+    with torch.no_grad():
+        out0, _ = lower(x)
+        _, hidden = upper(out0 * mask)
+    ref = (hidden[0] if kind == "lstm" else hidden)[-1]
+    sd = {"rnn." + k: v.detach() for k, v in rnn.state_dict().items()}
+    fn = encoder_oracle.lstm_last_hidden if kind == "lstm" else encoder_oracle.gru_last_hidden
+    assert _maxabs(fn(sd, "rnn", x, 2, None, {1: mask}), ref) <= TOL
+    assert _maxabs(fn(sd, "rnn", x, 2, None, {1: mask}), fn(sd, "rnn", x, 2)) > 1e-3   # the mask matters
+
+
 def test_mlp_encoder_and_layernorm_oracle_match_reference():
     g = Golden("encoders_small.npz")
     sd = g.group("mlp/sd")
