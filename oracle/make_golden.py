@@ -355,8 +355,7 @@ def encoder_cases():
         for k, v in enc.state_dict().items():
             payload[f"{kind}/sd/{k}"] = _np(v)
         payload[f"{kind}/out"] = _np(enc(x))
-        if kind == "lstm":
-            payload["lstm/out_lengths"] = _np(enc(x, lengths))
+        payload[f"{kind}/out_lengths"] = _np(enc(x, lengths))   # ragged windows: the reference packs them (encoders.py:140-156)
         enc.train()
         xg = x.clone().requires_grad_(True)
         out = enc(xg)

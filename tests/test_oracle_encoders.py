@@ -38,10 +38,12 @@ def test_sequence_encoder_oracle_matches_reference(kind):
         assert _maxabs(sdg[key].grad, ref) <= 5 * TOL, key
 
 
-def test_lstm_lengths_stop_the_state():
+@pytest.mark.parametrize("kind", ["lstm", "gru"])
+def test_lengths_stop_the_state(kind):
+    """Ragged windows through the unmodified reference (SequenceEncoder.forward(x, lengths): packed sequence)."""
     g = Golden("encoders_small.npz")
-    out = encoder_oracle.sequence_encoder_forward(g.group("lstm/sd"), g.t("seq/x"), 2, "lstm", g.t("seq/lengths"))
-    assert _maxabs(out, g.t("lstm/out_lengths")) <= TOL
+    out = encoder_oracle.sequence_encoder_forward(g.group(f"{kind}/sd"), g.t("seq/x"), 2, kind, g.t("seq/lengths"))
+    assert _maxabs(out, g.t(f"{kind}/out_lengths")) <= TOL
 
 
 @pytest.mark.parametrize("kind", ["lstm", "gru"])
