@@ -40,6 +40,31 @@ def test_struct_layout_matches_header(pkg):
     assert ctypes.sizeof(n.FusionCall) == 16 + 16 + 8 * (1 + 2 + 8 + 1 + 2 + 3 + 2 + 8 + 1) + 8 * 16 + 8
 
 
+def test_header_is_plain_c_and_lstm_record_matches_field_by_field(pkg, tmp_path):
+    """include/msf_b200.h is what a foreign-function binding reads: it must compile as C99 on its own (no C++, no torch
+    types), and the ctypes mirror of msf_lstm_seq (the record of the recurrence entry points) must agree with the
+    compiler about the offset of every field."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    n = pkg.native
+    fields = [name for name, _ in n.LstmSeq._fields_]
+    src = tmp_path / "layout.c"
+    lines = ['#include <stddef.h>', '#include <stdio.h>', '#include "msf_b200.h"', "int main(void) {",
+             '  printf("%zu\\n", sizeof(msf_lstm_seq));']
+    lines += [f'  printf("%zu\\n", offsetof(msf_lstm_seq, {f}));' for f in fields]
+    lines += ["  return 0;", "}"]
+    src.write_text("\n".join(lines) + "\n")
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.dirname(HEADER), str(src), "-o", str(exe)],
+                   check=True)
+    out = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert out[0] == ctypes.sizeof(n.LstmSeq) == pkg.lib().msf_lstm_seq_bytes()
+    assert out[1:] == [getattr(n.LstmSeq, f).offset for f in fields]
+
+
 @pytest.mark.parametrize("case", ["fusion_tiny.npz", "fusion_pamap_small.npz", "fusion_missing_pair.npz"])
 def test_arena_layout_is_reference_parameter_order(pkg, case):
     g = Golden(case)
