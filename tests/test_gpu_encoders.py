@@ -78,7 +78,7 @@ def test_frame_encoder_shapes_and_masking():
     assert torch.allclose(enc(frames2, mask)[0], out[0], atol=1e-6)
 
 
-@pytest.mark.parametrize("batch,steps,feat,hidden", [(5, 7, 17, 64), (300, 96, 17, 256), (130, 1024, 1, 256),
+@pytest.mark.parametrize("batch,steps,feat,hidden", [(3, 1, 4, 64), (5, 7, 17, 64), (300, 96, 17, 256), (130, 1024, 1, 256),
                                                       (2500, 33, 17, 256), (700, 20, 64, 128), (129, 12, 17, 384)])
 @pytest.mark.parametrize("path", ["sequence", "steps"])
 def test_tensor_core_lstm_matches_oracle(batch, steps, feat, hidden, path, monkeypatch):
@@ -154,7 +154,7 @@ def _relerr(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-@pytest.mark.parametrize("batch,steps,feat,hidden,ragged", [(5, 7, 17, 64, False), (300, 40, 17, 256, False),
+@pytest.mark.parametrize("batch,steps,feat,hidden,ragged", [(3, 1, 4, 64, False), (5, 7, 17, 64, False), (300, 40, 17, 256, False),
                                                              (130, 300, 1, 256, False), (2500, 21, 3, 128, True),
                                                              (260, 33, 17, 256, True)])
 def test_tensor_core_lstm_training_matches_oracle(batch, steps, feat, hidden, ragged):
