@@ -461,6 +461,11 @@ typedef struct msf_lstm_seq {
                             (d_w_ih rows of n_h and d_w_hh rows of n_x are meaningless; d_bias = (d b_r, d b_z, d b_in, d b_hn)) */
 } msf_lstm_seq;
 int msf_lstm_forward(const msf_lstm_seq* seqs, int32_t n, int64_t batch, int32_t steps, int32_t hidden, void* stream);
+/* x (B, T, F) fp32 windows (batch_first, contiguous) -> x_bf16 [T][B][64] as msf_lstm_forward reads it: time-major, bf16,
+ * F <= 64 features zero-padded to 64 columns; ones_column != 0 (F <= 63): 1.0 in column F (bias gradient of
+ * msf_lstm_backward).  out_bf16 must be 32-byte aligned. */
+int msf_lstm_pack_input(const float* x, int64_t batch, int32_t steps, int32_t features, int32_t ones_column,
+                        void* out_bf16, void* stream);
 /* sizeof(msf_lstm_seq) as compiled, for binding self-checks */
 int msf_lstm_seq_bytes(void);
 

@@ -175,6 +175,7 @@ PROTOTYPES = {
                                               c_void_p, c_void_p]),
     "msf_lstm_forward": (c_int32, [POINTER(LstmSeq), c_int32, c_int64, c_int32, c_int32, c_void_p]),
     "msf_lstm_seq_bytes": (c_int32, []),
+    "msf_lstm_pack_input": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "msf_lstm_backward": (c_int32, [POINTER(LstmSeq), c_int32, c_int64, c_int32, c_int32, c_void_p]),
     "msf_lstm_f32_forward": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
                                        c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -11,11 +11,56 @@
 #include <string.h>
 
 #include "tc_gemm.cuh"
+#include "tc_ptx.cuh"
 
 namespace msf {
 bool lstm_seq_eligible(int hidden, int n, long long batch, int sms);   // lstm_seq.cu: one persistent launch
 int lstm_seq_launch(const msf_lstm_seq* seqs, int n, long long batch, int steps, int hidden, cudaStream_t st);
 }  // namespace msf
+
+namespace msf {
+namespace {
+// (B, T, F) fp32 windows -> the recurrence's A operand [T][B][64] bf16: features zero-padded to 64 columns, optionally
+// 1.0 in column F (the ones of the bias gradient).  One thread per (t, window): a full 128-byte line written with four
+// 256-bit stores, windows fastest so that a warp writes 4 KB contiguously.
+__global__ void __launch_bounds__(256) lstm_pack_input_kernel(const float* __restrict__ x, long long B, int T, int F, int ones,
+                                                              __nv_bfloat16* __restrict__ out) {
+  const long long total = B * T;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long t = e / B, b = e % B;
+    const float* src = x + (b * T + t) * F;
+    __nv_bfloat16* dst = out + e * 64;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t w[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = 16 * q + 2 * k;
+        const float lo = c < F ? __ldg(src + c) : (ones && c == F ? 1.0f : 0.0f);
+        const float hi = c + 1 < F ? __ldg(src + c + 1) : (ones && c + 1 == F ? 1.0f : 0.0f);
+        __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+        w[k] = *reinterpret_cast<uint32_t*>(&p);
+      }
+      st_global_v8(dst + 16 * q, w);
+    }
+  }
+}
+}  // namespace
+}  // namespace msf
+
+extern "C" int msf_lstm_pack_input(const float* x, int64_t batch, int32_t steps, int32_t features, int32_t ones_column,
+                                   void* out_bf16, void* stream) {
+  using namespace msf;
+  MSF_REQUIRE(x && out_bf16 && batch >= 1 && steps >= 1 && features >= 1 && features <= 64,
+              "msf_lstm_pack_input: bad arguments (1..64 features)");
+  MSF_REQUIRE((reinterpret_cast<uintptr_t>(out_bf16) & 31) == 0, "msf_lstm_pack_input: output not 32-byte aligned");
+  long long blocks = ceil_div((long long)batch * steps, 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  lstm_pack_input_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, batch, steps, features, ones_column ? 1 : 0,
+                                                                            static_cast<__nv_bfloat16*>(out_bf16));
+  MSF_LAUNCH_CHECK();
+  return MSF_OK;
+}
 
 extern "C" int msf_lstm_forward(const msf_lstm_seq* seqs, int32_t n, int64_t batch, int32_t steps, int32_t hidden,
                                 void* stream) {

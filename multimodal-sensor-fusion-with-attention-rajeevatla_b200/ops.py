@@ -786,7 +786,13 @@ def lstm_pack_input(x: torch.Tensor, ones_column: bool = False) -> torch.Tensor:
     ``ones_column``: column F carries 1.0 (its weight column is zero), so that the weight-gradient GEMM of
     msf_lstm_backward yields the bias gradient as column F of d W_ih."""
     B, T, F = x.shape
-    out = torch.zeros(T, B, 64, dtype=torch.bfloat16, device=x.device)
+    if x.is_cuda and F <= 64:   # one kernel: pad, transpose to time-major, round to bf16 (msf_lstm_pack_input)
+        src = x.detach().to(torch.float32).contiguous()
+        out = torch.empty(T, B, 64, dtype=torch.bfloat16, device=x.device)
+        with torch.cuda.device(x.device):
+            N.check(N.lib().msf_lstm_pack_input(_p(src), B, T, F, int(ones_column and F < 64), _p(out), _stream()))
+        return out
+    out = torch.zeros(T, B, 64, dtype=torch.bfloat16, device=x.device)   # host tensors (CPU tests of the layout)
     out[:, :, :F] = x.detach().transpose(0, 1)
     if ones_column and F < 64:   # F == 64: no spare column, msf_lstm_backward sums the columns of d a instead
         out[:, :, F] = 1.0

@@ -149,6 +149,19 @@ def test_tensor_core_lstm_ragged_windows(batch, steps, feat, hidden):
         dropin_encoders._lstm_tensor_core(enc.rnn, x.cuda(), torch.zeros(batch, dtype=torch.int64))
 
 
+@pytest.mark.parametrize("batch,steps,feat,ones", [(3, 1, 4, True), (130, 33, 17, True), (257, 5, 64, True), (64, 70, 1, False)])
+def test_lstm_pack_input_kernel_matches_the_host_layout(batch, steps, feat, ones):
+    """msf_lstm_pack_input (pad to 64 columns, time-major, bf16, ones column) against the same layout built with tensor
+    ops on the host (ops.lstm_pack_input on a CPU tensor, which tests/test_cpu_recurrence_host.py ties to the cell)."""
+    pkg_ops = dropin_encoders.ops
+    gen = torch.Generator().manual_seed(batch + steps)
+    x = torch.randn(batch, steps, feat, generator=gen) * 3.0
+    ref = pkg_ops.lstm_pack_input(x, ones_column=ones)
+    got = pkg_ops.lstm_pack_input(x.cuda(), ones_column=ones)
+    assert got.shape == ref.shape == (steps, batch, 64) and got.dtype == torch.bfloat16
+    assert torch.equal(got.cpu().view(torch.int16), ref.view(torch.int16))
+
+
 def _relerr(a, b):
     a, b = a.detach().cpu().double(), b.detach().cpu().double()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
